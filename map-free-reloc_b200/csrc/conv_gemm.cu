@@ -1,0 +1,377 @@
+// tcgen05 implicit-GEMM convolution kernel (sm_100a). See conv_gemm.cuh for the op definition.
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      : TMA producer. Per k-block it loads a [TH x TW pixels] x [32 channels] activation
+//                 box (rank-4 tensor map over NHWC; halo / padding comes back as zeros through the
+//                 TMA out-of-bounds fill, stride-2 through the map's traversal stride) and a
+//                 [BN filters] x [32 channels] weight box, both 128B-swizzled, into a 4-stage ring.
+//   warp 1      : MMA issuer. One elected lane issues 4 x tcgen05.mma (128 x BN x 8, kind::tf32)
+//                 per stage into one of two TMEM accumulators (2 x 256 columns), then
+//                 tcgen05.commit frees the stage / publishes the accumulator.
+//   warps 2..5  : epilogue. tcgen05.ld the accumulator (thread = output pixel, 32 channels per
+//                 load), apply alpha / bias / residual / activation, write NHWC fp32.
+// The epilogue of tile i overlaps the main loop of tile i+1 through the double-buffered TMEM.
+#include "conv_gemm.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+namespace mfr {
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kBlockK = 32;                     // fp32 elements per k-block = 128 B = swizzle span
+constexpr int kUmmaK = 8;                       // tf32: 32 B of K per instruction
+constexpr int kTileM = 128;
+constexpr int kMaxBN = 256;
+constexpr int kAStage = kTileM * kBlockK * 4;   // 16 KB
+constexpr int kBStage = kMaxBN * kBlockK * 4;   // 32 KB
+constexpr int kSmemBytes = kStages * (kAStage + kBStage) + 1024 /*align slack*/;
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_LEAKY) return v > 0.f ? v : 0.01f * v;
+  if (act == ACT_ELU1) return v > 0.f ? v + 1.f : __expf(v);
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_bars[2 * kStages + 4];
+  __shared__ uint32_t s_tmem_base;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + kStages * kAStage;
+  const uint32_t bar_base = smem_u32(s_bars);
+  // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&s_tmem_base), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  const int m_tiles = p.N * p.tiles_y * p.tiles_x;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int num_kb = p.R * p.S * p.kb_per_tap;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile % m_tiles, nt = tile / m_tiles;
+        const int tx = mt % p.tiles_x;
+        const int ty = (mt / p.tiles_x) % p.tiles_y;
+        const int img = mt / (p.tiles_x * p.tiles_y);
+        const int x_in0 = tx * p.TW * p.stride - p.pad;
+        const int y_in0 = ty * p.TH * p.stride - p.pad;
+        const int n0 = nt * p.BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / p.kb_per_tap;
+          const int cb = kb - tap * p.kb_per_tap;
+          const int ky = tap / p.S, kx = tap - ky * p.S;
+          mbar_wait(empty_bar(stage), phase ^ 1u, 1);
+          mbar_arrive_expect_tx(full_bar(stage), static_cast<uint32_t>(p.a_bytes + p.b_bytes));
+          tma_load_4d(smem_a + stage * kAStage, &p.tmA, full_bar(stage), cb * kBlockK, x_in0 + kx,
+                      y_in0 + ky, img);
+          tma_load_3d(smem_b + stage * kBStage, &p.tmB, full_bar(stage), cb * kBlockK,
+                      p.b_batched ? img : tap, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(2u, kTileM, static_cast<uint32_t>(p.BN));
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase, 3);
+          tc_fence_after();
+          const uint32_t a_addr = smem_a + stage * kAStage;
+          const uint32_t b_addr = smem_b + stage * kBStage;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t adesc = umma_desc_sw128_kmajor(a_addr + k * kUmmaK * 4);
+            const uint64_t bdesc = umma_desc_sw128_kmajor(b_addr + k * kUmmaK * 4);
+            tc_mma_tf32(tmem_acc, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int q = warp & 3;  // TMEM lane quadrant this warp is allowed to read
+    const int row = q * 32 + lane;
+    const int ly = row / p.TW, lx = row - ly * p.TW;
+    const bool vec_ok = ((p.Cout & 3) == 0) && ((p.ldo & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                        (p.residual == nullptr ||
+                         (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)));
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int mt = tile % m_tiles, nt = tile / m_tiles;
+      const int tx = mt % p.tiles_x;
+      const int ty = (mt / p.tiles_x) % p.tiles_y;
+      const int img = mt / (p.tiles_x * p.tiles_y);
+      const int y = ty * p.TH + ly, x = tx * p.TW + lx;
+      const bool row_ok = (row < p.TW * p.TH) && (y < p.Ho) && (x < p.Wo);
+      const long long pix = (static_cast<long long>(img) * p.Ho + y) * p.Wo + x;
+      float* orow = p.out + pix * p.ldo;
+      const float* rrow = p.residual ? p.residual + pix * p.ldr : nullptr;
+      const int n0 = nt * p.BN;
+
+      mbar_wait(tfull_bar(acc), acc_phase, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxBN) +
+                             (static_cast<uint32_t>(q * 32) << 16);
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
+        tmem_ld_wait();
+        if (row_ok) {
+          if (vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int n = n0 + c0 + j;
+              if (n < p.Cout) {
+                float4 v;
+                v.x = __uint_as_float(r[j + 0]) * p.alpha;
+                v.y = __uint_as_float(r[j + 1]) * p.alpha;
+                v.z = __uint_as_float(r[j + 2]) * p.alpha;
+                v.w = __uint_as_float(r[j + 3]) * p.alpha;
+                if (p.bias) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                  v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                }
+                if (rrow) {
+                  const float4 s = __ldg(reinterpret_cast<const float4*>(rrow + n));
+                  v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+                }
+                v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
+                v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+                *reinterpret_cast<float4*>(orow + n) = v;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + c0 + j;
+              if (n < p.Cout) {
+                float v = __uint_as_float(r[j]) * p.alpha;
+                if (p.bias) v += __ldg(p.bias + n);
+                if (rrow) v += __ldg(rrow + n);
+                orow[n] = apply_act(v, p.act);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+  });
+  return fn;
+}
+
+// Pick the output tile (TW x TH <= 128 pixels) that wastes the fewest MMA rows.
+void choose_tile(int Wo, int Ho, int stride, int* TW, int* TH) {
+  double best = -1.0;
+  int bw = 1, bh = 1;
+  for (int tw = 1; tw <= 128; ++tw) {
+    if (tw * stride > 256) break;
+    int th = 128 / tw;
+    if (th > Ho) th = Ho;
+    if (th * stride > 256) th = 256 / stride;
+    if (th < 1) continue;
+    const long long tiles = static_cast<long long>((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
+    const double eff = static_cast<double>(Wo) * Ho / (static_cast<double>(tiles) * 128.0);
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > bw)) {
+      best = std::max(best, eff);
+      bw = tw;
+      bh = th;
+    }
+  }
+  *TW = bw;
+  *TH = bh;
+}
+
+}  // namespace
+
+int conv_gemm_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  return sms;
+}
+
+int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    fprintf(stderr, "[mfr_b200] cuTensorMapEncodeTiled unavailable (no CUDA driver?)\n");
+    return MFR_ERR_CUDA;
+  }
+  if (d.Cin % 4 != 0 || d.ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(d.x) & 15) ||
+      (reinterpret_cast<uintptr_t>(d.w) & 15)) {
+    fprintf(stderr, "[mfr_b200] conv_gemm: Cin/ldx must be multiples of 4 and pointers 16B aligned\n");
+    return MFR_ERR_ARG;
+  }
+  if (d.stride != 1 && d.stride != 2) return MFR_ERR_ARG;
+  memset(p, 0, sizeof(*p));
+  p->N = d.N;
+  p->Ho = (d.H + 2 * d.pad - d.R) / d.stride + 1;
+  p->Wo = (d.W + 2 * d.pad - d.S) / d.stride + 1;
+  p->Cout = d.Cout;
+  p->Cin = d.Cin;
+  p->R = d.R; p->S = d.S; p->stride = d.stride; p->pad = d.pad;
+  choose_tile(p->Wo, p->Ho, d.stride, &p->TW, &p->TH);
+  p->tiles_x = (p->Wo + p->TW - 1) / p->TW;
+  p->tiles_y = (p->Ho + p->TH - 1) / p->TH;
+  // N tile: whole Cout when it fits one UMMA (<= 256), else equal 16-aligned slices.
+  const int c16 = (d.Cout + 15) / 16 * 16;
+  p->n_tiles = (c16 + kMaxBN - 1) / kMaxBN;
+  p->BN = ((c16 / 16 + p->n_tiles - 1) / p->n_tiles) * 16;
+  p->kb_per_tap = (d.Cin + kBlockK - 1) / kBlockK;
+  p->b_batched = d.b_batched;
+  p->a_bytes = p->TW * p->TH * kBlockK * 4;
+  p->b_bytes = p->BN * kBlockK * 4;
+  p->act = d.act;
+  p->alpha = d.alpha;
+  p->bias = d.bias;
+  p->residual = d.residual;
+  p->ldr = d.ldr;
+  p->out = d.out;
+  p->ldo = d.ldo;
+
+  {  // activations: {C, W, H, N}
+    cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};
+    cuuint64_t strides[3] = {(cuuint64_t)d.ldx * 4, (cuuint64_t)d.ldx * 4 * d.W,
+                             (cuuint64_t)d.ldx * 4 * d.W * d.H};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(p->TW * d.stride),
+                         (cuuint32_t)(p->TH * d.stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
+    CUresult r = enc(&p->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d.x), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      fprintf(stderr, "[mfr_b200] cuTensorMapEncodeTiled(A) failed: %d\n", (int)r);
+      return MFR_ERR_CUDA;
+    }
+  }
+  {  // weights: {Cin, Z, Cout}; Z = tap (shared weights) or image (batched B operand)
+    const int taps = d.R * d.S;
+    cuuint64_t dims[3];
+    cuuint64_t strides[2];
+    if (d.b_batched) {
+      dims[0] = d.Cin; dims[1] = d.N; dims[2] = d.Cout;
+      strides[0] = (cuuint64_t)d.Cout * d.Cin * 4;  // next image
+      strides[1] = (cuuint64_t)d.Cin * 4;           // next output row
+    } else {
+      dims[0] = d.Cin; dims[1] = taps; dims[2] = d.Cout;
+      strides[0] = (cuuint64_t)d.Cin * 4;
+      strides[1] = (cuuint64_t)d.Cin * 4 * taps;
+    }
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, 1, (cuuint32_t)p->BN};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&p->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d.w), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      fprintf(stderr, "[mfr_b200] cuTensorMapEncodeTiled(B) failed: %d\n", (int)r);
+      return MFR_ERR_CUDA;
+    }
+  }
+  return MFR_OK;
+}
+
+int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tf32_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const int total = p.N * p.tiles_y * p.tiles_x * p.n_tiles;
+  if (total <= 0) return MFR_OK;
+  const int grid = std::min(total, conv_gemm_num_sms());
+  conv_gemm_tf32_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+}  // namespace mfr

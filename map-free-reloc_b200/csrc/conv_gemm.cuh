@@ -1,0 +1,53 @@
+// Implicit-GEMM convolution / GEMM on the 5th-gen tensor cores (tcgen05, TF32 in, fp32 accumulate).
+//
+// One kernel serves every GEMM-shaped op of the matcher networks:
+//   * 3x3 / 1x1 convolutions over NHWC activations (stride 1 or 2, zero padding),
+//   * Linear layers over token sequences  (H = 1, W = tokens),
+//   * batched  X * Y^T  products (correlation volumes), B operand indexed by the image.
+// out[n, y, x, co] = act( alpha * sum_{ky,kx,ci} in[n, y*s-p+ky, x*s-p+kx, ci] * w[co, ky*S+kx, ci]
+//                         + bias[co] + residual[n, y, x, co] )
+#pragma once
+#include "common.cuh"
+
+namespace mfr {
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_ELU1 = 3 };
+
+struct alignas(64) ConvGemmParams {
+  CUtensorMap tmA;  // rank 4 {C, W, H, N}   box {32, TW*s, TH*s, 1}, 128B swizzle, zero OOB fill
+  CUtensorMap tmB;  // rank 3 {Cin, Z, Cout} box {32, 1, BN}          (Z = filter tap or image)
+  int N, Ho, Wo, Cout, Cin;
+  int R, S, stride, pad;
+  int TW, TH, tiles_x, tiles_y;
+  int BN, n_tiles, kb_per_tap, b_batched;
+  int a_bytes, b_bytes;
+  int act;
+  float alpha;
+  const float* bias;
+  const float* residual;
+  float* out;
+  long long ldr, ldo;
+};
+
+// Describes one op; build once (tensor maps are encoded on the host), launch many times.
+struct ConvGemmDesc {
+  const float* x;      // activations, NHWC with pixel stride ldx (elements)
+  int N, H, W, Cin;
+  long long ldx;
+  const float* w;      // [Cout][R*S][Cin] (Cin fastest); for batched GEMM: [N][Cout][Cin]
+  int Cout, R, S, stride, pad;
+  int b_batched;       // 0: shared weights; 1: per-image B operand
+  const float* bias;   // [Cout] or null
+  const float* residual;  // NHWC like out (pixel stride ldr) or null
+  long long ldr;
+  int act;
+  float alpha;
+  float* out;          // NHWC, pixel stride ldo
+  long long ldo;
+};
+
+int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p);
+int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream);
+int conv_gemm_num_sms();
+
+}  // namespace mfr

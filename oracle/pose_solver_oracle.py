@@ -1,0 +1,219 @@
+"""ORACLE (test infrastructure only — never imported by the product path).
+
+CPU restatement of the reference's online estimator back end,
+``lib/models/matching/pose_solver.py`` of nianticlabs/map-free-reloc, on plain numpy arrays.
+The arithmetic of the reference lives in OpenCV (un-vendored wheel, pinned
+``opencv-python==4.8.0.74`` in the reference's environment.yml:17; this image has 4.13.0) and is
+called here through exactly the same cv2 entry points and arguments as the reference's call
+sites. Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / reference arm
+may import this module.
+
+Parity status: the reference has no tests or golden vectors for this path, so
+this restatement is pinned against the *reference module itself*, imported from
+/root/reference in the build container by ``tests/golden/make_golden.py``; the resulting vectors
+are committed under ``tests/golden/`` and ``tests/test_oracle_golden.py`` replays them.
+"""
+import numpy as np
+import cv2 as cv
+
+
+def backproject_3d(uv, depth, K):
+    """pose_solver.py:6-17. ``K`` arrives as a float32 tensor in the reference (model.py feeds
+    data['K_color0'].squeeze(0)); np.linalg.inv therefore runs in float32 and the product is
+    promoted to float64 by the integer/float64 ``uv1``."""
+    uv1 = np.concatenate([uv, np.ones((uv.shape[0], 1))], axis=1)
+    xyz = depth.reshape(-1, 1) * (np.linalg.inv(np.asarray(K)) @ uv1.T).T
+    return xyz
+
+
+def normalise_kpts(kpts0, kpts1, K0, K1):
+    """pose_solver.py:39-40."""
+    k0 = (kpts0 - K0[[0, 1], [2, 2]][None]) / K0[[0, 1], [0, 1]][None]
+    k1 = (kpts1 - K1[[0, 1], [2, 2]][None]) / K1[[0, 1], [0, 1]][None]
+    return k0, k1
+
+
+def ransac_threshold(pix_threshold, K0, K1):
+    """pose_solver.py:43 (mean of K0.fx, K1.fy, K0.fy, K1.fx)."""
+    return pix_threshold / np.mean([K0[0, 0], K1[1, 1], K0[1, 1], K1[0, 0]])
+
+
+def essential_matrix_solver(kpts0, kpts1, K0, K1, pix_threshold, confidence):
+    """EssentialMatrixSolver.estimate_pose, pose_solver.py:29-61.
+    Returns (R[3,3], t[3] or [3,1] NaN, n_inliers, mask) where ``mask`` is what the reference keeps
+    in ``self.mask`` *after* cv.recoverPose mutated it in place (cheirality-filtered)."""
+    R = np.full((3, 3), np.nan)
+    t = np.full((3, 1), np.nan)
+    if len(kpts0) < 5:
+        return R, t, 0, None
+    K0 = np.asarray(K0)
+    K1 = np.asarray(K1)
+    k0, k1 = normalise_kpts(kpts0, kpts1, K0, K1)
+    thr = ransac_threshold(pix_threshold, K0, K1)
+    E, mask = cv.findEssentialMat(k0, k1, np.eye(3), threshold=thr, prob=confidence,
+                                  method=cv.USAC_MAGSAC)
+    if E is None:
+        return R, t, 0, mask
+    best_num_inliers = 0
+    ret = (R, t, 0)
+    for _E in np.split(E, len(E) / 3):
+        n, R, t, _ = cv.recoverPose(_E, k0, k1, np.eye(3), 1e9, mask=mask)
+        if n > best_num_inliers:
+            best_num_inliers = n
+            ret = (R, t[:, 0], n)
+    return ret[0], ret[1], ret[2], mask
+
+
+def scale_from_depth(R, t, mask, kpts0, kpts1, depth0, depth1, K0, K1, scale_threshold):
+    """EssentialMatrixMetricSolver.estimate_pose, pose_solver.py:132-172, the part after the
+    scale-free solve. depth0/depth1 are [H,W] float32 (the reference indexes data['depth0'][0])."""
+    m = mask.ravel() == 1
+    ik0 = np.int32(kpts0[m])
+    ik1 = np.int32(kpts1[m])
+    d0 = depth0[ik0[:, 1], ik0[:, 0]]
+    d1 = depth1[ik1[:, 1], ik1[:, 0]]
+    valid = (d0 > 0) * (d1 > 0)
+    if valid.sum() < 1:
+        return np.full((3, 3), np.nan), np.full((3, 1), np.nan), 0
+    xyz0 = backproject_3d(ik0[valid], d0[valid], K0)
+    xyz1 = backproject_3d(ik1[valid], d1[valid], K1)
+    xyz0 = (R @ xyz0.T).T
+    scale = np.dot(xyz1 - xyz0, t.reshape(3, 1))
+    best_inliers = 0
+    best_scale = None
+    for scale_hyp in scale:
+        inliers_hyp = (np.abs(scale - scale_hyp) < scale_threshold).sum().item()
+        if inliers_hyp > best_inliers:
+            best_scale = scale_hyp
+            best_inliers = inliers_hyp
+    t_metric = (best_scale * t).reshape(3, 1)
+    return R, t_metric, best_inliers
+
+
+def essential_matrix_metric_solver(kpts0, kpts1, depth0, depth1, K0, K1, pix_threshold,
+                                   confidence, scale_threshold):
+    """EssentialMatrixMetricSolver.estimate_pose, pose_solver.py:125-172."""
+    R, t, inliers, mask = essential_matrix_solver(kpts0, kpts1, K0, K1, pix_threshold, confidence)
+    if inliers == 0:
+        return R, t, inliers
+    return scale_from_depth(R, t, mask, kpts0, kpts1, depth0, depth1, K0, K1, scale_threshold)
+
+
+def pnp_solver(pts0, pts1, depth0, K0, K1, ransac_iter, reproj_threshold, confidence,
+               return_inliers=False):
+    """PnPSolver.estimate_pose, pose_solver.py:184-235."""
+    nan = (np.full((3, 3), np.nan), np.full((3, 1), np.nan), 0)
+    pts0 = np.int32(pts0)
+    if len(pts0) < 4:
+        return nan + (None,) if return_inliers else nan
+    depth_pts0 = depth0[pts0[:, 1], pts0[:, 0]]
+    valid = depth_pts0 > depth0.min()
+    if valid.sum() < 4:
+        return nan + (None,) if return_inliers else nan
+    pts0 = pts0[valid]
+    pts1 = pts1[valid]
+    depth_pts0 = depth_pts0[valid]
+    xyz_0 = backproject_3d(pts0, depth_pts0, K0)
+    K1 = np.asarray(K1)
+    succ, rvec, tvec, inliers = cv.solvePnPRansac(
+        xyz_0, pts1, K1, None, iterationsCount=ransac_iter,
+        reprojectionError=reproj_threshold, confidence=confidence, flags=cv.SOLVEPNP_P3P)
+    if succ and len(inliers) >= 6:
+        succ, rvec, tvec, _ = cv.solvePnPGeneric(
+            xyz_0[inliers], pts1[inliers], K1, None, useExtrinsicGuess=True, rvec=rvec, tvec=tvec,
+            flags=cv.SOLVEPNP_ITERATIVE)
+        rvec = rvec[0]
+        tvec = tvec[0]
+    if succ:
+        if np.linalg.norm(tvec) > 1000:
+            succ = False
+    if succ:
+        R, _ = cv.Rodrigues(rvec)
+        t = tvec.reshape(3, 1)
+    else:
+        R = np.full((3, 3), np.nan)
+        t = np.full((3, 1), np.nan)
+        inliers = []
+    if return_inliers:
+        idx = np.where(valid)[0][np.asarray(inliers).ravel()] if len(inliers) else np.zeros(0, int)
+        return R, t, len(inliers), idx
+    return R, t, len(inliers)
+
+
+# --------------------------------------------------------------------------------------------
+# Oracle extensions (not in the reference): the "polished oracle" of SURVEY.md §7 hard part 1
+# --------------------------------------------------------------------------------------------
+def sampson_sq(E, k0, k1):
+    """Squared Sampson distance of normalised correspondences under x1^T E x0 = 0 (the quantity
+    OpenCV thresholds to build the findEssentialMat mask)."""
+    x0 = np.concatenate([k0, np.ones((len(k0), 1))], 1)
+    x1 = np.concatenate([k1, np.ones((len(k1), 1))], 1)
+    Ex0 = x0 @ E.T
+    Etx1 = x1 @ E
+    num = np.sum(x1 * Ex0, 1) ** 2
+    den = Ex0[:, 0] ** 2 + Ex0[:, 1] ** 2 + Etx1[:, 0] ** 2 + Etx1[:, 1] ** 2
+    return num / den
+
+
+def _skew(v):
+    return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+
+
+def _expm_so3(w):
+    th = np.linalg.norm(w)
+    if th < 1e-14:
+        return np.eye(3) + _skew(w)
+    k = w / th
+    Kx = _skew(k)
+    return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+
+
+def polish_pose_sampson(R, t, k0, k1, mask, iters=50):
+    """Deterministic Gauss-Newton/LM on the Sampson error over a FIXED inlier mask, pose
+    parameterised as (so(3) increment, tangent-plane increment of the unit translation).
+    Returns the locally optimal (R, t_unit)."""
+    from scipy.optimize import least_squares
+    m = np.asarray(mask).ravel().astype(bool)
+    a0, a1 = k0[m].astype(np.float64), k1[m].astype(np.float64)
+    R0 = np.asarray(R, dtype=np.float64)
+    t0 = np.asarray(t, dtype=np.float64).ravel()
+    t0 = t0 / np.linalg.norm(t0)
+    # tangent basis of the sphere at t0
+    a = np.array([1.0, 0, 0]) if abs(t0[0]) < 0.9 else np.array([0, 1.0, 0])
+    b1 = np.cross(t0, a)
+    b1 /= np.linalg.norm(b1)
+    b2 = np.cross(t0, b1)
+
+    def unpack(p):
+        Rn = _expm_so3(p[:3]) @ R0
+        tn = t0 + p[3] * b1 + p[4] * b2
+        tn = tn / np.linalg.norm(tn)
+        return Rn, tn
+
+    def resid(p):
+        Rn, tn = unpack(p)
+        E = _skew(tn) @ Rn
+        x0 = np.concatenate([a0, np.ones((len(a0), 1))], 1)
+        x1 = np.concatenate([a1, np.ones((len(a1), 1))], 1)
+        Ex0 = x0 @ E.T
+        Etx1 = x1 @ E
+        num = np.sum(x1 * Ex0, 1)
+        den = np.sqrt(Ex0[:, 0] ** 2 + Ex0[:, 1] ** 2 + Etx1[:, 0] ** 2 + Etx1[:, 1] ** 2)
+        return num / den
+
+    sol = least_squares(resid, np.zeros(5), method="lm", xtol=1e-15, ftol=1e-15, gtol=1e-15,
+                        max_nfev=200 * iters)
+    return unpack(sol.x)
+
+
+def rotation_angle(Ra, Rb):
+    """angle(Ra Rb^T) in radians (lib/utils/metrics.py:24-28 formula)."""
+    c = (np.trace(Ra @ Rb.T) - 1.0) / 2.0
+    return float(np.arccos(np.clip(c, -1.0, 1.0)))
+
+
+def vector_angle(a, b):
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    c = np.dot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b))
+    return float(np.arccos(np.clip(c, -1.0, 1.0)))

@@ -1,0 +1,87 @@
+"""GPU parity of the tcgen05 implicit-GEMM conv kernel against plain PyTorch fp32 (cuDNN/cuBLAS
+with TF32 disabled). TF32 inputs => tolerance 3e-3 of the output range (stated here)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 3e-3
+
+
+def _run(mfr, x_nhwc, w, stride, pad, bias=None, residual=None, act=0, alpha=1.0, batched=False):
+    lib = mfr.load()
+    N, H, W, Cin = x_nhwc.shape
+    if batched:
+        Cout, R, S = w.shape[1], 1, 1
+    else:
+        Cout, R, S = w.shape[0], w.shape[1], w.shape[2]
+    Ho = (H + 2 * pad - R) // stride + 1
+    Wo = (W + 2 * pad - S) // stride + 1
+    out = torch.full((N, Ho, Wo, Cout), float("nan"), device="cuda", dtype=torch.float32)
+    rc = lib.mfr_conv2d_nhwc_tf32(
+        mfr.ptr(x_nhwc), N, H, W, Cin, Cin, mfr.ptr(w), Cout, R, S, stride, pad, int(batched),
+        mfr.ptr(bias), mfr.ptr(residual), Cout, act, alpha, mfr.ptr(out), Cout, mfr.cur_stream())
+    mfr.check(rc)
+    torch.cuda.synchronize()
+    return out
+
+
+def _ref(x_nhwc, w, stride, pad, bias=None, residual=None, act=0, alpha=1.0):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x = x_nhwc.permute(0, 3, 1, 2).double()
+    wt = w.permute(0, 3, 1, 2).double()  # [Cout][R][S][Cin] -> [Cout][Cin][R][S]
+    y = F.conv2d(x, wt, None, stride=stride, padding=pad) * alpha
+    y = y.permute(0, 2, 3, 1)
+    if bias is not None:
+        y = y + bias.double()
+    if residual is not None:
+        y = y + residual.double()
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = F.leaky_relu(y, 0.01)
+    elif act == 3:
+        y = F.elu(y) + 1
+    return y.float()
+
+
+def _check(out, ref):
+    assert torch.isfinite(out).all(), "non-finite / unwritten outputs"
+    scale = ref.abs().max().item()
+    err = (out - ref).abs().max().item()
+    assert err <= TOL * scale, f"max err {err} vs scale {scale}"
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,R,stride,act,use_bias,use_res", [
+    (1, 1, 300, 256, 256, 1, 1, 0, False, False),     # plain linear layer
+    (1, 1, 300, 512, 512, 1, 1, 1, False, False),     # two N tiles
+    (2, 40, 36, 128, 128, 3, 1, 1, True, True),       # residual block conv
+    (2, 40, 36, 128, 196, 3, 2, 1, True, False),      # stride-2 conv, odd Cout
+    (2, 23, 17, 196, 256, 3, 2, 2, True, False),      # channel tail (196 = 6*32+4), ragged tiles
+    (2, 40, 36, 128, 196, 1, 2, 0, True, False),      # 1x1 stride-2 shortcut
+    (1, 45, 34, 196, 196, 3, 1, 3, False, False),     # elu+1 epilogue
+    (2, 90, 68, 256, 256, 3, 1, 0, False, False),     # coarse-level size
+])
+def test_conv_matches_torch(mfr, N, H, W, Cin, Cout, R, stride, act, use_bias, use_res):
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    x = torch.randn(N, H, W, Cin, generator=g).cuda()
+    w = (torch.randn(Cout, R, R, Cin, generator=g) / (R * R * Cin) ** 0.5).cuda()
+    pad = R // 2
+    Ho = (H + 2 * pad - R) // stride + 1
+    Wo = (W + 2 * pad - R) // stride + 1
+    bias = torch.randn(Cout, generator=g).cuda() if use_bias else None
+    res = torch.randn(N, Ho, Wo, Cout, generator=g).cuda() if use_res else None
+    out = _run(mfr, x, w, stride, pad, bias, res, act, 0.5)
+    ref = _ref(x, w, stride, pad, bias, res, act, 0.5)
+    _check(out, ref)
+
+
+def test_batched_xyt(mfr):
+    g = torch.Generator(device="cpu").manual_seed(7)
+    a = torch.randn(2, 1, 300, 256, generator=g).cuda()
+    b = torch.randn(2, 500, 256, generator=g).cuda()
+    out = _run(mfr, a, b, 1, 0, alpha=1.0 / 25.6, batched=True)
+    ref = torch.einsum("nlc,nsc->nls", a[:, 0].double(), b.double()).float() / 25.6
+    _check(out[:, 0], ref)
