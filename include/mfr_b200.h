@@ -43,6 +43,93 @@ int mfr_conv2d_nhwc_tf32(const float* x, int N, int H, int W, int Cin, long long
                          int b_batched, const float* bias, const float* residual, long long ldr,
                          int act, float alpha, float* out, long long ldo, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * LoFTR matcher engine. Replaces LoFTR.forward of the reference
+ * (etc/feature_matching_baselines/LoFTR/src/loftr/loftr.py:29-75) as driven by
+ * LoFTR_matcher.match (etc/feature_matching_baselines/matchers.py:24-59), for B image pairs per
+ * call. Images are device fp32 [B][H][W] in [0,1], already padded to multiples of 8
+ * (matchers.py:41-46). Weights are set tensor by tensor in the engine's own layout (BN folded,
+ * conv weights [Cout][R*S][Cin]); mfr_loftr_weight_name/numel enumerate what is expected.
+ * Outputs stay on the device (pointers owned by the engine), ordered by (pair, i) exactly like
+ * torch.where in coarse_matching.py:194. */
+typedef struct mfr_loftr mfr_loftr;
+typedef struct {
+  const int* m_total;    /* device int[4]: {M, 2M, 25M, 50M}, M = matches in the batch */
+  const int* m_offsets;  /* device int[B+1] */
+  const int* b_ids; const int* i_ids; const int* j_ids; /* device int[capacity] */
+  const float* mconf;                                   /* device float[capacity] */
+  const float* mkpts0_f; const float* mkpts1_f;         /* device float[capacity][2], pixels (x,y) */
+  const float* mkpts1_c; const float* expec_f;          /* device float[capacity][2] / [capacity][3] */
+  int capacity;
+} mfr_loftr_outputs;
+
+int mfr_loftr_create(int B, int H, int W, float thr, int border_rm, float temperature,
+                     mfr_loftr** out);
+void mfr_loftr_destroy(mfr_loftr* h);
+int mfr_loftr_num_weights(const mfr_loftr* h);
+const char* mfr_loftr_weight_name(const mfr_loftr* h, int i);
+long long mfr_loftr_weight_numel(const mfr_loftr* h, int i);
+int mfr_loftr_set_weight(mfr_loftr* h, int i, const float* host, long long numel, void* stream);
+int mfr_loftr_forward(mfr_loftr* h, const float* img0, const float* img1, void* stream);
+void mfr_loftr_set_graph(mfr_loftr* h, int enabled);
+int mfr_loftr_get_outputs(mfr_loftr* h, mfr_loftr_outputs* out);
+/* named intermediate buffers for stage-wise parity tests ("feat_c_backbone", "feat_f", "tok", "sim", ...) */
+int mfr_loftr_debug_tensor(mfr_loftr* h, const char* name, float** ptr, long long* numel);
+int mfr_loftr_num_kernels(const mfr_loftr* h); /* launches per forward (steps of the launch list) */
+
+/* ---------------------------------------------------------------------------------------------
+ * Pose back end (batched-hypothesis RANSAC). Replaces lib/models/matching/pose_solver.py.
+ * Correspondences of P pairs are concatenated: kpts0/kpts1 device float[total][2] in pixels (x,y),
+ * offsets device int[P+1]; K0/K1 device float[P][9] row-major intrinsics; depth maps device
+ * float[P][H][W] metres (0 = invalid). Outputs: R float[P][9], t float[P][3], inliers int[P],
+ * mask unsigned char[total]. Failure of a pair = NaN-filled R,t and 0 inliers
+ * (pose_solver.py:30-33,50-51,146-150,189,198,231-233).
+ * A solver handle owns the scratch memory; correspondences per pair are capped at 8192.       */
+typedef struct mfr_pose_solver mfr_pose_solver;
+int mfr_pose_solver_create(int max_pairs, int max_pts_per_pair, int max_hypotheses,
+                           mfr_pose_solver** out);
+void mfr_pose_solver_destroy(mfr_pose_solver* s);
+
+/* EssentialMatrixSolver.estimate_pose (pose_solver.py:29-61): cv.findEssentialMat(USAC_MAGSAC) +
+ * cv.recoverPose. `num_hyp` 5-point hypotheses per pair (MSAC-scored), then local optimisation
+ * (LM on the Sampson error over the inliers) when lo_enabled != 0. t has unit norm. The final
+ * (R, t) is also kept in fp64 inside the handle for mfr_scale_from_depth. */
+int mfr_emat_ransac(mfr_pose_solver* s, const float* kpts0, const float* kpts1, const int* offsets,
+                    int P, const float* K0, const float* K1, float pix_threshold, int num_hyp,
+                    unsigned long long seed, int lo_enabled, float* R, float* t, int* n_inliers,
+                    unsigned char* mask, void* stream);
+
+/* EssentialMatrixMetricSolver.estimate_pose (pose_solver.py:132-172), the part after the
+ * scale-free solve: depth lookup at int-truncated inlier keypoints, back-projection, per-point
+ * scale, exhaustive consensus with |s - s_hyp| < scale_threshold. Rd/td: device double[P][9]/[P][3]
+ * pose to use, or NULL to take the pose left in the handle by mfr_emat_ransac. */
+int mfr_scale_from_depth(mfr_pose_solver* s, const float* kpts0, const float* kpts1,
+                         const int* offsets, int P, const float* K0, const float* K1,
+                         const unsigned char* mask, const double* Rd, const double* td,
+                         const float* depth0, const float* depth1, int H, int W,
+                         float scale_threshold, float* R_out, float* t_metric, int* inliers,
+                         void* stream);
+
+/* PnPSolver.estimate_pose (pose_solver.py:184-235): lift kpts0 through depth0 (valid iff depth >
+ * depth0.min()), P3P RANSAC on (xyz0, kpts1) with reprojection threshold in pixels, LM refinement
+ * on the inliers when there are >= 6, reject |t| > 1000. */
+int mfr_pnp_ransac(mfr_pose_solver* s, const float* kpts0, const float* kpts1, const int* offsets,
+                   int P, const float* K0, const float* K1, const float* depth0, int H, int W,
+                   int num_hyp, float reproj_threshold, unsigned long long seed, float* R, float* t,
+                   int* n_inliers, unsigned char* mask, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host test hooks: the minimal solvers used inside the RANSAC kernels are __host__ __device__
+ * functions; these run the very same code on the CPU so that it can be unit-tested without a GPU.
+ * They are NOT a CPU fallback: no product entry point calls them.
+ *   five_point : x0, x1 double[5][2] normalised points, E_out double[10][9]; returns #solutions
+ *   p3p        : X double[3][3] points, f double[3][3] unit bearings, R_out [4][9], t_out [4][3]
+ *   poly roots : coef[0..deg] ascending, deg <= 10; returns #real roots (ascending)          */
+int mfr_host_five_point(const double* x0, const double* x1, double* E_out);
+int mfr_host_p3p(const double* X, const double* f, double* R_out, double* t_out);
+int mfr_host_poly_real_roots(const double* coef, int deg, double* roots);
+int mfr_host_decompose_essential(const double* E, double* R1, double* R2, double* t);
+
 #ifdef __cplusplus
 }
 #endif

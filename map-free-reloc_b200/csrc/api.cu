@@ -3,6 +3,9 @@
 
 #include "common.cuh"
 #include "conv_gemm.cuh"
+#include "loftr_engine.cuh"
+#include "geometry_solvers.cuh"
+#include "geometry.cuh"
 
 extern "C" {
 
@@ -27,6 +30,101 @@ int mfr_conv2d_nhwc_tf32(const float* x, int N, int H, int W, int Cin, long long
   int rc = mfr::conv_gemm_build(d, &p);
   if (rc != MFR_OK) return rc;
   return mfr::conv_gemm_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------ LoFTR
+struct mfr_loftr { mfr::LoftrEngine* e; };
+
+int mfr_loftr_create(int B, int H, int W, float thr, int border_rm, float temperature, mfr_loftr** out) {
+  if (!out) return MFR_ERR_ARG;
+  mfr::LoftrEngine* e = nullptr;
+  int rc = mfr::loftr_create(B, H, W, thr, border_rm, temperature, &e);
+  if (rc != MFR_OK) return rc;
+  *out = new mfr_loftr{e};
+  return MFR_OK;
+}
+void mfr_loftr_destroy(mfr_loftr* h) {
+  if (!h) return;
+  mfr::loftr_destroy(h->e);
+  delete h;
+}
+int mfr_loftr_num_weights(const mfr_loftr* h) { return mfr::loftr_num_weights(h->e); }
+const char* mfr_loftr_weight_name(const mfr_loftr* h, int i) { return mfr::loftr_weight_name(h->e, i); }
+long long mfr_loftr_weight_numel(const mfr_loftr* h, int i) { return mfr::loftr_weight_numel(h->e, i); }
+int mfr_loftr_set_weight(mfr_loftr* h, int i, const float* host, long long numel, void* stream) {
+  return mfr::loftr_set_weight(h->e, i, host, numel, static_cast<cudaStream_t>(stream));
+}
+int mfr_loftr_forward(mfr_loftr* h, const float* img0, const float* img1, void* stream) {
+  return mfr::loftr_forward(h->e, img0, img1, static_cast<cudaStream_t>(stream));
+}
+void mfr_loftr_set_graph(mfr_loftr* h, int enabled) { mfr::loftr_set_graph(h->e, enabled); }
+int mfr_loftr_get_outputs(mfr_loftr* h, mfr_loftr_outputs* out) {
+  if (!h || !out) return MFR_ERR_ARG;
+  mfr::LoftrOutputs o = mfr::loftr_outputs(h->e);
+  out->m_total = o.m_total; out->m_offsets = o.m_offsets; out->b_ids = o.b_ids; out->i_ids = o.i_ids;
+  out->j_ids = o.j_ids; out->mconf = o.mconf; out->mkpts0_f = o.mkpts0_f; out->mkpts1_f = o.mkpts1_f;
+  out->mkpts1_c = o.mkpts1_c; out->expec_f = o.expec_f; out->capacity = o.capacity;
+  return MFR_OK;
+}
+int mfr_loftr_debug_tensor(mfr_loftr* h, const char* name, float** ptr, long long* numel) {
+  return mfr::loftr_debug_tensor(h->e, name, ptr, numel);
+}
+int mfr_loftr_num_kernels(const mfr_loftr* h) { return mfr::loftr_num_steps(h->e); }
+
+// ------------------------------------------------------------------------------------------ pose back end
+struct mfr_pose_solver { mfr::PoseSolver* s; };
+
+int mfr_pose_solver_create(int max_pairs, int max_pts_per_pair, int max_hypotheses, mfr_pose_solver** out) {
+  if (!out) return MFR_ERR_ARG;
+  mfr::PoseSolver* s = nullptr;
+  int rc = mfr::pose_solver_create(max_pairs, max_pts_per_pair, max_hypotheses, &s);
+  if (rc != MFR_OK) return rc;
+  *out = new mfr_pose_solver{s};
+  return MFR_OK;
+}
+void mfr_pose_solver_destroy(mfr_pose_solver* s) {
+  if (!s) return;
+  mfr::pose_solver_destroy(s->s);
+  delete s;
+}
+int mfr_emat_ransac(mfr_pose_solver* s, const float* kpts0, const float* kpts1, const int* offsets, int P,
+                    const float* K0, const float* K1, float pix_threshold, int num_hyp,
+                    unsigned long long seed, int lo_enabled, float* R, float* t, int* n_inliers,
+                    unsigned char* mask, void* stream) {
+  return mfr::emat_ransac(s->s, kpts0, kpts1, offsets, P, K0, K1, pix_threshold, num_hyp, seed, lo_enabled, R,
+                          t, n_inliers, mask, static_cast<cudaStream_t>(stream));
+}
+int mfr_scale_from_depth(mfr_pose_solver* s, const float* kpts0, const float* kpts1, const int* offsets, int P,
+                         const float* K0, const float* K1, const unsigned char* mask, const double* Rd,
+                         const double* td, const float* depth0, const float* depth1, int H, int W,
+                         float scale_threshold, float* R_out, float* t_metric, int* inliers, void* stream) {
+  return mfr::scale_from_depth(s->s, kpts0, kpts1, offsets, P, K0, K1, mask, Rd, td, depth0, depth1, H, W,
+                               scale_threshold, R_out, t_metric, inliers, static_cast<cudaStream_t>(stream));
+}
+int mfr_pnp_ransac(mfr_pose_solver* s, const float* kpts0, const float* kpts1, const int* offsets, int P,
+                   const float* K0, const float* K1, const float* depth0, int H, int W, int num_hyp,
+                   float reproj_threshold, unsigned long long seed, float* R, float* t, int* n_inliers,
+                   unsigned char* mask, void* stream) {
+  return mfr::pnp_ransac(s->s, kpts0, kpts1, offsets, P, K0, K1, depth0, H, W, num_hyp, reproj_threshold, seed,
+                         R, t, n_inliers, mask, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------ host test hooks
+int mfr_host_five_point(const double* x0, const double* x1, double* E_out) {
+  return mfr::geo::five_point(reinterpret_cast<const double(*)[2]>(x0), reinterpret_cast<const double(*)[2]>(x1),
+                              reinterpret_cast<double(*)[9]>(E_out));
+}
+int mfr_host_p3p(const double* X, const double* f, double* R_out, double* t_out) {
+  return mfr::geo::p3p(reinterpret_cast<const double(*)[3]>(X), reinterpret_cast<const double(*)[3]>(f),
+                       reinterpret_cast<double(*)[9]>(R_out), reinterpret_cast<double(*)[3]>(t_out));
+}
+int mfr_host_poly_real_roots(const double* coef, int deg, double* roots) {
+  if (deg < 1 || deg > mfr::geo::kMaxDeg) return -1;
+  return mfr::geo::poly_real_roots(coef, deg, roots);
+}
+int mfr_host_decompose_essential(const double* E, double* R1, double* R2, double* t) {
+  mfr::geo::decompose_essential(E, R1, R2, t);
+  return MFR_OK;
 }
 
 }  // extern "C"

@@ -78,7 +78,12 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
 
-  const int m_tiles = p.N * p.tiles_y * p.tiles_x;
+  int w_lim = p.Wo, tiles_x = p.tiles_x;
+  if (p.dyn_w != nullptr) {
+    w_lim = min(p.Wo, *p.dyn_w);
+    tiles_x = (w_lim + p.TW - 1) / p.TW;
+  }
+  const int m_tiles = p.N * p.tiles_y * tiles_x;
   const int total_tiles = m_tiles * p.n_tiles;
   const int num_kb = p.R * p.S * p.kb_per_tap;
 
@@ -89,9 +94,9 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile % m_tiles, nt = tile / m_tiles;
-        const int tx = mt % p.tiles_x;
-        const int ty = (mt / p.tiles_x) % p.tiles_y;
-        const int img = mt / (p.tiles_x * p.tiles_y);
+        const int tx = mt % tiles_x;
+        const int ty = (mt / tiles_x) % p.tiles_y;
+        const int img = mt / (tiles_x * p.tiles_y);
         const int x_in0 = tx * p.TW * p.stride - p.pad;
         const int y_in0 = ty * p.TH * p.stride - p.pad;
         const int n0 = nt * p.BN;
@@ -153,11 +158,11 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int mt = tile % m_tiles, nt = tile / m_tiles;
-      const int tx = mt % p.tiles_x;
-      const int ty = (mt / p.tiles_x) % p.tiles_y;
-      const int img = mt / (p.tiles_x * p.tiles_y);
+      const int tx = mt % tiles_x;
+      const int ty = (mt / tiles_x) % p.tiles_y;
+      const int img = mt / (tiles_x * p.tiles_y);
       const int y = ty * p.TH + ly, x = tx * p.TW + lx;
-      const bool row_ok = (row < p.TW * p.TH) && (y < p.Ho) && (x < p.Wo);
+      const bool row_ok = (row < p.TW * p.TH) && (y < p.Ho) && (x < w_lim);
       const long long pix = (static_cast<long long>(img) * p.Ho + y) * p.Wo + x;
       float* orow = p.out + pix * p.ldo;
       const float* rrow = p.residual ? p.residual + pix * p.ldr : nullptr;
@@ -190,8 +195,10 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
                   const float4 s = __ldg(reinterpret_cast<const float4*>(rrow + n));
                   v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
                 }
-                v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
-                v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+                if (n < p.act_cols) {
+                  v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
+                  v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+                }
                 *reinterpret_cast<float4*>(orow + n) = v;
               }
             }
@@ -203,7 +210,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
                 float v = __uint_as_float(r[j]) * p.alpha;
                 if (p.bias) v += __ldg(p.bias + n);
                 if (rrow) v += __ldg(rrow + n);
-                orow[n] = apply_act(v, p.act);
+                orow[n] = n < p.act_cols ? apply_act(v, p.act) : v;
               }
             }
           }
@@ -311,6 +318,9 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
   p->a_bytes = p->TW * p->TH * kBlockK * 4;
   p->b_bytes = p->BN * kBlockK * 4;
   p->act = d.act;
+  p->act_cols = d.act_cols > 0 ? d.act_cols : d.Cout;
+  p->dyn_w = d.dyn_w;
+  if (d.dyn_w != nullptr && (d.H != 1 || d.R != 1 || d.S != 1 || d.stride != 1)) return MFR_ERR_ARG;
   p->alpha = d.alpha;
   p->bias = d.bias;
   p->residual = d.residual;
@@ -338,9 +348,11 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
     cuuint64_t dims[3];
     cuuint64_t strides[2];
     if (d.b_batched) {
+      const long long ldw = d.ldw > 0 ? d.ldw : d.Cin;
+      if (ldw % 4) return MFR_ERR_ARG;
       dims[0] = d.Cin; dims[1] = d.N; dims[2] = d.Cout;
-      strides[0] = (cuuint64_t)d.Cout * d.Cin * 4;  // next image
-      strides[1] = (cuuint64_t)d.Cin * 4;           // next output row
+      strides[0] = (cuuint64_t)d.Cout * ldw * 4;  // next image
+      strides[1] = (cuuint64_t)ldw * 4;           // next output row
     } else {
       dims[0] = d.Cin; dims[1] = taps; dims[2] = d.Cout;
       strides[0] = (cuuint64_t)d.Cin * 4;

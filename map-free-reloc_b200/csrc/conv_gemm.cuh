@@ -21,7 +21,8 @@ struct alignas(64) ConvGemmParams {
   int TW, TH, tiles_x, tiles_y;
   int BN, n_tiles, kb_per_tap, b_batched;
   int a_bytes, b_bytes;
-  int act;
+  int act, act_cols;    // activation applies to output channels < act_cols
+  const int* dyn_w;     // optional device int: effective W (rows of a token GEMM), H must be 1
   float alpha;
   const float* bias;
   const float* residual;
@@ -34,9 +35,12 @@ struct ConvGemmDesc {
   const float* x;      // activations, NHWC with pixel stride ldx (elements)
   int N, H, W, Cin;
   long long ldx;
-  const float* w;      // [Cout][R*S][Cin] (Cin fastest); for batched GEMM: [N][Cout][Cin]
+  const float* w;      // [Cout][R*S][Cin] (Cin fastest); for batched GEMM: [N][Cout][ldw]
   int Cout, R, S, stride, pad;
   int b_batched;       // 0: shared weights; 1: per-image B operand
+  long long ldw;       // batched only: row stride of w in floats (0 = Cin)
+  int act_cols;        // 0 = all output channels
+  const int* dyn_w;    // optional device row count (token GEMMs with data-dependent length)
   const float* bias;   // [Cout] or null
   const float* residual;  // NHWC like out (pixel stride ldr) or null
   long long ldr;

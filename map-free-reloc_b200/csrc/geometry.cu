@@ -1,0 +1,989 @@
+// Pose back end on the GPU: batched-hypothesis RANSAC for the essential matrix (5-point) and for
+// PnP (P3P), local optimisation, cheirality, depth lift and the scale consensus.
+// Replaces the OpenCV calls of the reference's lib/models/matching/pose_solver.py:
+//   EssentialMatrixSolver.estimate_pose        :29-61   -> emat_ransac
+//   EssentialMatrixMetricSolver.estimate_pose  :125-172 -> scale_from_depth
+//   PnPSolver.estimate_pose                    :184-235 -> pnp_ransac
+// Hypothesis kernels: every lane of a warp draws its own minimal sample and solves it in fp64
+// registers/local memory (fixed work bound, no complex arithmetic); the warp then scores its 32
+// hypotheses one after the other with all lanes striding over the correspondences held in shared
+// memory, inlier counts via __ballot_sync/__popc. Thousands of hypotheses per pair, many pairs per
+// launch (grid.y = pair).
+#include "geometry.cuh"
+
+#include <algorithm>
+
+#include "geometry_solvers.cuh"
+
+namespace mfr {
+
+namespace {
+
+using namespace geo;
+
+constexpr int kHypPerBlock = 128;  // 4 warps x 32 lanes
+
+struct HypResult {   // best hypothesis of one block
+  double cost;       // MSAC cost (emat) or -inlier count (pnp): lower is better
+  int count;
+  int valid;
+  double model[12];  // E[9] or R[9] t[3]
+};
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long& s) {
+  s += 0x9E3779B97F4A7C15ull;
+  unsigned long long z = s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+template <int K>
+__device__ __forceinline__ void sample_distinct(unsigned long long& st, int n, int* idx) {
+  for (int k = 0; k < K; ++k) {
+    int v = 0;
+    for (int tries = 0; tries < 64; ++tries) {
+      v = static_cast<int>(splitmix64(st) % static_cast<unsigned long long>(n));
+      bool dup = false;
+      for (int j = 0; j < k; ++j) dup |= (idx[j] == v);
+      if (!dup) break;
+    }
+    idx[k] = v;
+  }
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of K doubles per thread (blockDim.x = 256); result valid in thread 0
+template <int K>
+__device__ __forceinline__ void block_sum_256(double (&v)[K], double* sh /*[8*K]*/) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum_d(v[k]);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < K; ++k) sh[w * K + k] = v[k];
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int k = 0; k < K; ++k) {
+      double s = 0.0;
+      for (int ww = 0; ww < 8; ++ww) s += sh[ww * K + k];
+      v[k] = s;
+    }
+  __syncthreads();
+}
+
+// float32 normalisation exactly as numpy does it on float32 arrays (pose_solver.py:39-40)
+__device__ __forceinline__ float4 normalise_pt(const float* k0, const float* k1, int i, const float* K0,
+                                               const float* K1) {
+  float4 p;
+  p.x = __fdiv_rn(__fsub_rn(k0[2 * i], K0[2]), K0[0]);
+  p.y = __fdiv_rn(__fsub_rn(k0[2 * i + 1], K0[5]), K0[4]);
+  p.z = __fdiv_rn(__fsub_rn(k1[2 * i], K1[2]), K1[0]);
+  p.w = __fdiv_rn(__fsub_rn(k1[2 * i + 1], K1[5]), K1[4]);
+  return p;
+}
+// pose_solver.py:43 in float32
+__device__ __forceinline__ float emat_threshold(float pix_thr, const float* K0, const float* K1) {
+  const float m = __fmul_rn(__fadd_rn(__fadd_rn(K0[0], K1[4]), __fadd_rn(K0[4], K1[0])), 0.25f);
+  return __fdiv_rn(pix_thr, m);
+}
+
+__device__ __forceinline__ float sampson_sq_f(const float* E, float4 p) {
+  const float a0 = fmaf(E[0], p.x, fmaf(E[1], p.y, E[2]));
+  const float a1 = fmaf(E[3], p.x, fmaf(E[4], p.y, E[5]));
+  const float a2 = fmaf(E[6], p.x, fmaf(E[7], p.y, E[8]));
+  const float b0 = fmaf(E[0], p.z, fmaf(E[3], p.w, E[6]));
+  const float b1 = fmaf(E[1], p.z, fmaf(E[4], p.w, E[7]));
+  const float num = fmaf(p.z, a0, fmaf(p.w, a1, a2));
+  const float den = fmaf(a0, a0, fmaf(a1, a1, fmaf(b0, b0, b1 * b1)));
+  return __fdividef(num * num, den);
+}
+
+// ================================================================================================
+// essential matrix: hypothesis generation + scoring
+// ================================================================================================
+__global__ void __launch_bounds__(kHypPerBlock) emat_hyp_kernel(
+    const float* __restrict__ kpts0, const float* __restrict__ kpts1, const int* __restrict__ offsets,
+    const float* __restrict__ K0s, const float* __restrict__ K1s, float pix_thr, int num_hyp,
+    unsigned long long seed, int max_pts, HypResult* __restrict__ results) {
+  extern __shared__ float4 s_pts[];
+  __shared__ HypResult s_best[kHypPerBlock / 32];
+  const int pair = blockIdx.y;
+  const int n0 = offsets[pair];
+  const int N = min(offsets[pair + 1] - n0, max_pts);
+  HypResult* out = results + static_cast<size_t>(pair) * gridDim.x + blockIdx.x;
+  if (N < 5) {
+    if (threadIdx.x == 0) { out->valid = 0; out->cost = 1e300; out->count = 0; }
+    return;
+  }
+  const float* K0 = K0s + 9 * pair;
+  const float* K1 = K1s + 9 * pair;
+  const float* k0 = kpts0 + 2 * static_cast<size_t>(n0);
+  const float* k1 = kpts1 + 2 * static_cast<size_t>(n0);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s_pts[i] = normalise_pt(k0, k1, i, K0, K1);
+  __syncthreads();
+  const float thr = emat_threshold(pix_thr, K0, K1);
+  const float thr2 = thr * thr;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = blockIdx.x * kHypPerBlock + threadIdx.x;
+  double Ec[10][9];
+  int ncand = 0;
+  if (h < num_hyp) {
+    unsigned long long st = seed ^ (0xD1B54A32D192ED03ull * (static_cast<unsigned long long>(pair) + 1)) ^
+                            (0x9E3779B97F4A7C15ull * (static_cast<unsigned long long>(h) + 1));
+    int idx[5];
+    sample_distinct<5>(st, N, idx);
+    double x0[5][2], x1[5][2];
+    for (int k = 0; k < 5; ++k) {
+      const float4 p = s_pts[idx[k]];
+      x0[k][0] = p.x; x0[k][1] = p.y; x1[k][0] = p.z; x1[k][1] = p.w;
+    }
+    ncand = five_point(x0, x1, Ec);
+  }
+  // ---- scoring: the warp walks over its 32 hypotheses
+  float best_cost = 3.0e38f;
+  int best_cnt = 0, best_src = -1, best_c = 0;
+  for (int src = 0; src < 32; ++src) {
+    const int cnt = __shfl_sync(0xffffffffu, ncand, src);
+    for (int c = 0; c < cnt; ++c) {
+      float E[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) E[k] = __shfl_sync(0xffffffffu, static_cast<float>(Ec[c][k]), src);
+      float cost = 0.f;
+      int inl = 0;
+      bool dead = false;
+      for (int i0 = 0; i0 < N; i0 += 128) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 32 + lane;
+          float d2 = thr2;
+          bool ok = false;
+          if (i < N) {
+            d2 = sampson_sq_f(E, s_pts[i]);
+            ok = d2 < thr2;
+            cost += fminf(d2, thr2);
+          }
+          inl += __popc(__ballot_sync(0xffffffffu, ok));
+        }
+        // MSAC cost only grows: give up on this model once it cannot beat the best so far
+        const float partial = warp_sum_f(cost);
+        if (partial >= best_cost) { dead = true; break; }
+      }
+      if (dead) continue;
+      const float total = warp_sum_f(cost);
+      if (total < best_cost) {
+        best_cost = total;
+        best_cnt = inl;
+        best_src = src;
+        best_c = c;
+      }
+    }
+  }
+  if (lane == 0) {
+    s_best[warp].valid = best_src >= 0 ? 1 : 0;
+    s_best[warp].cost = best_src >= 0 ? static_cast<double>(best_cost) : 1e300;
+    s_best[warp].count = best_cnt;
+  }
+  if (best_src >= 0 && lane == best_src)
+    for (int k = 0; k < 9; ++k) s_best[warp].model[k] = Ec[best_c][k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int bw = 0;
+    for (int w = 1; w < kHypPerBlock / 32; ++w)
+      if (s_best[w].cost < s_best[bw].cost) bw = w;
+    *out = s_best[bw];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sampson residual and its Jacobian w.r.t. (d_omega[3], d_tau[2]) for E = [t]x R
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tangent_basis(const double* t, double* b1, double* b2) {
+  double a[3] = {0, 0, 0};
+  const double ax = fabs(t[0]), ay = fabs(t[1]), az = fabs(t[2]);
+  if (ax <= ay && ax <= az) a[0] = 1.0; else if (ay <= az) a[1] = 1.0; else a[2] = 1.0;
+  cross3(t, a, b1);
+  const double n = norm3(b1);
+  for (int k = 0; k < 3; ++k) b1[k] /= n;
+  cross3(t, b1, b2);
+}
+
+__device__ __forceinline__ double sampson_res_jac(const double* R, const double* t, const double* b1,
+                                                  const double* b2, float4 p, double* J) {
+  const double x0[3] = {p.x, p.y, 1.0}, x1[3] = {p.z, p.w, 1.0};
+  double y[3], w[3], a[3], b[3], tmp[3];
+  mat3_vec(R, x0, y);   // y = R x0
+  cross3(t, y, a);      // a = E x0 = t x (R x0)
+  cross3(t, x1, w);     // w = t x x1 ; E^T x1 = -R^T w
+  // b = E^T x1 = R^T [t]x^T x1 = -R^T (t x x1)
+  for (int i = 0; i < 3; ++i) b[i] = -(R[i] * w[0] + R[3 + i] * w[1] + R[6 + i] * w[2]);
+  const double n = dot3(x1, a);
+  const double s = a[0] * a[0] + a[1] * a[1] + b[0] * b[0] + b[1] * b[1];
+  const double is = 1.0 / sqrt(s);
+  const double r = n * is;
+  const double c2 = -0.5 * n * is * is * is;
+  for (int k = 0; k < 5; ++k) {
+    double da[3], db[3];
+    if (k < 3) {
+      double ek[3] = {0, 0, 0};
+      ek[k] = 1.0;
+      cross3(ek, y, tmp);
+      cross3(t, tmp, da);                 // da = t x (e_k x y)
+      cross3(ek, w, tmp);                 // db = R^T (e_k x w)
+      for (int i = 0; i < 3; ++i) db[i] = R[i] * tmp[0] + R[3 + i] * tmp[1] + R[6 + i] * tmp[2];
+    } else {
+      const double* bj = (k == 3) ? b1 : b2;
+      cross3(bj, y, da);                  // da = b_j x y
+      cross3(bj, x1, tmp);                // db = -R^T (b_j x x1)
+      for (int i = 0; i < 3; ++i) db[i] = -(R[i] * tmp[0] + R[3 + i] * tmp[1] + R[6 + i] * tmp[2]);
+    }
+    const double dn = dot3(x1, da);
+    const double ds = 2.0 * (a[0] * da[0] + a[1] * da[1] + b[0] * db[0] + b[1] * db[1]);
+    J[k] = dn * is + c2 * ds;
+  }
+  return r;
+}
+
+// cheirality of one correspondence for a candidate (R, t): both depths positive
+__device__ __forceinline__ bool cheirality_ok(const double* R, const double* t, float4 p) {
+  const double d0[3] = {p.x, p.y, 1.0}, d1[3] = {p.z, p.w, 1.0};
+  double a[3];
+  mat3_vec(R, d0, a);
+  const double aa = dot3(a, a), bb = dot3(d1, d1), ab = dot3(a, d1), at = dot3(a, t), bt = dot3(d1, t);
+  const double det = aa * bb - ab * ab;
+  if (!(fabs(det) > 1e-300)) return false;
+  const double l0 = (-at * bb + ab * bt) / det;
+  const double l1 = (aa * bt - ab * at) / det;
+  return l0 > 0.0 && l1 > 0.0 && l0 < 1e9 && l1 < 1e9;
+}
+
+// solve (H + lambda diag(H)) d = -g for an n x n SPD system stored full (row-major, n <= 6)
+__device__ inline bool solve_damped(const double* H, const double* g, double lambda, int n, double* d) {
+  double A[6][7];
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) A[i][j] = H[i * n + j];
+    A[i][i] += lambda * (H[i * n + i] + 1e-12);
+    A[i][n] = -g[i];
+  }
+  for (int k = 0; k < n; ++k) {
+    int pr = k;
+    for (int i = k + 1; i < n; ++i)
+      if (fabs(A[i][k]) > fabs(A[pr][k])) pr = i;
+    if (fabs(A[pr][k]) < 1e-300) return false;
+    if (pr != k)
+      for (int j = 0; j <= n; ++j) { const double tt = A[k][j]; A[k][j] = A[pr][j]; A[pr][j] = tt; }
+    for (int i = k + 1; i < n; ++i) {
+      const double f = A[i][k] / A[k][k];
+      for (int j = k; j <= n; ++j) A[i][j] -= f * A[k][j];
+    }
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = A[i][n];
+    for (int j = i + 1; j < n; ++j) s -= A[i][j] * d[j];
+    d[i] = s / A[i][i];
+  }
+  return true;
+}
+
+// ================================================================================================
+// essential matrix: best-of-blocks, local optimisation, cheirality, final mask
+// ================================================================================================
+constexpr int kLoOuter = 4, kLoInner = 6;
+
+__global__ void __launch_bounds__(256) emat_final_kernel(
+    const float* __restrict__ kpts0, const float* __restrict__ kpts1, const int* __restrict__ offsets,
+    const float* __restrict__ K0s, const float* __restrict__ K1s, float pix_thr, int blocks_per_pair,
+    int max_pts, const HypResult* __restrict__ results, double* __restrict__ Rd, double* __restrict__ td,
+    float* __restrict__ Rf, float* __restrict__ tf, int* __restrict__ n_inl,
+    unsigned char* __restrict__ mask, int lo_enabled) {
+  extern __shared__ float4 s_pts[];
+  __shared__ double sh_red[8 * 21];
+  __shared__ double s_R[9], s_t[3], s_E[9], s_Eo[9], s_prevR[9], s_prevt[3], s_H[25], s_g[5];
+  __shared__ double s_prev_cost, s_lambda;
+  __shared__ int s_flag, s_cnt[4];
+  __shared__ double c_R1[9], c_R2[9], c_t[3];
+  const int pair = blockIdx.x;
+  const int n0 = offsets[pair];
+  const int Nall = offsets[pair + 1] - n0;
+  const int N = min(Nall, max_pts);
+  auto fail = [&]() {
+    for (int i = threadIdx.x; i < Nall; i += blockDim.x) mask[n0 + i] = 0;
+    if (threadIdx.x < 9) { Rf[9 * pair + threadIdx.x] = NAN; Rd[9 * pair + threadIdx.x] = NAN; }
+    if (threadIdx.x < 3) { tf[3 * pair + threadIdx.x] = NAN; td[3 * pair + threadIdx.x] = NAN; }
+    if (threadIdx.x == 0) n_inl[pair] = 0;
+  };
+  if (N < 5) { fail(); return; }
+  const float* K0 = K0s + 9 * pair;
+  const float* K1 = K1s + 9 * pair;
+  const float* k0 = kpts0 + 2 * static_cast<size_t>(n0);
+  const float* k1 = kpts1 + 2 * static_cast<size_t>(n0);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s_pts[i] = normalise_pt(k0, k1, i, K0, K1);
+  const double thr = static_cast<double>(emat_threshold(pix_thr, K0, K1));
+  const double thr2 = thr * thr;
+  if (threadIdx.x == 0) {
+    const HypResult* r = results + static_cast<size_t>(pair) * blocks_per_pair;
+    int b = -1;
+    for (int k = 0; k < blocks_per_pair; ++k)
+      if (r[k].valid && (b < 0 || r[k].cost < r[b].cost)) b = k;
+    s_flag = b;
+    if (b >= 0)
+      for (int k = 0; k < 9; ++k) s_E[k] = r[b].model[k];
+  }
+  __syncthreads();
+  if (s_flag < 0) { fail(); return; }
+
+  // ---- pick (R, t) among the four decompositions by cheirality over the inliers of E
+  auto choose_pose = [&]() {
+    if (threadIdx.x == 0) decompose_essential(s_E, c_R1, c_R2, c_t);
+    __syncthreads();
+    double cnt[4] = {0, 0, 0, 0};
+    double tn[3] = {-c_t[0], -c_t[1], -c_t[2]};
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const float4 p = s_pts[i];
+      if (sampson_sq(s_E, p.x, p.y, p.z, p.w) < thr2) {
+        cnt[0] += cheirality_ok(c_R1, c_t, p) ? 1.0 : 0.0;
+        cnt[1] += cheirality_ok(c_R2, c_t, p) ? 1.0 : 0.0;
+        cnt[2] += cheirality_ok(c_R1, tn, p) ? 1.0 : 0.0;
+        cnt[3] += cheirality_ok(c_R2, tn, p) ? 1.0 : 0.0;
+      }
+    }
+    block_sum_256<4>(cnt, sh_red);
+    if (threadIdx.x == 0) {
+      int b = 0;
+      for (int k = 1; k < 4; ++k)
+        if (cnt[k] > cnt[b]) b = k;
+      const double* Rb = (b == 0 || b == 2) ? c_R1 : c_R2;
+      for (int k = 0; k < 9; ++k) s_R[k] = Rb[k];
+      for (int k = 0; k < 3; ++k) s_t[k] = (b < 2) ? c_t[k] : -c_t[k];
+      s_cnt[0] = static_cast<int>(cnt[b] + 0.5);
+    }
+    __syncthreads();
+  };
+  choose_pose();
+
+  // ---- local optimisation: LM on the Sampson error over the inliers of the current model
+  if (lo_enabled) {
+    for (int outer = 0; outer < kLoOuter; ++outer) {
+      if (threadIdx.x == 0) {
+        essential_from_rt(s_R, s_t, s_Eo);   // the model that defines this round's inlier set
+        s_lambda = 1e-6;
+        s_prev_cost = 1e300;
+      }
+      __syncthreads();
+      for (int it = 0; it <= kLoInner; ++it) {
+        double R[9], t[3], b1[3], b2[3];
+        for (int k = 0; k < 9; ++k) R[k] = s_R[k];
+        for (int k = 0; k < 3; ++k) t[k] = s_t[k];
+        tangent_basis(t, b1, b2);
+        double acc[21];
+        for (int k = 0; k < 21; ++k) acc[k] = 0.0;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+          const float4 p = s_pts[i];
+          if (!(sampson_sq(s_Eo, p.x, p.y, p.z, p.w) < thr2)) continue;
+          double J[5];
+          const double r = sampson_res_jac(R, t, b1, b2, p, J);
+          int q = 0;
+          for (int a = 0; a < 5; ++a)
+            for (int b = a; b < 5; ++b) acc[q++] += J[a] * J[b];
+          for (int a = 0; a < 5; ++a) acc[15 + a] += J[a] * r;
+          acc[20] += r * r;
+        }
+        block_sum_256<21>(acc, sh_red);
+        if (threadIdx.x == 0) {
+          const double cost = acc[20];
+          if (cost <= s_prev_cost) {  // accept the parameters that produced this pass
+            s_prev_cost = cost;
+            for (int k = 0; k < 9; ++k) s_prevR[k] = s_R[k];
+            for (int k = 0; k < 3; ++k) s_prevt[k] = s_t[k];
+            int q = 0;
+            for (int a = 0; a < 5; ++a)
+              for (int b = a; b < 5; ++b) { s_H[a * 5 + b] = acc[q]; s_H[b * 5 + a] = acc[q]; ++q; }
+            for (int a = 0; a < 5; ++a) s_g[a] = acc[15 + a];
+            s_lambda = fmax(s_lambda * 0.1, 1e-12);
+          } else {                    // reject: back to the last accepted point, more damping
+            s_lambda *= 10.0;
+          }
+          double d[5];
+          double pb1[3], pb2[3];
+          tangent_basis(s_prevt, pb1, pb2);
+          if (it < kLoInner && solve_damped(s_H, s_g, s_lambda, 5, d)) {
+            double dR[9], Rn[9];
+            so3_exp(d, dR);
+            mat3_mul(dR, s_prevR, Rn);
+            double tn[3];
+            for (int k = 0; k < 3; ++k) tn[k] = s_prevt[k] + d[3] * pb1[k] + d[4] * pb2[k];
+            const double nn = norm3(tn);
+            for (int k = 0; k < 9; ++k) s_R[k] = Rn[k];
+            for (int k = 0; k < 3; ++k) s_t[k] = tn[k] / nn;
+          } else {
+            for (int k = 0; k < 9; ++k) s_R[k] = s_prevR[k];
+            for (int k = 0; k < 3; ++k) s_t[k] = s_prevt[k];
+          }
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) {  // leave the round at the last accepted parameters
+        for (int k = 0; k < 9; ++k) s_R[k] = s_prevR[k];
+        for (int k = 0; k < 3; ++k) s_t[k] = s_prevt[k];
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) essential_from_rt(s_R, s_t, s_E);
+  __syncthreads();
+  // ---- final mask: Sampson^2 < thr^2 under the final E (what cv.findEssentialMat returns), then
+  // the cheirality filter that cv.recoverPose applies to the mask in place (pose_solver.py:57)
+  choose_pose();
+  double cnt[1] = {0.0};
+  for (int i = threadIdx.x; i < Nall; i += blockDim.x) {
+    unsigned char m = 0;
+    if (i < N) {
+      const float4 p = s_pts[i];
+      if (sampson_sq(s_E, p.x, p.y, p.z, p.w) < thr2 && cheirality_ok(s_R, s_t, p)) m = 1;
+    }
+    mask[n0 + i] = m;
+    cnt[0] += m;
+  }
+  block_sum_256<1>(cnt, sh_red);
+  const int n = static_cast<int>(cnt[0] + 0.5);
+  if (threadIdx.x == 0) s_cnt[1] = n;
+  __syncthreads();
+  if (s_cnt[1] == 0) { fail(); return; }
+  if (threadIdx.x < 9) { Rd[9 * pair + threadIdx.x] = s_R[threadIdx.x]; Rf[9 * pair + threadIdx.x] = static_cast<float>(s_R[threadIdx.x]); }
+  if (threadIdx.x < 3) { td[3 * pair + threadIdx.x] = s_t[threadIdx.x]; tf[3 * pair + threadIdx.x] = static_cast<float>(s_t[threadIdx.x]); }
+  if (threadIdx.x == 0) n_inl[pair] = s_cnt[1];
+}
+
+// ================================================================================================
+// scale from depth (EssentialMatrixMetricSolver, pose_solver.py:132-172)
+// ================================================================================================
+__device__ __forceinline__ void inverse_K_f32(const float* K, float* Ki) {
+  // np.linalg.inv on the float32 intrinsics; adjugate in double, rounded to float32
+  double A[9];
+  for (int k = 0; k < 9; ++k) A[k] = K[k];
+  const double d = det3(A);
+  const double inv[9] = {
+      (A[4] * A[8] - A[5] * A[7]) / d, (A[2] * A[7] - A[1] * A[8]) / d, (A[1] * A[5] - A[2] * A[4]) / d,
+      (A[5] * A[6] - A[3] * A[8]) / d, (A[0] * A[8] - A[2] * A[6]) / d, (A[2] * A[3] - A[0] * A[5]) / d,
+      (A[3] * A[7] - A[4] * A[6]) / d, (A[1] * A[6] - A[0] * A[7]) / d, (A[0] * A[4] - A[1] * A[3]) / d};
+  for (int k = 0; k < 9; ++k) Ki[k] = static_cast<float>(inv[k]);
+}
+
+__device__ __forceinline__ void backproject(const float* Ki, int u, int v, float depth, double* xyz) {
+  const double d = depth;
+  for (int r = 0; r < 3; ++r)
+    xyz[r] = d * (static_cast<double>(Ki[3 * r]) * u + static_cast<double>(Ki[3 * r + 1]) * v +
+                  static_cast<double>(Ki[3 * r + 2]));
+}
+
+__global__ void __launch_bounds__(1024) scale_consensus_kernel(
+    const float* __restrict__ kpts0, const float* __restrict__ kpts1, const int* __restrict__ offsets,
+    const float* __restrict__ K0s, const float* __restrict__ K1s, const unsigned char* __restrict__ mask,
+    const double* __restrict__ Rd, const double* __restrict__ td, const float* __restrict__ depth0,
+    const float* __restrict__ depth1, int H, int W, double scale_thr, int max_pts, float* __restrict__ R_out,
+    float* __restrict__ t_out, int* __restrict__ inl_out) {
+  extern __shared__ double s_scale[];
+  __shared__ int s_bc[32], s_bi[32];
+  __shared__ float s_Ki0[9], s_Ki1[9];
+  const int pair = blockIdx.x;
+  const int n0 = offsets[pair];
+  const int N = min(offsets[pair + 1] - n0, max_pts);
+  const double* R = Rd + 9 * pair;
+  const double* t = td + 3 * pair;
+  if (threadIdx.x == 0) {
+    inverse_K_f32(K0s + 9 * pair, s_Ki0);
+    inverse_K_f32(K1s + 9 * pair, s_Ki1);
+  }
+  __syncthreads();
+  const bool pose_ok = (R[0] == R[0]) && (t[0] == t[0]);
+  const float* d0 = depth0 + static_cast<size_t>(pair) * H * W;
+  const float* d1 = depth1 + static_cast<size_t>(pair) * H * W;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double s = NAN;
+    if (pose_ok && mask[n0 + i]) {
+      int u0 = static_cast<int>(kpts0[2 * (n0 + i)]), v0 = static_cast<int>(kpts0[2 * (n0 + i) + 1]);
+      int u1 = static_cast<int>(kpts1[2 * (n0 + i)]), v1 = static_cast<int>(kpts1[2 * (n0 + i) + 1]);
+      if (u0 >= 0 && u0 < W && v0 >= 0 && v0 < H && u1 >= 0 && u1 < W && v1 >= 0 && v1 < H) {
+        const float z0 = d0[v0 * W + u0], z1 = d1[v1 * W + u1];
+        if (z0 > 0.f && z1 > 0.f) {
+          double X0[3], X1[3], RX0[3];
+          backproject(s_Ki0, u0, v0, z0, X0);
+          backproject(s_Ki1, u1, v1, z1, X1);
+          mat3_vec(R, X0, RX0);
+          s = (X1[0] - RX0[0]) * t[0] + (X1[1] - RX0[1]) * t[1] + (X1[2] - RX0[2]) * t[2];
+        }
+      }
+    }
+    s_scale[i] = s;
+  }
+  __syncthreads();
+  // exhaustive consensus, strict '<', first best wins (pose_solver.py:160-166)
+  int bc = 0, bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double si = s_scale[i];
+    if (!(si == si)) continue;
+    int c = 0;
+    for (int j = 0; j < N; ++j) c += (fabs(s_scale[j] - si) < scale_thr) ? 1 : 0;
+    if (c > bc) { bc = c; bi = i; }
+  }
+  // block arg-max (count desc, index asc)
+  for (int o = 16; o > 0; o >>= 1) {
+    const int oc = __shfl_xor_sync(0xffffffffu, bc, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oc > bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_bc[threadIdx.x >> 5] = bc; s_bi[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 32; ++w)
+      if (s_bc[w] > bc || (s_bc[w] == bc && s_bi[w] < bi)) { bc = s_bc[w]; bi = s_bi[w]; }
+    if (bc > 0) {
+      const double s = s_scale[bi];
+      for (int k = 0; k < 9; ++k) R_out[9 * pair + k] = static_cast<float>(R[k]);
+      for (int k = 0; k < 3; ++k) t_out[3 * pair + k] = static_cast<float>(s * t[k]);
+      inl_out[pair] = bc;
+    } else {
+      for (int k = 0; k < 9; ++k) R_out[9 * pair + k] = NAN;
+      for (int k = 0; k < 3; ++k) t_out[3 * pair + k] = NAN;
+      inl_out[pair] = 0;
+    }
+  }
+}
+
+// ================================================================================================
+// PnP (pose_solver.py:184-235)
+// ================================================================================================
+__global__ void depth_min_kernel(const float* __restrict__ depth, long long hw, unsigned int* __restrict__ dmin) {
+  const int pair = blockIdx.y;
+  const float* d = depth + static_cast<size_t>(pair) * hw;
+  float m = 3.0e38f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < hw;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    m = fminf(m, d[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMin(dmin + pair, __float_as_uint(fmaxf(m, 0.f)));
+}
+
+// ordered compaction of the depth-valid correspondences of each pair + 3-D lift in camera 0
+__global__ void __launch_bounds__(1024) pnp_prepare_kernel(
+    const float* __restrict__ kpts0, const float* __restrict__ kpts1, const int* __restrict__ offsets,
+    const float* __restrict__ K0s, const float* __restrict__ depth0, int H, int W,
+    const unsigned int* __restrict__ dmin, int max_pts, double* __restrict__ Xw, float* __restrict__ uv,
+    int* __restrict__ vidx, int* __restrict__ nvalid) {
+  __shared__ int wsum[32];
+  __shared__ int base;
+  __shared__ float s_Ki[9];
+  const int pair = blockIdx.x;
+  const int n0 = offsets[pair];
+  const int N = min(offsets[pair + 1] - n0, max_pts);
+  if (threadIdx.x == 0) { base = 0; inverse_K_f32(K0s + 9 * pair, s_Ki); }
+  __syncthreads();
+  const float dm = __uint_as_float(dmin[pair]);
+  const float* d0 = depth0 + static_cast<size_t>(pair) * H * W;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < N; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    int flag = 0, u = 0, v = 0;
+    float z = 0.f;
+    if (i < N) {
+      u = static_cast<int>(kpts0[2 * (n0 + i)]);
+      v = static_cast<int>(kpts0[2 * (n0 + i) + 1]);
+      if (u >= 0 && u < W && v >= 0 && v < H) {
+        z = d0[v * W + u];
+        flag = z > dm ? 1 : 0;
+      }
+    }
+    int inc = flag;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int tt = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += tt;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      int w = wsum[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int tt = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += tt;
+      }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    if (flag) {
+      const int slot = n0 + base + (wid > 0 ? wsum[wid - 1] : 0) + inc - 1;
+      double X[3];
+      backproject(s_Ki, u, v, z, X);
+      Xw[3 * slot] = X[0]; Xw[3 * slot + 1] = X[1]; Xw[3 * slot + 2] = X[2];
+      uv[2 * slot] = kpts1[2 * (n0 + i)];
+      uv[2 * slot + 1] = kpts1[2 * (n0 + i) + 1];
+      vidx[slot] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) base += wsum[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) nvalid[pair] = base;
+}
+
+struct PnpPt { float X, Y, Z, u, v; };
+
+__global__ void __launch_bounds__(kHypPerBlock) pnp_hyp_kernel(
+    const double* __restrict__ Xw, const float* __restrict__ uv, const int* __restrict__ offsets,
+    const int* __restrict__ nvalid, const float* __restrict__ K1s, float reproj_thr, int num_hyp,
+    unsigned long long seed, HypResult* __restrict__ results) {
+  extern __shared__ float s_raw[];
+  __shared__ HypResult s_best[kHypPerBlock / 32];
+  const int pair = blockIdx.y;
+  const int n0 = offsets[pair];
+  const int N = nvalid[pair];
+  HypResult* out = results + static_cast<size_t>(pair) * gridDim.x + blockIdx.x;
+  if (N < 4) {
+    if (threadIdx.x == 0) { out->valid = 0; out->cost = 1e300; out->count = 0; }
+    return;
+  }
+  float* sX = s_raw;            // [N][3]
+  float* sU = s_raw + 3 * N;    // [N][2]
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    sX[3 * i] = static_cast<float>(Xw[3 * (n0 + i)]);
+    sX[3 * i + 1] = static_cast<float>(Xw[3 * (n0 + i) + 1]);
+    sX[3 * i + 2] = static_cast<float>(Xw[3 * (n0 + i) + 2]);
+    sU[2 * i] = uv[2 * (n0 + i)];
+    sU[2 * i + 1] = uv[2 * (n0 + i) + 1];
+  }
+  __syncthreads();
+  const float* K1 = K1s + 9 * pair;
+  const float fx = K1[0], fy = K1[4], cx = K1[2], cy = K1[5];
+  const float thr2 = reproj_thr * reproj_thr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = blockIdx.x * kHypPerBlock + threadIdx.x;
+  double Rm[9], tm[3];
+  int have = 0;
+  if (h < num_hyp) {
+    unsigned long long st = seed ^ (0xA24BAED4963EE407ull * (static_cast<unsigned long long>(pair) + 1)) ^
+                            (0x9E3779B97F4A7C15ull * (static_cast<unsigned long long>(h) + 1));
+    int idx[4];
+    sample_distinct<4>(st, N, idx);
+    double X[3][3], f[3][3];
+    for (int k = 0; k < 3; ++k) {
+      for (int c = 0; c < 3; ++c) X[k][c] = Xw[3 * (n0 + idx[k]) + c];
+      const double bx = (static_cast<double>(uv[2 * (n0 + idx[k])]) - cx) / fx;
+      const double by = (static_cast<double>(uv[2 * (n0 + idx[k]) + 1]) - cy) / fy;
+      const double nn = 1.0 / sqrt(bx * bx + by * by + 1.0);
+      f[k][0] = bx * nn; f[k][1] = by * nn; f[k][2] = nn;
+    }
+    double Rs[4][9], ts[4][3];
+    const int ns = p3p(X, f, Rs, ts);
+    // disambiguate with the 4th point (what cv's P3P does with 4 input points)
+    double best = 1e300;
+    const double X4[3] = {Xw[3 * (n0 + idx[3])], Xw[3 * (n0 + idx[3]) + 1], Xw[3 * (n0 + idx[3]) + 2]};
+    const double u4 = uv[2 * (n0 + idx[3])], v4 = uv[2 * (n0 + idx[3]) + 1];
+    for (int s = 0; s < ns; ++s) {
+      double Xc[3];
+      mat3_vec(Rs[s], X4, Xc);
+      for (int c = 0; c < 3; ++c) Xc[c] += ts[s][c];
+      if (!(Xc[2] > 1e-9)) continue;
+      const double du = fx * Xc[0] / Xc[2] + cx - u4, dv = fy * Xc[1] / Xc[2] + cy - v4;
+      const double e = du * du + dv * dv;
+      if (e < best) {
+        best = e;
+        have = 1;
+        for (int c = 0; c < 9; ++c) Rm[c] = Rs[s][c];
+        for (int c = 0; c < 3; ++c) tm[c] = ts[s][c];
+      }
+    }
+  }
+  int best_cnt = -1, best_src = -1;
+  for (int src = 0; src < 32; ++src) {
+    if (!__shfl_sync(0xffffffffu, have, src)) continue;
+    float R[9], t[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = __shfl_sync(0xffffffffu, static_cast<float>(Rm[k]), src);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t[k] = __shfl_sync(0xffffffffu, static_cast<float>(tm[k]), src);
+    int inl = 0;
+    for (int i0 = 0; i0 < N; i0 += 32) {
+      const int i = i0 + lane;
+      bool ok = false;
+      if (i < N) {
+        const float X = sX[3 * i], Y = sX[3 * i + 1], Z = sX[3 * i + 2];
+        const float xc = fmaf(R[0], X, fmaf(R[1], Y, fmaf(R[2], Z, t[0])));
+        const float yc = fmaf(R[3], X, fmaf(R[4], Y, fmaf(R[5], Z, t[1])));
+        const float zc = fmaf(R[6], X, fmaf(R[7], Y, fmaf(R[8], Z, t[2])));
+        if (zc > 1e-6f) {
+          const float iz = 1.f / zc;
+          const float du = fmaf(fx * xc, iz, cx) - sU[2 * i], dv = fmaf(fy * yc, iz, cy) - sU[2 * i + 1];
+          ok = fmaf(du, du, dv * dv) < thr2;
+        }
+      }
+      inl += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    if (inl > best_cnt) { best_cnt = inl; best_src = src; }
+  }
+  if (lane == 0) {
+    s_best[warp].valid = best_src >= 0 ? 1 : 0;
+    s_best[warp].cost = best_src >= 0 ? -static_cast<double>(best_cnt) : 1e300;
+    s_best[warp].count = best_cnt;
+  }
+  if (best_src >= 0 && lane == best_src) {
+    for (int k = 0; k < 9; ++k) s_best[warp].model[k] = Rm[k];
+    for (int k = 0; k < 3; ++k) s_best[warp].model[9 + k] = tm[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int bw = 0;
+    for (int w = 1; w < kHypPerBlock / 32; ++w)
+      if (s_best[w].cost < s_best[bw].cost) bw = w;
+    *out = s_best[bw];
+  }
+}
+
+constexpr int kPnpIters = 20;
+
+__global__ void __launch_bounds__(256) pnp_final_kernel(
+    const double* __restrict__ Xw, const float* __restrict__ uv, const int* __restrict__ vidx,
+    const int* __restrict__ offsets, const int* __restrict__ nvalid, const float* __restrict__ K1s,
+    float reproj_thr, int blocks_per_pair, const HypResult* __restrict__ results, float* __restrict__ Rf,
+    float* __restrict__ tf, int* __restrict__ n_inl, unsigned char* __restrict__ mask) {
+  __shared__ double sh_red[8 * 28];
+  __shared__ double s_R[9], s_t[3], s_R0[9], s_t0[3], s_prevR[9], s_prevt[3], s_H[36], s_g[6];
+  __shared__ double s_prev_cost, s_lambda;
+  __shared__ int s_flag, s_n;
+  const int pair = blockIdx.x;
+  const int n0 = offsets[pair];
+  const int Nall = offsets[pair + 1] - n0;
+  const int N = nvalid[pair];
+  for (int i = threadIdx.x; i < Nall; i += blockDim.x) mask[n0 + i] = 0;
+  auto fail = [&]() {
+    if (threadIdx.x < 9) Rf[9 * pair + threadIdx.x] = NAN;
+    if (threadIdx.x < 3) tf[3 * pair + threadIdx.x] = NAN;
+    if (threadIdx.x == 0) n_inl[pair] = 0;
+  };
+  if (threadIdx.x == 0) {
+    int b = -1;
+    if (N >= 4) {
+      const HypResult* r = results + static_cast<size_t>(pair) * blocks_per_pair;
+      for (int k = 0; k < blocks_per_pair; ++k)
+        if (r[k].valid && (b < 0 || r[k].cost < r[b].cost)) b = k;
+      if (b >= 0) {
+        for (int k = 0; k < 9; ++k) { s_R[k] = r[b].model[k]; s_R0[k] = s_R[k]; }
+        for (int k = 0; k < 3; ++k) { s_t[k] = r[b].model[9 + k]; s_t0[k] = s_t[k]; }
+      }
+    }
+    s_flag = b;
+  }
+  __syncthreads();
+  if (s_flag < 0) { fail(); return; }
+  const float* K1 = K1s + 9 * pair;
+  const double fx = K1[0], fy = K1[4], cx = K1[2], cy = K1[5];
+  const double thr2 = static_cast<double>(reproj_thr) * reproj_thr;
+  __syncthreads();
+  // inlier set of the RANSAC model (fixed during the refinement, like cv.solvePnPRansac's)
+  auto is_inlier = [&](int i) {
+    const double* X = Xw + 3 * (n0 + i);
+    double Xc[3];
+    mat3_vec(s_R0, X, Xc);
+    for (int c = 0; c < 3; ++c) Xc[c] += s_t0[c];
+    if (!(Xc[2] > 1e-9)) return false;
+    const double du = fx * Xc[0] / Xc[2] + cx - uv[2 * (n0 + i)], dv = fy * Xc[1] / Xc[2] + cy - uv[2 * (n0 + i) + 1];
+    return du * du + dv * dv < thr2;
+  };
+  double cnt[1] = {0.0};
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    if (is_inlier(i)) { cnt[0] += 1.0; mask[n0 + vidx[n0 + i]] = 1; }
+  block_sum_256<1>(cnt, sh_red);
+  if (threadIdx.x == 0) { s_n = static_cast<int>(cnt[0] + 0.5); s_lambda = 1e-6; s_prev_cost = 1e300; }
+  __syncthreads();
+  const int n_in = s_n;
+  if (n_in < 4) { fail(); for (int i = threadIdx.x; i < Nall; i += blockDim.x) mask[n0 + i] = 0; return; }
+  if (n_in >= 6) {  // LM refinement on the inliers (pose_solver.py:216-220)
+    for (int it = 0; it <= kPnpIters; ++it) {
+      double R[9], t[3];
+      for (int k = 0; k < 9; ++k) R[k] = s_R[k];
+      for (int k = 0; k < 3; ++k) t[k] = s_t[k];
+      double acc[28];
+      for (int k = 0; k < 28; ++k) acc[k] = 0.0;
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        if (!is_inlier(i)) continue;
+        const double* X = Xw + 3 * (n0 + i);
+        double RX[3], Xc[3];
+        mat3_vec(R, X, RX);
+        for (int c = 0; c < 3; ++c) Xc[c] = RX[c] + t[c];
+        const double iz = 1.0 / Xc[2];
+        const double ru = fx * Xc[0] * iz + cx - uv[2 * (n0 + i)];
+        const double rv = fy * Xc[1] * iz + cy - uv[2 * (n0 + i) + 1];
+        // d(u,v)/dXc
+        const double a0 = fx * iz, a2 = -fx * Xc[0] * iz * iz, b1 = fy * iz, b2 = -fy * Xc[1] * iz * iz;
+        // dXc/d(omega) = -[RX]x ; dXc/dt = I
+        double Ju[6], Jv[6];
+        Ju[0] = a2 * RX[1];                 // a . (e0 x RX) = a0*0 + 0 + a2*( RX[1]) ... see below
+        Ju[1] = a0 * RX[2] - a2 * RX[0];
+        Ju[2] = -a0 * RX[1];
+        Jv[0] = -b1 * RX[2] + b2 * RX[1];
+        Jv[1] = -b2 * RX[0];
+        Jv[2] = b1 * RX[0];
+        Ju[3] = a0; Ju[4] = 0.0; Ju[5] = a2;
+        Jv[3] = 0.0; Jv[4] = b1; Jv[5] = b2;
+        int q = 0;
+        for (int a = 0; a < 6; ++a)
+          for (int b = a; b < 6; ++b) acc[q++] += Ju[a] * Ju[b] + Jv[a] * Jv[b];
+        for (int a = 0; a < 6; ++a) acc[21 + a] += Ju[a] * ru + Jv[a] * rv;
+        acc[27] += ru * ru + rv * rv;
+      }
+      block_sum_256<28>(acc, sh_red);
+      if (threadIdx.x == 0) {
+        const double cost = acc[27];
+        if (cost <= s_prev_cost) {
+          s_prev_cost = cost;
+          for (int k = 0; k < 9; ++k) s_prevR[k] = s_R[k];
+          for (int k = 0; k < 3; ++k) s_prevt[k] = s_t[k];
+          int q = 0;
+          for (int a = 0; a < 6; ++a)
+            for (int b = a; b < 6; ++b) { s_H[a * 6 + b] = acc[q]; s_H[b * 6 + a] = acc[q]; ++q; }
+          for (int a = 0; a < 6; ++a) s_g[a] = acc[21 + a];
+          s_lambda = fmax(s_lambda * 0.1, 1e-12);
+        } else {
+          s_lambda *= 10.0;
+        }
+        double d[6];
+        if (it < kPnpIters && solve_damped(s_H, s_g, s_lambda, 6, d)) {
+          double dR[9], Rn[9];
+          so3_exp(d, dR);
+          mat3_mul(dR, s_prevR, Rn);
+          for (int k = 0; k < 9; ++k) s_R[k] = Rn[k];
+          for (int k = 0; k < 3; ++k) s_t[k] = s_prevt[k] + d[3 + k];
+        } else {
+          for (int k = 0; k < 9; ++k) s_R[k] = s_prevR[k];
+          for (int k = 0; k < 3; ++k) s_t[k] = s_prevt[k];
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < 9; ++k) s_R[k] = s_prevR[k];
+      for (int k = 0; k < 3; ++k) s_t[k] = s_prevt[k];
+    }
+    __syncthreads();
+  }
+  const double tn = sqrt(s_t[0] * s_t[0] + s_t[1] * s_t[1] + s_t[2] * s_t[2]);
+  if (!(tn <= 1000.0)) {  // pose_solver.py:223-225
+    fail();
+    for (int i = threadIdx.x; i < Nall; i += blockDim.x) mask[n0 + i] = 0;
+    return;
+  }
+  if (threadIdx.x < 9) Rf[9 * pair + threadIdx.x] = static_cast<float>(s_R[threadIdx.x]);
+  if (threadIdx.x < 3) tf[3 * pair + threadIdx.x] = static_cast<float>(s_t[threadIdx.x]);
+  if (threadIdx.x == 0) n_inl[pair] = n_in;
+}
+
+}  // namespace
+
+// ================================================================================================
+// host side
+// ================================================================================================
+struct PoseSolver {
+  int max_pairs, max_pts, max_hyp;
+  HypResult* results = nullptr;
+  double *Rd = nullptr, *td = nullptr, *Xw = nullptr;
+  float* uv = nullptr;
+  int *vidx = nullptr, *nvalid = nullptr;
+  unsigned int* dmin = nullptr;
+  size_t total_pts;
+};
+
+int pose_solver_create(int max_pairs, int max_pts, int max_hyp, PoseSolver** out) {
+  if (max_pairs < 1 || max_pts < 8 || max_hyp < kHypPerBlock) return MFR_ERR_ARG;
+  if (max_pts > 8192) max_pts = 8192;  // correspondences live in shared memory (16 B each)
+  auto* s = new PoseSolver();
+  s->max_pairs = max_pairs; s->max_pts = max_pts; s->max_hyp = max_hyp;
+  s->total_pts = static_cast<size_t>(max_pairs) * max_pts;
+  const int blocks = (max_hyp + kHypPerBlock - 1) / kHypPerBlock;
+  bool ok = true;
+  ok &= cudaMalloc(&s->results, sizeof(HypResult) * max_pairs * blocks) == cudaSuccess;
+  ok &= cudaMalloc(&s->Rd, sizeof(double) * 9 * max_pairs) == cudaSuccess;
+  ok &= cudaMalloc(&s->td, sizeof(double) * 3 * max_pairs) == cudaSuccess;
+  ok &= cudaMalloc(&s->Xw, sizeof(double) * 3 * s->total_pts) == cudaSuccess;
+  ok &= cudaMalloc(&s->uv, sizeof(float) * 2 * s->total_pts) == cudaSuccess;
+  ok &= cudaMalloc(&s->vidx, sizeof(int) * s->total_pts) == cudaSuccess;
+  ok &= cudaMalloc(&s->nvalid, sizeof(int) * max_pairs) == cudaSuccess;
+  ok &= cudaMalloc(&s->dmin, sizeof(unsigned int) * max_pairs) == cudaSuccess;
+  if (!ok) { pose_solver_destroy(s); return MFR_ERR_CUDA; }
+  static bool attrs = false;
+  if (!attrs) {
+    cudaFuncSetAttribute(emat_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
+    cudaFuncSetAttribute(emat_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
+    cudaFuncSetAttribute(scale_consensus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
+    cudaFuncSetAttribute(pnp_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 20);
+    attrs = true;
+  }
+  *out = s;
+  return MFR_OK;
+}
+
+void pose_solver_destroy(PoseSolver* s) {
+  if (!s) return;
+  cudaFree(s->results); cudaFree(s->Rd); cudaFree(s->td); cudaFree(s->Xw); cudaFree(s->uv);
+  cudaFree(s->vidx); cudaFree(s->nvalid); cudaFree(s->dmin);
+  delete s;
+}
+
+double* pose_solver_Rd(PoseSolver* s) { return s->Rd; }
+double* pose_solver_td(PoseSolver* s) { return s->td; }
+
+int emat_ransac(PoseSolver* s, const float* kpts0, const float* kpts1, const int* offsets, int P,
+                const float* K0, const float* K1, float pix_thr, int num_hyp, unsigned long long seed,
+                int lo_enabled, float* R, float* t, int* n_inl, unsigned char* mask, cudaStream_t st) {
+  if (P < 1 || P > s->max_pairs || num_hyp < 1) return MFR_ERR_ARG;
+  num_hyp = std::min(num_hyp, s->max_hyp);
+  const int blocks = (num_hyp + kHypPerBlock - 1) / kHypPerBlock;
+  const size_t smem = static_cast<size_t>(s->max_pts) * 16;
+  emat_hyp_kernel<<<dim3(blocks, P), kHypPerBlock, smem, st>>>(kpts0, kpts1, offsets, K0, K1, pix_thr, num_hyp,
+                                                               seed, s->max_pts, s->results);
+  emat_final_kernel<<<P, 256, smem, st>>>(kpts0, kpts1, offsets, K0, K1, pix_thr, blocks, s->max_pts,
+                                          s->results, s->Rd, s->td, R, t, n_inl, mask, lo_enabled);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int scale_from_depth(PoseSolver* s, const float* kpts0, const float* kpts1, const int* offsets, int P,
+                     const float* K0, const float* K1, const unsigned char* mask, const double* Rd,
+                     const double* td, const float* depth0, const float* depth1, int H, int W,
+                     float scale_thr, float* R_out, float* t_out, int* inliers, cudaStream_t st) {
+  if (P < 1 || P > s->max_pairs) return MFR_ERR_ARG;
+  const double* Rp = Rd ? Rd : s->Rd;
+  const double* tp = td ? td : s->td;
+  scale_consensus_kernel<<<P, 1024, static_cast<size_t>(s->max_pts) * 8, st>>>(
+      kpts0, kpts1, offsets, K0, K1, mask, Rp, tp, depth0, depth1, H, W, static_cast<double>(scale_thr),
+      s->max_pts, R_out, t_out, inliers);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int pnp_ransac(PoseSolver* s, const float* kpts0, const float* kpts1, const int* offsets, int P,
+               const float* K0, const float* K1, const float* depth0, int H, int W, int num_hyp,
+               float reproj_thr, unsigned long long seed, float* R, float* t, int* n_inl,
+               unsigned char* mask, cudaStream_t st) {
+  if (P < 1 || P > s->max_pairs || num_hyp < 1) return MFR_ERR_ARG;
+  num_hyp = std::min(num_hyp, s->max_hyp);
+  const int blocks = (num_hyp + kHypPerBlock - 1) / kHypPerBlock;
+  MFR_CUDA_CHECK(cudaMemsetAsync(s->dmin, 0x7f, sizeof(unsigned int) * P, st));
+  depth_min_kernel<<<dim3(64, P), 256, 0, st>>>(depth0, static_cast<long long>(H) * W, s->dmin);
+  pnp_prepare_kernel<<<P, 1024, 0, st>>>(kpts0, kpts1, offsets, K0, depth0, H, W, s->dmin, s->max_pts, s->Xw,
+                                         s->uv, s->vidx, s->nvalid);
+  pnp_hyp_kernel<<<dim3(blocks, P), kHypPerBlock, static_cast<size_t>(s->max_pts) * 20, st>>>(
+      s->Xw, s->uv, offsets, s->nvalid, K1, reproj_thr, num_hyp, seed, s->results);
+  pnp_final_kernel<<<P, 256, 0, st>>>(s->Xw, s->uv, s->vidx, offsets, s->nvalid, K1, reproj_thr, blocks,
+                                      s->results, R, t, n_inl, mask);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+}  // namespace mfr

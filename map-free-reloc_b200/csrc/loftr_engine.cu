@@ -1,0 +1,462 @@
+// LoFTR matcher engine: the whole coarse-to-fine network as a static launch list of hand-written
+// sm_100a kernels (tcgen05 implicit-GEMM convs / linears + SIMT glue), replayed through a CUDA graph.
+// Mirrors etc/feature_matching_baselines/LoFTR/src/loftr/loftr.py:29-75 of the reference
+// (backbone -> pos-enc -> coarse transformer -> dual-softmax mutual-NN -> fine windows -> fine
+// transformer -> expectation), for B image pairs per call, channel-last fp32 activations.
+#include "loftr_engine.cuh"
+
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conv_gemm.cuh"
+#include "loftr_ops.cuh"
+
+namespace mfr {
+
+struct WeightSpec {
+  std::string name;
+  size_t numel;
+  size_t offset;  // floats, 64-float aligned
+};
+
+struct DebugTensor {
+  float* ptr;
+  long long numel;
+};
+
+struct LoftrEngine {
+  int B, H, W, NI;
+  int H2, W2, H4, W4, H8, W8, L, Mcap;
+  float thr, temperature;
+  int border;
+  int splits_kv = 16, splits_col = 32;
+
+  std::vector<WeightSpec> specs;
+  std::map<std::string, size_t> spec_index;
+  float* wblob = nullptr;
+  size_t wtotal = 0;
+  bool weights_loaded = false;
+
+  std::vector<void*> allocs;
+  std::map<std::string, DebugTensor> dbg;
+  std::vector<std::function<int(cudaStream_t)>> steps;
+  // buffers
+  float* img = nullptr;
+  float *a0, *a1, *a2, *b0, *b1, *b2, *c0, *c1, *c2, *fc, *p4a, *p4b, *p4c, *p2a, *p2b;
+  float *tok, *qkv, *msg, *mrg, *h1, *h2, *kvp, *kv, *S;
+  CoarseMatchBuffers cm;
+  float *cin, *cproj, *win, *ftok, *fqkv, *fmsg, *fmrg, *fh1, *fh2, *mk1f, *expec;
+  // graph
+  cudaGraphExec_t graph_exec = nullptr;
+  bool use_graph = true;
+  int build_rc = MFR_OK;
+
+  float* W_(const std::string& n) {
+    auto it = spec_index.find(n);
+    if (it == spec_index.end()) {
+      fprintf(stderr, "[mfr_b200] unknown weight %s\n", n.c_str());
+      build_rc = MFR_ERR_ARG;
+      return wblob;
+    }
+    return wblob + specs[it->second].offset;
+  }
+  void add_spec(const std::string& n, size_t numel) {
+    WeightSpec s{n, numel, wtotal};
+    spec_index[n] = specs.size();
+    specs.push_back(s);
+    wtotal += (numel + 63) / 64 * 64;
+  }
+  template <typename T>
+  T* alloc(size_t n, const char* name = nullptr) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) {
+      fprintf(stderr, "[mfr_b200] cudaMalloc of %zu bytes failed (%s)\n", n * sizeof(T), name ? name : "");
+      build_rc = MFR_ERR_CUDA;
+      return nullptr;
+    }
+    cudaMemset(p, 0, n * sizeof(T));
+    allocs.push_back(p);
+    if (name) dbg[name] = DebugTensor{reinterpret_cast<float*>(p), static_cast<long long>(n)};
+    return reinterpret_cast<T*>(p);
+  }
+
+  // ---- step builders -----------------------------------------------------------------------
+  void conv(const std::string& wname, const float* x, int N, int Hh, int Ww, int Cin, long long ldx,
+            int Cout, int R, int stride, bool bias, const float* residual, int act, float* out,
+            long long ldo, int act_cols = 0, const int* dyn_w = nullptr, const float* w_override = nullptr,
+            const float* bias_override = nullptr) {
+    ConvGemmDesc d{};
+    d.x = x; d.N = N; d.H = Hh; d.W = Ww; d.Cin = Cin; d.ldx = ldx;
+    d.w = w_override ? w_override : W_(wname + ".w");
+    d.Cout = Cout; d.R = R; d.S = R; d.stride = stride; d.pad = R / 2;
+    d.b_batched = 0; d.ldw = 0; d.act_cols = act_cols; d.dyn_w = dyn_w;
+    d.bias = bias ? (bias_override ? bias_override : W_(wname + ".b")) : nullptr;
+    d.residual = residual; d.ldr = ldo;
+    d.act = act; d.alpha = 1.f; d.out = out; d.ldo = ldo;
+    ConvGemmParams p;
+    int rc = conv_gemm_build(d, &p);
+    if (rc != MFR_OK) { build_rc = rc; return; }
+    steps.push_back([p](cudaStream_t st) { return conv_gemm_launch(p, st); });
+  }
+
+  void specs_backbone() {
+    add_spec("stem.w", 128 * 49);
+    add_spec("stem.b", 128);
+    auto cv = [&](const std::string& n, int cin, int cout, int r, bool bias) {
+      add_spec(n + ".w", static_cast<size_t>(cout) * r * r * cin);
+      if (bias) add_spec(n + ".b", cout);
+    };
+    int cin = 128;
+    const int dims[3] = {128, 196, 256};
+    for (int li = 0; li < 3; ++li) {
+      const int c = dims[li];
+      for (int bi = 0; bi < 2; ++bi) {
+        const std::string p = "layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+        cv(p + ".conv1", bi == 0 ? cin : c, c, 3, true);
+        cv(p + ".conv2", c, c, 3, true);
+        if (bi == 0 && li > 0) cv(p + ".down", cin, c, 1, true);
+      }
+      cin = c;
+    }
+    cv("layer3_outconv", 256, 256, 1, false);
+    cv("layer2_outconv", 196, 256, 1, false);
+    cv("layer2_outconv2.0", 256, 256, 3, true);
+    cv("layer2_outconv2.3", 256, 196, 3, false);
+    cv("layer1_outconv", 128, 196, 1, false);
+    cv("layer1_outconv2.0", 196, 196, 3, true);
+    cv("layer1_outconv2.3", 196, 128, 3, false);
+    add_spec("pos_enc", static_cast<size_t>(L) * 256);
+  }
+  void specs_transformer(const std::string& pre, int C, int layers) {
+    for (int i = 0; i < layers; ++i) {
+      const std::string p = pre + "." + std::to_string(i);
+      add_spec(p + ".qkv.w", static_cast<size_t>(3) * C * C);
+      add_spec(p + ".merge.w", static_cast<size_t>(C) * C);
+      add_spec(p + ".mlp0.w", static_cast<size_t>(4) * C * C);
+      add_spec(p + ".mlp2.w", static_cast<size_t>(2) * C * C);
+      add_spec(p + ".norm1.g", C);
+      add_spec(p + ".norm1.b", C);
+      add_spec(p + ".norm2.g", C);
+      add_spec(p + ".norm2.b", C);
+    }
+  }
+
+  // One LoFTREncoderLayer (transformer.py:35-58) on `n` "images" of `rows` tokens each.
+  //   x, src : token buffers with row stride 2C (cols [0,C) = features, [C,2C) = message scratch)
+  //   q/k/v live in `qkv_x` / `qkv_s` (row stride 3C) at the rows of the x / src images.
+  void encoder_layer(const std::string& p, int C, float* x, float* src, float* qkv_x, float* qkv_s,
+                     float* msg_x, float* mrg_x, float* h1_x, float* h2_x, int n, int rows,
+                     const int* dyn_rows, const int* dyn_items, bool windows) {
+    float* wq = W_(p + ".qkv.w");
+    const long long ld2 = 2 * C, ld3 = 3 * C;
+    if (x == src) {
+      conv("", x, n, 1, rows, C, ld2, 3 * C, 1, 1, false, nullptr, ACT_ELU1, qkv_x, ld3, 2 * C, dyn_rows, wq);
+    } else {
+      conv("", x, n, 1, rows, C, ld2, C, 1, 1, false, nullptr, ACT_ELU1, qkv_x, ld3, C, dyn_rows, wq);
+      conv("", src, n, 1, rows, C, ld2, 2 * C, 1, 1, false, nullptr, ACT_ELU1, qkv_s + C, ld3, C, dyn_rows,
+           wq + static_cast<size_t>(C) * C);
+    }
+    if (!windows) {
+      float* kvp_ = kvp; float* kv_ = kv;
+      const int Lr = rows, sk = splits_kv;
+      steps.push_back([=](cudaStream_t st) {
+        return linear_attention_long(qkv_x, ld3, qkv_s + C, ld3, qkv_s + 2 * C, ld3, msg_x, C, kvp_, kv_, n,
+                                     Lr, Lr, 8, 32, sk, st);
+      });
+    } else {
+      const int items_cap = rows / 25;
+      for (int side = 0; side < n; ++side) {
+        const size_t off3 = static_cast<size_t>(side) * rows * ld3;
+        const size_t off1 = static_cast<size_t>(side) * rows * C;
+        steps.push_back([=](cudaStream_t st) {
+          return linear_attention_windows(qkv_x + off3, ld3, qkv_s + off3 + C, ld3, qkv_s + off3 + 2 * C, ld3,
+                                          msg_x + off1, C, dyn_items, items_cap, 25, st);
+        });
+      }
+    }
+    conv(p + ".merge", msg_x, n, 1, rows, C, C, C, 1, 1, false, nullptr, ACT_NONE, mrg_x, C, 0, dyn_rows);
+    const float *g1 = W_(p + ".norm1.g"), *b1 = W_(p + ".norm1.b");
+    const float *g2 = W_(p + ".norm2.g"), *b2 = W_(p + ".norm2.b");
+    const long long tot = static_cast<long long>(n) * rows;
+    if (dyn_rows == nullptr) {
+      steps.push_back([=](cudaStream_t st) {
+        return layernorm_rows(mrg_x, C, g1, b1, nullptr, 0, x + C, ld2, tot, C, nullptr, st);
+      });
+    } else {
+      for (int side = 0; side < n; ++side) {
+        const size_t o1 = static_cast<size_t>(side) * rows * C, o2 = static_cast<size_t>(side) * rows * ld2;
+        steps.push_back([=](cudaStream_t st) {
+          return layernorm_rows(mrg_x + o1, C, g1, b1, nullptr, 0, x + o2 + C, ld2, rows, C, dyn_rows, st);
+        });
+      }
+    }
+    conv(p + ".mlp0", x, n, 1, rows, 2 * C, ld2, 2 * C, 1, 1, false, nullptr, ACT_RELU, h1_x, ld2, 0, dyn_rows);
+    conv(p + ".mlp2", h1_x, n, 1, rows, 2 * C, ld2, C, 1, 1, false, nullptr, ACT_NONE, h2_x, C, 0, dyn_rows);
+    if (dyn_rows == nullptr) {
+      steps.push_back([=](cudaStream_t st) {
+        return layernorm_rows(h2_x, C, g2, b2, x, ld2, x, ld2, tot, C, nullptr, st);
+      });
+    } else {
+      for (int side = 0; side < n; ++side) {
+        const size_t o1 = static_cast<size_t>(side) * rows * C, o2 = static_cast<size_t>(side) * rows * ld2;
+        steps.push_back([=](cudaStream_t st) {
+          return layernorm_rows(h2_x + o1, C, g2, b2, x + o2, ld2, x + o2, ld2, rows, C, dyn_rows, st);
+        });
+      }
+    }
+  }
+
+  int build() {
+    NI = 2 * B;
+    H2 = H / 2; W2 = W / 2; H4 = H / 4; W4 = W / 4; H8 = H / 8; W8 = W / 8;
+    L = H8 * W8;
+    Mcap = B * L;
+    specs_backbone();
+    specs_transformer("coarse", 256, 8);
+    add_spec("fine.down_proj.w", 128 * 256);
+    add_spec("fine.down_proj.b", 128);
+    add_spec("fine.merge_feat.w", 128 * 256);
+    add_spec("fine.merge_feat.b", 128);
+    specs_transformer("fine", 128, 2);
+    wblob = alloc<float>(wtotal, "weights");
+
+    const size_t px2 = static_cast<size_t>(NI) * H2 * W2, px4 = static_cast<size_t>(NI) * H4 * W4,
+                 px8 = static_cast<size_t>(NI) * H8 * W8;
+    img = alloc<float>(static_cast<size_t>(NI) * H * W, "img");
+    a0 = alloc<float>(px2 * 128, "a0"); a1 = alloc<float>(px2 * 128, "a1"); a2 = alloc<float>(px2 * 128, "a2");
+    b0 = alloc<float>(px4 * 196, "b0"); b1 = alloc<float>(px4 * 196, "b1"); b2 = alloc<float>(px4 * 196, "b2");
+    c0 = alloc<float>(px8 * 256, "c0"); c1 = alloc<float>(px8 * 256, "c1"); c2 = alloc<float>(px8 * 256, "c2");
+    fc = alloc<float>(px8 * 256, "feat_c_backbone");
+    p4a = alloc<float>(px4 * 256, "p4a"); p4b = alloc<float>(px4 * 256, "p4b"); p4c = alloc<float>(px4 * 196, "p4c");
+    p2a = alloc<float>(px2 * 196, "p2a"); p2b = alloc<float>(px2 * 196, "p2b");
+    tok = alloc<float>(px8 * 512, "tok");
+    qkv = alloc<float>(px8 * 768, "qkv"); msg = alloc<float>(px8 * 256, "msg"); mrg = alloc<float>(px8 * 256, "mrg");
+    h1 = alloc<float>(px8 * 512, "h1"); h2 = alloc<float>(px8 * 256, "h2");
+    kvp = alloc<float>(static_cast<size_t>(NI) * 8 * splits_kv * 1056, "kvp");
+    kv = alloc<float>(static_cast<size_t>(NI) * 8 * 1056, "kv");
+    S = alloc<float>(static_cast<size_t>(B) * L * L, "sim");
+    const size_t BL = static_cast<size_t>(B) * L;
+    cm.row_max = alloc<float>(BL); cm.row_rsum = alloc<float>(BL);
+    cm.col_max = alloc<float>(BL); cm.col_rsum = alloc<float>(BL);
+    cm.col_part = alloc<float>(BL * splits_col * 2);
+    cm.rconf_max = alloc<float>(BL); cm.rconf_arg = alloc<int>(BL); cm.rconf_ties = alloc<int>(BL);
+    cm.cconf_max = alloc<float>(BL); cm.jsel = alloc<int>(BL);
+    cm.m_total = alloc<int>(4); cm.m_offsets = alloc<int>(B + 1);
+    cm.b_ids = alloc<int>(BL); cm.i_ids = alloc<int>(BL); cm.j_ids = alloc<int>(BL);
+    cm.mconf = alloc<float>(BL, "mconf"); cm.mkpts0_c = alloc<float>(BL * 2, "mkpts0_c");
+    cm.mkpts1_c = alloc<float>(BL * 2, "mkpts1_c");
+    const size_t frows = static_cast<size_t>(2) * Mcap * 25;
+    cin = alloc<float>(static_cast<size_t>(2) * Mcap * 256, "fine_cin");
+    cproj = alloc<float>(static_cast<size_t>(2) * Mcap * 128, "fine_cproj");
+    win = alloc<float>(frows * 256, "fine_win");
+    ftok = alloc<float>(frows * 256, "fine_tok");
+    fqkv = alloc<float>(frows * 384, "fine_qkv"); fmsg = alloc<float>(frows * 128); fmrg = alloc<float>(frows * 128);
+    fh1 = alloc<float>(frows * 256); fh2 = alloc<float>(frows * 128);
+    mk1f = alloc<float>(BL * 2, "mkpts1_f"); expec = alloc<float>(BL * 3, "expec_f");
+    if (build_rc != MFR_OK) return build_rc;
+
+    // ---------------------------------------------------------------- backbone (resnet_fpn.py:100-119)
+    {
+      float *img_ = img, *a0_ = a0; float* ws = W_("stem.w"); float* bs = W_("stem.b");
+      const int NI_ = NI, H_ = H, W_w = W;
+      steps.push_back([=](cudaStream_t st) { return stem_conv7x7(img_, ws, bs, a0_, NI_, H_, W_w, st); });
+    }
+    conv("layer1.0.conv1", a0, NI, H2, W2, 128, 128, 128, 3, 1, true, nullptr, ACT_RELU, a1, 128);
+    conv("layer1.0.conv2", a1, NI, H2, W2, 128, 128, 128, 3, 1, true, a0, ACT_RELU, a2, 128);
+    conv("layer1.1.conv1", a2, NI, H2, W2, 128, 128, 128, 3, 1, true, nullptr, ACT_RELU, a1, 128);
+    conv("layer1.1.conv2", a1, NI, H2, W2, 128, 128, 128, 3, 1, true, a2, ACT_RELU, a0, 128);  // x1 = a0
+    conv("layer2.0.conv1", a0, NI, H2, W2, 128, 128, 196, 3, 2, true, nullptr, ACT_RELU, b1, 196);
+    conv("layer2.0.down", a0, NI, H2, W2, 128, 128, 196, 1, 2, true, nullptr, ACT_NONE, b2, 196);
+    conv("layer2.0.conv2", b1, NI, H4, W4, 196, 196, 196, 3, 1, true, b2, ACT_RELU, b0, 196);
+    conv("layer2.1.conv1", b0, NI, H4, W4, 196, 196, 196, 3, 1, true, nullptr, ACT_RELU, b1, 196);
+    conv("layer2.1.conv2", b1, NI, H4, W4, 196, 196, 196, 3, 1, true, b0, ACT_RELU, b2, 196);  // x2 = b2
+    conv("layer3.0.conv1", b2, NI, H4, W4, 196, 196, 256, 3, 2, true, nullptr, ACT_RELU, c1, 256);
+    conv("layer3.0.down", b2, NI, H4, W4, 196, 196, 256, 1, 2, true, nullptr, ACT_NONE, c2, 256);
+    conv("layer3.0.conv2", c1, NI, H8, W8, 256, 256, 256, 3, 1, true, c2, ACT_RELU, c0, 256);
+    conv("layer3.1.conv1", c0, NI, H8, W8, 256, 256, 256, 3, 1, true, nullptr, ACT_RELU, c1, 256);
+    conv("layer3.1.conv2", c1, NI, H8, W8, 256, 256, 256, 3, 1, true, c0, ACT_RELU, c2, 256);  // x3 = c2
+    conv("layer3_outconv", c2, NI, H8, W8, 256, 256, 256, 1, 1, false, nullptr, ACT_NONE, fc, 256);
+    conv("layer2_outconv", b2, NI, H4, W4, 196, 196, 256, 1, 1, false, nullptr, ACT_NONE, p4a, 256);
+    {
+      float *s = fc, *d = p4a; const int n = NI, hs = H8, wsz = W8;
+      steps.push_back([=](cudaStream_t st) { return upsample2x_add(s, d, n, hs, wsz, 256, st); });
+    }
+    conv("layer2_outconv2.0", p4a, NI, H4, W4, 256, 256, 256, 3, 1, true, nullptr, ACT_LEAKY, p4b, 256);
+    conv("layer2_outconv2.3", p4b, NI, H4, W4, 256, 256, 196, 3, 1, false, nullptr, ACT_NONE, p4c, 196);
+    conv("layer1_outconv", a0, NI, H2, W2, 128, 128, 196, 1, 1, false, nullptr, ACT_NONE, p2a, 196);
+    {
+      float *s = p4c, *d = p2a; const int n = NI, hs = H4, wsz = W4;
+      steps.push_back([=](cudaStream_t st) { return upsample2x_add(s, d, n, hs, wsz, 196, st); });
+    }
+    conv("layer1_outconv2.0", p2a, NI, H2, W2, 196, 196, 196, 3, 1, true, nullptr, ACT_LEAKY, p2b, 196);
+    conv("layer1_outconv2.3", p2b, NI, H2, W2, 196, 196, 128, 3, 1, false, nullptr, ACT_NONE, a1, 128);
+    dbg["feat_f"] = DebugTensor{a1, static_cast<long long>(px2 * 128)};
+    float* featf = a1;
+
+    // ---------------------------------------------------------------- pos-enc + coarse transformer
+    {
+      float *f = fc, *t = tok; float* pe = W_("pos_enc"); const int n = NI, l = L;
+      steps.push_back([=](cudaStream_t st) { return posenc_tokens(f, pe, t, 512, n, l, 256, st); });
+    }
+    const size_t half_tok = static_cast<size_t>(B) * L * 512, half_qkv = static_cast<size_t>(B) * L * 768;
+    const size_t half_c = static_cast<size_t>(B) * L * 256, half_2c = static_cast<size_t>(B) * L * 512;
+    for (int i = 0; i < 8; ++i) {
+      const std::string p = "coarse." + std::to_string(i);
+      if (i % 2 == 0) {  // self: both image sets at once
+        encoder_layer(p, 256, tok, tok, qkv, qkv, msg, mrg, h1, h2, NI, L, nullptr, nullptr, false);
+      } else {  // cross: feat0 <- (feat0, feat1), then feat1 <- (feat1, updated feat0)
+        encoder_layer(p, 256, tok, tok + half_tok, qkv, qkv + half_qkv, msg, mrg, h1, h2, B, L, nullptr,
+                      nullptr, false);
+        encoder_layer(p, 256, tok + half_tok, tok, qkv + half_qkv, qkv, msg + half_c, mrg + half_c,
+                      h1 + half_2c, h2 + half_c, B, L, nullptr, nullptr, false);
+      }
+    }
+
+    // ---------------------------------------------------------------- coarse matching
+    {
+      ConvGemmDesc d{};
+      d.x = tok; d.N = B; d.H = 1; d.W = L; d.Cin = 256; d.ldx = 512;
+      d.w = tok + half_tok; d.Cout = L; d.R = 1; d.S = 1; d.stride = 1; d.pad = 0;
+      d.b_batched = 1; d.ldw = 512; d.act = ACT_NONE; d.alpha = 1.f / (256.f * temperature);
+      d.out = S; d.ldo = L; d.ldr = L;
+      ConvGemmParams p;
+      int rc = conv_gemm_build(d, &p);
+      if (rc != MFR_OK) return rc;
+      steps.push_back([p](cudaStream_t st) { return conv_gemm_launch(p, st); });
+      CoarseMatchBuffers cmb = cm; float* S_ = S;
+      const int B_ = B, L_ = L, hc = H8, wc = W8, bd = border, sc = splits_col; const float th = thr;
+      const float scale = static_cast<float>(H) / static_cast<float>(H8);
+      steps.push_back([=](cudaStream_t st) {
+        return coarse_match(S_, cmb, B_, L_, hc, wc, th, bd, scale, sc, st);
+      });
+    }
+
+    // ---------------------------------------------------------------- fine level
+    {
+      CoarseMatchBuffers cmb = cm; float *tok_ = tok, *cin_ = cin, *cproj_ = cproj, *win_ = win;
+      const int B_ = B, L_ = L, Mc = Mcap, Hf = H2, Wf = W2, wc = W8;
+      steps.push_back([=](cudaStream_t st) {
+        return fine_gather_coarse(tok_, 512, B_, L_, cmb.b_ids, cmb.i_ids, cmb.j_ids, cmb.m_total, Mc, cin_, st);
+      });
+      conv("fine.down_proj", cin, 2, 1, Mcap, 256, 256, 128, 1, 1, true, nullptr, ACT_NONE, cproj, 128, 0,
+           cm.m_total);
+      steps.push_back([=](cudaStream_t st) {
+        return fine_gather_windows(featf, B_, Hf, Wf, wc, cmb.b_ids, cmb.i_ids, cmb.j_ids, cmb.m_total, Mc,
+                                   cproj_, win_, st);
+      });
+      conv("fine.merge_feat", win, 2, 1, Mcap * 25, 256, 256, 128, 1, 1, true, nullptr, ACT_NONE, ftok, 256, 0,
+           cm.m_total + 2);
+    }
+    {
+      const int rows = Mcap * 25;
+      const size_t s_tok = static_cast<size_t>(rows) * 256, s_qkv = static_cast<size_t>(rows) * 384,
+                   s_c = static_cast<size_t>(rows) * 128, s_2c = static_cast<size_t>(rows) * 256;
+      encoder_layer("fine.0", 128, ftok, ftok, fqkv, fqkv, fmsg, fmrg, fh1, fh2, 2, rows, cm.m_total + 2,
+                    cm.m_total, true);
+      encoder_layer("fine.1", 128, ftok, ftok + s_tok, fqkv, fqkv + s_qkv, fmsg, fmrg, fh1, fh2, 1, rows,
+                    cm.m_total + 2, cm.m_total, true);
+      encoder_layer("fine.1", 128, ftok + s_tok, ftok, fqkv + s_qkv, fqkv, fmsg + s_c, fmrg + s_c, fh1 + s_2c,
+                    fh2 + s_c, 1, rows, cm.m_total + 2, cm.m_total, true);
+      CoarseMatchBuffers cmb = cm; float *f0 = ftok, *f1 = ftok + s_tok, *mk = mk1f, *ex = expec;
+      const int Mc = Mcap; const float scale_f = static_cast<float>(H) / static_cast<float>(H2);
+      steps.push_back([=](cudaStream_t st) {
+        return fine_match(f0, f1, 256, cmb.mkpts1_c, cmb.m_total, Mc, scale_f, mk, ex, st);
+      });
+    }
+    return build_rc;
+  }
+
+  int run_steps(cudaStream_t st) {
+    for (auto& s : steps) {
+      int rc = s(st);
+      if (rc != MFR_OK) return rc;
+    }
+    return MFR_OK;
+  }
+
+  int forward(const float* img0, const float* img1, cudaStream_t st) {
+    if (!weights_loaded) {
+      fprintf(stderr, "[mfr_b200] loftr forward before weights were loaded\n");
+      return MFR_ERR_ARG;
+    }
+    const size_t half = static_cast<size_t>(B) * H * W;
+    MFR_CUDA_CHECK(cudaMemcpyAsync(img, img0, half * 4, cudaMemcpyDeviceToDevice, st));
+    MFR_CUDA_CHECK(cudaMemcpyAsync(img + half, img1, half * 4, cudaMemcpyDeviceToDevice, st));
+    if (!use_graph) return run_steps(st);
+    if (!graph_exec) {
+      // warm (sets function attributes outside capture), then capture the launch list once
+      int rc = run_steps(st);
+      if (rc != MFR_OK) return rc;
+      MFR_CUDA_CHECK(cudaStreamSynchronize(st));
+      cudaGraph_t g;
+      MFR_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      rc = run_steps(st);
+      cudaError_t e = cudaStreamEndCapture(st, &g);
+      if (rc != MFR_OK || e != cudaSuccess) {
+        fprintf(stderr, "[mfr_b200] graph capture failed (%d, %s); running eagerly\n", rc, cudaGetErrorString(e));
+        use_graph = false;
+        cudaGetLastError();
+        return run_steps(st);
+      }
+      MFR_CUDA_CHECK(cudaGraphInstantiate(&graph_exec, g, 0));
+      cudaGraphDestroy(g);
+      return MFR_OK;  // the warm-up pass above already produced this call's results
+    }
+    MFR_CUDA_CHECK(cudaGraphLaunch(graph_exec, st));
+    return MFR_OK;
+  }
+
+  ~LoftrEngine() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    for (void* p : allocs) cudaFree(p);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+int loftr_create(int B, int H, int W, float thr, int border, float temperature, LoftrEngine** out) {
+  if (B < 1 || H % 8 || W % 8 || H < 32 || W < 32) return MFR_ERR_ARG;
+  auto* e = new LoftrEngine();
+  e->B = B; e->H = H; e->W = W; e->thr = thr; e->border = border; e->temperature = temperature;
+  int rc = e->build();
+  if (rc != MFR_OK) { delete e; return rc; }
+  *out = e;
+  return MFR_OK;
+}
+void loftr_destroy(LoftrEngine* e) { delete e; }
+int loftr_num_weights(const LoftrEngine* e) { return static_cast<int>(e->specs.size()); }
+const char* loftr_weight_name(const LoftrEngine* e, int i) { return e->specs[i].name.c_str(); }
+long long loftr_weight_numel(const LoftrEngine* e, int i) { return static_cast<long long>(e->specs[i].numel); }
+int loftr_set_weight(LoftrEngine* e, int i, const float* host, long long numel, cudaStream_t st) {
+  if (i < 0 || i >= static_cast<int>(e->specs.size()) || numel != static_cast<long long>(e->specs[i].numel))
+    return MFR_ERR_ARG;
+  MFR_CUDA_CHECK(cudaMemcpyAsync(e->wblob + e->specs[i].offset, host, numel * 4, cudaMemcpyHostToDevice, st));
+  MFR_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (i == static_cast<int>(e->specs.size()) - 1) e->weights_loaded = true;
+  return MFR_OK;
+}
+void loftr_mark_weights_loaded(LoftrEngine* e) { e->weights_loaded = true; }
+int loftr_forward(LoftrEngine* e, const float* img0, const float* img1, cudaStream_t st) {
+  return e->forward(img0, img1, st);
+}
+void loftr_set_graph(LoftrEngine* e, int on) { e->use_graph = on != 0; }
+LoftrOutputs loftr_outputs(LoftrEngine* e) {
+  LoftrOutputs o;
+  o.m_total = e->cm.m_total; o.m_offsets = e->cm.m_offsets; o.b_ids = e->cm.b_ids;
+  o.i_ids = e->cm.i_ids; o.j_ids = e->cm.j_ids; o.mconf = e->cm.mconf;
+  o.mkpts0_f = e->cm.mkpts0_c; o.mkpts1_f = e->mk1f; o.mkpts1_c = e->cm.mkpts1_c; o.expec_f = e->expec;
+  o.capacity = e->Mcap;
+  return o;
+}
+int loftr_debug_tensor(LoftrEngine* e, const char* name, float** ptr, long long* numel) {
+  auto it = e->dbg.find(name);
+  if (it == e->dbg.end()) return MFR_ERR_ARG;
+  *ptr = it->second.ptr;
+  *numel = it->second.numel;
+  return MFR_OK;
+}
+int loftr_num_steps(const LoftrEngine* e) { return static_cast<int>(e->steps.size()); }
+
+}  // namespace mfr

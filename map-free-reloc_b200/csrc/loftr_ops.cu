@@ -1,0 +1,765 @@
+// SIMT kernels of the LoFTR matcher (everything that is not a GEMM). See loftr_ops.cuh.
+#include "loftr_ops.cuh"
+
+#include <algorithm>
+
+namespace mfr {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------ stem
+constexpr int kStemPx = 32;
+__global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ img,
+                                                   const float* __restrict__ w,
+                                                   const float* __restrict__ bias,
+                                                   float* __restrict__ out, int H, int W, int Ho,
+                                                   int Wo) {
+  __shared__ float patch[7][2 * kStemPx + 8];
+  const int n = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * kStemPx;
+  const int c = threadIdx.x;
+  constexpr int PW = 2 * kStemPx + 5;
+  for (int idx = threadIdx.x; idx < 7 * PW; idx += 128) {
+    const int ky = idx / PW, kx = idx - ky * PW;
+    const int iy = 2 * y - 3 + ky, ix = 2 * x0 - 3 + kx;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[(static_cast<size_t>(n) * H + iy) * W + ix];
+    patch[ky][kx] = v;
+  }
+  float wr[49];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) wr[k] = w[c * 49 + k];
+  const float b = bias[c];
+  __syncthreads();
+  for (int px0 = 0; px0 < kStemPx; px0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) acc[p] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky) {
+      float row[21];
+#pragma unroll
+      for (int j = 0; j < 21; ++j) row[j] = patch[ky][2 * px0 + j];
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) acc[p] = fmaf(wr[ky * 7 + kx], row[2 * p + kx], acc[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int x = x0 + px0 + p;
+      if (x < Wo)
+        out[((static_cast<size_t>(n) * Ho + y) * Wo + x) * 128 + c] = fmaxf(acc[p] + b, 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ upsample
+__global__ void upsample2x_add_kernel(const float* __restrict__ src, float* __restrict__ dst, int N,
+                                      int Hs, int Ws, int C4, float ry, float rx) {
+  const int Hd = 2 * Hs, Wd = 2 * Ws;
+  const size_t total = static_cast<size_t>(N) * Hd * Wd * C4;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = static_cast<int>(idx % C4);
+  size_t pix = idx / C4;
+  const int x = static_cast<int>(pix % Wd);
+  pix /= Wd;
+  const int y = static_cast<int>(pix % Hd);
+  const int n = static_cast<int>(pix / Hd);
+  const float sy = ry * y, sx = rx * x;
+  const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+  const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+  const float ly = sy - y0, lx = sx - x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float4* s = reinterpret_cast<const float4*>(src) + static_cast<size_t>(n) * Hs * Ws * C4;
+  const float4 a = s[(static_cast<size_t>(y0) * Ws + x0) * C4 + c4];
+  const float4 b = s[(static_cast<size_t>(y0) * Ws + x1) * C4 + c4];
+  const float4 c = s[(static_cast<size_t>(y1) * Ws + x0) * C4 + c4];
+  const float4 d = s[(static_cast<size_t>(y1) * Ws + x1) * C4 + c4];
+  float4* o = reinterpret_cast<float4*>(dst) + idx;
+  float4 v = *o;
+  v.x += hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x);
+  v.y += hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y);
+  v.z += hy * (hx * a.z + lx * b.z) + ly * (hx * c.z + lx * d.z);
+  v.w += hy * (hx * a.w + lx * b.w) + ly * (hx * c.w + lx * d.w);
+  *o = v;
+}
+
+// ------------------------------------------------------------------------------------------ posenc
+__global__ void posenc_kernel(const float* __restrict__ feat, const float* __restrict__ pe,
+                              float* __restrict__ tok, long long ldt, int N, int L, int C4) {
+  const size_t total = static_cast<size_t>(N) * L * C4;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = static_cast<int>(idx % C4);
+  const size_t row = idx / C4;
+  const int l = static_cast<int>(row % L);
+  const float4 f = reinterpret_cast<const float4*>(feat)[idx];
+  const float4 p = reinterpret_cast<const float4*>(pe)[static_cast<size_t>(l) * C4 + c4];
+  float4 o;
+  o.x = f.x + p.x; o.y = f.y + p.y; o.z = f.z + p.z; o.w = f.w + p.w;
+  *reinterpret_cast<float4*>(tok + row * ldt + c4 * 4) = o;
+}
+
+// ------------------------------------------------------------------------------------------ linear attention (long)
+// D = 32 only (coarse: 8 heads x 32).
+constexpr int kKvTile = 64;
+__global__ void __launch_bounds__(256) kv_partial_kernel(const float* __restrict__ K, long long ldk,
+                                                         const float* __restrict__ V, long long ldv,
+                                                         float* __restrict__ kv_part, int S, int heads,
+                                                         int splits) {
+  __shared__ float sK[kKvTile][33];
+  __shared__ float sV[kKvTile][33];
+  const int split = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int chunk = (S + splits - 1) / splits;
+  const int s_beg = split * chunk, s_end = min(S, s_beg + chunk);
+  const int t = threadIdx.x, v = t & 31, dg = t >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float ks = 0.f;
+  const float fS = static_cast<float>(S);
+  for (int s0 = s_beg; s0 < s_end; s0 += kKvTile) {
+    const int cnt = min(kKvTile, s_end - s0);
+    for (int idx = t; idx < kKvTile * 32; idx += 256) {
+      const int r = idx >> 5, cc = idx & 31;
+      float kk = 0.f, vv = 0.f;
+      if (r < cnt) {
+        const size_t row = static_cast<size_t>(n) * S + s0 + r;
+        kk = K[row * ldk + h * 32 + cc];
+        vv = __fdiv_rn(V[row * ldv + h * 32 + cc], fS);
+      }
+      sK[r][cc] = kk;
+      sV[r][cc] = vv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < kKvTile; ++r) {
+      const float vv = sV[r][v];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(sK[r][dg * 4 + j], vv, acc[j]);
+      if (t < 32) ks += sK[r][t];
+    }
+    __syncthreads();
+  }
+  float* o = kv_part + ((static_cast<size_t>(n) * heads + h) * splits + split) * 1056;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[(dg * 4 + j) * 32 + v] = acc[j];
+  if (t < 32) o[1024 + t] = ks;
+}
+
+__global__ void kv_reduce_kernel(const float* __restrict__ kv_part, float* __restrict__ kv, int splits) {
+  const size_t nh = blockIdx.x;
+  for (int e = threadIdx.x; e < 1056; e += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += kv_part[(nh * splits + k) * 1056 + e];
+    kv[nh * 1056 + e] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict__ Q, long long ldq,
+                                                         const float* __restrict__ kv,
+                                                         float* __restrict__ msg, long long ldm, int L,
+                                                         int S, float eps) {
+  __shared__ float sKV[8][1057];
+  const int n = blockIdx.y;
+  for (int idx = threadIdx.x; idx < 8 * 1056; idx += 256) {
+    const int h = idx / 1056, e = idx - h * 1056;
+    sKV[h][e] = kv[(static_cast<size_t>(n) * 8 + h) * 1056 + e];
+  }
+  __syncthreads();
+  const int h = threadIdx.x & 7;
+  const int l = blockIdx.x * 32 + (threadIdx.x >> 3);
+  if (l >= L) return;
+  const size_t row = static_cast<size_t>(n) * L + l;
+  float q[32];
+  const float4* qp = reinterpret_cast<const float4*>(Q + row * ldq + h * 32);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 f = qp[j];
+    q[4 * j] = f.x; q[4 * j + 1] = f.y; q[4 * j + 2] = f.z; q[4 * j + 3] = f.w;
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int d = 0; d < 32; ++d) den = fmaf(q[d], sKV[h][1024 + d], den);
+  const float z = 1.f / (den + eps);
+  const float fS = static_cast<float>(S);
+  float4* op = reinterpret_cast<float4*>(msg + row * ldm + h * 32);
+#pragma unroll
+  for (int v4 = 0; v4 < 8; ++v4) {
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) a = fmaf(q[d], sKV[h][d * 32 + v4 * 4 + j], a);
+      o[j] = a * z * fS;
+    }
+    op[v4] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ linear attention (windows)
+// C = 128 (8 heads x 16), T tokens per item (T <= 32). One block (128 threads) per item.
+template <int T>
+__global__ void __launch_bounds__(128) attn_windows_kernel(const float* __restrict__ Q, long long ldq,
+                                                           const float* __restrict__ K, long long ldk,
+                                                           const float* __restrict__ V, long long ldv,
+                                                           float* __restrict__ msg, long long ldm,
+                                                           const int* __restrict__ n_items_dev,
+                                                           float eps) {
+  const int item = blockIdx.x;
+  if (item >= *n_items_dev) return;
+  __shared__ float sQ[32][128];
+  __shared__ float sK[32][128];
+  const int t = threadIdx.x;
+  const int hb = (t >> 4) << 4;  // first channel of this thread's head
+  float vcol[T];
+  const float fT = static_cast<float>(T);
+#pragma unroll
+  for (int s = 0; s < T; ++s) {
+    const size_t row = static_cast<size_t>(item) * T + s;
+    sQ[s][t] = Q[row * ldq + t];
+    sK[s][t] = K[row * ldk + t];
+    vcol[s] = __fdiv_rn(V[row * ldv + t], fT);
+  }
+  __syncthreads();
+  float kvc[16], ks[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int s = 0; s < T; ++s) {
+      const float kk = sK[s][hb + d];
+      a = fmaf(kk, vcol[s], a);
+      b += kk;
+    }
+    kvc[d] = a;
+    ks[d] = b;
+  }
+  for (int l = 0; l < T; ++l) {
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+      const float qq = sQ[l][hb + d];
+      num = fmaf(qq, kvc[d], num);
+      den = fmaf(qq, ks[d], den);
+    }
+    msg[(static_cast<size_t>(item) * T + l) * ldm + t] = num * (1.f / (den + eps)) * fT;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ layernorm
+template <int C>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, long long ldi,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta,
+                                                        const float* __restrict__ res, long long ldr,
+                                                        float* __restrict__ out, long long ldo,
+                                                        long long rows, const int* __restrict__ dyn_rows) {
+  constexpr int V = C / 128;  // float4 per lane
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  long long lim = rows;
+  if (dyn_rows) lim = min(lim, static_cast<long long>(*dyn_rows));
+  if (row >= lim) return;
+  const int lane = threadIdx.x & 31;
+  float x[4 * V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const float4 f = *reinterpret_cast<const float4*>(in + row * ldi + k * 128 + lane * 4);
+    x[4 * k] = f.x; x[4 * k + 1] = f.y; x[4 * k + 2] = f.z; x[4 * k + 3] = f.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4 * V; ++k) s += x[k];
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4 * V; ++k) {
+    const float d = x[k] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = 1.f / sqrtf(warp_sum(q) / C + 1e-5f);
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int c = k * 128 + lane * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 b = *reinterpret_cast<const float4*>(beta + c);
+    float4 o;
+    o.x = (x[4 * k] - mean) * rstd * g.x + b.x;
+    o.y = (x[4 * k + 1] - mean) * rstd * g.y + b.y;
+    o.z = (x[4 * k + 2] - mean) * rstd * g.z + b.z;
+    o.w = (x[4 * k + 3] - mean) * rstd * g.w + b.w;
+    if (res) {
+      const float4 r = *reinterpret_cast<const float4*>(res + row * ldr + c);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    *reinterpret_cast<float4*>(out + row * ldo + c) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ coarse matching
+// conf = softmax_col(S) * softmax_row(S); the expression is written with explicit rounding
+// intrinsics so that every pass reproduces the identical fp32 value (the mutual-NN test compares
+// for float equality, coarse_matching.py:187-189).
+__device__ __forceinline__ float conf_value(float s, float rmax, float rrs, float cmax, float crs) {
+  const float pr = __fmul_rn(__expf(__fsub_rn(s, rmax)), rrs);
+  const float pc = __fmul_rn(__expf(__fsub_rn(s, cmax)), crs);
+  return __fmul_rn(pc, pr);
+}
+
+__device__ __forceinline__ float block_max_256(float v, float* sh) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) r = fmaxf(r, sh[k]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum_256(float v, float* sh) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r += sh[k];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ S,
+                                                        float* __restrict__ row_max,
+                                                        float* __restrict__ row_rsum, int L) {
+  __shared__ float sh[8];
+  const size_t r = static_cast<size_t>(blockIdx.y) * L + blockIdx.x;
+  const float* p = S + r * L;
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < L; j += 256) m = fmaxf(m, p[j]);
+  m = block_max_256(m, sh);
+  float s = 0.f;
+  for (int j = threadIdx.x; j < L; j += 256) s += __expf(__fsub_rn(p[j], m));
+  s = block_sum_256(s, sh);
+  if (threadIdx.x == 0) {
+    row_max[r] = m;
+    row_rsum[r] = 1.f / s;
+  }
+}
+
+// column stats: partial online (max, sum) over a slab of rows
+__global__ void __launch_bounds__(256) col_stats_partial_kernel(const float* __restrict__ S,
+                                                                float* __restrict__ part, int L,
+                                                                int splits) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int split = blockIdx.y, b = blockIdx.z;
+  if (j >= L) return;
+  const int chunk = (L + splits - 1) / splits;
+  const int i0 = split * chunk, i1 = min(L, i0 + chunk);
+  const float* p = S + static_cast<size_t>(b) * L * L + j;
+  float m = -INFINITY;
+  for (int i = i0; i < i1; ++i) m = fmaxf(m, p[static_cast<size_t>(i) * L]);
+  float s = 0.f;
+  for (int i = i0; i < i1; ++i) s += __expf(__fsub_rn(p[static_cast<size_t>(i) * L], m));
+  float* o = part + ((static_cast<size_t>(b) * splits + split) * L + j) * 2;
+  o[0] = m;
+  o[1] = s;
+}
+__global__ void col_stats_combine_kernel(const float* __restrict__ part, float* __restrict__ col_max,
+                                         float* __restrict__ col_rsum, int L, int splits) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (j >= L) return;
+  float m = -INFINITY;
+  for (int k = 0; k < splits; ++k)
+    m = fmaxf(m, part[((static_cast<size_t>(b) * splits + k) * L + j) * 2]);
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) {
+    const float* q = part + ((static_cast<size_t>(b) * splits + k) * L + j) * 2;
+    if (q[0] > -INFINITY) s += q[1] * __expf(q[0] - m);
+  }
+  col_max[static_cast<size_t>(b) * L + j] = m;
+  col_rsum[static_cast<size_t>(b) * L + j] = 1.f / s;
+}
+
+__global__ void __launch_bounds__(256) row_conf_kernel(const float* __restrict__ S,
+                                                       const float* __restrict__ row_max,
+                                                       const float* __restrict__ row_rsum,
+                                                       const float* __restrict__ col_max,
+                                                       const float* __restrict__ col_rsum,
+                                                       float* __restrict__ rconf_max,
+                                                       int* __restrict__ rconf_arg,
+                                                       int* __restrict__ rconf_ties, int L) {
+  __shared__ float sh[8];
+  __shared__ int shi[8];
+  const int b = blockIdx.y;
+  const size_t r = static_cast<size_t>(b) * L + blockIdx.x;
+  const float* p = S + r * L;
+  const float rm = row_max[r], rr = row_rsum[r];
+  const float* cm = col_max + static_cast<size_t>(b) * L;
+  const float* cr = col_rsum + static_cast<size_t>(b) * L;
+  float best = -1.f;
+  int arg = 0x7fffffff;
+  for (int j = threadIdx.x; j < L; j += 256) {
+    const float c = conf_value(p[j], rm, rr, cm[j], cr[j]);
+    if (c > best) { best = c; arg = j; }
+  }
+  const float bm = block_max_256(best, sh);
+  // first index attaining the max, and how many attain it
+  int cand = (best == bm) ? arg : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+  if ((threadIdx.x & 31) == 0) shi[threadIdx.x >> 5] = cand;
+  __syncthreads();
+  int first = shi[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) first = min(first, shi[k]);
+  __syncthreads();
+  int ties = 0;
+  for (int j = threadIdx.x; j < L; j += 256)
+    ties += (conf_value(p[j], rm, rr, cm[j], cr[j]) == bm) ? 1 : 0;
+  const float tsum = block_sum_256(static_cast<float>(ties), sh);
+  if (threadIdx.x == 0) {
+    rconf_max[r] = bm;
+    rconf_arg[r] = first;
+    rconf_ties[r] = static_cast<int>(tsum + 0.5f);
+  }
+}
+
+__global__ void __launch_bounds__(256) col_conf_partial_kernel(const float* __restrict__ S,
+                                                               const float* __restrict__ row_max,
+                                                               const float* __restrict__ row_rsum,
+                                                               const float* __restrict__ col_max,
+                                                               const float* __restrict__ col_rsum,
+                                                               float* __restrict__ part, int L,
+                                                               int splits) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int split = blockIdx.y, b = blockIdx.z;
+  if (j >= L) return;
+  const int chunk = (L + splits - 1) / splits;
+  const int i0 = split * chunk, i1 = min(L, i0 + chunk);
+  const float* p = S + static_cast<size_t>(b) * L * L + j;
+  const float cm = col_max[static_cast<size_t>(b) * L + j], cr = col_rsum[static_cast<size_t>(b) * L + j];
+  const float* rm = row_max + static_cast<size_t>(b) * L;
+  const float* rr = row_rsum + static_cast<size_t>(b) * L;
+  float best = -1.f;
+  for (int i = i0; i < i1; ++i)
+    best = fmaxf(best, conf_value(p[static_cast<size_t>(i) * L], rm[i], rr[i], cm, cr));
+  part[(static_cast<size_t>(b) * splits + split) * L + j] = best;
+}
+__global__ void col_conf_combine_kernel(const float* __restrict__ part, float* __restrict__ cconf_max,
+                                        int L, int splits) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (j >= L) return;
+  float m = -1.f;
+  for (int k = 0; k < splits; ++k) m = fmaxf(m, part[(static_cast<size_t>(b) * splits + k) * L + j]);
+  cconf_max[static_cast<size_t>(b) * L + j] = m;
+}
+
+__device__ __forceinline__ bool border_ok(int idx, int h, int w, int bd) {
+  const int y = idx / w, x = idx - y * w;
+  return y >= bd && y < h - bd && x >= bd && x < w - bd;
+}
+
+__global__ void select_kernel(const float* __restrict__ S, const float* __restrict__ row_max,
+                              const float* __restrict__ row_rsum, const float* __restrict__ col_max,
+                              const float* __restrict__ col_rsum, const float* __restrict__ rconf_max,
+                              const int* __restrict__ rconf_arg, const int* __restrict__ rconf_ties,
+                              const float* __restrict__ cconf_max, int* __restrict__ jsel, int L,
+                              int h_c, int w_c, float thr, int border) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= L) return;
+  const size_t r = static_cast<size_t>(b) * L + i;
+  const float v = rconf_max[r];
+  int sel = -1;
+  if (v > thr && border_ok(i, h_c, w_c, border)) {
+    const float* cc = cconf_max + static_cast<size_t>(b) * L;
+    const int j = rconf_arg[r];
+    if (border_ok(j, h_c, w_c, border) && v == cc[j]) {
+      sel = j;
+    } else if (rconf_ties[r] > 1) {
+      // rare: several columns attain the row maximum; take the first that is also a column maximum
+      const float* p = S + r * L;
+      const float rm = row_max[r], rr = row_rsum[r];
+      const float* cm = col_max + static_cast<size_t>(b) * L;
+      const float* cr = col_rsum + static_cast<size_t>(b) * L;
+      for (int jj = j + 1; jj < L; ++jj) {
+        const float c = conf_value(p[jj], rm, rr, cm[jj], cr[jj]);
+        if (c == v && c == cc[jj] && border_ok(jj, h_c, w_c, border)) { sel = jj; break; }
+      }
+    }
+  }
+  jsel[r] = sel;
+}
+
+// single block: ordered compaction over (b, i)
+__global__ void __launch_bounds__(1024) compact_kernel(const int* __restrict__ jsel,
+                                                       const float* __restrict__ rconf_max, int B, int L,
+                                                       int w_c, float scale, int* __restrict__ m_total,
+                                                       int* __restrict__ m_offsets, int* __restrict__ b_ids,
+                                                       int* __restrict__ i_ids, int* __restrict__ j_ids,
+                                                       float* __restrict__ mconf, float* __restrict__ mk0,
+                                                       float* __restrict__ mk1) {
+  __shared__ int wsum[32];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int b = 0; b < B; ++b) {
+    if (threadIdx.x == 0) m_offsets[b] = base;
+    for (int i0 = 0; i0 < L; i0 += 1024) {
+      const int i = i0 + threadIdx.x;
+      int j = -1;
+      if (i < L) j = jsel[static_cast<size_t>(b) * L + i];
+      const int flag = j >= 0 ? 1 : 0;
+      int inc = flag;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane == 31) wsum[wid] = inc;
+      __syncthreads();
+      if (wid == 0) {
+        int w = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, w, o);
+          if (lane >= o) w += t;
+        }
+        wsum[lane] = w;
+      }
+      __syncthreads();
+      const int prefix = base + (wid > 0 ? wsum[wid - 1] : 0) + inc - flag;
+      if (flag) {
+        b_ids[prefix] = b;
+        i_ids[prefix] = i;
+        j_ids[prefix] = j;
+        mconf[prefix] = rconf_max[static_cast<size_t>(b) * L + i];
+        mk0[2 * prefix] = static_cast<float>(i % w_c) * scale;
+        mk0[2 * prefix + 1] = static_cast<float>(i / w_c) * scale;
+        mk1[2 * prefix] = static_cast<float>(j % w_c) * scale;
+        mk1[2 * prefix + 1] = static_cast<float>(j / w_c) * scale;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) base += wsum[31];
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    m_offsets[B] = base;
+    m_total[0] = base;
+    m_total[1] = 2 * base;
+    m_total[2] = 25 * base;
+    m_total[3] = 50 * base;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ fine level
+__global__ void __launch_bounds__(64) fine_gather_coarse_kernel(const float* __restrict__ tok,
+                                                                long long ldt, int B, int L,
+                                                                const int* __restrict__ b_ids,
+                                                                const int* __restrict__ i_ids,
+                                                                const int* __restrict__ j_ids,
+                                                                const int* __restrict__ m_total,
+                                                                int Mcap, float* __restrict__ cin) {
+  const int m = blockIdx.x, s = blockIdx.y;
+  if (m >= m_total[0]) return;
+  const int b = b_ids[m];
+  const int tokidx = s == 0 ? i_ids[m] : j_ids[m];
+  const size_t row = (static_cast<size_t>(s == 0 ? b : B + b)) * L + tokidx;
+  const float4 v = *reinterpret_cast<const float4*>(tok + row * ldt + threadIdx.x * 4);
+  *reinterpret_cast<float4*>(cin + (static_cast<size_t>(s) * Mcap + m) * 256 + threadIdx.x * 4) = v;
+}
+
+__global__ void __launch_bounds__(128) fine_gather_windows_kernel(
+    const float* __restrict__ featf, int B, int Hf, int Wf, int w_c, int stride,
+    const int* __restrict__ b_ids, const int* __restrict__ i_ids, const int* __restrict__ j_ids,
+    const int* __restrict__ m_total, int Mcap, const float* __restrict__ cproj, float* __restrict__ win) {
+  const int m = blockIdx.x, s = blockIdx.y;
+  if (m >= m_total[0]) return;
+  const int b = b_ids[m];
+  const int idx = s == 0 ? i_ids[m] : j_ids[m];
+  const int cy = idx / w_c, cx = idx - cy * w_c;
+  const int img = s == 0 ? b : B + b;
+  const int c = threadIdx.x;
+  const float cp = cproj[(static_cast<size_t>(s) * Mcap + m) * 128 + c];
+  float* o = win + (static_cast<size_t>(s) * Mcap + m) * 25 * 256;
+#pragma unroll 5
+  for (int tap = 0; tap < 25; ++tap) {
+    const int y = cy * stride - 2 + tap / 5, x = cx * stride - 2 + tap % 5;
+    float v = 0.f;
+    if (y >= 0 && y < Hf && x >= 0 && x < Wf)
+      v = featf[((static_cast<size_t>(img) * Hf + y) * Wf + x) * 128 + c];
+    o[tap * 256 + c] = v;
+    o[tap * 256 + 128 + c] = cp;
+  }
+}
+
+__global__ void __launch_bounds__(128) fine_match_kernel(const float* __restrict__ f0,
+                                                         const float* __restrict__ f1, long long ldf,
+                                                         const float* __restrict__ mk1c,
+                                                         const int* __restrict__ m_total, float scale_f,
+                                                         float* __restrict__ mk1f, float* __restrict__ expec) {
+  const int m = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (m >= m_total[0]) return;
+  const int lane = threadIdx.x & 31;
+  const float* c0 = f0 + (static_cast<size_t>(m) * 25 + 12) * ldf;
+  float sim = -INFINITY;
+  if (lane < 25) {
+    const float* r1 = f1 + (static_cast<size_t>(m) * 25 + lane) * ldf;
+    float a = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float4 u = *reinterpret_cast<const float4*>(c0 + 4 * k);
+      const float4 w = *reinterpret_cast<const float4*>(r1 + 4 * k);
+      a = fmaf(u.x, w.x, a); a = fmaf(u.y, w.y, a); a = fmaf(u.z, w.z, a); a = fmaf(u.w, w.w, a);
+    }
+    sim = a * 0.08838834764831845f;  // 1/sqrt(128)
+  }
+  const float mx = warp_max(sim);
+  const float e = lane < 25 ? __expf(sim - mx) : 0.f;
+  const float heat = e / warp_sum(e);
+  const float gx = -1.f + 0.5f * (lane % 5), gy = -1.f + 0.5f * (lane / 5);
+  const float ex = warp_sum(heat * gx), ey = warp_sum(heat * gy);
+  const float vx = warp_sum(heat * gx * gx) - ex * ex, vy = warp_sum(heat * gy * gy) - ey * ey;
+  if (lane == 0) {
+    mk1f[2 * m] = mk1c[2 * m] + ex * 2.f * scale_f;
+    mk1f[2 * m + 1] = mk1c[2 * m + 1] + ey * 2.f * scale_f;
+    expec[3 * m] = ex;
+    expec[3 * m + 1] = ey;
+    expec[3 * m + 2] = sqrtf(fmaxf(vx, 1e-10f)) + sqrtf(fmaxf(vy, 1e-10f));
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// launch wrappers
+// ================================================================================================
+int stem_conv7x7(const float* img, const float* w, const float* bias, float* out, int NI, int H, int W,
+                 cudaStream_t st) {
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  dim3 grid((Wo + kStemPx - 1) / kStemPx, Ho, NI);
+  stem_kernel<<<grid, 128, 0, st>>>(img, w, bias, out, H, W, Ho, Wo);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int upsample2x_add(const float* src, float* dst, int N, int Hs, int Ws, int C, cudaStream_t st) {
+  if (C % 4) return MFR_ERR_ARG;
+  const int Hd = 2 * Hs, Wd = 2 * Ws;
+  const float ry = Hd > 1 ? static_cast<float>(Hs - 1) / static_cast<float>(Hd - 1) : 0.f;
+  const float rx = Wd > 1 ? static_cast<float>(Ws - 1) / static_cast<float>(Wd - 1) : 0.f;
+  const size_t total = static_cast<size_t>(N) * Hd * Wd * (C / 4);
+  upsample2x_add_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, dst, N, Hs, Ws,
+                                                                                   C / 4, ry, rx);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int posenc_tokens(const float* feat, const float* pe, float* tok, long long ldt, int N, int L, int C,
+                  cudaStream_t st) {
+  const size_t total = static_cast<size_t>(N) * L * (C / 4);
+  posenc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(feat, pe, tok, ldt, N, L,
+                                                                           C / 4);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int linear_attention_long(const float* Q, long long ldq, const float* K, long long ldk, const float* V,
+                          long long ldv, float* msg, long long ldm, float* kv_part, float* kv, int n,
+                          int L, int S, int heads, int dim, int splits, cudaStream_t st) {
+  if (dim != 32 || heads != 8) return MFR_ERR_UNSUPPORTED;
+  kv_partial_kernel<<<dim3(splits, heads, n), 256, 0, st>>>(K, ldk, V, ldv, kv_part, S, heads, splits);
+  kv_reduce_kernel<<<n * heads, 256, 0, st>>>(kv_part, kv, splits);
+  attn_apply_kernel<<<dim3((L + 31) / 32, n), 256, 0, st>>>(Q, ldq, kv, msg, ldm, L, S, 1e-6f);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int linear_attention_windows(const float* Q, long long ldq, const float* K, long long ldk, const float* V,
+                             long long ldv, float* msg, long long ldm, const int* n_items_dev,
+                             int max_items, int T, cudaStream_t st) {
+  if (T != 25 || max_items <= 0) return MFR_ERR_UNSUPPORTED;
+  attn_windows_kernel<25><<<max_items, 128, 0, st>>>(Q, ldq, K, ldk, V, ldv, msg, ldm, n_items_dev, 1e-6f);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int layernorm_rows(const float* in, long long ldi, const float* gamma, const float* beta,
+                   const float* res, long long ldr, float* out, long long ldo, long long rows, int C,
+                   const int* dyn_rows, cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  if (grid == 0) return MFR_OK;
+  if (C == 256)
+    layernorm_kernel<256><<<grid, 256, 0, st>>>(in, ldi, gamma, beta, res, ldr, out, ldo, rows, dyn_rows);
+  else if (C == 128)
+    layernorm_kernel<128><<<grid, 256, 0, st>>>(in, ldi, gamma, beta, res, ldr, out, ldo, rows, dyn_rows);
+  else
+    return MFR_ERR_UNSUPPORTED;
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int coarse_match(const float* S, CoarseMatchBuffers f, int B, int L, int h_c, int w_c, float thr,
+                 int border, float scale, int splits, cudaStream_t st) {
+  const int cb = (L + 255) / 256;
+  row_stats_kernel<<<dim3(L, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, L);
+  col_stats_partial_kernel<<<dim3(cb, splits, B), 256, 0, st>>>(S, f.col_part, L, splits);
+  col_stats_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.col_max, f.col_rsum, L, splits);
+  row_conf_kernel<<<dim3(L, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max, f.col_rsum,
+                                              f.rconf_max, f.rconf_arg, f.rconf_ties, L);
+  col_conf_partial_kernel<<<dim3(cb, splits, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max,
+                                                               f.col_rsum, f.col_part, L, splits);
+  col_conf_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.cconf_max, L, splits);
+  select_kernel<<<dim3(cb, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max, f.col_rsum,
+                                             f.rconf_max, f.rconf_arg, f.rconf_ties, f.cconf_max, f.jsel,
+                                             L, h_c, w_c, thr, border);
+  compact_kernel<<<1, 1024, 0, st>>>(f.jsel, f.rconf_max, B, L, w_c, scale, f.m_total, f.m_offsets,
+                                     f.b_ids, f.i_ids, f.j_ids, f.mconf, f.mkpts0_c, f.mkpts1_c);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int fine_gather_coarse(const float* tok, long long ldt, int B, int L, const int* b_ids, const int* i_ids,
+                       const int* j_ids, const int* m_total, int Mcap, float* cin, cudaStream_t st) {
+  fine_gather_coarse_kernel<<<dim3(Mcap, 2), 64, 0, st>>>(tok, ldt, B, L, b_ids, i_ids, j_ids, m_total,
+                                                          Mcap, cin);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int fine_gather_windows(const float* featf, int B, int Hf, int Wf, int w_c, const int* b_ids,
+                        const int* i_ids, const int* j_ids, const int* m_total, int Mcap,
+                        const float* cproj, float* win, cudaStream_t st) {
+  const int h_c_times_stride = Hf;  // stride = Hf / h_c, computed by the caller through w_c
+  (void)h_c_times_stride;
+  const int stride = Wf / w_c;
+  fine_gather_windows_kernel<<<dim3(Mcap, 2), 128, 0, st>>>(featf, B, Hf, Wf, w_c, stride, b_ids, i_ids,
+                                                            j_ids, m_total, Mcap, cproj, win);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int fine_match(const float* f0, const float* f1, long long ldf, const float* mkpts1_c,
+               const int* m_total, int Mcap, float scale_f, float* mkpts1_f, float* expec,
+               cudaStream_t st) {
+  fine_match_kernel<<<(Mcap + 3) / 4, 128, 0, st>>>(f0, f1, ldf, mkpts1_c, m_total, scale_f, mkpts1_f,
+                                                    expec);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+}  // namespace mfr

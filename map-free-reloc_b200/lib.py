@@ -15,6 +15,15 @@ c_int = ctypes.c_int
 c_float = ctypes.c_float
 c_vp = ctypes.c_void_p
 
+class LoftrOutputs(ctypes.Structure):
+    """mfr_loftr_outputs of include/mfr_b200.h."""
+    _fields_ = [("m_total", c_vp), ("m_offsets", c_vp), ("b_ids", c_vp), ("i_ids", c_vp),
+                ("j_ids", c_vp), ("mconf", c_vp), ("mkpts0_f", c_vp), ("mkpts1_f", c_vp),
+                ("mkpts1_c", c_vp), ("expec_f", c_vp), ("capacity", c_int)]
+
+
+c_pp = ctypes.POINTER(ctypes.c_void_p)
+
 # name -> (restype, argtypes); mirrors include/mfr_b200.h one to one
 SIGNATURES = {
     "mfr_version": (c_int, []),
@@ -22,6 +31,29 @@ SIGNATURES = {
     "mfr_conv2d_nhwc_tf32": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_ll, c_vp, c_int, c_int,
                                      c_int, c_int, c_int, c_int, c_vp, c_vp, c_ll, c_int, c_float,
                                      c_vp, c_ll, c_vp]),
+    "mfr_loftr_create": (c_int, [c_int, c_int, c_int, c_float, c_int, c_float, c_pp]),
+    "mfr_loftr_destroy": (None, [c_vp]),
+    "mfr_loftr_num_weights": (c_int, [c_vp]),
+    "mfr_loftr_weight_name": (ctypes.c_char_p, [c_vp, c_int]),
+    "mfr_loftr_weight_numel": (c_ll, [c_vp, c_int]),
+    "mfr_loftr_set_weight": (c_int, [c_vp, c_int, c_vp, c_ll, c_vp]),
+    "mfr_loftr_forward": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "mfr_loftr_set_graph": (None, [c_vp, c_int]),
+    "mfr_loftr_get_outputs": (c_int, [c_vp, ctypes.POINTER(LoftrOutputs)]),
+    "mfr_loftr_debug_tensor": (c_int, [c_vp, ctypes.c_char_p, c_pp, ctypes.POINTER(c_ll)]),
+    "mfr_loftr_num_kernels": (c_int, [c_vp]),
+    "mfr_pose_solver_create": (c_int, [c_int, c_int, c_int, c_pp]),
+    "mfr_pose_solver_destroy": (None, [c_vp]),
+    "mfr_emat_ransac": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_float, c_int,
+                                ctypes.c_ulonglong, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mfr_scale_from_depth": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                     c_vp, c_vp, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_vp]),
+    "mfr_pnp_ransac": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int,
+                               c_float, ctypes.c_ulonglong, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mfr_host_five_point": (c_int, [c_vp, c_vp, c_vp]),
+    "mfr_host_p3p": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "mfr_host_poly_real_roots": (c_int, [c_vp, c_int, c_vp]),
+    "mfr_host_decompose_essential": (c_int, [c_vp, c_vp, c_vp, c_vp]),
 }
 
 

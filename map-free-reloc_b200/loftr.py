@@ -1,0 +1,268 @@
+"""Host side of the LoFTR matcher: weight preparation for the CUDA engine and the matcher plugin
+with the reference's interface (``LoFTR_matcher(resize, outdoor).match((path0, path1)) -> [N,4]``,
+etc/feature_matching_baselines/matchers.py:12-59 of the reference).
+
+All network arithmetic runs in libmfr_b200.so (hand-written sm_100a kernels); torch is used for
+device memory and streams only. There is no CPU fallback.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+
+DEFAULT_CFG = {"thr": 0.2, "border_rm": 2, "temperature": 0.1}  # cvpr_ds_config.py:31-35
+
+
+def position_encoding(d_model, h, w):
+    """Sinusoidal table added to the 1/8 feature map, ``temp_bug_fix=False`` variant
+    (LoFTR/src/loftr/utils/position_encoding.py:22-38): the divisor evaluates to -1.0, i.e.
+    div_term = exp(-2k). Returned channel-last [h, w, d_model] float32."""
+    pe = torch.zeros((d_model, h, w), dtype=torch.float32)
+    ypos = torch.arange(1, h + 1, dtype=torch.float32)[:, None].expand(h, w)[None]
+    xpos = torch.arange(1, w + 1, dtype=torch.float32)[None, :].expand(h, w)[None]
+    k = torch.arange(0, d_model // 2, 2, dtype=torch.float32)
+    div = torch.exp(k * float(-math.log(10000.0) / d_model // 2))[:, None, None]
+    pe[0::4] = torch.sin(xpos * div)
+    pe[1::4] = torch.cos(xpos * div)
+    pe[2::4] = torch.sin(ypos * div)
+    pe[3::4] = torch.cos(ypos * div)
+    return pe.permute(1, 2, 0).contiguous()
+
+
+def _fold_bn(conv_w, sd, bn, eps=1e-5):
+    """Folds an eval-mode BatchNorm2d into the preceding bias-free conv:
+    w' = w * g/sqrt(var+eps), b' = beta - mean * g/sqrt(var+eps)."""
+    g = sd[bn + ".weight"].double()
+    b = sd[bn + ".bias"].double()
+    mean = sd[bn + ".running_mean"].double()
+    var = sd[bn + ".running_var"].double()
+    s = g / torch.sqrt(var + eps)
+    w = conv_w.double() * s[:, None, None, None]
+    return w.float(), (b - mean * s).float()
+
+
+def _conv_layout(w):
+    """[Cout, Cin, R, S] -> [Cout, R*S, Cin] (channel-last taps, what the implicit GEMM reads)."""
+    co, ci, r, s = w.shape
+    return w.permute(0, 2, 3, 1).reshape(co, r * s, ci).contiguous()
+
+
+def prepare_weights(sd, h_c, w_c):
+    """Reference-format LoFTR ``state_dict`` -> {engine tensor name: float32 ndarray}."""
+    sd = {k[len("matcher."):] if k.startswith("matcher.") else k: v.detach().float().cpu()
+          for k, v in sd.items()}  # loftr.py:77-81 strips the Lightning prefix
+    out = {}
+    w, b = _fold_bn(sd["backbone.conv1.weight"], sd, "backbone.bn1")
+    out["stem.w"] = w.reshape(128, 49)
+    out["stem.b"] = b
+    for li in (1, 2, 3):
+        for bi in (0, 1):
+            p = f"backbone.layer{li}.{bi}"
+            q = f"layer{li}.{bi}"
+            for cv, bn in (("conv1", "bn1"), ("conv2", "bn2")):
+                w, b = _fold_bn(sd[f"{p}.{cv}.weight"], sd, f"{p}.{bn}")
+                out[f"{q}.{cv}.w"] = _conv_layout(w)
+                out[f"{q}.{cv}.b"] = b
+            if f"{p}.downsample.0.weight" in sd:
+                w, b = _fold_bn(sd[f"{p}.downsample.0.weight"], sd, f"{p}.downsample.1")
+                out[f"{q}.down.w"] = _conv_layout(w)
+                out[f"{q}.down.b"] = b
+    for name in ("layer3_outconv", "layer2_outconv", "layer1_outconv"):
+        out[name + ".w"] = _conv_layout(sd[f"backbone.{name}.weight"])
+    for name in ("layer2_outconv2", "layer1_outconv2"):
+        w, b = _fold_bn(sd[f"backbone.{name}.0.weight"], sd, f"backbone.{name}.1")
+        out[name + ".0.w"] = _conv_layout(w)
+        out[name + ".0.b"] = b
+        out[name + ".3.w"] = _conv_layout(sd[f"backbone.{name}.3.weight"])
+    out["pos_enc"] = position_encoding(256, h_c, w_c)
+    for pre, ref, nl in (("coarse", "loftr_coarse", 8), ("fine", "loftr_fine", 2)):
+        for i in range(nl):
+            r = f"{ref}.layers.{i}"
+            q = f"{pre}.{i}"
+            out[q + ".qkv.w"] = torch.cat([sd[r + ".q_proj.weight"], sd[r + ".k_proj.weight"],
+                                           sd[r + ".v_proj.weight"]], 0)
+            out[q + ".merge.w"] = sd[r + ".merge.weight"]
+            out[q + ".mlp0.w"] = sd[r + ".mlp.0.weight"]
+            out[q + ".mlp2.w"] = sd[r + ".mlp.2.weight"]
+            out[q + ".norm1.g"] = sd[r + ".norm1.weight"]
+            out[q + ".norm1.b"] = sd[r + ".norm1.bias"]
+            out[q + ".norm2.g"] = sd[r + ".norm2.weight"]
+            out[q + ".norm2.b"] = sd[r + ".norm2.bias"]
+    out["fine.down_proj.w"] = sd["fine_preprocess.down_proj.weight"]
+    out["fine.down_proj.b"] = sd["fine_preprocess.down_proj.bias"]
+    out["fine.merge_feat.w"] = sd["fine_preprocess.merge_feat.weight"]
+    out["fine.merge_feat.b"] = sd["fine_preprocess.merge_feat.bias"]
+    return {k: np.ascontiguousarray(v.numpy().astype(np.float32)) for k, v in out.items()}
+
+
+class LoFTR:
+    """CUDA LoFTR engine for ``batch`` pairs of [H, W] images (H, W multiples of 8)."""
+
+    def __init__(self, state_dict, batch=1, height=720, width=544, cfg=None, device=0, graph=True):
+        if not torch.cuda.is_available():
+            raise _lib.MfrError("mfr_b200.LoFTR needs a CUDA device (no CPU fallback)")
+        self._l = _lib.load()
+        self.cfg = {**DEFAULT_CFG, **(cfg or {})}
+        self.B, self.H, self.W = int(batch), int(height), int(width)
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        h = ctypes.c_void_p()
+        _lib.check(self._l.mfr_loftr_create(self.B, self.H, self.W, float(self.cfg["thr"]),
+                                            int(self.cfg["border_rm"]), float(self.cfg["temperature"]),
+                                            ctypes.byref(h)), "mfr_loftr_create")
+        self._h = h
+        self._l.mfr_loftr_set_graph(self._h, int(bool(graph)))
+        self.load_state_dict(state_dict)
+        o = _lib.LoftrOutputs()
+        _lib.check(self._l.mfr_loftr_get_outputs(self._h, ctypes.byref(o)))
+        self._o = o
+        self.capacity = o.capacity
+        self._host_counts = torch.zeros(4 + self.B + 1, dtype=torch.int32).pin_memory()
+
+    def load_state_dict(self, state_dict):
+        w = prepare_weights(state_dict, self.H // 8, self.W // 8)
+        n = self._l.mfr_loftr_num_weights(self._h)
+        sp = ctypes.c_void_p(self.stream.cuda_stream)
+        for i in range(n):
+            name = self._l.mfr_loftr_weight_name(self._h, i).decode()
+            numel = self._l.mfr_loftr_weight_numel(self._h, i)
+            if name not in w:
+                raise _lib.MfrError(f"missing weight tensor {name}")
+            a = w[name].reshape(-1)
+            if a.size != numel:
+                raise _lib.MfrError(f"weight {name}: {a.size} elements, engine expects {numel}")
+            _lib.check(self._l.mfr_loftr_set_weight(self._h, i, a.ctypes.data_as(ctypes.c_void_p),
+                                                    numel, sp), f"set_weight {name}")
+
+    def num_kernels(self):
+        return self._l.mfr_loftr_num_kernels(self._h)
+
+    def _wrap(self, ptr, shape, dtype):
+        """Zero-copy torch view of an engine-owned device buffer."""
+        n = int(np.prod(shape))
+        itemsize = 4
+        class _Arr:  # __cuda_array_interface__ carrier
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = {
+            "shape": (n,), "typestr": "<f4" if dtype == torch.float32 else "<i4",
+            "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(a, device=self.device).view(*shape)
+
+    def debug_tensor(self, name, shape):
+        p = ctypes.c_void_p()
+        n = ctypes.c_longlong()
+        _lib.check(self._l.mfr_loftr_debug_tensor(self._h, name.encode(), ctypes.byref(p), ctypes.byref(n)),
+                   f"debug tensor {name}")
+        assert int(np.prod(shape)) <= n.value, (name, shape, n.value)
+        return self._wrap(p.value, shape, torch.float32)
+
+    def forward_async(self, img0, img1):
+        """Enqueues one batch on the engine stream. img0/img1: CUDA float32 [B,1,H,W] or [B,H,W]."""
+        img0 = img0.reshape(self.B, self.H, self.W).contiguous()
+        img1 = img1.reshape(self.B, self.H, self.W).contiguous()
+        assert img0.is_cuda and img0.dtype == torch.float32
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            _lib.check(self._l.mfr_loftr_forward(self._h, _lib.ptr(img0), _lib.ptr(img1),
+                                                 ctypes.c_void_p(self.stream.cuda_stream)), "loftr forward")
+        img0.record_stream(self.stream)
+        img1.record_stream(self.stream)
+
+    def device_outputs(self):
+        """Views of the engine's output buffers (valid until the next forward)."""
+        cap = self.capacity
+        o = self._o
+        return {
+            "m_total": self._wrap(o.m_total, (4,), torch.int32),
+            "m_offsets": self._wrap(o.m_offsets, (self.B + 1,), torch.int32),
+            "b_ids": self._wrap(o.b_ids, (cap,), torch.int32),
+            "i_ids": self._wrap(o.i_ids, (cap,), torch.int32),
+            "j_ids": self._wrap(o.j_ids, (cap,), torch.int32),
+            "mconf": self._wrap(o.mconf, (cap,), torch.float32),
+            "mkpts0_f": self._wrap(o.mkpts0_f, (cap, 2), torch.float32),
+            "mkpts1_f": self._wrap(o.mkpts1_f, (cap, 2), torch.float32),
+            "mkpts1_c": self._wrap(o.mkpts1_c, (cap, 2), torch.float32),
+            "expec_f": self._wrap(o.expec_f, (cap, 3), torch.float32),
+        }
+
+    def forward(self, img0, img1):
+        """Runs the batch and returns the live matches (device tensors, sliced to M)."""
+        self.forward_async(img0, img1)
+        d = self.device_outputs()
+        with torch.cuda.stream(self.stream):
+            self._host_counts[:4].copy_(d["m_total"], non_blocking=True)
+            self._host_counts[4:].copy_(d["m_offsets"], non_blocking=True)
+        self.stream.synchronize()
+        m = int(self._host_counts[0])
+        out = {k: v[:m] for k, v in d.items() if k not in ("m_total", "m_offsets")}
+        out["m_offsets"] = self._host_counts[4:].clone()
+        out["M"] = m
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._l.mfr_loftr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def read_image_gray(path, resize):
+    """Reference image loader (SuperGlue/models/utils.py:263-285 with resize_float=True):
+    grayscale imread, float32 cv2.resize to (W, H), /255 -> float32 [H, W] numpy."""
+    import cv2
+    image = cv2.imread(str(path), cv2.IMREAD_GRAYSCALE)
+    if image is None:
+        return None
+    w_new, h_new = int(resize[0]), int(resize[1])
+    image = cv2.resize(image.astype("float32"), (w_new, h_new))
+    return (image / 255.0).astype(np.float32)
+
+
+def pad_to_8(img):
+    """matchers.py:41-46 quirk kept: pads right/bottom by ``size % 8`` (not the complement) and the
+    test ``inp.size(1) % 8`` looks at the channel axis (=1), so it always fires. img [.., H, W]."""
+    pad_bottom = img.shape[-2] % 8
+    pad_right = img.shape[-1] % 8
+    return torch.nn.functional.pad(img, (0, pad_right, 0, pad_bottom), value=0.0)
+
+
+class LoFTR_matcher:
+    """Drop-in for the reference's offline matcher plugin (matchers.py:12-59). ``weights`` is a
+    reference-format state_dict or a checkpoint path ({'state_dict': ...}); the reference reads
+    LoFTR/weights/{indoor,outdoor}_ot.ckpt, which are not distributed with it."""
+
+    def __init__(self, resize, outdoor=False, weights=None, cfg=None):
+        if weights is None:
+            weights = "LoFTR/weights/outdoor_ot.ckpt" if outdoor else "LoFTR/weights/indoor_ot.ckpt"
+        if isinstance(weights, str):
+            weights = torch.load(weights, map_location="cpu")["state_dict"]
+        self.resize = resize
+        w, h = int(resize[0]), int(resize[1])
+        self.hp, self.wp = h + h % 8, w + w % 8
+        if self.hp % 8 or self.wp % 8:
+            raise ValueError("LoFTR needs a resolution that the reference's padding turns into a multiple of 8")
+        self.engine = LoFTR(weights, batch=1, height=self.hp, width=self.wp, cfg=cfg)
+
+    def match(self, pair_path):
+        im0 = read_image_gray(pair_path[0], self.resize)
+        im1 = read_image_gray(pair_path[1], self.resize)
+        return self.match_arrays(im0, im1)
+
+    def match_arrays(self, im0, im1):
+        dev = self.engine.device
+        t0 = pad_to_8(torch.from_numpy(im0)[None, None].to(dev))
+        t1 = pad_to_8(torch.from_numpy(im1)[None, None].to(dev))
+        out = self.engine.forward(t0, t1)
+        if out["M"] > 0:
+            return torch.cat([out["mkpts0_f"], out["mkpts1_f"]], 1).cpu().numpy()
+        return np.full((1, 4), np.nan)

@@ -1,0 +1,204 @@
+"""Host side of the pose back end. Mirrors the reference's solver plugins
+(lib/models/matching/pose_solver.py): classes with ``__init__(cfg)`` and
+``estimate_pose(kpts0, kpts1, data) -> (R[3,3], t, inliers)``, NaN-filled on failure, while the
+arithmetic runs in the batched-hypothesis CUDA kernels of libmfr_b200.so. ``PoseBackend`` is the
+batched device-resident interface the fused matcher+solver pipeline and the benchmark use.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+
+DEFAULT_NUM_HYP = 2048
+DEFAULT_SEED = 0x5EED
+
+
+def _cfg_get(cfg, path, default=None):
+    cur = cfg
+    for k in path.split("."):
+        try:
+            cur = cur[k] if isinstance(cur, dict) else getattr(cur, k)
+        except (KeyError, AttributeError):
+            return default
+    return default if cur is None else cur
+
+
+class PoseBackend:
+    """Batched GPU pose solver for up to ``max_pairs`` pairs per call."""
+
+    def __init__(self, max_pairs=1, max_pts=8192, max_hyp=8192, device=0):
+        if not torch.cuda.is_available():
+            raise _lib.MfrError("mfr_b200.PoseBackend needs a CUDA device (no CPU fallback)")
+        self._l = _lib.load()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        h = ctypes.c_void_p()
+        _lib.check(self._l.mfr_pose_solver_create(int(max_pairs), int(max_pts), int(max_hyp), ctypes.byref(h)),
+                   "mfr_pose_solver_create")
+        self._h = h
+        self.max_pairs, self.max_pts, self.max_hyp = max_pairs, min(max_pts, 8192), max_hyp
+
+    def _outs(self, P, total):
+        dev = self.device
+        return (torch.empty(P, 3, 3, device=dev), torch.empty(P, 3, device=dev),
+                torch.empty(P, dtype=torch.int32, device=dev), torch.empty(max(total, 1), dtype=torch.uint8, device=dev))
+
+    @staticmethod
+    def _prep(kpts0, kpts1, offsets, K0, K1):
+        assert kpts0.is_cuda and kpts0.dtype == torch.float32 and kpts0.is_contiguous()
+        assert kpts1.is_cuda and kpts1.dtype == torch.float32 and kpts1.is_contiguous()
+        assert offsets.is_cuda and offsets.dtype == torch.int32
+        assert K0.is_cuda and K0.dtype == torch.float32 and K0.is_contiguous()
+        assert K1.is_cuda and K1.dtype == torch.float32 and K1.is_contiguous()
+        return offsets.numel() - 1
+
+    def emat(self, kpts0, kpts1, offsets, K0, K1, pix_thr, num_hyp=DEFAULT_NUM_HYP, seed=DEFAULT_SEED,
+             lo=True, total=None):
+        """EssentialMatrixSolver for P pairs. Returns R [P,3,3], t [P,3] (unit), n [P], mask [total]."""
+        P = self._prep(kpts0, kpts1, offsets, K0, K1)
+        total = kpts0.shape[0] if total is None else total
+        R, t, n, mask = self._outs(P, total)
+        _lib.check(self._l.mfr_emat_ransac(self._h, _lib.ptr(kpts0), _lib.ptr(kpts1), _lib.ptr(offsets), P,
+                                           _lib.ptr(K0), _lib.ptr(K1), float(pix_thr), int(num_hyp),
+                                           ctypes.c_ulonglong(seed), int(bool(lo)), _lib.ptr(R), _lib.ptr(t),
+                                           _lib.ptr(n), _lib.ptr(mask), _lib.cur_stream()), "mfr_emat_ransac")
+        return R, t, n, mask
+
+    def scale(self, kpts0, kpts1, offsets, K0, K1, mask, depth0, depth1, scale_thr, Rd=None, td=None):
+        """Scale-from-depth step of EssentialMatrixMetricSolver (uses the pose kept by ``emat`` when
+        Rd/td are None). depth0/depth1: [P,H,W] float32 CUDA."""
+        P = self._prep(kpts0, kpts1, offsets, K0, K1)
+        H, W = depth0.shape[-2:]
+        R = torch.empty(P, 3, 3, device=self.device)
+        t = torch.empty(P, 3, device=self.device)
+        n = torch.empty(P, dtype=torch.int32, device=self.device)
+        _lib.check(self._l.mfr_scale_from_depth(
+            self._h, _lib.ptr(kpts0), _lib.ptr(kpts1), _lib.ptr(offsets), P, _lib.ptr(K0), _lib.ptr(K1),
+            _lib.ptr(mask), _lib.ptr(Rd), _lib.ptr(td), _lib.ptr(depth0.contiguous()),
+            _lib.ptr(depth1.contiguous()), int(H), int(W), float(scale_thr), _lib.ptr(R), _lib.ptr(t),
+            _lib.ptr(n), _lib.cur_stream()), "mfr_scale_from_depth")
+        return R, t, n
+
+    def emat_metric(self, kpts0, kpts1, offsets, K0, K1, depth0, depth1, pix_thr, scale_thr,
+                    num_hyp=DEFAULT_NUM_HYP, seed=DEFAULT_SEED, lo=True):
+        """EssentialMatrixMetricSolver for P pairs: R [P,3,3], t [P,3] metres, inliers [P]."""
+        _, _, _, mask = self.emat(kpts0, kpts1, offsets, K0, K1, pix_thr, num_hyp, seed, lo)
+        return self.scale(kpts0, kpts1, offsets, K0, K1, mask, depth0, depth1, scale_thr)
+
+    def pnp(self, kpts0, kpts1, offsets, K0, K1, depth0, reproj_thr, num_hyp=DEFAULT_NUM_HYP,
+            seed=DEFAULT_SEED):
+        """PnPSolver for P pairs: R [P,3,3], t [P,3], inliers [P], mask [total]."""
+        P = self._prep(kpts0, kpts1, offsets, K0, K1)
+        H, W = depth0.shape[-2:]
+        R, t, n, mask = self._outs(P, kpts0.shape[0])
+        _lib.check(self._l.mfr_pnp_ransac(self._h, _lib.ptr(kpts0), _lib.ptr(kpts1), _lib.ptr(offsets), P,
+                                          _lib.ptr(K0), _lib.ptr(K1), _lib.ptr(depth0.contiguous()), int(H),
+                                          int(W), int(num_hyp), float(reproj_thr), ctypes.c_ulonglong(seed),
+                                          _lib.ptr(R), _lib.ptr(t), _lib.ptr(n), _lib.ptr(mask),
+                                          _lib.cur_stream()), "mfr_pnp_ransac")
+        return R, t, n, mask
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._l.mfr_pose_solver_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-shaped plugins (one pair per call, host arrays in / host arrays out)
+# ------------------------------------------------------------------------------------------------
+class _SolverBase:
+    def __init__(self, cfg):
+        self.num_hyp = int(_cfg_get(cfg, "GPU_RANSAC.NUM_HYPOTHESES", DEFAULT_NUM_HYP))
+        self.seed = int(_cfg_get(cfg, "GPU_RANSAC.SEED", DEFAULT_SEED))
+        self.lo = bool(_cfg_get(cfg, "GPU_RANSAC.LOCAL_OPTIMISATION", True))
+        self.backend = PoseBackend(max_pairs=1, max_hyp=max(self.num_hyp, 128))
+        self.dev = self.backend.device
+
+    def _upload(self, kpts0, kpts1, data):
+        k0 = torch.as_tensor(np.ascontiguousarray(kpts0, dtype=np.float32)).to(self.dev).reshape(-1, 2)
+        k1 = torch.as_tensor(np.ascontiguousarray(kpts1, dtype=np.float32)).to(self.dev).reshape(-1, 2)
+        off = torch.tensor([0, k0.shape[0]], dtype=torch.int32, device=self.dev)
+        K0 = torch.as_tensor(data["K_color0"]).float().reshape(1, 3, 3).to(self.dev).contiguous()
+        K1 = torch.as_tensor(data["K_color1"]).float().reshape(1, 3, 3).to(self.dev).contiguous()
+        return k0, k1, off, K0, K1
+
+    @staticmethod
+    def _nan():
+        return np.full((3, 3), np.nan), np.full((3, 1), np.nan), 0
+
+
+class EssentialMatrixSolver(_SolverBase):
+    """Relative pose up to scale from 2D-2D correspondences (pose_solver.py:20-61)."""
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.ransac_pix_threshold = float(_cfg_get(cfg, "EMAT_RANSAC.PIX_THRESHOLD"))
+        self.ransac_confidence = _cfg_get(cfg, "EMAT_RANSAC.CONFIDENCE")  # kept for the surface; the
+        # GPU solver runs a fixed hypothesis budget instead of a confidence-driven early exit
+        self.mask = None
+
+    def estimate_pose(self, kpts0, kpts1, data):
+        if len(kpts0) < 5:
+            return self._nan()
+        k0, k1, off, K0, K1 = self._upload(kpts0, kpts1, data)
+        R, t, n, mask = self.backend.emat(k0, k1, off, K0, K1, self.ransac_pix_threshold, self.num_hyp,
+                                          self.seed, self.lo)
+        n = int(n.item())
+        self.mask = mask.cpu().numpy().reshape(-1, 1)
+        self._dev = (k0, k1, off, K0, K1, mask)
+        if n == 0:
+            return self._nan()
+        return R[0].double().cpu().numpy(), t[0].double().cpu().numpy(), n
+
+
+class EssentialMatrixMetricSolver(EssentialMatrixSolver):
+    """E-mat decomposition + scale from depth at the inliers (pose_solver.py:115-172)."""
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.ransac_scale_threshold = float(_cfg_get(cfg, "EMAT_RANSAC.SCALE_THRESHOLD"))
+
+    def estimate_pose(self, kpts0, kpts1, data):
+        R, t, inliers = super().estimate_pose(kpts0, kpts1, data)
+        if inliers == 0:
+            return R, t, inliers
+        k0, k1, off, K0, K1, mask = self._dev
+        d0 = torch.as_tensor(data["depth0"]).float().reshape(1, *torch.as_tensor(data["depth0"]).shape[-2:]).to(self.dev)
+        d1 = torch.as_tensor(data["depth1"]).float().reshape(1, *torch.as_tensor(data["depth1"]).shape[-2:]).to(self.dev)
+        R, t, n = self.backend.scale(k0, k1, off, K0, K1, mask, d0, d1, self.ransac_scale_threshold)
+        n = int(n.item())
+        if n == 0:
+            return self._nan()
+        return R[0].double().cpu().numpy(), t[0].double().cpu().numpy().reshape(3, 1), n
+
+
+class PnPSolver(_SolverBase):
+    """Metric relative pose from 2D-3D correspondences (pose_solver.py:175-235)."""
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.ransac_iterations = _cfg_get(cfg, "PNP.RANSAC_ITER")   # surface only (fixed GPU budget)
+        self.reprojection_inlier_threshold = float(_cfg_get(cfg, "PNP.REPROJECTION_INLIER_THRESHOLD"))
+        self.confidence = _cfg_get(cfg, "PNP.CONFIDENCE")
+
+    def estimate_pose(self, pts0, pts1, data):
+        if len(pts0) < 4:
+            return self._nan()
+        k0, k1, off, K0, K1 = self._upload(pts0, pts1, data)
+        d0 = torch.as_tensor(data["depth0"]).float()
+        d0 = d0.reshape(1, *d0.shape[-2:]).to(self.dev)
+        R, t, n, _ = self.backend.pnp(k0, k1, off, K0, K1, d0, self.reprojection_inlier_threshold,
+                                      self.num_hyp, self.seed)
+        n = int(n.item())
+        if n == 0:
+            return self._nan()
+        return R[0].double().cpu().numpy(), t[0].double().cpu().numpy().reshape(3, 1), n
