@@ -47,8 +47,8 @@ int mfr_conv2d_nhwc_tf32(const float* x, int N, int H, int W, int Cin, long long
  * LoFTR matcher engine. Replaces LoFTR.forward of the reference
  * (etc/feature_matching_baselines/LoFTR/src/loftr/loftr.py:29-75) as driven by
  * LoFTR_matcher.match (etc/feature_matching_baselines/matchers.py:24-59), for B image pairs per
- * call. Images are device fp32 [B][H][W] in [0,1], already padded to multiples of 8
- * (matchers.py:41-46). Weights are set tensor by tensor in the engine's own layout (BN folded,
+ * call. Images are device fp32 [B][src_h][src_w] in [0,1]; the engine frame [H][W] (multiples of 8)
+ * is zero-padded on the right/bottom like the reference's ConstantPad2d (matchers.py:41-46). Weights are set tensor by tensor in the engine's own layout (BN folded,
  * conv weights [Cout][R*S][Cin]); mfr_loftr_weight_name/numel enumerate what is expected.
  * Outputs stay on the device (pointers owned by the engine), ordered by (pair, i) exactly like
  * torch.where in coarse_matching.py:194. */
@@ -70,12 +70,31 @@ int mfr_loftr_num_weights(const mfr_loftr* h);
 const char* mfr_loftr_weight_name(const mfr_loftr* h, int i);
 long long mfr_loftr_weight_numel(const mfr_loftr* h, int i);
 int mfr_loftr_set_weight(mfr_loftr* h, int i, const float* host, long long numel, void* stream);
-int mfr_loftr_forward(mfr_loftr* h, const float* img0, const float* img1, void* stream);
+int mfr_loftr_forward(mfr_loftr* h, const float* img0, const float* img1, int src_h, int src_w,
+                      void* stream);
 void mfr_loftr_set_graph(mfr_loftr* h, int enabled);
 int mfr_loftr_get_outputs(mfr_loftr* h, mfr_loftr_outputs* out);
 /* named intermediate buffers for stage-wise parity tests ("feat_c_backbone", "feat_f", "tok", "sim", ...) */
 int mfr_loftr_debug_tensor(mfr_loftr* h, const char* name, float** ptr, long long* numel);
-int mfr_loftr_num_kernels(const mfr_loftr* h); /* launches per forward (steps of the launch list) */
+int mfr_loftr_num_kernels(const mfr_loftr* h);  /* steps of the launch list per forward */
+int mfr_loftr_num_launches(const mfr_loftr* h); /* kernel launches per forward */
+/* Eager run with a CUDA-event pair around every step of the launch list (host arrays out):
+ * ms[i] device time, flops[i] algorithmic FLOPs, kinds[i] 1 = tcgen05 conv/GEMM, names 32 bytes each.
+ * Returns the number of steps (or a negative MFR_ERR_*). */
+int mfr_loftr_profile(mfr_loftr* h, const float* img0, const float* img1, int src_h, int src_w,
+                      void* stream, int max_steps, float* ms, double* flops, int* kinds, char* names);
+
+/* Coarse matching on a materialised matrix (stage-boundary entry point of the LoFTR matcher):
+ * CoarseMatching.forward dual-softmax + get_coarse_match of the reference
+ * (LoFTR/src/loftr/utils/coarse_matching.py:109-119,175-196,242-259).
+ *   sim: device float[B][L][L] similarity (already scaled by 1/(C*temperature)), or, when
+ *   input_is_conf != 0, the confidence matrix itself (then the selection is bit-exact w.r.t. the
+ *   reference's float-equality mutual-NN test on the same matrix).
+ * Outputs (device, caller-owned): count int[1], offsets int[B+1], b/i/j_ids int[B*L],
+ * mconf float[B*L], mkpts0_c/mkpts1_c float[B*L][2] = (idx % w_c, idx / w_c) * scale. */
+int mfr_coarse_match(const float* sim, int B, int h_c, int w_c, float thr, int border_rm, float scale,
+                     int input_is_conf, int* count, int* offsets, int* b_ids, int* i_ids, int* j_ids,
+                     float* mconf, float* mkpts0_c, float* mkpts1_c, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Pose back end (batched-hypothesis RANSAC). Replaces lib/models/matching/pose_solver.py.
@@ -129,6 +148,13 @@ int mfr_host_five_point(const double* x0, const double* x1, double* E_out);
 int mfr_host_p3p(const double* X, const double* f, double* R_out, double* t_out);
 int mfr_host_poly_real_roots(const double* coef, int deg, double* roots);
 int mfr_host_decompose_essential(const double* E, double* R1, double* R2, double* t);
+
+/* Debug probes (microbenchmarks used by scripts/, not part of the product path): microseconds per
+ * launch of an empty / TMEM-allocating kernel with the GEMM's launch shape, and of a prebuilt
+ * conv/GEMM op launched back to back. */
+float mfr_debug_probe_overhead(int mode, int smem_bytes, int grid, int iters);
+float mfr_debug_time_conv(const float* x, int N, int H, int W, int Cin, const float* w, int Cout, int R,
+                          int stride, float* out, int iters);
 
 #ifdef __cplusplus
 }

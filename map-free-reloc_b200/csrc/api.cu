@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "conv_gemm.cuh"
 #include "loftr_engine.cuh"
+#include "loftr_ops.cuh"
 #include "geometry_solvers.cuh"
 #include "geometry.cuh"
 
@@ -54,8 +55,8 @@ long long mfr_loftr_weight_numel(const mfr_loftr* h, int i) { return mfr::loftr_
 int mfr_loftr_set_weight(mfr_loftr* h, int i, const float* host, long long numel, void* stream) {
   return mfr::loftr_set_weight(h->e, i, host, numel, static_cast<cudaStream_t>(stream));
 }
-int mfr_loftr_forward(mfr_loftr* h, const float* img0, const float* img1, void* stream) {
-  return mfr::loftr_forward(h->e, img0, img1, static_cast<cudaStream_t>(stream));
+int mfr_loftr_forward(mfr_loftr* h, const float* img0, const float* img1, int src_h, int src_w, void* stream) {
+  return mfr::loftr_forward(h->e, img0, img1, src_h, src_w, static_cast<cudaStream_t>(stream));
 }
 void mfr_loftr_set_graph(mfr_loftr* h, int enabled) { mfr::loftr_set_graph(h->e, enabled); }
 int mfr_loftr_get_outputs(mfr_loftr* h, mfr_loftr_outputs* out) {
@@ -70,6 +71,38 @@ int mfr_loftr_debug_tensor(mfr_loftr* h, const char* name, float** ptr, long lon
   return mfr::loftr_debug_tensor(h->e, name, ptr, numel);
 }
 int mfr_loftr_num_kernels(const mfr_loftr* h) { return mfr::loftr_num_steps(h->e); }
+int mfr_loftr_num_launches(const mfr_loftr* h) { return mfr::loftr_num_launches(h->e); }
+int mfr_loftr_profile(mfr_loftr* h, const float* img0, const float* img1, int src_h, int src_w, void* stream,
+                      int max_steps, float* ms, double* flops, int* kinds, char* names) {
+  return mfr::loftr_profile(h->e, img0, img1, src_h, src_w, static_cast<cudaStream_t>(stream), max_steps, ms, flops,
+                            kinds, names);
+}
+
+int mfr_coarse_match(const float* sim, int B, int h_c, int w_c, float thr, int border_rm, float scale,
+                     int input_is_conf, int* count, int* offsets, int* b_ids, int* i_ids, int* j_ids,
+                     float* mconf, float* mkpts0_c, float* mkpts1_c, void* stream) {
+  if (!sim || B < 1 || h_c < 1 || w_c < 1) return MFR_ERR_ARG;
+  const int L = h_c * w_c, splits = 32;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mfr::CoarseMatchBuffers b;
+  int rc = mfr::coarse_match_alloc(B, L, splits, &b);
+  if (rc != MFR_OK) return rc;
+  rc = mfr::coarse_match(sim, b, B, L, h_c, w_c, thr, border_rm, scale, splits, st, input_is_conf != 0);
+  const size_t BL = static_cast<size_t>(B) * L;
+  if (rc == MFR_OK) {
+    cudaMemcpyAsync(count, b.m_total, 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(offsets, b.m_offsets, (B + 1) * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(b_ids, b.b_ids, BL * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(i_ids, b.i_ids, BL * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(j_ids, b.j_ids, BL * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(mconf, b.mconf, BL * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(mkpts0_c, b.mkpts0_c, BL * 8, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(mkpts1_c, b.mkpts1_c, BL * 8, cudaMemcpyDeviceToDevice, st);
+  }
+  cudaStreamSynchronize(st);
+  mfr::coarse_match_free(&b);
+  return rc;
+}
 
 // ------------------------------------------------------------------------------------------ pose back end
 struct mfr_pose_solver { mfr::PoseSolver* s; };
@@ -125,6 +158,21 @@ int mfr_host_poly_real_roots(const double* coef, int deg, double* roots) {
 int mfr_host_decompose_essential(const double* E, double* R1, double* R2, double* t) {
   mfr::geo::decompose_essential(E, R1, R2, t);
   return MFR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ debug probes
+float mfr_debug_probe_overhead(int mode, int smem_bytes, int grid, int iters) {
+  return mfr::conv_gemm_probe_overhead(mode, smem_bytes, grid, iters, nullptr);
+}
+float mfr_debug_time_conv(const float* x, int N, int H, int W, int Cin, const float* w, int Cout, int R,
+                          int stride, float* out, int iters) {
+  mfr::ConvGemmDesc d{};
+  d.x = x; d.N = N; d.H = H; d.W = W; d.Cin = Cin; d.ldx = Cin;
+  d.w = w; d.Cout = Cout; d.R = R; d.S = R; d.stride = stride; d.pad = R / 2;
+  d.act = 1; d.alpha = 1.f; d.out = out; d.ldo = Cout; d.ldr = Cout;
+  mfr::ConvGemmParams p;
+  if (mfr::conv_gemm_build(d, &p) != MFR_OK) return -1.f;
+  return mfr::conv_gemm_time_prebuilt(p, iters, nullptr);
 }
 
 }  // extern "C"

@@ -31,6 +31,13 @@ constexpr int kSmemBytes = kStages * (kAStage + kBStage) + 1024 /*align slack*/;
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
 
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define MFR_STAMP(i) do { if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[i] = gtime(); } while (0)
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.f);
   if (act == ACT_LEAKY) return v > 0.f ? v : 0.01f * v;
@@ -55,6 +62,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) MFR_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -77,6 +85,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  if (threadIdx.x == 0) MFR_STAMP(1);
 
   int w_lim = p.Wo, tiles_x = p.tiles_x;
   if (p.dyn_w != nullptr) {
@@ -110,6 +119,8 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
                       y_in0 + ky, img);
           tma_load_3d(smem_b + stage * kBStage, &p.tmB, full_bar(stage), cb * kBlockK,
                       p.b_batched ? img : tap, n0);
+          if (kb == 0 && tile == static_cast<int>(blockIdx.x)) MFR_STAMP(2);
+          if (kb == num_kb - 1 && tile == static_cast<int>(blockIdx.x)) MFR_STAMP(3);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -130,6 +141,8 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase, 3);
           tc_fence_after();
+          if (kb == 0 && it == 0) MFR_STAMP(4);
+          if (kb == num_kb - 1 && it == 0) MFR_STAMP(5);
           const uint32_t a_addr = smem_a + stage * kAStage;
           const uint32_t b_addr = smem_b + stage * kBStage;
 #pragma unroll
@@ -170,6 +183,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
 
       mbar_wait(tfull_bar(acc), acc_phase, 4);
       tc_fence_after();
+      if (it == 0 && threadIdx.x == 64) MFR_STAMP(6);
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxBN) +
                              (static_cast<uint32_t>(q * 32) << 16);
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
@@ -219,6 +233,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (it == 0 && threadIdx.x == 64) MFR_STAMP(7);
     }
   }
 
@@ -228,6 +243,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (threadIdx.x == 0) MFR_STAMP(8);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -327,6 +343,7 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
   p->ldr = d.ldr;
   p->out = d.out;
   p->ldo = d.ldo;
+  p->dbg = nullptr;
 
   {  // activations: {C, W, H, N}
     cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};
@@ -384,6 +401,84 @@ int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream) {
   conv_gemm_tf32_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch-overhead probes (debug): same launch shape as the GEMM kernel, progressively more set-up
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(kThreads, 1) overhead_probe_kernel(int mode, int* sink) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_bars[2 * kStages + 4];
+  __shared__ uint32_t s_tmem_base;
+  if (mode == 0) return;
+  const int warp = threadIdx.x >> 5;
+  if (mode >= 2 && threadIdx.x == 0) {
+    for (int s = 0; s < 2 * kStages + 4; ++s) mbar_init(smem_u32(s_bars) + 8u * s, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&s_tmem_base), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (mode >= 3 && threadIdx.x == 0 && sink != nullptr) smem_raw[0] = static_cast<uint8_t>(*sink);
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(s_tmem_base, kTmemCols);
+}
+}  // namespace
+
+float conv_gemm_probe_overhead(int mode, int smem_bytes, int grid, int iters, cudaStream_t st) {
+  cudaFuncSetAttribute(overhead_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int i = 0; i < 5; ++i) overhead_probe_kernel<<<grid, kThreads, smem_bytes, st>>>(mode, nullptr);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters; ++i) overhead_probe_kernel<<<grid, kThreads, smem_bytes, st>>>(mode, nullptr);
+  cudaEventRecord(e1, st);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return ms * 1000.f / iters;
+}
+
+float conv_gemm_time_prebuilt(const ConvGemmParams& p, int iters, cudaStream_t st) {
+  {  // one instrumented launch: milestone stamps of block 0
+    long long* d = nullptr;
+    cudaMalloc(&d, 16 * sizeof(long long));
+    cudaMemset(d, 0, 16 * sizeof(long long));
+    ConvGemmParams q = p;
+    q.dbg = d;
+    conv_gemm_launch(q, st);
+    conv_gemm_launch(q, st);
+    cudaStreamSynchronize(st);
+    long long h[16];
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    const char* names[9] = {"start", "setup done", "first TMA issued", "last TMA issued", "first stage landed",
+                            "last stage landed", "accumulator ready", "epilogue done", "exit"};
+    fprintf(stderr, "[conv_gemm stamps, block 0, ns since start]");
+    for (int i = 0; i < 9; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] ? h[i] - h[0] : -1);
+    fprintf(stderr, "\n");
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int i = 0; i < 5; ++i) conv_gemm_launch(p, st);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters; ++i) conv_gemm_launch(p, st);
+  cudaEventRecord(e1, st);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return ms * 1000.f / iters;
 }
 
 }  // namespace mfr

@@ -28,6 +28,7 @@ struct alignas(64) ConvGemmParams {
   const float* residual;
   float* out;
   long long ldr, ldo;
+  long long* dbg;       // optional: block 0 writes globaltimer stamps (ns) at pipeline milestones
 };
 
 // Describes one op; build once (tensor maps are encoded on the host), launch many times.
@@ -53,5 +54,7 @@ struct ConvGemmDesc {
 int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p);
 int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream);
 int conv_gemm_num_sms();
+float conv_gemm_probe_overhead(int mode, int smem_bytes, int grid, int iters, cudaStream_t st);
+float conv_gemm_time_prebuilt(const ConvGemmParams& p, int iters, cudaStream_t st);
 
 }  // namespace mfr

@@ -296,9 +296,132 @@ __device__ inline bool solve_damped(const double* H, const double* g, double lam
 }
 
 // ================================================================================================
-// essential matrix: best-of-blocks, local optimisation, cheirality, final mask
+// essential matrix: top-K block winners -> local optimisation -> best final model, cheirality, mask
 // ================================================================================================
-constexpr int kLoOuter = 4, kLoInner = 6;
+constexpr int kLoRounds = 6, kLoInner = 5, kLoTopK = 4, kTightRounds = 3;
+
+struct EmatShared {
+  double R[9], t[3], E[9], prevR[9], prevt[3], H[25], g[5];
+  double bestR[9], bestt[3], best_cost;
+  double c_R1[9], c_R2[9], c_t[3];
+  double prev_cost, lambda;
+  double red[8 * 21];
+  int hist[256];
+  int cand[kLoTopK];
+  int ncand, cnt;
+};
+
+// LM rounds on the Tukey-biweight M-estimator of the Sampson distance with cut-off sqrt(T2),
+// starting from (S.R, S.t); leaves the last accepted parameters there. All threads must call it.
+__device__ void emat_lm_round(EmatShared& S, const float4* pts, int N, double T2) {
+  if (threadIdx.x == 0) { S.lambda = 1e-6; S.prev_cost = 1e300; }
+  __syncthreads();
+  for (int it = 0; it <= kLoInner; ++it) {
+    double R[9], t[3], b1[3], b2[3];
+    for (int k = 0; k < 9; ++k) R[k] = S.R[k];
+    for (int k = 0; k < 3; ++k) t[k] = S.t[k];
+    tangent_basis(t, b1, b2);
+    double acc[21];
+    for (int k = 0; k < 21; ++k) acc[k] = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      double J[5];
+      const double r = sampson_res_jac(R, t, b1, b2, pts[i], J);
+      const double q = r * r / T2;
+      if (q < 1.0) {
+        const double u = 1.0 - q, w = u * u;
+        int qq = 0;
+        for (int a = 0; a < 5; ++a)
+          for (int b = a; b < 5; ++b) acc[qq++] += w * J[a] * J[b];
+        for (int a = 0; a < 5; ++a) acc[15 + a] += w * J[a] * r;
+        acc[20] += (1.0 - u * u * u);
+      } else {
+        acc[20] += 1.0;
+      }
+    }
+    block_sum_256<21>(acc, S.red);
+    if (threadIdx.x == 0) {
+      const double cost = acc[20];
+      if (cost <= S.prev_cost) {  // accept the parameters that produced this pass
+        S.prev_cost = cost;
+        for (int k = 0; k < 9; ++k) S.prevR[k] = S.R[k];
+        for (int k = 0; k < 3; ++k) S.prevt[k] = S.t[k];
+        int q = 0;
+        for (int a = 0; a < 5; ++a)
+          for (int b = a; b < 5; ++b) { S.H[a * 5 + b] = acc[q]; S.H[b * 5 + a] = acc[q]; ++q; }
+        for (int a = 0; a < 5; ++a) S.g[a] = acc[15 + a];
+        S.lambda = fmax(S.lambda * 0.1, 1e-12);
+      } else {                    // reject: back to the last accepted point, more damping
+        S.lambda *= 10.0;
+      }
+      double d[5], pb1[3], pb2[3];
+      tangent_basis(S.prevt, pb1, pb2);
+      if (it < kLoInner && solve_damped(S.H, S.g, S.lambda, 5, d)) {
+        double dR[9], Rn[9], tn[3];
+        so3_exp(d, dR);
+        mat3_mul(dR, S.prevR, Rn);
+        for (int k = 0; k < 3; ++k) tn[k] = S.prevt[k] + d[3] * pb1[k] + d[4] * pb2[k];
+        const double nn = norm3(tn);
+        for (int k = 0; k < 9; ++k) S.R[k] = Rn[k];
+        for (int k = 0; k < 3; ++k) S.t[k] = tn[k] / nn;
+      } else {
+        for (int k = 0; k < 9; ++k) S.R[k] = S.prevR[k];
+        for (int k = 0; k < 3; ++k) S.t[k] = S.prevt[k];
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 9; ++k) S.R[k] = S.prevR[k];
+    for (int k = 0; k < 3; ++k) S.t[k] = S.prevt[k];
+  }
+  __syncthreads();
+}
+
+// (R, t) <- the decomposition of S.E with the most points in front of both cameras among the
+// correspondences with Sampson^2 < thr2 (cv.recoverPose's vote). S.cnt = that count.
+__device__ void emat_choose_pose(EmatShared& S, const float4* pts, int N, double thr2) {
+  if (threadIdx.x == 0) decompose_essential(S.E, S.c_R1, S.c_R2, S.c_t);
+  __syncthreads();
+  double cnt[4] = {0, 0, 0, 0};
+  const double tn[3] = {-S.c_t[0], -S.c_t[1], -S.c_t[2]};
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float4 p = pts[i];
+    if (sampson_sq(S.E, p.x, p.y, p.z, p.w) < thr2) {
+      cnt[0] += cheirality_ok(S.c_R1, S.c_t, p) ? 1.0 : 0.0;
+      cnt[1] += cheirality_ok(S.c_R2, S.c_t, p) ? 1.0 : 0.0;
+      cnt[2] += cheirality_ok(S.c_R1, tn, p) ? 1.0 : 0.0;
+      cnt[3] += cheirality_ok(S.c_R2, tn, p) ? 1.0 : 0.0;
+    }
+  }
+  block_sum_256<4>(cnt, S.red);
+  if (threadIdx.x == 0) {
+    int b = 0;
+    for (int k = 1; k < 4; ++k)
+      if (cnt[k] > cnt[b]) b = k;
+    const double* Rb = (b == 0 || b == 2) ? S.c_R1 : S.c_R2;
+    for (int k = 0; k < 9; ++k) S.R[k] = Rb[k];
+    for (int k = 0; k < 3; ++k) S.t[k] = (b < 2) ? S.c_t[k] : -S.c_t[k];
+    S.cnt = static_cast<int>(cnt[b] + 0.5);
+  }
+  __syncthreads();
+}
+
+// MSAC cost (sum of min(d^2, thr2)) of the model (S.R, S.t); result broadcast to all threads
+__device__ double emat_msac(EmatShared& S, const float4* pts, int N, double thr2) {
+  double E[9];
+  essential_from_rt(S.R, S.t, E);
+  double c[1] = {0.0};
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float4 p = pts[i];
+    c[0] += fmin(sampson_sq(E, p.x, p.y, p.z, p.w), thr2);
+  }
+  block_sum_256<1>(c, S.red);
+  if (threadIdx.x == 0) S.prev_cost = c[0];
+  __syncthreads();
+  const double r = S.prev_cost;
+  __syncthreads();
+  return r;
+}
 
 __global__ void __launch_bounds__(256) emat_final_kernel(
     const float* __restrict__ kpts0, const float* __restrict__ kpts1, const int* __restrict__ offsets,
@@ -307,11 +430,7 @@ __global__ void __launch_bounds__(256) emat_final_kernel(
     float* __restrict__ Rf, float* __restrict__ tf, int* __restrict__ n_inl,
     unsigned char* __restrict__ mask, int lo_enabled) {
   extern __shared__ float4 s_pts[];
-  __shared__ double sh_red[8 * 21];
-  __shared__ double s_R[9], s_t[3], s_E[9], s_Eo[9], s_prevR[9], s_prevt[3], s_H[25], s_g[5];
-  __shared__ double s_prev_cost, s_lambda;
-  __shared__ int s_flag, s_cnt[4];
-  __shared__ double c_R1[9], c_R2[9], c_t[3];
+  __shared__ EmatShared S;
   const int pair = blockIdx.x;
   const int n0 = offsets[pair];
   const int Nall = offsets[pair + 1] - n0;
@@ -330,138 +449,111 @@ __global__ void __launch_bounds__(256) emat_final_kernel(
   for (int i = threadIdx.x; i < N; i += blockDim.x) s_pts[i] = normalise_pt(k0, k1, i, K0, K1);
   const double thr = static_cast<double>(emat_threshold(pix_thr, K0, K1));
   const double thr2 = thr * thr;
+  const HypResult* res = results + static_cast<size_t>(pair) * blocks_per_pair;
   if (threadIdx.x == 0) {
-    const HypResult* r = results + static_cast<size_t>(pair) * blocks_per_pair;
-    int b = -1;
-    for (int k = 0; k < blocks_per_pair; ++k)
-      if (r[k].valid && (b < 0 || r[k].cost < r[b].cost)) b = k;
-    s_flag = b;
-    if (b >= 0)
-      for (int k = 0; k < 9; ++k) s_E[k] = r[b].model[k];
+    // the kLoTopK cheapest block winners, cheapest first
+    int n = 0;
+    for (int k = 0; k < blocks_per_pair; ++k) {
+      if (!res[k].valid) continue;
+      int pos = n < kLoTopK ? n : kLoTopK;
+      while (pos > 0 && res[S.cand[pos - 1]].cost > res[k].cost) --pos;
+      if (pos >= kLoTopK) continue;
+      const int last = n < kLoTopK ? n : kLoTopK - 1;
+      for (int q = last; q > pos; --q) S.cand[q] = S.cand[q - 1];
+      S.cand[pos] = k;
+      if (n < kLoTopK) ++n;
+    }
+    S.ncand = n;
+    S.best_cost = 1e300;
   }
   __syncthreads();
-  if (s_flag < 0) { fail(); return; }
+  if (S.ncand == 0) { fail(); return; }
 
-  // ---- pick (R, t) among the four decompositions by cheirality over the inliers of E
-  auto choose_pose = [&]() {
-    if (threadIdx.x == 0) decompose_essential(s_E, c_R1, c_R2, c_t);
+  const int ncand = lo_enabled ? S.ncand : 1;
+  for (int c = 0; c < ncand; ++c) {
+    if (threadIdx.x == 0)
+      for (int k = 0; k < 9; ++k) S.E[k] = res[S.cand[c]].model[k];
     __syncthreads();
-    double cnt[4] = {0, 0, 0, 0};
-    double tn[3] = {-c_t[0], -c_t[1], -c_t[2]};
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-      const float4 p = s_pts[i];
-      if (sampson_sq(s_E, p.x, p.y, p.z, p.w) < thr2) {
-        cnt[0] += cheirality_ok(c_R1, c_t, p) ? 1.0 : 0.0;
-        cnt[1] += cheirality_ok(c_R2, c_t, p) ? 1.0 : 0.0;
-        cnt[2] += cheirality_ok(c_R1, tn, p) ? 1.0 : 0.0;
-        cnt[3] += cheirality_ok(c_R2, tn, p) ? 1.0 : 0.0;
-      }
+    emat_choose_pose(S, s_pts, N, thr2);
+    if (lo_enabled) {
+      // cut-off shrinking from 3x to 1x the RANSAC threshold
+      const double sched[kLoRounds] = {3.0, 2.0, 1.5, 1.0, 1.0, 1.0};
+      for (int r = 0; r < kLoRounds; ++r) emat_lm_round(S, s_pts, N, sched[r] * sched[r] * thr2);
     }
-    block_sum_256<4>(cnt, sh_red);
-    if (threadIdx.x == 0) {
-      int b = 0;
-      for (int k = 1; k < 4; ++k)
-        if (cnt[k] > cnt[b]) b = k;
-      const double* Rb = (b == 0 || b == 2) ? c_R1 : c_R2;
-      for (int k = 0; k < 9; ++k) s_R[k] = Rb[k];
-      for (int k = 0; k < 3; ++k) s_t[k] = (b < 2) ? c_t[k] : -c_t[k];
-      s_cnt[0] = static_cast<int>(cnt[b] + 0.5);
+    const double cost = emat_msac(S, s_pts, N, thr2);
+    if (threadIdx.x == 0 && cost < S.best_cost) {
+      S.best_cost = cost;
+      for (int k = 0; k < 9; ++k) S.bestR[k] = S.R[k];
+      for (int k = 0; k < 3; ++k) S.bestt[k] = S.t[k];
     }
     __syncthreads();
-  };
-  choose_pose();
-
-  // ---- local optimisation: LM on the Sampson error over the inliers of the current model
-  if (lo_enabled) {
-    for (int outer = 0; outer < kLoOuter; ++outer) {
-      if (threadIdx.x == 0) {
-        essential_from_rt(s_R, s_t, s_Eo);   // the model that defines this round's inlier set
-        s_lambda = 1e-6;
-        s_prev_cost = 1e300;
-      }
-      __syncthreads();
-      for (int it = 0; it <= kLoInner; ++it) {
-        double R[9], t[3], b1[3], b2[3];
-        for (int k = 0; k < 9; ++k) R[k] = s_R[k];
-        for (int k = 0; k < 3; ++k) t[k] = s_t[k];
-        tangent_basis(t, b1, b2);
-        double acc[21];
-        for (int k = 0; k < 21; ++k) acc[k] = 0.0;
-        for (int i = threadIdx.x; i < N; i += blockDim.x) {
-          const float4 p = s_pts[i];
-          if (!(sampson_sq(s_Eo, p.x, p.y, p.z, p.w) < thr2)) continue;
-          double J[5];
-          const double r = sampson_res_jac(R, t, b1, b2, p, J);
-          int q = 0;
-          for (int a = 0; a < 5; ++a)
-            for (int b = a; b < 5; ++b) acc[q++] += J[a] * J[b];
-          for (int a = 0; a < 5; ++a) acc[15 + a] += J[a] * r;
-          acc[20] += r * r;
-        }
-        block_sum_256<21>(acc, sh_red);
-        if (threadIdx.x == 0) {
-          const double cost = acc[20];
-          if (cost <= s_prev_cost) {  // accept the parameters that produced this pass
-            s_prev_cost = cost;
-            for (int k = 0; k < 9; ++k) s_prevR[k] = s_R[k];
-            for (int k = 0; k < 3; ++k) s_prevt[k] = s_t[k];
-            int q = 0;
-            for (int a = 0; a < 5; ++a)
-              for (int b = a; b < 5; ++b) { s_H[a * 5 + b] = acc[q]; s_H[b * 5 + a] = acc[q]; ++q; }
-            for (int a = 0; a < 5; ++a) s_g[a] = acc[15 + a];
-            s_lambda = fmax(s_lambda * 0.1, 1e-12);
-          } else {                    // reject: back to the last accepted point, more damping
-            s_lambda *= 10.0;
-          }
-          double d[5];
-          double pb1[3], pb2[3];
-          tangent_basis(s_prevt, pb1, pb2);
-          if (it < kLoInner && solve_damped(s_H, s_g, s_lambda, 5, d)) {
-            double dR[9], Rn[9];
-            so3_exp(d, dR);
-            mat3_mul(dR, s_prevR, Rn);
-            double tn[3];
-            for (int k = 0; k < 3; ++k) tn[k] = s_prevt[k] + d[3] * pb1[k] + d[4] * pb2[k];
-            const double nn = norm3(tn);
-            for (int k = 0; k < 9; ++k) s_R[k] = Rn[k];
-            for (int k = 0; k < 3; ++k) s_t[k] = tn[k] / nn;
-          } else {
-            for (int k = 0; k < 9; ++k) s_R[k] = s_prevR[k];
-            for (int k = 0; k < 3; ++k) s_t[k] = s_prevt[k];
-          }
-        }
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) {  // leave the round at the last accepted parameters
-        for (int k = 0; k < 9; ++k) s_R[k] = s_prevR[k];
-        for (int k = 0; k < 3; ++k) s_t[k] = s_prevt[k];
-      }
-      __syncthreads();
-    }
   }
-  if (threadIdx.x == 0) essential_from_rt(s_R, s_t, s_E);
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 9; ++k) S.R[k] = S.bestR[k];
+    for (int k = 0; k < 3; ++k) S.t[k] = S.bestt[k];
+  }
+  __syncthreads();
+  if (lo_enabled) {
+    // noise-adaptive tightening: robust scale of the inlier residuals (1.4826 * median |r|), cut-off
+    // = clamp(3 sigma, ., thr). With clean data this discards chance near-threshold outliers that a
+    // fixed cut-off keeps (the sigma-consensus idea of MAGSAC++).
+    for (int round = 0; round < kTightRounds; ++round) {
+      for (int k = threadIdx.x; k < 256; k += blockDim.x) S.hist[k] = 0;
+      __syncthreads();
+      double E[9];
+      essential_from_rt(S.R, S.t, E);
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float4 p = s_pts[i];
+        const double d2 = sampson_sq(E, p.x, p.y, p.z, p.w);
+        if (d2 < thr2) atomicAdd(&S.hist[min(255, static_cast<int>(sqrt(d2 / thr2) * 256.0))], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < 256; ++k) tot += S.hist[k];
+        int acc = 0, med = 255;
+        for (int k = 0; k < 256; ++k) {
+          acc += S.hist[k];
+          if (2 * acc >= tot) { med = k; break; }
+        }
+        const double sigma = 1.4826 * (med + 1) / 256.0 * thr;
+        S.lambda = fmin(thr, fmax(3.0 * sigma, 0.02 * thr));  // cut-off for this round
+      }
+      __syncthreads();
+      const double T = S.lambda;
+      __syncthreads();
+      emat_lm_round(S, s_pts, N, T * T);
+    }
+    // safeguard: keep the pre-tightening model if tightening made the MSAC cost at thr worse by > 2 %
+    const double cost = emat_msac(S, s_pts, N, thr2);
+    if (threadIdx.x == 0 && cost > 1.02 * S.best_cost) {
+      for (int k = 0; k < 9; ++k) S.R[k] = S.bestR[k];
+      for (int k = 0; k < 3; ++k) S.t[k] = S.bestt[k];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) essential_from_rt(S.R, S.t, S.E);
   __syncthreads();
   // ---- final mask: Sampson^2 < thr^2 under the final E (what cv.findEssentialMat returns), then
   // the cheirality filter that cv.recoverPose applies to the mask in place (pose_solver.py:57)
-  choose_pose();
+  emat_choose_pose(S, s_pts, N, thr2);
   double cnt[1] = {0.0};
   for (int i = threadIdx.x; i < Nall; i += blockDim.x) {
     unsigned char m = 0;
     if (i < N) {
       const float4 p = s_pts[i];
-      if (sampson_sq(s_E, p.x, p.y, p.z, p.w) < thr2 && cheirality_ok(s_R, s_t, p)) m = 1;
+      if (sampson_sq(S.E, p.x, p.y, p.z, p.w) < thr2 && cheirality_ok(S.R, S.t, p)) m = 1;
     }
     mask[n0 + i] = m;
     cnt[0] += m;
   }
-  block_sum_256<1>(cnt, sh_red);
-  const int n = static_cast<int>(cnt[0] + 0.5);
-  if (threadIdx.x == 0) s_cnt[1] = n;
+  block_sum_256<1>(cnt, S.red);
+  if (threadIdx.x == 0) S.cnt = static_cast<int>(cnt[0] + 0.5);
   __syncthreads();
-  if (s_cnt[1] == 0) { fail(); return; }
-  if (threadIdx.x < 9) { Rd[9 * pair + threadIdx.x] = s_R[threadIdx.x]; Rf[9 * pair + threadIdx.x] = static_cast<float>(s_R[threadIdx.x]); }
-  if (threadIdx.x < 3) { td[3 * pair + threadIdx.x] = s_t[threadIdx.x]; tf[3 * pair + threadIdx.x] = static_cast<float>(s_t[threadIdx.x]); }
-  if (threadIdx.x == 0) n_inl[pair] = s_cnt[1];
+  if (S.cnt == 0) { fail(); return; }
+  if (threadIdx.x < 9) { Rd[9 * pair + threadIdx.x] = S.R[threadIdx.x]; Rf[9 * pair + threadIdx.x] = static_cast<float>(S.R[threadIdx.x]); }
+  if (threadIdx.x < 3) { td[3 * pair + threadIdx.x] = S.t[threadIdx.x]; tf[3 * pair + threadIdx.x] = static_cast<float>(S.t[threadIdx.x]); }
+  if (threadIdx.x == 0) n_inl[pair] = S.cnt;
 }
 
 // ================================================================================================

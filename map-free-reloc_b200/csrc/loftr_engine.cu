@@ -27,12 +27,21 @@ struct DebugTensor {
   long long numel;
 };
 
+struct StepInfo {
+  std::string name;
+  int kind;             // 1 = tcgen05 conv/GEMM launch, 0 = SIMT kernel(s)
+  double flops;         // algorithmic FLOPs (static part); for dyn steps: FLOPs per live row
+  const int* dyn_rows;  // device row count (per image) or null
+  int dyn_images;
+  int launches = 1;     // kernels this step launches
+};
+
 struct LoftrEngine {
   int B, H, W, NI;
   int H2, W2, H4, W4, H8, W8, L, Mcap;
   float thr, temperature;
   int border;
-  int splits_kv = 16, splits_col = 32;
+  int splits_kv = 96, splits_col = 32;
 
   std::vector<WeightSpec> specs;
   std::map<std::string, size_t> spec_index;
@@ -43,6 +52,13 @@ struct LoftrEngine {
   std::vector<void*> allocs;
   std::map<std::string, DebugTensor> dbg;
   std::vector<std::function<int(cudaStream_t)>> steps;
+  std::vector<StepInfo> infos;
+  void push(const std::string& name, std::function<int(cudaStream_t)> f, int launches = 1) {
+    steps.push_back(std::move(f));
+    StepInfo inf{name, 0, 0.0, nullptr, 0};
+    inf.launches = launches;
+    infos.push_back(inf);
+  }
   // buffers
   float* img = nullptr;
   float *a0, *a1, *a2, *b0, *b1, *b2, *c0, *c1, *c2, *fc, *p4a, *p4b, *p4c, *p2a, *p2b;
@@ -100,6 +116,14 @@ struct LoftrEngine {
     int rc = conv_gemm_build(d, &p);
     if (rc != MFR_OK) { build_rc = rc; return; }
     steps.push_back([p](cudaStream_t st) { return conv_gemm_launch(p, st); });
+    StepInfo inf;
+    inf.name = wname.empty() ? "qkv" : wname;
+    inf.kind = 1;
+    inf.dyn_rows = dyn_w;
+    inf.dyn_images = N;
+    const double per_pixel = 2.0 * Cout * Cin * R * R;
+    inf.flops = dyn_w ? per_pixel : per_pixel * N * p.Ho * p.Wo;
+    infos.push_back(inf);
   }
 
   void specs_backbone() {
@@ -162,16 +186,16 @@ struct LoftrEngine {
     if (!windows) {
       float* kvp_ = kvp; float* kv_ = kv;
       const int Lr = rows, sk = splits_kv;
-      steps.push_back([=](cudaStream_t st) {
+      push("simt", [=](cudaStream_t st) {
         return linear_attention_long(qkv_x, ld3, qkv_s + C, ld3, qkv_s + 2 * C, ld3, msg_x, C, kvp_, kv_, n,
                                      Lr, Lr, 8, 32, sk, st);
-      });
+      }, 3);
     } else {
       const int items_cap = rows / 25;
       for (int side = 0; side < n; ++side) {
         const size_t off3 = static_cast<size_t>(side) * rows * ld3;
         const size_t off1 = static_cast<size_t>(side) * rows * C;
-        steps.push_back([=](cudaStream_t st) {
+        push("simt", [=](cudaStream_t st) {
           return linear_attention_windows(qkv_x + off3, ld3, qkv_s + off3 + C, ld3, qkv_s + off3 + 2 * C, ld3,
                                           msg_x + off1, C, dyn_items, items_cap, 25, st);
         });
@@ -182,13 +206,13 @@ struct LoftrEngine {
     const float *g2 = W_(p + ".norm2.g"), *b2 = W_(p + ".norm2.b");
     const long long tot = static_cast<long long>(n) * rows;
     if (dyn_rows == nullptr) {
-      steps.push_back([=](cudaStream_t st) {
+      push("simt", [=](cudaStream_t st) {
         return layernorm_rows(mrg_x, C, g1, b1, nullptr, 0, x + C, ld2, tot, C, nullptr, st);
       });
     } else {
       for (int side = 0; side < n; ++side) {
         const size_t o1 = static_cast<size_t>(side) * rows * C, o2 = static_cast<size_t>(side) * rows * ld2;
-        steps.push_back([=](cudaStream_t st) {
+        push("simt", [=](cudaStream_t st) {
           return layernorm_rows(mrg_x + o1, C, g1, b1, nullptr, 0, x + o2 + C, ld2, rows, C, dyn_rows, st);
         });
       }
@@ -196,13 +220,13 @@ struct LoftrEngine {
     conv(p + ".mlp0", x, n, 1, rows, 2 * C, ld2, 2 * C, 1, 1, false, nullptr, ACT_RELU, h1_x, ld2, 0, dyn_rows);
     conv(p + ".mlp2", h1_x, n, 1, rows, 2 * C, ld2, C, 1, 1, false, nullptr, ACT_NONE, h2_x, C, 0, dyn_rows);
     if (dyn_rows == nullptr) {
-      steps.push_back([=](cudaStream_t st) {
+      push("simt", [=](cudaStream_t st) {
         return layernorm_rows(h2_x, C, g2, b2, x, ld2, x, ld2, tot, C, nullptr, st);
       });
     } else {
       for (int side = 0; side < n; ++side) {
         const size_t o1 = static_cast<size_t>(side) * rows * C, o2 = static_cast<size_t>(side) * rows * ld2;
-        steps.push_back([=](cudaStream_t st) {
+        push("simt", [=](cudaStream_t st) {
           return layernorm_rows(h2_x + o1, C, g2, b2, x + o2, ld2, x + o2, ld2, rows, C, dyn_rows, st);
         });
       }
@@ -262,7 +286,7 @@ struct LoftrEngine {
     {
       float *img_ = img, *a0_ = a0; float* ws = W_("stem.w"); float* bs = W_("stem.b");
       const int NI_ = NI, H_ = H, W_w = W;
-      steps.push_back([=](cudaStream_t st) { return stem_conv7x7(img_, ws, bs, a0_, NI_, H_, W_w, st); });
+      push("simt", [=](cudaStream_t st) { return stem_conv7x7(img_, ws, bs, a0_, NI_, H_, W_w, st); });
     }
     conv("layer1.0.conv1", a0, NI, H2, W2, 128, 128, 128, 3, 1, true, nullptr, ACT_RELU, a1, 128);
     conv("layer1.0.conv2", a1, NI, H2, W2, 128, 128, 128, 3, 1, true, a0, ACT_RELU, a2, 128);
@@ -282,14 +306,14 @@ struct LoftrEngine {
     conv("layer2_outconv", b2, NI, H4, W4, 196, 196, 256, 1, 1, false, nullptr, ACT_NONE, p4a, 256);
     {
       float *s = fc, *d = p4a; const int n = NI, hs = H8, wsz = W8;
-      steps.push_back([=](cudaStream_t st) { return upsample2x_add(s, d, n, hs, wsz, 256, st); });
+      push("simt", [=](cudaStream_t st) { return upsample2x_add(s, d, n, hs, wsz, 256, st); });
     }
     conv("layer2_outconv2.0", p4a, NI, H4, W4, 256, 256, 256, 3, 1, true, nullptr, ACT_LEAKY, p4b, 256);
     conv("layer2_outconv2.3", p4b, NI, H4, W4, 256, 256, 196, 3, 1, false, nullptr, ACT_NONE, p4c, 196);
     conv("layer1_outconv", a0, NI, H2, W2, 128, 128, 196, 1, 1, false, nullptr, ACT_NONE, p2a, 196);
     {
       float *s = p4c, *d = p2a; const int n = NI, hs = H4, wsz = W4;
-      steps.push_back([=](cudaStream_t st) { return upsample2x_add(s, d, n, hs, wsz, 196, st); });
+      push("simt", [=](cudaStream_t st) { return upsample2x_add(s, d, n, hs, wsz, 196, st); });
     }
     conv("layer1_outconv2.0", p2a, NI, H2, W2, 196, 196, 196, 3, 1, true, nullptr, ACT_LEAKY, p2b, 196);
     conv("layer1_outconv2.3", p2b, NI, H2, W2, 196, 196, 128, 3, 1, false, nullptr, ACT_NONE, a1, 128);
@@ -299,7 +323,7 @@ struct LoftrEngine {
     // ---------------------------------------------------------------- pos-enc + coarse transformer
     {
       float *f = fc, *t = tok; float* pe = W_("pos_enc"); const int n = NI, l = L;
-      steps.push_back([=](cudaStream_t st) { return posenc_tokens(f, pe, t, 512, n, l, 256, st); });
+      push("simt", [=](cudaStream_t st) { return posenc_tokens(f, pe, t, 512, n, l, 256, st); });
     }
     const size_t half_tok = static_cast<size_t>(B) * L * 512, half_qkv = static_cast<size_t>(B) * L * 768;
     const size_t half_c = static_cast<size_t>(B) * L * 256, half_2c = static_cast<size_t>(B) * L * 512;
@@ -326,24 +350,25 @@ struct LoftrEngine {
       int rc = conv_gemm_build(d, &p);
       if (rc != MFR_OK) return rc;
       steps.push_back([p](cudaStream_t st) { return conv_gemm_launch(p, st); });
+      infos.push_back(StepInfo{"correlation", 1, 2.0 * B * static_cast<double>(L) * L * 256, nullptr, 0});
       CoarseMatchBuffers cmb = cm; float* S_ = S;
       const int B_ = B, L_ = L, hc = H8, wc = W8, bd = border, sc = splits_col; const float th = thr;
       const float scale = static_cast<float>(H) / static_cast<float>(H8);
-      steps.push_back([=](cudaStream_t st) {
+      push("simt", [=](cudaStream_t st) {
         return coarse_match(S_, cmb, B_, L_, hc, wc, th, bd, scale, sc, st);
-      });
+      }, 8);
     }
 
     // ---------------------------------------------------------------- fine level
     {
       CoarseMatchBuffers cmb = cm; float *tok_ = tok, *cin_ = cin, *cproj_ = cproj, *win_ = win;
       const int B_ = B, L_ = L, Mc = Mcap, Hf = H2, Wf = W2, wc = W8;
-      steps.push_back([=](cudaStream_t st) {
+      push("simt", [=](cudaStream_t st) {
         return fine_gather_coarse(tok_, 512, B_, L_, cmb.b_ids, cmb.i_ids, cmb.j_ids, cmb.m_total, Mc, cin_, st);
       });
       conv("fine.down_proj", cin, 2, 1, Mcap, 256, 256, 128, 1, 1, true, nullptr, ACT_NONE, cproj, 128, 0,
            cm.m_total);
-      steps.push_back([=](cudaStream_t st) {
+      push("simt", [=](cudaStream_t st) {
         return fine_gather_windows(featf, B_, Hf, Wf, wc, cmb.b_ids, cmb.i_ids, cmb.j_ids, cmb.m_total, Mc,
                                    cproj_, win_, st);
       });
@@ -362,7 +387,7 @@ struct LoftrEngine {
                     fh2 + s_c, 1, rows, cm.m_total + 2, cm.m_total, true);
       CoarseMatchBuffers cmb = cm; float *f0 = ftok, *f1 = ftok + s_tok, *mk = mk1f, *ex = expec;
       const int Mc = Mcap; const float scale_f = static_cast<float>(H) / static_cast<float>(H2);
-      steps.push_back([=](cudaStream_t st) {
+      push("simt", [=](cudaStream_t st) {
         return fine_match(f0, f1, 256, cmb.mkpts1_c, cmb.m_total, Mc, scale_f, mk, ex, st);
       });
     }
@@ -377,14 +402,28 @@ struct LoftrEngine {
     return MFR_OK;
   }
 
-  int forward(const float* img0, const float* img1, cudaStream_t st) {
+  // src images are [B][src_h][src_w] (src_h <= H, src_w <= W); the right/bottom remainder of the
+  // engine's [H][W] frame stays zero: the reference's ConstantPad2d (matchers.py:41-46).
+  int forward(const float* img0, const float* img1, int src_h, int src_w, cudaStream_t st) {
     if (!weights_loaded) {
       fprintf(stderr, "[mfr_b200] loftr forward before weights were loaded\n");
       return MFR_ERR_ARG;
     }
+    if (src_h > H || src_w > W || src_h < 1 || src_w < 1) return MFR_ERR_ARG;
     const size_t half = static_cast<size_t>(B) * H * W;
-    MFR_CUDA_CHECK(cudaMemcpyAsync(img, img0, half * 4, cudaMemcpyDeviceToDevice, st));
-    MFR_CUDA_CHECK(cudaMemcpyAsync(img + half, img1, half * 4, cudaMemcpyDeviceToDevice, st));
+    if (src_h == H && src_w == W) {
+      MFR_CUDA_CHECK(cudaMemcpyAsync(img, img0, half * 4, cudaMemcpyDeviceToDevice, st));
+      MFR_CUDA_CHECK(cudaMemcpyAsync(img + half, img1, half * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+      for (int b = 0; b < B; ++b) {
+        MFR_CUDA_CHECK(cudaMemcpy2DAsync(img + static_cast<size_t>(b) * H * W, static_cast<size_t>(W) * 4,
+                                         img0 + static_cast<size_t>(b) * src_h * src_w, static_cast<size_t>(src_w) * 4,
+                                         static_cast<size_t>(src_w) * 4, src_h, cudaMemcpyDeviceToDevice, st));
+        MFR_CUDA_CHECK(cudaMemcpy2DAsync(img + half + static_cast<size_t>(b) * H * W, static_cast<size_t>(W) * 4,
+                                         img1 + static_cast<size_t>(b) * src_h * src_w, static_cast<size_t>(src_w) * 4,
+                                         static_cast<size_t>(src_w) * 4, src_h, cudaMemcpyDeviceToDevice, st));
+      }
+    }
     if (!use_graph) return run_steps(st);
     if (!graph_exec) {
       // warm (sets function attributes outside capture), then capture the launch list once
@@ -407,6 +446,42 @@ struct LoftrEngine {
     }
     MFR_CUDA_CHECK(cudaGraphLaunch(graph_exec, st));
     return MFR_OK;
+  }
+
+  // eager run with a CUDA event pair around every step; ms[i] = device time of step i
+  int profile(const float* img0, const float* img1, int src_h, int src_w, cudaStream_t st, int max_steps,
+              float* ms, double* flops, int* kinds, char* names) {
+    const bool g = use_graph;
+    use_graph = false;
+    int rc = forward(img0, img1, src_h, src_w, st);  // warm
+    if (rc != MFR_OK) { use_graph = g; return -rc; }
+    const int n = static_cast<int>(steps.size());
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], st);
+    for (int i = 0; i < n; ++i) {
+      rc = steps[i](st);
+      if (rc != MFR_OK) break;
+      cudaEventRecord(ev[i + 1], st);
+    }
+    cudaStreamSynchronize(st);
+    int m_total_h[4] = {0, 0, 0, 0};
+    cudaMemcpy(m_total_h, cm.m_total, sizeof(m_total_h), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < n && i < max_steps && rc == MFR_OK; ++i) {
+      cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+      double f = infos[i].flops;
+      if (infos[i].dyn_rows) {
+        const int idx = static_cast<int>(infos[i].dyn_rows - cm.m_total);
+        f *= static_cast<double>(m_total_h[idx]) * infos[i].dyn_images;
+      }
+      flops[i] = f;
+      kinds[i] = infos[i].kind;
+      strncpy(names + 32 * i, infos[i].name.c_str(), 31);
+      names[32 * i + 31] = 0;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    use_graph = g;
+    return rc == MFR_OK ? n : -rc;
   }
 
   ~LoftrEngine() {
@@ -438,8 +513,8 @@ int loftr_set_weight(LoftrEngine* e, int i, const float* host, long long numel, 
   return MFR_OK;
 }
 void loftr_mark_weights_loaded(LoftrEngine* e) { e->weights_loaded = true; }
-int loftr_forward(LoftrEngine* e, const float* img0, const float* img1, cudaStream_t st) {
-  return e->forward(img0, img1, st);
+int loftr_forward(LoftrEngine* e, const float* img0, const float* img1, int src_h, int src_w, cudaStream_t st) {
+  return e->forward(img0, img1, src_h, src_w, st);
 }
 void loftr_set_graph(LoftrEngine* e, int on) { e->use_graph = on != 0; }
 LoftrOutputs loftr_outputs(LoftrEngine* e) {
@@ -458,5 +533,14 @@ int loftr_debug_tensor(LoftrEngine* e, const char* name, float** ptr, long long*
   return MFR_OK;
 }
 int loftr_num_steps(const LoftrEngine* e) { return static_cast<int>(e->steps.size()); }
+int loftr_num_launches(const LoftrEngine* e) {
+  int n = 0;
+  for (const auto& i : e->infos) n += i.launches;
+  return n;
+}
+int loftr_profile(LoftrEngine* e, const float* img0, const float* img1, int src_h, int src_w, cudaStream_t st,
+                  int max_steps, float* ms, double* flops, int* kinds, char* names) {
+  return e->profile(img0, img1, src_h, src_w, st, max_steps, ms, flops, kinds, names);
+}
 
 }  // namespace mfr

@@ -22,10 +22,13 @@ int loftr_num_weights(const LoftrEngine* e);
 const char* loftr_weight_name(const LoftrEngine* e, int i);
 long long loftr_weight_numel(const LoftrEngine* e, int i);
 int loftr_set_weight(LoftrEngine* e, int i, const float* host, long long numel, cudaStream_t st);
-int loftr_forward(LoftrEngine* e, const float* img0, const float* img1, cudaStream_t st);
+int loftr_forward(LoftrEngine* e, const float* img0, const float* img1, int src_h, int src_w, cudaStream_t st);
 void loftr_set_graph(LoftrEngine* e, int on);
 LoftrOutputs loftr_outputs(LoftrEngine* e);
 int loftr_debug_tensor(LoftrEngine* e, const char* name, float** ptr, long long* numel);
 int loftr_num_steps(const LoftrEngine* e);
+int loftr_num_launches(const LoftrEngine* e);
+int loftr_profile(LoftrEngine* e, const float* img0, const float* img1, int src_h, int src_w, cudaStream_t st,
+                  int max_steps, float* ms, double* flops, int* kinds, char* names);
 
 }  // namespace mfr

@@ -2,6 +2,7 @@
 #include "loftr_ops.cuh"
 
 #include <algorithm>
+#include <cstring>
 
 namespace mfr {
 
@@ -113,98 +114,93 @@ __global__ void posenc_kernel(const float* __restrict__ feat, const float* __res
 }
 
 // ------------------------------------------------------------------------------------------ linear attention (long)
-// D = 32 only (coarse: 8 heads x 32).
-constexpr int kKvTile = 64;
+// 8 heads x 32 (coarse level). One warp = one head; lane = value column v.
+//   kv_partial : block (8 warps) reduces a slab of tokens for all heads. K rows are staged in shared
+//                memory (broadcast reads), V is read straight into registers (coalesced).
+//   kv_reduce  : sums the slabs.
+//   attn_apply : each lane keeps KV[h][:, v] and Ksum[h][lane] in registers; q rows are broadcast
+//                from shared memory; one warp-shuffle reduction per token for the normaliser.
+constexpr int kKvTok = 32;  // tokens staged per iteration
 __global__ void __launch_bounds__(256) kv_partial_kernel(const float* __restrict__ K, long long ldk,
                                                          const float* __restrict__ V, long long ldv,
-                                                         float* __restrict__ kv_part, int S, int heads,
-                                                         int splits) {
-  __shared__ float sK[kKvTile][33];
-  __shared__ float sV[kKvTile][33];
-  const int split = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+                                                         float* __restrict__ kv_part, int S, int splits) {
+  __shared__ __align__(16) float sK[kKvTok][256];
+  const int split = blockIdx.x, n = blockIdx.y;
   const int chunk = (S + splits - 1) / splits;
   const int s_beg = split * chunk, s_end = min(S, s_beg + chunk);
-  const int t = threadIdx.x, v = t & 31, dg = t >> 5;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int t = threadIdx.x, h = t >> 5, lane = t & 31;
+  float acc[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) acc[d] = 0.f;
   float ks = 0.f;
   const float fS = static_cast<float>(S);
-  for (int s0 = s_beg; s0 < s_end; s0 += kKvTile) {
-    const int cnt = min(kKvTile, s_end - s0);
-    for (int idx = t; idx < kKvTile * 32; idx += 256) {
-      const int r = idx >> 5, cc = idx & 31;
-      float kk = 0.f, vv = 0.f;
-      if (r < cnt) {
-        const size_t row = static_cast<size_t>(n) * S + s0 + r;
-        kk = K[row * ldk + h * 32 + cc];
-        vv = __fdiv_rn(V[row * ldv + h * 32 + cc], fS);
+  for (int s0 = s_beg; s0 < s_end; s0 += kKvTok) {
+    const int cnt = min(kKvTok, s_end - s0);
+    __syncthreads();
+    for (int r = 0; r < cnt; ++r) sK[r][t] = K[(static_cast<size_t>(n) * S + s0 + r) * ldk + t];
+    __syncthreads();
+    for (int r = 0; r < cnt; ++r) {
+      const float vv = __fdiv_rn(V[(static_cast<size_t>(n) * S + s0 + r) * ldv + t], fS);
+      const float4* kr = reinterpret_cast<const float4*>(&sK[r][h * 32]);
+#pragma unroll
+      for (int d4 = 0; d4 < 8; ++d4) {
+        const float4 kk = kr[d4];
+        acc[4 * d4] = fmaf(kk.x, vv, acc[4 * d4]);
+        acc[4 * d4 + 1] = fmaf(kk.y, vv, acc[4 * d4 + 1]);
+        acc[4 * d4 + 2] = fmaf(kk.z, vv, acc[4 * d4 + 2]);
+        acc[4 * d4 + 3] = fmaf(kk.w, vv, acc[4 * d4 + 3]);
       }
-      sK[r][cc] = kk;
-      sV[r][cc] = vv;
+      ks += sK[r][t];
     }
-    __syncthreads();
-#pragma unroll 8
-    for (int r = 0; r < kKvTile; ++r) {
-      const float vv = sV[r][v];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(sK[r][dg * 4 + j], vv, acc[j]);
-      if (t < 32) ks += sK[r][t];
-    }
-    __syncthreads();
   }
-  float* o = kv_part + ((static_cast<size_t>(n) * heads + h) * splits + split) * 1056;
+  float* o = kv_part + ((static_cast<size_t>(n) * splits + split) * 8 + h) * 1056;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) o[(dg * 4 + j) * 32 + v] = acc[j];
-  if (t < 32) o[1024 + t] = ks;
+  for (int d = 0; d < 32; ++d) o[d * 32 + lane] = acc[d];
+  o[1024 + lane] = ks;
 }
 
-__global__ void kv_reduce_kernel(const float* __restrict__ kv_part, float* __restrict__ kv, int splits) {
-  const size_t nh = blockIdx.x;
-  for (int e = threadIdx.x; e < 1056; e += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += kv_part[(nh * splits + k) * 1056 + e];
-    kv[nh * 1056 + e] = s;
-  }
+__global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict__ kv_part,
+                                                        float* __restrict__ kv, int splits) {
+  // grid (ceil(8448/256), n): element e of the [8][1056] block of image n
+  const int n = blockIdx.y;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= 8 * 1056) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += kv_part[(static_cast<size_t>(n) * splits + k) * 8448 + e];
+  kv[static_cast<size_t>(n) * 8448 + e] = s;
 }
 
+constexpr int kApplyTok = 32;
 __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict__ Q, long long ldq,
                                                          const float* __restrict__ kv,
                                                          float* __restrict__ msg, long long ldm, int L,
                                                          int S, float eps) {
-  __shared__ float sKV[8][1057];
+  __shared__ __align__(16) float sQ[kApplyTok][256];
   const int n = blockIdx.y;
-  for (int idx = threadIdx.x; idx < 8 * 1056; idx += 256) {
-    const int h = idx / 1056, e = idx - h * 1056;
-    sKV[h][e] = kv[(static_cast<size_t>(n) * 8 + h) * 1056 + e];
-  }
+  const int l0 = blockIdx.x * kApplyTok;
+  const int t = threadIdx.x, h = t >> 5, lane = t & 31;
+  const float* kvh = kv + (static_cast<size_t>(n) * 8 + h) * 1056;
+  float kvr[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) kvr[d] = kvh[d * 32 + lane];
+  const float ksum = kvh[1024 + lane];
+  const int cnt = min(kApplyTok, L - l0);
+  for (int r = 0; r < cnt; ++r) sQ[r][t] = Q[(static_cast<size_t>(n) * L + l0 + r) * ldq + t];
   __syncthreads();
-  const int h = threadIdx.x & 7;
-  const int l = blockIdx.x * 32 + (threadIdx.x >> 3);
-  if (l >= L) return;
-  const size_t row = static_cast<size_t>(n) * L + l;
-  float q[32];
-  const float4* qp = reinterpret_cast<const float4*>(Q + row * ldq + h * 32);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 f = qp[j];
-    q[4 * j] = f.x; q[4 * j + 1] = f.y; q[4 * j + 2] = f.z; q[4 * j + 3] = f.w;
-  }
-  float den = 0.f;
-#pragma unroll
-  for (int d = 0; d < 32; ++d) den = fmaf(q[d], sKV[h][1024 + d], den);
-  const float z = 1.f / (den + eps);
   const float fS = static_cast<float>(S);
-  float4* op = reinterpret_cast<float4*>(msg + row * ldm + h * 32);
+  for (int r = 0; r < cnt; ++r) {
+    const float4* qr = reinterpret_cast<const float4*>(&sQ[r][h * 32]);
+    float a = 0.f;
 #pragma unroll
-  for (int v4 = 0; v4 < 8; ++v4) {
-    float o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a = 0.f;
-#pragma unroll
-      for (int d = 0; d < 32; ++d) a = fmaf(q[d], sKV[h][d * 32 + v4 * 4 + j], a);
-      o[j] = a * z * fS;
+    for (int d4 = 0; d4 < 8; ++d4) {
+      const float4 q = qr[d4];
+      a = fmaf(q.x, kvr[4 * d4], a);
+      a = fmaf(q.y, kvr[4 * d4 + 1], a);
+      a = fmaf(q.z, kvr[4 * d4 + 2], a);
+      a = fmaf(q.w, kvr[4 * d4 + 3], a);
     }
-    op[v4] = make_float4(o[0], o[1], o[2], o[3]);
+    const float den = warp_sum(sQ[r][t] * ksum);
+    msg[(static_cast<size_t>(n) * L + l0 + r) * ldm + t] = a * (1.f / (den + eps)) * fS;
   }
 }
 
@@ -311,7 +307,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // conf = softmax_col(S) * softmax_row(S); the expression is written with explicit rounding
 // intrinsics so that every pass reproduces the identical fp32 value (the mutual-NN test compares
 // for float equality, coarse_matching.py:187-189).
-__device__ __forceinline__ float conf_value(float s, float rmax, float rrs, float cmax, float crs) {
+__device__ __forceinline__ float conf_value(float s, float rmax, float rrs, float cmax, float crs,
+                                            bool raw = false) {
+  if (raw) return s;  // the input already is the confidence matrix (stage-boundary entry point)
   const float pr = __fmul_rn(__expf(__fsub_rn(s, rmax)), rrs);
   const float pc = __fmul_rn(__expf(__fsub_rn(s, cmax)), crs);
   return __fmul_rn(pc, pr);
@@ -398,19 +396,19 @@ __global__ void __launch_bounds__(256) row_conf_kernel(const float* __restrict__
                                                        const float* __restrict__ col_rsum,
                                                        float* __restrict__ rconf_max,
                                                        int* __restrict__ rconf_arg,
-                                                       int* __restrict__ rconf_ties, int L) {
+                                                       int* __restrict__ rconf_ties, int L, bool raw) {
   __shared__ float sh[8];
   __shared__ int shi[8];
   const int b = blockIdx.y;
   const size_t r = static_cast<size_t>(b) * L + blockIdx.x;
   const float* p = S + r * L;
-  const float rm = row_max[r], rr = row_rsum[r];
+  const float rm = raw ? 0.f : row_max[r], rr = raw ? 0.f : row_rsum[r];
   const float* cm = col_max + static_cast<size_t>(b) * L;
   const float* cr = col_rsum + static_cast<size_t>(b) * L;
   float best = -1.f;
   int arg = 0x7fffffff;
   for (int j = threadIdx.x; j < L; j += 256) {
-    const float c = conf_value(p[j], rm, rr, cm[j], cr[j]);
+    const float c = conf_value(p[j], rm, rr, raw ? 0.f : cm[j], raw ? 0.f : cr[j], raw);
     if (c > best) { best = c; arg = j; }
   }
   const float bm = block_max_256(best, sh);
@@ -426,7 +424,7 @@ __global__ void __launch_bounds__(256) row_conf_kernel(const float* __restrict__
   __syncthreads();
   int ties = 0;
   for (int j = threadIdx.x; j < L; j += 256)
-    ties += (conf_value(p[j], rm, rr, cm[j], cr[j]) == bm) ? 1 : 0;
+    ties += (conf_value(p[j], rm, rr, raw ? 0.f : cm[j], raw ? 0.f : cr[j], raw) == bm) ? 1 : 0;
   const float tsum = block_sum_256(static_cast<float>(ties), sh);
   if (threadIdx.x == 0) {
     rconf_max[r] = bm;
@@ -441,19 +439,20 @@ __global__ void __launch_bounds__(256) col_conf_partial_kernel(const float* __re
                                                                const float* __restrict__ col_max,
                                                                const float* __restrict__ col_rsum,
                                                                float* __restrict__ part, int L,
-                                                               int splits) {
+                                                               int splits, bool raw) {
   const int j = blockIdx.x * 256 + threadIdx.x;
   const int split = blockIdx.y, b = blockIdx.z;
   if (j >= L) return;
   const int chunk = (L + splits - 1) / splits;
   const int i0 = split * chunk, i1 = min(L, i0 + chunk);
   const float* p = S + static_cast<size_t>(b) * L * L + j;
-  const float cm = col_max[static_cast<size_t>(b) * L + j], cr = col_rsum[static_cast<size_t>(b) * L + j];
+  const float cm = raw ? 0.f : col_max[static_cast<size_t>(b) * L + j];
+  const float cr = raw ? 0.f : col_rsum[static_cast<size_t>(b) * L + j];
   const float* rm = row_max + static_cast<size_t>(b) * L;
   const float* rr = row_rsum + static_cast<size_t>(b) * L;
   float best = -1.f;
   for (int i = i0; i < i1; ++i)
-    best = fmaxf(best, conf_value(p[static_cast<size_t>(i) * L], rm[i], rr[i], cm, cr));
+    best = fmaxf(best, conf_value(p[static_cast<size_t>(i) * L], raw ? 0.f : rm[i], raw ? 0.f : rr[i], cm, cr, raw));
   part[(static_cast<size_t>(b) * splits + split) * L + j] = best;
 }
 __global__ void col_conf_combine_kernel(const float* __restrict__ part, float* __restrict__ cconf_max,
@@ -476,7 +475,7 @@ __global__ void select_kernel(const float* __restrict__ S, const float* __restri
                               const float* __restrict__ col_rsum, const float* __restrict__ rconf_max,
                               const int* __restrict__ rconf_arg, const int* __restrict__ rconf_ties,
                               const float* __restrict__ cconf_max, int* __restrict__ jsel, int L,
-                              int h_c, int w_c, float thr, int border) {
+                              int h_c, int w_c, float thr, int border, bool raw) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (i >= L) return;
@@ -491,11 +490,11 @@ __global__ void select_kernel(const float* __restrict__ S, const float* __restri
     } else if (rconf_ties[r] > 1) {
       // rare: several columns attain the row maximum; take the first that is also a column maximum
       const float* p = S + r * L;
-      const float rm = row_max[r], rr = row_rsum[r];
+      const float rm = raw ? 0.f : row_max[r], rr = raw ? 0.f : row_rsum[r];
       const float* cm = col_max + static_cast<size_t>(b) * L;
       const float* cr = col_rsum + static_cast<size_t>(b) * L;
       for (int jj = j + 1; jj < L; ++jj) {
-        const float c = conf_value(p[jj], rm, rr, cm[jj], cr[jj]);
+        const float c = conf_value(p[jj], rm, rr, raw ? 0.f : cm[jj], raw ? 0.f : cr[jj], raw);
         if (c == v && c == cc[jj] && border_ok(jj, h_c, w_c, border)) { sel = jj; break; }
       }
     }
@@ -682,9 +681,9 @@ int linear_attention_long(const float* Q, long long ldq, const float* K, long lo
                           long long ldv, float* msg, long long ldm, float* kv_part, float* kv, int n,
                           int L, int S, int heads, int dim, int splits, cudaStream_t st) {
   if (dim != 32 || heads != 8) return MFR_ERR_UNSUPPORTED;
-  kv_partial_kernel<<<dim3(splits, heads, n), 256, 0, st>>>(K, ldk, V, ldv, kv_part, S, heads, splits);
-  kv_reduce_kernel<<<n * heads, 256, 0, st>>>(kv_part, kv, splits);
-  attn_apply_kernel<<<dim3((L + 31) / 32, n), 256, 0, st>>>(Q, ldq, kv, msg, ldm, L, S, 1e-6f);
+  kv_partial_kernel<<<dim3(splits, n), 256, 0, st>>>(K, ldk, V, ldv, kv_part, S, splits);
+  kv_reduce_kernel<<<dim3((8 * 1056 + 255) / 256, n), 256, 0, st>>>(kv_part, kv, splits);
+  attn_apply_kernel<<<dim3((L + kApplyTok - 1) / kApplyTok, n), 256, 0, st>>>(Q, ldq, kv, msg, ldm, L, S, 1e-6f);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }
@@ -714,23 +713,49 @@ int layernorm_rows(const float* in, long long ldi, const float* gamma, const flo
 }
 
 int coarse_match(const float* S, CoarseMatchBuffers f, int B, int L, int h_c, int w_c, float thr,
-                 int border, float scale, int splits, cudaStream_t st) {
+                 int border, float scale, int splits, cudaStream_t st, bool input_is_conf) {
   const int cb = (L + 255) / 256;
-  row_stats_kernel<<<dim3(L, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, L);
-  col_stats_partial_kernel<<<dim3(cb, splits, B), 256, 0, st>>>(S, f.col_part, L, splits);
-  col_stats_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.col_max, f.col_rsum, L, splits);
+  const bool raw = input_is_conf;
+  if (!raw) {
+    row_stats_kernel<<<dim3(L, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, L);
+    col_stats_partial_kernel<<<dim3(cb, splits, B), 256, 0, st>>>(S, f.col_part, L, splits);
+    col_stats_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.col_max, f.col_rsum, L, splits);
+  }
   row_conf_kernel<<<dim3(L, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max, f.col_rsum,
-                                              f.rconf_max, f.rconf_arg, f.rconf_ties, L);
+                                              f.rconf_max, f.rconf_arg, f.rconf_ties, L, raw);
   col_conf_partial_kernel<<<dim3(cb, splits, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max,
-                                                               f.col_rsum, f.col_part, L, splits);
+                                                               f.col_rsum, f.col_part, L, splits, raw);
   col_conf_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.cconf_max, L, splits);
   select_kernel<<<dim3(cb, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max, f.col_rsum,
                                              f.rconf_max, f.rconf_arg, f.rconf_ties, f.cconf_max, f.jsel,
-                                             L, h_c, w_c, thr, border);
+                                             L, h_c, w_c, thr, border, raw);
   compact_kernel<<<1, 1024, 0, st>>>(f.jsel, f.rconf_max, B, L, w_c, scale, f.m_total, f.m_offsets,
                                      f.b_ids, f.i_ids, f.j_ids, f.mconf, f.mkpts0_c, f.mkpts1_c);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
+}
+
+int coarse_match_alloc(int B, int L, int splits, CoarseMatchBuffers* o) {
+  const size_t BL = static_cast<size_t>(B) * L;
+  memset(o, 0, sizeof(*o));
+  bool ok = true;
+  auto A = [&](void** p, size_t bytes) { ok &= cudaMalloc(p, bytes) == cudaSuccess; };
+  A((void**)&o->row_max, BL * 4); A((void**)&o->row_rsum, BL * 4); A((void**)&o->col_max, BL * 4);
+  A((void**)&o->col_rsum, BL * 4); A((void**)&o->col_part, BL * splits * 2 * 4);
+  A((void**)&o->rconf_max, BL * 4); A((void**)&o->rconf_arg, BL * 4); A((void**)&o->rconf_ties, BL * 4);
+  A((void**)&o->cconf_max, BL * 4); A((void**)&o->jsel, BL * 4); A((void**)&o->m_total, 16);
+  A((void**)&o->m_offsets, (B + 1) * 4); A((void**)&o->b_ids, BL * 4); A((void**)&o->i_ids, BL * 4);
+  A((void**)&o->j_ids, BL * 4); A((void**)&o->mconf, BL * 4); A((void**)&o->mkpts0_c, BL * 8);
+  A((void**)&o->mkpts1_c, BL * 8);
+  if (!ok) { coarse_match_free(o); return MFR_ERR_CUDA; }
+  return MFR_OK;
+}
+void coarse_match_free(CoarseMatchBuffers* o) {
+  void* ps[] = {o->row_max, o->row_rsum, o->col_max, o->col_rsum, o->col_part, o->rconf_max, o->rconf_arg,
+                o->rconf_ties, o->cconf_max, o->jsel, o->m_total, o->m_offsets, o->b_ids, o->i_ids, o->j_ids,
+                o->mconf, o->mkpts0_c, o->mkpts1_c};
+  for (void* p : ps) if (p) cudaFree(p);
+  memset(o, 0, sizeof(*o));
 }
 
 int fine_gather_coarse(const float* tok, long long ldt, int B, int L, const int* b_ids, const int* i_ids,

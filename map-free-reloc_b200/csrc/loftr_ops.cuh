@@ -52,7 +52,10 @@ struct CoarseMatchBuffers {
   float* mkpts0_c; float* mkpts1_c;    // [B*L][2]
 };
 int coarse_match(const float* S, CoarseMatchBuffers bufs, int B, int L, int h_c, int w_c, float thr,
-                 int border, float scale, int splits, cudaStream_t st);
+                 int border, float scale, int splits, cudaStream_t st, bool input_is_conf = false);
+// scratch + output buffers for a standalone call (freed with coarse_match_free)
+int coarse_match_alloc(int B, int L, int splits, CoarseMatchBuffers* out);
+void coarse_match_free(CoarseMatchBuffers* b);
 
 // ---- fine level ----
 // cin[(s*Mcap + m), 0:256] = feat_c{s}[b, i or j, :]   (fine_preprocess.py:51-52), tokens ld = ldt

@@ -37,11 +37,15 @@ SIGNATURES = {
     "mfr_loftr_weight_name": (ctypes.c_char_p, [c_vp, c_int]),
     "mfr_loftr_weight_numel": (c_ll, [c_vp, c_int]),
     "mfr_loftr_set_weight": (c_int, [c_vp, c_int, c_vp, c_ll, c_vp]),
-    "mfr_loftr_forward": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "mfr_loftr_forward": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "mfr_loftr_set_graph": (None, [c_vp, c_int]),
     "mfr_loftr_get_outputs": (c_int, [c_vp, ctypes.POINTER(LoftrOutputs)]),
     "mfr_loftr_debug_tensor": (c_int, [c_vp, ctypes.c_char_p, c_pp, ctypes.POINTER(c_ll)]),
     "mfr_loftr_num_kernels": (c_int, [c_vp]),
+    "mfr_loftr_num_launches": (c_int, [c_vp]),
+    "mfr_loftr_profile": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "mfr_coarse_match": (c_int, [c_vp, c_int, c_int, c_int, c_float, c_int, c_float, c_int, c_vp, c_vp,
+                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mfr_pose_solver_create": (c_int, [c_int, c_int, c_int, c_pp]),
     "mfr_pose_solver_destroy": (None, [c_vp]),
     "mfr_emat_ransac": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_float, c_int,
@@ -50,6 +54,8 @@ SIGNATURES = {
                                      c_vp, c_vp, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_vp]),
     "mfr_pnp_ransac": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int,
                                c_float, ctypes.c_ulonglong, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mfr_debug_probe_overhead": (c_float, [c_int, c_int, c_int, c_int]),
+    "mfr_debug_time_conv": (c_float, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp, c_int]),
     "mfr_host_five_point": (c_int, [c_vp, c_vp, c_vp]),
     "mfr_host_p3p": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "mfr_host_poly_real_roots": (c_int, [c_vp, c_int, c_vp]),

@@ -98,6 +98,81 @@ def prepare_weights(sd, h_c, w_c):
     return {k: np.ascontiguousarray(v.numpy().astype(np.float32)) for k, v in out.items()}
 
 
+# ---- synthetic weights (the real indoor/outdoor checkpoints are not distributed with the reference)
+def _state_dict_shapes():
+    s = {}
+    def bn(p, c):
+        s[p + ".weight"] = (c,); s[p + ".bias"] = (c,)
+        s[p + ".running_mean"] = (c,); s[p + ".running_var"] = (c,)
+    s["backbone.conv1.weight"] = (128, 1, 7, 7)
+    bn("backbone.bn1", 128)
+    cin = 128
+    for li, c in zip((1, 2, 3), (128, 196, 256)):
+        for bi in (0, 1):
+            p = f"backbone.layer{li}.{bi}"
+            s[p + ".conv1.weight"] = (c, cin if bi == 0 else c, 3, 3)
+            s[p + ".conv2.weight"] = (c, c, 3, 3)
+            bn(p + ".bn1", c)
+            bn(p + ".bn2", c)
+            if bi == 0 and li > 1:
+                s[p + ".downsample.0.weight"] = (c, cin, 1, 1)
+                bn(p + ".downsample.1", c)
+        cin = c
+    s["backbone.layer3_outconv.weight"] = (256, 256, 1, 1)
+    s["backbone.layer2_outconv.weight"] = (256, 196, 1, 1)
+    s["backbone.layer2_outconv2.0.weight"] = (256, 256, 3, 3)
+    bn("backbone.layer2_outconv2.1", 256)
+    s["backbone.layer2_outconv2.3.weight"] = (196, 256, 3, 3)
+    s["backbone.layer1_outconv.weight"] = (196, 128, 1, 1)
+    s["backbone.layer1_outconv2.0.weight"] = (196, 196, 3, 3)
+    bn("backbone.layer1_outconv2.1", 196)
+    s["backbone.layer1_outconv2.3.weight"] = (128, 196, 3, 3)
+    for pre, c, nl in (("loftr_coarse", 256, 8), ("loftr_fine", 128, 2)):
+        for i in range(nl):
+            p = f"{pre}.layers.{i}"
+            for nme in ("q_proj", "k_proj", "v_proj", "merge"):
+                s[f"{p}.{nme}.weight"] = (c, c)
+            s[p + ".mlp.0.weight"] = (2 * c, 2 * c)
+            s[p + ".mlp.2.weight"] = (c, 2 * c)
+            for nme in ("norm1", "norm2"):
+                s[f"{p}.{nme}.weight"] = (c,)
+                s[f"{p}.{nme}.bias"] = (c,)
+    s["fine_preprocess.down_proj.weight"] = (128, 256)
+    s["fine_preprocess.down_proj.bias"] = (128,)
+    s["fine_preprocess.merge_feat.weight"] = (128, 256)
+    s["fine_preprocess.merge_feat.bias"] = (128,)
+    return s
+
+
+def synthetic_state_dict(seed=0):
+    """Deterministic synthetic LoFTR weights with the reference's state_dict names and shapes
+    (the real indoor/outdoor checkpoints are not in the reference tree).
+    He-style conv init, Xavier-style linear init, and NON-trivial BatchNorm statistics / affine
+    terms / LayerNorm affine terms so that folding and normalisation are actually exercised."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in _state_dict_shapes().items():
+        if k.endswith("running_var"):
+            v = 0.5 + torch.rand(shp, generator=g)
+        elif k.endswith("running_mean"):
+            v = 0.1 * torch.randn(shp, generator=g)
+        elif ".bn" in k or "downsample.1" in k or "outconv2.1" in k or ".norm" in k:
+            if k.endswith(".weight"):
+                v = 0.75 + 0.5 * torch.rand(shp, generator=g)
+            else:
+                v = 0.1 * torch.randn(shp, generator=g)
+        elif len(shp) == 4:
+            fan_out = shp[0] * shp[2] * shp[3]
+            v = torch.randn(shp, generator=g) * (2.0 / fan_out) ** 0.5
+        elif len(shp) == 2:
+            bound = (6.0 / (shp[0] + shp[1])) ** 0.5
+            v = (torch.rand(shp, generator=g) * 2 - 1) * bound
+        else:
+            v = 0.05 * torch.randn(shp, generator=g)
+        sd[k] = v.float().contiguous()
+    return sd
+
+
 class LoFTR:
     """CUDA LoFTR engine for ``batch`` pairs of [H, W] images (H, W multiples of 8)."""
 
@@ -141,6 +216,30 @@ class LoFTR:
     def num_kernels(self):
         return self._l.mfr_loftr_num_kernels(self._h)
 
+    def num_launches(self):
+        """Kernel launches of one forward (a step of the launch list may launch several kernels)."""
+        return self._l.mfr_loftr_num_launches(self._h)
+
+    def profile(self, img0, img1):
+        """Per-step device times of one eager forward: list of (name, kind, ms, flops)."""
+        h, w = img0.shape[-2:]
+        img0 = img0.reshape(self.B, h, w).contiguous()
+        img1 = img1.reshape(self.B, h, w).contiguous()
+        n = self.num_kernels()
+        ms = np.zeros(n, np.float32); fl = np.zeros(n, np.float64); kinds = np.zeros(n, np.int32)
+        names = ctypes.create_string_buffer(32 * n)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            rc = self._l.mfr_loftr_profile(self._h, _lib.ptr(img0), _lib.ptr(img1), int(h), int(w),
+                                           ctypes.c_void_p(self.stream.cuda_stream), n,
+                                           ms.ctypes.data_as(ctypes.c_void_p), fl.ctypes.data_as(ctypes.c_void_p),
+                                           kinds.ctypes.data_as(ctypes.c_void_p), names)
+        if rc < 0:
+            raise _lib.MfrError(f"mfr_loftr_profile failed rc={rc}")
+        raw = names.raw
+        return [(raw[32 * i:32 * i + 32].split(b"\0")[0].decode(), int(kinds[i]), float(ms[i]), float(fl[i]))
+                for i in range(rc)]
+
     def _wrap(self, ptr, shape, dtype):
         """Zero-copy torch view of an engine-owned device buffer."""
         n = int(np.prod(shape))
@@ -162,13 +261,15 @@ class LoFTR:
         return self._wrap(p.value, shape, torch.float32)
 
     def forward_async(self, img0, img1):
-        """Enqueues one batch on the engine stream. img0/img1: CUDA float32 [B,1,H,W] or [B,H,W]."""
-        img0 = img0.reshape(self.B, self.H, self.W).contiguous()
-        img1 = img1.reshape(self.B, self.H, self.W).contiguous()
+        """Enqueues one batch on the engine stream. img0/img1: CUDA float32 [B,(1,)h,w] with h <= H,
+        w <= W; the engine zero-pads to its [H, W] frame (the reference's pad-to-8)."""
+        h, w = img0.shape[-2:]
+        img0 = img0.reshape(self.B, h, w).contiguous()
+        img1 = img1.reshape(self.B, h, w).contiguous()
         assert img0.is_cuda and img0.dtype == torch.float32
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
-            _lib.check(self._l.mfr_loftr_forward(self._h, _lib.ptr(img0), _lib.ptr(img1),
+            _lib.check(self._l.mfr_loftr_forward(self._h, _lib.ptr(img0), _lib.ptr(img1), int(h), int(w),
                                                  ctypes.c_void_p(self.stream.cuda_stream)), "loftr forward")
         img0.record_stream(self.stream)
         img1.record_stream(self.stream)
@@ -260,9 +361,9 @@ class LoFTR_matcher:
 
     def match_arrays(self, im0, im1):
         dev = self.engine.device
-        t0 = pad_to_8(torch.from_numpy(im0)[None, None].to(dev))
-        t1 = pad_to_8(torch.from_numpy(im1)[None, None].to(dev))
-        out = self.engine.forward(t0, t1)
+        t0 = torch.from_numpy(np.ascontiguousarray(im0, dtype=np.float32))[None].to(dev)
+        t1 = torch.from_numpy(np.ascontiguousarray(im1, dtype=np.float32))[None].to(dev)
+        out = self.engine.forward(t0, t1)     # padding to the engine frame happens on the device
         if out["M"] > 0:
             return torch.cat([out["mkpts0_f"], out["mkpts1_f"]], 1).cpu().numpy()
         return np.full((1, 4), np.nan)

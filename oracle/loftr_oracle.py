@@ -222,75 +222,8 @@ def loftr_forward(img0, img1, sd, cfg=None, return_intermediates=False):
 
 
 # ------------------------------------------------------------------------------ synthetic weights
-def _shapes():
-    s = {}
-    def bn(p, c):
-        s[p + ".weight"] = (c,); s[p + ".bias"] = (c,)
-        s[p + ".running_mean"] = (c,); s[p + ".running_var"] = (c,)
-    s["backbone.conv1.weight"] = (128, 1, 7, 7)
-    bn("backbone.bn1", 128)
-    cin = 128
-    for li, c in zip((1, 2, 3), (128, 196, 256)):
-        for bi in (0, 1):
-            p = f"backbone.layer{li}.{bi}"
-            s[p + ".conv1.weight"] = (c, cin if bi == 0 else c, 3, 3)
-            s[p + ".conv2.weight"] = (c, c, 3, 3)
-            bn(p + ".bn1", c)
-            bn(p + ".bn2", c)
-            if bi == 0 and li > 1:
-                s[p + ".downsample.0.weight"] = (c, cin, 1, 1)
-                bn(p + ".downsample.1", c)
-        cin = c
-    s["backbone.layer3_outconv.weight"] = (256, 256, 1, 1)
-    s["backbone.layer2_outconv.weight"] = (256, 196, 1, 1)
-    s["backbone.layer2_outconv2.0.weight"] = (256, 256, 3, 3)
-    bn("backbone.layer2_outconv2.1", 256)
-    s["backbone.layer2_outconv2.3.weight"] = (196, 256, 3, 3)
-    s["backbone.layer1_outconv.weight"] = (196, 128, 1, 1)
-    s["backbone.layer1_outconv2.0.weight"] = (196, 196, 3, 3)
-    bn("backbone.layer1_outconv2.1", 196)
-    s["backbone.layer1_outconv2.3.weight"] = (128, 196, 3, 3)
-    for pre, c, nl in (("loftr_coarse", 256, 8), ("loftr_fine", 128, 2)):
-        for i in range(nl):
-            p = f"{pre}.layers.{i}"
-            for nme in ("q_proj", "k_proj", "v_proj", "merge"):
-                s[f"{p}.{nme}.weight"] = (c, c)
-            s[p + ".mlp.0.weight"] = (2 * c, 2 * c)
-            s[p + ".mlp.2.weight"] = (c, 2 * c)
-            for nme in ("norm1", "norm2"):
-                s[f"{p}.{nme}.weight"] = (c,)
-                s[f"{p}.{nme}.bias"] = (c,)
-    s["fine_preprocess.down_proj.weight"] = (128, 256)
-    s["fine_preprocess.down_proj.bias"] = (128,)
-    s["fine_preprocess.merge_feat.weight"] = (128, 256)
-    s["fine_preprocess.merge_feat.bias"] = (128,)
-    return s
-
-
 def make_state_dict(seed=0):
-    """Deterministic synthetic LoFTR weights with the reference's state_dict names and shapes
-    (the real indoor/outdoor checkpoints are not in the reference tree).
-    He-style conv init, Xavier-style linear init, and NON-trivial BatchNorm statistics / affine
-    terms / LayerNorm affine terms so that folding and normalisation are actually exercised."""
-    g = torch.Generator().manual_seed(seed)
-    sd = {}
-    for k, shp in _shapes().items():
-        if k.endswith("running_var"):
-            v = 0.5 + torch.rand(shp, generator=g)
-        elif k.endswith("running_mean"):
-            v = 0.1 * torch.randn(shp, generator=g)
-        elif ".bn" in k or "downsample.1" in k or "outconv2.1" in k or ".norm" in k:
-            if k.endswith(".weight"):
-                v = 0.75 + 0.5 * torch.rand(shp, generator=g)
-            else:
-                v = 0.1 * torch.randn(shp, generator=g)
-        elif len(shp) == 4:
-            fan_out = shp[0] * shp[2] * shp[3]
-            v = torch.randn(shp, generator=g) * (2.0 / fan_out) ** 0.5
-        elif len(shp) == 2:
-            bound = (6.0 / (shp[0] + shp[1])) ** 0.5
-            v = (torch.rand(shp, generator=g) * 2 - 1) * bound
-        else:
-            v = 0.05 * torch.randn(shp, generator=g)
-        sd[k] = v.float().contiguous()
-    return sd
+    """Deterministic synthetic LoFTR weights in the reference's state_dict format (shared with the
+    product package so that the oracle, the reference module and the CUDA engine see the same bits)."""
+    from mfr_b200.loftr import synthetic_state_dict
+    return synthetic_state_dict(seed)

@@ -1,0 +1,96 @@
+"""Generates the committed golden vectors by running the UNMODIFIED reference modules
+(imported from /root/reference with the shims of oracle/ref_import.py) on seeded synthetic inputs.
+Run in the build container:  python tests/golden/make_golden.py
+Inputs are regenerated from their seeds at test time (mfr_b200.synth, oracle.loftr_oracle.make_state_dict
+are deterministic); an input checksum is stored next to the reference outputs to detect drift.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import mfr_b200  # noqa: E402,F401
+from mfr_b200 import synth  # noqa: E402
+from oracle import ref_import, loftr_oracle  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+POSE_CASES = [  # seed, n, inlier_ratio, noise_px
+    (11, 400, 0.6, 0.3), (12, 800, 0.5, 0.5), (13, 300, 0.8, 0.0), (14, 1000, 0.4, 1.0),
+    (15, 4, 1.0, 0.0), (16, 600, 0.7, 0.2),
+]
+GOLD_H, GOLD_W = 180, 136
+GOLD_K = np.array([[150.0, 0, 67.5], [0, 150.0, 89.5], [0, 0, 1]])
+
+
+def checksum(*arrays):
+    return float(sum(np.float64(np.asarray(a, dtype=np.float64)).sum() for a in arrays))
+
+
+def pose_case(seed, n, ratio, noise):
+    return synth.make_correspondences(seed, n=n, inlier_ratio=ratio, noise_px=noise, h=GOLD_H, w=GOLD_W, K=GOLD_K)
+
+
+def make_pose_golden():
+    model = ref_import.load_model_module()
+    base = dict(FEATURE_MATCHING="Precomputed", DEBUG=False, MATCHES_FILE_PATH="/tmp/_mfr_gold_corr.npz",
+                EMAT_RANSAC=dict(PIX_THRESHOLD=2.0, SCALE_THRESHOLD=0.1, CONFIDENCE=0.9999),
+                PNP=dict(RANSAC_ITER=1000, REPROJECTION_INLIER_THRESHOLD=3, CONFIDENCE=0.9999),
+                DATASET=dict(PAIRS_TXT=dict(TEST=None)))
+    out = {}
+    for ci, (seed, n, ratio, noise) in enumerate(POSE_CASES):
+        c = pose_case(seed, n, ratio, noise)
+        corr = np.concatenate([c["kpts0"], c["kpts1"]], 1)[None].astype(np.float64)
+        np.savez_compressed(base["MATCHES_FILE_PATH"], correspondences=corr)
+        data0 = {"depth0": torch.from_numpy(c["depth0"])[None], "depth1": torch.from_numpy(c["depth1"])[None],
+                 "K_color0": torch.from_numpy(c["K_color0"])[None], "K_color1": torch.from_numpy(c["K_color1"])[None],
+                 "pair_id": torch.tensor([0])}
+        out[f"c{ci}_checksum"] = checksum(c["kpts0"], c["kpts1"], c["depth0"], c["depth1"])
+        for solver in ("EssentialMatrix", "EssentialMatrixMetric", "PNP"):
+            cfg = ref_import.Cfg.wrap(dict(base, POSE_SOLVER=solver))
+            m = model.FeatureMatchingModel(cfg)
+            data = dict(data0)
+            R, t = m(data)
+            out[f"c{ci}_{solver}_R"] = R[0].numpy()
+            out[f"c{ci}_{solver}_t"] = t[0, 0].numpy()
+            out[f"c{ci}_{solver}_inliers"] = np.int64(data["inliers"])
+            if solver == "EssentialMatrix":
+                mask = getattr(m.pose_solver, "mask", None)
+                out[f"c{ci}_emat_mask"] = (np.zeros(0, np.uint8) if mask is None else mask.ravel().astype(np.uint8))
+    np.savez_compressed(os.path.join(HERE, "pose_solver_reference.npz"), **out)
+    print("pose golden:", len(out), "arrays")
+
+
+def make_loftr_golden():
+    LoFTR, default_cfg = ref_import.load_loftr()
+    sd = loftr_oracle.make_state_dict(0)
+    m = LoFTR(config=default_cfg).eval()
+    m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=False)
+    out = {}
+    for ci, (pair, thr, same) in enumerate([(0, 0.0, True), (1, 0.0, False)]):
+        p = synth.make_pair(pair)
+        g0 = synth.rgb_to_gray_u8(p["image0"]).astype(np.float32) / 255.0
+        g1 = synth.rgb_to_gray_u8(p["image1"]).astype(np.float32) / 255.0
+        H, W = 128, 96
+        i0 = torch.from_numpy(g0[100:100 + H, 100:100 + W].copy())[None, None]
+        i1 = torch.from_numpy((g0[108:108 + H, 116:116 + W] if same else g1[100:100 + H, 100:100 + W]).copy())[None, None]
+        m.coarse_matching.thr = thr
+        with torch.no_grad():
+            b = {"image0": i0, "image1": i1}
+            m(b)
+        out[f"c{ci}_checksum"] = checksum(i0.numpy(), i1.numpy())
+        out[f"c{ci}_conf_sum"] = np.float64(b["conf_matrix"].double().sum().item())
+        out[f"c{ci}_conf_sample"] = b["conf_matrix"][0, ::7, ::5].numpy()
+        for k in ("i_ids", "j_ids", "mconf", "mkpts0_f", "mkpts1_f", "expec_f"):
+            out[f"c{ci}_{k}"] = b[k].numpy()
+    np.savez_compressed(os.path.join(HERE, "loftr_reference.npz"), **out)
+    print("loftr golden:", len(out), "arrays; M =", [len(out[f'c{i}_i_ids']) for i in range(2)])
+
+
+if __name__ == "__main__":
+    assert ref_import.available(), "needs /root/reference"
+    make_pose_golden()
+    make_loftr_golden()

@@ -1,0 +1,156 @@
+"""GPU parity of the CUDA LoFTR engine: stage-wise against the torch fp32 CPU oracle, end to end
+against the committed reference vectors, and bit-exact match selection at the conf-matrix boundary.
+
+Tolerances (TF32 tensor-core inputs, fp32 accumulate; the reference's own GPU path runs cuDNN convs in
+TF32 too): feature maps within 2e-2 of the tensor's max magnitude; fine-level keypoints within 0.25 px;
+integer outputs (i_ids / j_ids) bit-exact given the same confidence matrix."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, loftr_case
+from oracle import loftr_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+FEAT_TOL = 2e-2
+PIX_TOL = 0.25
+
+
+def _rel(a, b):
+    a = a.float().cpu(); b = b.float().cpu()
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return lo.make_state_dict(0)
+
+
+def _pairs(B, H, W):
+    from mfr_b200 import synth
+    i0, i1 = [], []
+    for b in range(B):
+        p = synth.make_pair(20 + b)
+        g0 = synth.rgb_to_gray_u8(p["image0"]).astype(np.float32) / 255.0
+        g1 = synth.rgb_to_gray_u8(p["image1"]).astype(np.float32) / 255.0
+        i0.append(g0[40:40 + H, 30:30 + W])
+        i1.append(g0[48:48 + H, 46:46 + W] if b % 2 == 0 else g1[40:40 + H, 30:30 + W])
+    return torch.from_numpy(np.stack(i0))[:, None], torch.from_numpy(np.stack(i1))[:, None]
+
+
+@pytest.mark.parametrize("B,H,W,graph", [(1, 96, 128, False), (2, 160, 120, True)])
+def test_stages_match_oracle(sd, B, H, W, graph):
+    from mfr_b200 import loftr
+    i0, i1 = _pairs(B, H, W)
+    with torch.no_grad():
+        o = lo.loftr_forward(i0, i1, sd, {"thr": 0.0}, True)
+        fcb, ffb = lo.backbone(torch.cat([i0, i1], 0), sd)
+    eng = loftr.LoFTR(sd, batch=B, height=H, width=W, cfg={"thr": 0.0}, graph=graph)
+    assert eng.num_kernels() > 100      # the launch list is our own kernels, not a library call
+    out = eng.forward(i0.cuda(), i1.cuda())
+    out2 = eng.forward(i0.cuda(), i1.cuda())       # second call: CUDA-graph replay must reproduce it
+    h8, w8 = H // 8, W // 8
+    L = h8 * w8
+    assert _rel(eng.debug_tensor("feat_c_backbone", (2 * B, h8, w8, 256)), fcb.permute(0, 2, 3, 1)) < FEAT_TOL
+    assert _rel(eng.debug_tensor("feat_f", (2 * B, H // 2, W // 2, 128)), ffb.permute(0, 2, 3, 1)) < FEAT_TOL
+    tok = eng.debug_tensor("tok", (2 * B, L, 512))[:, :, :256]
+    assert _rel(tok[:B], o["feat_c0"]) < FEAT_TOL and _rel(tok[B:], o["feat_c1"]) < FEAT_TOL
+    assert _rel(eng.debug_tensor("sim", (B, L, L)), o["sim"]) < FEAT_TOL
+    # matches: ordered by (pair, i) like torch.where; compare as sets (TF32 may flip near-ties)
+    keys = list(zip(out["b_ids"].tolist(), out["i_ids"].tolist()))
+    assert keys == sorted(keys)
+    assert out["M"] == out2["M"] and torch.equal(out["i_ids"], out2["i_ids"]) and torch.equal(out["j_ids"], out2["j_ids"])
+    e = {k: n for n, k in enumerate(zip(out["b_ids"].tolist(), out["i_ids"].tolist(), out["j_ids"].tolist()))}
+    r = {k: n for n, k in enumerate(zip(o["b_ids"].tolist(), o["i_ids"].tolist(), o["j_ids"].tolist()))}
+    common = sorted(set(e) & set(r))
+    assert len(common) >= 0.8 * max(1, len(set(e) | set(r)))
+    ie = torch.tensor([e[k] for k in common]); io = torch.tensor([r[k] for k in common])
+    assert torch.equal(out["mkpts0_f"].cpu()[ie], o["mkpts0_f"][io])          # grid points: exact
+    assert (out["mkpts1_f"].cpu()[ie] - o["mkpts1_f"][io]).abs().max().item() < PIX_TOL
+    eng.close()
+
+
+@pytest.mark.parametrize("ci", range(2))
+def test_end_to_end_vs_reference_golden(sd, ci):
+    """CUDA engine vs vectors produced by the UNMODIFIED reference LoFTR (tests/golden)."""
+    from mfr_b200 import loftr
+    G = np.load(GOLDEN + "/loftr_reference.npz")
+    i0, i1, thr = loftr_case(ci)
+    eng = loftr.LoFTR(sd, batch=1, height=i0.shape[2], width=i0.shape[3], cfg={"thr": thr}, graph=False)
+    out = eng.forward(i0.cuda(), i1.cuda())
+    ref = set(zip(G[f"c{ci}_i_ids"].tolist(), G[f"c{ci}_j_ids"].tolist()))
+    got = set(zip(out["i_ids"].tolist(), out["j_ids"].tolist()))
+    assert len(ref & got) >= 0.8 * len(ref | got)
+    ridx = {k: n for n, k in enumerate(zip(G[f"c{ci}_i_ids"].tolist(), G[f"c{ci}_j_ids"].tolist()))}
+    gidx = {k: n for n, k in enumerate(zip(out["i_ids"].tolist(), out["j_ids"].tolist()))}
+    for k in ref & got:
+        assert np.abs(out["mkpts1_f"][gidx[k]].cpu().numpy() - G[f"c{ci}_mkpts1_f"][ridx[k]]).max() < PIX_TOL
+        assert np.array_equal(out["mkpts0_f"][gidx[k]].cpu().numpy(), G[f"c{ci}_mkpts0_f"][ridx[k]])
+    eng.close()
+
+
+def _coarse_match(mfr, mat, h_c, w_c, thr, border, is_conf):
+    lib = mfr.load()
+    B, L, _ = mat.shape
+    dev = mat.device
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev); off = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+    ids = [torch.zeros(B * L, dtype=torch.int32, device=dev) for _ in range(3)]
+    mconf = torch.zeros(B * L, device=dev); mk0 = torch.zeros(B * L, 2, device=dev); mk1 = torch.zeros(B * L, 2, device=dev)
+    mfr.check(lib.mfr_coarse_match(mfr.ptr(mat), B, h_c, w_c, thr, border, 8.0, int(is_conf), mfr.ptr(cnt), mfr.ptr(off),
+                                   mfr.ptr(ids[0]), mfr.ptr(ids[1]), mfr.ptr(ids[2]), mfr.ptr(mconf), mfr.ptr(mk0),
+                                   mfr.ptr(mk1), mfr.cur_stream()))
+    m = int(cnt.item())
+    return [t[:m].cpu() for t in ids] + [mconf[:m].cpu(), mk0[:m].cpu(), mk1[:m].cpu(), off.cpu()]
+
+
+def test_selection_bit_exact_given_conf(mfr):
+    """Stage boundary: identical fp32 confidence matrix in -> identical int indices out, including exact
+    ties (lowest column wins, coarse_matching.py:187-193) and the 2-cell border removal (:8-25)."""
+    g = torch.Generator().manual_seed(3)
+    B, h_c, w_c = 2, 12, 9
+    L = h_c * w_c
+    conf = torch.rand(B, L, L, generator=g) * 0.15
+    perm = torch.randperm(L, generator=g)
+    for b in range(B):
+        for i in range(0, L, 2):
+            conf[b, i, perm[i]] = 0.3 + 0.6 * torch.rand(1, generator=g).item()
+    conf[0, 30, 40] = conf[0, 30, 41] = 0.99   # exact tie inside one row
+    conf[1, 50, 20] = conf[1, 51, 20] = 0.98   # exact tie inside one column
+    bo, io, jo, mo = lo.coarse_select(conf, h_c, w_c, h_c, w_c, 0.2, 2)
+    b_, i_, j_, mc, mk0, mk1, off = _coarse_match(mfr, conf.cuda().contiguous(), h_c, w_c, 0.2, 2, True)
+    assert torch.equal(b_.long(), bo) and torch.equal(i_.long(), io) and torch.equal(j_.long(), jo)
+    assert torch.equal(mc, mo)
+    assert torch.equal(mk0, torch.stack([io % w_c, io // w_c], 1).float() * 8)
+    assert torch.equal(mk1, torch.stack([jo % w_c, jo // w_c], 1).float() * 8)
+    assert off.tolist() == [0, int((bo == 0).sum()), len(bo)]
+
+
+def test_dual_softmax_selection_matches_oracle(mfr):
+    g = torch.Generator().manual_seed(4)
+    B, h_c, w_c = 1, 16, 11
+    L = h_c * w_c
+    f0 = torch.randn(B, L, 64, generator=g)
+    f1 = f0[:, torch.randperm(L, generator=g)] + 0.05 * torch.randn(B, L, 64, generator=g)
+    sim = torch.einsum("nlc,nsc->nls", f0, f1) / 0.8
+    conf = torch.softmax(sim, 1) * torch.softmax(sim, 2)
+    bo, io, jo, mo = lo.coarse_select(conf, h_c, w_c, h_c, w_c, 0.2, 2)
+    b_, i_, j_, mc, _, _, _ = _coarse_match(mfr, sim.cuda().contiguous(), h_c, w_c, 0.2, 2, False)
+    assert len(io) > 20
+    assert torch.equal(i_.long(), io) and torch.equal(j_.long(), jo)
+    torch.testing.assert_close(mc, mo, rtol=1e-4, atol=1e-6)
+
+
+def test_empty_match_set(sd):
+    from mfr_b200 import loftr
+    i0, i1 = _pairs(1, 96, 96)
+    eng = loftr.LoFTR(sd, batch=1, height=96, width=96, cfg={"thr": 0.999}, graph=False)
+    out = eng.forward(i0.cuda(), i1.cuda())
+    assert out["M"] == 0 and out["mkpts0_f"].shape == (0, 2)
+    m = loftr.LoFTR_matcher.__new__(loftr.LoFTR_matcher)
+    m.engine, m.resize = eng, (96, 96)
+    pts = m.match_arrays(i0[0, 0].numpy(), i1[0, 0].numpy())
+    assert pts.shape == (1, 4) and np.isnan(pts).all()      # matchers.py:58-59 NaN row
+    eng.close()
