@@ -20,14 +20,16 @@ namespace mfr {
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kBlockK = 32;                     // fp32 elements per k-block = 128 B = swizzle span
 constexpr int kUmmaK = 8;                       // tf32: 32 B of K per instruction
 constexpr int kTileM = 128;
 constexpr int kMaxBN = 256;
 constexpr int kAStage = kTileM * kBlockK * 4;   // 16 KB
-constexpr int kBStage = kMaxBN * kBlockK * 4;   // 32 KB
-constexpr int kSmemBytes = kStages * (kAStage + kBStage) + 1024 /*align slack*/;
+constexpr int kRingBytes = 192 * 1024;          // operand ring: stages = kRingBytes / (16 KB + BN * 128 B)
+constexpr int kStgStride = 36;                  // floats per staged row (144 B: conflict-free 128-bit access)
+constexpr int kStgBytes = 4 * 32 * kStgStride * 4;  // epilogue transpose buffers, one per epilogue warp
+constexpr int kSmemBytes = kRingBytes + kStgBytes + 1024 /*align slack*/;
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
 
@@ -48,17 +50,20 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bars[2 * kStages + 4];
+  __shared__ __align__(8) uint64_t s_bars[2 * kMaxStages + 4];
   __shared__ uint32_t s_tmem_base;
+  const int kStages = p.num_stages;
+  const int kBStage = p.b_bytes;                 // BN rows x 128 B
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + kStages * kAStage;
+  const uint32_t smem_stg = smem_base + kRingBytes;
   const uint32_t bar_base = smem_u32(s_bars);
-  // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+  // barriers: full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -159,13 +164,18 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps)
+    // TMEM -> registers (thread = output pixel) -> per-warp shared-memory transpose -> coalesced
+    // global stores (8 lanes cover 128 contiguous bytes of one pixel, 4 pixels per instruction).
     const int q = warp & 3;  // TMEM lane quadrant this warp is allowed to read
     const int row = q * 32 + lane;
     const int ly = row / p.TW, lx = row - ly * p.TW;
     const bool vec_ok = ((p.Cout & 3) == 0) && ((p.ldo & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                        (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
                         (p.residual == nullptr ||
                          (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)));
+    const uint32_t stg = smem_stg + static_cast<uint32_t>(q) * (32 * kStgStride * 4);
+    const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -177,8 +187,6 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       const int y = ty * p.TH + ly, x = tx * p.TW + lx;
       const bool row_ok = (row < p.TW * p.TH) && (y < p.Ho) && (x < w_lim);
       const long long pix = (static_cast<long long>(img) * p.Ho + y) * p.Wo + x;
-      float* orow = p.out + pix * p.ldo;
-      const float* rrow = p.residual ? p.residual + pix * p.ldr : nullptr;
       const int n0 = nt * p.BN;
 
       mbar_wait(tfull_bar(acc), acc_phase, 4);
@@ -190,42 +198,54 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
         tmem_ld_wait();
-        if (row_ok) {
-          if (vec_ok) {
+        if (vec_ok) {
+          // stage: this thread's pixel, 32 consecutive channels
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const int n = n0 + c0 + j;
-              if (n < p.Cout) {
-                float4 v;
-                v.x = __uint_as_float(r[j + 0]) * p.alpha;
-                v.y = __uint_as_float(r[j + 1]) * p.alpha;
-                v.z = __uint_as_float(r[j + 2]) * p.alpha;
-                v.w = __uint_as_float(r[j + 3]) * p.alpha;
-                if (p.bias) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                  v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                }
-                if (rrow) {
-                  const float4 s = __ldg(reinterpret_cast<const float4*>(rrow + n));
-                  v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
-                }
-                if (n < p.act_cols) {
-                  v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
-                  v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
-                }
-                *reinterpret_cast<float4*>(orow + n) = v;
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * (kStgStride * 4) + j * 16),
+                         "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                         : "memory");
+          __syncwarp();
+          const int n = n0 + c0 + sub_c;
+          const bool n_ok = n < p.Cout;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr && n_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          const bool do_act = n < p.act_cols;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int rr = k * 4 + sub_r;
+            const long long pix_r = __shfl_sync(0xffffffffu, pix, rr);
+            const bool ok_r = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, rr) != 0;
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(stg + rr * (kStgStride * 4) + sub_c * 4));
+            if (ok_r && n_ok) {
+              v.x = fmaf(v.x, p.alpha, b4.x); v.y = fmaf(v.y, p.alpha, b4.y);
+              v.z = fmaf(v.z, p.alpha, b4.z); v.w = fmaf(v.w, p.alpha, b4.w);
+              if (p.residual != nullptr) {
+                const float4 sres = __ldg(reinterpret_cast<const float4*>(p.residual + pix_r * p.ldr + n));
+                v.x += sres.x; v.y += sres.y; v.z += sres.z; v.w += sres.w;
               }
+              if (do_act) {
+                v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
+                v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+              }
+              *reinterpret_cast<float4*>(p.out + pix_r * p.ldo + n) = v;
             }
-          } else {
+          }
+          __syncwarp();
+        } else if (row_ok) {
+          float* orow = p.out + pix * p.ldo;
+          const float* rrow = p.residual ? p.residual + pix * p.ldr : nullptr;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = n0 + c0 + j;
-              if (n < p.Cout) {
-                float v = __uint_as_float(r[j]) * p.alpha;
-                if (p.bias) v += __ldg(p.bias + n);
-                if (rrow) v += __ldg(rrow + n);
-                orow[n] = n < p.act_cols ? apply_act(v, p.act) : v;
-              }
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < p.Cout) {
+              float v = __uint_as_float(r[j]) * p.alpha;
+              if (p.bias) v += __ldg(p.bias + n);
+              if (rrow) v += __ldg(rrow + n);
+              orow[n] = n < p.act_cols ? apply_act(v, p.act) : v;
             }
           }
         }
@@ -325,14 +345,21 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
   choose_tile(p->Wo, p->Ho, d.stride, &p->TW, &p->TH);
   p->tiles_x = (p->Wo + p->TW - 1) / p->TW;
   p->tiles_y = (p->Ho + p->TH - 1) / p->TH;
-  // N tile: whole Cout when it fits one UMMA (<= 256), else equal 16-aligned slices.
+  // N tile: whole Cout when it fits one UMMA (<= 256), else equal 16-aligned slices; problems with
+  // fewer tiles than SMs are cut into narrower N tiles (down to 64) so that more SMs take part.
   const int c16 = (d.Cout + 15) / 16 * 16;
-  p->n_tiles = (c16 + kMaxBN - 1) / kMaxBN;
+  const int m_tiles = p->N * p->tiles_x * p->tiles_y;
+  int max_bn = kMaxBN;
+  while (max_bn > 64 && static_cast<long long>(m_tiles) * ((c16 + max_bn - 1) / max_bn) < conv_gemm_num_sms() &&
+         c16 > max_bn / 2)
+    max_bn /= 2;
+  p->n_tiles = (c16 + max_bn - 1) / max_bn;
   p->BN = ((c16 / 16 + p->n_tiles - 1) / p->n_tiles) * 16;
   p->kb_per_tap = (d.Cin + kBlockK - 1) / kBlockK;
   p->b_batched = d.b_batched;
   p->a_bytes = p->TW * p->TH * kBlockK * 4;
   p->b_bytes = p->BN * kBlockK * 4;
+  p->num_stages = std::min(kMaxStages, kRingBytes / (kAStage + p->b_bytes));  // BN*128 B is 2 KB aligned
   p->act = d.act;
   p->act_cols = d.act_cols > 0 ? d.act_cols : d.Cout;
   p->dyn_w = d.dyn_w;
@@ -409,12 +436,12 @@ int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream) {
 namespace {
 __global__ void __launch_bounds__(kThreads, 1) overhead_probe_kernel(int mode, int* sink) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bars[2 * kStages + 4];
+  __shared__ __align__(8) uint64_t s_bars[2 * kMaxStages + 4];
   __shared__ uint32_t s_tmem_base;
   if (mode == 0) return;
   const int warp = threadIdx.x >> 5;
   if (mode >= 2 && threadIdx.x == 0) {
-    for (int s = 0; s < 2 * kStages + 4; ++s) mbar_init(smem_u32(s_bars) + 8u * s, 1);
+    for (int s = 0; s < 2 * kMaxStages + 4; ++s) mbar_init(smem_u32(s_bars) + 8u * s, 1);
     fence_barrier_init();
   }
   if (warp == 1) {

@@ -20,7 +20,8 @@ struct alignas(64) ConvGemmParams {
   int R, S, stride, pad;
   int TW, TH, tiles_x, tiles_y;
   int BN, n_tiles, kb_per_tap, b_batched;
-  int a_bytes, b_bytes;
+  int a_bytes, b_bytes;   // TMA transaction bytes per stage
+  int num_stages;         // operand ring depth = 192 KB / (16 KB + BN * 128 B), at most 8
   int act, act_cols;    // activation applies to output channels < act_cols
   const int* dyn_w;     // optional device int: effective W (rows of a token GEMM), H must be 1
   float alpha;

@@ -137,10 +137,22 @@ __global__ void __launch_bounds__(256) kv_partial_kernel(const float* __restrict
   for (int s0 = s_beg; s0 < s_end; s0 += kKvTok) {
     const int cnt = min(kKvTok, s_end - s0);
     __syncthreads();
-    for (int r = 0; r < cnt; ++r) sK[r][t] = K[(static_cast<size_t>(n) * S + s0 + r) * ldk + t];
+    float vreg[kKvTok];
+#pragma unroll
+    for (int r = 0; r < kKvTok; ++r) {   // all loads of the slab are issued before any is consumed
+      float kk = 0.f, vv = 0.f;
+      if (r < cnt) {
+        const size_t row = static_cast<size_t>(n) * S + s0 + r;
+        kk = K[row * ldk + t];
+        vv = V[row * ldv + t];
+      }
+      sK[r][t] = kk;
+      vreg[r] = __fdiv_rn(vv, fS);
+    }
     __syncthreads();
-    for (int r = 0; r < cnt; ++r) {
-      const float vv = __fdiv_rn(V[(static_cast<size_t>(n) * S + s0 + r) * ldv + t], fS);
+#pragma unroll
+    for (int r = 0; r < kKvTok; ++r) {
+      const float vv = vreg[r];
       const float4* kr = reinterpret_cast<const float4*>(&sK[r][h * 32]);
 #pragma unroll
       for (int d4 = 0; d4 < 8; ++d4) {
@@ -263,11 +275,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         float* __restrict__ out, long long ldo,
                                                         long long rows, const int* __restrict__ dyn_rows) {
   constexpr int V = C / 128;  // float4 per lane
-  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   long long lim = rows;
   if (dyn_rows) lim = min(lim, static_cast<long long>(*dyn_rows));
-  if (row >= lim) return;
   const int lane = threadIdx.x & 31;
+  for (long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5); row < lim;
+       row += static_cast<long long>(gridDim.x) * 8) {
   float x[4 * V];
 #pragma unroll
   for (int k = 0; k < V; ++k) {
@@ -300,6 +312,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
     *reinterpret_cast<float4*>(out + row * ldo + c) = o;
+  }
   }
 }
 
@@ -700,7 +713,7 @@ int linear_attention_windows(const float* Q, long long ldq, const float* K, long
 int layernorm_rows(const float* in, long long ldi, const float* gamma, const float* beta,
                    const float* res, long long ldr, float* out, long long ldo, long long rows, int C,
                    const int* dyn_rows, cudaStream_t st) {
-  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  unsigned grid = static_cast<unsigned>(std::min<long long>((rows + 7) / 8, 148LL * 16));
   if (grid == 0) return MFR_OK;
   if (C == 256)
     layernorm_kernel<256><<<grid, 256, 0, st>>>(in, ldi, gamma, beta, res, ldr, out, ldo, rows, dyn_rows);
