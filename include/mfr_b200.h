@@ -96,6 +96,15 @@ int mfr_coarse_match(const float* sim, int B, int h_c, int w_c, float thr, int b
                      int input_is_conf, int* count, int* offsets, int* b_ids, int* i_ids, int* j_ids,
                      float* mconf, float* mkpts0_c, float* mkpts1_c, void* stream);
 
+/* Exact 2-nearest-neighbour search (L2) of every query descriptor among the train descriptors:
+ * the matcher of the reference's SIFT plugin (lib/models/matching/feature_matching.py:87-99),
+ * knnMatch(k=2), as an exact brute-force search (the reference's FLANN kd-tree is approximate and
+ * non-deterministic). query float[nq][dim], train float[nt][dim], dim % 4 == 0, dim <= 256 (device).
+ * Outputs (device): idx1/idx2 int[nq] (-1 if absent), dist1/dist2 float[nq] (Euclidean). Ties go
+ * to the lower index. */
+int mfr_knn2_l2(const float* query, int nq, const float* train, int nt, int dim, int* idx1,
+                float* dist1, int* idx2, float* dist2, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Pose back end (batched-hypothesis RANSAC). Replaces lib/models/matching/pose_solver.py.
  * Correspondences of P pairs are concatenated: kpts0/kpts1 device float[total][2] in pixels (x,y),

@@ -7,6 +7,7 @@
 #include "loftr_ops.cuh"
 #include "geometry_solvers.cuh"
 #include "geometry.cuh"
+#include "descriptor_match.cuh"
 
 extern "C" {
 
@@ -102,6 +103,11 @@ int mfr_coarse_match(const float* sim, int B, int h_c, int w_c, float thr, int b
   cudaStreamSynchronize(st);
   mfr::coarse_match_free(&b);
   return rc;
+}
+
+int mfr_knn2_l2(const float* query, int nq, const float* train, int nt, int dim, int* idx1, float* dist1,
+                int* idx2, float* dist2, void* stream) {
+  return mfr::knn2_l2(query, nq, train, nt, dim, idx1, dist1, idx2, dist2, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------ pose back end

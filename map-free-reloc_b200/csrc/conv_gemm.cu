@@ -46,6 +46,39 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_ELU1) return v > 0.f ? v + 1.f : __expf(v);
   return v;
 }
+template <int ACT>
+__device__ __forceinline__ float act_fn(float v) {
+  if constexpr (ACT == ACT_RELU) return fmaxf(v, 0.f);
+  if constexpr (ACT == ACT_LEAKY) return v > 0.f ? v : 0.01f * v;
+  if constexpr (ACT == ACT_ELU1) return v > 0.f ? v + 1.f : __expf(v);
+  return v;
+}
+
+// Coalesced part of the epilogue for one 32-channel chunk: 8 x (LDS.128 -> alpha/bias/residual/act ->
+// STG.128); lane (sub_r, sub_c) handles staged row k*4+sub_r, channels sub_c..sub_c+3.
+template <int ACT, bool RES>
+__device__ __forceinline__ void store_chunk(const float* __restrict__ stg_rd, const long long (&off_o)[8],
+                                            const long long (&off_r)[8], uint32_t okmask, float alpha,
+                                            float4 b4, const float* __restrict__ res_n,
+                                            float* __restrict__ out_n) {
+  float4 vv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) vv[k] = *reinterpret_cast<const float4*>(stg_rd + k * (4 * kStgStride));
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float4 v = vv[k];
+    if (okmask & (1u << k)) {
+      v.x = fmaf(v.x, alpha, b4.x); v.y = fmaf(v.y, alpha, b4.y);
+      v.z = fmaf(v.z, alpha, b4.z); v.w = fmaf(v.w, alpha, b4.w);
+      if constexpr (RES) {
+        const float4 r4 = __ldg(reinterpret_cast<const float4*>(res_n + off_r[k]));
+        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+      }
+      v.x = act_fn<ACT>(v.x); v.y = act_fn<ACT>(v.y); v.z = act_fn<ACT>(v.z); v.w = act_fn<ACT>(v.w);
+      *reinterpret_cast<float4*>(out_n + off_o[k]) = v;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -174,7 +207,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
                         (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
                         (p.residual == nullptr ||
                          (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)));
-    const uint32_t stg = smem_stg + static_cast<uint32_t>(q) * (32 * kStgStride * 4);
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem_stg - smem_u32(smem_raw))) + q * (32 * kStgStride);
     const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -188,6 +221,17 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       const bool row_ok = (row < p.TW * p.TH) && (y < p.Ho) && (x < w_lim);
       const long long pix = (static_cast<long long>(img) * p.Ho + y) * p.Wo + x;
       const int n0 = nt * p.BN;
+      // rows this lane stores in the coalesced phase: staged row k*4+sub_r of this warp's 32 pixels
+      long long off_o[8], off_r[8];
+      uint32_t okmask = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int rr = k * 4 + sub_r;
+        const long long pr = __shfl_sync(0xffffffffu, pix, rr);
+        okmask |= (__shfl_sync(0xffffffffu, row_ok ? 1 : 0, rr) != 0 ? 1u : 0u) << k;
+        off_o[k] = pr * p.ldo;
+        off_r[k] = pr * p.ldr;
+      }
 
       mbar_wait(tfull_bar(acc), acc_phase, 4);
       tc_fence_after();
@@ -196,45 +240,43 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
                              (static_cast<uint32_t>(q * 32) << 16);
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t r[32];
+        if (it == 0 && c0 == 0 && threadIdx.x == 64) MFR_STAMP(9);
         tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
         tmem_ld_wait();
+        if (it == 0 && c0 == 0 && threadIdx.x == 64) MFR_STAMP(10);
         if (vec_ok) {
           // stage: this thread's pixel, 32 consecutive channels
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * (kStgStride * 4) + j * 16),
-                         "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
-                         : "memory");
+            *reinterpret_cast<uint4*>(stg + lane * kStgStride + j * 4) =
+                make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
           __syncwarp();
+          if (it == 0 && c0 == 0 && threadIdx.x == 64) MFR_STAMP(11);
           const int n = n0 + c0 + sub_c;
-          const bool n_ok = n < p.Cout;
+          const uint32_t okm = n < p.Cout ? okmask : 0u;
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr && n_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-          const bool do_act = n < p.act_cols;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int rr = k * 4 + sub_r;
-            const long long pix_r = __shfl_sync(0xffffffffu, pix, rr);
-            const bool ok_r = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, rr) != 0;
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                         : "r"(stg + rr * (kStgStride * 4) + sub_c * 4));
-            if (ok_r && n_ok) {
-              v.x = fmaf(v.x, p.alpha, b4.x); v.y = fmaf(v.y, p.alpha, b4.y);
-              v.z = fmaf(v.z, p.alpha, b4.z); v.w = fmaf(v.w, p.alpha, b4.w);
-              if (p.residual != nullptr) {
-                const float4 sres = __ldg(reinterpret_cast<const float4*>(p.residual + pix_r * p.ldr + n));
-                v.x += sres.x; v.y += sres.y; v.z += sres.z; v.w += sres.w;
-              }
-              if (do_act) {
-                v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
-                v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
-              }
-              *reinterpret_cast<float4*>(p.out + pix_r * p.ldo + n) = v;
+          if (p.bias != nullptr && okm) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          const int act = n < p.act_cols ? p.act : ACT_NONE;   // n..n+3 never straddle act_cols (multiple of 4)
+          const float* stg_rd = stg + sub_r * kStgStride + sub_c;
+          float* out_n = p.out + n;
+          const float* res_n = p.residual + n;
+          if (p.residual != nullptr) {
+            switch (act) {
+              case ACT_RELU: store_chunk<ACT_RELU, true>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
+              case ACT_LEAKY: store_chunk<ACT_LEAKY, true>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
+              case ACT_ELU1: store_chunk<ACT_ELU1, true>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
+              default: store_chunk<ACT_NONE, true>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
+            }
+          } else {
+            switch (act) {
+              case ACT_RELU: store_chunk<ACT_RELU, false>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
+              case ACT_LEAKY: store_chunk<ACT_LEAKY, false>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
+              case ACT_ELU1: store_chunk<ACT_ELU1, false>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
+              default: store_chunk<ACT_NONE, false>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
             }
           }
           __syncwarp();
+          if (it == 0 && c0 == 0 && threadIdx.x == 64) MFR_STAMP(12);
         } else if (row_ok) {
           float* orow = p.out + pix * p.ldo;
           const float* rrow = p.residual ? p.residual + pix * p.ldr : nullptr;
@@ -487,10 +529,11 @@ float conv_gemm_time_prebuilt(const ConvGemmParams& p, int iters, cudaStream_t s
     long long h[16];
     cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(d);
-    const char* names[9] = {"start", "setup done", "first TMA issued", "last TMA issued", "first stage landed",
-                            "last stage landed", "accumulator ready", "epilogue done", "exit"};
+    const char* names[13] = {"start", "setup done", "first TMA issued", "last TMA issued", "first stage landed",
+                             "last stage landed", "accumulator ready", "epilogue done", "exit", "c0 begin",
+                             "c0 tmem loaded", "c0 staged", "c0 stored"};
     fprintf(stderr, "[conv_gemm stamps, block 0, ns since start]");
-    for (int i = 0; i < 9; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] ? h[i] - h[0] : -1);
+    for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] ? h[i] - h[0] : -1);
     fprintf(stderr, "\n");
   }
   cudaEvent_t e0, e1;

@@ -13,8 +13,8 @@ from mfr_b200 import synth  # noqa: E402
 
 POSE_CASES = [(11, 400, 0.6, 0.3), (12, 800, 0.5, 0.5), (13, 300, 0.8, 0.0), (14, 1000, 0.4, 1.0),
               (15, 4, 1.0, 0.0), (16, 600, 0.7, 0.2)]
-GOLD_H, GOLD_W = 180, 136
-GOLD_K = np.array([[150.0, 0, 67.5], [0, 150.0, 89.5], [0, 0, 1]])
+GOLD_H, GOLD_W = 720, 540
+GOLD_K = np.array([[600.0, 0, 269.5], [0, 600.0, 359.5], [0, 0, 1]])
 
 
 def pose_case(ci):

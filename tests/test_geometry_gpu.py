@@ -104,25 +104,21 @@ def test_failure_conventions(solvers):
     assert n == 0 and np.isnan(R).all()
 
 
-@pytest.mark.parametrize("ci", [0, 1, 3, 5])
+@pytest.mark.parametrize("ci", [0, 1, 2, 3, 5])
 def test_vs_reference_golden(solvers, ci):
-    """CUDA path vs the committed outputs of the UNMODIFIED reference (PnP: raw tolerance;
-    E-mat metric: no worse than the reference against ground truth)."""
+    """CUDA path vs the committed outputs of the UNMODIFIED reference on the same seeded inputs.
+    PnP: raw tolerance (2e-3 covers the 1 px-noise case, where two RANSAC runs keep different
+    borderline inliers); E-mat metric: no worse than the reference against ground truth."""
     G = np.load(GOLDEN + "/pose_solver_reference.npz")
     c = pose_case(ci)
     R, t, n = solvers[2].estimate_pose(c["kpts0"], c["kpts1"], _data(c))
-    # low-resolution fixtures (f = 150 px, 3 px threshold): the inlier sets of two RANSAC runs differ
-    # more than at f = 600, so the tolerance is 5e-3 here; the 1e-3 bar is test_pnp_matches_oracle
-    assert rot_angle(R, G[f"c{ci}_PNP_R"]) < 5e-3
-    assert np.linalg.norm(t.ravel() - G[f"c{ci}_PNP_t"]) < 5e-3
+    tol = 2e-3 if POSE_CASES[ci][3] >= 1.0 else 1e-3
+    assert rot_angle(R, G[f"c{ci}_PNP_R"]) < tol
+    assert np.linalg.norm(t.ravel() - G[f"c{ci}_PNP_t"]) < tol
+    assert abs(n - int(G[f"c{ci}_PNP_inliers"])) <= max(3, 0.02 * n)
     Rm, tm, nm = solvers[1].estimate_pose(c["kpts0"], c["kpts1"], _data(c))
-    ref_err = np.linalg.norm(G[f"c{ci}_EssentialMatrixMetric_t"] - c["t_gt"])
-    # these low-resolution cases (f = 150 px, 2 px threshold) leave the translation direction weakly
-    # constrained; where the reference itself is off by decimetres the metric translation is not a
-    # meaningful comparison, the rotation still is
-    if ref_err < 0.05:
-        assert np.linalg.norm(tm.ravel() - c["t_gt"]) <= ref_err + 2e-3
-    assert rot_angle(Rm, c["R_gt"]) <= rot_angle(G[f"c{ci}_EssentialMatrixMetric_R"], c["R_gt"]) + 2e-3
+    assert rot_angle(Rm, c["R_gt"]) <= rot_angle(G[f"c{ci}_EssentialMatrixMetric_R"], c["R_gt"]) + 1e-3
+    assert np.linalg.norm(tm.ravel() - c["t_gt"]) <= np.linalg.norm(G[f"c{ci}_EssentialMatrixMetric_t"] - c["t_gt"]) + 1e-3
 
 
 def test_batched_equals_single(solvers):
