@@ -84,6 +84,44 @@ int mfr_loftr_num_launches(const mfr_loftr* h); /* kernel launches per forward *
 int mfr_loftr_profile(mfr_loftr* h, const float* img0, const float* img1, int src_h, int src_w,
                       void* stream, int max_steps, float* ms, double* flops, int* kinds, char* names);
 
+/* ---------------------------------------------------------------------------------------------
+ * SuperPoint + SuperGlue matcher engine. Replaces Matching.forward of the reference
+ * (etc/feature_matching_baselines/SuperGlue/models/matching.py:56-84 = superpoint.py:145-202 x2 +
+ * superglue.py:228-283) as driven by SuperGlue_matcher.match (matchers.py:93-120), B pairs per
+ * call, images device fp32 [B][H][W] in [0,1]. Settings of matchers.py:65-71 are the defaults of
+ * the Python wrapper (nms 4, threshold 0.005, border 4, 1024 keypoints, 20 Sinkhorn iterations,
+ * match threshold 0.2). Weights in the engine's layout (mfr_spsg_weight_name enumerates them). */
+typedef struct mfr_spsg mfr_spsg;
+typedef struct {
+  const int* counts;             /* device int[2B], pair-interleaved (2p = image0 of pair p) */
+  const float* keypoints;        /* device float[2B][K][2] pixel (x,y) */
+  const float* scores;           /* device float[2B][K] */
+  const float* descriptors;      /* device float[2B][K][desc_ld] */
+  int desc_ld;
+  const int* matches0;           /* device int[B][K], -1 = unmatched (superglue.py:274) */
+  const float* matching_scores0; /* device float[B][K] */
+  const int* m_offsets;          /* device int[B+1] */
+  const float* mkpts0; const float* mkpts1; /* device float[total][2], ordered by (pair, i) */
+  int max_keypoints;
+} mfr_spsg_outputs;
+int mfr_spsg_create(int B, int H, int W, int max_keypoints, int nms_radius, float keypoint_threshold,
+                    int remove_borders, int sinkhorn_iterations, float match_threshold, mfr_spsg** out);
+void mfr_spsg_destroy(mfr_spsg* h);
+int mfr_spsg_num_weights(const mfr_spsg* h);
+const char* mfr_spsg_weight_name(const mfr_spsg* h, int i);
+long long mfr_spsg_weight_numel(const mfr_spsg* h, int i);
+int mfr_spsg_set_weight(mfr_spsg* h, int i, const float* host, long long numel, void* stream);
+int mfr_spsg_forward(mfr_spsg* h, const float* img0, const float* img1, void* stream);
+void mfr_spsg_set_graph(mfr_spsg* h, int enabled);
+int mfr_spsg_get_outputs(mfr_spsg* h, mfr_spsg_outputs* out);
+int mfr_spsg_debug_tensor(mfr_spsg* h, const char* name, float** ptr, long long* numel);
+int mfr_spsg_num_launches(const mfr_spsg* h);
+/* SuperGlue alone (superglue.py:228-283) on caller-supplied SuperPoint outputs, HOST arrays in the
+ * engine's layout: counts int[2B], keypoints float[2B][K][2], scores float[2B][K], descriptors
+ * float[2B][K][256] (unused slots zero). Stage-boundary entry point. */
+int mfr_spsg_forward_superglue(mfr_spsg* h, const int* counts, const float* keypoints, const float* scores,
+                               const float* descriptors, void* stream);
+
 /* Coarse matching on a materialised matrix (stage-boundary entry point of the LoFTR matcher):
  * CoarseMatching.forward dual-softmax + get_coarse_match of the reference
  * (LoFTR/src/loftr/utils/coarse_matching.py:109-119,175-196,242-259).

@@ -5,6 +5,7 @@
 #include "conv_gemm.cuh"
 #include "loftr_engine.cuh"
 #include "loftr_ops.cuh"
+#include "spsg_engine.cuh"
 #include "geometry_solvers.cuh"
 #include "geometry.cuh"
 #include "descriptor_match.cuh"
@@ -77,6 +78,46 @@ int mfr_loftr_profile(mfr_loftr* h, const float* img0, const float* img1, int sr
                       int max_steps, float* ms, double* flops, int* kinds, char* names) {
   return mfr::loftr_profile(h->e, img0, img1, src_h, src_w, static_cast<cudaStream_t>(stream), max_steps, ms, flops,
                             kinds, names);
+}
+
+// ------------------------------------------------------------------------------------------ SuperPoint + SuperGlue
+struct mfr_spsg { mfr::SpsgEngine* e; };
+int mfr_spsg_create(int B, int H, int W, int max_keypoints, int nms_radius, float keypoint_threshold,
+                    int remove_borders, int sinkhorn_iterations, float match_threshold, mfr_spsg** out) {
+  if (!out) return MFR_ERR_ARG;
+  mfr::SpsgEngine* e = nullptr;
+  int rc = mfr::spsg_create(B, H, W, max_keypoints, nms_radius, keypoint_threshold, remove_borders,
+                            sinkhorn_iterations, match_threshold, &e);
+  if (rc != MFR_OK) return rc;
+  *out = new mfr_spsg{e};
+  return MFR_OK;
+}
+void mfr_spsg_destroy(mfr_spsg* h) { if (h) { mfr::spsg_destroy(h->e); delete h; } }
+int mfr_spsg_num_weights(const mfr_spsg* h) { return mfr::spsg_num_weights(h->e); }
+const char* mfr_spsg_weight_name(const mfr_spsg* h, int i) { return mfr::spsg_weight_name(h->e, i); }
+long long mfr_spsg_weight_numel(const mfr_spsg* h, int i) { return mfr::spsg_weight_numel(h->e, i); }
+int mfr_spsg_set_weight(mfr_spsg* h, int i, const float* host, long long numel, void* stream) {
+  return mfr::spsg_set_weight(h->e, i, host, numel, static_cast<cudaStream_t>(stream));
+}
+int mfr_spsg_forward(mfr_spsg* h, const float* img0, const float* img1, void* stream) {
+  return mfr::spsg_forward(h->e, img0, img1, static_cast<cudaStream_t>(stream));
+}
+void mfr_spsg_set_graph(mfr_spsg* h, int enabled) { mfr::spsg_set_graph(h->e, enabled); }
+int mfr_spsg_get_outputs(mfr_spsg* h, mfr_spsg_outputs* out) {
+  if (!h || !out) return MFR_ERR_ARG;
+  mfr::SpsgOutputs o = mfr::spsg_outputs(h->e);
+  out->counts = o.counts; out->keypoints = o.keypoints; out->scores = o.scores; out->descriptors = o.descriptors;
+  out->desc_ld = o.desc_ld; out->matches0 = o.matches0; out->matching_scores0 = o.matching_scores0;
+  out->m_offsets = o.m_offsets; out->mkpts0 = o.mkpts0; out->mkpts1 = o.mkpts1; out->max_keypoints = o.max_keypoints;
+  return MFR_OK;
+}
+int mfr_spsg_debug_tensor(mfr_spsg* h, const char* name, float** ptr, long long* numel) {
+  return mfr::spsg_debug_tensor(h->e, name, ptr, numel);
+}
+int mfr_spsg_num_launches(const mfr_spsg* h) { return mfr::spsg_num_launches(h->e); }
+int mfr_spsg_forward_superglue(mfr_spsg* h, const int* counts, const float* keypoints, const float* scores,
+                               const float* descriptors, void* stream) {
+  return mfr::spsg_forward_superglue(h->e, counts, keypoints, scores, descriptors, static_cast<cudaStream_t>(stream));
 }
 
 int mfr_coarse_match(const float* sim, int B, int h_c, int w_c, float thr, int border_rm, float scale,

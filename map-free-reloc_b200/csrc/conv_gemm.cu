@@ -219,7 +219,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       const int img = mt / (tiles_x * p.tiles_y);
       const int y = ty * p.TH + ly, x = tx * p.TW + lx;
       const bool row_ok = (row < p.TW * p.TH) && (y < p.Ho) && (x < w_lim);
-      const long long pix = (static_cast<long long>(img) * p.Ho + y) * p.Wo + x;
+      const long long pix = static_cast<long long>(y) * p.Wo + x;   // pixel inside the image
       const int n0 = nt * p.BN;
       // rows this lane stores in the coalesced phase: staged row k*4+sub_r of this warp's 32 pixels
       long long off_o[8], off_r[8];
@@ -229,8 +229,8 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
         const int rr = k * 4 + sub_r;
         const long long pr = __shfl_sync(0xffffffffu, pix, rr);
         okmask |= (__shfl_sync(0xffffffffu, row_ok ? 1 : 0, rr) != 0 ? 1u : 0u) << k;
-        off_o[k] = pr * p.ldo;
-        off_r[k] = pr * p.ldr;
+        off_o[k] = img * p.out_img_stride + pr * p.ldo;
+        off_r[k] = img * p.res_img_stride + pr * p.ldr;
       }
 
       mbar_wait(tfull_bar(acc), acc_phase, 4);
@@ -278,8 +278,8 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
           __syncwarp();
           if (it == 0 && c0 == 0 && threadIdx.x == 64) MFR_STAMP(12);
         } else if (row_ok) {
-          float* orow = p.out + pix * p.ldo;
-          const float* rrow = p.residual ? p.residual + pix * p.ldr : nullptr;
+          float* orow = p.out + img * p.out_img_stride + pix * p.ldo;
+          const float* rrow = p.residual ? p.residual + img * p.res_img_stride + pix * p.ldr : nullptr;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + c0 + j;
@@ -412,12 +412,14 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
   p->ldr = d.ldr;
   p->out = d.out;
   p->ldo = d.ldo;
+  p->out_img_stride = d.out_img_stride > 0 ? d.out_img_stride : static_cast<long long>(p->Ho) * p->Wo * d.ldo;
+  p->res_img_stride = static_cast<long long>(p->Ho) * p->Wo * d.ldr;
   p->dbg = nullptr;
 
   {  // activations: {C, W, H, N}
     cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};
     cuuint64_t strides[3] = {(cuuint64_t)d.ldx * 4, (cuuint64_t)d.ldx * 4 * d.W,
-                             (cuuint64_t)d.ldx * 4 * d.W * d.H};
+                             d.x_img_stride > 0 ? (cuuint64_t)d.x_img_stride * 4 : (cuuint64_t)d.ldx * 4 * d.W * d.H};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(p->TW * d.stride),
                          (cuuint32_t)(p->TH * d.stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
@@ -437,7 +439,7 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
       const long long ldw = d.ldw > 0 ? d.ldw : d.Cin;
       if (ldw % 4) return MFR_ERR_ARG;
       dims[0] = d.Cin; dims[1] = d.N; dims[2] = d.Cout;
-      strides[0] = (cuuint64_t)d.Cout * ldw * 4;  // next image
+      strides[0] = d.w_img_stride > 0 ? (cuuint64_t)d.w_img_stride * 4 : (cuuint64_t)d.Cout * ldw * 4;  // next image
       strides[1] = (cuuint64_t)ldw * 4;           // next output row
     } else {
       dims[0] = d.Cin; dims[1] = taps; dims[2] = d.Cout;

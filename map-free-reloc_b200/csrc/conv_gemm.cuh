@@ -29,6 +29,7 @@ struct alignas(64) ConvGemmParams {
   const float* residual;
   float* out;
   long long ldr, ldo;
+  long long out_img_stride, res_img_stride;  // elements between images of out / residual
   long long* dbg;       // optional: block 0 writes globaltimer stamps (ns) at pipeline milestones
 };
 
@@ -43,6 +44,7 @@ struct ConvGemmDesc {
   long long ldw;       // batched only: row stride of w in floats (0 = Cin)
   int act_cols;        // 0 = all output channels
   const int* dyn_w;    // optional device row count (token GEMMs with data-dependent length)
+  long long x_img_stride, w_img_stride, out_img_stride;  // elements between images; 0 = dense
   const float* bias;   // [Cout] or null
   const float* residual;  // NHWC like out (pixel stride ldr) or null
   long long ldr;

@@ -22,6 +22,13 @@ class LoftrOutputs(ctypes.Structure):
                 ("mkpts1_c", c_vp), ("expec_f", c_vp), ("capacity", c_int)]
 
 
+class SpsgOutputs(ctypes.Structure):
+    """mfr_spsg_outputs of include/mfr_b200.h."""
+    _fields_ = [("counts", c_vp), ("keypoints", c_vp), ("scores", c_vp), ("descriptors", c_vp),
+                ("desc_ld", c_int), ("matches0", c_vp), ("matching_scores0", c_vp), ("m_offsets", c_vp),
+                ("mkpts0", c_vp), ("mkpts1", c_vp), ("max_keypoints", c_int)]
+
+
 c_pp = ctypes.POINTER(ctypes.c_void_p)
 
 # name -> (restype, argtypes); mirrors include/mfr_b200.h one to one
@@ -44,6 +51,18 @@ SIGNATURES = {
     "mfr_loftr_num_kernels": (c_int, [c_vp]),
     "mfr_loftr_num_launches": (c_int, [c_vp]),
     "mfr_loftr_profile": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "mfr_spsg_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_float, c_pp]),
+    "mfr_spsg_destroy": (None, [c_vp]),
+    "mfr_spsg_num_weights": (c_int, [c_vp]),
+    "mfr_spsg_weight_name": (ctypes.c_char_p, [c_vp, c_int]),
+    "mfr_spsg_weight_numel": (c_ll, [c_vp, c_int]),
+    "mfr_spsg_set_weight": (c_int, [c_vp, c_int, c_vp, c_ll, c_vp]),
+    "mfr_spsg_forward": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "mfr_spsg_set_graph": (None, [c_vp, c_int]),
+    "mfr_spsg_get_outputs": (c_int, [c_vp, ctypes.POINTER(SpsgOutputs)]),
+    "mfr_spsg_debug_tensor": (c_int, [c_vp, ctypes.c_char_p, c_pp, ctypes.POINTER(c_ll)]),
+    "mfr_spsg_num_launches": (c_int, [c_vp]),
+    "mfr_spsg_forward_superglue": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mfr_coarse_match": (c_int, [c_vp, c_int, c_int, c_int, c_float, c_int, c_float, c_int, c_vp, c_vp,
                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mfr_knn2_l2": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),

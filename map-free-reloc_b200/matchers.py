@@ -7,6 +7,7 @@ import numpy as np
 
 from .loftr import LoFTR_matcher
 from .model import knn2_gpu, root_sift
+from .spsg import SuperGlue_matcher
 
 
 class SIFT_matcher:
@@ -37,7 +38,7 @@ class SIFT_matcher:
         return np.concatenate([pts1, pts2], axis=1)
 
 
-MATCHERS = {"LoFTR": LoFTR_matcher, "SIFT": SIFT_matcher}
+MATCHERS = {"LoFTR": LoFTR_matcher, "SG": SuperGlue_matcher, "SIFT": SIFT_matcher}
 
 
 def stack_pts(pts_list):

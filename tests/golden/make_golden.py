@@ -90,7 +90,36 @@ def make_loftr_golden():
     print("loftr golden:", len(out), "arrays; M =", [len(out[f'c{i}_i_ids']) for i in range(2)])
 
 
+def spsg_case():
+    p = synth.make_pair(5)
+    g0 = synth.rgb_to_gray_u8(p["image0"]).astype(np.float32) / 255.0
+    return (torch.from_numpy(g0[40:280, 30:350].copy())[None, None], torch.from_numpy(g0[48:288, 46:366].copy())[None, None])
+
+
+def make_spsg_golden():
+    """Reference SuperPoint/SuperGlue modules with the synthetic seeded weights loaded over the
+    in-tree ones (same architecture), settings of matchers.py:65-71 except max_keypoints 256 and
+    match_threshold 0 (so that the tiny synthetic case has matches)."""
+    from mfr_b200 import spsg
+    SuperPoint, SuperGlue, Matching = ref_import.load_superglue()
+    sp_sd, sg_sd = spsg.synthetic_state_dicts(0)
+    m = Matching({"superpoint": {"nms_radius": 4, "keypoint_threshold": 0.005, "max_keypoints": 256},
+                  "superglue": {"weights": "indoor", "sinkhorn_iterations": 20, "match_threshold": 0.0}}).eval()
+    m.superpoint.load_state_dict(sp_sd)
+    m.superglue.load_state_dict(sg_sd)
+    i0, i1 = spsg_case()
+    with torch.no_grad():
+        pred = m({"image0": i0, "image1": i1})
+    out = {"checksum": checksum(i0.numpy(), i1.numpy())}
+    for k in ("keypoints0", "keypoints1", "scores0", "scores1", "matches0", "matching_scores0"):
+        out[k] = pred[k][0].numpy()
+    out["descriptors0_sample"] = pred["descriptors0"][0][::8, ::4].numpy()
+    np.savez_compressed(os.path.join(HERE, "spsg_reference.npz"), **out)
+    print("spsg golden: kpts", out["keypoints0"].shape, out["keypoints1"].shape, "matches", int((out["matches0"] > -1).sum()))
+
+
 if __name__ == "__main__":
     assert ref_import.available(), "needs /root/reference"
     make_pose_golden()
     make_loftr_golden()
+    make_spsg_golden()

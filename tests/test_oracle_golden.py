@@ -48,3 +48,27 @@ def test_loftr_oracle_reproduces_reference(ci):
     np.testing.assert_array_equal(o["mkpts0_f"].numpy(), GL[f"c{ci}_mkpts0_f"])
     np.testing.assert_allclose(o["mkpts1_f"].numpy(), GL[f"c{ci}_mkpts1_f"], atol=2e-4)  # pixels
     np.testing.assert_allclose(o["expec_f"].numpy(), GL[f"c{ci}_expec_f"], atol=1e-4)
+
+
+def test_spsg_oracle_reproduces_reference():
+    """SuperPoint + SuperGlue restatement vs the reference modules (synthetic seeded weights)."""
+    from mfr_b200 import spsg, synth
+    from oracle import spsg_oracle as so
+    GS = np.load(GOLDEN + "/spsg_reference.npz")
+    p = synth.make_pair(5)
+    g0 = synth.rgb_to_gray_u8(p["image0"]).astype(np.float32) / 255.0
+    i0 = torch.from_numpy(g0[40:280, 30:350].copy())[None, None]
+    i1 = torch.from_numpy(g0[48:288, 46:366].copy())[None, None]
+    assert checksum(i0.numpy(), i1.numpy()) == pytest.approx(float(GS["checksum"]), abs=1e-6)
+    sp, sg = spsg.synthetic_state_dicts(0)
+    cfg = {"max_keypoints": 256, "match_threshold": 0.0}
+    with torch.no_grad():
+        k0, s0, d0 = so.superpoint(i0, sp, cfg)
+        k1, s1, d1 = so.superpoint(i1, sp, cfg)
+        m0, ms0 = so.superglue(k0, s0, d0, k1, s1, d1, 240, 320, sg, cfg)
+    np.testing.assert_array_equal(k0.numpy(), GS["keypoints0"])      # integer-valued keypoints: exact
+    np.testing.assert_array_equal(k1.numpy(), GS["keypoints1"])
+    np.testing.assert_allclose(s0.numpy(), GS["scores0"], rtol=1e-5)
+    np.testing.assert_allclose(d0[::8, ::4].numpy(), GS["descriptors0_sample"], atol=1e-5)
+    np.testing.assert_array_equal(m0.numpy(), GS["matches0"])        # integer matches: exact
+    np.testing.assert_allclose(ms0.numpy(), GS["matching_scores0"], atol=1e-5)

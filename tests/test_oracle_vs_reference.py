@@ -54,3 +54,32 @@ def test_loftr_module_matches_oracle():
     assert torch.equal(b["i_ids"], o["i_ids"]) and torch.equal(b["j_ids"], o["j_ids"])
     torch.testing.assert_close(b["conf_matrix"], o["conf"], rtol=1e-5, atol=1e-12)
     torch.testing.assert_close(b["mkpts1_f"], o["mkpts1_f"], atol=2e-4, rtol=0)
+
+
+def test_spsg_modules_match_oracle_with_real_weights():
+    """The in-tree SuperPoint/SuperGlue weights on an in-tree ScanNet sample pair: identical keypoints,
+    descriptors and matches (the reference README's known-answer pair, SuperGlue/README.md:121-127)."""
+    import cv2
+    from oracle import spsg_oracle as so
+    SuperPoint, SuperGlue, Matching = ref_import.load_superglue()
+    wdir = ref_import.FMB + "/SuperGlue/models/weights/"
+    sp_sd = torch.load(wdir + "superpoint_v1.pth", map_location="cpu")
+    sg_sd = torch.load(wdir + "superglue_indoor.pth", map_location="cpu")
+    adir = ref_import.FMB + "/SuperGlue/assets/scannet_sample_images/"
+
+    def load(n):
+        im = cv2.resize(cv2.imread(adir + n, cv2.IMREAD_GRAYSCALE).astype("float32"), (640, 480))
+        return torch.from_numpy(im / 255.0).float()[None, None]
+
+    i0, i1 = load("scene0711_00_frame-001680.jpg"), load("scene0711_00_frame-001995.jpg")
+    m = Matching({"superpoint": {"nms_radius": 4, "keypoint_threshold": 0.005, "max_keypoints": 1024},
+                  "superglue": {"weights": "indoor", "sinkhorn_iterations": 20, "match_threshold": 0.2}}).eval()
+    with torch.no_grad():
+        pred = m({"image0": i0, "image1": i1})
+        k0, s0, d0 = so.superpoint(i0, sp_sd)
+        k1, s1, d1 = so.superpoint(i1, sp_sd)
+        m0, ms0 = so.superglue(k0, s0, d0, k1, s1, d1, 480, 640, sg_sd)
+    assert torch.equal(k0, pred["keypoints0"][0]) and torch.equal(k1, pred["keypoints1"][0])
+    torch.testing.assert_close(d0, pred["descriptors0"][0], atol=1e-6, rtol=0)
+    assert torch.equal(m0, pred["matches0"][0]) and int((m0 > -1).sum()) > 100
+    torch.testing.assert_close(ms0, pred["matching_scores0"][0], atol=1e-5, rtol=0)
