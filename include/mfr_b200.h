@@ -184,6 +184,15 @@ int mfr_pnp_ransac(mfr_pose_solver* s, const float* kpts0, const float* kpts1, c
                    int num_hyp, float reproj_threshold, unsigned long long seed, float* R, float* t,
                    int* n_inliers, unsigned char* mask, void* stream);
 
+/* ProcrustesSolver.estimate_pose with REFINE = False (pose_solver.py:247-320): lift both keypoint sets
+ * through their depth maps (valid iff depth > depth.min() on both sides), RANSAC over 3-point Kabsch
+ * alignments with inlier distance max_corr_dist (metres), refit on the inliers. The reference calls
+ * Open3D's registration_ransac_based_on_correspondence for this step. */
+int mfr_procrustes_ransac(mfr_pose_solver* s, const float* kpts0, const float* kpts1, const int* offsets,
+                          int P, const float* K0, const float* K1, const float* depth0,
+                          const float* depth1, int H, int W, int num_hyp, float max_corr_dist,
+                          unsigned long long seed, float* R, float* t, int* n_inliers, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host test hooks: the minimal solvers used inside the RANSAC kernels are __host__ __device__
  * functions; these run the very same code on the CPU so that it can be unit-tested without a GPU.

@@ -189,6 +189,14 @@ int mfr_pnp_ransac(mfr_pose_solver* s, const float* kpts0, const float* kpts1, c
                          R, t, n_inliers, mask, static_cast<cudaStream_t>(stream));
 }
 
+int mfr_procrustes_ransac(mfr_pose_solver* s, const float* kpts0, const float* kpts1, const int* offsets, int P,
+                          const float* K0, const float* K1, const float* depth0, const float* depth1, int H, int W,
+                          int num_hyp, float max_corr_dist, unsigned long long seed, float* R, float* t,
+                          int* n_inliers, void* stream) {
+  return mfr::procrustes_ransac(s->s, kpts0, kpts1, offsets, P, K0, K1, depth0, depth1, H, W, num_hyp, max_corr_dist,
+                                seed, R, t, n_inliers, static_cast<cudaStream_t>(stream));
+}
+
 // ------------------------------------------------------------------------------------------ host test hooks
 int mfr_host_five_point(const double* x0, const double* x1, double* E_out) {
   return mfr::geo::five_point(reinterpret_cast<const double(*)[2]>(x0), reinterpret_cast<const double(*)[2]>(x1),

@@ -976,6 +976,267 @@ __global__ void __launch_bounds__(256) pnp_final_kernel(
   if (threadIdx.x == 0) n_inl[pair] = n_in;
 }
 
+
+// ================================================================================================
+// Procrustes (pose_solver.py:238-320, REFINE = False): 3-D/3-D correspondences from both depth maps,
+// RANSAC over 3-point Kabsch alignments, refit on the inliers. (The reference delegates this to
+// Open3D's registration_ransac_based_on_correspondence.)
+// ================================================================================================
+// R, t minimising sum |R p + t - q|^2 from the moment sums (n, sum p, sum q, sum p q^T)
+__device__ inline bool kabsch_from_sums(double n, const double* sp, const double* sq, const double* spq,
+                                        double* R, double* t) {
+  if (n < 3.0) return false;
+  double pb[3], qb[3], Hm[9];
+  for (int k = 0; k < 3; ++k) { pb[k] = sp[k] / n; qb[k] = sq[k] / n; }
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) Hm[3 * a + b] = spq[3 * a + b] - n * pb[a] * qb[b];
+  double M[9], V[9], w[3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) M[3 * i + j] = Hm[i] * Hm[j] + Hm[3 + i] * Hm[3 + j] + Hm[6 + i] * Hm[6 + j];  // H^T H
+  jacobi_eig3(M, V, w);
+  int o[3] = {0, 1, 2};
+  for (int a = 0; a < 2; ++a)
+    for (int b = a + 1; b < 3; ++b)
+      if (w[o[b]] > w[o[a]]) { const int tmp = o[a]; o[a] = o[b]; o[b] = tmp; }
+  double v0[3], v1[3], v2[3], u0[3], u1[3], u2[3];
+  for (int k = 0; k < 3; ++k) { v0[k] = V[3 * k + o[0]]; v1[k] = V[3 * k + o[1]]; }
+  cross3(v0, v1, v2);
+  mat3_vec(Hm, v0, u0);
+  mat3_vec(Hm, v1, u1);
+  const double n0 = norm3(u0);
+  if (!(n0 > 1e-12)) return false;
+  for (int k = 0; k < 3; ++k) u0[k] /= n0;
+  const double d01 = dot3(u0, u1);
+  for (int k = 0; k < 3; ++k) u1[k] -= d01 * u0[k];
+  const double n1 = norm3(u1);
+  if (!(n1 > 1e-12 * n0)) return false;     // collinear sample
+  for (int k = 0; k < 3; ++k) u1[k] /= n1;
+  cross3(u0, u1, u2);
+  // H = U S V^T  with U's columns u_i, V's columns v_i (both right-handed)  =>  R = V U^T
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) R[3 * a + b] = v0[a] * u0[b] + v1[a] * u1[b] + v2[a] * u2[b];
+  double Rp[3];
+  mat3_vec(R, pb, Rp);
+  for (int k = 0; k < 3; ++k) t[k] = qb[k] - Rp[k];
+  return true;
+}
+
+__global__ void __launch_bounds__(1024) procrustes_prepare_kernel(
+    const float* __restrict__ kpts0, const float* __restrict__ kpts1, const int* __restrict__ offsets,
+    const float* __restrict__ K0s, const float* __restrict__ K1s, const float* __restrict__ depth0,
+    const float* __restrict__ depth1, int H, int W, const unsigned int* __restrict__ dmin0,
+    const unsigned int* __restrict__ dmin1, int max_pts, double* __restrict__ X0, double* __restrict__ X1,
+    int* __restrict__ nvalid) {
+  __shared__ int wsum[32];
+  __shared__ int base;
+  __shared__ float s_Ki0[9], s_Ki1[9];
+  const int pair = blockIdx.x;
+  const int n0 = offsets[pair];
+  const int N = min(offsets[pair + 1] - n0, max_pts);
+  if (threadIdx.x == 0) { base = 0; inverse_K_f32(K0s + 9 * pair, s_Ki0); inverse_K_f32(K1s + 9 * pair, s_Ki1); }
+  __syncthreads();
+  const float m0 = __uint_as_float(dmin0[pair]), m1 = __uint_as_float(dmin1[pair]);
+  const float* d0 = depth0 + static_cast<size_t>(pair) * H * W;
+  const float* d1 = depth1 + static_cast<size_t>(pair) * H * W;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < N; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    int flag = 0, u0 = 0, v0 = 0, u1 = 0, v1 = 0;
+    float z0 = 0.f, z1 = 0.f;
+    if (i < N) {
+      u0 = static_cast<int>(kpts0[2 * (n0 + i)]); v0 = static_cast<int>(kpts0[2 * (n0 + i) + 1]);
+      u1 = static_cast<int>(kpts1[2 * (n0 + i)]); v1 = static_cast<int>(kpts1[2 * (n0 + i) + 1]);
+      if (u0 >= 0 && u0 < W && v0 >= 0 && v0 < H && u1 >= 0 && u1 < W && v1 >= 0 && v1 < H) {
+        z0 = d0[v0 * W + u0]; z1 = d1[v1 * W + u1];
+        flag = (z0 > m0 && z1 > m1) ? 1 : 0;       // pose_solver.py:261
+      }
+    }
+    int inc = flag;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int tt = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += tt;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      int w = wsum[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int tt = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += tt;
+      }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    if (flag) {
+      const int slot = n0 + base + (wid > 0 ? wsum[wid - 1] : 0) + inc - 1;
+      double A[3], Bq[3];
+      backproject(s_Ki0, u0, v0, z0, A);
+      backproject(s_Ki1, u1, v1, z1, Bq);
+      for (int k = 0; k < 3; ++k) { X0[3 * slot + k] = A[k]; X1[3 * slot + k] = Bq[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) base += wsum[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) nvalid[pair] = base;
+}
+
+__global__ void __launch_bounds__(kHypPerBlock) procrustes_hyp_kernel(
+    const double* __restrict__ X0, const double* __restrict__ X1, const int* __restrict__ offsets,
+    const int* __restrict__ nvalid, float max_dist, int num_hyp, unsigned long long seed,
+    HypResult* __restrict__ results) {
+  extern __shared__ float s_raw[];
+  __shared__ HypResult s_best[kHypPerBlock / 32];
+  const int pair = blockIdx.y;
+  const int n0 = offsets[pair];
+  const int N = nvalid[pair];
+  HypResult* out = results + static_cast<size_t>(pair) * gridDim.x + blockIdx.x;
+  if (N < 3) {
+    if (threadIdx.x == 0) { out->valid = 0; out->cost = 1e300; out->count = 0; }
+    return;
+  }
+  float* sP = s_raw;          // [N][3]
+  float* sQ = s_raw + 3 * N;  // [N][3]
+  for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) {
+    sP[i] = static_cast<float>(X0[3 * static_cast<size_t>(n0) + i]);
+    sQ[i] = static_cast<float>(X1[3 * static_cast<size_t>(n0) + i]);
+  }
+  __syncthreads();
+  const float thr2 = max_dist * max_dist;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = blockIdx.x * kHypPerBlock + threadIdx.x;
+  double Rm[9], tm[3];
+  int have = 0;
+  if (h < num_hyp) {
+    unsigned long long st = seed ^ (0xC2B2AE3D27D4EB4Full * (static_cast<unsigned long long>(pair) + 1)) ^
+                            (0x9E3779B97F4A7C15ull * (static_cast<unsigned long long>(h) + 1));
+    int idx[3];
+    sample_distinct<3>(st, N, idx);
+    double sp[3] = {0, 0, 0}, sq[3] = {0, 0, 0}, spq[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 3; ++k) {
+      const double* pp = X0 + 3 * (static_cast<size_t>(n0) + idx[k]);
+      const double* qq = X1 + 3 * (static_cast<size_t>(n0) + idx[k]);
+      for (int a = 0; a < 3; ++a) {
+        sp[a] += pp[a]; sq[a] += qq[a];
+        for (int b = 0; b < 3; ++b) spq[3 * a + b] += pp[a] * qq[b];
+      }
+    }
+    have = kabsch_from_sums(3.0, sp, sq, spq, Rm, tm) ? 1 : 0;
+  }
+  int best_cnt = -1, best_src = -1;
+  float best_err = 3.0e38f;
+  for (int src = 0; src < 32; ++src) {
+    if (!__shfl_sync(0xffffffffu, have, src)) continue;
+    float R[9], t[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = __shfl_sync(0xffffffffu, static_cast<float>(Rm[k]), src);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t[k] = __shfl_sync(0xffffffffu, static_cast<float>(tm[k]), src);
+    int inl = 0;
+    float err = 0.f;
+    for (int i0 = 0; i0 < N; i0 += 32) {
+      const int i = i0 + lane;
+      bool ok = false;
+      if (i < N) {
+        const float X = sP[3 * i], Y = sP[3 * i + 1], Z = sP[3 * i + 2];
+        const float dx = fmaf(R[0], X, fmaf(R[1], Y, fmaf(R[2], Z, t[0]))) - sQ[3 * i];
+        const float dy = fmaf(R[3], X, fmaf(R[4], Y, fmaf(R[5], Z, t[1]))) - sQ[3 * i + 1];
+        const float dz = fmaf(R[6], X, fmaf(R[7], Y, fmaf(R[8], Z, t[2]))) - sQ[3 * i + 2];
+        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        ok = d2 < thr2;
+        if (ok) err += d2;
+      }
+      inl += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    err = warp_sum_f(err);
+    if (inl > best_cnt || (inl == best_cnt && err < best_err)) { best_cnt = inl; best_err = err; best_src = src; }
+  }
+  if (lane == 0) {
+    s_best[warp].valid = best_src >= 0 ? 1 : 0;
+    s_best[warp].cost = best_src >= 0 ? -static_cast<double>(best_cnt) + 1e-9 * best_err : 1e300;
+    s_best[warp].count = best_cnt;
+  }
+  if (best_src >= 0 && lane == best_src) {
+    for (int k = 0; k < 9; ++k) s_best[warp].model[k] = Rm[k];
+    for (int k = 0; k < 3; ++k) s_best[warp].model[9 + k] = tm[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int bw = 0;
+    for (int w = 1; w < kHypPerBlock / 32; ++w)
+      if (s_best[w].cost < s_best[bw].cost) bw = w;
+    *out = s_best[bw];
+  }
+}
+
+__global__ void __launch_bounds__(256) procrustes_final_kernel(
+    const double* __restrict__ X0, const double* __restrict__ X1, const int* __restrict__ offsets,
+    const int* __restrict__ nvalid, float max_dist, int blocks_per_pair, const HypResult* __restrict__ results,
+    float* __restrict__ Rf, float* __restrict__ tf, int* __restrict__ n_inl) {
+  __shared__ double sh_red[8 * 16];
+  __shared__ double s_R[9], s_t[3];
+  __shared__ int s_flag, s_cnt;
+  const int pair = blockIdx.x;
+  const int n0 = offsets[pair];
+  const int N = nvalid[pair];
+  auto fail = [&]() {
+    if (threadIdx.x < 9) Rf[9 * pair + threadIdx.x] = NAN;
+    if (threadIdx.x < 3) tf[3 * pair + threadIdx.x] = NAN;
+    if (threadIdx.x == 0) n_inl[pair] = 0;
+  };
+  if (threadIdx.x == 0) {
+    int b = -1;
+    if (N >= 3) {
+      const HypResult* r = results + static_cast<size_t>(pair) * blocks_per_pair;
+      for (int k = 0; k < blocks_per_pair; ++k)
+        if (r[k].valid && (b < 0 || r[k].cost < r[b].cost)) b = k;
+      if (b >= 0) {
+        for (int k = 0; k < 9; ++k) s_R[k] = r[b].model[k];
+        for (int k = 0; k < 3; ++k) s_t[k] = r[b].model[9 + k];
+      }
+    }
+    s_flag = b;
+  }
+  __syncthreads();
+  if (s_flag < 0) { fail(); return; }
+  const double thr2 = static_cast<double>(max_dist) * max_dist;
+  // refit on the inliers of the current model, re-select, twice (Open3D re-estimates on the inliers)
+  for (int round = 0; round < 3; ++round) {
+    double acc[16];
+    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const double* p = X0 + 3 * (static_cast<size_t>(n0) + i);
+      const double* q = X1 + 3 * (static_cast<size_t>(n0) + i);
+      double Rp[3];
+      mat3_vec(s_R, p, Rp);
+      const double dx = Rp[0] + s_t[0] - q[0], dy = Rp[1] + s_t[1] - q[1], dz = Rp[2] + s_t[2] - q[2];
+      if (dx * dx + dy * dy + dz * dz < thr2) {
+        acc[0] += 1.0;
+        for (int a = 0; a < 3; ++a) {
+          acc[1 + a] += p[a]; acc[4 + a] += q[a];
+          for (int b = 0; b < 3; ++b) acc[7 + 3 * a + b] += p[a] * q[b];
+        }
+      }
+    }
+    block_sum_256<16>(acc, sh_red);
+    if (threadIdx.x == 0) {
+      s_cnt = static_cast<int>(acc[0] + 0.5);
+      if (round < 2) {
+        double R[9], t[3];
+        if (kabsch_from_sums(acc[0], acc + 1, acc + 4, acc + 7, R, t)) {
+          for (int k = 0; k < 9; ++k) s_R[k] = R[k];
+          for (int k = 0; k < 3; ++k) s_t[k] = t[k];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (s_cnt < 3) { fail(); return; }
+  if (threadIdx.x < 9) Rf[9 * pair + threadIdx.x] = static_cast<float>(s_R[threadIdx.x]);
+  if (threadIdx.x < 3) tf[3 * pair + threadIdx.x] = static_cast<float>(s_t[threadIdx.x]);
+  if (threadIdx.x == 0) n_inl[pair] = s_cnt;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -984,10 +1245,10 @@ __global__ void __launch_bounds__(256) pnp_final_kernel(
 struct PoseSolver {
   int max_pairs, max_pts, max_hyp;
   HypResult* results = nullptr;
-  double *Rd = nullptr, *td = nullptr, *Xw = nullptr;
+  double *Rd = nullptr, *td = nullptr, *Xw = nullptr, *X1w = nullptr;
   float* uv = nullptr;
   int *vidx = nullptr, *nvalid = nullptr;
-  unsigned int* dmin = nullptr;
+  unsigned int *dmin = nullptr, *dmin1 = nullptr;
   size_t total_pts;
 };
 
@@ -1003,10 +1264,12 @@ int pose_solver_create(int max_pairs, int max_pts, int max_hyp, PoseSolver** out
   ok &= cudaMalloc(&s->Rd, sizeof(double) * 9 * max_pairs) == cudaSuccess;
   ok &= cudaMalloc(&s->td, sizeof(double) * 3 * max_pairs) == cudaSuccess;
   ok &= cudaMalloc(&s->Xw, sizeof(double) * 3 * s->total_pts) == cudaSuccess;
+  ok &= cudaMalloc(&s->X1w, sizeof(double) * 3 * s->total_pts) == cudaSuccess;
   ok &= cudaMalloc(&s->uv, sizeof(float) * 2 * s->total_pts) == cudaSuccess;
   ok &= cudaMalloc(&s->vidx, sizeof(int) * s->total_pts) == cudaSuccess;
   ok &= cudaMalloc(&s->nvalid, sizeof(int) * max_pairs) == cudaSuccess;
   ok &= cudaMalloc(&s->dmin, sizeof(unsigned int) * max_pairs) == cudaSuccess;
+  ok &= cudaMalloc(&s->dmin1, sizeof(unsigned int) * max_pairs) == cudaSuccess;
   if (!ok) { pose_solver_destroy(s); return MFR_ERR_CUDA; }
   static bool attrs = false;
   if (!attrs) {
@@ -1014,6 +1277,7 @@ int pose_solver_create(int max_pairs, int max_pts, int max_hyp, PoseSolver** out
     cudaFuncSetAttribute(emat_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
     cudaFuncSetAttribute(scale_consensus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
     cudaFuncSetAttribute(pnp_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 20);
+    cudaFuncSetAttribute(procrustes_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 24);
     attrs = true;
   }
   *out = s;
@@ -1023,7 +1287,7 @@ int pose_solver_create(int max_pairs, int max_pts, int max_hyp, PoseSolver** out
 void pose_solver_destroy(PoseSolver* s) {
   if (!s) return;
   cudaFree(s->results); cudaFree(s->Rd); cudaFree(s->td); cudaFree(s->Xw); cudaFree(s->uv);
-  cudaFree(s->vidx); cudaFree(s->nvalid); cudaFree(s->dmin);
+  cudaFree(s->vidx); cudaFree(s->nvalid); cudaFree(s->dmin); cudaFree(s->dmin1); cudaFree(s->X1w);
   delete s;
 }
 
@@ -1074,6 +1338,27 @@ int pnp_ransac(PoseSolver* s, const float* kpts0, const float* kpts1, const int*
       s->Xw, s->uv, offsets, s->nvalid, K1, reproj_thr, num_hyp, seed, s->results);
   pnp_final_kernel<<<P, 256, 0, st>>>(s->Xw, s->uv, s->vidx, offsets, s->nvalid, K1, reproj_thr, blocks,
                                       s->results, R, t, n_inl, mask);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int procrustes_ransac(PoseSolver* s, const float* kpts0, const float* kpts1, const int* offsets, int P,
+                      const float* K0, const float* K1, const float* depth0, const float* depth1, int H, int W,
+                      int num_hyp, float max_corr_dist, unsigned long long seed, float* R, float* t, int* n_inl,
+                      cudaStream_t st) {
+  if (P < 1 || P > s->max_pairs || num_hyp < 1) return MFR_ERR_ARG;
+  num_hyp = std::min(num_hyp, s->max_hyp);
+  const int blocks = (num_hyp + kHypPerBlock - 1) / kHypPerBlock;
+  MFR_CUDA_CHECK(cudaMemsetAsync(s->dmin, 0x7f, sizeof(unsigned int) * P, st));
+  MFR_CUDA_CHECK(cudaMemsetAsync(s->dmin1, 0x7f, sizeof(unsigned int) * P, st));
+  depth_min_kernel<<<dim3(64, P), 256, 0, st>>>(depth0, static_cast<long long>(H) * W, s->dmin);
+  depth_min_kernel<<<dim3(64, P), 256, 0, st>>>(depth1, static_cast<long long>(H) * W, s->dmin1);
+  procrustes_prepare_kernel<<<P, 1024, 0, st>>>(kpts0, kpts1, offsets, K0, K1, depth0, depth1, H, W, s->dmin,
+                                                s->dmin1, s->max_pts, s->Xw, s->X1w, s->nvalid);
+  procrustes_hyp_kernel<<<dim3(blocks, P), kHypPerBlock, static_cast<size_t>(s->max_pts) * 24, st>>>(
+      s->Xw, s->X1w, offsets, s->nvalid, max_corr_dist, num_hyp, seed, s->results);
+  procrustes_final_kernel<<<P, 256, 0, st>>>(s->Xw, s->X1w, offsets, s->nvalid, max_corr_dist, blocks, s->results, R,
+                                             t, n_inl);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }

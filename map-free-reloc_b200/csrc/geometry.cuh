@@ -23,4 +23,9 @@ int pnp_ransac(PoseSolver* s, const float* kpts0, const float* kpts1, const int*
                float reproj_thr, unsigned long long seed, float* R, float* t, int* n_inl,
                unsigned char* mask, cudaStream_t st);
 
+int procrustes_ransac(PoseSolver* s, const float* kpts0, const float* kpts1, const int* offsets, int P,
+                      const float* K0, const float* K1, const float* depth0, const float* depth1, int H, int W,
+                      int num_hyp, float max_corr_dist, unsigned long long seed, float* R, float* t, int* n_inl,
+                      cudaStream_t st);
+
 }  // namespace mfr

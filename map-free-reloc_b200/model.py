@@ -8,7 +8,7 @@ solvers ``estimate_pose(kpts0, kpts1, data)``. All geometry runs in the CUDA bac
 import numpy as np
 import torch
 
-from .pose_solver import EssentialMatrixMetricSolver, EssentialMatrixSolver, PnPSolver
+from .pose_solver import EssentialMatrixMetricSolver, EssentialMatrixSolver, PnPSolver, ProcrustesSolver
 
 
 class PrecomputedMatching:
@@ -142,7 +142,7 @@ class FeatureMatchingModel(torch.nn.Module):
         elif cfg.POSE_SOLVER == "PNP":
             self.pose_solver = PnPSolver(cfg)
         elif cfg.POSE_SOLVER == "Procrustes":
-            raise NotImplementedError("Procrustes solver is not built yet (SURVEY.md §8(f) rank 2)")
+            self.pose_solver = ProcrustesSolver(cfg)
         else:
             raise NotImplementedError("Invalid pose solver")
 

@@ -100,6 +100,20 @@ class PoseBackend:
                                           _lib.cur_stream()), "mfr_pnp_ransac")
         return R, t, n, mask
 
+    def procrustes(self, kpts0, kpts1, offsets, K0, K1, depth0, depth1, max_corr_dist,
+                   num_hyp=DEFAULT_NUM_HYP, seed=DEFAULT_SEED):
+        """ProcrustesSolver (REFINE=False) for P pairs: R [P,3,3], t [P,3], inliers [P]."""
+        P = self._prep(kpts0, kpts1, offsets, K0, K1)
+        H, W = depth0.shape[-2:]
+        R = torch.empty(P, 3, 3, device=self.device); t = torch.empty(P, 3, device=self.device)
+        n = torch.empty(P, dtype=torch.int32, device=self.device)
+        _lib.check(self._l.mfr_procrustes_ransac(
+            self._h, _lib.ptr(kpts0), _lib.ptr(kpts1), _lib.ptr(offsets), P, _lib.ptr(K0), _lib.ptr(K1),
+            _lib.ptr(depth0.contiguous()), _lib.ptr(depth1.contiguous()), int(H), int(W), int(num_hyp),
+            float(max_corr_dist), ctypes.c_ulonglong(seed), _lib.ptr(R), _lib.ptr(t), _lib.ptr(n),
+            _lib.cur_stream()), "mfr_procrustes_ransac")
+        return R, t, n
+
     def close(self):
         if getattr(self, "_h", None):
             self._l.mfr_pose_solver_destroy(self._h)
@@ -198,6 +212,31 @@ class PnPSolver(_SolverBase):
         d0 = d0.reshape(1, *d0.shape[-2:]).to(self.dev)
         R, t, n, _ = self.backend.pnp(k0, k1, off, K0, K1, d0, self.reprojection_inlier_threshold,
                                       self.num_hyp, self.seed)
+        n = int(n.item())
+        if n == 0:
+            return self._nan()
+        return R[0].double().cpu().numpy(), t[0].double().cpu().numpy().reshape(3, 1), n
+
+
+class ProcrustesSolver(_SolverBase):
+    """Metric relative pose from 3D-3D correspondences (pose_solver.py:238-320). The ICP refinement
+    over the full point clouds (PROCRUSTES.REFINE, Open3D registration_icp) is not built."""
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.ransac_max_corr_distance = float(_cfg_get(cfg, "PROCRUSTES.MAX_CORR_DIST"))
+        self.refine = bool(_cfg_get(cfg, "PROCRUSTES.REFINE", False))
+        if self.refine:
+            raise NotImplementedError("PROCRUSTES.REFINE (ICP over the full clouds) is not built")
+
+    def estimate_pose(self, pts0, pts1, data):
+        if len(pts0) < 3:
+            return self._nan()
+        k0, k1, off, K0, K1 = self._upload(pts0, pts1, data)
+        d0 = torch.as_tensor(data["depth0"]).float(); d0 = d0.reshape(1, *d0.shape[-2:]).to(self.dev)
+        d1 = torch.as_tensor(data["depth1"]).float(); d1 = d1.reshape(1, *d1.shape[-2:]).to(self.dev)
+        R, t, n = self.backend.procrustes(k0, k1, off, K0, K1, d0, d1, self.ransac_max_corr_distance,
+                                          self.num_hyp, self.seed)
         n = int(n.item())
         if n == 0:
             return self._nan()

@@ -140,6 +140,48 @@ def pnp_solver(pts0, pts1, depth0, K0, K1, ransac_iter, reproj_threshold, confid
     return R, t, len(inliers)
 
 
+def kabsch(P, Q):
+    """Least-squares rigid transform Q ~ R P + t (lib/utils/solver.py:4-37 states the same maths)."""
+    pb, qb = P.mean(0), Q.mean(0)
+    Hm = (P - pb).T @ (Q - qb)
+    U, S, Vt = np.linalg.svd(Hm)
+    d = np.sign(np.linalg.det(Vt.T @ U.T))
+    R = Vt.T @ np.diag([1.0, 1.0, d]) @ U.T
+    return R, qb - R @ pb
+
+
+def procrustes_solver(pts0, pts1, depth0, depth1, K0, K1, max_corr_dist, iters=4096, seed=0):
+    """ProcrustesSolver.estimate_pose, pose_solver.py:247-320 with REFINE=False. PARITY UNPINNED for
+    the RANSAC core: the reference calls Open3D 0.17 `registration_ransac_based_on_correspondence`,
+    which cannot be installed here; it is replaced by the textbook algorithm it implements (3-point
+    Kabsch hypotheses, inliers by 3-D distance < max_corr_dist, refit on the inliers). Everything
+    around it (int truncation, depth > depth.min() validity, back-projection) follows the reference."""
+    nan = (np.full((3, 3), np.nan), np.full((3, 1), np.nan), 0)
+    pts0 = np.int32(pts0); pts1 = np.int32(pts1)
+    if len(pts0) < 3:
+        return nan
+    d0 = depth0[pts0[:, 1], pts0[:, 0]]; d1 = depth1[pts1[:, 1], pts1[:, 0]]
+    valid = (d0 > depth0.min()) * (d1 > depth1.min())
+    if valid.sum() < 3:
+        return nan
+    X0 = backproject_3d(pts0[valid], d0[valid], K0); X1 = backproject_3d(pts1[valid], d1[valid], K1)
+    rng = np.random.default_rng(seed)
+    best = (-1, None)
+    for _ in range(iters):
+        idx = rng.choice(len(X0), 3, replace=False)
+        R, t = kabsch(X0[idx], X1[idx])
+        inl = np.linalg.norm(X0 @ R.T + t - X1, axis=1) < max_corr_dist
+        if inl.sum() > best[0]:
+            best = (int(inl.sum()), inl)
+    inl = best[1]
+    for _ in range(2):
+        if inl.sum() < 3:
+            return nan
+        R, t = kabsch(X0[inl], X1[inl])
+        inl = np.linalg.norm(X0 @ R.T + t - X1, axis=1) < max_corr_dist
+    return R, t.reshape(3, 1), int(inl.sum())
+
+
 # --------------------------------------------------------------------------------------------
 # Oracle extensions (not in the reference): the "polished oracle" of SURVEY.md §7 hard part 1
 # --------------------------------------------------------------------------------------------
