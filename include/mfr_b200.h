@@ -43,6 +43,14 @@ int mfr_conv2d_nhwc_tf32(const float* x, int N, int H, int W, int Cin, long long
                          int b_batched, const float* bias, const float* residual, long long ldr,
                          int act, float alpha, float* out, long long ldo, void* stream);
 
+/* Same op with bf16 operands (x, w as bf16 bits; tcgen05 kind::f16, fp32 accumulate). ldx / ldw are
+ * element strides with ldx*2 and ldw*2 multiples of 16 bytes (ldw = per-tap row stride of w, >= Cin).
+ * out / residual are bf16 when out_bf16 != 0 (then Cout % 4 == 0), else fp32. bias is fp32. */
+int mfr_conv2d_nhwc_bf16(const void* x, int N, int H, int W, int Cin, long long ldx, const void* w,
+                         long long ldw, int Cout, int R, int S, int stride, int pad, const float* bias,
+                         const void* residual, long long ldr, int act, float alpha, void* out,
+                         long long ldo, int out_bf16, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * LoFTR matcher engine. Replaces LoFTR.forward of the reference
  * (etc/feature_matching_baselines/LoFTR/src/loftr/loftr.py:29-75) as driven by
@@ -63,7 +71,12 @@ typedef struct {
   int capacity;
 } mfr_loftr_outputs;
 
-int mfr_loftr_create(int B, int H, int W, float thr, int border_rm, float temperature,
+/* precision: 0 = fp32 storage, TF32 tensor-core inputs everywhere (parity mode; what torch+cuDNN do
+ * by default for the convs); 1 = bf16 storage and bf16 tensor-core inputs in the ResNet-FPN backbone
+ * (fp32 accumulate, fp32 feature maps out), everything after the backbone as in mode 0. */
+#define MFR_PRECISION_TF32 0
+#define MFR_PRECISION_BF16 1
+int mfr_loftr_create(int B, int H, int W, float thr, int border_rm, float temperature, int precision,
                      mfr_loftr** out);
 void mfr_loftr_destroy(mfr_loftr* h);
 int mfr_loftr_num_weights(const mfr_loftr* h);

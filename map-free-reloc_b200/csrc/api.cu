@@ -35,13 +35,28 @@ int mfr_conv2d_nhwc_tf32(const float* x, int N, int H, int W, int Cin, long long
   return mfr::conv_gemm_launch(p, static_cast<cudaStream_t>(stream));
 }
 
+int mfr_conv2d_nhwc_bf16(const void* x, int N, int H, int W, int Cin, long long ldx, const void* w, long long ldw,
+                         int Cout, int R, int S, int stride, int pad, const float* bias, const void* residual,
+                         long long ldr, int act, float alpha, void* out, long long ldo, int out_bf16, void* stream) {
+  mfr::ConvGemmDesc d{};
+  d.x = static_cast<const float*>(x); d.N = N; d.H = H; d.W = W; d.Cin = Cin; d.ldx = ldx;
+  d.w = static_cast<const float*>(w); d.ldw = ldw; d.Cout = Cout; d.R = R; d.S = S; d.stride = stride; d.pad = pad;
+  d.bias = bias; d.residual = static_cast<const float*>(residual); d.ldr = ldr; d.act = act; d.alpha = alpha;
+  d.out = static_cast<float*>(out); d.ldo = ldo; d.in_bf16 = 1; d.out_bf16 = out_bf16;
+  mfr::ConvGemmParams p;
+  int rc = mfr::conv_gemm_build(d, &p);
+  if (rc != MFR_OK) return rc;
+  return mfr::conv_gemm_launch(p, static_cast<cudaStream_t>(stream));
+}
+
 // ------------------------------------------------------------------------------------------ LoFTR
 struct mfr_loftr { mfr::LoftrEngine* e; };
 
-int mfr_loftr_create(int B, int H, int W, float thr, int border_rm, float temperature, mfr_loftr** out) {
+int mfr_loftr_create(int B, int H, int W, float thr, int border_rm, float temperature, int precision,
+                     mfr_loftr** out) {
   if (!out) return MFR_ERR_ARG;
   mfr::LoftrEngine* e = nullptr;
-  int rc = mfr::loftr_create(B, H, W, thr, border_rm, temperature, &e);
+  int rc = mfr::loftr_create(B, H, W, thr, border_rm, temperature, precision, &e);
   if (rc != MFR_OK) return rc;
   *out = new mfr_loftr{e};
   return MFR_OK;

@@ -56,7 +56,19 @@ __device__ __forceinline__ float act_fn(float v) {
 
 // Coalesced part of the epilogue for one 32-channel chunk: 8 x (LDS.128 -> alpha/bias/residual/act ->
 // STG.128); lane (sub_r, sub_c) handles staged row k*4+sub_r, channels sub_c..sub_c+3.
-template <int ACT, bool RES>
+__device__ __forceinline__ float4 bf16x4_to_float4(uint2 u) {
+  float4 f;
+  f.x = __uint_as_float(u.x << 16); f.y = __uint_as_float(u.x & 0xffff0000u);
+  f.z = __uint_as_float(u.y << 16); f.w = __uint_as_float(u.y & 0xffff0000u);
+  return f;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <int ACT, bool RES, bool OBF>
 __device__ __forceinline__ void store_chunk(const float* __restrict__ stg_rd, const long long (&off_o)[8],
                                             const long long (&off_r)[8], uint32_t okmask, float alpha,
                                             float4 b4, const float* __restrict__ res_n,
@@ -71,11 +83,19 @@ __device__ __forceinline__ void store_chunk(const float* __restrict__ stg_rd, co
       v.x = fmaf(v.x, alpha, b4.x); v.y = fmaf(v.y, alpha, b4.y);
       v.z = fmaf(v.z, alpha, b4.z); v.w = fmaf(v.w, alpha, b4.w);
       if constexpr (RES) {
-        const float4 r4 = __ldg(reinterpret_cast<const float4*>(res_n + off_r[k]));
+        float4 r4;
+        if constexpr (OBF)   // res_n / out_n point at bf16 storage: element offsets count 2-byte units
+          r4 = bf16x4_to_float4(__ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(res_n) + off_r[k])));
+        else
+          r4 = __ldg(reinterpret_cast<const float4*>(res_n + off_r[k]));
         v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
       }
       v.x = act_fn<ACT>(v.x); v.y = act_fn<ACT>(v.y); v.z = act_fn<ACT>(v.z); v.w = act_fn<ACT>(v.w);
-      *reinterpret_cast<float4*>(out_n + off_o[k]) = v;
+      if constexpr (OBF)
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out_n) + off_o[k]) =
+            make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      else
+        *reinterpret_cast<float4*>(out_n + off_o[k]) = v;
     }
   }
 }
@@ -153,9 +173,9 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
           const int ky = tap / p.S, kx = tap - ky * p.S;
           mbar_wait(empty_bar(stage), phase ^ 1u, 1);
           mbar_arrive_expect_tx(full_bar(stage), static_cast<uint32_t>(p.a_bytes + p.b_bytes));
-          tma_load_4d(smem_a + stage * kAStage, &p.tmA, full_bar(stage), cb * kBlockK, x_in0 + kx,
+          tma_load_4d(smem_a + stage * kAStage, &p.tmA, full_bar(stage), cb * p.kblk, x_in0 + kx,
                       y_in0 + ky, img);
-          tma_load_3d(smem_b + stage * kBStage, &p.tmB, full_bar(stage), cb * kBlockK,
+          tma_load_3d(smem_b + stage * kBStage, &p.tmB, full_bar(stage), cb * p.kblk,
                       p.b_batched ? img : tap, n0);
           if (kb == 0 && tile == static_cast<int>(blockIdx.x)) MFR_STAMP(2);
           if (kb == num_kb - 1 && tile == static_cast<int>(blockIdx.x)) MFR_STAMP(3);
@@ -166,7 +186,8 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(2u, kTileM, static_cast<uint32_t>(p.BN));
+      const uint32_t idesc = umma_idesc(p.in_bf16 ? 1u : 2u, kTileM, static_cast<uint32_t>(p.BN));
+      const bool bf16_in = p.in_bf16 != 0;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -187,7 +208,8 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t adesc = umma_desc_sw128_kmajor(a_addr + k * kUmmaK * 4);
             const uint64_t bdesc = umma_desc_sw128_kmajor(b_addr + k * kUmmaK * 4);
-            tc_mma_tf32(tmem_acc, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (bf16_in) tc_mma_bf16(tmem_acc, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            else tc_mma_tf32(tmem_acc, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           tc_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -203,10 +225,10 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     const int row = q * 32 + lane;
     const int ly = row / p.TW, lx = row - ly * p.TW;
     const bool vec_ok = ((p.Cout & 3) == 0) && ((p.ldo & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.out) & (p.out_bf16 ? 7 : 15)) == 0) &&
                         (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
                         (p.residual == nullptr ||
-                         (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)));
+                         (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & (p.out_bf16 ? 7 : 15)) == 0)));
     float* stg = reinterpret_cast<float*>(smem_raw + (smem_stg - smem_u32(smem_raw))) + q * (32 * kStgStride);
     const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
     int it = 0;
@@ -258,23 +280,31 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
           if (p.bias != nullptr && okm) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
           const int act = n < p.act_cols ? p.act : ACT_NONE;   // n..n+3 never straddle act_cols (multiple of 4)
           const float* stg_rd = stg + sub_r * kStgStride + sub_c;
-          float* out_n = p.out + n;
-          const float* res_n = p.residual + n;
+          // base pointers advanced by n elements of the output type
+          float* out_n = p.out_bf16 ? reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(p.out) + n) : p.out + n;
+          const float* res_n = p.out_bf16 ? reinterpret_cast<const float*>(reinterpret_cast<const uint16_t*>(p.residual) + n)
+                                          : p.residual + n;
+#define MFR_STORE(ACTV, RESV)                                                                                   \
+  do {                                                                                                          \
+    if (p.out_bf16) store_chunk<ACTV, RESV, true>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n);        \
+    else store_chunk<ACTV, RESV, false>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n);                  \
+  } while (0)
           if (p.residual != nullptr) {
             switch (act) {
-              case ACT_RELU: store_chunk<ACT_RELU, true>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
-              case ACT_LEAKY: store_chunk<ACT_LEAKY, true>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
-              case ACT_ELU1: store_chunk<ACT_ELU1, true>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
-              default: store_chunk<ACT_NONE, true>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
+              case ACT_RELU: MFR_STORE(ACT_RELU, true); break;
+              case ACT_LEAKY: MFR_STORE(ACT_LEAKY, true); break;
+              case ACT_ELU1: MFR_STORE(ACT_ELU1, true); break;
+              default: MFR_STORE(ACT_NONE, true); break;
             }
           } else {
             switch (act) {
-              case ACT_RELU: store_chunk<ACT_RELU, false>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
-              case ACT_LEAKY: store_chunk<ACT_LEAKY, false>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
-              case ACT_ELU1: store_chunk<ACT_ELU1, false>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
-              default: store_chunk<ACT_NONE, false>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n); break;
+              case ACT_RELU: MFR_STORE(ACT_RELU, false); break;
+              case ACT_LEAKY: MFR_STORE(ACT_LEAKY, false); break;
+              case ACT_ELU1: MFR_STORE(ACT_ELU1, false); break;
+              default: MFR_STORE(ACT_NONE, false); break;
             }
           }
+#undef MFR_STORE
           __syncwarp();
           if (it == 0 && c0 == 0 && threadIdx.x == 64) MFR_STAMP(12);
         } else if (row_ok) {
@@ -371,11 +401,15 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
     fprintf(stderr, "[mfr_b200] cuTensorMapEncodeTiled unavailable (no CUDA driver?)\n");
     return MFR_ERR_CUDA;
   }
-  if (d.Cin % 4 != 0 || d.ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(d.x) & 15) ||
+  const int es = d.in_bf16 ? 2 : 4;           // operand element size
+  const int kblk = 128 / es;                  // K elements per 128-byte k-block
+  const long long ldw_e = d.ldw > 0 ? d.ldw : d.Cin;
+  if ((d.ldx * es) % 16 != 0 || (ldw_e * es) % 16 != 0 || (reinterpret_cast<uintptr_t>(d.x) & 15) ||
       (reinterpret_cast<uintptr_t>(d.w) & 15)) {
-    fprintf(stderr, "[mfr_b200] conv_gemm: Cin/ldx must be multiples of 4 and pointers 16B aligned\n");
+    fprintf(stderr, "[mfr_b200] conv_gemm: operand row strides must be multiples of 16 bytes, pointers 16B aligned\n");
     return MFR_ERR_ARG;
   }
+  if (d.out_bf16 && ((d.Cout & 3) || (d.ldo & 3))) return MFR_ERR_ARG;   // bf16 output: vector path only
   if (d.stride != 1 && d.stride != 2) return MFR_ERR_ARG;
   memset(p, 0, sizeof(*p));
   p->N = d.N;
@@ -397,10 +431,13 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
     max_bn /= 2;
   p->n_tiles = (c16 + max_bn - 1) / max_bn;
   p->BN = ((c16 / 16 + p->n_tiles - 1) / p->n_tiles) * 16;
-  p->kb_per_tap = (d.Cin + kBlockK - 1) / kBlockK;
+  p->kb_per_tap = (d.Cin + kblk - 1) / kblk;
+  p->kblk = kblk;
+  p->in_bf16 = d.in_bf16;
+  p->out_bf16 = d.out_bf16;
   p->b_batched = d.b_batched;
-  p->a_bytes = p->TW * p->TH * kBlockK * 4;
-  p->b_bytes = p->BN * kBlockK * 4;
+  p->a_bytes = p->TW * p->TH * 128;
+  p->b_bytes = p->BN * 128;
   p->num_stages = std::min(kMaxStages, kRingBytes / (kAStage + p->b_bytes));  // BN*128 B is 2 KB aligned
   p->act = d.act;
   p->act_cols = d.act_cols > 0 ? d.act_cols : d.Cout;
@@ -418,12 +455,13 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
 
   {  // activations: {C, W, H, N}
     cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};
-    cuuint64_t strides[3] = {(cuuint64_t)d.ldx * 4, (cuuint64_t)d.ldx * 4 * d.W,
-                             d.x_img_stride > 0 ? (cuuint64_t)d.x_img_stride * 4 : (cuuint64_t)d.ldx * 4 * d.W * d.H};
-    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(p->TW * d.stride),
+    cuuint64_t strides[3] = {(cuuint64_t)d.ldx * es, (cuuint64_t)d.ldx * es * d.W,
+                             d.x_img_stride > 0 ? (cuuint64_t)d.x_img_stride * es : (cuuint64_t)d.ldx * es * d.W * d.H};
+    cuuint32_t box[4] = {(cuuint32_t)kblk, (cuuint32_t)(p->TW * d.stride),
                          (cuuint32_t)(p->TH * d.stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
-    CUresult r = enc(&p->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d.x), dims,
+    CUresult r = enc(&p->tmA, d.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                     const_cast<float*>(d.x), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -436,19 +474,19 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
     cuuint64_t dims[3];
     cuuint64_t strides[2];
     if (d.b_batched) {
-      const long long ldw = d.ldw > 0 ? d.ldw : d.Cin;
-      if (ldw % 4) return MFR_ERR_ARG;
+      const long long ldw = ldw_e;
       dims[0] = d.Cin; dims[1] = d.N; dims[2] = d.Cout;
-      strides[0] = d.w_img_stride > 0 ? (cuuint64_t)d.w_img_stride * 4 : (cuuint64_t)d.Cout * ldw * 4;  // next image
-      strides[1] = (cuuint64_t)ldw * 4;           // next output row
+      strides[0] = d.w_img_stride > 0 ? (cuuint64_t)d.w_img_stride * es : (cuuint64_t)d.Cout * ldw * es;  // next image
+      strides[1] = (cuuint64_t)ldw * es;           // next output row
     } else {
       dims[0] = d.Cin; dims[1] = taps; dims[2] = d.Cout;
-      strides[0] = (cuuint64_t)d.Cin * 4;
-      strides[1] = (cuuint64_t)d.Cin * 4 * taps;
+      strides[0] = (cuuint64_t)ldw_e * es;
+      strides[1] = (cuuint64_t)ldw_e * es * taps;
     }
-    cuuint32_t box[3] = {(cuuint32_t)kBlockK, 1, (cuuint32_t)p->BN};
+    cuuint32_t box[3] = {(cuuint32_t)kblk, 1, (cuuint32_t)p->BN};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&p->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d.w), dims,
+    CUresult r = enc(&p->tmB, d.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                     const_cast<float*>(d.w), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

@@ -23,6 +23,8 @@ struct alignas(64) ConvGemmParams {
   int a_bytes, b_bytes;   // TMA transaction bytes per stage
   int num_stages;         // operand ring depth = 192 KB / (16 KB + BN * 128 B), at most 8
   int act, act_cols;    // activation applies to output channels < act_cols
+  int in_bf16, out_bf16;  // operands bf16 (kind::f16) instead of fp32 (kind::tf32); out/residual bf16
+  int kblk;             // K elements per 128-byte k-block: 32 (fp32) or 64 (bf16)
   const int* dyn_w;     // optional device int: effective W (rows of a token GEMM), H must be 1
   float alpha;
   const float* bias;
@@ -41,10 +43,11 @@ struct ConvGemmDesc {
   const float* w;      // [Cout][R*S][Cin] (Cin fastest); for batched GEMM: [N][Cout][ldw]
   int Cout, R, S, stride, pad;
   int b_batched;       // 0: shared weights; 1: per-image B operand
-  long long ldw;       // batched only: row stride of w in floats (0 = Cin)
+  long long ldw;       // row stride of w in elements (0 = Cin): per tap for shared weights, per row if batched
   int act_cols;        // 0 = all output channels
   const int* dyn_w;    // optional device row count (token GEMMs with data-dependent length)
   long long x_img_stride, w_img_stride, out_img_stride;  // elements between images; 0 = dense
+  int in_bf16, out_bf16;  // x / w are bf16 ; out / residual are bf16 (pointers reinterpret the storage)
   const float* bias;   // [Cout] or null
   const float* residual;  // NHWC like out (pixel stride ldr) or null
   long long ldr;

@@ -42,6 +42,12 @@ struct LoftrEngine {
   float thr, temperature;
   int border;
   int splits_kv = 96, splits_col = 32;
+  int precision = 0;   // 0: fp32 storage / TF32 MMA everywhere; 1: bf16 storage + bf16 MMA in the ResNet-FPN backbone
+  struct Bf16Conv { std::string name; int cout, taps, cin, cin_pad; size_t off; };
+  std::vector<Bf16Conv> bf16_convs;
+  unsigned short* wblob16 = nullptr;
+  size_t w16_total = 0;
+  bool w16_ready = false;
 
   std::vector<WeightSpec> specs;
   std::map<std::string, size_t> spec_index;
@@ -103,12 +109,21 @@ struct LoftrEngine {
   void conv(const std::string& wname, const float* x, int N, int Hh, int Ww, int Cin, long long ldx,
             int Cout, int R, int stride, bool bias, const float* residual, int act, float* out,
             long long ldo, int act_cols = 0, const int* dyn_w = nullptr, const float* w_override = nullptr,
-            const float* bias_override = nullptr) {
+            const float* bias_override = nullptr, int in_bf16 = 0, int out_bf16 = 0) {
     ConvGemmDesc d{};
     d.x = x; d.N = N; d.H = Hh; d.W = Ww; d.Cin = Cin; d.ldx = ldx;
+    d.in_bf16 = in_bf16; d.out_bf16 = out_bf16;
+    if (in_bf16) {   // bf16 copy of the weights, Cin padded to a multiple of 8 (16-byte TMA strides)
+      const int cin_pad = (Cin + 7) / 8 * 8;
+      Bf16Conv bc{wname, Cout, R * R, Cin, cin_pad, w16_total};
+      bf16_convs.push_back(bc);
+      w16_total += (static_cast<size_t>(Cout) * R * R * cin_pad + 63) / 64 * 64;
+      d.ldw = cin_pad;
+      w_override = reinterpret_cast<const float*>(wblob16 + bc.off);
+    }
     d.w = w_override ? w_override : W_(wname + ".w");
     d.Cout = Cout; d.R = R; d.S = R; d.stride = stride; d.pad = R / 2;
-    d.b_batched = 0; d.ldw = 0; d.act_cols = act_cols; d.dyn_w = dyn_w;
+    d.b_batched = 0; if (!in_bf16) d.ldw = 0; d.act_cols = act_cols; d.dyn_w = dyn_w;
     d.bias = bias ? (bias_override ? bias_override : W_(wname + ".b")) : nullptr;
     d.residual = residual; d.ldr = ldo;
     d.act = act; d.alpha = 1.f; d.out = out; d.ldo = ldo;
@@ -186,7 +201,7 @@ struct LoftrEngine {
     if (!windows) {
       float* kvp_ = kvp; float* kv_ = kv;
       const int Lr = rows, sk = splits_kv;
-      push("simt", [=](cudaStream_t st) {
+      push("attn_long", [=](cudaStream_t st) {
         return linear_attention_long(qkv_x, ld3, qkv_s + C, ld3, qkv_s + 2 * C, ld3, msg_x, C, kvp_, kv_, n,
                                      Lr, Lr, 8, 32, sk, st);
       }, 3);
@@ -195,7 +210,7 @@ struct LoftrEngine {
       for (int side = 0; side < n; ++side) {
         const size_t off3 = static_cast<size_t>(side) * rows * ld3;
         const size_t off1 = static_cast<size_t>(side) * rows * C;
-        push("simt", [=](cudaStream_t st) {
+        push("attn_windows", [=](cudaStream_t st) {
           return linear_attention_windows(qkv_x + off3, ld3, qkv_s + off3 + C, ld3, qkv_s + off3 + 2 * C, ld3,
                                           msg_x + off1, C, dyn_items, items_cap, 25, st);
         });
@@ -206,13 +221,13 @@ struct LoftrEngine {
     const float *g2 = W_(p + ".norm2.g"), *b2 = W_(p + ".norm2.b");
     const long long tot = static_cast<long long>(n) * rows;
     if (dyn_rows == nullptr) {
-      push("simt", [=](cudaStream_t st) {
+      push("layernorm", [=](cudaStream_t st) {
         return layernorm_rows(mrg_x, C, g1, b1, nullptr, 0, x + C, ld2, tot, C, nullptr, st);
       });
     } else {
       for (int side = 0; side < n; ++side) {
         const size_t o1 = static_cast<size_t>(side) * rows * C, o2 = static_cast<size_t>(side) * rows * ld2;
-        push("simt", [=](cudaStream_t st) {
+        push("layernorm", [=](cudaStream_t st) {
           return layernorm_rows(mrg_x + o1, C, g1, b1, nullptr, 0, x + o2 + C, ld2, rows, C, dyn_rows, st);
         });
       }
@@ -220,13 +235,13 @@ struct LoftrEngine {
     conv(p + ".mlp0", x, n, 1, rows, 2 * C, ld2, 2 * C, 1, 1, false, nullptr, ACT_RELU, h1_x, ld2, 0, dyn_rows);
     conv(p + ".mlp2", h1_x, n, 1, rows, 2 * C, ld2, C, 1, 1, false, nullptr, ACT_NONE, h2_x, C, 0, dyn_rows);
     if (dyn_rows == nullptr) {
-      push("simt", [=](cudaStream_t st) {
+      push("layernorm", [=](cudaStream_t st) {
         return layernorm_rows(h2_x, C, g2, b2, x, ld2, x, ld2, tot, C, nullptr, st);
       });
     } else {
       for (int side = 0; side < n; ++side) {
         const size_t o1 = static_cast<size_t>(side) * rows * C, o2 = static_cast<size_t>(side) * rows * ld2;
-        push("simt", [=](cudaStream_t st) {
+        push("layernorm", [=](cudaStream_t st) {
           return layernorm_rows(h2_x + o1, C, g2, b2, x + o2, ld2, x + o2, ld2, rows, C, dyn_rows, st);
         });
       }
@@ -250,12 +265,22 @@ struct LoftrEngine {
     const size_t px2 = static_cast<size_t>(NI) * H2 * W2, px4 = static_cast<size_t>(NI) * H4 * W4,
                  px8 = static_cast<size_t>(NI) * H8 * W8;
     img = alloc<float>(static_cast<size_t>(NI) * H * W, "img");
-    a0 = alloc<float>(px2 * 128, "a0"); a1 = alloc<float>(px2 * 128, "a1"); a2 = alloc<float>(px2 * 128, "a2");
-    b0 = alloc<float>(px4 * 196, "b0"); b1 = alloc<float>(px4 * 196, "b1"); b2 = alloc<float>(px4 * 196, "b2");
-    c0 = alloc<float>(px8 * 256, "c0"); c1 = alloc<float>(px8 * 256, "c1"); c2 = alloc<float>(px8 * 256, "c2");
+    const bool bf = precision == 1;
+    const int c196 = bf ? 200 : 196;                  // pixel stride of the 196-channel maps (16-byte rows in bf16)
+    const size_t esz = bf ? 2 : 4;
+    auto balloc = [&](size_t elems, const char* name) {  // backbone activation buffer (fp32 or bf16 storage)
+      return reinterpret_cast<float*>(alloc<unsigned char>(elems * esz, name));
+    };
+    // the bf16 weight blob must exist before the conv steps are built (its size is known only afterwards:
+    // reserve the upper bound = all backbone conv weights)
+    if (bf) wblob16 = alloc<unsigned short>(static_cast<size_t>(8) * 1024 * 1024, "weights_bf16");
+    a0 = balloc(px2 * 128, "a0"); a1 = balloc(px2 * 128, "a1"); a2 = balloc(px2 * 128, "a2");
+    b0 = balloc(px4 * c196, "b0"); b1 = balloc(px4 * c196, "b1"); b2 = balloc(px4 * c196, "b2");
+    c0 = balloc(px8 * 256, "c0"); c1 = balloc(px8 * 256, "c1"); c2 = balloc(px8 * 256, "c2");
     fc = alloc<float>(px8 * 256, "feat_c_backbone");
-    p4a = alloc<float>(px4 * 256, "p4a"); p4b = alloc<float>(px4 * 256, "p4b"); p4c = alloc<float>(px4 * 196, "p4c");
-    p2a = alloc<float>(px2 * 196, "p2a"); p2b = alloc<float>(px2 * 196, "p2b");
+    p4a = balloc(px4 * 256, "p4a"); p4b = balloc(px4 * 256, "p4b"); p4c = balloc(px4 * c196, "p4c");
+    p2a = balloc(px2 * c196, "p2a"); p2b = balloc(px2 * c196, "p2b");
+    float* featf = alloc<float>(px2 * 128, "feat_f");
     tok = alloc<float>(px8 * 512, "tok");
     qkv = alloc<float>(px8 * 768, "qkv"); msg = alloc<float>(px8 * 256, "msg"); mrg = alloc<float>(px8 * 256, "mrg");
     h1 = alloc<float>(px8 * 512, "h1"); h2 = alloc<float>(px8 * 256, "h2");
@@ -283,47 +308,55 @@ struct LoftrEngine {
     if (build_rc != MFR_OK) return build_rc;
 
     // ---------------------------------------------------------------- backbone (resnet_fpn.py:100-119)
+    const int B16 = bf ? 1 : 0;
     {
       float *img_ = img, *a0_ = a0; float* ws = W_("stem.w"); float* bs = W_("stem.b");
-      const int NI_ = NI, H_ = H, W_w = W;
-      push("simt", [=](cudaStream_t st) { return stem_conv7x7(img_, ws, bs, a0_, NI_, H_, W_w, st); });
+      const int NI_ = NI, H_ = H, W_w = W, ob = B16;
+      push("stem", [=](cudaStream_t st) { return stem_conv7x7(img_, ws, bs, a0_, NI_, H_, W_w, st, ob); });
     }
-    conv("layer1.0.conv1", a0, NI, H2, W2, 128, 128, 128, 3, 1, true, nullptr, ACT_RELU, a1, 128);
-    conv("layer1.0.conv2", a1, NI, H2, W2, 128, 128, 128, 3, 1, true, a0, ACT_RELU, a2, 128);
-    conv("layer1.1.conv1", a2, NI, H2, W2, 128, 128, 128, 3, 1, true, nullptr, ACT_RELU, a1, 128);
-    conv("layer1.1.conv2", a1, NI, H2, W2, 128, 128, 128, 3, 1, true, a2, ACT_RELU, a0, 128);  // x1 = a0
-    conv("layer2.0.conv1", a0, NI, H2, W2, 128, 128, 196, 3, 2, true, nullptr, ACT_RELU, b1, 196);
-    conv("layer2.0.down", a0, NI, H2, W2, 128, 128, 196, 1, 2, true, nullptr, ACT_NONE, b2, 196);
-    conv("layer2.0.conv2", b1, NI, H4, W4, 196, 196, 196, 3, 1, true, b2, ACT_RELU, b0, 196);
-    conv("layer2.1.conv1", b0, NI, H4, W4, 196, 196, 196, 3, 1, true, nullptr, ACT_RELU, b1, 196);
-    conv("layer2.1.conv2", b1, NI, H4, W4, 196, 196, 196, 3, 1, true, b0, ACT_RELU, b2, 196);  // x2 = b2
-    conv("layer3.0.conv1", b2, NI, H4, W4, 196, 196, 256, 3, 2, true, nullptr, ACT_RELU, c1, 256);
-    conv("layer3.0.down", b2, NI, H4, W4, 196, 196, 256, 1, 2, true, nullptr, ACT_NONE, c2, 256);
-    conv("layer3.0.conv2", c1, NI, H8, W8, 256, 256, 256, 3, 1, true, c2, ACT_RELU, c0, 256);
-    conv("layer3.1.conv1", c0, NI, H8, W8, 256, 256, 256, 3, 1, true, nullptr, ACT_RELU, c1, 256);
-    conv("layer3.1.conv2", c1, NI, H8, W8, 256, 256, 256, 3, 1, true, c0, ACT_RELU, c2, 256);  // x3 = c2
-    conv("layer3_outconv", c2, NI, H8, W8, 256, 256, 256, 1, 1, false, nullptr, ACT_NONE, fc, 256);
-    conv("layer2_outconv", b2, NI, H4, W4, 196, 196, 256, 1, 1, false, nullptr, ACT_NONE, p4a, 256);
+    auto bconv = [&](const std::string& name, const float* x, int Hh, int Ww, int Cin, int ldx, int Cout, int R,
+                     int stride, bool bias, const float* res, int act, float* out, int ldo, int out16) {
+      conv(name, x, NI, Hh, Ww, Cin, ldx, Cout, R, stride, bias, res, act, out, ldo, 0, nullptr, nullptr, nullptr, B16,
+           out16);
+    };
+    bconv("layer1.0.conv1", a0, H2, W2, 128, 128, 128, 3, 1, true, nullptr, ACT_RELU, a1, 128, B16);
+    bconv("layer1.0.conv2", a1, H2, W2, 128, 128, 128, 3, 1, true, a0, ACT_RELU, a2, 128, B16);
+    bconv("layer1.1.conv1", a2, H2, W2, 128, 128, 128, 3, 1, true, nullptr, ACT_RELU, a1, 128, B16);
+    bconv("layer1.1.conv2", a1, H2, W2, 128, 128, 128, 3, 1, true, a2, ACT_RELU, a0, 128, B16);  // x1 = a0
+    bconv("layer2.0.conv1", a0, H2, W2, 128, 128, 196, 3, 2, true, nullptr, ACT_RELU, b1, c196, B16);
+    bconv("layer2.0.down", a0, H2, W2, 128, 128, 196, 1, 2, true, nullptr, ACT_NONE, b2, c196, B16);
+    bconv("layer2.0.conv2", b1, H4, W4, 196, c196, 196, 3, 1, true, b2, ACT_RELU, b0, c196, B16);
+    bconv("layer2.1.conv1", b0, H4, W4, 196, c196, 196, 3, 1, true, nullptr, ACT_RELU, b1, c196, B16);
+    bconv("layer2.1.conv2", b1, H4, W4, 196, c196, 196, 3, 1, true, b0, ACT_RELU, b2, c196, B16);  // x2 = b2
+    bconv("layer3.0.conv1", b2, H4, W4, 196, c196, 256, 3, 2, true, nullptr, ACT_RELU, c1, 256, B16);
+    bconv("layer3.0.down", b2, H4, W4, 196, c196, 256, 1, 2, true, nullptr, ACT_NONE, c2, 256, B16);
+    bconv("layer3.0.conv2", c1, H8, W8, 256, 256, 256, 3, 1, true, c2, ACT_RELU, c0, 256, B16);
+    bconv("layer3.1.conv1", c0, H8, W8, 256, 256, 256, 3, 1, true, nullptr, ACT_RELU, c1, 256, B16);
+    bconv("layer3.1.conv2", c1, H8, W8, 256, 256, 256, 3, 1, true, c0, ACT_RELU, c2, 256, B16);  // x3 = c2
+    bconv("layer3_outconv", c2, H8, W8, 256, 256, 256, 1, 1, false, nullptr, ACT_NONE, fc, 256, 0);   // fp32 out
+    bconv("layer2_outconv", b2, H4, W4, 196, c196, 256, 1, 1, false, nullptr, ACT_NONE, p4a, 256, B16);
     {
-      float *s = fc, *d = p4a; const int n = NI, hs = H8, wsz = W8;
-      push("simt", [=](cudaStream_t st) { return upsample2x_add(s, d, n, hs, wsz, 256, st); });
+      float *s_ = fc, *d_ = p4a; const int n = NI, hs = H8, wsz = W8, ob = B16;
+      push("upsample", [=](cudaStream_t st) { return upsample2x_add(s_, d_, n, hs, wsz, 256, 256, 256, 0, ob, st); });
     }
-    conv("layer2_outconv2.0", p4a, NI, H4, W4, 256, 256, 256, 3, 1, true, nullptr, ACT_LEAKY, p4b, 256);
-    conv("layer2_outconv2.3", p4b, NI, H4, W4, 256, 256, 196, 3, 1, false, nullptr, ACT_NONE, p4c, 196);
-    conv("layer1_outconv", a0, NI, H2, W2, 128, 128, 196, 1, 1, false, nullptr, ACT_NONE, p2a, 196);
+    bconv("layer2_outconv2.0", p4a, H4, W4, 256, 256, 256, 3, 1, true, nullptr, ACT_LEAKY, p4b, 256, B16);
+    bconv("layer2_outconv2.3", p4b, H4, W4, 256, 256, 196, 3, 1, false, nullptr, ACT_NONE, p4c, c196, B16);
+    bconv("layer1_outconv", a0, H2, W2, 128, 128, 196, 1, 1, false, nullptr, ACT_NONE, p2a, c196, B16);
     {
-      float *s = p4c, *d = p2a; const int n = NI, hs = H4, wsz = W4;
-      push("simt", [=](cudaStream_t st) { return upsample2x_add(s, d, n, hs, wsz, 196, st); });
+      float *s_ = p4c, *d_ = p2a; const int n = NI, hs = H4, wsz = W4, ld = c196, ob = B16;
+      push("upsample", [=](cudaStream_t st) { return upsample2x_add(s_, d_, n, hs, wsz, 196, ld, ld, ob, ob, st); });
     }
-    conv("layer1_outconv2.0", p2a, NI, H2, W2, 196, 196, 196, 3, 1, true, nullptr, ACT_LEAKY, p2b, 196);
-    conv("layer1_outconv2.3", p2b, NI, H2, W2, 196, 196, 128, 3, 1, false, nullptr, ACT_NONE, a1, 128);
-    dbg["feat_f"] = DebugTensor{a1, static_cast<long long>(px2 * 128)};
-    float* featf = a1;
+    bconv("layer1_outconv2.0", p2a, H2, W2, 196, c196, 196, 3, 1, true, nullptr, ACT_LEAKY, p2b, c196, B16);
+    bconv("layer1_outconv2.3", p2b, H2, W2, 196, c196, 128, 3, 1, false, nullptr, ACT_NONE, featf, 128, 0);   // fp32 out
+    if (bf && w16_total > static_cast<size_t>(8) * 1024 * 1024) {
+      fprintf(stderr, "[mfr_b200] bf16 weight blob too small\n");
+      return MFR_ERR_ARG;
+    }
 
     // ---------------------------------------------------------------- pos-enc + coarse transformer
     {
       float *f = fc, *t = tok; float* pe = W_("pos_enc"); const int n = NI, l = L;
-      push("simt", [=](cudaStream_t st) { return posenc_tokens(f, pe, t, 512, n, l, 256, st); });
+      push("posenc", [=](cudaStream_t st) { return posenc_tokens(f, pe, t, 512, n, l, 256, st); });
     }
     const size_t half_tok = static_cast<size_t>(B) * L * 512, half_qkv = static_cast<size_t>(B) * L * 768;
     const size_t half_c = static_cast<size_t>(B) * L * 256, half_2c = static_cast<size_t>(B) * L * 512;
@@ -354,7 +387,7 @@ struct LoftrEngine {
       CoarseMatchBuffers cmb = cm; float* S_ = S;
       const int B_ = B, L_ = L, hc = H8, wc = W8, bd = border, sc = splits_col; const float th = thr;
       const float scale = static_cast<float>(H) / static_cast<float>(H8);
-      push("simt", [=](cudaStream_t st) {
+      push("coarse_match", [=](cudaStream_t st) {
         return coarse_match(S_, cmb, B_, L_, hc, wc, th, bd, scale, sc, st);
       }, 8);
     }
@@ -363,12 +396,12 @@ struct LoftrEngine {
     {
       CoarseMatchBuffers cmb = cm; float *tok_ = tok, *cin_ = cin, *cproj_ = cproj, *win_ = win;
       const int B_ = B, L_ = L, Mc = Mcap, Hf = H2, Wf = W2, wc = W8;
-      push("simt", [=](cudaStream_t st) {
+      push("fine_gather_coarse", [=](cudaStream_t st) {
         return fine_gather_coarse(tok_, 512, B_, L_, cmb.b_ids, cmb.i_ids, cmb.j_ids, cmb.m_total, Mc, cin_, st);
       });
       conv("fine.down_proj", cin, 2, 1, Mcap, 256, 256, 128, 1, 1, true, nullptr, ACT_NONE, cproj, 128, 0,
            cm.m_total);
-      push("simt", [=](cudaStream_t st) {
+      push("fine_gather_windows", [=](cudaStream_t st) {
         return fine_gather_windows(featf, B_, Hf, Wf, wc, cmb.b_ids, cmb.i_ids, cmb.j_ids, cmb.m_total, Mc,
                                    cproj_, win_, st);
       });
@@ -387,7 +420,7 @@ struct LoftrEngine {
                     fh2 + s_c, 1, rows, cm.m_total + 2, cm.m_total, true);
       CoarseMatchBuffers cmb = cm; float *f0 = ftok, *f1 = ftok + s_tok, *mk = mk1f, *ex = expec;
       const int Mc = Mcap; const float scale_f = static_cast<float>(H) / static_cast<float>(H2);
-      push("simt", [=](cudaStream_t st) {
+      push("fine_match", [=](cudaStream_t st) {
         return fine_match(f0, f1, 256, cmb.mkpts1_c, cmb.m_total, Mc, scale_f, mk, ex, st);
       });
     }
@@ -410,6 +443,14 @@ struct LoftrEngine {
       return MFR_ERR_ARG;
     }
     if (src_h > H || src_w > W || src_h < 1 || src_w < 1) return MFR_ERR_ARG;
+    if (precision == 1 && !w16_ready) {   // bf16 copies of the (folded) backbone conv weights
+      for (const auto& bc : bf16_convs) {
+        int rc = weights_to_bf16(W_(bc.name + ".w"), wblob16 + bc.off, static_cast<size_t>(bc.cout) * bc.taps, bc.cin,
+                                 bc.cin_pad, st);
+        if (rc != MFR_OK) return rc;
+      }
+      w16_ready = true;
+    }
     const size_t half = static_cast<size_t>(B) * H * W;
     if (src_h == H && src_w == W) {
       MFR_CUDA_CHECK(cudaMemcpyAsync(img, img0, half * 4, cudaMemcpyDeviceToDevice, st));
@@ -491,10 +532,11 @@ struct LoftrEngine {
 };
 
 // ---------------------------------------------------------------------------------------------
-int loftr_create(int B, int H, int W, float thr, int border, float temperature, LoftrEngine** out) {
-  if (B < 1 || H % 8 || W % 8 || H < 32 || W < 32) return MFR_ERR_ARG;
+int loftr_create(int B, int H, int W, float thr, int border, float temperature, int precision, LoftrEngine** out) {
+  if (B < 1 || H % 8 || W % 8 || H < 32 || W < 32 || precision < 0 || precision > 1) return MFR_ERR_ARG;
   auto* e = new LoftrEngine();
   e->B = B; e->H = H; e->W = W; e->thr = thr; e->border = border; e->temperature = temperature;
+  e->precision = precision;
   int rc = e->build();
   if (rc != MFR_OK) { delete e; return rc; }
   *out = e;

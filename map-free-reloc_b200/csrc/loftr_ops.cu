@@ -21,6 +21,14 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // ------------------------------------------------------------------------------------------ stem
 constexpr int kStemPx = 32;
+__device__ __forceinline__ unsigned short f2bf(float f) {
+  unsigned short r;
+  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(f));
+  return r;
+}
+__device__ __forceinline__ float bf2f(unsigned short b) { return __uint_as_float(static_cast<unsigned>(b) << 16); }
+
+template <bool OBF>
 __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ img,
                                                    const float* __restrict__ w,
                                                    const float* __restrict__ bias,
@@ -59,21 +67,37 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ img
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
       const int x = x0 + px0 + p;
-      if (x < Wo)
-        out[((static_cast<size_t>(n) * Ho + y) * Wo + x) * 128 + c] = fmaxf(acc[p] + b, 0.f);
+      if (x < Wo) {
+        const size_t o = ((static_cast<size_t>(n) * Ho + y) * Wo + x) * 128 + c;
+        if constexpr (OBF) reinterpret_cast<unsigned short*>(out)[o] = f2bf(fmaxf(acc[p] + b, 0.f));
+        else out[o] = fmaxf(acc[p] + b, 0.f);
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------ upsample
-__global__ void upsample2x_add_kernel(const float* __restrict__ src, float* __restrict__ dst, int N,
-                                      int Hs, int Ws, int C4, float ry, float rx) {
+template <bool SBF>
+__device__ __forceinline__ float4 ld4(const void* base, size_t elem) {
+  if constexpr (SBF) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(base) + elem);
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+  } else {
+    return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem);
+  }
+}
+// dst[n,y,x,c] += bilinear(src)[n,y,x,c]; pixel strides lds / ldd (elements), C4 = C / 4
+template <bool SBF, bool DBF>
+__global__ void upsample2x_add_kernel(const void* __restrict__ src, void* __restrict__ dst, int N, int Hs, int Ws,
+                                      int C4, int lds, int ldd, float ry, float rx) {
   const int Hd = 2 * Hs, Wd = 2 * Ws;
   const size_t total = static_cast<size_t>(N) * Hd * Wd * C4;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c4 = static_cast<int>(idx % C4);
   size_t pix = idx / C4;
+  const size_t dpix = pix;
   const int x = static_cast<int>(pix % Wd);
   pix /= Wd;
   const int y = static_cast<int>(pix % Hd);
@@ -83,18 +107,35 @@ __global__ void upsample2x_add_kernel(const float* __restrict__ src, float* __re
   const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
   const float ly = sy - y0, lx = sx - x0;
   const float hy = 1.f - ly, hx = 1.f - lx;
-  const float4* s = reinterpret_cast<const float4*>(src) + static_cast<size_t>(n) * Hs * Ws * C4;
-  const float4 a = s[(static_cast<size_t>(y0) * Ws + x0) * C4 + c4];
-  const float4 b = s[(static_cast<size_t>(y0) * Ws + x1) * C4 + c4];
-  const float4 c = s[(static_cast<size_t>(y1) * Ws + x0) * C4 + c4];
-  const float4 d = s[(static_cast<size_t>(y1) * Ws + x1) * C4 + c4];
-  float4* o = reinterpret_cast<float4*>(dst) + idx;
-  float4 v = *o;
+  const size_t sb = static_cast<size_t>(n) * Hs * Ws;
+  const float4 a = ld4<SBF>(src, (sb + static_cast<size_t>(y0) * Ws + x0) * lds + c4 * 4);
+  const float4 b = ld4<SBF>(src, (sb + static_cast<size_t>(y0) * Ws + x1) * lds + c4 * 4);
+  const float4 c = ld4<SBF>(src, (sb + static_cast<size_t>(y1) * Ws + x0) * lds + c4 * 4);
+  const float4 d = ld4<SBF>(src, (sb + static_cast<size_t>(y1) * Ws + x1) * lds + c4 * 4);
+  const size_t de = dpix * ldd + c4 * 4;
+  float4 v = ld4<DBF>(dst, de);
   v.x += hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x);
   v.y += hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y);
   v.z += hy * (hx * a.z + lx * b.z) + ly * (hx * c.z + lx * d.z);
   v.w += hy * (hx * a.w + lx * b.w) + ly * (hx * c.w + lx * d.w);
-  *o = v;
+  if constexpr (DBF) {
+    uint2 o;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(v.y), "f"(v.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(v.w), "f"(v.z));
+    *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(dst) + de) = o;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + de) = v;
+  }
+}
+
+// fp32 [rows][cin] -> bf16 [rows][cin_pad] (zero padded): conv weights for the bf16 tensor-core path
+__global__ void weights_to_bf16_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, size_t rows,
+                                       int cin, int cin_pad) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= rows * cin_pad) return;
+  const size_t r = idx / cin_pad;
+  const int c = static_cast<int>(idx % cin_pad);
+  dst[idx] = c < cin ? f2bf(src[r * cin + c]) : static_cast<unsigned short>(0);
 }
 
 // ------------------------------------------------------------------------------------------ posenc
@@ -661,22 +702,35 @@ __global__ void __launch_bounds__(128) fine_match_kernel(const float* __restrict
 // launch wrappers
 // ================================================================================================
 int stem_conv7x7(const float* img, const float* w, const float* bias, float* out, int NI, int H, int W,
-                 cudaStream_t st) {
+                 cudaStream_t st, int out_bf16) {
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   dim3 grid((Wo + kStemPx - 1) / kStemPx, Ho, NI);
-  stem_kernel<<<grid, 128, 0, st>>>(img, w, bias, out, H, W, Ho, Wo);
+  if (out_bf16) stem_kernel<true><<<grid, 128, 0, st>>>(img, w, bias, out, H, W, Ho, Wo);
+  else stem_kernel<false><<<grid, 128, 0, st>>>(img, w, bias, out, H, W, Ho, Wo);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }
 
-int upsample2x_add(const float* src, float* dst, int N, int Hs, int Ws, int C, cudaStream_t st) {
-  if (C % 4) return MFR_ERR_ARG;
+int upsample2x_add(const void* src, void* dst, int N, int Hs, int Ws, int C, int lds, int ldd, int src_bf16,
+                   int dst_bf16, cudaStream_t st) {
+  if (C % 4 || lds % 4 || ldd % 4) return MFR_ERR_ARG;
   const int Hd = 2 * Hs, Wd = 2 * Ws;
   const float ry = Hd > 1 ? static_cast<float>(Hs - 1) / static_cast<float>(Hd - 1) : 0.f;
   const float rx = Wd > 1 ? static_cast<float>(Ws - 1) / static_cast<float>(Wd - 1) : 0.f;
   const size_t total = static_cast<size_t>(N) * Hd * Wd * (C / 4);
-  upsample2x_add_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, dst, N, Hs, Ws,
-                                                                                   C / 4, ry, rx);
+  const unsigned g = static_cast<unsigned>((total + 255) / 256);
+  if (src_bf16 && dst_bf16) upsample2x_add_kernel<true, true><<<g, 256, 0, st>>>(src, dst, N, Hs, Ws, C / 4, lds, ldd, ry, rx);
+  else if (!src_bf16 && dst_bf16) upsample2x_add_kernel<false, true><<<g, 256, 0, st>>>(src, dst, N, Hs, Ws, C / 4, lds, ldd, ry, rx);
+  else if (!src_bf16 && !dst_bf16) upsample2x_add_kernel<false, false><<<g, 256, 0, st>>>(src, dst, N, Hs, Ws, C / 4, lds, ldd, ry, rx);
+  else return MFR_ERR_UNSUPPORTED;
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int weights_to_bf16(const float* src, void* dst, size_t rows, int cin, int cin_pad, cudaStream_t st) {
+  const size_t total = rows * cin_pad;
+  weights_to_bf16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      src, static_cast<unsigned short*>(dst), rows, cin, cin_pad);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }

@@ -7,10 +7,14 @@ namespace mfr {
 
 // stem: conv7x7 stride 2 pad 3, 1 -> 128 channels, folded BN bias, ReLU (resnet_fpn.py:60-62,102)
 int stem_conv7x7(const float* img, const float* w /*[128][49]*/, const float* bias, float* out,
-                 int NI, int H, int W, cudaStream_t st);
+                 int NI, int H, int W, cudaStream_t st, int out_bf16 = 0);
 
 // dst[n,y,x,:] += bilinear_x2_align_corners(src)[n,y,x,:]   (resnet_fpn.py:110,114)
-int upsample2x_add(const float* src, float* dst, int N, int Hs, int Ws, int C, cudaStream_t st);
+// pixel strides lds / ldd in elements; src / dst fp32 or bf16
+int upsample2x_add(const void* src, void* dst, int N, int Hs, int Ws, int C, int lds, int ldd, int src_bf16,
+                   int dst_bf16, cudaStream_t st);
+// fp32 [rows][cin] -> bf16 [rows][cin_pad], zero padded
+int weights_to_bf16(const float* src, void* dst, size_t rows, int cin, int cin_pad, cudaStream_t st);
 
 // tok[n,l,0:C] = feat[n,l,:] + pe[l,:]   (loftr.py:58-59, position_encoding.py:42)
 int posenc_tokens(const float* feat, const float* pe, float* tok, long long ldt, int N, int L, int C,

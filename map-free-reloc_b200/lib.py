@@ -38,7 +38,9 @@ SIGNATURES = {
     "mfr_conv2d_nhwc_tf32": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_ll, c_vp, c_int, c_int,
                                      c_int, c_int, c_int, c_int, c_vp, c_vp, c_ll, c_int, c_float,
                                      c_vp, c_ll, c_vp]),
-    "mfr_loftr_create": (c_int, [c_int, c_int, c_int, c_float, c_int, c_float, c_pp]),
+    "mfr_conv2d_nhwc_bf16": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_ll, c_vp, c_ll, c_int, c_int, c_int,
+                                     c_int, c_int, c_vp, c_vp, c_ll, c_int, c_float, c_vp, c_ll, c_int, c_vp]),
+    "mfr_loftr_create": (c_int, [c_int, c_int, c_int, c_float, c_int, c_float, c_int, c_pp]),
     "mfr_loftr_destroy": (None, [c_vp]),
     "mfr_loftr_num_weights": (c_int, [c_vp]),
     "mfr_loftr_weight_name": (ctypes.c_char_p, [c_vp, c_int]),

@@ -176,7 +176,8 @@ def synthetic_state_dict(seed=0):
 class LoFTR:
     """CUDA LoFTR engine for ``batch`` pairs of [H, W] images (H, W multiples of 8)."""
 
-    def __init__(self, state_dict, batch=1, height=720, width=544, cfg=None, device=0, graph=True):
+    def __init__(self, state_dict, batch=1, height=720, width=544, cfg=None, device=0, graph=True,
+                 precision="tf32"):
         if not torch.cuda.is_available():
             raise _lib.MfrError("mfr_b200.LoFTR needs a CUDA device (no CPU fallback)")
         self._l = _lib.load()
@@ -186,9 +187,10 @@ class LoFTR:
         torch.cuda.set_device(self.device)
         self.stream = torch.cuda.Stream(device=self.device)
         h = ctypes.c_void_p()
+        self.precision = {"tf32": 0, "bf16": 1}[precision]
         _lib.check(self._l.mfr_loftr_create(self.B, self.H, self.W, float(self.cfg["thr"]),
                                             int(self.cfg["border_rm"]), float(self.cfg["temperature"]),
-                                            ctypes.byref(h)), "mfr_loftr_create")
+                                            self.precision, ctypes.byref(h)), "mfr_loftr_create")
         self._h = h
         self._l.mfr_loftr_set_graph(self._h, int(bool(graph)))
         self.load_state_dict(state_dict)

@@ -26,7 +26,7 @@ t0 = time.time()
 with torch.no_grad():
     o = lo.loftr_forward(i0, i1, sd, {"thr": thr}, True)
 print("oracle time %.2fs, M=%d" % (time.time() - t0, len(o["mkpts0_f"])))
-eng = loftr.LoFTR(sd, batch=B, height=H, width=W, cfg={"thr": thr}, graph=bool(int(os.environ.get("GRAPH", 1))))
+eng = loftr.LoFTR(sd, batch=B, height=H, width=W, cfg={"thr": thr}, graph=bool(int(os.environ.get("GRAPH", 1))), precision=os.environ.get("PRECISION", "tf32"))
 print("kernels per forward:", eng.num_kernels())
 out = eng.forward(i0.cuda(), i1.cuda())
 out = eng.forward(i0.cuda(), i1.cuda())  # second call exercises the graph replay

@@ -85,3 +85,37 @@ def test_batched_xyt(mfr):
     out = _run(mfr, a, b, 1, 0, alpha=1.0 / 25.6, batched=True)
     ref = torch.einsum("nlc,nsc->nls", a[:, 0].double(), b.double()).float() / 25.6
     _check(out[:, 0], ref)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,R,stride,out_bf16,use_res", [
+    (2, 40, 36, 128, 128, 3, 1, True, True),
+    (2, 40, 36, 128, 196, 3, 2, True, False),
+    (2, 23, 17, 196, 256, 3, 1, False, False),     # Cin 196 padded to 200 in memory (16-byte strides)
+    (1, 1, 300, 256, 256, 1, 1, False, False),
+])
+def test_bf16_conv_matches_torch(mfr, N, H, W, Cin, Cout, R, stride, out_bf16, use_res):
+    """bf16 operands / fp32 accumulate vs an fp64 reference on the same bf16-rounded inputs
+    (tolerance 1e-2 of the output range covers the bf16 rounding of the output itself)."""
+    lib = mfr.load()
+    g = torch.Generator(device="cpu").manual_seed(99)
+    Cp = (Cin + 7) // 8 * 8
+    x = torch.zeros(N, H, W, Cp); x[..., :Cin] = torch.randn(N, H, W, Cin, generator=g)
+    w = torch.zeros(Cout, R * R, Cp); w[..., :Cin] = torch.randn(Cout, R * R, Cin, generator=g) / (R * R * Cin) ** 0.5
+    xb, wb = x.bfloat16().cuda(), w.bfloat16().cuda()
+    pad = R // 2
+    Ho = (H + 2 * pad - R) // stride + 1; Wo = (W + 2 * pad - R) // stride + 1
+    bias = torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(N, Ho, Wo, Cout, generator=g).bfloat16().cuda() if use_res else None
+    out = torch.zeros(N, Ho, Wo, Cout, device="cuda", dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    mfr.check(lib.mfr_conv2d_nhwc_bf16(mfr.ptr(xb), N, H, W, Cin, Cp, mfr.ptr(wb), Cp, Cout, R, R, stride, pad,
+                                       mfr.ptr(bias), mfr.ptr(res), Cout, 1, 1.0, mfr.ptr(out), Cout, int(out_bf16),
+                                       mfr.cur_stream()))
+    torch.cuda.synchronize()
+    xr = xb[..., :Cin].double().permute(0, 3, 1, 2)
+    wr = wb[..., :Cin].double().reshape(Cout, R, R, Cin).permute(0, 3, 1, 2)
+    ref = F.conv2d(xr, wr, None, stride=stride, padding=pad).permute(0, 2, 3, 1) + bias.double()
+    if use_res:
+        ref = ref + res.double()
+    ref = torch.relu(ref)
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 1e-2 * ref.abs().max().item(), err

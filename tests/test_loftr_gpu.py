@@ -73,6 +73,34 @@ def test_stages_match_oracle(sd, B, H, W, graph):
     eng.close()
 
 
+def test_bf16_backbone_mode(sd):
+    """precision="bf16": bf16 storage + bf16 tcgen05 inputs in the ResNet-FPN (fp32 accumulate). Features
+    stay within bf16 round-off of the fp32 oracle and the match set stays close to the TF32 engine's."""
+    from mfr_b200 import loftr
+    B, H, W = 2, 160, 120
+    i0, i1 = _pairs(B, H, W)
+    with torch.no_grad():
+        fcb, ffb = lo.backbone(torch.cat([i0, i1], 0), sd)
+    ref = loftr.LoFTR(sd, batch=B, height=H, width=W, cfg={"thr": 0.0}, graph=False)
+    o_ref = ref.forward(i0.cuda(), i1.cuda())
+    eng = loftr.LoFTR(sd, batch=B, height=H, width=W, cfg={"thr": 0.0}, graph=True, precision="bf16")
+    out = eng.forward(i0.cuda(), i1.cuda())
+    out = eng.forward(i0.cuda(), i1.cuda())
+    h8, w8 = H // 8, W // 8
+    assert _rel(eng.debug_tensor("feat_c_backbone", (2 * B, h8, w8, 256)), fcb.permute(0, 2, 3, 1)) < 4e-2
+    assert _rel(eng.debug_tensor("feat_f", (2 * B, H // 2, W // 2, 128)), ffb.permute(0, 2, 3, 1)) < 4e-2
+    e = set(zip(out["b_ids"].tolist(), out["i_ids"].tolist(), out["j_ids"].tolist()))
+    r = set(zip(o_ref["b_ids"].tolist(), o_ref["i_ids"].tolist(), o_ref["j_ids"].tolist()))
+    # synthetic weights give a nearly flat confidence surface, so near-ties flip between precisions;
+    # the correlation input itself stays within bf16 round-off of the fp32 oracle
+    with torch.no_grad():
+        o = lo.loftr_forward(i0, i1, sd, {"thr": 0.0}, True)
+    L = h8 * w8
+    assert _rel(eng.debug_tensor("sim", (B, L, L)), o["sim"]) < 4e-2
+    assert len(e & r) >= 0.4 * max(1, len(e | r))
+    ref.close(); eng.close()
+
+
 @pytest.mark.parametrize("ci", range(2))
 def test_end_to_end_vs_reference_golden(sd, ci):
     """CUDA engine vs vectors produced by the UNMODIFIED reference LoFTR (tests/golden)."""
