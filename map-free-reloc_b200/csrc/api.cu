@@ -234,12 +234,17 @@ int mfr_host_decompose_essential(const double* E, double* R1, double* R2, double
 float mfr_debug_probe_overhead(int mode, int smem_bytes, int grid, int iters) {
   return mfr::conv_gemm_probe_overhead(mode, smem_bytes, grid, iters, nullptr);
 }
+float mfr_debug_mma_probe(int n_per_commit, int BN, int bf16, int wait_each, int iters, int grid, int two_commits) {
+  return mfr::conv_gemm_mma_probe(n_per_commit, BN, bf16, wait_each, iters, grid, two_commits);
+}
+
 float mfr_debug_time_conv(const float* x, int N, int H, int W, int Cin, const float* w, int Cout, int R,
-                          int stride, float* out, int iters) {
+                          int stride, float* out, int iters, int flags, const float* residual) {
   mfr::ConvGemmDesc d{};
   d.x = x; d.N = N; d.H = H; d.W = W; d.Cin = Cin; d.ldx = Cin;
   d.w = w; d.Cout = Cout; d.R = R; d.S = R; d.stride = stride; d.pad = R / 2;
   d.act = 1; d.alpha = 1.f; d.out = out; d.ldo = Cout; d.ldr = Cout;
+  d.in_bf16 = flags & 1; d.out_bf16 = (flags >> 1) & 1; d.residual = residual;
   mfr::ConvGemmParams p;
   if (mfr::conv_gemm_build(d, &p) != MFR_OK) return -1.f;
   return mfr::conv_gemm_time_prebuilt(p, iters, nullptr);

@@ -74,8 +74,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
-  if (mbar_try_wait(bar, parity)) return;
+// Slow path kept out of line so that the waits inside the single-thread TMA / MMA issue loops stay a
+// handful of instructions (those loops are instruction-issue bound).
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int tag) {
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > MFR_SPIN_TIMEOUT_CYCLES) {
@@ -84,6 +85,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, tag);
+}
+// One lane of a converged warp (elect.sync): lets ptxas emit a single UTMALDG / UTCHMMA instead of the
+// per-active-thread loop it wraps around uniform-datapath instructions in divergent code.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---------------------------------------------------------------------------------------------

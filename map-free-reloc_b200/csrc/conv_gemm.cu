@@ -14,19 +14,23 @@
 #include "conv_gemm.cuh"
 
 #include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 namespace mfr {
 
 namespace {
 
-constexpr int kMaxStages = 8;
+constexpr int kMaxSlots = 8;                    // slots per operand ring (A ring and B ring)
 constexpr int kBlockK = 32;                     // fp32 elements per k-block = 128 B = swizzle span
 constexpr int kUmmaK = 8;                       // tf32: 32 B of K per instruction
 constexpr int kTileM = 128;
 constexpr int kMaxBN = 256;
 constexpr int kAStage = kTileM * kBlockK * 4;   // 16 KB
-constexpr int kRingBytes = 192 * 1024;          // operand ring: stages = kRingBytes / (16 KB + BN * 128 B)
+constexpr int kRingBytes = 204 * 1024;          // operand rings (A slots + B slots)
 constexpr int kStgStride = 36;                  // floats per staged row (144 B: conflict-free 128-bit access)
 constexpr int kStgBytes = 4 * 32 * kStgStride * 4;  // epilogue transpose buffers, one per epilogue warp
 constexpr int kSmemBytes = kRingBytes + kStgBytes + 1024 /*align slack*/;
@@ -68,55 +72,136 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
+// Epilogue of one 128-pixel sub-tile, run by the 4 epilogue warps (warp q owns TMEM lanes 32q..32q+31):
+// per 32-channel chunk  tcgen05.ld (thread = pixel) -> per-warp shared-memory transpose -> 8 x
+// (LDS.128 -> alpha/bias/residual/act -> coalesced STG); lane (sub_r, sub_c) handles staged rows
+// k*4+sub_r, channels sub_c..sub_c+3. The residual of chunk c+1 is fetched before chunk c is stored
+// (and the first one before the accumulator wait), so its HBM latency never sits in front of a store.
 template <int ACT, bool RES, bool OBF>
-__device__ __forceinline__ void store_chunk(const float* __restrict__ stg_rd, const long long (&off_o)[8],
-                                            const long long (&off_r)[8], uint32_t okmask, float alpha,
-                                            float4 b4, const float* __restrict__ res_n,
-                                            float* __restrict__ out_n) {
-  float4 vv[8];
+__device__ __forceinline__ void epilogue_subtile(const ConvGemmParams& p, uint32_t taddr, float* stg, int lane,
+                                                 int n0, const long long (&off_o)[8], const long long (&off_r)[8],
+                                                 uint32_t okmask, uint32_t wait_bar, uint32_t wait_phase,
+                                                 bool do_wait) {
+  using RT = typename std::conditional<OBF, uint2, float4>::type;
+  const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+  RT rnext[8];
+  auto issue_res = [&](int c0) {
+    const int n = n0 + c0 + sub_c;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) vv[k] = *reinterpret_cast<const float4*>(stg_rd + k * (4 * kStgStride));
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float4 v = vv[k];
-    if (okmask & (1u << k)) {
-      v.x = fmaf(v.x, alpha, b4.x); v.y = fmaf(v.y, alpha, b4.y);
-      v.z = fmaf(v.z, alpha, b4.z); v.w = fmaf(v.w, alpha, b4.w);
-      if constexpr (RES) {
-        float4 r4;
-        if constexpr (OBF)   // res_n / out_n point at bf16 storage: element offsets count 2-byte units
-          r4 = bf16x4_to_float4(__ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(res_n) + off_r[k])));
+    for (int k = 0; k < 8; ++k) {
+      if constexpr (OBF) rnext[k] = make_uint2(0u, 0u);
+      else rnext[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (((okmask >> k) & 1u) && n < p.Cout && c0 + sub_c < p.BN) {
+        if constexpr (OBF)
+          rnext[k] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + off_r[k] + n));
         else
-          r4 = __ldg(reinterpret_cast<const float4*>(res_n + off_r[k]));
-        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+          rnext[k] = __ldg(reinterpret_cast<const float4*>(p.residual + off_r[k] + n));
       }
-      v.x = act_fn<ACT>(v.x); v.y = act_fn<ACT>(v.y); v.z = act_fn<ACT>(v.z); v.w = act_fn<ACT>(v.w);
-      if constexpr (OBF)
-        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out_n) + off_o[k]) =
-            make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-      else
-        *reinterpret_cast<float4*>(out_n + off_o[k]) = v;
+    }
+  };
+  if constexpr (RES) issue_res(0);
+  if (do_wait) {
+    mbar_wait(wait_bar, wait_phase, 4);
+    tc_fence_after();
+  }
+  const float alpha = p.alpha;
+  for (int c0 = 0; c0 < p.BN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4*>(stg + lane * kStgStride + j * 4) =
+          make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    __syncwarp();
+    RT rcur[8];
+    if constexpr (RES) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) rcur[k] = rnext[k];
+      if (c0 + 32 < p.BN) issue_res(c0 + 32);
+    }
+    const int n = n0 + c0 + sub_c;
+    const uint32_t okm = (n < p.Cout && c0 + sub_c < p.BN) ? okmask : 0u;   // BN need not be a multiple of 32
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias != nullptr && okm) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    const bool do_act = n < p.act_cols;   // n..n+3 never straddle act_cols (multiple of 4)
+    const float* stg_rd = stg + sub_r * kStgStride + sub_c;
+    float4 vv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) vv[k] = *reinterpret_cast<const float4*>(stg_rd + k * (4 * kStgStride));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float4 v = vv[k];
+      if (okm & (1u << k)) {
+        v.x = fmaf(v.x, alpha, b4.x); v.y = fmaf(v.y, alpha, b4.y);
+        v.z = fmaf(v.z, alpha, b4.z); v.w = fmaf(v.w, alpha, b4.w);
+        if constexpr (RES) {
+          float4 r4;
+          if constexpr (OBF) r4 = bf16x4_to_float4(rcur[k]);
+          else r4 = rcur[k];
+          v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+        }
+        if (do_act) {
+          v.x = act_fn<ACT>(v.x); v.y = act_fn<ACT>(v.y); v.z = act_fn<ACT>(v.z); v.w = act_fn<ACT>(v.w);
+        }
+        if constexpr (OBF)
+          *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + off_o[k] + n) =
+              make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        else
+          *reinterpret_cast<float4*>(p.out + off_o[k] + n) = v;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Scalar epilogue for shapes the vector path cannot take (Cout or strides not multiples of 4); fp32 only.
+__device__ __forceinline__ void epilogue_subtile_scalar(const ConvGemmParams& p, uint32_t taddr, int n0, bool row_ok,
+                                                        long long o_off, long long r_off) {
+  for (int c0 = 0; c0 < p.BN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
+    tmem_ld_wait();
+    if (row_ok) {
+      float* orow = p.out + o_off;
+      const float* rrow = p.residual ? p.residual + r_off : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = n0 + c0 + j;
+        if (n < p.Cout && c0 + j < p.BN) {
+          float v = __uint_as_float(r[j]) * p.alpha;
+          if (p.bias) v += __ldg(p.bias + n);
+          if (rrow) v += __ldg(rrow + n);
+          orow[n] = n < p.act_cols ? apply_act(v, p.act) : v;
+        }
+      }
     }
   }
 }
 
+// 64-bit shared-memory matrix descriptor = constant high part | ((address >> 4) & 0x3fff)
+constexpr uint64_t kDescHi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+__device__ __forceinline__ uint64_t desc_at(uint32_t addr) { return kDescHi | ((addr >> 4) & 0x3fffu); }
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bars[2 * kMaxStages + 4];
+  __shared__ __align__(8) uint64_t s_bars[4 * kMaxSlots + 4];
   __shared__ uint32_t s_tmem_base;
-  const int kStages = p.num_stages;
-  const int kBStage = p.b_bytes;                 // BN rows x 128 B
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
-  const uint32_t smem_b = smem_base + kStages * kAStage;
+  const uint32_t smem_b = smem_base + p.a_slots * p.a_slot_bytes;
   const uint32_t smem_stg = smem_base + kRingBytes;
   const uint32_t bar_base = smem_u32(s_bars);
-  // barriers: full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2]
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
+  // barriers: a_full[8], a_empty[8], b_full[8], b_empty[8], tmem_full[2], tmem_empty[2].
+  // Generic mode uses one ring (A and B tile of a k-block share slot and barriers: the "a" set);
+  // halo mode uses both rings.
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (kMaxSlots + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * kMaxSlots + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (3 * kMaxSlots + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (4 * kMaxSlots + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (4 * kMaxSlots + 2 + a); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -125,10 +210,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
+    for (int s = 0; s < 4 * kMaxSlots; ++s) mbar_init(bar_base + 8u * s, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 4);
@@ -152,85 +234,172 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   }
   const int m_tiles = p.N * p.tiles_y * tiles_x;
   const int total_tiles = m_tiles * p.n_tiles;
-  const int num_kb = p.R * p.S * p.kb_per_tap;
+  const int tile_rows = p.MT * p.TH;          // output rows of one CTA tile
+  // The two issue loops below are executed by whole (converged) warps with elect.sync around the
+  // TMA / MMA instructions, and keep their per-k-block instruction count minimal: with one thread
+  // issuing, instruction latency is what bounds them.
+  const int kb_per_tap = p.kb_per_tap, kblk = p.kblk, R = p.R, S = p.S;
+  const int a_slots = p.a_slots, b_slots = p.b_slots, cbatch = p.cbatch;
+  const uint32_t a_slot_bytes = p.a_slot_bytes, a_bytes = p.a_bytes, b_bytes = p.b_bytes;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile % m_tiles, nt = tile / m_tiles;
-        const int tx = mt % tiles_x;
-        const int ty = (mt / tiles_x) % p.tiles_y;
-        const int img = mt / (tiles_x * p.tiles_y);
-        const int x_in0 = tx * p.TW * p.stride - p.pad;
-        const int y_in0 = ty * p.TH * p.stride - p.pad;
-        const int n0 = nt * p.BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / p.kb_per_tap;
-          const int cb = kb - tap * p.kb_per_tap;
-          const int ky = tap / p.S, kx = tap - ky * p.S;
-          mbar_wait(empty_bar(stage), phase ^ 1u, 1);
-          mbar_arrive_expect_tx(full_bar(stage), static_cast<uint32_t>(p.a_bytes + p.b_bytes));
-          tma_load_4d(smem_a + stage * kAStage, &p.tmA, full_bar(stage), cb * p.kblk, x_in0 + kx,
-                      y_in0 + ky, img);
-          tma_load_3d(smem_b + stage * kBStage, &p.tmB, full_bar(stage), cb * p.kblk,
-                      p.b_batched ? img : tap, n0);
-          if (kb == 0 && tile == static_cast<int>(blockIdx.x)) MFR_STAMP(2);
-          if (kb == num_kb - 1 && tile == static_cast<int>(blockIdx.x)) MFR_STAMP(3);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile % m_tiles, nt = tile / m_tiles;
+      const int tx = mt % tiles_x;
+      const int ty = (mt / tiles_x) % p.tiles_y;
+      const int img = mt / (tiles_x * p.tiles_y);
+      const int x_in0 = tx * p.TW * p.stride - p.pad;
+      const int y_in0 = ty * tile_rows * p.stride - p.pad;
+      const int n0 = nt * p.BN;
+      if (p.halo) {
+        for (int cb = 0; cb < kb_per_tap; ++cb) {
+          const int c0 = cb * kblk;
+          for (int kx = 0; kx < 3; ++kx) {
+            mbar_wait(a_empty(sa), pa ^ 1u, 1);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(a_full(sa), a_bytes);
+              tma_load_4d(smem_a + sa * a_slot_bytes, &p.tmA, a_full(sa), c0, x_in0 + kx, y_in0, img);
+            }
+            if (++sa == a_slots) { sa = 0; pa ^= 1u; }
+            for (int ky = 0; ky < 3; ++ky) {
+              mbar_wait(b_empty(sb), pb ^ 1u, 5);
+              if (elect_one_sync()) {
+                mbar_arrive_expect_tx(b_full(sb), b_bytes);
+                tma_load_3d(smem_b + sb * b_bytes, &p.tmB, b_full(sb), c0, ky * 3 + kx, n0);
+              }
+              if (++sb == b_slots) { sb = 0; pb ^= 1u; }
+            }
+          }
+        }
+      } else {
+        const int bz = p.b_batched ? img : -1;
+        for (int cb = 0; cb < kb_per_tap; ++cb) {
+          const int c0 = cb * kblk;
+          int tap = 0;
+          for (int ky = 0; ky < R; ++ky) {
+            for (int kx = 0; kx < S; ++kx, ++tap) {
+              mbar_wait(a_empty(sa), pa ^ 1u, 1);
+              if (elect_one_sync()) {
+                mbar_arrive_expect_tx(a_full(sa), a_bytes + b_bytes);
+                tma_load_4d(smem_a + sa * a_slot_bytes, &p.tmA, a_full(sa), c0, x_in0 + kx, y_in0 + ky, img);
+                tma_load_3d(smem_b + sa * b_bytes, &p.tmB, a_full(sa), c0, bz >= 0 ? bz : tap, n0);
+              }
+              if (++sa == a_slots) { sa = 0; pa ^= 1u; }
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(p.in_bf16 ? 1u : 2u, kTileM, static_cast<uint32_t>(p.BN));
-      const bool bf16_in = p.in_bf16 != 0;
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1u;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
-        tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase, 3);
-          tc_fence_after();
-          if (kb == 0 && it == 0) MFR_STAMP(4);
-          if (kb == num_kb - 1 && it == 0) MFR_STAMP(5);
-          const uint32_t a_addr = smem_a + stage * kAStage;
-          const uint32_t b_addr = smem_b + stage * kBStage;
-#pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t adesc = umma_desc_sw128_kmajor(a_addr + k * kUmmaK * 4);
-            const uint64_t bdesc = umma_desc_sw128_kmajor(b_addr + k * kUmmaK * 4);
-            if (bf16_in) tc_mma_bf16(tmem_acc, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-            else tc_mma_tf32(tmem_acc, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+    const uint32_t idesc = umma_idesc(p.in_bf16 ? 1u : 2u, kTileM, static_cast<uint32_t>(p.BN));
+    const bool bf16_in = p.in_bf16 != 0;
+    const int MT = p.MT, ksteps_last = p.ksteps_last;
+    const uint32_t sub_bytes = static_cast<uint32_t>(p.TH * p.TW * 128);   // A bytes of one 128-row sub-tile
+    const uint32_t ky_bytes = static_cast<uint32_t>(p.TW * 128);           // one halo row
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
+      uint32_t accum = 0;   // first MMA of the tile overwrites the accumulator
+      if (p.halo) {
+        for (int cb = 0; cb < kb_per_tap; ++cb) {
+          const int nk = cb == kb_per_tap - 1 ? ksteps_last : kBlockK / kUmmaK;
+          for (int kx = 0; kx < 3; ++kx) {
+            mbar_wait(a_full(sa), pa, 3);
+            const uint32_t a_slot = smem_a + sa * a_slot_bytes;
+            const int sb0 = sb;
+            for (int ky = 0; ky < 3; ++ky) {
+              mbar_wait(b_full(sb), pb, 6);
+              tc_fence_after();
+              if (elect_one_sync()) {
+                const uint64_t bdesc = desc_at(smem_b + sb * b_bytes);
+                for (int m = 0; m < MT; ++m) {
+                  const uint64_t adesc = desc_at(a_slot + m * sub_bytes + ky * ky_bytes);
+                  const uint32_t d_addr = tmem_acc + static_cast<uint32_t>(m * 128);
+                  uint32_t acc_m = accum;
+                  for (int k = 0; k < nk; ++k) {   // +32 B of K per step = +2 in the descriptor address field
+                    if (bf16_in) tc_mma_bf16(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, acc_m);
+                    else tc_mma_tf32(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, acc_m);
+                    acc_m = 1u;
+                  }
+                }
+              }
+              accum = 1u;
+              if (++sb == b_slots) { sb = 0; pb ^= 1u; }
+            }
+            // one pipeline drain per group: release the three B slots and the A slot together
+            if (elect_one_sync()) {
+              int s2 = sb0;
+              tc_commit(b_empty(s2));
+              if (++s2 == b_slots) s2 = 0;
+              tc_commit(b_empty(s2));
+              if (++s2 == b_slots) s2 = 0;
+              tc_commit(b_empty(s2));
+              tc_commit(a_empty(sa));
+            }
+            if (++sa == a_slots) { sa = 0; pa ^= 1u; }
           }
-          tc_commit(empty_bar(stage));
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(tfull_bar(acc));
+      } else {
+        const int num_kb = R * S * kb_per_tap, taps = R * S;
+        int in_batch = 0, batch_first = sa, tap = 0, cb = 0;
+        for (int i = 0; i < num_kb; ++i) {
+          const int nk = cb == kb_per_tap - 1 ? ksteps_last : kBlockK / kUmmaK;
+          mbar_wait(a_full(sa), pa, 3);
+          tc_fence_after();
+          ++in_batch;
+          const bool close = in_batch == cbatch || i == num_kb - 1;
+          if (elect_one_sync()) {
+            const uint64_t bdesc = desc_at(smem_b + sa * b_bytes);
+            const uint32_t a_slot = smem_a + sa * a_slot_bytes;
+            for (int m = 0; m < MT; ++m) {
+              const uint64_t adesc = desc_at(a_slot + m * sub_bytes);
+              const uint32_t d_addr = tmem_acc + static_cast<uint32_t>(m * 128);
+              uint32_t acc_m = accum;
+              for (int k = 0; k < nk; ++k) {
+                if (bf16_in) tc_mma_bf16(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, acc_m);
+                else tc_mma_tf32(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, acc_m);
+                acc_m = 1u;
+              }
+            }
+            if (close) {   // one pipeline drain per batch of k-blocks
+              int s2 = batch_first;
+              for (int j = 0; j < in_batch; ++j) {
+                tc_commit(a_empty(s2));
+                if (++s2 == a_slots) s2 = 0;
+              }
+            }
+          }
+          accum = 1u;
+          if (++sa == a_slots) { sa = 0; pa ^= 1u; }
+          if (close) { in_batch = 0; batch_first = sa; }
+          if (++tap == taps) { tap = 0; ++cb; }
+        }
       }
+      if (elect_one_sync()) tc_commit(tfull_bar(acc));
     }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps)
-    // TMEM -> registers (thread = output pixel) -> per-warp shared-memory transpose -> coalesced
-    // global stores (8 lanes cover 128 contiguous bytes of one pixel, 4 pixels per instruction).
     const int q = warp & 3;  // TMEM lane quadrant this warp is allowed to read
     const int row = q * 32 + lane;
-    const int ly = row / p.TW, lx = row - ly * p.TW;
+    const int ly0 = row / p.TW, lx = row - ly0 * p.TW;
+    const int obf = p.out_bf16;
     const bool vec_ok = ((p.Cout & 3) == 0) && ((p.ldo & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.out) & (p.out_bf16 ? 7 : 15)) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.out) & (obf ? 7 : 15)) == 0) &&
                         (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
                         (p.residual == nullptr ||
-                         (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & (p.out_bf16 ? 7 : 15)) == 0)));
+                         (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & (obf ? 7 : 15)) == 0)));
     float* stg = reinterpret_cast<float*>(smem_raw + (smem_stg - smem_u32(smem_raw))) + q * (32 * kStgStride);
-    const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+    const int sub_r = lane >> 3;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -239,88 +408,52 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       const int tx = mt % tiles_x;
       const int ty = (mt / tiles_x) % p.tiles_y;
       const int img = mt / (tiles_x * p.tiles_y);
-      const int y = ty * p.TH + ly, x = tx * p.TW + lx;
-      const bool row_ok = (row < p.TW * p.TH) && (y < p.Ho) && (x < w_lim);
-      const long long pix = static_cast<long long>(y) * p.Wo + x;   // pixel inside the image
       const int n0 = nt * p.BN;
-      // rows this lane stores in the coalesced phase: staged row k*4+sub_r of this warp's 32 pixels
-      long long off_o[8], off_r[8];
-      uint32_t okmask = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int rr = k * 4 + sub_r;
-        const long long pr = __shfl_sync(0xffffffffu, pix, rr);
-        okmask |= (__shfl_sync(0xffffffffu, row_ok ? 1 : 0, rr) != 0 ? 1u : 0u) << k;
-        off_o[k] = img * p.out_img_stride + pr * p.ldo;
-        off_r[k] = img * p.res_img_stride + pr * p.ldr;
-      }
-
-      mbar_wait(tfull_bar(acc), acc_phase, 4);
-      tc_fence_after();
-      if (it == 0 && threadIdx.x == 64) MFR_STAMP(6);
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxBN) +
-                             (static_cast<uint32_t>(q * 32) << 16);
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        uint32_t r[32];
-        if (it == 0 && c0 == 0 && threadIdx.x == 64) MFR_STAMP(9);
-        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
-        tmem_ld_wait();
-        if (it == 0 && c0 == 0 && threadIdx.x == 64) MFR_STAMP(10);
+      for (int m = 0; m < p.MT; ++m) {
+        const int y = ty * tile_rows + m * p.TH + ly0, x = tx * p.TW + lx;
+        const bool row_ok = (row < p.TW * p.TH) && (y < p.Ho) && (x < w_lim);
+        const long long pix = static_cast<long long>(y) * p.Wo + x;   // pixel inside the image
+        const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxBN + m * 128) +
+                               (static_cast<uint32_t>(q * 32) << 16);
+        const bool do_wait = m == 0;
         if (vec_ok) {
-          // stage: this thread's pixel, 32 consecutive channels
+          // rows this lane stores in the coalesced phase: staged row k*4+sub_r of this warp's 32 pixels
+          long long off_o[8], off_r[8];
+          uint32_t okmask = 0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * kStgStride + j * 4) =
-                make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-          __syncwarp();
-          if (it == 0 && c0 == 0 && threadIdx.x == 64) MFR_STAMP(11);
-          const int n = n0 + c0 + sub_c;
-          const uint32_t okm = n < p.Cout ? okmask : 0u;
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr && okm) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-          const int act = n < p.act_cols ? p.act : ACT_NONE;   // n..n+3 never straddle act_cols (multiple of 4)
-          const float* stg_rd = stg + sub_r * kStgStride + sub_c;
-          // base pointers advanced by n elements of the output type
-          float* out_n = p.out_bf16 ? reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(p.out) + n) : p.out + n;
-          const float* res_n = p.out_bf16 ? reinterpret_cast<const float*>(reinterpret_cast<const uint16_t*>(p.residual) + n)
-                                          : p.residual + n;
-#define MFR_STORE(ACTV, RESV)                                                                                   \
-  do {                                                                                                          \
-    if (p.out_bf16) store_chunk<ACTV, RESV, true>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n);        \
-    else store_chunk<ACTV, RESV, false>(stg_rd, off_o, off_r, okm, p.alpha, b4, res_n, out_n);                  \
+          for (int k = 0; k < 8; ++k) {
+            const int rr = k * 4 + sub_r;
+            const long long pr = __shfl_sync(0xffffffffu, pix, rr);
+            okmask |= (__shfl_sync(0xffffffffu, row_ok ? 1 : 0, rr) != 0 ? 1u : 0u) << k;
+            off_o[k] = img * p.out_img_stride + pr * p.ldo;
+            off_r[k] = img * p.res_img_stride + pr * p.ldr;
+          }
+#define MFR_EPI(ACTV)                                                                                               \
+  do {                                                                                                              \
+    if (p.residual != nullptr) {                                                                                    \
+      if (obf) epilogue_subtile<ACTV, true, true>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait);   \
+      else epilogue_subtile<ACTV, true, false>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait);      \
+    } else {                                                                                                        \
+      if (obf) epilogue_subtile<ACTV, false, true>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait);  \
+      else epilogue_subtile<ACTV, false, false>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait);     \
+    }                                                                                                               \
   } while (0)
-          if (p.residual != nullptr) {
-            switch (act) {
-              case ACT_RELU: MFR_STORE(ACT_RELU, true); break;
-              case ACT_LEAKY: MFR_STORE(ACT_LEAKY, true); break;
-              case ACT_ELU1: MFR_STORE(ACT_ELU1, true); break;
-              default: MFR_STORE(ACT_NONE, true); break;
-            }
-          } else {
-            switch (act) {
-              case ACT_RELU: MFR_STORE(ACT_RELU, false); break;
-              case ACT_LEAKY: MFR_STORE(ACT_LEAKY, false); break;
-              case ACT_ELU1: MFR_STORE(ACT_ELU1, false); break;
-              default: MFR_STORE(ACT_NONE, false); break;
-            }
+          switch (p.act) {
+            case ACT_RELU: MFR_EPI(ACT_RELU); break;
+            case ACT_LEAKY: MFR_EPI(ACT_LEAKY); break;
+            case ACT_ELU1: MFR_EPI(ACT_ELU1); break;
+            default: MFR_EPI(ACT_NONE); break;
           }
-#undef MFR_STORE
-          __syncwarp();
-          if (it == 0 && c0 == 0 && threadIdx.x == 64) MFR_STAMP(12);
-        } else if (row_ok) {
-          float* orow = p.out + img * p.out_img_stride + pix * p.ldo;
-          const float* rrow = p.residual ? p.residual + img * p.res_img_stride + pix * p.ldr : nullptr;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            if (n < p.Cout) {
-              float v = __uint_as_float(r[j]) * p.alpha;
-              if (p.bias) v += __ldg(p.bias + n);
-              if (rrow) v += __ldg(rrow + n);
-              orow[n] = n < p.act_cols ? apply_act(v, p.act) : v;
-            }
+#undef MFR_EPI
+        } else {
+          if (do_wait) {
+            mbar_wait(tfull_bar(acc), acc_phase, 4);
+            tc_fence_after();
           }
+          epilogue_subtile_scalar(p, taddr, n0, row_ok, img * p.out_img_stride + pix * p.ldo,
+                                  img * p.res_img_stride + pix * p.ldr);
         }
+        if (it == 0 && m == 0 && threadIdx.x == 64) MFR_STAMP(6);
       }
       tc_fence_before();
       __syncwarp();
@@ -361,26 +494,96 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// Pick the output tile (TW x TH <= 128 pixels) that wastes the fewest MMA rows.
-void choose_tile(int Wo, int Ho, int stride, int* TW, int* TH) {
-  double best = -1.0;
-  int bw = 1, bh = 1;
-  for (int tw = 1; tw <= 128; ++tw) {
-    if (tw * stride > 256) break;
-    int th = 128 / tw;
-    if (th > Ho) th = Ho;
-    if (th * stride > 256) th = 256 / stride;
-    if (th < 1) continue;
-    const long long tiles = static_cast<long long>((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
-    const double eff = static_cast<double>(Wo) * Ho / (static_cast<double>(tiles) * 128.0);
-    if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > bw)) {
-      best = std::max(best, eff);
-      bw = tw;
-      bh = th;
+// Tiling of one op: output tile = MT sub-tiles of TW x TH (<= 128) pixels, BN output channels.
+struct TileCfg {
+  int TW, TH, MT, BN, n_tiles, halo;
+  double cost;
+};
+
+// Cost model used to pick the tiling (ns per CTA tile; constants measured with mfr_debug_mma_probe on B200):
+//   MMA      : one 128 x BN x (32 B of K) tcgen05.mma takes 30.5 + 0.2415 * BN ns when issued back to back;
+//              every tcgen05.commit that releases operand slots drains the pipe, ~215 ns
+//   feed     : operand bytes through L2 -> shared memory at ~100 GB/s per SM when all SMs pull at once
+//   epilogue : ~500 ns per 32-channel chunk of a 128-pixel sub-tile (4 epilogue warps)
+// times the number of waves of tiles over the SMs.
+struct RingCfg { int a_slots, b_slots, cbatch, a_slot_bytes; };
+RingCfg ring_cfg(int halo, int MT, int TW, int TH, int BN) {
+  RingCfg r{};
+  const int b_bytes = BN * 128;
+  if (halo) {
+    r.a_slot_bytes = TW * (MT * TH + 2) * 128;   // multiple of 1 KB (TW % 8 == 0)
+    r.a_slots = 3;
+    r.b_slots = std::min(kMaxSlots, (kRingBytes - r.a_slots * r.a_slot_bytes) / b_bytes);
+    if (r.b_slots < 6) {
+      r.a_slots = 2;
+      r.b_slots = std::min(kMaxSlots, (kRingBytes - r.a_slots * r.a_slot_bytes) / b_bytes);
+    }
+    r.cbatch = 3;
+  } else {
+    // generic mode pads the A slot to whole 128-row sub-tiles (the MMA reads 128 rows regardless)
+    r.a_slot_bytes = std::max((TW * TH * MT * 128 + 1023) / 1024 * 1024, MT * kAStage);
+    r.a_slots = r.b_slots = std::min(kMaxSlots, kRingBytes / (r.a_slot_bytes + b_bytes));
+    r.cbatch = std::max(1, std::min(4, r.a_slots / 2));
+    if (const char* e = getenv("MFR_CONV_CBATCH")) r.cbatch = std::max(1, std::min(r.a_slots - 1, atoi(e)));
+  }
+  return r;
+}
+
+TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, int pad, int kb_per_tap,
+                   int ksteps_last, bool allow_mt2) {
+  const int sms = conv_gemm_num_sms();
+  const int c16 = (Cout + 15) / 16 * 16;
+  const int taps = R * S;
+  const int ksteps_tap = (kb_per_tap - 1) * 4 + ksteps_last;
+  const bool can_halo = R == 3 && S == 3 && stride == 1 && pad == 1;
+  TileCfg best{};
+  best.cost = 1e300;
+  // test hook: MFR_CONV_FORCE="halo,MT,TW" restricts the search (-1 = free); unusable values fall back to free
+  int f_halo = -1, f_mt = -1, f_tw = -1;
+  if (const char* e = getenv("MFR_CONV_FORCE")) sscanf(e, "%d,%d,%d", &f_halo, &f_mt, &f_tw);
+  for (int pass = 0; pass < 2 && best.cost > 1e299; ++pass) {
+  if (pass == 1) f_halo = f_mt = f_tw = -1;
+  const int nt0 = (c16 + kMaxBN - 1) / kMaxBN;
+  for (int nt = nt0; nt <= nt0 * 4; nt *= 2) {
+    const int BN = ((c16 / 16 + nt - 1) / nt) * 16;
+    if (nt > nt0 && BN < 64) break;
+    for (int halo = 0; halo <= (can_halo ? 1 : 0); ++halo) {
+      for (int MT = 1; MT <= 2; ++MT) {
+        if (MT == 2 && (BN > 128 || Ho == 1 || !allow_mt2)) continue;
+        if ((f_halo >= 0 && halo != f_halo) || (f_mt > 0 && MT != f_mt)) continue;
+        for (int tw = 1; tw <= 128; ++tw) {
+          if (f_tw > 0 && tw != f_tw) continue;
+          if (halo && (tw % 8 != 0 || 128 % tw != 0)) continue;
+          if (tw * stride > 256) break;
+          int th = 128 / tw;
+          if (!halo && th > Ho) th = Ho;
+          if (MT == 2 && (tw * th) % 8 != 0) continue;
+          const int box_rows = halo ? MT * th + 2 : MT * th * stride;
+          if (box_rows > 256) continue;
+          const long long tiles = static_cast<long long>(N) * ((Wo + tw - 1) / tw) * ((Ho + MT * th - 1) / (MT * th)) * nt;
+          const RingCfg rc = ring_cfg(halo, MT, tw, th, BN);
+          if (rc.a_slots < 2 || rc.b_slots < (halo ? 4 : 2)) continue;
+          const double commits = halo ? 3.0 * kb_per_tap : std::ceil(static_cast<double>(taps) * kb_per_tap / rc.cbatch);
+          const double mma = static_cast<double>(MT) * taps * ksteps_tap * (30.5 + 0.2415 * BN) + commits * 215.0;
+          const double a_bytes = halo ? static_cast<double>(tw) * (MT * th + 2) * 128.0 * 3 * kb_per_tap
+                                      : static_cast<double>(tw) * th * MT * 128.0 * taps * kb_per_tap;
+          const double b_bytes = static_cast<double>(BN) * 128.0 * taps * kb_per_tap;
+          const double l2 = (a_bytes + b_bytes) / 100.0;
+          const double epi = MT * ((BN + 31) / 32) * 500.0;
+          const double t = std::max(mma, std::max(l2, epi)) + 800.0;
+          const double cost = static_cast<double>((tiles + sms - 1) / sms) * t;
+          if (cost < best.cost * (1.0 - 1e-9) || (cost < best.cost * (1.0 + 1e-9) && tw > best.TW)) {
+            best = TileCfg{tw, th, MT, BN, nt, halo, cost};
+          }
+        }
+      }
     }
   }
-  *TW = bw;
-  *TH = bh;
+  }
+  if (getenv("MFR_CONV_DEBUG"))
+    fprintf(stderr, "[conv_gemm cfg] N%d %dx%d Cout%d R%d s%d kb%d -> TW%d TH%d MT%d BN%d nt%d halo%d cost %.0f\n", N, Ho, Wo,
+            Cout, R, stride, kb_per_tap, best.TW, best.TH, best.MT, best.BN, best.n_tiles, best.halo, best.cost);
+  return best;
 }
 
 }  // namespace
@@ -418,27 +621,30 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
   p->Cout = d.Cout;
   p->Cin = d.Cin;
   p->R = d.R; p->S = d.S; p->stride = d.stride; p->pad = d.pad;
-  choose_tile(p->Wo, p->Ho, d.stride, &p->TW, &p->TH);
-  p->tiles_x = (p->Wo + p->TW - 1) / p->TW;
-  p->tiles_y = (p->Ho + p->TH - 1) / p->TH;
-  // N tile: whole Cout when it fits one UMMA (<= 256), else equal 16-aligned slices; problems with
-  // fewer tiles than SMs are cut into narrower N tiles (down to 64) so that more SMs take part.
-  const int c16 = (d.Cout + 15) / 16 * 16;
-  const int m_tiles = p->N * p->tiles_x * p->tiles_y;
-  int max_bn = kMaxBN;
-  while (max_bn > 64 && static_cast<long long>(m_tiles) * ((c16 + max_bn - 1) / max_bn) < conv_gemm_num_sms() &&
-         c16 > max_bn / 2)
-    max_bn /= 2;
-  p->n_tiles = (c16 + max_bn - 1) / max_bn;
-  p->BN = ((c16 / 16 + p->n_tiles - 1) / p->n_tiles) * 16;
   p->kb_per_tap = (d.Cin + kblk - 1) / kblk;
   p->kblk = kblk;
+  {  // MMAs in the last k-block of a tap: the channel tail is zero-filled by TMA, no need to multiply all of it
+    const int tail = d.Cin - (p->kb_per_tap - 1) * kblk;
+    const int ummak = kblk / 4;
+    p->ksteps_last = (tail + ummak - 1) / ummak;
+  }
+  const TileCfg cfg = choose_cfg(d.N, p->Ho, p->Wo, d.Cout, d.R, d.S, d.stride, d.pad, p->kb_per_tap, p->ksteps_last,
+                                 d.dyn_w == nullptr);
+  p->TW = cfg.TW; p->TH = cfg.TH; p->MT = cfg.MT; p->halo = cfg.halo;
+  p->BN = cfg.BN; p->n_tiles = cfg.n_tiles;
+  p->tiles_x = (p->Wo + p->TW - 1) / p->TW;
+  p->tiles_y = (p->Ho + p->MT * p->TH - 1) / (p->MT * p->TH);
   p->in_bf16 = d.in_bf16;
   p->out_bf16 = d.out_bf16;
   p->b_batched = d.b_batched;
-  p->a_bytes = p->TW * p->TH * 128;
-  p->b_bytes = p->BN * 128;
-  p->num_stages = std::min(kMaxStages, kRingBytes / (kAStage + p->b_bytes));  // BN*128 B is 2 KB aligned
+  const int a_rows = p->halo ? p->MT * p->TH + 2 : p->MT * p->TH;   // pixel rows of the A box
+  p->a_bytes = p->TW * a_rows * 128;
+  p->b_bytes = p->BN * 128;                                        // multiple of 2 KB (BN % 16 == 0)
+  {
+    const RingCfg rc = ring_cfg(p->halo, p->MT, p->TW, p->TH, p->BN);
+    p->a_slot_bytes = rc.a_slot_bytes; p->a_slots = rc.a_slots; p->b_slots = rc.b_slots; p->cbatch = rc.cbatch;
+  }
+  if (p->a_slots < 2 || p->b_slots < 2) return MFR_ERR_ARG;
   p->act = d.act;
   p->act_cols = d.act_cols > 0 ? d.act_cols : d.Cout;
   p->dyn_w = d.dyn_w;
@@ -458,7 +664,7 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
     cuuint64_t strides[3] = {(cuuint64_t)d.ldx * es, (cuuint64_t)d.ldx * es * d.W,
                              d.x_img_stride > 0 ? (cuuint64_t)d.x_img_stride * es : (cuuint64_t)d.ldx * es * d.W * d.H};
     cuuint32_t box[4] = {(cuuint32_t)kblk, (cuuint32_t)(p->TW * d.stride),
-                         (cuuint32_t)(p->TH * d.stride), 1};
+                         (cuuint32_t)(p->halo ? p->MT * p->TH + 2 : p->MT * p->TH * d.stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
     CUresult r = enc(&p->tmA, d.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                      const_cast<float*>(d.x), dims,
@@ -518,12 +724,12 @@ int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream) {
 namespace {
 __global__ void __launch_bounds__(kThreads, 1) overhead_probe_kernel(int mode, int* sink) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bars[2 * kMaxStages + 4];
+  __shared__ __align__(8) uint64_t s_bars[4 * kMaxSlots + 4];
   __shared__ uint32_t s_tmem_base;
   if (mode == 0) return;
   const int warp = threadIdx.x >> 5;
   if (mode >= 2 && threadIdx.x == 0) {
-    for (int s = 0; s < 2 * kMaxStages + 4; ++s) mbar_init(smem_u32(s_bars) + 8u * s, 1);
+    for (int s = 0; s < 4 * kMaxSlots + 4; ++s) mbar_init(smem_u32(s_bars) + 8u * s, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -538,6 +744,81 @@ __global__ void __launch_bounds__(kThreads, 1) overhead_probe_kernel(int mode, i
   if (warp == 1) tmem_dealloc(s_tmem_base, kTmemCols);
 }
 }  // namespace
+
+namespace {
+// Tensor-pipe probe: operands static in shared memory (no TMA), one thread issues `n_per_commit`
+// 128 x BN x (32 B of K) MMAs followed by one tcgen05.commit, `iters` times; optionally waits for
+// every commit before issuing the next group (the dependency a 1-slot ring would impose).
+__global__ void __launch_bounds__(kThreads, 1) mma_probe_kernel(int n_per_commit, int BN, int bf16, int wait_each,
+                                                                 int iters, int two_commits) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar[3];
+  __shared__ uint32_t s_tmem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&s_bar[0]), 1);
+    mbar_init(smem_u32(&s_bar[1]), 1);
+    mbar_init(smem_u32(&s_bar[2]), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&s_tmem_base), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  if (warp == 1 && lane == 0) {
+    const uint32_t idesc = umma_idesc(bf16 ? 1u : 2u, kTileM, static_cast<uint32_t>(BN));
+    const uint32_t a_addr = smem_base, b_addr = smem_base + 64 * 1024;
+    uint32_t phase = 0;
+    for (int it = 0; it < iters; ++it) {
+      for (int k = 0; k < n_per_commit; ++k) {
+        const uint32_t off = static_cast<uint32_t>((k & 3) * 32 + (k >> 2) * 16384) & 0xffffu;
+        const uint64_t adesc = umma_desc_sw128_kmajor(a_addr + off);
+        const uint64_t bdesc = umma_desc_sw128_kmajor(b_addr + ((k & 3) * 32));
+        if (bf16) tc_mma_bf16(tmem_base, adesc, bdesc, idesc, 1u);
+        else tc_mma_tf32(tmem_base, adesc, bdesc, idesc, 1u);
+      }
+      tc_commit(smem_u32(&s_bar[0]));
+      if (two_commits) tc_commit(smem_u32(&s_bar[2]));
+      if (wait_each) {
+        mbar_wait(smem_u32(&s_bar[0]), phase, 7);
+        phase ^= 1u;
+      }
+    }
+    tc_commit(smem_u32(&s_bar[1]));
+    mbar_wait(smem_u32(&s_bar[1]), 0u, 8);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+}  // namespace
+
+// ns per MMA instruction of the probe above (CUDA events around one launch of `grid` CTAs).
+float conv_gemm_mma_probe(int n_per_commit, int BN, int bf16, int wait_each, int iters, int grid, int two_commits) {
+  cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  mma_probe_kernel<<<grid, kThreads, kSmemBytes>>>(n_per_commit, BN, bf16, wait_each, 10, two_commits);
+  cudaEventRecord(e0);
+  mma_probe_kernel<<<grid, kThreads, kSmemBytes>>>(n_per_commit, BN, bf16, wait_each, iters, two_commits);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (cudaGetLastError() != cudaSuccess) return -1.f;
+  return ms * 1e6f / (static_cast<float>(iters) * n_per_commit);
+}
 
 float conv_gemm_probe_overhead(int mode, int smem_bytes, int grid, int iters, cudaStream_t st) {
   cudaFuncSetAttribute(overhead_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -559,14 +840,16 @@ float conv_gemm_probe_overhead(int mode, int smem_bytes, int grid, int iters, cu
 float conv_gemm_time_prebuilt(const ConvGemmParams& p, int iters, cudaStream_t st) {
   {  // one instrumented launch: milestone stamps of block 0
     long long* d = nullptr;
-    cudaMalloc(&d, 16 * sizeof(long long));
-    cudaMemset(d, 0, 16 * sizeof(long long));
+    cudaMalloc(&d, 32 * sizeof(long long));
+    cudaMemset(d, 0, 32 * sizeof(long long));
     ConvGemmParams q = p;
     q.dbg = d;
     conv_gemm_launch(q, st);
+    cudaStreamSynchronize(st);
+    cudaMemset(d, 0, 32 * sizeof(long long));
     conv_gemm_launch(q, st);
     cudaStreamSynchronize(st);
-    long long h[16];
+    long long h[32];
     cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(d);
     const char* names[13] = {"start", "setup done", "first TMA issued", "last TMA issued", "first stage landed",
@@ -574,7 +857,8 @@ float conv_gemm_time_prebuilt(const ConvGemmParams& p, int iters, cudaStream_t s
                              "c0 tmem loaded", "c0 staged", "c0 stored"};
     fprintf(stderr, "[conv_gemm stamps, block 0, ns since start]");
     for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] ? h[i] - h[0] : -1);
-    fprintf(stderr, "\n");
+    fprintf(stderr, "\n[conv_gemm cfg] TW%d TH%d MT%d BN%d nt%d halo%d slots %d/%d cbatch %d\n", p.TW, p.TH, p.MT, p.BN,
+            p.n_tiles, p.halo, p.a_slots, p.b_slots, p.cbatch);
   }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);

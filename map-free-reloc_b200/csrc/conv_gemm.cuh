@@ -14,14 +14,20 @@ namespace mfr {
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_ELU1 = 3 };
 
 struct alignas(64) ConvGemmParams {
-  CUtensorMap tmA;  // rank 4 {C, W, H, N}   box {32, TW*s, TH*s, 1}, 128B swizzle, zero OOB fill
+  CUtensorMap tmA;  // rank 4 {C, W, H, N}   box {32|64, TW*s, MT*TH*s (halo: MT*TH+2), 1}, 128B swizzle, zero OOB fill
   CUtensorMap tmB;  // rank 3 {Cin, Z, Cout} box {32, 1, BN}          (Z = filter tap or image)
   int N, Ho, Wo, Cout, Cin;
   int R, S, stride, pad;
   int TW, TH, tiles_x, tiles_y;
   int BN, n_tiles, kb_per_tap, b_batched;
-  int a_bytes, b_bytes;   // TMA transaction bytes per stage
-  int num_stages;         // operand ring depth = 192 KB / (16 KB + BN * 128 B), at most 8
+  int a_bytes, b_bytes;   // TMA transaction bytes of one A / B load
+  int MT;                 // 128-pixel sub-tiles per CTA tile (2 only when BN <= 128: 2 x 2 x 128 TMEM columns)
+  int halo;               // 3x3 stride-1 conv: A is loaded as a (MT*TH+2)-row box per (k-block, kx) and the three
+                          // ky taps read it at row offsets 0, TW, 2*TW (TW % 8 == 0 keeps the swizzle phase)
+  int a_slots, b_slots;   // depth of the A ring / B ring (two rings: one A slot serves 3 B tiles in halo mode)
+  int a_slot_bytes;
+  int cbatch;             // generic mode: k-blocks whose slots are released by one tcgen05.commit batch (pipe drain)
+  int ksteps_last;        // MMAs issued for the last k-block of a tap (channel tail)
   int act, act_cols;    // activation applies to output channels < act_cols
   int in_bf16, out_bf16;  // operands bf16 (kind::f16) instead of fp32 (kind::tf32); out/residual bf16
   int kblk;             // K elements per 128-byte k-block: 32 (fp32) or 64 (bf16)
@@ -61,6 +67,7 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p);
 int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream);
 int conv_gemm_num_sms();
 float conv_gemm_probe_overhead(int mode, int smem_bytes, int grid, int iters, cudaStream_t st);
+float conv_gemm_mma_probe(int n_per_commit, int BN, int bf16, int wait_each, int iters, int grid, int two_commits);
 float conv_gemm_time_prebuilt(const ConvGemmParams& p, int iters, cudaStream_t st);
 
 }  // namespace mfr

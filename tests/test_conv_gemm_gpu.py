@@ -78,6 +78,58 @@ def test_conv_matches_torch(mfr, N, H, W, Cin, Cout, R, stride, act, use_bias, u
     _check(out, ref)
 
 
+@pytest.mark.parametrize("force", ["0,1,-1", "1,1,8", "1,1,16", "1,2,8", "1,2,16", "1,2,32", "0,2,-1", "1,1,128"])
+@pytest.mark.parametrize("N,H,W,Cin,Cout,use_res", [
+    (2, 70, 52, 128, 128, True),      # ragged in x and y for every tile shape
+    (1, 37, 50, 196, 196, False),     # BN = 208 (MT stays 1), channel tail in K
+    (2, 33, 24, 64, 64, True),        # narrow N
+])
+def test_conv3x3_tilings_agree(mfr, monkeypatch, force, N, H, W, Cin, Cout, use_res):
+    """Every tiling of the 3x3 stride-1 path (per-tap A loads vs halo A box shared by the three ky taps,
+    one or two 128-pixel sub-tiles per CTA) against the fp64 reference."""
+    monkeypatch.setenv("MFR_CONV_FORCE", force)
+    g = torch.Generator(device="cpu").manual_seed(4321)
+    x = torch.randn(N, H, W, Cin, generator=g).cuda()
+    w = (torch.randn(Cout, 3, 3, Cin, generator=g) / (9 * Cin) ** 0.5).cuda()
+    bias = torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(N, H, W, Cout, generator=g).cuda() if use_res else None
+    out = _run(mfr, x, w, 1, 1, bias, res, 1, 1.0)
+    _check(out, _ref(x, w, 1, 1, bias, res, 1, 1.0))
+
+
+@pytest.mark.parametrize("force", ["0,1,-1", "0,2,-1"])
+def test_conv1x1_and_stride2_two_subtiles(mfr, monkeypatch, force):
+    monkeypatch.setenv("MFR_CONV_FORCE", force)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for (N, H, W, Cin, Cout, R, stride) in [(2, 64, 40, 128, 64, 1, 1), (2, 50, 48, 128, 128, 3, 2), (2, 50, 48, 96, 128, 1, 2)]:
+        x = torch.randn(N, H, W, Cin, generator=g).cuda()
+        w = (torch.randn(Cout, R, R, Cin, generator=g) / (R * R * Cin) ** 0.5).cuda()
+        out = _run(mfr, x, w, stride, R // 2, None, None, 0, 1.0)
+        _check(out, _ref(x, w, stride, R // 2, None, None, 0, 1.0))
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,R,stride,act,use_res", [
+    (2, 48, 64, 128, 128, 3, 1, 1, True), (2, 48, 64, 128, 196, 3, 2, 1, False), (2, 48, 64, 128, 196, 1, 2, 0, False),
+    (2, 24, 32, 196, 196, 3, 1, 1, True), (2, 24, 32, 196, 256, 3, 2, 1, False), (2, 24, 32, 196, 256, 1, 2, 0, False),
+    (2, 12, 16, 256, 256, 3, 1, 1, True), (2, 12, 16, 256, 256, 1, 1, 0, False), (2, 24, 32, 196, 256, 1, 1, 0, False),
+    (2, 24, 32, 256, 256, 3, 1, 2, False), (2, 24, 32, 256, 196, 3, 1, 0, False), (2, 48, 64, 128, 196, 1, 1, 0, False),
+    (2, 48, 64, 196, 196, 3, 1, 2, False), (2, 48, 64, 196, 128, 3, 1, 0, False),
+    (4, 80, 60, 128, 128, 3, 1, 1, True), (4, 80, 60, 196, 128, 3, 1, 0, False), (4, 40, 30, 256, 196, 3, 1, 0, False),
+])
+def test_backbone_shapes_small_images(mfr, N, H, W, Cin, Cout, R, stride, act, use_res):
+    """The ResNet-FPN conv shapes at the image sizes the engine tests use (few tiles, narrow N tiles)."""
+    g = torch.Generator(device="cpu").manual_seed(77)
+    x = torch.randn(N, H, W, Cin, generator=g).cuda()
+    w = (torch.randn(Cout, R, R, Cin, generator=g) / (R * R * Cin) ** 0.5).cuda()
+    pad = R // 2
+    Ho = (H + 2 * pad - R) // stride + 1
+    Wo = (W + 2 * pad - R) // stride + 1
+    bias = torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(N, Ho, Wo, Cout, generator=g).cuda() if use_res else None
+    out = _run(mfr, x, w, stride, pad, bias, res, act, 1.0)
+    _check(out, _ref(x, w, stride, pad, bias, res, act, 1.0))
+
+
 def test_batched_xyt(mfr):
     g = torch.Generator(device="cpu").manual_seed(7)
     a = torch.randn(2, 1, 300, 256, generator=g).cuda()
