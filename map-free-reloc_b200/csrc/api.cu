@@ -139,7 +139,7 @@ int mfr_coarse_match(const float* sim, int B, int h_c, int w_c, float thr, int b
                      int input_is_conf, int* count, int* offsets, int* b_ids, int* i_ids, int* j_ids,
                      float* mconf, float* mkpts0_c, float* mkpts1_c, void* stream) {
   if (!sim || B < 1 || h_c < 1 || w_c < 1) return MFR_ERR_ARG;
-  const int L = h_c * w_c, splits = 32;
+  const int L = h_c * w_c, splits = mfr::coarse_match_splits(B, L);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   mfr::CoarseMatchBuffers b;
   int rc = mfr::coarse_match_alloc(B, L, splits, &b);

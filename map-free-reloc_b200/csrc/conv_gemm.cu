@@ -32,9 +32,11 @@ constexpr int kMaxBN = 256;
 constexpr int kAStage = kTileM * kBlockK * 4;   // 16 KB
 constexpr int kRingBytes = 204 * 1024;          // operand rings (A slots + B slots)
 constexpr int kStgStride = 36;                  // floats per staged row (144 B: conflict-free 128-bit access)
-constexpr int kStgBytes = 4 * 32 * kStgStride * 4;  // epilogue transpose buffers, one per epilogue warp
+constexpr int kEpiWarps = 4;                    // 4 or 8 (two per TMEM lane quarter, alternating 32-channel chunks);
+                                                // 8 measured no faster: the store phase is bound by the memory system
+constexpr int kStgBytes = kEpiWarps * 32 * kStgStride * 4;  // epilogue transpose buffers, one per epilogue warp
 constexpr int kSmemBytes = kRingBytes + kStgBytes + 1024 /*align slack*/;
-constexpr int kThreads = 192;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kTmemCols = 512;
 
 __device__ __forceinline__ long long gtime() {
@@ -81,7 +83,7 @@ template <int ACT, bool RES, bool OBF>
 __device__ __forceinline__ void epilogue_subtile(const ConvGemmParams& p, uint32_t taddr, float* stg, int lane,
                                                  int n0, const long long (&off_o)[8], const long long (&off_r)[8],
                                                  uint32_t okmask, uint32_t wait_bar, uint32_t wait_phase,
-                                                 bool do_wait) {
+                                                 bool do_wait, int c_begin) {
   using RT = typename std::conditional<OBF, uint2, float4>::type;
   const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
   RT rnext[8];
@@ -99,13 +101,14 @@ __device__ __forceinline__ void epilogue_subtile(const ConvGemmParams& p, uint32
       }
     }
   };
-  if constexpr (RES) issue_res(0);
+  constexpr int kStep = 32 * (kEpiWarps / 4);   // this warp's chunks: c_begin, c_begin + kStep, ...
+  if constexpr (RES) issue_res(c_begin);
   if (do_wait) {
     mbar_wait(wait_bar, wait_phase, 4);
     tc_fence_after();
   }
   const float alpha = p.alpha;
-  for (int c0 = 0; c0 < p.BN; c0 += 32) {
+  for (int c0 = c_begin; c0 < p.BN; c0 += kStep) {
     uint32_t r[32];
     tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
     tmem_ld_wait();
@@ -118,7 +121,7 @@ __device__ __forceinline__ void epilogue_subtile(const ConvGemmParams& p, uint32
     if constexpr (RES) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) rcur[k] = rnext[k];
-      if (c0 + 32 < p.BN) issue_res(c0 + 32);
+      if (c0 + kStep < p.BN) issue_res(c0 + kStep);
     }
     const int n = n0 + c0 + sub_c;
     const uint32_t okm = (n < p.Cout && c0 + sub_c < p.BN) ? okmask : 0u;   // BN need not be a multiple of 32
@@ -157,8 +160,8 @@ __device__ __forceinline__ void epilogue_subtile(const ConvGemmParams& p, uint32
 
 // Scalar epilogue for shapes the vector path cannot take (Cout or strides not multiples of 4); fp32 only.
 __device__ __forceinline__ void epilogue_subtile_scalar(const ConvGemmParams& p, uint32_t taddr, int n0, bool row_ok,
-                                                        long long o_off, long long r_off) {
-  for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                                                        long long o_off, long long r_off, int c_begin) {
+  for (int c0 = c_begin; c0 < p.BN; c0 += 32 * (kEpiWarps / 4)) {
     uint32_t r[32];
     tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
     tmem_ld_wait();
@@ -213,7 +216,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int s = 0; s < 4 * kMaxSlots; ++s) mbar_init(bar_base + 8u * s, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -388,8 +391,9 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       if (elect_one_sync()) tc_commit(tfull_bar(acc));
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps)
+    // ------------------------------------------------------------------ epilogue (kEpiWarps warps)
     const int q = warp & 3;  // TMEM lane quadrant this warp is allowed to read
+    const int c_begin = kEpiWarps == 4 ? 0 : ((warp - 2) >> 2) * 32;   // 8 warps: the two warps of a quadrant alternate chunks
     const int row = q * 32 + lane;
     const int ly0 = row / p.TW, lx = row - ly0 * p.TW;
     const int obf = p.out_bf16;
@@ -398,7 +402,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
                         (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
                         (p.residual == nullptr ||
                          (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & (obf ? 7 : 15)) == 0)));
-    float* stg = reinterpret_cast<float*>(smem_raw + (smem_stg - smem_u32(smem_raw))) + q * (32 * kStgStride);
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem_stg - smem_u32(smem_raw))) + (warp - 2) * (32 * kStgStride);
     const int sub_r = lane >> 3;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -431,11 +435,11 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
 #define MFR_EPI(ACTV)                                                                                               \
   do {                                                                                                              \
     if (p.residual != nullptr) {                                                                                    \
-      if (obf) epilogue_subtile<ACTV, true, true>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait);   \
-      else epilogue_subtile<ACTV, true, false>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait);      \
+      if (obf) epilogue_subtile<ACTV, true, true>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait, c_begin);   \
+      else epilogue_subtile<ACTV, true, false>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait, c_begin);      \
     } else {                                                                                                        \
-      if (obf) epilogue_subtile<ACTV, false, true>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait);  \
-      else epilogue_subtile<ACTV, false, false>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait);     \
+      if (obf) epilogue_subtile<ACTV, false, true>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait, c_begin);  \
+      else epilogue_subtile<ACTV, false, false>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait, c_begin);     \
     }                                                                                                               \
   } while (0)
           switch (p.act) {
@@ -451,7 +455,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
             tc_fence_after();
           }
           epilogue_subtile_scalar(p, taddr, n0, row_ok, img * p.out_img_stride + pix * p.ldo,
-                                  img * p.res_img_stride + pix * p.ldr);
+                                  img * p.res_img_stride + pix * p.ldr, c_begin);
         }
         if (it == 0 && m == 0 && threadIdx.x == 64) MFR_STAMP(6);
       }

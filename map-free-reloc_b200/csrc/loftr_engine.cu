@@ -41,7 +41,7 @@ struct LoftrEngine {
   int H2, W2, H4, W4, H8, W8, L, Mcap;
   float thr, temperature;
   int border;
-  int splits_kv = 96, splits_col = 32;
+  int splits_kv = 96, splits_col = 32;   // splits_kv is set from the image count in build()
   int precision = 0;   // 0: fp32 storage / TF32 MMA everywhere; 1: bf16 storage + bf16 MMA in the ResNet-FPN backbone
   struct Bf16Conv { std::string name; int cout, taps, cin, cin_pad; size_t off; };
   std::vector<Bf16Conv> bf16_convs;
@@ -200,7 +200,7 @@ struct LoftrEngine {
     }
     if (!windows) {
       float* kvp_ = kvp; float* kv_ = kv;
-      const int Lr = rows, sk = splits_kv;
+      const int Lr = rows, sk = splits_kv * NI / n;   // same partial-buffer footprint for n = B or n = 2B images
       push("attn_long", [=](cudaStream_t st) {
         return linear_attention_long(qkv_x, ld3, qkv_s + C, ld3, qkv_s + 2 * C, ld3, msg_x, C, kvp_, kv_, n,
                                      Lr, Lr, 8, 32, sk, st);
@@ -284,12 +284,14 @@ struct LoftrEngine {
     tok = alloc<float>(px8 * 512, "tok");
     qkv = alloc<float>(px8 * 768, "qkv"); msg = alloc<float>(px8 * 256, "msg"); mrg = alloc<float>(px8 * 256, "mrg");
     h1 = alloc<float>(px8 * 512, "h1"); h2 = alloc<float>(px8 * 256, "h2");
+    splits_kv = std::max(1, std::min(L / 16, (2 * 148 + NI - 1) / NI));   // ~2 blocks per SM when all images run
     kvp = alloc<float>(static_cast<size_t>(NI) * 8 * splits_kv * 1056, "kvp");
     kv = alloc<float>(static_cast<size_t>(NI) * 8 * 1056, "kv");
     S = alloc<float>(static_cast<size_t>(B) * L * L, "sim");
     const size_t BL = static_cast<size_t>(B) * L;
     cm.row_max = alloc<float>(BL); cm.row_rsum = alloc<float>(BL);
     cm.col_max = alloc<float>(BL); cm.col_rsum = alloc<float>(BL);
+    splits_col = coarse_match_splits(B, L);
     cm.col_part = alloc<float>(BL * splits_col * 2);
     cm.rconf_max = alloc<float>(BL); cm.rconf_arg = alloc<int>(BL); cm.rconf_ties = alloc<int>(BL);
     cm.cconf_max = alloc<float>(BL); cm.jsel = alloc<int>(BL);

@@ -161,40 +161,75 @@ __global__ void posenc_kernel(const float* __restrict__ feat, const float* __res
 //   kv_reduce  : sums the slabs.
 //   attn_apply : each lane keeps KV[h][:, v] and Ksum[h][lane] in registers; q rows are broadcast
 //                from shared memory; one warp-shuffle reduction per token for the normaliser.
-constexpr int kKvTok = 32;  // tokens staged per iteration
+// Both streaming kernels move their token rows with a 3-stage cp.async pipeline (16 tokens x 1 KB per
+// operand per stage), so the HBM latency is paid once per block, not once per slab.
+constexpr int kSlab = 16;     // tokens per pipeline stage
+constexpr int kAttStages = 3;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 16 : 0;   // src-size 0 => the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// rows [r0, r0+kSlab) of a [rows][256] fp32 matrix (row stride ld) -> dst[kSlab][256]; rows >= r_end zero-filled
+__device__ __forceinline__ void slab_load(float* dst, const float* __restrict__ src, long long ld, long long r0,
+                                          long long r_end, int t) {
+#pragma unroll
+  for (int i = 0; i < kSlab * 64 / 256; ++i) {
+    const int c = t + 256 * i;
+    const int r = c >> 6, col = (c & 63) * 4;
+    const bool ok = r0 + r < r_end;
+    cp_async16(dst + r * 256 + col, src + (ok ? (r0 + r) : r0) * ld + col, ok);
+  }
+}
+
 __global__ void __launch_bounds__(256) kv_partial_kernel(const float* __restrict__ K, long long ldk,
                                                          const float* __restrict__ V, long long ldv,
                                                          float* __restrict__ kv_part, int S, int splits) {
-  __shared__ __align__(16) float sK[kKvTok][256];
+  extern __shared__ __align__(16) float att_smem[];
+  float* sK = att_smem;                                   // [stages][kSlab][256]
+  float* sV = att_smem + kAttStages * kSlab * 256;        // [stages][kSlab][256]
   const int split = blockIdx.x, n = blockIdx.y;
   const int chunk = (S + splits - 1) / splits;
   const int s_beg = split * chunk, s_end = min(S, s_beg + chunk);
   const int t = threadIdx.x, h = t >> 5, lane = t & 31;
+  const long long base = static_cast<long long>(n) * S;
+  const int nslab = s_end > s_beg ? (s_end - s_beg + kSlab - 1) / kSlab : 0;
   float acc[32];
 #pragma unroll
   for (int d = 0; d < 32; ++d) acc[d] = 0.f;
   float ks = 0.f;
   const float fS = static_cast<float>(S);
-  for (int s0 = s_beg; s0 < s_end; s0 += kKvTok) {
-    const int cnt = min(kKvTok, s_end - s0);
-    __syncthreads();
-    float vreg[kKvTok];
 #pragma unroll
-    for (int r = 0; r < kKvTok; ++r) {   // all loads of the slab are issued before any is consumed
-      float kk = 0.f, vv = 0.f;
-      if (r < cnt) {
-        const size_t row = static_cast<size_t>(n) * S + s0 + r;
-        kk = K[row * ldk + t];
-        vv = V[row * ldv + t];
-      }
-      sK[r][t] = kk;
-      vreg[r] = __fdiv_rn(vv, fS);
+  for (int st = 0; st < kAttStages - 1; ++st) {
+    if (st < nslab) {
+      slab_load(sK + st * kSlab * 256, K, ldk, base + s_beg + st * kSlab, base + s_end, t);
+      slab_load(sV + st * kSlab * 256, V, ldv, base + s_beg + st * kSlab, base + s_end, t);
     }
-    __syncthreads();
+    cp_async_commit();
+  }
+  for (int i = 0; i < nslab; ++i) {
+    cp_async_wait<kAttStages - 2>();
+    __syncthreads();   // slab i has landed for everyone; everyone is done with slab i-1 (its stage is refilled now)
+    {
+      const int nx = i + kAttStages - 1;
+      if (nx < nslab) {
+        const int st = nx % kAttStages;
+        slab_load(sK + st * kSlab * 256, K, ldk, base + s_beg + nx * kSlab, base + s_end, t);
+        slab_load(sV + st * kSlab * 256, V, ldv, base + s_beg + nx * kSlab, base + s_end, t);
+      }
+      cp_async_commit();
+    }
+    const float* k0 = sK + (i % kAttStages) * kSlab * 256;
+    const float* v0 = sV + (i % kAttStages) * kSlab * 256;
 #pragma unroll
-    for (int r = 0; r < kKvTok; ++r) {
-      const float vv = vreg[r];
-      const float4* kr = reinterpret_cast<const float4*>(&sK[r][h * 32]);
+    for (int r = 0; r < kSlab; ++r) {
+      const float vv = __fdiv_rn(v0[r * 256 + t], fS);     // values / v_length (linear_attention.py:40)
+      const float4* kr = reinterpret_cast<const float4*>(k0 + r * 256 + h * 32);
 #pragma unroll
       for (int d4 = 0; d4 < 8; ++d4) {
         const float4 kk = kr[d4];
@@ -203,7 +238,7 @@ __global__ void __launch_bounds__(256) kv_partial_kernel(const float* __restrict
         acc[4 * d4 + 2] = fmaf(kk.z, vv, acc[4 * d4 + 2]);
         acc[4 * d4 + 3] = fmaf(kk.w, vv, acc[4 * d4 + 3]);
       }
-      ks += sK[r][t];
+      ks += k0[r * 256 + t];
     }
   }
   float* o = kv_part + ((static_cast<size_t>(n) * splits + split) * 8 + h) * 1056;
@@ -223,37 +258,54 @@ __global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict_
   kv[static_cast<size_t>(n) * 8448 + e] = s;
 }
 
-constexpr int kApplyTok = 32;
 __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict__ Q, long long ldq,
                                                          const float* __restrict__ kv,
                                                          float* __restrict__ msg, long long ldm, int L,
-                                                         int S, float eps) {
-  __shared__ __align__(16) float sQ[kApplyTok][256];
+                                                         int S, float eps, int splits) {
+  extern __shared__ __align__(16) float att_smem[];
+  float* sQ = att_smem;                                   // [stages][kSlab][256]
   const int n = blockIdx.y;
-  const int l0 = blockIdx.x * kApplyTok;
+  const int chunk = (L + splits - 1) / splits;
+  const int l_beg = blockIdx.x * chunk, l_end = min(L, l_beg + chunk);
+  const int nslab = l_end > l_beg ? (l_end - l_beg + kSlab - 1) / kSlab : 0;
   const int t = threadIdx.x, h = t >> 5, lane = t & 31;
+  const long long base = static_cast<long long>(n) * L;
+#pragma unroll
+  for (int st = 0; st < kAttStages - 1; ++st) {
+    if (st < nslab) slab_load(sQ + st * kSlab * 256, Q, ldq, base + l_beg + st * kSlab, base + l_end, t);
+    cp_async_commit();
+  }
   const float* kvh = kv + (static_cast<size_t>(n) * 8 + h) * 1056;
   float kvr[32];
 #pragma unroll
   for (int d = 0; d < 32; ++d) kvr[d] = kvh[d * 32 + lane];
   const float ksum = kvh[1024 + lane];
-  const int cnt = min(kApplyTok, L - l0);
-  for (int r = 0; r < cnt; ++r) sQ[r][t] = Q[(static_cast<size_t>(n) * L + l0 + r) * ldq + t];
-  __syncthreads();
   const float fS = static_cast<float>(S);
-  for (int r = 0; r < cnt; ++r) {
-    const float4* qr = reinterpret_cast<const float4*>(&sQ[r][h * 32]);
-    float a = 0.f;
-#pragma unroll
-    for (int d4 = 0; d4 < 8; ++d4) {
-      const float4 q = qr[d4];
-      a = fmaf(q.x, kvr[4 * d4], a);
-      a = fmaf(q.y, kvr[4 * d4 + 1], a);
-      a = fmaf(q.z, kvr[4 * d4 + 2], a);
-      a = fmaf(q.w, kvr[4 * d4 + 3], a);
+  for (int i = 0; i < nslab; ++i) {
+    cp_async_wait<kAttStages - 2>();
+    __syncthreads();
+    {
+      const int nx = i + kAttStages - 1;
+      if (nx < nslab) slab_load(sQ + (nx % kAttStages) * kSlab * 256, Q, ldq, base + l_beg + nx * kSlab, base + l_end, t);
+      cp_async_commit();
     }
-    const float den = warp_sum(sQ[r][t] * ksum);
-    msg[(static_cast<size_t>(n) * L + l0 + r) * ldm + t] = a * (1.f / (den + eps)) * fS;
+    const float* q0 = sQ + (i % kAttStages) * kSlab * 256;
+    const int cnt = min(kSlab, l_end - l_beg - i * kSlab);
+#pragma unroll 4
+    for (int r = 0; r < cnt; ++r) {
+      const float4* qr = reinterpret_cast<const float4*>(q0 + r * 256 + h * 32);
+      float a = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < 8; ++d4) {
+        const float4 q = qr[d4];
+        a = fmaf(q.x, kvr[4 * d4], a);
+        a = fmaf(q.y, kvr[4 * d4 + 1], a);
+        a = fmaf(q.z, kvr[4 * d4 + 2], a);
+        a = fmaf(q.w, kvr[4 * d4 + 3], a);
+      }
+      const float den = warp_sum(q0[r * 256 + t] * ksum);
+      msg[(base + l_beg + i * kSlab + r) * ldm + t] = a * (1.f / (den + eps)) * fS;
+    }
   }
 }
 
@@ -519,6 +571,218 @@ __global__ void col_conf_combine_kernel(const float* __restrict__ part, float* _
   cconf_max[static_cast<size_t>(b) * L + j] = m;
 }
 
+// ---- fused passes (L % 4 == 0, L <= 6144): S is read from DRAM twice instead of four times.
+// A block owns a slab of rows and all columns; thread t holds float4 column groups t, t+256, ... (6 per row).
+//   stats_fused : row (max, 1/sum exp) per row + online per-column (max, sum exp) partials of the slab
+//   conf_fused  : conf = softmax_row * softmax_col per element; row max / first argmax / tie count,
+//                 per-column partial max of the slab
+constexpr int kF4 = 6;   // float4 groups per thread per row
+
+template <int NV, bool IS_MAX>
+__device__ __forceinline__ void block_reduce_n(float (&v)[NV], float* sh /* [NV][8] */) {
+#pragma unroll
+  for (int q = 0; q < NV; ++q) v[q] = IS_MAX ? warp_max(v[q]) : warp_sum(v[q]);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) sh[q * 8 + (threadIdx.x >> 5)] = v[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    float r = sh[q * 8];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r = IS_MAX ? fmaxf(r, sh[q * 8 + k]) : r + sh[q * 8 + k];
+    v[q] = r;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) stats_fused_kernel(const float* __restrict__ S, float* __restrict__ row_max,
+                                                          float* __restrict__ row_rsum, float* __restrict__ part,
+                                                          int L, int rows_per_block, int splits) {
+  constexpr int R = 4;
+  __shared__ float sh[R * 8];
+  const int b = blockIdx.y, t = threadIdx.x;
+  const int i0 = blockIdx.x * rows_per_block, i1 = min(L, i0 + rows_per_block);
+  const int L4 = L >> 2;
+  const float4* Sb = reinterpret_cast<const float4*>(S + static_cast<size_t>(b) * L * L);
+  float cm[kF4 * 4], cs[kF4 * 4];
+#pragma unroll
+  for (int c = 0; c < kF4 * 4; ++c) { cm[c] = -INFINITY; cs[c] = 0.f; }
+  const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (int i = i0; i < i1; i += R) {
+    float4 v[R][kF4];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < kF4; ++k) {
+        const int f = t + 256 * k;
+        v[r][k] = (i + r < i1 && f < L4) ? __ldg(Sb + static_cast<size_t>(i + r) * L4 + f) : ninf;
+      }
+    float rm[R], rs[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < kF4; ++k) m = fmaxf(fmaxf(m, fmaxf(v[r][k].x, v[r][k].y)), fmaxf(v[r][k].z, v[r][k].w));
+      rm[r] = m;
+    }
+    block_reduce_n<R, true>(rm, sh);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float a = 0.f;
+      if (i + r < i1) {
+#pragma unroll
+        for (int k = 0; k < kF4; ++k) {
+          a += __expf(__fsub_rn(v[r][k].x, rm[r])); a += __expf(__fsub_rn(v[r][k].y, rm[r]));
+          a += __expf(__fsub_rn(v[r][k].z, rm[r])); a += __expf(__fsub_rn(v[r][k].w, rm[r]));
+        }
+      }
+      rs[r] = a;
+    }
+    block_reduce_n<R, false>(rs, sh);
+    if (t < R && i + t < i1) {
+      row_max[static_cast<size_t>(b) * L + i + t] = rm[t];
+      row_rsum[static_cast<size_t>(b) * L + i + t] = 1.f / rs[t];
+    }
+    // online per-column (max, sum exp) over these R rows
+#pragma unroll
+    for (int k = 0; k < kF4; ++k) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float x[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r] = e == 0 ? v[r][k].x : e == 1 ? v[r][k].y : e == 2 ? v[r][k].z : v[r][k].w;
+        float m4 = x[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) m4 = fmaxf(m4, x[r]);
+        const int c = k * 4 + e;
+        const float mn = fmaxf(cm[c], m4);
+        if (mn > -INFINITY) {
+          float a = cs[c] * __expf(cm[c] - mn);
+#pragma unroll
+          for (int r = 0; r < R; ++r) a += __expf(x[r] - mn);
+          cs[c] = a;
+          cm[c] = mn;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kF4; ++k) {
+    const int f = t + 256 * k;
+    if (f < L4) {
+      float* o = part + ((static_cast<size_t>(b) * splits + blockIdx.x) * L + 4 * f) * 2;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { o[2 * e] = cm[k * 4 + e]; o[2 * e + 1] = cs[k * 4 + e]; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) conf_fused_kernel(const float* __restrict__ S, const float* __restrict__ row_max,
+                                                         const float* __restrict__ row_rsum,
+                                                         const float* __restrict__ col_max,
+                                                         const float* __restrict__ col_rsum,
+                                                         float* __restrict__ rconf_max, int* __restrict__ rconf_arg,
+                                                         int* __restrict__ rconf_ties, float* __restrict__ part,
+                                                         int L, int rows_per_block, int splits, bool raw) {
+  constexpr int R = 2;
+  __shared__ float sh[2 * R * 8];
+  const int b = blockIdx.y, t = threadIdx.x;
+  const int i0 = blockIdx.x * rows_per_block, i1 = min(L, i0 + rows_per_block);
+  const int L4 = L >> 2;
+  const float4* Sb = reinterpret_cast<const float4*>(S + static_cast<size_t>(b) * L * L);
+  float4 cmv[kF4], crv[kF4];
+  float cbest[kF4 * 4];
+#pragma unroll
+  for (int k = 0; k < kF4; ++k) {
+    const int f = t + 256 * k;
+    const bool ok = f < L4 && !raw;
+    cmv[k] = ok ? __ldg(reinterpret_cast<const float4*>(col_max + static_cast<size_t>(b) * L) + f) : make_float4(0, 0, 0, 0);
+    crv[k] = ok ? __ldg(reinterpret_cast<const float4*>(col_rsum + static_cast<size_t>(b) * L) + f) : make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cbest[k * 4 + e] = -1.f;
+  }
+  for (int i = i0; i < i1; i += R) {
+    float4 v[R][kF4];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < kF4; ++k) {
+        const int f = t + 256 * k;
+        v[r][k] = (i + r < i1 && f < L4) ? __ldg(Sb + static_cast<size_t>(i + r) * L4 + f) : make_float4(0, 0, 0, 0);
+      }
+    float best[R];
+    int arg[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool rok = i + r < i1;
+      const size_t row = static_cast<size_t>(b) * L + (rok ? i + r : i);
+      const float rmx = raw ? 0.f : row_max[row], rrs = raw ? 0.f : row_rsum[row];
+      best[r] = -1.f;
+      arg[r] = 0x7fffffff;
+#pragma unroll
+      for (int k = 0; k < kF4; ++k) {
+        const int f = t + 256 * k;
+        const bool ok = rok && f < L4;
+        float4 c;
+        c.x = ok ? conf_value(v[r][k].x, rmx, rrs, cmv[k].x, crv[k].x, raw) : -1.f;
+        c.y = ok ? conf_value(v[r][k].y, rmx, rrs, cmv[k].y, crv[k].y, raw) : -1.f;
+        c.z = ok ? conf_value(v[r][k].z, rmx, rrs, cmv[k].z, crv[k].z, raw) : -1.f;
+        c.w = ok ? conf_value(v[r][k].w, rmx, rrs, cmv[k].w, crv[k].w, raw) : -1.f;
+        v[r][k] = c;   // keep the confidences for the tie count
+        if (c.x > best[r]) { best[r] = c.x; arg[r] = 4 * f; }
+        if (c.y > best[r]) { best[r] = c.y; arg[r] = 4 * f + 1; }
+        if (c.z > best[r]) { best[r] = c.z; arg[r] = 4 * f + 2; }
+        if (c.w > best[r]) { best[r] = c.w; arg[r] = 4 * f + 3; }
+        cbest[k * 4] = fmaxf(cbest[k * 4], c.x); cbest[k * 4 + 1] = fmaxf(cbest[k * 4 + 1], c.y);
+        cbest[k * 4 + 2] = fmaxf(cbest[k * 4 + 2], c.z); cbest[k * 4 + 3] = fmaxf(cbest[k * 4 + 3], c.w);
+      }
+    }
+    float bm[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) bm[r] = best[r];
+    block_reduce_n<R, true>(bm, sh);
+    // first index attaining the max (max of the negated candidate), and how many attain it
+    float q[2 * R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      q[r] = (best[r] == bm[r] && arg[r] != 0x7fffffff) ? -static_cast<float>(arg[r]) : -INFINITY;   // indices < 2^24: exact
+      int ties = 0;
+#pragma unroll
+      for (int k = 0; k < kF4; ++k)
+        ties += (v[r][k].x == bm[r]) + (v[r][k].y == bm[r]) + (v[r][k].z == bm[r]) + (v[r][k].w == bm[r]);
+      q[R + r] = static_cast<float>(ties);
+    }
+    {  // one barrier pair for both reductions: max over q[0..R), sum over q[R..2R)
+#pragma unroll
+      for (int r = 0; r < R; ++r) { q[r] = warp_max(q[r]); q[R + r] = warp_sum(q[R + r]); }
+      if ((t & 31) == 0) {
+#pragma unroll
+        for (int z = 0; z < 2 * R; ++z) sh[z * 8 + (t >> 5)] = q[z];
+      }
+      __syncthreads();
+      if (t < R && i + t < i1) {
+        float fm = sh[t * 8], ts = sh[(R + t) * 8];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { fm = fmaxf(fm, sh[t * 8 + k]); ts += sh[(R + t) * 8 + k]; }
+        const size_t row = static_cast<size_t>(b) * L + i + t;
+        rconf_max[row] = bm[t];
+        rconf_arg[row] = static_cast<int>(-fm);
+        rconf_ties[row] = static_cast<int>(ts + 0.5f);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kF4; ++k) {
+    const int f = t + 256 * k;
+    if (f < L4)
+      *reinterpret_cast<float4*>(part + (static_cast<size_t>(b) * splits + blockIdx.x) * L + 4 * f) =
+          make_float4(cbest[k * 4], cbest[k * 4 + 1], cbest[k * 4 + 2], cbest[k * 4 + 3]);
+  }
+}
+
 __device__ __forceinline__ bool border_ok(int idx, int h, int w, int bd) {
   const int y = idx / w, x = idx - y * w;
   return y >= bd && y < h - bd && x >= bd && x < w - bd;
@@ -748,9 +1012,18 @@ int linear_attention_long(const float* Q, long long ldq, const float* K, long lo
                           long long ldv, float* msg, long long ldm, float* kv_part, float* kv, int n,
                           int L, int S, int heads, int dim, int splits, cudaStream_t st) {
   if (dim != 32 || heads != 8) return MFR_ERR_UNSUPPORTED;
-  kv_partial_kernel<<<dim3(splits, n), 256, 0, st>>>(K, ldk, V, ldv, kv_part, S, splits);
+  if ((ldq | ldk | ldv) & 3) return MFR_ERR_ARG;                    // 16-byte cp.async chunks
+  constexpr int kKvSmem = 2 * kAttStages * kSlab * 256 * 4, kApSmem = kAttStages * kSlab * 256 * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmem));
+    attr_set = true;
+  }
+  kv_partial_kernel<<<dim3(splits, n), 256, kKvSmem, st>>>(K, ldk, V, ldv, kv_part, S, splits);
   kv_reduce_kernel<<<dim3((8 * 1056 + 255) / 256, n), 256, 0, st>>>(kv_part, kv, splits);
-  attn_apply_kernel<<<dim3((L + kApplyTok - 1) / kApplyTok, n), 256, 0, st>>>(Q, ldq, kv, msg, ldm, L, S, 1e-6f);
+  const int asplits = std::max(1, std::min((L + kSlab - 1) / kSlab, (4 * 148 + n - 1) / n));
+  attn_apply_kernel<<<dim3(asplits, n), 256, kApSmem, st>>>(Q, ldq, kv, msg, ldm, L, S, 1e-6f, asplits);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }
@@ -783,16 +1056,30 @@ int coarse_match(const float* S, CoarseMatchBuffers f, int B, int L, int h_c, in
                  int border, float scale, int splits, cudaStream_t st, bool input_is_conf) {
   const int cb = (L + 255) / 256;
   const bool raw = input_is_conf;
-  if (!raw) {
-    row_stats_kernel<<<dim3(L, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, L);
-    col_stats_partial_kernel<<<dim3(cb, splits, B), 256, 0, st>>>(S, f.col_part, L, splits);
-    col_stats_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.col_max, f.col_rsum, L, splits);
+  const bool fused = (L % 4 == 0) && L <= 256 * 4 * kF4 && (reinterpret_cast<uintptr_t>(S) & 15) == 0;
+  if (fused) {
+    // a block owns ceil(L / splits) rows (rounded to the row batch) and all columns
+    const int rpb = ((L + splits - 1) / splits + 3) / 4 * 4;
+    const int nblk = (L + rpb - 1) / rpb;
+    if (!raw) {
+      stats_fused_kernel<<<dim3(nblk, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_part, L, rpb, nblk);
+      col_stats_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.col_max, f.col_rsum, L, nblk);
+    }
+    conf_fused_kernel<<<dim3(nblk, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max, f.col_rsum, f.rconf_max,
+                                                     f.rconf_arg, f.rconf_ties, f.col_part, L, rpb, nblk, raw);
+    col_conf_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.cconf_max, L, nblk);
+  } else {
+    if (!raw) {
+      row_stats_kernel<<<dim3(L, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, L);
+      col_stats_partial_kernel<<<dim3(cb, splits, B), 256, 0, st>>>(S, f.col_part, L, splits);
+      col_stats_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.col_max, f.col_rsum, L, splits);
+    }
+    row_conf_kernel<<<dim3(L, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max, f.col_rsum,
+                                                f.rconf_max, f.rconf_arg, f.rconf_ties, L, raw);
+    col_conf_partial_kernel<<<dim3(cb, splits, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max,
+                                                                 f.col_rsum, f.col_part, L, splits, raw);
+    col_conf_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.cconf_max, L, splits);
   }
-  row_conf_kernel<<<dim3(L, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max, f.col_rsum,
-                                              f.rconf_max, f.rconf_arg, f.rconf_ties, L, raw);
-  col_conf_partial_kernel<<<dim3(cb, splits, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max,
-                                                               f.col_rsum, f.col_part, L, splits, raw);
-  col_conf_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.cconf_max, L, splits);
   select_kernel<<<dim3(cb, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max, f.col_rsum,
                                              f.rconf_max, f.rconf_arg, f.rconf_ties, f.cconf_max, f.jsel,
                                              L, h_c, w_c, thr, border, raw);
@@ -801,6 +1088,8 @@ int coarse_match(const float* S, CoarseMatchBuffers f, int B, int L, int h_c, in
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }
+
+int coarse_match_splits(int B, int L) { return std::max(1, std::min((L + 3) / 4, (2 * 148 + B - 1) / B)); }
 
 int coarse_match_alloc(int B, int L, int splits, CoarseMatchBuffers* o) {
   const size_t BL = static_cast<size_t>(B) * L;

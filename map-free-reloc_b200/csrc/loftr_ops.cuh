@@ -58,6 +58,8 @@ struct CoarseMatchBuffers {
 int coarse_match(const float* S, CoarseMatchBuffers bufs, int B, int L, int h_c, int w_c, float thr,
                  int border, float scale, int splits, cudaStream_t st, bool input_is_conf = false);
 // scratch + output buffers for a standalone call (freed with coarse_match_free)
+// row slabs per pair such that all pairs together give ~2 blocks per SM
+int coarse_match_splits(int B, int L);
 int coarse_match_alloc(int B, int L, int splits, CoarseMatchBuffers* out);
 void coarse_match_free(CoarseMatchBuffers* b);
 

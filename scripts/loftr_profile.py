@@ -22,7 +22,7 @@ groups = collections.OrderedDict()
 for i, (name, kind, ms, fl) in enumerate(prof):
     key = name if kind == 1 else "simt"
     # coarse grouping by weight-name prefix
-    if name.startswith("layer"): key = "backbone conv"
+    if name.startswith("layer") and kind == 1: key = "backbone conv"
     elif name.startswith("coarse") or name == "qkv": key = "transformer gemm"
     elif name.startswith("fine"): key = "fine gemm"
     g = groups.setdefault(key, [0, 0.0, 0.0]); g[0] += 1; g[1] += ms; g[2] += fl
@@ -36,6 +36,6 @@ print("--- SIMT steps by name")
 for k, (n, ms) in sorted(simt.items(), key=lambda kv: -kv[1][1]):
     print(f"{k:24s} x{n:3d} {ms*1e3:9.1f} us")
 print("--- slowest steps")
-for i in sorted(range(len(prof)), key=lambda i: -prof[i][2])[:28]:
+for i in sorted(range(len(prof)), key=lambda i: -prof[i][2])[:int(os.environ.get('TOP', 28))]:
     n, k, ms, fl = prof[i]
     print(f"{i:4d} {n:24s} kind {k} {ms*1e3:9.1f} us {fl/ms/1e9 if ms>0 else 0:8.1f} TF/s")
