@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("MFR_BENCH_BATCH", 4)), help="pairs per step per GPU")
     ap.add_argument("--hyp", type=int, default=1024, help="5-point hypotheses per pair")
     ap.add_argument("--match-thr", type=float, default=0.2, help="LoFTR coarse confidence threshold (reference: 0.2)")
-    ap.add_argument("--precision", default=os.environ.get("MFR_BENCH_PRECISION", "tf32"), choices=["tf32", "bf16"],
+    ap.add_argument("--precision", default=os.environ.get("MFR_BENCH_PRECISION", "bf16"), choices=["tf32", "bf16"],
                     help="LoFTR backbone tensor-core input type (tf32 = parity mode; bf16 = bf16 storage + MMA in the ResNet-FPN)")
     ap.add_argument("--pool", type=int, default=8, help="distinct synthetic pairs cycled through")
     ap.add_argument("--cpu-sample", type=int, default=2, help="pairs timed for the cpu_baseline leg")
@@ -116,8 +116,18 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
-    return 6650.0, 1590.0, "fallback"
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured", d.get("bf16_tflops_sustained")
+    return 6650.0, 1590.0, "fallback", 1400.0
+
+
+def load_traffic(precision, batch):
+    """DRAM bytes of the ResNet-FPN conv launches of one step, from the committed ncu capture of this
+    workload (profiles/README.md); None when no capture exists for the configuration."""
+    p = os.path.join(ROOT, "profiles", f"r01_conv_gemm_metrics_{precision}_B{batch}.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))["backbone"]
+    return int(d["dram_read"] + d["dram_write"]), os.path.relpath(p, ROOT)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -231,7 +241,8 @@ def run_ours(args):
         # ---- roofline of the dominant kernel (tcgen05 conv/GEMM), per-launch device times by CUDA events
         prof = eng.profile(dres["g0"][idx_cache[0]], dres["g1"][idx_cache[0]])
         tot_ms = sum(p[2] for p in prof)
-        hbm, bf16, how = load_peaks()
+        hbm, bf16, how, bf16_sus = load_peaks()
+        traffic, traffic_src = load_traffic(args.precision, B)
         is_bb = lambda p: p[1] == 1 and p[0].startswith("layer")          # ResNet-FPN implicit-GEMM convs
         bb = [p for p in prof if is_bb(p)]
         og = [p for p in prof if p[1] == 1 and not is_bb(p)]             # transformer / correlation GEMMs (always TF32)
@@ -245,7 +256,10 @@ def run_ours(args):
                     "bound": "tensor", "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "TFLOP/s",
                     "frac": round(achieved / peak, 4),
                     "peak_note": f"{how} cuBLAS bf16 {bf16} TFLOP/s" + ("" if kind == "bf16" else " / 2 (kind::tf32 issues at half the bf16 rate)"),
-                    "share_of_step": round(bb_ms / tot_ms, 3), "flops_per_step": bb_fl, "traffic": None,
+                    "frac_of_sustained_peak": round(achieved / (bf16_sus if kind == "bf16" else bf16_sus / 2.0), 4) if bf16_sus else None,
+                    "share_of_step": round(bb_ms / tot_ms, 3), "flops_per_step": bb_fl, "traffic": traffic,
+                    "traffic_note": (f"dram__bytes_read.sum + dram__bytes_write.sum summed over the {len(bb)} launches of one step, {traffic_src}"
+                                     if traffic else "no ncu capture committed for this precision / batch"),
                     "other_gemms": {"launches": len(og), "achieved": round(og_fl / (og_ms * 1e-3) / 1e12, 1),
                                     "peak": round(bf16 / 2.0, 1), "share_of_step": round(og_ms / tot_ms, 3)}}
         cpu = cpu_baseline(args, sample=args.cpu_sample)
