@@ -112,6 +112,9 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+WORKLOAD = "LoFTR coarse-to-fine + 5-pt essential (EssentialMatrixMetric, scale from depth), 540x720 (720x544 padded), 1xB200 per rank"
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -268,7 +271,7 @@ def run_ours(args):
             "steps": K, "warmup": Wm, "ms_per_step": round(ms_res / K, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": ("bf16 backbone (bf16 storage, fp32 accumulate) + tf32 transformer/correlation; pose solve fp64/fp32"
                                          if args.precision == "bf16" else "tf32 (fp32 storage/accumulate; pose solve fp64/fp32)"), "data": "synthetic",
-            "config": {"workload": "LoFTR coarse-to-fine + 5-pt essential (EssentialMatrixMetric, scale from depth), 540x720 (720x544 padded), 1xB200 per rank",
+            "config": {"workload": WORKLOAD,
                        "pairs_per_step_per_gpu": B, "precision": args.precision, "hypotheses_per_pair": args.hyp, "match_thr": args.match_thr,
                        "matches_last_batch": m_last, "weights": "synthetic (seeded); reference checkpoints not distributed",
                        "l2": "per-step working set (activations + 150 MB similarity matrix per pair) far exceeds the 126 MB L2; inputs rotate over %d distinct pairs" % n_pool},
@@ -308,9 +311,21 @@ def cpu_pairs(n_pairs, match_thr, seed0=1000):
     return t_net, t_solve
 
 
-def cpu_baseline(args, sample):
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every core the process may run on."""
     import torch
-    cores = torch.get_num_threads()
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(n)
+    try:
+        import cv2
+        cv2.setNumThreads(n)
+    except Exception:
+        pass
+    return torch.get_num_threads()
+
+
+def cpu_baseline(args, sample):
+    cores = use_all_host_threads()
     t_net, t_solve = cpu_pairs(sample, args.match_thr)
     return {"value": round(sample / (t_net + t_solve), 4), "unit": "pairs/s", "cores": cores, "kind": "port",
             "sample": f"{sample} pairs of the same workload: oracle LoFTR (torch CPU fp32, {cores} threads) {t_net / sample:.2f} s/pair + OpenCV USAC_MAGSAC 5-pt + scale consensus {t_solve / sample * 1e3:.1f} ms/pair"}
@@ -320,10 +335,10 @@ def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    import torch
     K, Wm = args.steps, args.warmup
-    cores = torch.get_num_threads()
-    cpu_pairs(min(Wm, 1), args.match_thr)                      # warm-up (thread pools, allocator)
+    cores = use_all_host_threads()
+    if Wm > 0:
+        cpu_pairs(1, args.match_thr)                           # warm-up (thread pools, allocator)
     t0 = time.perf_counter()
     t_net, t_solve = cpu_pairs(K, args.match_thr)              # one pair per step (bounded sample of a step)
     wall = time.perf_counter() - t0
@@ -332,8 +347,8 @@ def run_reference(args):
         "impl": "reference", "metric": "image-pairs/sec @ 540x720", "value": round(v, 4), "unit": "pairs/s",
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(wall / K * 1e3, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 (OpenCV solve f64)", "data": "synthetic",
-        "config": {"workload": "LoFTR coarse-to-fine + 5-pt essential (EssentialMatrixMetric, scale from depth), 540x720, reference CPU path (oracle port: torch CPU + OpenCV), 1 pair per step",
-                   "match_thr": args.match_thr},
+        "config": {"workload": WORKLOAD, "match_thr": args.match_thr, "weights": "synthetic (seeded); reference checkpoints not distributed",
+                   "reference_sample": "reference CPU path (oracle port: torch CPU fp32 LoFTR + OpenCV USAC_MAGSAC + scale consensus), 1 pair per step on rank 0"},
         "cpu_baseline": {"value": round(v, 4), "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": f"{K} pairs, LoFTR {t_net / K:.2f} s/pair + solver {t_solve / K * 1e3:.1f} ms/pair"},
         "e2e": {"value": round(v, 4), "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
