@@ -39,12 +39,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("MFR_BENCH_BATCH", 4)), help="pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("MFR_BENCH_BATCH", 8)), help="pairs per step per GPU")
     ap.add_argument("--hyp", type=int, default=1024, help="5-point hypotheses per pair")
     ap.add_argument("--match-thr", type=float, default=0.2, help="LoFTR coarse confidence threshold (reference: 0.2)")
     ap.add_argument("--precision", default=os.environ.get("MFR_BENCH_PRECISION", "bf16"), choices=["tf32", "bf16"],
                     help="LoFTR backbone tensor-core input type (tf32 = parity mode; bf16 = bf16 storage + MMA in the ResNet-FPN)")
-    ap.add_argument("--pool", type=int, default=8, help="distinct synthetic pairs cycled through")
+    ap.add_argument("--pool", type=int, default=16, help="distinct synthetic pairs cycled through")
     ap.add_argument("--cpu-sample", type=int, default=2, help="pairs timed for the cpu_baseline leg")
     return ap.parse_args()
 
@@ -66,6 +66,15 @@ def make_pool(n, seed0):
         d0.append(p["depth0"]); d1.append(p["depth1"]); K.append(p["K_color0"])
         gt.append((p["R_gt"], p["t_gt"]))
     return (np.stack(g0), np.stack(g1), np.stack(d0), np.stack(d1), np.stack(K).astype(np.float32), gt)
+
+
+def pose_errors(R, t, gt):
+    """Rotation error (deg) and translation error (m) of one estimate against ground truth; NaN -> inf."""
+    Rg, tg = gt
+    if not (np.all(np.isfinite(R)) and np.all(np.isfinite(t))):
+        return float("inf"), float("inf")
+    c = np.clip((np.trace(np.asarray(R, np.float64).T @ Rg) - 1.0) / 2.0, -1.0, 1.0)
+    return float(np.degrees(np.arccos(c))), float(np.linalg.norm(np.ravel(t).astype(np.float64) - np.ravel(tg)))
 
 
 class ClockSampler:
@@ -112,6 +121,8 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+WEIGHTS = ("hand-constructed functional LoFTR weights (loftr.functional_state_dict: full-shape layers that implement a patch "
+           "descriptor + normalised cross-correlation); the reference does not ship its checkpoints")
 WORKLOAD = "LoFTR coarse-to-fine + 5-pt essential (EssentialMatrixMetric, scale from depth), 540x720 (720x544 padded), 1xB200 per rank"
 
 
@@ -151,7 +162,7 @@ def run_ours(args):
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
     HP, WP = H0 + H0 % 8, W0 + W0 % 8                       # matchers.py:41-46 -> 720 x 544
 
-    eng = loftr.LoFTR(loftr.synthetic_state_dict(0), batch=B, height=HP, width=WP, cfg={"thr": args.match_thr},
+    eng = loftr.LoFTR(loftr.functional_state_dict(), batch=B, height=HP, width=WP, cfg={"thr": args.match_thr},
                       device=local_rank, graph=True, precision=args.precision)
     L = (HP // 8) * (WP // 8)
     be = pose_solver.PoseBackend(max_pairs=B, max_pts=L, max_hyp=max(args.hyp, 128), device=local_rank)
@@ -164,40 +175,26 @@ def run_ours(args):
     # pinned host copies (e2e) and device-resident copies (value)
     h = {k: torch.from_numpy(v).pin_memory() for k, v in (("g0", g0), ("g1", g1), ("d0", d0), ("d1", d1), ("K", Kc))}
     dres = {k: v.to(dev) for k, v in h.items()}
+    from mfr_b200.pipeline import RelocPipeline
     outs = eng.device_outputs()
-    rec_host = torch.zeros(B, 13, dtype=torch.float32).pin_memory()   # R(9) t(3) inliers(1)
-
-    def solve(dep0, dep1, Kb):
-        """5-point RANSAC + LO + scale-from-depth on the engine's device-resident matches."""
-        with torch.cuda.stream(eng.stream):
-            R, t, n = be.emat_metric(outs["mkpts0_f"], outs["mkpts1_f"], outs["m_offsets"], Kb, Kb, dep0, dep1,
-                                     PIX_THR, SCALE_THR, args.hyp)
-        return R, t, n
-
+    # the repo's public streaming API: copy / matcher / RANSAC stages of consecutive batches overlap on three streams
+    pipe = RelocPipeline(eng, be, PIX_THR, SCALE_THR, args.hyp, depth_hw=(H0, W0))
     idx_cache = [torch.tensor(batch_idx(s), device=dev) for s in range(n_pool)]   # period divides n_pool
 
     def step_resident(step):
+        """inputs already in HBM; returns the poses of the previous step's batch (one-deep pipeline)"""
         idx = idx_cache[step % n_pool]
         with torch.cuda.stream(eng.stream):
             a, b_, p0, p1, Kb = (dres["g0"][idx], dres["g1"][idx], dres["d0"][idx], dres["d1"][idx], dres["K"][idx].contiguous())
-        eng.forward_async(a, b_)
-        return solve(p0, p1, Kb)
-
-    dstage = {k: torch.empty((B,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev) for k, v in h.items()}
+        return pipe.submit_device(a, b_, p0, p1, Kb)
 
     def step_e2e(step):
+        """host (pinned) inputs -> device copies inside the step; the previous batch's poses are read back"""
         idx = batch_idx(step)
-        with torch.cuda.stream(eng.stream):  # host (pinned) -> device copies of this step's inputs
-            for k in dstage:
-                for j, i in enumerate(idx):
-                    dstage[k][j].copy_(h[k][i], non_blocking=True)
-        eng.forward_async(dstage["g0"], dstage["g1"])
-        R, t, n = solve(dstage["d0"], dstage["d1"], dstage["K"])
-        with torch.cuda.stream(eng.stream):
-            rec = torch.cat([R.reshape(B, 9), t.reshape(B, 3), n.reshape(B, 1).float()], 1)
-            rec_host.copy_(rec, non_blocking=True)
-        eng.stream.synchronize()             # the caller consumes the poses of this step
-        return rec_host
+        return pipe.submit_host(*[[h[k][i] for i in idx] for k in ("g0", "g1", "d0", "d1", "K")])
+
+    in_bytes = sum(int(np.prod(h[k].shape[1:])) * h[k].element_size() * B for k in h)
+    out_bytes = int(pipe.slots[0]["rec_host"].numel() * 4)
 
     def barrier():
         if world > 1:
@@ -207,20 +204,22 @@ def run_ours(args):
     def timed(fn, gather_at_end=False):
         for s in range(Wm):
             fn(s)
+        pipe.drain()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(eng.stream):
             e0.record()
-        last = None
         for s in range(K):
-            last = fn(Wm + s)
+            fn(Wm + s)
+        last = pipe.drain()                          # the timed region ends when the last batch's poses are on the host
         if gather_at_end and world > 1:
             R, t, n = last
             with torch.cuda.stream(eng.stream):
-                rec = torch.cat([R.reshape(B, 9), t.reshape(B, 3), n.reshape(B, 1).float()], 1).contiguous()
+                rec = torch.cat([R.reshape(B, 9), t.reshape(B, 3), n.reshape(B, 1).float()], 1).to(dev).contiguous()
                 allr = [torch.empty_like(rec) for _ in range(world)]
                 dist.all_gather(allr, rec)   # the path's only collective: 52-byte records per pair
         with torch.cuda.stream(eng.stream):
+            eng.stream.wait_stream(pipe.s_solve)
             e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -235,9 +234,18 @@ def run_ours(args):
     pairs = K * B * world
     value = pairs / (ms_res / 1e3)
     e2e_value = pairs / (ms_e2e / 1e3)
-    in_bytes = sum(int(np.prod(dstage[k].shape)) * dstage[k].element_size() for k in dstage)
     with torch.cuda.stream(eng.stream):
         m_last = int(outs["m_total"][0].item())
+
+    # ---- accuracy pass (untimed): every pair of the pool once through the host-buffer path
+    acc_rows = {}
+    n_acc = (n_pool + B - 1) // B
+    res_list = [step_e2e(s_) for s_ in range(n_acc)][1:] + [pipe.drain()]     # results arrive one call late
+    for s_, (Rb, tb, nb) in enumerate(res_list):
+        for j, i in enumerate(batch_idx(s_)):
+            if i not in acc_rows:
+                acc_rows[i] = (Rb[j].numpy(), tb[j].numpy(), int(nb[j]))
+    gpu_errs = [pose_errors(acc_rows[i][0], acc_rows[i][1], gt[i]) for i in sorted(acc_rows)]
 
     result = None
     if rank == 0:
@@ -266,6 +274,17 @@ def run_ours(args):
                     "other_gemms": {"launches": len(og), "achieved": round(og_fl / (og_ms * 1e-3) / 1e12, 1),
                                     "peak": round(bf16 / 2.0, 1), "share_of_step": round(og_ms / tot_ms, 3)}}
         cpu = cpu_baseline(args, sample=args.cpu_sample)
+        fin = lambda v: [x for x in v if np.isfinite(x)]
+        med = lambda v: round(float(np.median(v)), 4) if len(v) else None
+        accuracy = {"against": "synthetic ground-truth poses of the pool pairs (EssentialMatrixMetric: R, metric t)",
+                    "pairs": len(gpu_errs), "solved": len(fin([e[0] for e in gpu_errs])),
+                    "median_rot_err_deg": med(fin([e[0] for e in gpu_errs])),
+                    "median_trans_err_m": med(fin([e[1] for e in gpu_errs])),
+                    "median_inliers": med([acc_rows[i][2] for i in sorted(acc_rows)]),
+                    "reference_cpu_port": {"pairs": len(CPU_ERRS), "median_rot_err_deg": med(fin([e[0] for e in CPU_ERRS])),
+                                           "median_trans_err_m": med(fin([e[1] for e in CPU_ERRS])),
+                                           "median_matches": med([e[2] for e in CPU_ERRS]),
+                                           "note": "same first pairs of the pool, oracle LoFTR fp32 + OpenCV USAC_MAGSAC"}}
         result = {
             "metric": "image-pairs/sec @ 540x720", "value": round(value, 2), "unit": "pairs/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": round(ms_res / K, 3), "higher_is_better": True, "scaling": "weak",
@@ -273,12 +292,13 @@ def run_ours(args):
                                          if args.precision == "bf16" else "tf32 (fp32 storage/accumulate; pose solve fp64/fp32)"), "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "pairs_per_step_per_gpu": B, "precision": args.precision, "hypotheses_per_pair": args.hyp, "match_thr": args.match_thr,
-                       "matches_last_batch": m_last, "weights": "synthetic (seeded); reference checkpoints not distributed",
+                       "matches_last_batch": m_last, "weights": WEIGHTS,
                        "l2": "per-step working set (activations + 150 MB similarity matrix per pair) far exceeds the 126 MB L2; inputs rotate over %d distinct pairs" % n_pool},
             "e2e": {"value": round(e2e_value, 2), "unit": "pairs/s", "h2d_bytes_per_step": in_bytes,
-                    "d2h_bytes_per_step": int(rec_host.numel() * 4), "ms_per_step": round(ms_e2e / K, 3)},
+                    "d2h_bytes_per_step": out_bytes, "ms_per_step": round(ms_e2e / K, 3),
+                    "api": "mfr_b200.pipeline.RelocPipeline.submit_host (copy / matcher / RANSAC stages of consecutive batches overlap)"},
             "gpu_launches": int((eng.num_launches() + 3) * K), "kernels_per_step": eng.num_launches() + 3,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "accuracy": accuracy,
         }
     if world > 1:
         dist.barrier()
@@ -291,11 +311,14 @@ def run_ours(args):
 # CPU baseline / reference arm: the reference's algorithm restated in oracle/ (torch CPU LoFTR +
 # OpenCV USAC_MAGSAC + scale consensus), all host threads
 # ------------------------------------------------------------------------------------------------
+CPU_ERRS = []   # (rot err deg, trans err m, matches) of every pair the CPU leg solved
+
+
 def cpu_pairs(n_pairs, match_thr, seed0=1000):
     import torch
     from mfr_b200 import loftr
     from oracle import loftr_oracle as lo, pose_solver_oracle as po
-    sd = loftr.synthetic_state_dict(0)
+    sd = loftr.functional_state_dict()
     g0, g1, d0, d1, Kc, gt = make_pool(n_pairs, seed0)
     t_net = t_solve = 0.0
     for i in range(n_pairs):
@@ -305,9 +328,10 @@ def cpu_pairs(n_pairs, match_thr, seed0=1000):
             o = lo.loftr_forward(i0, i1, sd, {"thr": match_thr})
         t1 = time.perf_counter()
         k0, k1 = o["mkpts0_f"].numpy(), o["mkpts1_f"].numpy()
-        po.essential_matrix_metric_solver(k0, k1, d0[i], d1[i], Kc[i], Kc[i], PIX_THR, 0.9999, SCALE_THR)
+        Rc, tc = po.essential_matrix_metric_solver(k0, k1, d0[i], d1[i], Kc[i], Kc[i], PIX_THR, 0.9999, SCALE_THR)[:2]
         t2 = time.perf_counter()
         t_net += t1 - t0; t_solve += t2 - t1
+        CPU_ERRS.append(pose_errors(Rc, tc, gt[i]) + (len(k0),))
     return t_net, t_solve
 
 
@@ -315,6 +339,13 @@ def use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every core the process may run on."""
     import torch
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:                                   # one thread per physical core (SMT siblings only slow the GEMMs down)
+        import psutil
+        phys = psutil.cpu_count(logical=False)
+        if phys:
+            n = max(1, min(n, phys))
+    except Exception:
+        pass
     torch.set_num_threads(n)
     try:
         import cv2
@@ -347,11 +378,15 @@ def run_reference(args):
         "impl": "reference", "metric": "image-pairs/sec @ 540x720", "value": round(v, 4), "unit": "pairs/s",
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(wall / K * 1e3, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 (OpenCV solve f64)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "match_thr": args.match_thr, "weights": "synthetic (seeded); reference checkpoints not distributed",
+        "config": {"workload": WORKLOAD, "match_thr": args.match_thr, "weights": WEIGHTS,
                    "reference_sample": "reference CPU path (oracle port: torch CPU fp32 LoFTR + OpenCV USAC_MAGSAC + scale consensus), 1 pair per step on rank 0"},
         "cpu_baseline": {"value": round(v, 4), "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": f"{K} pairs, LoFTR {t_net / K:.2f} s/pair + solver {t_solve / K * 1e3:.1f} ms/pair"},
-        "e2e": {"value": round(v, 4), "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": round(v, 4), "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "accuracy": {"against": "synthetic ground-truth poses", "pairs": len(CPU_ERRS),
+                     "median_rot_err_deg": round(float(np.median([e[0] for e in CPU_ERRS])), 4),
+                     "median_trans_err_m": round(float(np.median([e[1] for e in CPU_ERRS])), 4),
+                     "median_matches": float(np.median([e[2] for e in CPU_ERRS]))}}))
 
 
 if __name__ == "__main__":

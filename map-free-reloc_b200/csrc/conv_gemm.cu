@@ -158,6 +158,60 @@ __device__ __forceinline__ void epilogue_subtile(const ConvGemmParams& p, uint32
   }
 }
 
+// TMA-store epilogue of one 128-pixel sub-tile (fp32 output, no residual, TW a power of two): the thread that
+// holds a pixel's 32 channels applies alpha / bias / activation in registers, writes them as the 128-byte row
+// `lane` of a 128B-swizzled 32 x 32 staging tile, and one elected lane hands the tile to the TMA engine. Edge
+// clipping (ragged tiles, channel tail) is the tensor map's bounds check; no per-thread global stores.
+template <int ACT>
+__device__ __forceinline__ void epilogue_subtile_tma(const ConvGemmParams& p, uint32_t taddr, uint32_t stg_addr, int lane,
+                                                     int n0, int x0, int y0, int img, uint32_t wait_bar,
+                                                     uint32_t wait_phase, bool do_wait) {
+  if (do_wait) {
+    mbar_wait(wait_bar, wait_phase, 4);
+    tc_fence_after();
+  }
+  const float alpha = p.alpha;
+  const uint32_t row_addr = stg_addr + static_cast<uint32_t>(lane) * 128u;
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+  for (int c0 = 0; c0 < p.BN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
+    tmem_ld_wait();
+    const int n = n0 + c0;
+    const bool do_act = n < p.act_cols;                 // act_cols is a multiple of 32 on this path
+    float v[32];
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias != nullptr && n + 4 * j4 < p.Cout) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j4));
+      v[4 * j4] = fmaf(__uint_as_float(r[4 * j4]), alpha, b4.x);
+      v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), alpha, b4.y);
+      v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), alpha, b4.z);
+      v[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), alpha, b4.w);
+    }
+    if (do_act) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = act_fn<ACT>(v[j]);
+    }
+    // the previous chunk's store must have finished reading the staging tile
+    if (elect_one_sync()) tma_store_wait_read<0>();
+    __syncwarp();
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const uint32_t a = row_addr + ((static_cast<uint32_t>(j4) ^ sw) << 4);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * j4]), "f"(v[4 * j4 + 1]),
+                   "f"(v[4 * j4 + 2]), "f"(v[4 * j4 + 3])
+                   : "memory");
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (elect_one_sync()) {
+      tma_store_4d(&p.tmC, stg_addr, n, x0, y0, img);
+      tma_store_commit();
+    }
+  }
+}
+
 // Scalar epilogue for shapes the vector path cannot take (Cout or strides not multiples of 4); fp32 only.
 __device__ __forceinline__ void epilogue_subtile_scalar(const ConvGemmParams& p, uint32_t taddr, int n0, bool row_ok,
                                                         long long o_off, long long r_off, int c_begin) {
@@ -420,7 +474,19 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
         const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxBN + m * 128) +
                                (static_cast<uint32_t>(q * 32) << 16);
         const bool do_wait = m == 0;
-        if (vec_ok) {
+        if (p.tma_store) {
+          // this warp's 32 pixels: rows q*32 .. q*32+31 of the sub-tile = a (min(TW,32) x 32/min(TW,32)) pixel box
+          const int r0 = q * 32;
+          const int bx = tx * p.TW + (r0 % p.TW);
+          const int by = ty * tile_rows + m * p.TH + r0 / p.TW;
+          const uint32_t stg_t = smem_stg + static_cast<uint32_t>(q) * 4096u;
+          switch (p.act) {
+            case ACT_RELU: epilogue_subtile_tma<ACT_RELU>(p, taddr, stg_t, lane, n0, bx, by, img, tfull_bar(acc), acc_phase, do_wait); break;
+            case ACT_LEAKY: epilogue_subtile_tma<ACT_LEAKY>(p, taddr, stg_t, lane, n0, bx, by, img, tfull_bar(acc), acc_phase, do_wait); break;
+            case ACT_ELU1: epilogue_subtile_tma<ACT_ELU1>(p, taddr, stg_t, lane, n0, bx, by, img, tfull_bar(acc), acc_phase, do_wait); break;
+            default: epilogue_subtile_tma<ACT_NONE>(p, taddr, stg_t, lane, n0, bx, by, img, tfull_bar(acc), acc_phase, do_wait); break;
+          }
+        } else if (vec_ok) {
           // rows this lane stores in the coalesced phase: staged row k*4+sub_r of this warp's 32 pixels
           long long off_o[8], off_r[8];
           uint32_t okmask = 0;
@@ -463,6 +529,9 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (it == 0 && threadIdx.x == 64) MFR_STAMP(7);
+    }
+    if (p.tma_store) {   // bulk stores are tracked per issuing thread: every lane may have been elected
+      tma_store_wait<0>();
     }
   }
 
@@ -534,7 +603,7 @@ RingCfg ring_cfg(int halo, int MT, int TW, int TH, int BN) {
 }
 
 TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, int pad, int kb_per_tap,
-                   int ksteps_last, bool allow_mt2) {
+                   int ksteps_last, bool allow_mt2, bool tma_store_ok) {
   const int sms = conv_gemm_num_sms();
   const int c16 = (Cout + 15) / 16 * 16;
   const int taps = R * S;
@@ -573,7 +642,9 @@ TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, in
                                       : static_cast<double>(tw) * th * MT * 128.0 * taps * kb_per_tap;
           const double b_bytes = static_cast<double>(BN) * 128.0 * taps * kb_per_tap;
           const double l2 = (a_bytes + b_bytes) / 100.0;
-          const double epi = MT * ((BN + 31) / 32) * 500.0;
+          // the TMA-store epilogue (fp32 out, power-of-two TW) costs roughly half of the STG one per chunk
+          const bool tma_epi = tma_store_ok && (tw & (tw - 1)) == 0 && tw >= 8 && tw * th == 128 && (BN % 32 == 0 || nt == 1);
+          const double epi = MT * ((BN + 31) / 32) * (tma_epi ? 250.0 : 500.0);
           const double t = std::max(mma, std::max(l2, epi)) + 800.0;
           const double cost = static_cast<double>((tiles + sms - 1) / sms) * t;
           if (cost < best.cost * (1.0 - 1e-9) || (cost < best.cost * (1.0 + 1e-9) && tw > best.TW)) {
@@ -633,7 +704,7 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
     p->ksteps_last = (tail + ummak - 1) / ummak;
   }
   const TileCfg cfg = choose_cfg(d.N, p->Ho, p->Wo, d.Cout, d.R, d.S, d.stride, d.pad, p->kb_per_tap, p->ksteps_last,
-                                 d.dyn_w == nullptr);
+                                 d.dyn_w == nullptr, !d.out_bf16 && d.residual == nullptr);
   p->TW = cfg.TW; p->TH = cfg.TH; p->MT = cfg.MT; p->halo = cfg.halo;
   p->BN = cfg.BN; p->n_tiles = cfg.n_tiles;
   p->tiles_x = (p->Wo + p->TW - 1) / p->TW;
@@ -677,6 +748,26 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
     if (r != CUDA_SUCCESS) {
       fprintf(stderr, "[mfr_b200] cuTensorMapEncodeTiled(A) failed: %d\n", (int)r);
       return MFR_ERR_CUDA;
+    }
+  }
+  {  // TMA-store epilogue: fp32 output without residual, power-of-two TW, whole 32-channel chunks per N tile
+    const bool pow2 = (p->TW & (p->TW - 1)) == 0;
+    const bool ok = !d.out_bf16 && d.residual == nullptr && pow2 && p->TW >= 8 && p->TW * p->TH == 128 &&
+                    (p->BN % 32 == 0 || p->n_tiles == 1) && (p->act_cols % 32 == 0 || p->act_cols >= d.Cout) &&
+                    (d.ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && (d.Cout % 4 == 0) &&
+                    (p->out_img_stride % 4 == 0) && (d.bias == nullptr || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0) &&
+                    getenv("MFR_CONV_NO_TMA_STORE") == nullptr;
+    p->tma_store = ok ? 1 : 0;
+    if (ok) {
+      const int bw = std::min(p->TW, 32);
+      cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)p->Wo, (cuuint64_t)p->Ho, (cuuint64_t)d.N};
+      cuuint64_t strides[3] = {(cuuint64_t)d.ldo * 4, (cuuint64_t)d.ldo * 4 * p->Wo, (cuuint64_t)p->out_img_stride * 4};
+      cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)(32 / bw), 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = enc(&p->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out, dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) p->tma_store = 0;   // e.g. strides the tensor map cannot express: keep the STG epilogue
     }
   }
   {  // weights: {Cin, Z, Cout}; Z = tap (shared weights) or image (batched B operand)

@@ -16,6 +16,7 @@ enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_ELU1 = 3 };
 struct alignas(64) ConvGemmParams {
   CUtensorMap tmA;  // rank 4 {C, W, H, N}   box {32|64, TW*s, MT*TH*s (halo: MT*TH+2), 1}, 128B swizzle, zero OOB fill
   CUtensorMap tmB;  // rank 3 {Cin, Z, Cout} box {32, 1, BN}          (Z = filter tap or image)
+  CUtensorMap tmC;  // rank 4 {Cout, Wo, Ho, N} fp32, box {32, min(TW,32), 32/min(TW,32), 1}, 128B swizzle (TMA-store epilogue)
   int N, Ho, Wo, Cout, Cin;
   int R, S, stride, pad;
   int TW, TH, tiles_x, tiles_y;
@@ -26,6 +27,7 @@ struct alignas(64) ConvGemmParams {
                           // ky taps read it at row offsets 0, TW, 2*TW (TW % 8 == 0 keeps the swizzle phase)
   int a_slots, b_slots;   // depth of the A ring / B ring (two rings: one A slot serves 3 B tiles in halo mode)
   int a_slot_bytes;
+  int tma_store;          // epilogue writes 32 px x 32 ch fp32 chunks with cp.async.bulk.tensor stores (see conv_gemm.cu)
   int cbatch;             // generic mode: k-blocks whose slots are released by one tcgen05.commit batch (pipe drain)
   int ksteps_last;        // MMAs issued for the last k-block of a tap (channel tail)
   int act, act_cols;    // activation applies to output channels < act_cols

@@ -63,9 +63,9 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   return v;
 }
 
-// block-wide sum of K doubles per thread (blockDim.x = 256); result valid in thread 0
+// block-wide sum of K doubles per thread (blockDim.x <= 512); result valid in thread 0
 template <int K>
-__device__ __forceinline__ void block_sum_256(double (&v)[K], double* sh /*[8*K]*/) {
+__device__ __forceinline__ void block_sum_256(double (&v)[K], double* sh /*[(blockDim.x / 32) * K]*/) {
 #pragma unroll
   for (int k = 0; k < K; ++k) v[k] = warp_sum_d(v[k]);
   const int w = threadIdx.x >> 5;
@@ -75,7 +75,7 @@ __device__ __forceinline__ void block_sum_256(double (&v)[K], double* sh /*[8*K]
   if (threadIdx.x == 0)
     for (int k = 0; k < K; ++k) {
       double s = 0.0;
-      for (int ww = 0; ww < 8; ++ww) s += sh[ww * K + k];
+      for (int ww = 0; ww < static_cast<int>(blockDim.x >> 5); ++ww) s += sh[ww * K + k];
       v[k] = s;
     }
   __syncthreads();
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kHypPerBlock) emat_hyp_kernel(
   const float thr2 = thr * thr;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int h = blockIdx.x * kHypPerBlock + threadIdx.x;
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;   // 32..128 hypotheses per block (host picks, to fill the SMs)
   double Ec[10][9];
   int ncand = 0;
   if (h < num_hyp) {
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kHypPerBlock) emat_hyp_kernel(
   __syncthreads();
   if (threadIdx.x == 0) {
     int bw = 0;
-    for (int w = 1; w < kHypPerBlock / 32; ++w)
+    for (int w = 1; w < static_cast<int>(blockDim.x) / 32; ++w)
       if (s_best[w].cost < s_best[bw].cost) bw = w;
     *out = s_best[bw];
   }
@@ -305,25 +305,31 @@ struct EmatShared {
   double bestR[9], bestt[3], best_cost;
   double c_R1[9], c_R2[9], c_t[3];
   double prev_cost, lambda;
-  double red[8 * 21];
+  double red[16 * 21];
   int hist[256];
   int cand[kLoTopK];
-  int ncand, cnt;
+  int ncand, cnt, done;
+};
+
+// one locally-optimised candidate: MSAC cost at the RANSAC threshold and its pose
+struct LoResult {
+  double cost, R[9], t[3];
 };
 
 // LM rounds on the Tukey-biweight M-estimator of the Sampson distance with cut-off sqrt(T2),
 // starting from (S.R, S.t); leaves the last accepted parameters there. All threads must call it.
-__device__ void emat_lm_round(EmatShared& S, const float4* pts, int N, double T2) {
-  if (threadIdx.x == 0) { S.lambda = 1e-6; S.prev_cost = 1e300; }
+__device__ void emat_lm_round(EmatShared& S, const float4* pts, int N, double T2, int step = 1) {
+  if (threadIdx.x == 0) { S.lambda = 1e-6; S.prev_cost = 1e300; S.done = 0; }
   __syncthreads();
   for (int it = 0; it <= kLoInner; ++it) {
+    if (S.done) break;   // converged: the accepted parameters are already in (prevR, prevt)
     double R[9], t[3], b1[3], b2[3];
     for (int k = 0; k < 9; ++k) R[k] = S.R[k];
     for (int k = 0; k < 3; ++k) t[k] = S.t[k];
     tangent_basis(t, b1, b2);
     double acc[21];
     for (int k = 0; k < 21; ++k) acc[k] = 0.0;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    for (int i = threadIdx.x * step; i < N; i += blockDim.x * step) {   // step > 1: every step-th correspondence
       double J[5];
       const double r = sampson_res_jac(R, t, b1, b2, pts[i], J);
       const double q = r * r / T2;
@@ -342,6 +348,7 @@ __device__ void emat_lm_round(EmatShared& S, const float4* pts, int N, double T2
     if (threadIdx.x == 0) {
       const double cost = acc[20];
       if (cost <= S.prev_cost) {  // accept the parameters that produced this pass
+        if (S.prev_cost - cost <= 1e-10 * cost) S.done = 1;   // no measurable progress any more
         S.prev_cost = cost;
         for (int k = 0; k < 9; ++k) S.prevR[k] = S.R[k];
         for (int k = 0; k < 3; ++k) S.prevt[k] = S.t[k];
@@ -423,35 +430,18 @@ __device__ double emat_msac(EmatShared& S, const float4* pts, int N, double thr2
   return r;
 }
 
-__global__ void __launch_bounds__(256) emat_final_kernel(
-    const float* __restrict__ kpts0, const float* __restrict__ kpts1, const int* __restrict__ offsets,
-    const float* __restrict__ K0s, const float* __restrict__ K1s, float pix_thr, int blocks_per_pair,
-    int max_pts, const HypResult* __restrict__ results, double* __restrict__ Rd, double* __restrict__ td,
-    float* __restrict__ Rf, float* __restrict__ tf, int* __restrict__ n_inl,
-    unsigned char* __restrict__ mask, int lo_enabled) {
-  extern __shared__ float4 s_pts[];
-  __shared__ EmatShared S;
-  const int pair = blockIdx.x;
+// Shared prologue of the two kernels below: points of the pair into shared memory, the kLoTopK
+// cheapest block winners (cheapest first) into S.cand. Returns N (0 = nothing to do).
+__device__ int emat_stage_in(EmatShared& S, float4* s_pts, const float* kpts0, const float* kpts1, const int* offsets,
+                             const float* K0, const float* K1, int pair, int max_pts, int blocks_per_pair,
+                             const HypResult* res) {
   const int n0 = offsets[pair];
-  const int Nall = offsets[pair + 1] - n0;
-  const int N = min(Nall, max_pts);
-  auto fail = [&]() {
-    for (int i = threadIdx.x; i < Nall; i += blockDim.x) mask[n0 + i] = 0;
-    if (threadIdx.x < 9) { Rf[9 * pair + threadIdx.x] = NAN; Rd[9 * pair + threadIdx.x] = NAN; }
-    if (threadIdx.x < 3) { tf[3 * pair + threadIdx.x] = NAN; td[3 * pair + threadIdx.x] = NAN; }
-    if (threadIdx.x == 0) n_inl[pair] = 0;
-  };
-  if (N < 5) { fail(); return; }
-  const float* K0 = K0s + 9 * pair;
-  const float* K1 = K1s + 9 * pair;
+  const int N = min(offsets[pair + 1] - n0, max_pts);
+  if (N < 5) return 0;
   const float* k0 = kpts0 + 2 * static_cast<size_t>(n0);
   const float* k1 = kpts1 + 2 * static_cast<size_t>(n0);
   for (int i = threadIdx.x; i < N; i += blockDim.x) s_pts[i] = normalise_pt(k0, k1, i, K0, K1);
-  const double thr = static_cast<double>(emat_threshold(pix_thr, K0, K1));
-  const double thr2 = thr * thr;
-  const HypResult* res = results + static_cast<size_t>(pair) * blocks_per_pair;
   if (threadIdx.x == 0) {
-    // the kLoTopK cheapest block winners, cheapest first
     int n = 0;
     for (int k = 0; k < blocks_per_pair; ++k) {
       if (!res[k].valid) continue;
@@ -464,30 +454,90 @@ __global__ void __launch_bounds__(256) emat_final_kernel(
       if (n < kLoTopK) ++n;
     }
     S.ncand = n;
-    S.best_cost = 1e300;
   }
   __syncthreads();
-  if (S.ncand == 0) { fail(); return; }
+  return S.ncand > 0 ? N : 0;
+}
 
-  const int ncand = lo_enabled ? S.ncand : 1;
-  for (int c = 0; c < ncand; ++c) {
-    if (threadIdx.x == 0)
-      for (int k = 0; k < 9; ++k) S.E[k] = res[S.cand[c]].model[k];
-    __syncthreads();
-    emat_choose_pose(S, s_pts, N, thr2);
-    if (lo_enabled) {
-      // cut-off shrinking from 3x to 1x the RANSAC threshold
-      const double sched[kLoRounds] = {3.0, 2.0, 1.5, 1.0, 1.0, 1.0};
-      for (int r = 0; r < kLoRounds; ++r) emat_lm_round(S, s_pts, N, sched[r] * sched[r] * thr2);
-    }
-    const double cost = emat_msac(S, s_pts, N, thr2);
-    if (threadIdx.x == 0 && cost < S.best_cost) {
-      S.best_cost = cost;
-      for (int k = 0; k < 9; ++k) S.bestR[k] = S.R[k];
-      for (int k = 0; k < 3; ++k) S.bestt[k] = S.t[k];
-    }
-    __syncthreads();
+// Local optimisation of ONE candidate per block: grid (pairs, kLoTopK). The candidates of a pair are
+// independent, so they run on different SMs instead of one after the other.
+constexpr int kLoThreads = 512;    // the LM passes are fp64-latency bound: more warps per pair
+constexpr int kLoMaxPts = 1024;    // correspondences used by the candidate LO rounds (strided subsample beyond that);
+                                   // the final tightening rounds and every cost / mask evaluation use all of them
+
+__global__ void __launch_bounds__(kLoThreads) emat_lo_kernel(
+    const float* __restrict__ kpts0, const float* __restrict__ kpts1, const int* __restrict__ offsets,
+    const float* __restrict__ K0s, const float* __restrict__ K1s, float pix_thr, int blocks_per_pair,
+    int max_pts, const HypResult* __restrict__ results, LoResult* __restrict__ lo_out, int lo_enabled) {
+  extern __shared__ float4 s_pts[];
+  __shared__ EmatShared S;
+  const int pair = blockIdx.x, c = blockIdx.y;
+  LoResult* out = lo_out + static_cast<size_t>(pair) * kLoTopK + c;
+  const float* K0 = K0s + 9 * pair;
+  const float* K1 = K1s + 9 * pair;
+  const HypResult* res = results + static_cast<size_t>(pair) * blocks_per_pair;
+  const int N = emat_stage_in(S, s_pts, kpts0, kpts1, offsets, K0, K1, pair, max_pts, blocks_per_pair, res);
+  if (N == 0 || c >= S.ncand || (!lo_enabled && c > 0)) {
+    if (threadIdx.x == 0) out->cost = 1e300;
+    return;
   }
+  const double thr = static_cast<double>(emat_threshold(pix_thr, K0, K1));
+  const double thr2 = thr * thr;
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 9; ++k) S.E[k] = res[S.cand[c]].model[k];
+  __syncthreads();
+  emat_choose_pose(S, s_pts, N, thr2);
+  if (lo_enabled) {
+    // cut-off shrinking from 3x to 1x the RANSAC threshold
+    const double sched[kLoRounds] = {3.0, 2.0, 1.5, 1.0, 1.0, 1.0};
+    const int step = (N + kLoMaxPts - 1) / kLoMaxPts;
+    for (int r = 0; r < kLoRounds; ++r) emat_lm_round(S, s_pts, N, sched[r] * sched[r] * thr2, step);
+  }
+  const double cost = emat_msac(S, s_pts, N, thr2);
+  if (threadIdx.x == 0) {
+    out->cost = cost;
+    for (int k = 0; k < 9; ++k) out->R[k] = S.R[k];
+    for (int k = 0; k < 3; ++k) out->t[k] = S.t[k];
+  }
+}
+
+__global__ void __launch_bounds__(kLoThreads) emat_final_kernel(
+    const float* __restrict__ kpts0, const float* __restrict__ kpts1, const int* __restrict__ offsets,
+    const float* __restrict__ K0s, const float* __restrict__ K1s, float pix_thr, int blocks_per_pair,
+    int max_pts, const HypResult* __restrict__ results, const LoResult* __restrict__ lo_out,
+    double* __restrict__ Rd, double* __restrict__ td,
+    float* __restrict__ Rf, float* __restrict__ tf, int* __restrict__ n_inl,
+    unsigned char* __restrict__ mask, int lo_enabled) {
+  extern __shared__ float4 s_pts[];
+  __shared__ EmatShared S;
+  const int pair = blockIdx.x;
+  const int n0 = offsets[pair];
+  const int Nall = offsets[pair + 1] - n0;
+  auto fail = [&]() {
+    for (int i = threadIdx.x; i < Nall; i += blockDim.x) mask[n0 + i] = 0;
+    if (threadIdx.x < 9) { Rf[9 * pair + threadIdx.x] = NAN; Rd[9 * pair + threadIdx.x] = NAN; }
+    if (threadIdx.x < 3) { tf[3 * pair + threadIdx.x] = NAN; td[3 * pair + threadIdx.x] = NAN; }
+    if (threadIdx.x == 0) n_inl[pair] = 0;
+  };
+  const float* K0 = K0s + 9 * pair;
+  const float* K1 = K1s + 9 * pair;
+  const HypResult* res = results + static_cast<size_t>(pair) * blocks_per_pair;
+  const int N = emat_stage_in(S, s_pts, kpts0, kpts1, offsets, K0, K1, pair, max_pts, blocks_per_pair, res);
+  if (N == 0) { fail(); return; }
+  const double thr = static_cast<double>(emat_threshold(pix_thr, K0, K1));
+  const double thr2 = thr * thr;
+  if (threadIdx.x == 0) {
+    // cheapest locally-optimised candidate, first one on ties (the order a sequential sweep would keep)
+    const LoResult* lo = lo_out + static_cast<size_t>(pair) * kLoTopK;
+    int bc = 0;
+    for (int c = 1; c < kLoTopK; ++c)
+      if (lo[c].cost < lo[bc].cost) bc = c;
+    S.best_cost = lo[bc].cost;
+    for (int k = 0; k < 9; ++k) S.bestR[k] = lo[bc].R[k];
+    for (int k = 0; k < 3; ++k) S.bestt[k] = lo[bc].t[k];
+  }
+  __syncthreads();
+  if (!(S.best_cost < 1e299)) { fail(); return; }
   if (threadIdx.x == 0) {
     for (int k = 0; k < 9; ++k) S.R[k] = S.bestR[k];
     for (int k = 0; k < 3; ++k) S.t[k] = S.bestt[k];
@@ -1245,6 +1295,7 @@ __global__ void __launch_bounds__(256) procrustes_final_kernel(
 struct PoseSolver {
   int max_pairs, max_pts, max_hyp;
   HypResult* results = nullptr;
+  void* lo_out = nullptr;   // LoResult[max_pairs][kLoTopK]
   double *Rd = nullptr, *td = nullptr, *Xw = nullptr, *X1w = nullptr;
   float* uv = nullptr;
   int *vidx = nullptr, *nvalid = nullptr;
@@ -1258,9 +1309,10 @@ int pose_solver_create(int max_pairs, int max_pts, int max_hyp, PoseSolver** out
   auto* s = new PoseSolver();
   s->max_pairs = max_pairs; s->max_pts = max_pts; s->max_hyp = max_hyp;
   s->total_pts = static_cast<size_t>(max_pairs) * max_pts;
-  const int blocks = (max_hyp + kHypPerBlock - 1) / kHypPerBlock;
+  const int blocks = (max_hyp + 31) / 32;   // the E-mat kernel may run with as few as 32 hypotheses per block
   bool ok = true;
   ok &= cudaMalloc(&s->results, sizeof(HypResult) * max_pairs * blocks) == cudaSuccess;
+  ok &= cudaMalloc(&s->lo_out, sizeof(LoResult) * max_pairs * kLoTopK) == cudaSuccess;
   ok &= cudaMalloc(&s->Rd, sizeof(double) * 9 * max_pairs) == cudaSuccess;
   ok &= cudaMalloc(&s->td, sizeof(double) * 3 * max_pairs) == cudaSuccess;
   ok &= cudaMalloc(&s->Xw, sizeof(double) * 3 * s->total_pts) == cudaSuccess;
@@ -1275,6 +1327,7 @@ int pose_solver_create(int max_pairs, int max_pts, int max_hyp, PoseSolver** out
   if (!attrs) {
     cudaFuncSetAttribute(emat_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
     cudaFuncSetAttribute(emat_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
+    cudaFuncSetAttribute(emat_lo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
     cudaFuncSetAttribute(scale_consensus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
     cudaFuncSetAttribute(pnp_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 20);
     cudaFuncSetAttribute(procrustes_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 24);
@@ -1286,7 +1339,7 @@ int pose_solver_create(int max_pairs, int max_pts, int max_hyp, PoseSolver** out
 
 void pose_solver_destroy(PoseSolver* s) {
   if (!s) return;
-  cudaFree(s->results); cudaFree(s->Rd); cudaFree(s->td); cudaFree(s->Xw); cudaFree(s->uv);
+  cudaFree(s->results); cudaFree(s->lo_out); cudaFree(s->Rd); cudaFree(s->td); cudaFree(s->Xw); cudaFree(s->uv);
   cudaFree(s->vidx); cudaFree(s->nvalid); cudaFree(s->dmin); cudaFree(s->dmin1); cudaFree(s->X1w);
   delete s;
 }
@@ -1299,12 +1352,18 @@ int emat_ransac(PoseSolver* s, const float* kpts0, const float* kpts1, const int
                 int lo_enabled, float* R, float* t, int* n_inl, unsigned char* mask, cudaStream_t st) {
   if (P < 1 || P > s->max_pairs || num_hyp < 1) return MFR_ERR_ARG;
   num_hyp = std::min(num_hyp, s->max_hyp);
-  const int blocks = (num_hyp + kHypPerBlock - 1) / kHypPerBlock;
+  // hypotheses per block: 128 when that already gives >= 2 blocks per SM, else down to one warp per block
+  int hpb = kHypPerBlock;
+  while (hpb > 32 && static_cast<long long>(P) * ((num_hyp + hpb - 1) / hpb) < 2LL * 148) hpb /= 2;
+  const int blocks = (num_hyp + hpb - 1) / hpb;
   const size_t smem = static_cast<size_t>(s->max_pts) * 16;
-  emat_hyp_kernel<<<dim3(blocks, P), kHypPerBlock, smem, st>>>(kpts0, kpts1, offsets, K0, K1, pix_thr, num_hyp,
-                                                               seed, s->max_pts, s->results);
-  emat_final_kernel<<<P, 256, smem, st>>>(kpts0, kpts1, offsets, K0, K1, pix_thr, blocks, s->max_pts,
-                                          s->results, s->Rd, s->td, R, t, n_inl, mask, lo_enabled);
+  emat_hyp_kernel<<<dim3(blocks, P), hpb, smem, st>>>(kpts0, kpts1, offsets, K0, K1, pix_thr, num_hyp,
+                                                      seed, s->max_pts, s->results);
+  emat_lo_kernel<<<dim3(P, kLoTopK), kLoThreads, smem, st>>>(kpts0, kpts1, offsets, K0, K1, pix_thr, blocks, s->max_pts,
+                                                      s->results, static_cast<LoResult*>(s->lo_out), lo_enabled);
+  emat_final_kernel<<<P, kLoThreads, smem, st>>>(kpts0, kpts1, offsets, K0, K1, pix_thr, blocks, s->max_pts,
+                                          s->results, static_cast<const LoResult*>(s->lo_out), s->Rd, s->td, R, t,
+                                          n_inl, mask, lo_enabled);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }

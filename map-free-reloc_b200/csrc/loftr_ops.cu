@@ -320,8 +320,8 @@ __global__ void __launch_bounds__(128) attn_windows_kernel(const float* __restri
                                                            float eps) {
   const int item = blockIdx.x;
   if (item >= *n_items_dev) return;
-  __shared__ float sQ[32][128];
-  __shared__ float sK[32][128];
+  __shared__ __align__(16) float sQ[32][128];
+  __shared__ __align__(16) float sK[32][128];
   const int t = threadIdx.x;
   const int hb = (t >> 4) << 4;  // first channel of this thread's head
   float vcol[T];
@@ -334,26 +334,33 @@ __global__ void __launch_bounds__(128) attn_windows_kernel(const float* __restri
     vcol[s] = __fdiv_rn(V[row * ldv + t], fT);
   }
   __syncthreads();
+  // shared memory is read 16 bytes at a time (the kernel is bound by shared-memory wavefronts otherwise)
   float kvc[16], ks[16];
 #pragma unroll
-  for (int d = 0; d < 16; ++d) {
-    float a = 0.f, b = 0.f;
+  for (int d = 0; d < 16; ++d) { kvc[d] = 0.f; ks[d] = 0.f; }
 #pragma unroll
-    for (int s = 0; s < T; ++s) {
-      const float kk = sK[s][hb + d];
-      a = fmaf(kk, vcol[s], a);
-      b += kk;
+  for (int s = 0; s < T; ++s) {
+    const float4* kr = reinterpret_cast<const float4*>(&sK[s][hb]);
+#pragma unroll
+    for (int d4 = 0; d4 < 4; ++d4) {
+      const float4 kk = kr[d4];
+      kvc[4 * d4] = fmaf(kk.x, vcol[s], kvc[4 * d4]);         ks[4 * d4] += kk.x;
+      kvc[4 * d4 + 1] = fmaf(kk.y, vcol[s], kvc[4 * d4 + 1]); ks[4 * d4 + 1] += kk.y;
+      kvc[4 * d4 + 2] = fmaf(kk.z, vcol[s], kvc[4 * d4 + 2]); ks[4 * d4 + 2] += kk.z;
+      kvc[4 * d4 + 3] = fmaf(kk.w, vcol[s], kvc[4 * d4 + 3]); ks[4 * d4 + 3] += kk.w;
     }
-    kvc[d] = a;
-    ks[d] = b;
   }
+#pragma unroll 5
   for (int l = 0; l < T; ++l) {
+    const float4* qr = reinterpret_cast<const float4*>(&sQ[l][hb]);
     float num = 0.f, den = 0.f;
 #pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      const float qq = sQ[l][hb + d];
-      num = fmaf(qq, kvc[d], num);
-      den = fmaf(qq, ks[d], den);
+    for (int d4 = 0; d4 < 4; ++d4) {
+      const float4 q = qr[d4];
+      num = fmaf(q.x, kvc[4 * d4], num);     den = fmaf(q.x, ks[4 * d4], den);
+      num = fmaf(q.y, kvc[4 * d4 + 1], num); den = fmaf(q.y, ks[4 * d4 + 1], den);
+      num = fmaf(q.z, kvc[4 * d4 + 2], num); den = fmaf(q.z, ks[4 * d4 + 2], den);
+      num = fmaf(q.w, kvc[4 * d4 + 3], num); den = fmaf(q.w, ks[4 * d4 + 3], den);
     }
     msg[(static_cast<size_t>(item) * T + l) * ldm + t] = num * (1.f / (den + eps)) * fT;
   }

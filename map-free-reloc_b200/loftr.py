@@ -173,6 +173,95 @@ def synthetic_state_dict(seed=0):
     return sd
 
 
+def functional_state_dict(coarse_scale=200.0, fine_scale=30.0, ln_gain=40.0):
+    """Hand-constructed LoFTR weights (reference state_dict names / shapes) that make the network a
+    working matcher on textured scenes, for benchmarking without the real checkpoints (which the
+    reference does not ship): every layer runs with its full shape and FLOPs, but the convolutions
+    implement a classical patch descriptor instead of learned features.
+
+    * stem: 7x7 Gaussian -> channel 0 = blurred image at 1/2 resolution (all values >= 0, so the
+      ReLUs are transparent; BatchNorms are identities);
+    * layer1: shift kernels build the 9x9 neighbourhood of channel 0 in other channels (fine
+      descriptor, 2 px sample spacing) while the residual path carries channel 0 on;
+    * layer2 / layer3.0.conv1: [1 2 1]^2 / 16 blur + stride 2 on channel 0 (down to 1/8), shortcut
+      convs zero; layer3: shift kernels build the 7x7 neighbourhood (8 px spacing);
+    * layer3_outconv / layer1_outconv2.3: centring matrices (sample - patch mean) and a scale; the
+      FPN top-down branches are zeroed;
+    * coarse transformer layer 0: message zeroed (norm1 gain 0), MLP = identity (relu(x) - relu(-x)),
+      norm2 gain ``ln_gain`` -> x + g * LayerNorm(x): tokens get (almost) unit norm, so the dual
+      softmax matches by normalised cross-correlation; the other layers are identities;
+    * fine level: merge_feat passes the window features through, transformer identity.
+    """
+    sd = {k: torch.zeros(shp) for k, shp in _state_dict_shapes().items()}
+    for k in sd:                                                       # identity BatchNorms / LayerNorm gains off
+        if k.endswith("running_var"):
+            sd[k] = torch.ones_like(sd[k])
+        elif (".bn" in k or "downsample.1" in k or "outconv2.1" in k) and k.endswith(".weight"):
+            sd[k] = torch.ones_like(sd[k])
+    ax = torch.arange(7, dtype=torch.float32) - 3
+    g1 = torch.exp(-ax ** 2 / (2 * 1.5 ** 2)); g1 = g1 / g1.sum()
+    sd["backbone.conv1.weight"][0, 0] = g1[:, None] * g1[None, :]
+    b3 = torch.tensor([1.0, 2.0, 1.0]) / 4
+    blur3 = b3[:, None] * b3[None, :]
+
+    def shift_kernel(dy, dx):            # out(y, x) = in(y + dy, x + dx)  (cross-correlation convention)
+        k = torch.zeros(3, 3); k[1 + dy, 1 + dx] = 1.0
+        return k
+
+    def grow(w, src, dst_base):
+        """src: {offset: channel}; add a ring: every offset within max|o|+1 gets a channel >= dst_base
+        fed from a neighbouring source offset through a one-hot 3x3 kernel. Returns {offset: channel}."""
+        r = max(max(abs(a), abs(b)) for a, b in src) + 1
+        out = {}
+        c = dst_base
+        for oy in range(-r, r + 1):
+            for ox in range(-r, r + 1):
+                sy, sx = max(-r + 1, min(r - 1, oy)), max(-r + 1, min(r - 1, ox))
+                w[c, src[(sy, sx)]] = shift_kernel(oy - sy, ox - sx)
+                out[(oy, ox)] = c
+                c += 1
+        return out
+
+    # ---- layer1 (1/2 res, 128 ch): ch 0 = blurred image, fine-descriptor samples in 1.. ; residual keeps ch 0
+    o = grow(sd["backbone.layer1.0.conv1.weight"], {(0, 0): 0}, 1)             # 3x3  -> internal ch 1..9
+    o = grow(sd["backbone.layer1.0.conv2.weight"], o, 1)                       # 5x5  -> x ch 1..25
+    o = grow(sd["backbone.layer1.1.conv1.weight"], o, 1)                       # 7x7  -> internal ch 1..49
+    fine = grow(sd["backbone.layer1.1.conv2.weight"], o, 26)                   # 9x9  -> x1 ch 26..106
+    # ---- layer2 / layer3: blur + subsample channel 0, then the 7x7 neighbourhood at 1/8
+    sd["backbone.layer2.0.conv1.weight"][0, 0] = blur3
+    sd["backbone.layer2.0.conv2.weight"][0, 0] = shift_kernel(0, 0)
+    sd["backbone.layer3.0.conv1.weight"][0, 0] = blur3
+    o = grow(sd["backbone.layer3.0.conv2.weight"], {(0, 0): 0}, 0)             # 3x3 -> x ch 0..8
+    o = grow(sd["backbone.layer3.1.conv1.weight"], o, 0)                       # 5x5 -> internal ch 0..24
+    coarse = grow(sd["backbone.layer3.1.conv2.weight"], o, 9)                  # 7x7 -> x3 ch 9..57 (0..8 keep the 3x3)
+    nc = len(coarse)
+    cen = (torch.eye(nc) - torch.full((nc, nc), 1.0 / nc)) * coarse_scale
+    chans = [coarse[k] for k in sorted(coarse)]
+    for r_ in range(nc):
+        for c_ in range(nc):
+            sd["backbone.layer3_outconv.weight"][r_, chans[c_], 0, 0] = cen[r_, c_]
+    # ---- fine branch: select the 81 samples, identity 3x3 (centre tap), centring + scale
+    fch = [fine[k] for k in sorted(fine)]
+    nf = len(fch)
+    for r_ in range(nf):
+        sd["backbone.layer1_outconv.weight"][r_, fch[r_], 0, 0] = 1.0
+        sd["backbone.layer1_outconv2.0.weight"][r_, r_, 1, 1] = 1.0
+    cenf = (torch.eye(nf) - torch.full((nf, nf), 1.0 / nf)) * fine_scale
+    sd["backbone.layer1_outconv2.3.weight"][:nf, :nf, 1, 1] = cenf
+    # ---- transformers
+    for pre, c, nl in (("loftr_coarse", 256, 8), ("loftr_fine", 128, 2)):
+        for i in range(nl):
+            p = f"{pre}.layers.{i}"
+            w0 = torch.zeros(2 * c, 2 * c); w0[:c, :c] = torch.eye(c); w0[c:, :c] = -torch.eye(c)
+            sd[p + ".mlp.0.weight"] = w0
+            sd[p + ".mlp.2.weight"] = torch.cat([torch.eye(c), -torch.eye(c)], 1)
+            for nme in ("q_proj", "k_proj", "v_proj", "merge"):     # attention runs, its message is gated off by norm1
+                sd[f"{p}.{nme}.weight"] = torch.eye(c)
+    sd["loftr_coarse.layers.0.norm2.weight"] = torch.full((256,), float(ln_gain))
+    sd["fine_preprocess.merge_feat.weight"] = torch.cat([torch.eye(128), torch.zeros(128, 128)], 1)
+    return {k: v.float().contiguous() for k, v in sd.items()}
+
+
 class LoFTR:
     """CUDA LoFTR engine for ``batch`` pairs of [H, W] images (H, W multiples of 8)."""
 

@@ -6,15 +6,15 @@ import numpy as np, torch
 import mfr_b200
 from mfr_b200 import loftr, synth, pose_solver
 B = int(os.environ.get("B", 4)); H, W = 720, 544
-eng = loftr.LoFTR(loftr.synthetic_state_dict(0), batch=B, height=H, width=W, cfg={"thr": 0.2}, graph=False,
+eng = loftr.LoFTR(loftr.functional_state_dict(), batch=B, height=H, width=W, cfg={"thr": 0.2}, graph=False,
                   precision=os.environ.get("PRECISION", "bf16"))
 be = pose_solver.PoseBackend(max_pairs=B, max_pts=(H // 8) * (W // 8), max_hyp=1024)
-p = synth.make_pair(0)
-g0 = torch.from_numpy(synth.rgb_to_gray_u8(p["image0"]).astype(np.float32) / 255.0)[None].repeat(B, 1, 1).cuda()
-g1 = torch.from_numpy(synth.rgb_to_gray_u8(p["image1"]).astype(np.float32) / 255.0)[None].repeat(B, 1, 1).cuda()
-d0 = torch.from_numpy(p["depth0"].astype(np.float32))[None].repeat(B, 1, 1).cuda()
-d1 = torch.from_numpy(p["depth1"].astype(np.float32))[None].repeat(B, 1, 1).cuda()
-K = torch.from_numpy(np.asarray(p["K_color0"], np.float32))[None].repeat(B, 1, 1).cuda().contiguous()
+ps = [synth.make_pair(1000 + b) for b in range(B)]
+g0 = torch.from_numpy(np.stack([synth.rgb_to_gray_u8(p["image0"]).astype(np.float32) / 255.0 for p in ps])).cuda()
+g1 = torch.from_numpy(np.stack([synth.rgb_to_gray_u8(p["image1"]).astype(np.float32) / 255.0 for p in ps])).cuda()
+d0 = torch.from_numpy(np.stack([p["depth0"] for p in ps]).astype(np.float32)).cuda()
+d1 = torch.from_numpy(np.stack([p["depth1"] for p in ps]).astype(np.float32)).cuda()
+K = torch.from_numpy(np.stack([p["K_color0"] for p in ps]).astype(np.float32)).cuda().contiguous()
 outs = eng.device_outputs()
 for it in range(2):
     eng.forward_async(g0, g1)
