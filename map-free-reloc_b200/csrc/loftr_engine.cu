@@ -115,11 +115,16 @@ struct LoftrEngine {
     d.in_bf16 = in_bf16; d.out_bf16 = out_bf16;
     if (in_bf16) {   // bf16 copy of the weights, Cin padded to a multiple of 8 (16-byte TMA strides)
       const int cin_pad = (Cin + 7) / 8 * 8;
-      Bf16Conv bc{wname, Cout, R * R, Cin, cin_pad, w16_total};
-      bf16_convs.push_back(bc);
-      w16_total += (static_cast<size_t>(Cout) * R * R * cin_pad + 63) / 64 * 64;
+      size_t off = w16_total;
+      bool found = false;
+      for (const auto& e : bf16_convs)
+        if (e.name == wname) { off = e.off; found = true; }     // cross layers build the same weights twice
+      if (!found) {
+        bf16_convs.push_back(Bf16Conv{wname, Cout, R * R, Cin, cin_pad, off});
+        w16_total += (static_cast<size_t>(Cout) * R * R * cin_pad + 63) / 64 * 64;
+      }
       d.ldw = cin_pad;
-      w_override = reinterpret_cast<const float*>(wblob16 + bc.off);
+      w_override = reinterpret_cast<const float*>(wblob16 + off);
     }
     d.w = w_override ? w_override : W_(wname + ".w");
     d.Cout = Cout; d.R = R; d.S = R; d.stride = stride; d.pad = R / 2;
@@ -191,32 +196,38 @@ struct LoftrEngine {
                      const int* dyn_rows, const int* dyn_items, bool windows) {
     float* wq = W_(p + ".qkv.w");
     const long long ld2 = 2 * C, ld3 = 3 * C;
+    // bf16 mode: the big intermediates (q|k|v, attention message, MLP hidden) are stored in bf16 — these GEMMs and
+    // the attention kernels are HBM-bound — while the residual stream, LayerNorm inputs and outputs stay fp32.
+    // The buffers are float-typed: `tb` bf16 elements per float when converting element offsets.
+    const int tbf = precision == 1 ? 1 : 0, tb = tbf ? 2 : 1;
+    auto E = [tb](float* ptr, size_t elems) { return ptr + elems / tb; };
     if (x == src) {
-      conv("", x, n, 1, rows, C, ld2, 3 * C, 1, 1, false, nullptr, ACT_ELU1, qkv_x, ld3, 2 * C, dyn_rows, wq);
+      conv("", x, n, 1, rows, C, ld2, 3 * C, 1, 1, false, nullptr, ACT_ELU1, qkv_x, ld3, 2 * C, dyn_rows, wq, nullptr, 0, tbf);
     } else {
-      conv("", x, n, 1, rows, C, ld2, C, 1, 1, false, nullptr, ACT_ELU1, qkv_x, ld3, C, dyn_rows, wq);
-      conv("", src, n, 1, rows, C, ld2, 2 * C, 1, 1, false, nullptr, ACT_ELU1, qkv_s + C, ld3, C, dyn_rows,
-           wq + static_cast<size_t>(C) * C);
+      conv("", x, n, 1, rows, C, ld2, C, 1, 1, false, nullptr, ACT_ELU1, qkv_x, ld3, C, dyn_rows, wq, nullptr, 0, tbf);
+      conv("", src, n, 1, rows, C, ld2, 2 * C, 1, 1, false, nullptr, ACT_ELU1, E(qkv_s, C), ld3, C, dyn_rows,
+           wq + static_cast<size_t>(C) * C, nullptr, 0, tbf);
     }
     if (!windows) {
       float* kvp_ = kvp; float* kv_ = kv;
       const int Lr = rows, sk = splits_kv * NI / n;   // same partial-buffer footprint for n = B or n = 2B images
+      float *kp = E(qkv_s, C), *vp = E(qkv_s, 2 * C);
       push("attn_long", [=](cudaStream_t st) {
-        return linear_attention_long(qkv_x, ld3, qkv_s + C, ld3, qkv_s + 2 * C, ld3, msg_x, C, kvp_, kv_, n,
-                                     Lr, Lr, 8, 32, sk, st);
+        return linear_attention_long(qkv_x, ld3, kp, ld3, vp, ld3, msg_x, C, kvp_, kv_, n, Lr, Lr, 8, 32, sk, st, tbf);
       }, 3);
     } else {
       const int items_cap = rows / 25;
       for (int side = 0; side < n; ++side) {
         const size_t off3 = static_cast<size_t>(side) * rows * ld3;
         const size_t off1 = static_cast<size_t>(side) * rows * C;
+        float *qp = E(qkv_x, off3), *kp = E(qkv_s, off3 + C), *vp = E(qkv_s, off3 + 2 * C), *mp = E(msg_x, off1);
         push("attn_windows", [=](cudaStream_t st) {
-          return linear_attention_windows(qkv_x + off3, ld3, qkv_s + off3 + C, ld3, qkv_s + off3 + 2 * C, ld3,
-                                          msg_x + off1, C, dyn_items, items_cap, 25, st);
+          return linear_attention_windows(qp, ld3, kp, ld3, vp, ld3, mp, C, dyn_items, items_cap, 25, st, tbf);
         });
       }
     }
-    conv(p + ".merge", msg_x, n, 1, rows, C, C, C, 1, 1, false, nullptr, ACT_NONE, mrg_x, C, 0, dyn_rows);
+    conv(p + ".merge", msg_x, n, 1, rows, C, C, C, 1, 1, false, nullptr, ACT_NONE, mrg_x, C, 0, dyn_rows, nullptr, nullptr,
+         tbf, 0);
     const float *g1 = W_(p + ".norm1.g"), *b1 = W_(p + ".norm1.b");
     const float *g2 = W_(p + ".norm2.g"), *b2 = W_(p + ".norm2.b");
     const long long tot = static_cast<long long>(n) * rows;
@@ -232,8 +243,10 @@ struct LoftrEngine {
         });
       }
     }
-    conv(p + ".mlp0", x, n, 1, rows, 2 * C, ld2, 2 * C, 1, 1, false, nullptr, ACT_RELU, h1_x, ld2, 0, dyn_rows);
-    conv(p + ".mlp2", h1_x, n, 1, rows, 2 * C, ld2, C, 1, 1, false, nullptr, ACT_NONE, h2_x, C, 0, dyn_rows);
+    conv(p + ".mlp0", x, n, 1, rows, 2 * C, ld2, 2 * C, 1, 1, false, nullptr, ACT_RELU, h1_x, ld2, 0, dyn_rows, nullptr,
+         nullptr, 0, tbf);
+    conv(p + ".mlp2", h1_x, n, 1, rows, 2 * C, ld2, C, 1, 1, false, nullptr, ACT_NONE, h2_x, C, 0, dyn_rows, nullptr,
+         nullptr, tbf, 0);
     if (dyn_rows == nullptr) {
       push("layernorm", [=](cudaStream_t st) {
         return layernorm_rows(h2_x, C, g2, b2, x, ld2, x, ld2, tot, C, nullptr, st);
@@ -273,7 +286,7 @@ struct LoftrEngine {
     };
     // the bf16 weight blob must exist before the conv steps are built (its size is known only afterwards:
     // reserve the upper bound = all backbone conv weights)
-    if (bf) wblob16 = alloc<unsigned short>(static_cast<size_t>(8) * 1024 * 1024, "weights_bf16");
+    if (bf) wblob16 = alloc<unsigned short>(static_cast<size_t>(12) * 1024 * 1024, "weights_bf16");
     a0 = balloc(px2 * 128, "a0"); a1 = balloc(px2 * 128, "a1"); a2 = balloc(px2 * 128, "a2");
     b0 = balloc(px4 * c196, "b0"); b1 = balloc(px4 * c196, "b1"); b2 = balloc(px4 * c196, "b2");
     c0 = balloc(px8 * 256, "c0"); c1 = balloc(px8 * 256, "c1"); c2 = balloc(px8 * 256, "c2");
@@ -350,7 +363,7 @@ struct LoftrEngine {
     }
     bconv("layer1_outconv2.0", p2a, H2, W2, 196, c196, 196, 3, 1, true, nullptr, ACT_LEAKY, p2b, c196, B16);
     bconv("layer1_outconv2.3", p2b, H2, W2, 196, c196, 128, 3, 1, false, nullptr, ACT_NONE, featf, 128, 0);   // fp32 out
-    if (bf && w16_total > static_cast<size_t>(8) * 1024 * 1024) {
+    if (bf && w16_total > static_cast<size_t>(12) * 1024 * 1024) {
       fprintf(stderr, "[mfr_b200] bf16 weight blob too small\n");
       return MFR_ERR_ARG;
     }
@@ -367,10 +380,11 @@ struct LoftrEngine {
       if (i % 2 == 0) {  // self: both image sets at once
         encoder_layer(p, 256, tok, tok, qkv, qkv, msg, mrg, h1, h2, NI, L, nullptr, nullptr, false);
       } else {  // cross: feat0 <- (feat0, feat1), then feat1 <- (feat1, updated feat0)
-        encoder_layer(p, 256, tok, tok + half_tok, qkv, qkv + half_qkv, msg, mrg, h1, h2, B, L, nullptr,
+        const int tb = precision == 1 ? 2 : 1;   // qkv / msg / h1 hold bf16 in that mode (see encoder_layer)
+        encoder_layer(p, 256, tok, tok + half_tok, qkv, qkv + half_qkv / tb, msg, mrg, h1, h2, B, L, nullptr,
                       nullptr, false);
-        encoder_layer(p, 256, tok + half_tok, tok, qkv + half_qkv, qkv, msg + half_c, mrg + half_c,
-                      h1 + half_2c, h2 + half_c, B, L, nullptr, nullptr, false);
+        encoder_layer(p, 256, tok + half_tok, tok, qkv + half_qkv / tb, qkv, msg + half_c / tb, mrg + half_c,
+                      h1 + half_2c / tb, h2 + half_c, B, L, nullptr, nullptr, false);
       }
     }
 
@@ -416,10 +430,11 @@ struct LoftrEngine {
                    s_c = static_cast<size_t>(rows) * 128, s_2c = static_cast<size_t>(rows) * 256;
       encoder_layer("fine.0", 128, ftok, ftok, fqkv, fqkv, fmsg, fmrg, fh1, fh2, 2, rows, cm.m_total + 2,
                     cm.m_total, true);
-      encoder_layer("fine.1", 128, ftok, ftok + s_tok, fqkv, fqkv + s_qkv, fmsg, fmrg, fh1, fh2, 1, rows,
+      const int tb = precision == 1 ? 2 : 1;   // qkv / msg / h1 hold bf16 in that mode (see encoder_layer)
+      encoder_layer("fine.1", 128, ftok, ftok + s_tok, fqkv, fqkv + s_qkv / tb, fmsg, fmrg, fh1, fh2, 1, rows,
                     cm.m_total + 2, cm.m_total, true);
-      encoder_layer("fine.1", 128, ftok + s_tok, ftok, fqkv + s_qkv, fqkv, fmsg + s_c, fmrg + s_c, fh1 + s_2c,
-                    fh2 + s_c, 1, rows, cm.m_total + 2, cm.m_total, true);
+      encoder_layer("fine.1", 128, ftok + s_tok, ftok, fqkv + s_qkv / tb, fqkv, fmsg + s_c / tb, fmrg + s_c,
+                    fh1 + s_2c / tb, fh2 + s_c, 1, rows, cm.m_total + 2, cm.m_total, true);
       CoarseMatchBuffers cmb = cm; float *f0 = ftok, *f1 = ftok + s_tok, *mk = mk1f, *ex = expec;
       const int Mc = Mcap; const float scale_f = static_cast<float>(H) / static_cast<float>(H2);
       push("fine_match", [=](cudaStream_t st) {

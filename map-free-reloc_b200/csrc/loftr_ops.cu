@@ -175,24 +175,60 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// rows [r0, r0+kSlab) of a [rows][256] fp32 matrix (row stride ld) -> dst[kSlab][256]; rows >= r_end zero-filled
-__device__ __forceinline__ void slab_load(float* dst, const float* __restrict__ src, long long ld, long long r0,
+// rows [r0, r0+kSlab) of a [rows][256] matrix (fp32 or bf16, row stride ld elements) -> dst[kSlab][256];
+// rows >= r_end are zero-filled
+template <bool BF>
+__device__ __forceinline__ void slab_load(void* dst, const void* __restrict__ src, long long ld, long long r0,
                                           long long r_end, int t) {
+  constexpr int kChunks = BF ? 32 : 64;             // 16-byte chunks per row
+  constexpr int kEs = BF ? 2 : 4;
 #pragma unroll
-  for (int i = 0; i < kSlab * 64 / 256; ++i) {
+  for (int i = 0; i < kSlab * kChunks / 256; ++i) {
     const int c = t + 256 * i;
-    const int r = c >> 6, col = (c & 63) * 4;
+    const int r = c / kChunks, ch = c % kChunks;
     const bool ok = r0 + r < r_end;
-    cp_async16(dst + r * 256 + col, src + (ok ? (r0 + r) : r0) * ld + col, ok);
+    cp_async16(static_cast<char*>(dst) + (r * kChunks + ch) * 16,
+               static_cast<const char*>(src) + ((ok ? (r0 + r) : r0) * ld) * kEs + ch * 16, ok);
+  }
+}
+// element t of row r / the 32 channels of head h of row r, from a staged slab
+template <bool BF>
+__device__ __forceinline__ float slab_elem(const void* slab, int r, int t) {
+  if constexpr (BF) return bf2f(static_cast<const unsigned short*>(slab)[r * 256 + t]);
+  else return static_cast<const float*>(slab)[r * 256 + t];
+}
+template <bool BF>
+__device__ __forceinline__ void slab_head(const void* slab, int r, int h, float (&o)[32]) {
+  if constexpr (BF) {
+    const uint4* p = reinterpret_cast<const uint4*>(static_cast<const unsigned short*>(slab) + r * 256 + h * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 u = p[q];
+      const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[8 * q + 2 * e] = __uint_as_float(w[e] << 16);
+        o[8 * q + 2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+      }
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(slab) + r * 256 + h * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 f = p[q];
+      o[4 * q] = f.x; o[4 * q + 1] = f.y; o[4 * q + 2] = f.z; o[4 * q + 3] = f.w;
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) kv_partial_kernel(const float* __restrict__ K, long long ldk,
-                                                         const float* __restrict__ V, long long ldv,
+template <bool BF>
+__global__ void __launch_bounds__(256) kv_partial_kernel(const void* __restrict__ K, long long ldk,
+                                                         const void* __restrict__ V, long long ldv,
                                                          float* __restrict__ kv_part, int S, int splits) {
   extern __shared__ __align__(16) float att_smem[];
-  float* sK = att_smem;                                   // [stages][kSlab][256]
-  float* sV = att_smem + kAttStages * kSlab * 256;        // [stages][kSlab][256]
+  constexpr int kSlabBytes = kSlab * 256 * (BF ? 2 : 4);
+  char* sK = reinterpret_cast<char*>(att_smem);                          // [stages][kSlab][256]
+  char* sV = reinterpret_cast<char*>(att_smem) + kAttStages * kSlabBytes;
   const int split = blockIdx.x, n = blockIdx.y;
   const int chunk = (S + splits - 1) / splits;
   const int s_beg = split * chunk, s_end = min(S, s_beg + chunk);
@@ -207,8 +243,8 @@ __global__ void __launch_bounds__(256) kv_partial_kernel(const float* __restrict
 #pragma unroll
   for (int st = 0; st < kAttStages - 1; ++st) {
     if (st < nslab) {
-      slab_load(sK + st * kSlab * 256, K, ldk, base + s_beg + st * kSlab, base + s_end, t);
-      slab_load(sV + st * kSlab * 256, V, ldv, base + s_beg + st * kSlab, base + s_end, t);
+      slab_load<BF>(sK + st * kSlabBytes, K, ldk, base + s_beg + st * kSlab, base + s_end, t);
+      slab_load<BF>(sV + st * kSlabBytes, V, ldv, base + s_beg + st * kSlab, base + s_end, t);
     }
     cp_async_commit();
   }
@@ -219,26 +255,21 @@ __global__ void __launch_bounds__(256) kv_partial_kernel(const float* __restrict
       const int nx = i + kAttStages - 1;
       if (nx < nslab) {
         const int st = nx % kAttStages;
-        slab_load(sK + st * kSlab * 256, K, ldk, base + s_beg + nx * kSlab, base + s_end, t);
-        slab_load(sV + st * kSlab * 256, V, ldv, base + s_beg + nx * kSlab, base + s_end, t);
+        slab_load<BF>(sK + st * kSlabBytes, K, ldk, base + s_beg + nx * kSlab, base + s_end, t);
+        slab_load<BF>(sV + st * kSlabBytes, V, ldv, base + s_beg + nx * kSlab, base + s_end, t);
       }
       cp_async_commit();
     }
-    const float* k0 = sK + (i % kAttStages) * kSlab * 256;
-    const float* v0 = sV + (i % kAttStages) * kSlab * 256;
-#pragma unroll
+    const char* k0 = sK + (i % kAttStages) * kSlabBytes;
+    const char* v0 = sV + (i % kAttStages) * kSlabBytes;
+#pragma unroll 4
     for (int r = 0; r < kSlab; ++r) {
-      const float vv = __fdiv_rn(v0[r * 256 + t], fS);     // values / v_length (linear_attention.py:40)
-      const float4* kr = reinterpret_cast<const float4*>(k0 + r * 256 + h * 32);
+      const float vv = __fdiv_rn(slab_elem<BF>(v0, r, t), fS);     // values / v_length (linear_attention.py:40)
+      float kk[32];
+      slab_head<BF>(k0, r, h, kk);
 #pragma unroll
-      for (int d4 = 0; d4 < 8; ++d4) {
-        const float4 kk = kr[d4];
-        acc[4 * d4] = fmaf(kk.x, vv, acc[4 * d4]);
-        acc[4 * d4 + 1] = fmaf(kk.y, vv, acc[4 * d4 + 1]);
-        acc[4 * d4 + 2] = fmaf(kk.z, vv, acc[4 * d4 + 2]);
-        acc[4 * d4 + 3] = fmaf(kk.w, vv, acc[4 * d4 + 3]);
-      }
-      ks += k0[r * 256 + t];
+      for (int d = 0; d < 32; ++d) acc[d] = fmaf(kk[d], vv, acc[d]);
+      ks += slab_elem<BF>(k0, r, t);
     }
   }
   float* o = kv_part + ((static_cast<size_t>(n) * splits + split) * 8 + h) * 1056;
@@ -258,12 +289,14 @@ __global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict_
   kv[static_cast<size_t>(n) * 8448 + e] = s;
 }
 
-__global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict__ Q, long long ldq,
+template <bool BF>
+__global__ void __launch_bounds__(256) attn_apply_kernel(const void* __restrict__ Q, long long ldq,
                                                          const float* __restrict__ kv,
-                                                         float* __restrict__ msg, long long ldm, int L,
+                                                         void* __restrict__ msg, long long ldm, int L,
                                                          int S, float eps, int splits) {
   extern __shared__ __align__(16) float att_smem[];
-  float* sQ = att_smem;                                   // [stages][kSlab][256]
+  constexpr int kSlabBytes = kSlab * 256 * (BF ? 2 : 4);
+  char* sQ = reinterpret_cast<char*>(att_smem);                           // [stages][kSlab][256]
   const int n = blockIdx.y;
   const int chunk = (L + splits - 1) / splits;
   const int l_beg = blockIdx.x * chunk, l_end = min(L, l_beg + chunk);
@@ -272,7 +305,7 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict
   const long long base = static_cast<long long>(n) * L;
 #pragma unroll
   for (int st = 0; st < kAttStages - 1; ++st) {
-    if (st < nslab) slab_load(sQ + st * kSlab * 256, Q, ldq, base + l_beg + st * kSlab, base + l_end, t);
+    if (st < nslab) slab_load<BF>(sQ + st * kSlabBytes, Q, ldq, base + l_beg + st * kSlab, base + l_end, t);
     cp_async_commit();
   }
   const float* kvh = kv + (static_cast<size_t>(n) * 8 + h) * 1056;
@@ -286,36 +319,34 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict
     __syncthreads();
     {
       const int nx = i + kAttStages - 1;
-      if (nx < nslab) slab_load(sQ + (nx % kAttStages) * kSlab * 256, Q, ldq, base + l_beg + nx * kSlab, base + l_end, t);
+      if (nx < nslab) slab_load<BF>(sQ + (nx % kAttStages) * kSlabBytes, Q, ldq, base + l_beg + nx * kSlab, base + l_end, t);
       cp_async_commit();
     }
-    const float* q0 = sQ + (i % kAttStages) * kSlab * 256;
+    const char* q0 = sQ + (i % kAttStages) * kSlabBytes;
     const int cnt = min(kSlab, l_end - l_beg - i * kSlab);
 #pragma unroll 4
     for (int r = 0; r < cnt; ++r) {
-      const float4* qr = reinterpret_cast<const float4*>(q0 + r * 256 + h * 32);
+      float qq[32];
+      slab_head<BF>(q0, r, h, qq);
       float a = 0.f;
 #pragma unroll
-      for (int d4 = 0; d4 < 8; ++d4) {
-        const float4 q = qr[d4];
-        a = fmaf(q.x, kvr[4 * d4], a);
-        a = fmaf(q.y, kvr[4 * d4 + 1], a);
-        a = fmaf(q.z, kvr[4 * d4 + 2], a);
-        a = fmaf(q.w, kvr[4 * d4 + 3], a);
-      }
-      const float den = warp_sum(q0[r * 256 + t] * ksum);
-      msg[(base + l_beg + i * kSlab + r) * ldm + t] = a * (1.f / (den + eps)) * fS;
+      for (int d = 0; d < 32; ++d) a = fmaf(qq[d], kvr[d], a);
+      const float den = warp_sum(slab_elem<BF>(q0, r, t) * ksum);
+      const float o = a * (1.f / (den + eps)) * fS;
+      const long long oi = (base + l_beg + i * kSlab + r) * ldm + t;
+      if constexpr (BF) static_cast<unsigned short*>(msg)[oi] = f2bf(o);
+      else static_cast<float*>(msg)[oi] = o;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------ linear attention (windows)
 // C = 128 (8 heads x 16), T tokens per item (T <= 32). One block (128 threads) per item.
-template <int T>
-__global__ void __launch_bounds__(128) attn_windows_kernel(const float* __restrict__ Q, long long ldq,
-                                                           const float* __restrict__ K, long long ldk,
-                                                           const float* __restrict__ V, long long ldv,
-                                                           float* __restrict__ msg, long long ldm,
+template <int T, bool BF>
+__global__ void __launch_bounds__(128) attn_windows_kernel(const void* __restrict__ Qv, long long ldq,
+                                                           const void* __restrict__ Kv, long long ldk,
+                                                           const void* __restrict__ Vv, long long ldv,
+                                                           void* __restrict__ msgv, long long ldm,
                                                            const int* __restrict__ n_items_dev,
                                                            float eps) {
   const int item = blockIdx.x;
@@ -329,9 +360,15 @@ __global__ void __launch_bounds__(128) attn_windows_kernel(const float* __restri
 #pragma unroll
   for (int s = 0; s < T; ++s) {
     const size_t row = static_cast<size_t>(item) * T + s;
-    sQ[s][t] = Q[row * ldq + t];
-    sK[s][t] = K[row * ldk + t];
-    vcol[s] = __fdiv_rn(V[row * ldv + t], fT);
+    if constexpr (BF) {
+      sQ[s][t] = bf2f(static_cast<const unsigned short*>(Qv)[row * ldq + t]);
+      sK[s][t] = bf2f(static_cast<const unsigned short*>(Kv)[row * ldk + t]);
+      vcol[s] = __fdiv_rn(bf2f(static_cast<const unsigned short*>(Vv)[row * ldv + t]), fT);
+    } else {
+      sQ[s][t] = static_cast<const float*>(Qv)[row * ldq + t];
+      sK[s][t] = static_cast<const float*>(Kv)[row * ldk + t];
+      vcol[s] = __fdiv_rn(static_cast<const float*>(Vv)[row * ldv + t], fT);
+    }
   }
   __syncthreads();
   // shared memory is read 16 bytes at a time (the kernel is bound by shared-memory wavefronts otherwise)
@@ -362,7 +399,10 @@ __global__ void __launch_bounds__(128) attn_windows_kernel(const float* __restri
       num = fmaf(q.z, kvc[4 * d4 + 2], num); den = fmaf(q.z, ks[4 * d4 + 2], den);
       num = fmaf(q.w, kvc[4 * d4 + 3], num); den = fmaf(q.w, ks[4 * d4 + 3], den);
     }
-    msg[(static_cast<size_t>(item) * T + l) * ldm + t] = num * (1.f / (den + eps)) * fT;
+    const float o = num * (1.f / (den + eps)) * fT;
+    const size_t oi = (static_cast<size_t>(item) * T + l) * ldm + t;
+    if constexpr (BF) static_cast<unsigned short*>(msgv)[oi] = f2bf(o);
+    else static_cast<float*>(msgv)[oi] = o;
   }
 }
 
@@ -1015,31 +1055,40 @@ int posenc_tokens(const float* feat, const float* pe, float* tok, long long ldt,
   return MFR_OK;
 }
 
-int linear_attention_long(const float* Q, long long ldq, const float* K, long long ldk, const float* V,
-                          long long ldv, float* msg, long long ldm, float* kv_part, float* kv, int n,
-                          int L, int S, int heads, int dim, int splits, cudaStream_t st) {
+int linear_attention_long(const void* Q, long long ldq, const void* K, long long ldk, const void* V,
+                          long long ldv, void* msg, long long ldm, float* kv_part, float* kv, int n,
+                          int L, int S, int heads, int dim, int splits, cudaStream_t st, int bf16) {
   if (dim != 32 || heads != 8) return MFR_ERR_UNSUPPORTED;
-  if ((ldq | ldk | ldv) & 3) return MFR_ERR_ARG;                    // 16-byte cp.async chunks
+  if ((ldq | ldk | ldv) & (bf16 ? 7 : 3)) return MFR_ERR_ARG;                    // 16-byte cp.async chunks
   constexpr int kKvSmem = 2 * kAttStages * kSlab * 256 * 4, kApSmem = kAttStages * kSlab * 256 * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem));
-    MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmem));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmem));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem / 2));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmem / 2));
     attr_set = true;
   }
-  kv_partial_kernel<<<dim3(splits, n), 256, kKvSmem, st>>>(K, ldk, V, ldv, kv_part, S, splits);
-  kv_reduce_kernel<<<dim3((8 * 1056 + 255) / 256, n), 256, 0, st>>>(kv_part, kv, splits);
   const int asplits = std::max(1, std::min((L + kSlab - 1) / kSlab, (4 * 148 + n - 1) / n));
-  attn_apply_kernel<<<dim3(asplits, n), 256, kApSmem, st>>>(Q, ldq, kv, msg, ldm, L, S, 1e-6f, asplits);
+  if (bf16) {
+    kv_partial_kernel<true><<<dim3(splits, n), 256, kKvSmem / 2, st>>>(K, ldk, V, ldv, kv_part, S, splits);
+    kv_reduce_kernel<<<dim3((8 * 1056 + 255) / 256, n), 256, 0, st>>>(kv_part, kv, splits);
+    attn_apply_kernel<true><<<dim3(asplits, n), 256, kApSmem / 2, st>>>(Q, ldq, kv, msg, ldm, L, S, 1e-6f, asplits);
+  } else {
+    kv_partial_kernel<false><<<dim3(splits, n), 256, kKvSmem, st>>>(K, ldk, V, ldv, kv_part, S, splits);
+    kv_reduce_kernel<<<dim3((8 * 1056 + 255) / 256, n), 256, 0, st>>>(kv_part, kv, splits);
+    attn_apply_kernel<false><<<dim3(asplits, n), 256, kApSmem, st>>>(Q, ldq, kv, msg, ldm, L, S, 1e-6f, asplits);
+  }
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }
 
-int linear_attention_windows(const float* Q, long long ldq, const float* K, long long ldk, const float* V,
-                             long long ldv, float* msg, long long ldm, const int* n_items_dev,
-                             int max_items, int T, cudaStream_t st) {
+int linear_attention_windows(const void* Q, long long ldq, const void* K, long long ldk, const void* V,
+                             long long ldv, void* msg, long long ldm, const int* n_items_dev,
+                             int max_items, int T, cudaStream_t st, int bf16) {
   if (T != 25 || max_items <= 0) return MFR_ERR_UNSUPPORTED;
-  attn_windows_kernel<25><<<max_items, 128, 0, st>>>(Q, ldq, K, ldk, V, ldv, msg, ldm, n_items_dev, 1e-6f);
+  if (bf16) attn_windows_kernel<25, true><<<max_items, 128, 0, st>>>(Q, ldq, K, ldk, V, ldv, msg, ldm, n_items_dev, 1e-6f);
+  else attn_windows_kernel<25, false><<<max_items, 128, 0, st>>>(Q, ldq, K, ldk, V, ldv, msg, ldm, n_items_dev, 1e-6f);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }

@@ -24,15 +24,16 @@ int posenc_tokens(const float* feat, const float* pe, float* tok, long long ldt,
 //   K,V: [n][S][H*D] (row strides ldk, ldv), already elu+1'd K.  Q: [n][L][H*D].
 //   msg[n,l,h,:] = (Q . KV) / (Q . Ksum + eps),  KV = sum_s K^T (V/S) * S
 // scratch: kv_part [n][H][splits][(D+1)*D], kv [n][H][(D+1)*D]
-int linear_attention_long(const float* Q, long long ldq, const float* K, long long ldk, const float* V,
-                          long long ldv, float* msg, long long ldm, float* kv_part, float* kv, int n,
-                          int L, int S, int heads, int dim, int splits, cudaStream_t st);
+// bf16 != 0: Q / K / V / msg are bf16 (strides in elements), sums stay fp32
+int linear_attention_long(const void* Q, long long ldq, const void* K, long long ldk, const void* V,
+                          long long ldv, void* msg, long long ldm, float* kv_part, float* kv, int n,
+                          int L, int S, int heads, int dim, int splits, cudaStream_t st, int bf16 = 0);
 
 // Linear attention for many short sequences (fine level): items of `T` tokens (T <= 32), C = 128,
 // 8 heads x 16. x-side item i attends to src-side item i. n_items read from device (*n_items_dev).
-int linear_attention_windows(const float* Q, long long ldq, const float* K, long long ldk, const float* V,
-                             long long ldv, float* msg, long long ldm, const int* n_items_dev,
-                             int max_items, int T, cudaStream_t st);
+int linear_attention_windows(const void* Q, long long ldq, const void* K, long long ldk, const void* V,
+                             long long ldv, void* msg, long long ldm, const int* n_items_dev,
+                             int max_items, int T, cudaStream_t st, int bf16 = 0);
 
 // out[r,:] = (res ? res[r,:] : 0) + LayerNorm(in[r,:]) * gamma + beta, C in {128, 256}; rows may be
 // limited by *dyn_rows (device) when non-null.
