@@ -39,12 +39,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("MFR_BENCH_BATCH", 8)), help="pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("MFR_BENCH_BATCH", 16)), help="pairs per step per GPU")
     ap.add_argument("--hyp", type=int, default=1024, help="5-point hypotheses per pair")
     ap.add_argument("--match-thr", type=float, default=0.2, help="LoFTR coarse confidence threshold (reference: 0.2)")
     ap.add_argument("--precision", default=os.environ.get("MFR_BENCH_PRECISION", "bf16"), choices=["tf32", "bf16"],
                     help="LoFTR backbone tensor-core input type (tf32 = parity mode; bf16 = bf16 storage + MMA in the ResNet-FPN)")
-    ap.add_argument("--pool", type=int, default=16, help="distinct synthetic pairs cycled through")
+    ap.add_argument("--pool", type=int, default=32, help="distinct synthetic pairs cycled through")
     ap.add_argument("--cpu-sample", type=int, default=2, help="pairs timed for the cpu_baseline leg")
     return ap.parse_args()
 

@@ -21,14 +21,14 @@ print(f"{'launch':22s} {'us':>8s} {'DRAM rd MB':>10s} {'DRAM wr MB':>10s} {'L2 M
 for k, i in enumerate(ids):
     m = d[i]
     t = m["gpu__time_duration.sum"]; us = t[0] / 1e3 if t[1].startswith("n") else t[0]
-    name = NAMES[k] if k < len(NAMES) else ("correlation" if us > 150 else "token gemm")
+    name = NAMES[k] if k < len(NAMES) else "token / correlation / fine gemm"
     rec = {"name": name, "us": round(us, 1), "dram_read": b(m["dram__bytes_read.sum"]), "dram_write": b(m["dram__bytes_write.sum"]),
            "l2_bytes": b(m["lts__t_bytes.sum"]), "tensor_active_pct": m["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"][0],
            "sm_ghz": round(m["sm__cycles_elapsed.avg.per_second"][0] / 1e9, 3)}
     out["launches"].append(rec)
     grp = "backbone" if k < len(NAMES) else "tokens"
     for key in ("us", "dram_read", "dram_write", "l2_bytes"): tot[grp, key] += rec[key]
-    if k < len(NAMES) or us > 150:
+    if k < len(NAMES):
         print(f"{name:22s} {us:8.1f} {rec['dram_read']/1e6:10.1f} {rec['dram_write']/1e6:10.1f} {rec['l2_bytes']/1e6:9.1f} {rec['tensor_active_pct']:8.1f} {rec['sm_ghz']:7.3f}")
 for grp in ("backbone", "tokens"):
     out[grp] = {k: tot[grp, k] for k in ("us", "dram_read", "dram_write", "l2_bytes")}
