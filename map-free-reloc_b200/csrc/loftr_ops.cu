@@ -351,42 +351,63 @@ __global__ void __launch_bounds__(128) attn_windows_kernel(const void* __restric
                                                            float eps) {
   const int item = blockIdx.x;
   if (item >= *n_items_dev) return;
-  __shared__ __align__(16) float sQ[32][128];
-  __shared__ __align__(16) float sK[32][128];
+  __shared__ __align__(16) float sQ[T][128];
+  __shared__ __align__(16) float sK[T][128];   // K rows, later the output rows
+  __shared__ __align__(16) float sV[T][128];
   const int t = threadIdx.x;
   const int hb = (t >> 4) << 4;  // first channel of this thread's head
-  float vcol[T];
   const float fT = static_cast<float>(T);
-#pragma unroll
-  for (int s = 0; s < T; ++s) {
-    const size_t row = static_cast<size_t>(item) * T + s;
+  // cooperative 16-byte loads of the item's T x 128 q / k / v rows (fp32: 32 chunks per row, bf16: 16)
+  constexpr int CH = BF ? 16 : 32, EPC = BF ? 8 : 4;     // chunks per row, elements per chunk
+  const size_t row0 = static_cast<size_t>(item) * T;
+  for (int c = t; c < T * CH; c += 128) {
+    const int r = c / CH, e0 = (c % CH) * EPC;
+    float q[EPC], k[EPC], v[EPC];
     if constexpr (BF) {
-      sQ[s][t] = bf2f(static_cast<const unsigned short*>(Qv)[row * ldq + t]);
-      sK[s][t] = bf2f(static_cast<const unsigned short*>(Kv)[row * ldk + t]);
-      vcol[s] = __fdiv_rn(bf2f(static_cast<const unsigned short*>(Vv)[row * ldv + t]), fT);
+      const uint4 uq = *reinterpret_cast<const uint4*>(static_cast<const unsigned short*>(Qv) + (row0 + r) * ldq + e0);
+      const uint4 uk = *reinterpret_cast<const uint4*>(static_cast<const unsigned short*>(Kv) + (row0 + r) * ldk + e0);
+      const uint4 uv = *reinterpret_cast<const uint4*>(static_cast<const unsigned short*>(Vv) + (row0 + r) * ldv + e0);
+      const unsigned wq[4] = {uq.x, uq.y, uq.z, uq.w}, wk[4] = {uk.x, uk.y, uk.z, uk.w}, wv[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        q[2 * e] = __uint_as_float(wq[e] << 16); q[2 * e + 1] = __uint_as_float(wq[e] & 0xffff0000u);
+        k[2 * e] = __uint_as_float(wk[e] << 16); k[2 * e + 1] = __uint_as_float(wk[e] & 0xffff0000u);
+        v[2 * e] = __uint_as_float(wv[e] << 16); v[2 * e + 1] = __uint_as_float(wv[e] & 0xffff0000u);
+      }
     } else {
-      sQ[s][t] = static_cast<const float*>(Qv)[row * ldq + t];
-      sK[s][t] = static_cast<const float*>(Kv)[row * ldk + t];
-      vcol[s] = __fdiv_rn(static_cast<const float*>(Vv)[row * ldv + t], fT);
+      const float4 fq = *reinterpret_cast<const float4*>(static_cast<const float*>(Qv) + (row0 + r) * ldq + e0);
+      const float4 fk = *reinterpret_cast<const float4*>(static_cast<const float*>(Kv) + (row0 + r) * ldk + e0);
+      const float4 fv = *reinterpret_cast<const float4*>(static_cast<const float*>(Vv) + (row0 + r) * ldv + e0);
+      q[0] = fq.x; q[1] = fq.y; q[2] = fq.z; q[3] = fq.w;
+      k[0] = fk.x; k[1] = fk.y; k[2] = fk.z; k[3] = fk.w;
+      v[0] = fv.x; v[1] = fv.y; v[2] = fv.z; v[3] = fv.w;
+    }
+#pragma unroll
+    for (int e = 0; e < EPC; e += 4) {                 // 16-byte shared-memory stores
+      *reinterpret_cast<float4*>(&sQ[r][e0 + e]) = make_float4(q[e], q[e + 1], q[e + 2], q[e + 3]);
+      *reinterpret_cast<float4*>(&sK[r][e0 + e]) = make_float4(k[e], k[e + 1], k[e + 2], k[e + 3]);
+      *reinterpret_cast<float4*>(&sV[r][e0 + e]) =     // values / v_length (linear_attention.py:40)
+          make_float4(__fdiv_rn(v[e], fT), __fdiv_rn(v[e + 1], fT), __fdiv_rn(v[e + 2], fT), __fdiv_rn(v[e + 3], fT));
     }
   }
   __syncthreads();
-  // shared memory is read 16 bytes at a time (the kernel is bound by shared-memory wavefronts otherwise)
   float kvc[16], ks[16];
 #pragma unroll
   for (int d = 0; d < 16; ++d) { kvc[d] = 0.f; ks[d] = 0.f; }
 #pragma unroll
   for (int s = 0; s < T; ++s) {
+    const float vs = sV[s][t];
     const float4* kr = reinterpret_cast<const float4*>(&sK[s][hb]);
 #pragma unroll
     for (int d4 = 0; d4 < 4; ++d4) {
       const float4 kk = kr[d4];
-      kvc[4 * d4] = fmaf(kk.x, vcol[s], kvc[4 * d4]);         ks[4 * d4] += kk.x;
-      kvc[4 * d4 + 1] = fmaf(kk.y, vcol[s], kvc[4 * d4 + 1]); ks[4 * d4 + 1] += kk.y;
-      kvc[4 * d4 + 2] = fmaf(kk.z, vcol[s], kvc[4 * d4 + 2]); ks[4 * d4 + 2] += kk.z;
-      kvc[4 * d4 + 3] = fmaf(kk.w, vcol[s], kvc[4 * d4 + 3]); ks[4 * d4 + 3] += kk.w;
+      kvc[4 * d4] = fmaf(kk.x, vs, kvc[4 * d4]);         ks[4 * d4] += kk.x;
+      kvc[4 * d4 + 1] = fmaf(kk.y, vs, kvc[4 * d4 + 1]); ks[4 * d4 + 1] += kk.y;
+      kvc[4 * d4 + 2] = fmaf(kk.z, vs, kvc[4 * d4 + 2]); ks[4 * d4 + 2] += kk.z;
+      kvc[4 * d4 + 3] = fmaf(kk.w, vs, kvc[4 * d4 + 3]); ks[4 * d4 + 3] += kk.w;
     }
   }
+  __syncthreads();                                     // everyone is done with sK: it now collects the output rows
 #pragma unroll 5
   for (int l = 0; l < T; ++l) {
     const float4* qr = reinterpret_cast<const float4*>(&sQ[l][hb]);
@@ -399,10 +420,22 @@ __global__ void __launch_bounds__(128) attn_windows_kernel(const void* __restric
       num = fmaf(q.z, kvc[4 * d4 + 2], num); den = fmaf(q.z, ks[4 * d4 + 2], den);
       num = fmaf(q.w, kvc[4 * d4 + 3], num); den = fmaf(q.w, ks[4 * d4 + 3], den);
     }
-    const float o = num * (1.f / (den + eps)) * fT;
-    const size_t oi = (static_cast<size_t>(item) * T + l) * ldm + t;
-    if constexpr (BF) static_cast<unsigned short*>(msgv)[oi] = f2bf(o);
-    else static_cast<float*>(msgv)[oi] = o;
+    sK[l][t] = num * (1.f / (den + eps)) * fT;
+  }
+  __syncthreads();
+  for (int c = t; c < T * CH; c += 128) {              // 16-byte stores of the T x 128 message rows
+    const int r = c / CH, e0 = (c % CH) * EPC;
+    if constexpr (BF) {
+      uint4 o;
+      o.x = static_cast<unsigned>(f2bf(sK[r][e0])) | (static_cast<unsigned>(f2bf(sK[r][e0 + 1])) << 16);
+      o.y = static_cast<unsigned>(f2bf(sK[r][e0 + 2])) | (static_cast<unsigned>(f2bf(sK[r][e0 + 3])) << 16);
+      o.z = static_cast<unsigned>(f2bf(sK[r][e0 + 4])) | (static_cast<unsigned>(f2bf(sK[r][e0 + 5])) << 16);
+      o.w = static_cast<unsigned>(f2bf(sK[r][e0 + 6])) | (static_cast<unsigned>(f2bf(sK[r][e0 + 7])) << 16);
+      *reinterpret_cast<uint4*>(static_cast<unsigned short*>(msgv) + (row0 + r) * ldm + e0) = o;
+    } else {
+      *reinterpret_cast<float4*>(static_cast<float*>(msgv) + (row0 + r) * ldm + e0) =
+          make_float4(sK[r][e0], sK[r][e0 + 1], sK[r][e0 + 2], sK[r][e0 + 3]);
+    }
   }
 }
 
@@ -623,32 +656,34 @@ __global__ void col_conf_combine_kernel(const float* __restrict__ part, float* _
 //   stats_fused : row (max, 1/sum exp) per row + online per-column (max, sum exp) partials of the slab
 //   conf_fused  : conf = softmax_row * softmax_col per element; row max / first argmax / tie count,
 //                 per-column partial max of the slab
-constexpr int kF4 = 6;   // float4 groups per thread per row
+constexpr int kCmThreads = 512;   // 16 warps per block: the passes stream S with ~100 loads in flight per thread-pair
+constexpr int kF4 = 3;            // float4 groups per thread per row (kCmThreads * 4 * kF4 >= L)
 
+constexpr int kCmWarps = kCmThreads / 32;
 template <int NV, bool IS_MAX>
-__device__ __forceinline__ void block_reduce_n(float (&v)[NV], float* sh /* [NV][8] */) {
+__device__ __forceinline__ void block_reduce_n(float (&v)[NV], float* sh /* [NV][kCmWarps] */) {
 #pragma unroll
   for (int q = 0; q < NV; ++q) v[q] = IS_MAX ? warp_max(v[q]) : warp_sum(v[q]);
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int q = 0; q < NV; ++q) sh[q * 8 + (threadIdx.x >> 5)] = v[q];
+    for (int q = 0; q < NV; ++q) sh[q * kCmWarps + (threadIdx.x >> 5)] = v[q];
   }
   __syncthreads();
 #pragma unroll
   for (int q = 0; q < NV; ++q) {
-    float r = sh[q * 8];
+    float r = sh[q * kCmWarps];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) r = IS_MAX ? fmaxf(r, sh[q * 8 + k]) : r + sh[q * 8 + k];
+    for (int k = 1; k < kCmWarps; ++k) r = IS_MAX ? fmaxf(r, sh[q * kCmWarps + k]) : r + sh[q * kCmWarps + k];
     v[q] = r;
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) stats_fused_kernel(const float* __restrict__ S, float* __restrict__ row_max,
+__global__ void __launch_bounds__(kCmThreads) stats_fused_kernel(const float* __restrict__ S, float* __restrict__ row_max,
                                                           float* __restrict__ row_rsum, float* __restrict__ part,
                                                           int L, int rows_per_block, int splits) {
   constexpr int R = 4;
-  __shared__ float sh[R * 8];
+  __shared__ float sh[R * kCmWarps];
   const int b = blockIdx.y, t = threadIdx.x;
   const int i0 = blockIdx.x * rows_per_block, i1 = min(L, i0 + rows_per_block);
   const int L4 = L >> 2;
@@ -663,7 +698,7 @@ __global__ void __launch_bounds__(256) stats_fused_kernel(const float* __restric
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int k = 0; k < kF4; ++k) {
-        const int f = t + 256 * k;
+        const int f = t + kCmThreads * k;
         v[r][k] = (i + r < i1 && f < L4) ? __ldg(Sb + static_cast<size_t>(i + r) * L4 + f) : ninf;
       }
     float rm[R], rs[R];
@@ -717,7 +752,7 @@ __global__ void __launch_bounds__(256) stats_fused_kernel(const float* __restric
   }
 #pragma unroll
   for (int k = 0; k < kF4; ++k) {
-    const int f = t + 256 * k;
+    const int f = t + kCmThreads * k;
     if (f < L4) {
       float* o = part + ((static_cast<size_t>(b) * splits + blockIdx.x) * L + 4 * f) * 2;
 #pragma unroll
@@ -726,7 +761,7 @@ __global__ void __launch_bounds__(256) stats_fused_kernel(const float* __restric
   }
 }
 
-__global__ void __launch_bounds__(256) conf_fused_kernel(const float* __restrict__ S, const float* __restrict__ row_max,
+__global__ void __launch_bounds__(kCmThreads) conf_fused_kernel(const float* __restrict__ S, const float* __restrict__ row_max,
                                                          const float* __restrict__ row_rsum,
                                                          const float* __restrict__ col_max,
                                                          const float* __restrict__ col_rsum,
@@ -734,7 +769,7 @@ __global__ void __launch_bounds__(256) conf_fused_kernel(const float* __restrict
                                                          int* __restrict__ rconf_ties, float* __restrict__ part,
                                                          int L, int rows_per_block, int splits, bool raw) {
   constexpr int R = 2;
-  __shared__ float sh[2 * R * 8];
+  __shared__ float sh[2 * R * kCmWarps];
   const int b = blockIdx.y, t = threadIdx.x;
   const int i0 = blockIdx.x * rows_per_block, i1 = min(L, i0 + rows_per_block);
   const int L4 = L >> 2;
@@ -743,7 +778,7 @@ __global__ void __launch_bounds__(256) conf_fused_kernel(const float* __restrict
   float cbest[kF4 * 4];
 #pragma unroll
   for (int k = 0; k < kF4; ++k) {
-    const int f = t + 256 * k;
+    const int f = t + kCmThreads * k;
     const bool ok = f < L4 && !raw;
     cmv[k] = ok ? __ldg(reinterpret_cast<const float4*>(col_max + static_cast<size_t>(b) * L) + f) : make_float4(0, 0, 0, 0);
     crv[k] = ok ? __ldg(reinterpret_cast<const float4*>(col_rsum + static_cast<size_t>(b) * L) + f) : make_float4(0, 0, 0, 0);
@@ -756,7 +791,7 @@ __global__ void __launch_bounds__(256) conf_fused_kernel(const float* __restrict
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int k = 0; k < kF4; ++k) {
-        const int f = t + 256 * k;
+        const int f = t + kCmThreads * k;
         v[r][k] = (i + r < i1 && f < L4) ? __ldg(Sb + static_cast<size_t>(i + r) * L4 + f) : make_float4(0, 0, 0, 0);
       }
     float best[R];
@@ -770,7 +805,7 @@ __global__ void __launch_bounds__(256) conf_fused_kernel(const float* __restrict
       arg[r] = 0x7fffffff;
 #pragma unroll
       for (int k = 0; k < kF4; ++k) {
-        const int f = t + 256 * k;
+        const int f = t + kCmThreads * k;
         const bool ok = rok && f < L4;
         float4 c;
         c.x = ok ? conf_value(v[r][k].x, rmx, rrs, cmv[k].x, crv[k].x, raw) : -1.f;
@@ -806,13 +841,13 @@ __global__ void __launch_bounds__(256) conf_fused_kernel(const float* __restrict
       for (int r = 0; r < R; ++r) { q[r] = warp_max(q[r]); q[R + r] = warp_sum(q[R + r]); }
       if ((t & 31) == 0) {
 #pragma unroll
-        for (int z = 0; z < 2 * R; ++z) sh[z * 8 + (t >> 5)] = q[z];
+        for (int z = 0; z < 2 * R; ++z) sh[z * kCmWarps + (t >> 5)] = q[z];
       }
       __syncthreads();
       if (t < R && i + t < i1) {
-        float fm = sh[t * 8], ts = sh[(R + t) * 8];
+        float fm = sh[t * kCmWarps], ts = sh[(R + t) * kCmWarps];
 #pragma unroll
-        for (int k = 1; k < 8; ++k) { fm = fmaxf(fm, sh[t * 8 + k]); ts += sh[(R + t) * 8 + k]; }
+        for (int k = 1; k < kCmWarps; ++k) { fm = fmaxf(fm, sh[t * kCmWarps + k]); ts += sh[(R + t) * kCmWarps + k]; }
         const size_t row = static_cast<size_t>(b) * L + i + t;
         rconf_max[row] = bm[t];
         rconf_arg[row] = static_cast<int>(-fm);
@@ -823,7 +858,7 @@ __global__ void __launch_bounds__(256) conf_fused_kernel(const float* __restrict
   }
 #pragma unroll
   for (int k = 0; k < kF4; ++k) {
-    const int f = t + 256 * k;
+    const int f = t + kCmThreads * k;
     if (f < L4)
       *reinterpret_cast<float4*>(part + (static_cast<size_t>(b) * splits + blockIdx.x) * L + 4 * f) =
           make_float4(cbest[k * 4], cbest[k * 4 + 1], cbest[k * 4 + 2], cbest[k * 4 + 3]);
@@ -1112,16 +1147,16 @@ int coarse_match(const float* S, CoarseMatchBuffers f, int B, int L, int h_c, in
                  int border, float scale, int splits, cudaStream_t st, bool input_is_conf) {
   const int cb = (L + 255) / 256;
   const bool raw = input_is_conf;
-  const bool fused = (L % 4 == 0) && L <= 256 * 4 * kF4 && (reinterpret_cast<uintptr_t>(S) & 15) == 0;
+  const bool fused = (L % 4 == 0) && L <= kCmThreads * 4 * kF4 && (reinterpret_cast<uintptr_t>(S) & 15) == 0;
   if (fused) {
     // a block owns ceil(L / splits) rows (rounded to the row batch) and all columns
     const int rpb = ((L + splits - 1) / splits + 3) / 4 * 4;
     const int nblk = (L + rpb - 1) / rpb;
     if (!raw) {
-      stats_fused_kernel<<<dim3(nblk, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_part, L, rpb, nblk);
+      stats_fused_kernel<<<dim3(nblk, B), kCmThreads, 0, st>>>(S, f.row_max, f.row_rsum, f.col_part, L, rpb, nblk);
       col_stats_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.col_max, f.col_rsum, L, nblk);
     }
-    conf_fused_kernel<<<dim3(nblk, B), 256, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max, f.col_rsum, f.rconf_max,
+    conf_fused_kernel<<<dim3(nblk, B), kCmThreads, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max, f.col_rsum, f.rconf_max,
                                                      f.rconf_arg, f.rconf_ties, f.col_part, L, rpb, nblk, raw);
     col_conf_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.cconf_max, L, nblk);
   } else {
