@@ -21,6 +21,11 @@ from . import pose_solver as _ps
 
 class RelocPipeline:
     def __init__(self, engine, backend, pix_thr, scale_thr, num_hyp=_ps.DEFAULT_NUM_HYP, depth_hw=None):
+        # `engine` may be a list of identical engines: consecutive batches then alternate between them, each on
+        # its own stream, so that the HBM-bound kernels of one batch (attention, LayerNorm, dual softmax, token
+        # GEMMs) share the SMs with the tensor-core-bound convolutions of the next.
+        self.engines = list(engine) if isinstance(engine, (list, tuple)) else [engine]
+        engine = self.engines[0]
         self.eng, self.be = engine, backend
         self.pix_thr, self.scale_thr, self.num_hyp = float(pix_thr), float(scale_thr), int(num_hyp)
         dev = engine.device
@@ -45,20 +50,21 @@ class RelocPipeline:
                            "d0": torch.empty(B, h, w, device=dev), "d1": torch.empty(B, h, w, device=dev),
                            "K": torch.empty(B, 3, 3, device=dev)} for _ in range(2)]
         self.i = 0
-        self._outs = engine.device_outputs()
+        self._outs_all = [e.device_outputs() for e in self.engines]
 
     # ---------------------------------------------------------------- stages
     def _enqueue(self, g0, g1, d0, d1, K):
         """g0/g1/d0/d1/K: device tensors of this batch (already ordered after whatever produced them on the
         current stream or on self.s_copy via slot['ev_in'])."""
-        eng, slot = self.eng, self.slots[self.i % 2]
+        eng, slot = self.engines[self.i % len(self.engines)], self.slots[self.i % 2]
+        outs = self._outs_all[self.i % len(self.engines)]
         if slot["busy"]:                              # the solver of batch i-2 must be done with this slot
             eng.stream.wait_event(slot["ev_solved"])
         eng.forward_async(g0, g1)
         with torch.cuda.stream(eng.stream):
-            slot["k0"].copy_(self._outs["mkpts0_f"], non_blocking=True)
-            slot["k1"].copy_(self._outs["mkpts1_f"], non_blocking=True)
-            slot["off"].copy_(self._outs["m_offsets"], non_blocking=True)
+            slot["k0"].copy_(outs["mkpts0_f"], non_blocking=True)
+            slot["k1"].copy_(outs["mkpts1_f"], non_blocking=True)
+            slot["off"].copy_(outs["m_offsets"], non_blocking=True)
             slot["ev_fwd"].record(eng.stream)
         with torch.cuda.stream(self.s_solve):
             self.s_solve.wait_event(slot["ev_fwd"])
@@ -104,7 +110,7 @@ class RelocPipeline:
                 else:
                     st[k].copy_(src, non_blocking=True)
             slot["ev_in"].record(self.s_copy)
-        self.eng.stream.wait_event(slot["ev_in"])
+        self.engines[self.i % len(self.engines)].stream.wait_event(slot["ev_in"])
         self.s_solve.wait_event(slot["ev_in"])
         return self.submit_device(st["g0"], st["g1"], st["d0"], st["d1"], st["K"])
 
