@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--engines", type=int, default=int(os.environ.get("MFR_BENCH_ENGINES", 1)),
                     help="LoFTR engine instances that consecutive batches alternate between (streams overlap)")
     ap.add_argument("--pool", type=int, default=32, help="distinct synthetic pairs cycled through")
-    ap.add_argument("--cpu-sample", type=int, default=2, help="pairs timed for the cpu_baseline leg")
+    ap.add_argument("--cpu-sample", type=int, default=4, help="pairs timed for the cpu_baseline leg")
     return ap.parse_args()
 
 
@@ -287,6 +287,11 @@ def run_ours(args):
                     "median_rot_err_deg": med(fin([e[0] for e in gpu_errs])),
                     "median_trans_err_m": med(fin([e[1] for e in gpu_errs])),
                     "median_inliers": med([acc_rows[i][2] for i in sorted(acc_rows)]),
+                    "vs_reference_cpu_port": (lambda d: {"pairs": len(d), "median_rot_diff_deg": med(fin([x[0] for x in d])),
+                                                         "median_trans_diff_m": med(fin([x[1] for x in d])),
+                                                         "note": "angle(R_gpu R_cpu^T), |t_gpu - t_cpu| on the same pairs; the two paths differ in matcher precision "
+                                                                 "(bf16/tf32 vs fp32) and in the RANSAC (batched 5-pt + LO vs OpenCV USAC_MAGSAC)"})(
+                        [pose_errors(acc_rows[i][0], acc_rows[i][1], CPU_POSES[i]) for i in range(min(len(CPU_POSES), n_pool)) if i in acc_rows]),
                     "reference_cpu_port": {"pairs": len(CPU_ERRS), "median_rot_err_deg": med(fin([e[0] for e in CPU_ERRS])),
                                            "median_trans_err_m": med(fin([e[1] for e in CPU_ERRS])),
                                            "median_matches": med([e[2] for e in CPU_ERRS]),
@@ -318,6 +323,7 @@ def run_ours(args):
 # OpenCV USAC_MAGSAC + scale consensus), all host threads
 # ------------------------------------------------------------------------------------------------
 CPU_ERRS = []   # (rot err deg, trans err m, matches) of every pair the CPU leg solved
+CPU_POSES = []  # its (R, t) per pair, same order as the pool
 
 
 def cpu_pairs(n_pairs, match_thr, seed0=1000):
@@ -338,6 +344,7 @@ def cpu_pairs(n_pairs, match_thr, seed0=1000):
         t2 = time.perf_counter()
         t_net += t1 - t0; t_solve += t2 - t1
         CPU_ERRS.append(pose_errors(Rc, tc, gt[i]) + (len(k0),))
+        CPU_POSES.append((np.asarray(Rc, np.float64), np.ravel(tc).astype(np.float64)))
     return t_net, t_solve
 
 

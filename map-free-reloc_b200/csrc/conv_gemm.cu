@@ -212,6 +212,82 @@ __device__ __forceinline__ void epilogue_subtile_tma(const ConvGemmParams& p, ui
   }
 }
 
+// Epilogue of the swapped-operand mode: TMEM lane = output channel (warp q owns channels 32q..32q+31), TMEM column
+// = pixel of the 256-pixel tile. Per 32-pixel chunk: tcgen05.ld (thread = channel, 32 pixels) -> transposing
+// shared-memory write (element (pixel, channel): consecutive lanes hit consecutive banks) -> the same coalesced
+// store phase as the normal mode (lane (sub_r, sub_c): pixels k*4+sub_r of the chunk, channels sub_c..sub_c+3).
+template <int ACT, bool RES, bool OBF>
+__device__ __forceinline__ void epilogue_tile_swap(const ConvGemmParams& p, uint32_t taddr, float* stg, int lane, int q,
+                                                   int tx, int ty, int img, int tile_rows, int w_lim, uint32_t wait_bar,
+                                                   uint32_t wait_phase) {
+  using RT = typename std::conditional<OBF, uint2, float4>::type;
+  const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+  const int n = q * 32 + sub_c;                       // first of this lane's 4 output channels
+  const bool n_ok = n < p.Cout;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias != nullptr && n_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+  const float alpha = p.alpha;
+  const int tw_shift = 31 - __clz(p.TW);              // TW is a power of two in halo mode
+  // pixel k*4+sub_r of chunk c0 -> element offset of its channel n in an NHWC map with pixel stride ld, or -1
+  auto pix_off = [&](int c0, int k, long long img_stride, long long ld) -> long long {
+    const int pr = c0 + k * 4 + sub_r;                // pixel of the tile, (y, x) order over TW columns
+    const int ly = pr >> tw_shift, lx = pr & (p.TW - 1);
+    const int y = ty * tile_rows + ly, x = tx * p.TW + lx;
+    if (!(n_ok && y < p.Ho && x < w_lim)) return -1;
+    return img * img_stride + (static_cast<long long>(y) * p.Wo + x) * ld + n;
+  };
+  RT rnext[8];
+  auto issue_res = [&](int c0) {                      // residual of chunk c0, fetched one chunk ahead of its use
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if constexpr (OBF) rnext[k] = make_uint2(0u, 0u);
+      else rnext[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const long long ro = pix_off(c0, k, p.res_img_stride, p.ldr);
+      if (ro >= 0) {
+        if constexpr (OBF) rnext[k] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + ro));
+        else rnext[k] = __ldg(reinterpret_cast<const float4*>(p.residual + ro));
+      }
+    }
+  };
+  if constexpr (RES) issue_res(0);
+  mbar_wait(wait_bar, wait_phase, 4);
+  tc_fence_after();
+  for (int c0 = 0; c0 < 2 * kTileM; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stg[j * kStgStride + lane] = __uint_as_float(r[j]);
+    __syncwarp();
+    RT rcur[8];
+    if constexpr (RES) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) rcur[k] = rnext[k];
+      if (c0 + 32 < 2 * kTileM) issue_res(c0 + 32);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long oo = pix_off(c0, k, p.out_img_stride, p.ldo);
+      if (oo < 0) continue;
+      float4 v = *reinterpret_cast<const float4*>(stg + (k * 4 + sub_r) * kStgStride + sub_c);
+      v.x = fmaf(v.x, alpha, b4.x); v.y = fmaf(v.y, alpha, b4.y);
+      v.z = fmaf(v.z, alpha, b4.z); v.w = fmaf(v.w, alpha, b4.w);
+      if constexpr (RES) {
+        float4 r4;
+        if constexpr (OBF) r4 = bf16x4_to_float4(rcur[k]);
+        else r4 = rcur[k];
+        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+      }
+      v.x = act_fn<ACT>(v.x); v.y = act_fn<ACT>(v.y); v.z = act_fn<ACT>(v.z); v.w = act_fn<ACT>(v.w);
+      if constexpr (OBF)
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + oo) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      else
+        *reinterpret_cast<float4*>(p.out + oo) = v;
+    }
+    __syncwarp();
+  }
+}
+
 // Scalar epilogue for shapes the vector path cannot take (Cout or strides not multiples of 4); fp32 only.
 __device__ __forceinline__ void epilogue_subtile_scalar(const ConvGemmParams& p, uint32_t taddr, int n0, bool row_ok,
                                                         long long o_off, long long r_off, int c_begin) {
@@ -353,6 +429,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = umma_idesc(p.in_bf16 ? 1u : 2u, kTileM, static_cast<uint32_t>(p.BN));
+    const uint32_t idesc_swap = umma_idesc(p.in_bf16 ? 1u : 2u, kTileM, 2u * kTileM);
     const bool bf16_in = p.in_bf16 != 0;
     const int MT = p.MT, ksteps_last = p.ksteps_last;
     const uint32_t sub_bytes = static_cast<uint32_t>(p.TH * p.TW * 128);   // A bytes of one 128-row sub-tile
@@ -377,7 +454,18 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
             for (int ky = 0; ky < 3; ++ky) {
               mbar_wait(b_full(sb), pb, 6);
               tc_fence_after();
-              if (elect_one_sync()) {
+              if (p.swap) {
+                if (elect_one_sync()) {   // filters are the M operand, the tile's 256 pixels the N operand
+                  const uint64_t wdesc = desc_at(smem_b + sb * b_bytes);
+                  const uint64_t xdesc = desc_at(a_slot + ky * ky_bytes);
+                  uint32_t acc_m = accum;
+                  for (int k = 0; k < nk; ++k) {
+                    if (bf16_in) tc_mma_bf16(tmem_acc, wdesc + 2 * k, xdesc + 2 * k, idesc_swap, acc_m);
+                    else tc_mma_tf32(tmem_acc, wdesc + 2 * k, xdesc + 2 * k, idesc_swap, acc_m);
+                    acc_m = 1u;
+                  }
+                }
+              } else if (elect_one_sync()) {
                 const uint64_t bdesc = desc_at(smem_b + sb * b_bytes);
                 for (int m = 0; m < MT; ++m) {
                   const uint64_t adesc = desc_at(a_slot + m * sub_bytes + ky * ky_bytes);
@@ -467,6 +555,26 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       const int ty = (mt / tiles_x) % p.tiles_y;
       const int img = mt / (tiles_x * p.tiles_y);
       const int n0 = nt * p.BN;
+      if (p.swap) {
+        const uint32_t taddr_s = tmem_base + static_cast<uint32_t>(acc * kMaxBN) + (static_cast<uint32_t>(q * 32) << 16);
+#define MFR_EPS(ACTV)                                                                                              \
+  do {                                                                                                             \
+    if (p.residual != nullptr) {                                                                                   \
+      if (obf) epilogue_tile_swap<ACTV, true, true>(p, taddr_s, stg, lane, q, tx, ty, img, tile_rows, w_lim, tfull_bar(acc), acc_phase);      \
+      else epilogue_tile_swap<ACTV, true, false>(p, taddr_s, stg, lane, q, tx, ty, img, tile_rows, w_lim, tfull_bar(acc), acc_phase);         \
+    } else {                                                                                                       \
+      if (obf) epilogue_tile_swap<ACTV, false, true>(p, taddr_s, stg, lane, q, tx, ty, img, tile_rows, w_lim, tfull_bar(acc), acc_phase);     \
+      else epilogue_tile_swap<ACTV, false, false>(p, taddr_s, stg, lane, q, tx, ty, img, tile_rows, w_lim, tfull_bar(acc), acc_phase);        \
+    }                                                                                                              \
+  } while (0)
+        switch (p.act) {
+          case ACT_RELU: MFR_EPS(ACT_RELU); break;
+          case ACT_LEAKY: MFR_EPS(ACT_LEAKY); break;
+          case ACT_ELU1: MFR_EPS(ACT_ELU1); break;
+          default: MFR_EPS(ACT_NONE); break;
+        }
+#undef MFR_EPS
+      } else
       for (int m = 0; m < p.MT; ++m) {
         const int y = ty * tile_rows + m * p.TH + ly0, x = tx * p.TW + lx;
         const bool row_ok = (row < p.TW * p.TH) && (y < p.Ho) && (x < w_lim);
@@ -569,7 +677,7 @@ EncodeTiledFn get_encode_fn() {
 
 // Tiling of one op: output tile = MT sub-tiles of TW x TH (<= 128) pixels, BN output channels.
 struct TileCfg {
-  int TW, TH, MT, BN, n_tiles, halo;
+  int TW, TH, MT, BN, n_tiles, halo, swap;
   double cost;
 };
 
@@ -603,7 +711,7 @@ RingCfg ring_cfg(int halo, int MT, int TW, int TH, int BN) {
 }
 
 TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, int pad, int kb_per_tap,
-                   int ksteps_last, bool allow_mt2, bool tma_store_ok) {
+                   int ksteps_last, bool allow_mt2, bool tma_store_ok, bool allow_swap) {
   const int sms = conv_gemm_num_sms();
   const int c16 = (Cout + 15) / 16 * 16;
   const int taps = R * S;
@@ -612,10 +720,10 @@ TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, in
   TileCfg best{};
   best.cost = 1e300;
   // test hook: MFR_CONV_FORCE="halo,MT,TW" restricts the search (-1 = free); unusable values fall back to free
-  int f_halo = -1, f_mt = -1, f_tw = -1;
-  if (const char* e = getenv("MFR_CONV_FORCE")) sscanf(e, "%d,%d,%d", &f_halo, &f_mt, &f_tw);
+  int f_halo = -1, f_mt = -1, f_tw = -1, f_swap = -1;
+  if (const char* e = getenv("MFR_CONV_FORCE")) sscanf(e, "%d,%d,%d,%d", &f_halo, &f_mt, &f_tw, &f_swap);
   for (int pass = 0; pass < 2 && best.cost > 1e299; ++pass) {
-  if (pass == 1) f_halo = f_mt = f_tw = -1;
+  if (pass == 1) f_halo = f_mt = f_tw = f_swap = -1;
   const int nt0 = (c16 + kMaxBN - 1) / kMaxBN;
   for (int nt = nt0; nt <= nt0 * 4; nt *= 2) {
     const int BN = ((c16 / 16 + nt - 1) / nt) * 16;
@@ -647,8 +755,16 @@ TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, in
           const double epi = MT * ((BN + 31) / 32) * (tma_epi ? 250.0 : 500.0);
           const double t = std::max(mma, std::max(l2, epi)) + 800.0;
           const double cost = static_cast<double>((tiles + sms - 1) / sms) * t;
-          if (cost < best.cost * (1.0 - 1e-9) || (cost < best.cost * (1.0 + 1e-9) && tw > best.TW)) {
-            best = TileCfg{tw, th, MT, BN, nt, halo, cost};
+          if (f_swap != 1 && (cost < best.cost * (1.0 - 1e-9) || (cost < best.cost * (1.0 + 1e-9) && tw > best.TW))) {
+            best = TileCfg{tw, th, MT, BN, nt, halo, 0, cost};
+          }
+          // swapped operands: the MT = 2 halo geometry with the filters as the M operand (Cout <= 128, one N tile)
+          if (halo && MT == 2 && nt == nt0 && c16 <= 128 && allow_swap && f_swap != 0 && (tw & (tw - 1)) == 0) {
+            const double mma_s = static_cast<double>(taps) * ksteps_tap * (30.5 + 0.2415 * 256) + commits * 215.0;
+            const double b_s = 128.0 * 128.0 * taps * kb_per_tap;
+            const double t_s = std::max(mma_s, std::max((a_bytes + b_s) / 100.0, 8 * 500.0)) + 800.0;
+            const double cost_s = static_cast<double>((tiles + sms - 1) / sms) * t_s;
+            if (cost_s < best.cost * (1.0 - 1e-9)) best = TileCfg{tw, th, 2, 128, 1, 1, 1, cost_s};
           }
         }
       }
@@ -656,8 +772,8 @@ TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, in
   }
   }
   if (getenv("MFR_CONV_DEBUG"))
-    fprintf(stderr, "[conv_gemm cfg] N%d %dx%d Cout%d R%d s%d kb%d -> TW%d TH%d MT%d BN%d nt%d halo%d cost %.0f\n", N, Ho, Wo,
-            Cout, R, stride, kb_per_tap, best.TW, best.TH, best.MT, best.BN, best.n_tiles, best.halo, best.cost);
+    fprintf(stderr, "[conv_gemm cfg] N%d %dx%d Cout%d R%d s%d kb%d -> TW%d TH%d MT%d BN%d nt%d halo%d swap%d cost %.0f\n", N, Ho, Wo,
+            Cout, R, stride, kb_per_tap, best.TW, best.TH, best.MT, best.BN, best.n_tiles, best.halo, best.swap, best.cost);
   return best;
 }
 
@@ -704,8 +820,11 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
     p->ksteps_last = (tail + ummak - 1) / ummak;
   }
   const TileCfg cfg = choose_cfg(d.N, p->Ho, p->Wo, d.Cout, d.R, d.S, d.stride, d.pad, p->kb_per_tap, p->ksteps_last,
-                                 d.dyn_w == nullptr, !d.out_bf16 && d.residual == nullptr);
-  p->TW = cfg.TW; p->TH = cfg.TH; p->MT = cfg.MT; p->halo = cfg.halo;
+                                 d.dyn_w == nullptr, !d.out_bf16 && d.residual == nullptr,
+                                 // swapped operands: not with a residual (measured: its transposed epilogue then becomes the bottleneck)
+                                 (d.Cout % 4 == 0) && (d.ldo % 4 == 0) && !d.b_batched &&
+                                     (d.residual == nullptr || (getenv("MFR_CONV_FORCE") != nullptr && d.ldr % 4 == 0)));
+  p->TW = cfg.TW; p->TH = cfg.TH; p->MT = cfg.MT; p->halo = cfg.halo; p->swap = cfg.swap;
   p->BN = cfg.BN; p->n_tiles = cfg.n_tiles;
   p->tiles_x = (p->Wo + p->TW - 1) / p->TW;
   p->tiles_y = (p->Ho + p->MT * p->TH - 1) / (p->MT * p->TH);
@@ -752,7 +871,7 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
   }
   {  // TMA-store epilogue: fp32 output without residual, power-of-two TW, whole 32-channel chunks per N tile
     const bool pow2 = (p->TW & (p->TW - 1)) == 0;
-    const bool ok = !d.out_bf16 && d.residual == nullptr && pow2 && p->TW >= 8 && p->TW * p->TH == 128 &&
+    const bool ok = !p->swap && !d.out_bf16 && d.residual == nullptr && pow2 && p->TW >= 8 && p->TW * p->TH == 128 &&
                     (p->BN % 32 == 0 || p->n_tiles == 1) && (p->act_cols % 32 == 0 || p->act_cols >= d.Cout) &&
                     (d.ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && (d.Cout % 4 == 0) &&
                     (p->out_img_stride % 4 == 0) && (d.bias == nullptr || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0) &&
@@ -952,8 +1071,8 @@ float conv_gemm_time_prebuilt(const ConvGemmParams& p, int iters, cudaStream_t s
                              "c0 tmem loaded", "c0 staged", "c0 stored"};
     fprintf(stderr, "[conv_gemm stamps, block 0, ns since start]");
     for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] ? h[i] - h[0] : -1);
-    fprintf(stderr, "\n[conv_gemm cfg] TW%d TH%d MT%d BN%d nt%d halo%d slots %d/%d cbatch %d\n", p.TW, p.TH, p.MT, p.BN,
-            p.n_tiles, p.halo, p.a_slots, p.b_slots, p.cbatch);
+    fprintf(stderr, "\n[conv_gemm cfg] TW%d TH%d MT%d BN%d nt%d halo%d swap%d slots %d/%d cbatch %d\n", p.TW, p.TH, p.MT, p.BN,
+            p.n_tiles, p.halo, p.swap, p.a_slots, p.b_slots, p.cbatch);
   }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);

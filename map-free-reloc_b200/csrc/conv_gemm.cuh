@@ -25,6 +25,8 @@ struct alignas(64) ConvGemmParams {
   int MT;                 // 128-pixel sub-tiles per CTA tile (2 only when BN <= 128: 2 x 2 x 128 TMEM columns)
   int halo;               // 3x3 stride-1 conv: A is loaded as a (MT*TH+2)-row box per (k-block, kx) and the three
                           // ky taps read it at row offsets 0, TW, 2*TW (TW % 8 == 0 keeps the swizzle phase)
+  int swap;               // halo mode with swapped operands (Cout <= 128): M = 128 filters, N = the 256 pixels of the tile —
+                          // one N = 256 MMA per k-step instead of two N = 128 ones (92 ns vs 2 x 61 ns); TMEM lane = filter
   int a_slots, b_slots;   // depth of the A ring / B ring (two rings: one A slot serves 3 B tiles in halo mode)
   int a_slot_bytes;
   int tma_store;          // epilogue writes 32 px x 32 ch fp32 chunks with cp.async.bulk.tensor stores (see conv_gemm.cu)

@@ -128,6 +128,52 @@ __global__ void upsample2x_add_kernel(const void* __restrict__ src, void* __rest
   }
 }
 
+// Same op for a bf16 destination, 8 channels (16 bytes of dst) per thread; grid (ceil(Wd*C8/256), Hd, N), no 64-bit
+// divisions. C8 = ceil(C / 8): the pad channels of a 200-stride 196-channel map are read and written as zeros.
+__device__ __forceinline__ void ld8(const void* p, size_t e, bool bf, float (&o)[8]) {
+  if (bf) {
+    const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const unsigned short*>(p) + e);
+    const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { o[2 * k] = __uint_as_float(w[k] << 16); o[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(p) + e);
+    const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(p) + e + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+}
+template <bool SBF>
+__global__ void __launch_bounds__(256) upsample2x_add8_kernel(const void* __restrict__ src, void* __restrict__ dst, int Hs,
+                                                              int Ws, int C8, int lds, int ldd, float ry, float rx) {
+  const int Hd = 2 * Hs, Wd = 2 * Ws;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= Wd * C8) return;
+  const int x = idx / C8, c8 = idx - x * C8;
+  const int y = blockIdx.y, n = blockIdx.z;
+  const float sy = ry * y, sx = rx * x;
+  const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+  const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+  const float ly = sy - y0, lx = sx - x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const size_t sb = static_cast<size_t>(n) * Hs * Ws;
+  float a[8], b[8], c[8], d[8], v[8];
+  ld8(src, (sb + static_cast<size_t>(y0) * Ws + x0) * lds + c8 * 8, SBF, a);
+  ld8(src, (sb + static_cast<size_t>(y0) * Ws + x1) * lds + c8 * 8, SBF, b);
+  ld8(src, (sb + static_cast<size_t>(y1) * Ws + x0) * lds + c8 * 8, SBF, c);
+  ld8(src, (sb + static_cast<size_t>(y1) * Ws + x1) * lds + c8 * 8, SBF, d);
+  const size_t de = ((static_cast<size_t>(n) * Hd + y) * Wd + x) * ldd + c8 * 8;
+  ld8(dst, de, true, v);
+  uint4 o;
+  unsigned* ow = reinterpret_cast<unsigned*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float r0 = v[2 * k] + (hy * (hx * a[2 * k] + lx * b[2 * k]) + ly * (hx * c[2 * k] + lx * d[2 * k]));
+    const float r1 = v[2 * k + 1] + (hy * (hx * a[2 * k + 1] + lx * b[2 * k + 1]) + ly * (hx * c[2 * k + 1] + lx * d[2 * k + 1]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(ow[k]) : "f"(r1), "f"(r0));
+  }
+  *reinterpret_cast<uint4*>(static_cast<unsigned short*>(dst) + de) = o;
+}
+
 // fp32 [rows][cin] -> bf16 [rows][cin_pad] (zero padded): conv weights for the bf16 tensor-core path
 __global__ void weights_to_bf16_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, size_t rows,
                                        int cin, int cin_pad) {
@@ -1065,7 +1111,12 @@ int upsample2x_add(const void* src, void* dst, int N, int Hs, int Ws, int C, int
   const float rx = Wd > 1 ? static_cast<float>(Ws - 1) / static_cast<float>(Wd - 1) : 0.f;
   const size_t total = static_cast<size_t>(N) * Hd * Wd * (C / 4);
   const unsigned g = static_cast<unsigned>((total + 255) / 256);
-  if (src_bf16 && dst_bf16) upsample2x_add_kernel<true, true><<<g, 256, 0, st>>>(src, dst, N, Hs, Ws, C / 4, lds, ldd, ry, rx);
+  if (dst_bf16 && (ldd % 8 == 0) && (lds % (src_bf16 ? 8 : 4) == 0) && (C + 7) / 8 * 8 <= ldd && (C + 7) / 8 * 8 <= lds) {
+    const int C8 = (C + 7) / 8;
+    const dim3 g8(static_cast<unsigned>((Wd * C8 + 255) / 256), static_cast<unsigned>(Hd), static_cast<unsigned>(N));
+    if (src_bf16) upsample2x_add8_kernel<true><<<g8, 256, 0, st>>>(src, dst, Hs, Ws, C8, lds, ldd, ry, rx);
+    else upsample2x_add8_kernel<false><<<g8, 256, 0, st>>>(src, dst, Hs, Ws, C8, lds, ldd, ry, rx);
+  } else if (src_bf16 && dst_bf16) upsample2x_add_kernel<true, true><<<g, 256, 0, st>>>(src, dst, N, Hs, Ws, C / 4, lds, ldd, ry, rx);
   else if (!src_bf16 && dst_bf16) upsample2x_add_kernel<false, true><<<g, 256, 0, st>>>(src, dst, N, Hs, Ws, C / 4, lds, ldd, ry, rx);
   else if (!src_bf16 && !dst_bf16) upsample2x_add_kernel<false, false><<<g, 256, 0, st>>>(src, dst, N, Hs, Ws, C / 4, lds, ldd, ry, rx);
   else return MFR_ERR_UNSUPPORTED;

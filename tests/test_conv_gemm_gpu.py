@@ -78,7 +78,8 @@ def test_conv_matches_torch(mfr, N, H, W, Cin, Cout, R, stride, act, use_bias, u
     _check(out, ref)
 
 
-@pytest.mark.parametrize("force", ["0,1,-1", "1,1,8", "1,1,16", "1,2,8", "1,2,16", "1,2,32", "0,2,-1", "1,1,128"])
+@pytest.mark.parametrize("force", ["0,1,-1", "1,1,8", "1,1,16", "1,2,8,0", "1,2,16,0", "1,2,32,0", "0,2,-1", "1,1,128",
+                                   "1,2,8,1", "1,2,16,1", "1,2,32,1"])
 @pytest.mark.parametrize("N,H,W,Cin,Cout,use_res", [
     (2, 70, 52, 128, 128, True),      # ragged in x and y for every tile shape
     (1, 37, 50, 196, 196, False),     # BN = 208 (MT stays 1), channel tail in K
@@ -86,7 +87,8 @@ def test_conv_matches_torch(mfr, N, H, W, Cin, Cout, R, stride, act, use_bias, u
 ])
 def test_conv3x3_tilings_agree(mfr, monkeypatch, force, N, H, W, Cin, Cout, use_res):
     """Every tiling of the 3x3 stride-1 path (per-tap A loads vs halo A box shared by the three ky taps,
-    one or two 128-pixel sub-tiles per CTA) against the fp64 reference."""
+    one or two 128-pixel sub-tiles per CTA, swapped operands = filters as M / 256 pixels as N) against the
+    fp64 reference. Force string: halo,MT,TW[,swap]; shapes a mode cannot take fall back to the free search."""
     monkeypatch.setenv("MFR_CONV_FORCE", force)
     g = torch.Generator(device="cpu").manual_seed(4321)
     x = torch.randn(N, H, W, Cin, generator=g).cuda()
@@ -139,6 +141,14 @@ def test_batched_xyt(mfr):
     _check(out[:, 0], ref)
 
 
+@pytest.mark.parametrize("force", ["-1,-1,-1,0", "1,2,16,1"])
+def test_bf16_conv_swapped_operands(mfr, monkeypatch, force):
+    """bf16 residual block conv (layer1 shape class) with and without the swapped-operand mode."""
+    monkeypatch.setenv("MFR_CONV_FORCE", force)
+    _bf16_conv_case(mfr, 2, 72, 48, 128, 128, 3, 1, True, True)
+    _bf16_conv_case(mfr, 2, 40, 36, 196, 128, 3, 1, False, False)
+
+
 @pytest.mark.parametrize("N,H,W,Cin,Cout,R,stride,out_bf16,use_res", [
     (2, 40, 36, 128, 128, 3, 1, True, True),
     (2, 40, 36, 128, 196, 3, 2, True, False),
@@ -146,6 +156,10 @@ def test_batched_xyt(mfr):
     (1, 1, 300, 256, 256, 1, 1, False, False),
 ])
 def test_bf16_conv_matches_torch(mfr, N, H, W, Cin, Cout, R, stride, out_bf16, use_res):
+    _bf16_conv_case(mfr, N, H, W, Cin, Cout, R, stride, out_bf16, use_res)
+
+
+def _bf16_conv_case(mfr, N, H, W, Cin, Cout, R, stride, out_bf16, use_res):
     """bf16 operands / fp32 accumulate vs an fp64 reference on the same bf16-rounded inputs
     (tolerance 1e-2 of the output range covers the bf16 rounding of the output itself)."""
     lib = mfr.load()
