@@ -228,28 +228,37 @@ __device__ __forceinline__ void epilogue_tile_swap(const ConvGemmParams& p, uint
   if (p.bias != nullptr && n_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
   const float alpha = p.alpha;
   const int tw_shift = 31 - __clz(p.TW);              // TW is a power of two in halo mode
-  // pixel k*4+sub_r of chunk c0 -> element offset of its channel n in an NHWC map with pixel stride ld, or -1
-  auto pix_off = [&](int c0, int k, long long img_stride, long long ld) -> long long {
+  // pixel k*4+sub_r of chunk c0 -> its index inside the image (y*Wo + x, fits 32 bits), or -1 when it is not stored
+  auto pix_of = [&](int c0, int k) -> int {
     const int pr = c0 + k * 4 + sub_r;                // pixel of the tile, (y, x) order over TW columns
     const int ly = pr >> tw_shift, lx = pr & (p.TW - 1);
     const int y = ty * tile_rows + ly, x = tx * p.TW + lx;
-    if (!(n_ok && y < p.Ho && x < w_lim)) return -1;
-    return img * img_stride + (static_cast<long long>(y) * p.Wo + x) * ld + n;
+    return (n_ok && y < p.Ho && x < w_lim) ? y * p.Wo + x : -1;
   };
+  const int ldo = static_cast<int>(p.ldo), ldr = static_cast<int>(p.ldr);      // per-image offsets fit 32 bits
+  float* out_img = OBF ? reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(p.out) + img * p.out_img_stride + n)
+                       : p.out + img * p.out_img_stride + n;
+  const float* res_img = nullptr;
+  if constexpr (RES)
+    res_img = OBF ? reinterpret_cast<const float*>(reinterpret_cast<const uint16_t*>(p.residual) + img * p.res_img_stride + n)
+                  : p.residual + img * p.res_img_stride + n;
   RT rnext[8];
-  auto issue_res = [&](int c0) {                      // residual of chunk c0, fetched one chunk ahead of its use
+  int pnext[8];
+  auto prefetch = [&](int c0) {                       // pixel indices (and residual) of chunk c0, one chunk ahead of its use
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      if constexpr (OBF) rnext[k] = make_uint2(0u, 0u);
-      else rnext[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      const long long ro = pix_off(c0, k, p.res_img_stride, p.ldr);
-      if (ro >= 0) {
-        if constexpr (OBF) rnext[k] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + ro));
-        else rnext[k] = __ldg(reinterpret_cast<const float4*>(p.residual + ro));
+      pnext[k] = pix_of(c0, k);
+      if constexpr (RES) {
+        if constexpr (OBF) rnext[k] = make_uint2(0u, 0u);
+        else rnext[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pnext[k] >= 0) {
+          if constexpr (OBF) rnext[k] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(res_img) + pnext[k] * ldr));
+          else rnext[k] = __ldg(reinterpret_cast<const float4*>(res_img + pnext[k] * ldr));
+        }
       }
     }
   };
-  if constexpr (RES) issue_res(0);
+  prefetch(0);
   mbar_wait(wait_bar, wait_phase, 4);
   tc_fence_after();
   for (int c0 = 0; c0 < 2 * kTileM; c0 += 32) {
@@ -260,15 +269,16 @@ __device__ __forceinline__ void epilogue_tile_swap(const ConvGemmParams& p, uint
     for (int j = 0; j < 32; ++j) stg[j * kStgStride + lane] = __uint_as_float(r[j]);
     __syncwarp();
     RT rcur[8];
-    if constexpr (RES) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) rcur[k] = rnext[k];
-      if (c0 + 32 < 2 * kTileM) issue_res(c0 + 32);
-    }
+    int pcur[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const long long oo = pix_off(c0, k, p.out_img_stride, p.ldo);
-      if (oo < 0) continue;
+      pcur[k] = pnext[k];
+      if constexpr (RES) rcur[k] = rnext[k];
+    }
+    if (c0 + 32 < 2 * kTileM) prefetch(c0 + 32);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (pcur[k] < 0) continue;
       float4 v = *reinterpret_cast<const float4*>(stg + (k * 4 + sub_r) * kStgStride + sub_c);
       v.x = fmaf(v.x, alpha, b4.x); v.y = fmaf(v.y, alpha, b4.y);
       v.z = fmaf(v.z, alpha, b4.z); v.w = fmaf(v.w, alpha, b4.w);
@@ -280,9 +290,9 @@ __device__ __forceinline__ void epilogue_tile_swap(const ConvGemmParams& p, uint
       }
       v.x = act_fn<ACT>(v.x); v.y = act_fn<ACT>(v.y); v.z = act_fn<ACT>(v.z); v.w = act_fn<ACT>(v.w);
       if constexpr (OBF)
-        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + oo) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out_img) + pcur[k] * ldo) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
       else
-        *reinterpret_cast<float4*>(p.out + oo) = v;
+        *reinterpret_cast<float4*>(out_img + pcur[k] * ldo) = v;
     }
     __syncwarp();
   }
