@@ -325,6 +325,9 @@ __device__ __forceinline__ void epilogue_subtile_scalar(const ConvGemmParams& p,
 // 64-bit shared-memory matrix descriptor = constant high part | ((address >> 4) & 0x3fff)
 constexpr uint64_t kDescHi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 __device__ __forceinline__ uint64_t desc_at(uint32_t addr) { return kDescHi | ((addr >> 4) & 0x3fffu); }
+// same for 32-byte rows with the 32B swizzle (8-row groups 256 B apart): the narrow channel-tail tiles
+constexpr uint64_t kDescHi32 = (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);
+__device__ __forceinline__ uint64_t desc32_at(uint32_t addr) { return kDescHi32 | ((addr >> 4) & 0x3fffu); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -354,6 +357,8 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < 4 * kMaxSlots; ++s) mbar_init(bar_base + 8u * s, 1);
+    if (p.mcast)   // a shared weight slot is free when BOTH CTAs of the pair have consumed it
+      for (int s = 0; s < kMaxSlots; ++s) mbar_init(b_empty(s), 2);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kEpiWarps);
@@ -367,6 +372,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.mcast) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
   const uint32_t tmem_base = s_tmem_base;
   if (threadIdx.x == 0) MFR_STAMP(1);
 
@@ -378,6 +384,22 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   const int m_tiles = p.N * p.tiles_y * tiles_x;
   const int total_tiles = m_tiles * p.n_tiles;
   const int tile_rows = p.MT * p.TH;          // output rows of one CTA tile
+  // work items: tiles (item -> tile), or in multicast mode PAIRS of neighbouring pixel tiles of one N tile
+  // (item -> pair; this CTA takes tile 2*pm + rank of the pair, the last odd one is computed twice)
+  const int crank = p.mcast ? static_cast<int>(cluster_ctarank()) : 0;
+  const int pairs_per_nt = (m_tiles + 1) >> 1;
+  const int item_first = p.mcast ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int item_step = p.mcast ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int item_count = p.mcast ? pairs_per_nt * p.n_tiles : total_tiles;
+  auto item_tile = [&](int item, int& mt, int& nt) {
+    if (p.mcast) {
+      nt = item / pairs_per_nt;
+      mt = min(2 * (item - nt * pairs_per_nt) + crank, m_tiles - 1);
+    } else {
+      nt = item / m_tiles;
+      mt = item - nt * m_tiles;
+    }
+  };
   // The two issue loops below are executed by whole (converged) warps with elect.sync around the
   // TMA / MMA instructions, and keep their per-k-block instruction count minimal: with one thread
   // issuing, instruction latency is what bounds them.
@@ -389,8 +411,9 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     // ------------------------------------------------------------------ TMA producer
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile % m_tiles, nt = tile / m_tiles;
+    for (int item = item_first; item < item_count; item += item_step) {
+      int mt, nt;
+      item_tile(item, mt, nt);
       const int tx = mt % tiles_x;
       const int ty = (mt / tiles_x) % p.tiles_y;
       const int img = mt / (tiles_x * p.tiles_y);
@@ -400,18 +423,26 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       if (p.halo) {
         for (int cb = 0; cb < kb_per_tap; ++cb) {
           const int c0 = cb * kblk;
+          const bool tail = p.tail32 && cb == kb_per_tap - 1;       // narrow boxes for the channel tail
+          const CUtensorMap* tmA = tail ? &p.tmA2 : &p.tmA;
+          const CUtensorMap* tmB = tail ? &p.tmB2 : &p.tmB;
+          const uint32_t ab = tail ? p.a_bytes2 : a_bytes, bb = tail ? p.b_bytes2 : b_bytes;
           for (int kx = 0; kx < 3; ++kx) {
             mbar_wait(a_empty(sa), pa ^ 1u, 1);
             if (elect_one_sync()) {
-              mbar_arrive_expect_tx(a_full(sa), a_bytes);
-              tma_load_4d(smem_a + sa * a_slot_bytes, &p.tmA, a_full(sa), c0, x_in0 + kx, y_in0, img);
+              mbar_arrive_expect_tx(a_full(sa), ab);
+              tma_load_4d(smem_a + sa * a_slot_bytes, tmA, a_full(sa), c0, x_in0 + kx, y_in0, img);
             }
             if (++sa == a_slots) { sa = 0; pa ^= 1u; }
             for (int ky = 0; ky < 3; ++ky) {
               mbar_wait(b_empty(sb), pb ^ 1u, 5);
               if (elect_one_sync()) {
-                mbar_arrive_expect_tx(b_full(sb), b_bytes);
-                tma_load_3d(smem_b + sb * b_bytes, &p.tmB, b_full(sb), c0, ky * 3 + kx, n0);
+                mbar_arrive_expect_tx(b_full(sb), bb);
+                if (p.mcast)   // my half of the filter rows, to both CTAs of the pair
+                  tma_load_3d_mcast(smem_b + sb * b_bytes + crank * (bb >> 1), tmB, b_full(sb), c0, ky * 3 + kx,
+                                    n0 + crank * (p.BN >> 1), static_cast<uint16_t>(3));
+                else
+                  tma_load_3d(smem_b + sb * b_bytes, tmB, b_full(sb), c0, ky * 3 + kx, n0);
               }
               if (++sb == b_slots) { sb = 0; pb ^= 1u; }
             }
@@ -421,14 +452,18 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
         const int bz = p.b_batched ? img : -1;
         for (int cb = 0; cb < kb_per_tap; ++cb) {
           const int c0 = cb * kblk;
+          const bool tail = p.tail32 && cb == kb_per_tap - 1;
+          const CUtensorMap* tmA = tail ? &p.tmA2 : &p.tmA;
+          const CUtensorMap* tmB = tail ? &p.tmB2 : &p.tmB;
+          const uint32_t ab = tail ? p.a_bytes2 + p.b_bytes2 : a_bytes + b_bytes;
           int tap = 0;
           for (int ky = 0; ky < R; ++ky) {
             for (int kx = 0; kx < S; ++kx, ++tap) {
               mbar_wait(a_empty(sa), pa ^ 1u, 1);
               if (elect_one_sync()) {
-                mbar_arrive_expect_tx(a_full(sa), a_bytes + b_bytes);
-                tma_load_4d(smem_a + sa * a_slot_bytes, &p.tmA, a_full(sa), c0, x_in0 + kx, y_in0 + ky, img);
-                tma_load_3d(smem_b + sa * b_bytes, &p.tmB, a_full(sa), c0, bz >= 0 ? bz : tap, n0);
+                mbar_arrive_expect_tx(a_full(sa), ab);
+                tma_load_4d(smem_a + sa * a_slot_bytes, tmA, a_full(sa), c0, x_in0 + kx, y_in0 + ky, img);
+                tma_load_3d(smem_b + sa * b_bytes, tmB, a_full(sa), c0, bz >= 0 ? bz : tap, n0);
               }
               if (++sa == a_slots) { sa = 0; pa ^= 1u; }
             }
@@ -447,7 +482,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int item = item_first; item < item_count; item += item_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
@@ -457,6 +492,9 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       if (p.halo) {
         for (int cb = 0; cb < kb_per_tap; ++cb) {
           const int nk = cb == kb_per_tap - 1 ? ksteps_last : kBlockK / kUmmaK;
+          const bool tail = p.tail32 && cb == kb_per_tap - 1;   // 32-byte rows: one k-step, 32B-swizzle descriptors
+          const uint64_t dhi = tail ? kDescHi32 : kDescHi;
+          const uint32_t subb = tail ? sub_bytes >> 2 : sub_bytes, kyb = tail ? ky_bytes >> 2 : ky_bytes;
           for (int kx = 0; kx < 3; ++kx) {
             mbar_wait(a_full(sa), pa, 3);
             const uint32_t a_slot = smem_a + sa * a_slot_bytes;
@@ -466,8 +504,8 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
               tc_fence_after();
               if (p.swap) {
                 if (elect_one_sync()) {   // filters are the M operand, the tile's 256 pixels the N operand
-                  const uint64_t wdesc = desc_at(smem_b + sb * b_bytes);
-                  const uint64_t xdesc = desc_at(a_slot + ky * ky_bytes);
+                  const uint64_t wdesc = dhi | (((smem_b + sb * b_bytes) >> 4) & 0x3fffu);
+                  const uint64_t xdesc = dhi | (((a_slot + ky * kyb) >> 4) & 0x3fffu);
                   uint32_t acc_m = accum;
                   for (int k = 0; k < nk; ++k) {
                     if (bf16_in) tc_mma_bf16(tmem_acc, wdesc + 2 * k, xdesc + 2 * k, idesc_swap, acc_m);
@@ -476,9 +514,9 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
                   }
                 }
               } else if (elect_one_sync()) {
-                const uint64_t bdesc = desc_at(smem_b + sb * b_bytes);
+                const uint64_t bdesc = dhi | (((smem_b + sb * b_bytes) >> 4) & 0x3fffu);
                 for (int m = 0; m < MT; ++m) {
-                  const uint64_t adesc = desc_at(a_slot + m * sub_bytes + ky * ky_bytes);
+                  const uint64_t adesc = dhi | (((a_slot + m * subb + ky * kyb) >> 4) & 0x3fffu);
                   const uint32_t d_addr = tmem_acc + static_cast<uint32_t>(m * 128);
                   uint32_t acc_m = accum;
                   for (int k = 0; k < nk; ++k) {   // +32 B of K per step = +2 in the descriptor address field
@@ -494,11 +532,19 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
             // one pipeline drain per group: release the three B slots and the A slot together
             if (elect_one_sync()) {
               int s2 = sb0;
-              tc_commit(b_empty(s2));
-              if (++s2 == b_slots) s2 = 0;
-              tc_commit(b_empty(s2));
-              if (++s2 == b_slots) s2 = 0;
-              tc_commit(b_empty(s2));
+              if (p.mcast) {   // the weight slots are shared by the pair: tell both producers
+                tc_commit_mcast(b_empty(s2), 3);
+                if (++s2 == b_slots) s2 = 0;
+                tc_commit_mcast(b_empty(s2), 3);
+                if (++s2 == b_slots) s2 = 0;
+                tc_commit_mcast(b_empty(s2), 3);
+              } else {
+                tc_commit(b_empty(s2));
+                if (++s2 == b_slots) s2 = 0;
+                tc_commit(b_empty(s2));
+                if (++s2 == b_slots) s2 = 0;
+                tc_commit(b_empty(s2));
+              }
               tc_commit(a_empty(sa));
             }
             if (++sa == a_slots) { sa = 0; pa ^= 1u; }
@@ -514,10 +560,12 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
           ++in_batch;
           const bool close = in_batch == cbatch || i == num_kb - 1;
           if (elect_one_sync()) {
-            const uint64_t bdesc = desc_at(smem_b + sa * b_bytes);
+            const bool tail = p.tail32 && cb == kb_per_tap - 1;
+            const uint64_t dhi = tail ? kDescHi32 : kDescHi;
+            const uint64_t bdesc = dhi | (((smem_b + sa * b_bytes) >> 4) & 0x3fffu);
             const uint32_t a_slot = smem_a + sa * a_slot_bytes;
             for (int m = 0; m < MT; ++m) {
-              const uint64_t adesc = desc_at(a_slot + m * sub_bytes);
+              const uint64_t adesc = dhi | (((a_slot + m * (tail ? sub_bytes >> 2 : sub_bytes)) >> 4) & 0x3fffu);
               const uint32_t d_addr = tmem_acc + static_cast<uint32_t>(m * 128);
               uint32_t acc_m = accum;
               for (int k = 0; k < nk; ++k) {
@@ -557,10 +605,11 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     float* stg = reinterpret_cast<float*>(smem_raw + (smem_stg - smem_u32(smem_raw))) + (warp - 2) * (32 * kStgStride);
     const int sub_r = lane >> 3;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int item = item_first; item < item_count; item += item_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int mt = tile % m_tiles, nt = tile / m_tiles;
+      int mt, nt;
+      item_tile(item, mt, nt);
       const int tx = mt % tiles_x;
       const int ty = (mt / tiles_x) % p.tiles_y;
       const int img = mt / (tiles_x * p.tiles_y);
@@ -655,6 +704,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (p.mcast) cluster_sync_all();   // no CTA leaves while its peer may still multicast into its shared memory / barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -687,7 +737,7 @@ EncodeTiledFn get_encode_fn() {
 
 // Tiling of one op: output tile = MT sub-tiles of TW x TH (<= 128) pixels, BN output channels.
 struct TileCfg {
-  int TW, TH, MT, BN, n_tiles, halo, swap;
+  int TW, TH, MT, BN, n_tiles, halo, swap, mcast;
   double cost;
 };
 
@@ -721,7 +771,7 @@ RingCfg ring_cfg(int halo, int MT, int TW, int TH, int BN) {
 }
 
 TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, int pad, int kb_per_tap,
-                   int ksteps_last, bool allow_mt2, bool tma_store_ok, bool allow_swap) {
+                   int ksteps_last, bool allow_mt2, bool tma_store_ok, bool allow_swap, bool allow_mcast) {
   const int sms = conv_gemm_num_sms();
   const int c16 = (Cout + 15) / 16 * 16;
   const int taps = R * S;
@@ -730,10 +780,10 @@ TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, in
   TileCfg best{};
   best.cost = 1e300;
   // test hook: MFR_CONV_FORCE="halo,MT,TW" restricts the search (-1 = free); unusable values fall back to free
-  int f_halo = -1, f_mt = -1, f_tw = -1, f_swap = -1;
-  if (const char* e = getenv("MFR_CONV_FORCE")) sscanf(e, "%d,%d,%d,%d", &f_halo, &f_mt, &f_tw, &f_swap);
+  int f_halo = -1, f_mt = -1, f_tw = -1, f_swap = -1, f_mc = -1;
+  if (const char* e = getenv("MFR_CONV_FORCE")) sscanf(e, "%d,%d,%d,%d,%d", &f_halo, &f_mt, &f_tw, &f_swap, &f_mc);
   for (int pass = 0; pass < 2 && best.cost > 1e299; ++pass) {
-  if (pass == 1) f_halo = f_mt = f_tw = f_swap = -1;
+  if (pass == 1) f_halo = f_mt = f_tw = f_swap = f_mc = -1;
   const int nt0 = (c16 + kMaxBN - 1) / kMaxBN;
   for (int nt = nt0; nt <= nt0 * 4; nt *= 2) {
     const int BN = ((c16 / 16 + nt - 1) / nt) * 16;
@@ -765,8 +815,18 @@ TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, in
           const double epi = MT * ((BN + 31) / 32) * (tma_epi ? 250.0 : 500.0);
           const double t = std::max(mma, std::max(l2, epi)) + 800.0;
           const double cost = static_cast<double>((tiles + sms - 1) / sms) * t;
-          if (f_swap != 1 && (cost < best.cost * (1.0 - 1e-9) || (cost < best.cost * (1.0 + 1e-9) && tw > best.TW))) {
-            best = TileCfg{tw, th, MT, BN, nt, halo, 0, cost};
+          if (f_swap != 1 && f_mc != 1 && (cost < best.cost * (1.0 - 1e-9) || (cost < best.cost * (1.0 + 1e-9) && tw > best.TW))) {
+            best = TileCfg{tw, th, MT, BN, nt, halo, 0, 0, cost};
+          }
+          // CTA pairs sharing the weight tiles by TMA multicast: half the weight bytes per CTA through L2
+          if (halo && allow_mcast && f_mc != 0 && f_swap != 1 && BN % 16 == 0) {
+            const long long m_tiles_c = tiles / nt;
+            const long long pairs = ((m_tiles_c + 1) / 2) * nt;
+            const double l2_m = (a_bytes + 0.5 * b_bytes) / 100.0;
+            const double t_m = std::max(mma, std::max(l2_m, epi)) + 800.0;
+            const int clusters = sms / 2;
+            const double cost_m = static_cast<double>((pairs + clusters - 1) / clusters) * t_m;
+            if (cost_m < best.cost * (1.0 - 0.03)) best = TileCfg{tw, th, MT, BN, nt, 1, 0, 1, cost_m};   // needs a clear win
           }
           // swapped operands: the MT = 2 halo geometry with the filters as the M operand (Cout <= 128, one N tile)
           if (halo && MT == 2 && nt == nt0 && c16 <= 128 && allow_swap && f_swap != 0 && (tw & (tw - 1)) == 0) {
@@ -774,7 +834,7 @@ TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, in
             const double b_s = 128.0 * 128.0 * taps * kb_per_tap;
             const double t_s = std::max(mma_s, std::max((a_bytes + b_s) / 100.0, 8 * 500.0)) + 800.0;
             const double cost_s = static_cast<double>((tiles + sms - 1) / sms) * t_s;
-            if (cost_s < best.cost * (1.0 - 1e-9)) best = TileCfg{tw, th, 2, 128, 1, 1, 1, cost_s};
+            if (cost_s < best.cost * (1.0 - 1e-9)) best = TileCfg{tw, th, 2, 128, 1, 1, 1, 0, cost_s};
           }
         }
       }
@@ -782,8 +842,8 @@ TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, in
   }
   }
   if (getenv("MFR_CONV_DEBUG"))
-    fprintf(stderr, "[conv_gemm cfg] N%d %dx%d Cout%d R%d s%d kb%d -> TW%d TH%d MT%d BN%d nt%d halo%d swap%d cost %.0f\n", N, Ho, Wo,
-            Cout, R, stride, kb_per_tap, best.TW, best.TH, best.MT, best.BN, best.n_tiles, best.halo, best.swap, best.cost);
+    fprintf(stderr, "[conv_gemm cfg] N%d %dx%d Cout%d R%d s%d kb%d -> TW%d TH%d MT%d BN%d nt%d halo%d swap%d mcast%d cost %.0f\n", N, Ho, Wo,
+            Cout, R, stride, kb_per_tap, best.TW, best.TH, best.MT, best.BN, best.n_tiles, best.halo, best.swap, best.mcast, best.cost);
   return best;
 }
 
@@ -828,13 +888,19 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
     const int tail = d.Cin - (p->kb_per_tap - 1) * kblk;
     const int ummak = kblk / 4;
     p->ksteps_last = (tail + ummak - 1) / ummak;
+    // a tail of one k-step (<= 32 bytes of channels) is moved as 32-byte-wide tiles (32B swizzle) instead of zero-filled
+    // 128-byte ones: Cin = 196 otherwise spends a quarter of its operand traffic on 4 channels
+    p->tail32 = (p->ksteps_last == 1 && tail * es <= 32 && p->kb_per_tap > 1 && getenv("MFR_CONV_NO_TAIL32") == nullptr) ? 1 : 0;
   }
   const TileCfg cfg = choose_cfg(d.N, p->Ho, p->Wo, d.Cout, d.R, d.S, d.stride, d.pad, p->kb_per_tap, p->ksteps_last,
                                  d.dyn_w == nullptr, !d.out_bf16 && d.residual == nullptr,
                                  // swapped operands: not with a residual (measured: its transposed epilogue then becomes the bottleneck)
                                  (d.Cout % 4 == 0) && (d.ldo % 4 == 0) && !d.b_batched &&
-                                     (d.residual == nullptr || (getenv("MFR_CONV_FORCE") != nullptr && d.ldr % 4 == 0)));
-  p->TW = cfg.TW; p->TH = cfg.TH; p->MT = cfg.MT; p->halo = cfg.halo; p->swap = cfg.swap;
+                                     (d.residual == nullptr || (getenv("MFR_CONV_FORCE") != nullptr && d.ldr % 4 == 0)),
+                                 // CTA-pair weight multicast: measured no gain on B200 for these shapes (the layers are not L2-bound once the
+                                 // channel tail is narrow), so it is opt-in (MFR_CONV_MCAST=1 or the test hook)
+                                 !d.b_batched && d.dyn_w == nullptr && (getenv("MFR_CONV_MCAST") != nullptr || getenv("MFR_CONV_FORCE") != nullptr));
+  p->TW = cfg.TW; p->TH = cfg.TH; p->MT = cfg.MT; p->halo = cfg.halo; p->swap = cfg.swap; p->mcast = cfg.mcast;
   p->BN = cfg.BN; p->n_tiles = cfg.n_tiles;
   p->tiles_x = (p->Wo + p->TW - 1) / p->TW;
   p->tiles_y = (p->Ho + p->MT * p->TH - 1) / (p->MT * p->TH);
@@ -878,6 +944,14 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
       fprintf(stderr, "[mfr_b200] cuTensorMapEncodeTiled(A) failed: %d\n", (int)r);
       return MFR_ERR_CUDA;
     }
+    if (p->tail32) {
+      box[0] = static_cast<cuuint32_t>(32 / es);
+      p->a_bytes2 = p->a_bytes / 4;
+      r = enc(&p->tmA2, d.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+              const_cast<float*>(d.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) p->tail32 = 0;
+    }
   }
   {  // TMA-store epilogue: fp32 output without residual, power-of-two TW, whole 32-channel chunks per N tile
     const bool pow2 = (p->TW & (p->TW - 1)) == 0;
@@ -913,7 +987,7 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
       strides[0] = (cuuint64_t)ldw_e * es;
       strides[1] = (cuuint64_t)ldw_e * es * taps;
     }
-    cuuint32_t box[3] = {(cuuint32_t)kblk, 1, (cuuint32_t)p->BN};
+    cuuint32_t box[3] = {(cuuint32_t)kblk, 1, (cuuint32_t)(p->mcast ? p->BN / 2 : p->BN)};   // multicast: each CTA of the pair loads half the rows
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&p->tmB, d.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                      const_cast<float*>(d.w), dims,
@@ -922,6 +996,17 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
     if (r != CUDA_SUCCESS) {
       fprintf(stderr, "[mfr_b200] cuTensorMapEncodeTiled(B) failed: %d\n", (int)r);
       return MFR_ERR_CUDA;
+    }
+    if (p->tail32) {
+      box[0] = static_cast<cuuint32_t>(32 / es);
+      p->b_bytes2 = p->b_bytes / 4;
+      r = enc(&p->tmB2, d.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+              const_cast<float*>(d.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[mfr_b200] cuTensorMapEncodeTiled(B tail) failed: %d\n", (int)r);
+        return MFR_ERR_CUDA;   // tmA2 exists already: both or neither
+      }
     }
   }
   return MFR_OK;
@@ -936,6 +1021,23 @@ int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream) {
   }
   const int total = p.N * p.tiles_y * p.tiles_x * p.n_tiles;
   if (total <= 0) return MFR_OK;
+  if (p.mcast) {   // clusters of two CTAs, one pair of pixel tiles per cluster iteration
+    const int m_tiles = p.N * p.tiles_y * p.tiles_x;
+    const int pairs = ((m_tiles + 1) / 2) * p.n_tiles;
+    const int clusters = std::min(pairs, conv_gemm_num_sms() / 2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    MFR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_tf32_kernel, p));
+    return MFR_OK;
+  }
   const int grid = std::min(total, conv_gemm_num_sms());
   conv_gemm_tf32_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
   MFR_CUDA_CHECK(cudaGetLastError());
@@ -1081,8 +1183,8 @@ float conv_gemm_time_prebuilt(const ConvGemmParams& p, int iters, cudaStream_t s
                              "c0 tmem loaded", "c0 staged", "c0 stored"};
     fprintf(stderr, "[conv_gemm stamps, block 0, ns since start]");
     for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] ? h[i] - h[0] : -1);
-    fprintf(stderr, "\n[conv_gemm cfg] TW%d TH%d MT%d BN%d nt%d halo%d swap%d slots %d/%d cbatch %d\n", p.TW, p.TH, p.MT, p.BN,
-            p.n_tiles, p.halo, p.swap, p.a_slots, p.b_slots, p.cbatch);
+    fprintf(stderr, "\n[conv_gemm cfg] TW%d TH%d MT%d BN%d nt%d halo%d swap%d mcast%d slots %d/%d cbatch %d\n", p.TW, p.TH, p.MT, p.BN,
+            p.n_tiles, p.halo, p.swap, p.mcast, p.a_slots, p.b_slots, p.cbatch);
   }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);

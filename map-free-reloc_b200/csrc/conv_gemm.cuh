@@ -16,6 +16,8 @@ enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_ELU1 = 3 };
 struct alignas(64) ConvGemmParams {
   CUtensorMap tmA;  // rank 4 {C, W, H, N}   box {32|64, TW*s, MT*TH*s (halo: MT*TH+2), 1}, 128B swizzle, zero OOB fill
   CUtensorMap tmB;  // rank 3 {Cin, Z, Cout} box {32, 1, BN}          (Z = filter tap or image)
+  CUtensorMap tmA2; // channel tail (tail32): same tensors, 32-byte-wide boxes, 32B swizzle — the last k-block of a tap then moves
+  CUtensorMap tmB2; //   a quarter of the bytes (Cin = 196 leaves 4 channels for it) and issues one MMA per tap
   CUtensorMap tmC;  // rank 4 {Cout, Wo, Ho, N} fp32, box {32, min(TW,32), 32/min(TW,32), 1}, 128B swizzle (TMA-store epilogue)
   int N, Ho, Wo, Cout, Cin;
   int R, S, stride, pad;
@@ -27,11 +29,16 @@ struct alignas(64) ConvGemmParams {
                           // ky taps read it at row offsets 0, TW, 2*TW (TW % 8 == 0 keeps the swizzle phase)
   int swap;               // halo mode with swapped operands (Cout <= 128): M = 128 filters, N = the 256 pixels of the tile —
                           // one N = 256 MMA per k-step instead of two N = 128 ones (92 ns vs 2 x 61 ns); TMEM lane = filter
+  int mcast;              // halo mode in clusters of two CTAs: the pair works on neighbouring pixel tiles of the same N tile
+                          // and shares every weight tile — each CTA loads half of its rows and TMA-multicasts them to
+                          // both (the 196-channel layers are bound by L2 -> SM operand traffic, mostly weights)
   int a_slots, b_slots;   // depth of the A ring / B ring (two rings: one A slot serves 3 B tiles in halo mode)
   int a_slot_bytes;
   int tma_store;          // epilogue writes 32 px x 32 ch fp32 chunks with cp.async.bulk.tensor stores (see conv_gemm.cu)
   int cbatch;             // generic mode: k-blocks whose slots are released by one tcgen05.commit batch (pipe drain)
   int ksteps_last;        // MMAs issued for the last k-block of a tap (channel tail)
+  int tail32;             // the tail fits one 32-byte k-step: it is loaded through tmA2 / tmB2 (a_bytes2 / b_bytes2 per load)
+  int a_bytes2, b_bytes2;
   int act, act_cols;    // activation applies to output channels < act_cols
   int in_bf16, out_bf16;  // operands bf16 (kind::f16) instead of fp32 (kind::tf32); out/residual bf16
   int kblk;             // K elements per 128-byte k-block: 32 (fp32) or 64 (bf16)

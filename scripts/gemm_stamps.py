@@ -6,7 +6,7 @@ import torch
 import mfr_b200
 from mfr_b200 import lib as mfr
 lib = mfr.load()
-SHAPES = ((8, 360, 272, 128, 128, 3, 1), (8, 180, 136, 256, 256, 3, 1), (1, 1, 48960, 256, 256, 1, 1), (1, 1, 48960, 512, 512, 1, 1), (8, 360, 272, 128, 196, 3, 2))
+SHAPES = ((8, 360, 272, 128, 128, 3, 1), (8, 180, 136, 256, 256, 3, 1), (1, 1, 48960, 256, 256, 1, 1), (1, 1, 48960, 512, 512, 1, 1), (8, 360, 272, 128, 196, 3, 2), (8, 360, 272, 192, 196, 3, 1), (8, 360, 272, 196, 196, 3, 1), (8, 180, 136, 196, 196, 3, 1), (8, 360, 272, 196, 128, 3, 1))
 for bf in [int(a) for a in os.environ.get('BF', '0,1').split(',')]:
     for res in [int(a) for a in os.environ.get('RES', '0,1').split(',')]:
         for (N, H, W, cin, cout, R, s) in SHAPES:

@@ -79,7 +79,7 @@ def test_conv_matches_torch(mfr, N, H, W, Cin, Cout, R, stride, act, use_bias, u
 
 
 @pytest.mark.parametrize("force", ["0,1,-1", "1,1,8", "1,1,16", "1,2,8,0", "1,2,16,0", "1,2,32,0", "0,2,-1", "1,1,128",
-                                   "1,2,8,1", "1,2,16,1", "1,2,32,1"])
+                                   "1,2,8,1", "1,2,16,1", "1,2,32,1", "1,1,16,0,1", "1,2,16,0,1", "1,1,8,0,1"])
 @pytest.mark.parametrize("N,H,W,Cin,Cout,use_res", [
     (2, 70, 52, 128, 128, True),      # ragged in x and y for every tile shape
     (1, 37, 50, 196, 196, False),     # BN = 208 (MT stays 1), channel tail in K
@@ -88,7 +88,8 @@ def test_conv_matches_torch(mfr, N, H, W, Cin, Cout, R, stride, act, use_bias, u
 def test_conv3x3_tilings_agree(mfr, monkeypatch, force, N, H, W, Cin, Cout, use_res):
     """Every tiling of the 3x3 stride-1 path (per-tap A loads vs halo A box shared by the three ky taps,
     one or two 128-pixel sub-tiles per CTA, swapped operands = filters as M / 256 pixels as N) against the
-    fp64 reference. Force string: halo,MT,TW[,swap]; shapes a mode cannot take fall back to the free search."""
+    fp64 reference. Force string: halo,MT,TW[,swap[,mcast]] (mcast = CTA pairs sharing the weight tiles by TMA multicast);
+    shapes a mode cannot take fall back to the free search."""
     monkeypatch.setenv("MFR_CONV_FORCE", force)
     g = torch.Generator(device="cpu").manual_seed(4321)
     x = torch.randn(N, H, W, Cin, generator=g).cuda()
