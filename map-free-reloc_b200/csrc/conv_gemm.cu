@@ -36,7 +36,8 @@ constexpr int kEpiWarps = 4;                    // 4 or 8 (two per TMEM lane qua
                                                 // 8 measured no faster: the store phase is bound by the memory system
 constexpr int kStgBytes = kEpiWarps * 32 * kStgStride * 4;  // epilogue transpose buffers, one per epilogue warp
 constexpr int kSmemBytes = kRingBytes + kStgBytes + 1024 /*align slack*/;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kThreads = 64 + 32 * kEpiWarps + 32;   // TMA producer, MMA issuer 0, epilogue warps, MMA issuer 1 (last warp)
+constexpr int kMma2Warp = 2 + kEpiWarps;
 constexpr int kTmemCols = 512;
 
 __device__ __forceinline__ long long gtime() {
@@ -332,7 +333,7 @@ __device__ __forceinline__ uint64_t desc32_at(uint32_t addr) { return kDescHi32 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bars[4 * kMaxSlots + 4];
+  __shared__ __align__(8) uint64_t s_bars[4 * kMaxSlots + 6];
   __shared__ uint32_t s_tmem_base;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
@@ -348,6 +349,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   auto b_empty = [&](int s) { return bar_base + 8u * (3 * kMaxSlots + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (4 * kMaxSlots + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (4 * kMaxSlots + 2 + a); };
+  auto tstart_bar = [&](int a) { return bar_base + 8u * (4 * kMaxSlots + 4 + a); };   // "the tile's first MMA is in the pipe"
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -360,8 +362,9 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     if (p.mcast)   // a shared weight slot is free when BOTH CTAs of the pair have consumed it
       for (int s = 0; s < kMaxSlots; ++s) mbar_init(b_empty(s), 2);
     for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
+      mbar_init(tfull_bar(a), 2);           // both MMA issuers commit the accumulator
       mbar_init(tempty_bar(a), kEpiWarps);
+      mbar_init(tstart_bar(a), 1);
     }
     fence_barrier_init();
   }
@@ -471,8 +474,15 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 || warp == kMma2Warp) {
+    // ------------------------------------------------------------------ MMA issuers
+    // Two warps issue alternate commit groups into the same accumulator: a tcgen05.commit stalls its issuing thread
+    // until the MMAs before it have drained (~215 ns); with a second instruction stream the pipe keeps running
+    // (measured: 12 MMAs per commit cost 96 ns each from one thread, 75 ns from two; profiles/r01_mma_probe2.txt).
+    // Only the very first MMA of a tile overwrites the accumulator, so the issuer that owns the tile's first group
+    // tells the other one (tstart barrier) once that group is in the pipe.
+    const int role = warp == 1 ? 0 : 1;
+    int gcount = 0;                           // commit groups issued so far by both issuers together (parity = owner)
     const uint32_t idesc = umma_idesc(p.in_bf16 ? 1u : 2u, kTileM, static_cast<uint32_t>(p.BN));
     const uint32_t idesc_swap = umma_idesc(p.in_bf16 ? 1u : 2u, kTileM, 2u * kTileM);
     const bool bf16_in = p.in_bf16 != 0;
@@ -488,14 +498,27 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
-      uint32_t accum = 0;   // first MMA of the tile overwrites the accumulator
+      const bool first_owner = (gcount & 1) == role;   // this issuer has the tile's first group
+      uint32_t accum = first_owner ? 0u : 1u;          // first MMA of the tile overwrites the accumulator
+      bool started = first_owner;
+      int g = 0;                                       // group index inside the tile
       if (p.halo) {
         for (int cb = 0; cb < kb_per_tap; ++cb) {
           const int nk = cb == kb_per_tap - 1 ? ksteps_last : kBlockK / kUmmaK;
           const bool tail = p.tail32 && cb == kb_per_tap - 1;   // 32-byte rows: one k-step, 32B-swizzle descriptors
           const uint64_t dhi = tail ? kDescHi32 : kDescHi;
           const uint32_t subb = tail ? sub_bytes >> 2 : sub_bytes, kyb = tail ? ky_bytes >> 2 : ky_bytes;
-          for (int kx = 0; kx < 3; ++kx) {
+          for (int kx = 0; kx < 3; ++kx, ++g) {
+            if (((gcount + g) & 1) != role) {           // the other issuer's group: just step over its slots
+              if (++sa == a_slots) { sa = 0; pa ^= 1u; }
+              for (int j = 0; j < 3; ++j)
+                if (++sb == b_slots) { sb = 0; pb ^= 1u; }
+              continue;
+            }
+            if (!started) {
+              mbar_wait(tstart_bar(acc), acc_phase, 9);
+              started = true;
+            }
             mbar_wait(a_full(sa), pa, 3);
             const uint32_t a_slot = smem_a + sa * a_slot_bytes;
             const int sb0 = sb;
@@ -547,6 +570,10 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
               }
               tc_commit(a_empty(sa));
             }
+            if (g == 0) {                              // (first_owner) the tile's first MMAs are queued
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tstart_bar(acc));
+            }
             if (++sa == a_slots) { sa = 0; pa ^= 1u; }
           }
         }
@@ -555,10 +582,20 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
         int in_batch = 0, batch_first = sa, tap = 0, cb = 0;
         for (int i = 0; i < num_kb; ++i) {
           const int nk = cb == kb_per_tap - 1 ? ksteps_last : kBlockK / kUmmaK;
-          mbar_wait(a_full(sa), pa, 3);
-          tc_fence_after();
           ++in_batch;
           const bool close = in_batch == cbatch || i == num_kb - 1;
+          if (((gcount + g) & 1) != role) {             // the other issuer's batch
+            if (++sa == a_slots) { sa = 0; pa ^= 1u; }
+            if (close) { in_batch = 0; batch_first = sa; ++g; }
+            if (++tap == taps) { tap = 0; ++cb; }
+            continue;
+          }
+          if (!started) {
+            mbar_wait(tstart_bar(acc), acc_phase, 9);
+            started = true;
+          }
+          mbar_wait(a_full(sa), pa, 3);
+          tc_fence_after();
           if (elect_one_sync()) {
             const bool tail = p.tail32 && cb == kb_per_tap - 1;
             const uint64_t dhi = tail ? kDescHi32 : kDescHi;
@@ -584,10 +621,17 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
           }
           accum = 1u;
           if (++sa == a_slots) { sa = 0; pa ^= 1u; }
-          if (close) { in_batch = 0; batch_first = sa; }
+          if (close) {
+            if (g == 0) {                              // (first_owner) the tile's first batch is queued
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tstart_bar(acc));
+            }
+            in_batch = 0; batch_first = sa; ++g;
+          }
           if (++tap == taps) { tap = 0; ++cb; }
         }
       }
+      gcount += g;
       if (elect_one_sync()) tc_commit(tfull_bar(acc));
     }
   } else {
@@ -1078,14 +1122,13 @@ namespace {
 __global__ void __launch_bounds__(kThreads, 1) mma_probe_kernel(int n_per_commit, int BN, int bf16, int wait_each,
                                                                  int iters, int two_commits) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bar[3];
+  __shared__ __align__(8) uint64_t mfr_probe_bars_s[6];
+  uint64_t* mfr_probe_bars = mfr_probe_bars_s;
   __shared__ uint32_t s_tmem_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&s_bar[0]), 1);
-    mbar_init(smem_u32(&s_bar[1]), 1);
-    mbar_init(smem_u32(&s_bar[2]), 1);
+    for (int k = 0; k < 6; ++k) mbar_init(smem_u32(&mfr_probe_bars[k]), 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -1096,9 +1139,14 @@ __global__ void __launch_bounds__(kThreads, 1) mma_probe_kernel(int n_per_commit
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
-  if (warp == 1 && lane == 0) {
+  // two_commits == 2 / 3: TWO issuing threads (warps 1 and 2) run the same loop concurrently, into the same (2) or into
+  // different (3) accumulators — does a second instruction stream keep the pipe busy while the first sits at its commit?
+  const bool second = two_commits >= 2 && warp == 2 && lane == 0;
+  if ((warp == 1 && lane == 0) || second) {
     const uint32_t idesc = umma_idesc(bf16 ? 1u : 2u, kTileM, static_cast<uint32_t>(BN));
-    const uint32_t a_addr = smem_base, b_addr = smem_base + 64 * 1024;
+    const uint32_t a_addr = smem_base + (second ? 96 * 1024 : 0), b_addr = smem_base + 64 * 1024;
+    const uint32_t tmem_base = s_tmem_base + ((second && two_commits == 3) ? 256u : 0u);
+    uint64_t* s_bar = mfr_probe_bars + (second ? 3 : 0);
     uint32_t phase = 0;
     for (int it = 0; it < iters; ++it) {
       for (int k = 0; k < n_per_commit; ++k) {
@@ -1109,7 +1157,7 @@ __global__ void __launch_bounds__(kThreads, 1) mma_probe_kernel(int n_per_commit
         else tc_mma_tf32(tmem_base, adesc, bdesc, idesc, 1u);
       }
       tc_commit(smem_u32(&s_bar[0]));
-      if (two_commits) tc_commit(smem_u32(&s_bar[2]));
+      if (two_commits == 1) tc_commit(smem_u32(&s_bar[2]));
       if (wait_each) {
         mbar_wait(smem_u32(&s_bar[0]), phase, 7);
         phase ^= 1u;
