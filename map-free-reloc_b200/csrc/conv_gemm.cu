@@ -36,8 +36,13 @@ constexpr int kEpiWarps = 4;                    // 4 or 8 (two per TMEM lane qua
                                                 // 8 measured no faster: the store phase is bound by the memory system
 constexpr int kStgBytes = kEpiWarps * 32 * kStgStride * 4;  // epilogue transpose buffers, one per epilogue warp
 constexpr int kSmemBytes = kRingBytes + kStgBytes + 1024 /*align slack*/;
-constexpr int kThreads = 64 + 32 * kEpiWarps + 32;   // TMA producer, MMA issuer 0, epilogue warps, MMA issuer 1 (last warp)
-constexpr int kMma2Warp = 2 + kEpiWarps;
+// Two MMA-issuing warps that alternate commit groups hide the commit stall (profiles/r01_mma_probe2.txt) and were
+// measured 3 % faster on the backbone, but the two instruction streams interleave in the pipe in a timing-dependent
+// order, so the fp32 accumulation order — and with it the last bits of the result — changes from run to run. The
+// engine promises bit-identical replays (tests/test_loftr_gpu.py), so the second issuer is compiled out.
+constexpr bool kDualIssue = false;
+constexpr int kThreads = 64 + 32 * kEpiWarps + (kDualIssue ? 32 : 0);   // TMA producer, MMA issuer, epilogue warps[, MMA issuer 1]
+constexpr int kMma2Warp = kDualIssue ? 2 + kEpiWarps : -1;
 constexpr int kTmemCols = 512;
 
 __device__ __forceinline__ long long gtime() {
@@ -362,7 +367,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     if (p.mcast)   // a shared weight slot is free when BOTH CTAs of the pair have consumed it
       for (int s = 0; s < kMaxSlots; ++s) mbar_init(b_empty(s), 2);
     for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 2);           // both MMA issuers commit the accumulator
+      mbar_init(tfull_bar(a), kDualIssue ? 2 : 1);   // every MMA issuer commits the accumulator
       mbar_init(tempty_bar(a), kEpiWarps);
       mbar_init(tstart_bar(a), 1);
     }
@@ -498,7 +503,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
-      const bool first_owner = (gcount & 1) == role;   // this issuer has the tile's first group
+      const bool first_owner = !kDualIssue || (gcount & 1) == role;   // this issuer has the tile's first group
       uint32_t accum = first_owner ? 0u : 1u;          // first MMA of the tile overwrites the accumulator
       bool started = first_owner;
       int g = 0;                                       // group index inside the tile
@@ -509,7 +514,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
           const uint64_t dhi = tail ? kDescHi32 : kDescHi;
           const uint32_t subb = tail ? sub_bytes >> 2 : sub_bytes, kyb = tail ? ky_bytes >> 2 : ky_bytes;
           for (int kx = 0; kx < 3; ++kx, ++g) {
-            if (((gcount + g) & 1) != role) {           // the other issuer's group: just step over its slots
+            if (kDualIssue && ((gcount + g) & 1) != role) {   // the other issuer's group: just step over its slots
               if (++sa == a_slots) { sa = 0; pa ^= 1u; }
               for (int j = 0; j < 3; ++j)
                 if (++sb == b_slots) { sb = 0; pb ^= 1u; }
@@ -570,7 +575,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
               }
               tc_commit(a_empty(sa));
             }
-            if (g == 0) {                              // (first_owner) the tile's first MMAs are queued
+            if (kDualIssue && g == 0) {                // (first_owner) the tile's first MMAs are queued
               __syncwarp();
               if (lane == 0) mbar_arrive(tstart_bar(acc));
             }
@@ -584,7 +589,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
           const int nk = cb == kb_per_tap - 1 ? ksteps_last : kBlockK / kUmmaK;
           ++in_batch;
           const bool close = in_batch == cbatch || i == num_kb - 1;
-          if (((gcount + g) & 1) != role) {             // the other issuer's batch
+          if (kDualIssue && ((gcount + g) & 1) != role) {     // the other issuer's batch
             if (++sa == a_slots) { sa = 0; pa ^= 1u; }
             if (close) { in_batch = 0; batch_first = sa; ++g; }
             if (++tap == taps) { tap = 0; ++cb; }
@@ -622,7 +627,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
           accum = 1u;
           if (++sa == a_slots) { sa = 0; pa ^= 1u; }
           if (close) {
-            if (g == 0) {                              // (first_owner) the tile's first batch is queued
+            if (kDualIssue && g == 0) {                // (first_owner) the tile's first batch is queued
               __syncwarp();
               if (lane == 0) mbar_arrive(tstart_bar(acc));
             }
