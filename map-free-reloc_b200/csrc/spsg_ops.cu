@@ -304,14 +304,17 @@ __global__ void kenc_input_kernel(const float* __restrict__ kpts, const float* _
 }
 
 // ------------------------------------------------------------------------------------------ softmax attention
-// 4 heads x 64 (superglue.py:85-89): out[q, h, :] = softmax_k(q.k / 8) v. 16 queries per block
-// (8 lanes per query), key/value tiles of 64 in shared memory, online softmax.
-constexpr int kAtQ = 16, kAtK = 64;
+// 4 heads x 64 (superglue.py:85-89): out[q, h, :] = softmax_k(q.k / 8) v. 32 queries per block: 8 lanes per PAIR
+// of queries (q, q + 16) — every key / value row read from shared memory feeds two queries, which halves the
+// shared-memory traffic the kernel is bound by. Key/value tiles of 64 rows in shared memory, online softmax.
+constexpr int kAtQ = 32, kAtK = 64;
 __global__ void __launch_bounds__(128) sg_attention_kernel(const float* __restrict__ qkv, long long ld,
                                                            const int* __restrict__ counts, int src_xor,
                                                            int max_kp, float* __restrict__ out, long long ldo) {
-  __shared__ float sK[kAtK][65];
-  __shared__ float sV[kAtK][65];
+  // row stride 68 floats: 16-byte aligned rows, and the 8 key rows a quarter-warp reads at once (kk = sub + 8j) start
+  // 4 banks apart, so a 128-bit read of all of them is conflict-free
+  __shared__ __align__(16) float sK[kAtK][68];
+  __shared__ __align__(16) float sV[kAtK][68];
   __shared__ float sP[kAtQ][kAtK + 1];
   const int img = blockIdx.z, head = blockIdx.y;
   const int src = img ^ src_xor;
@@ -319,21 +322,22 @@ __global__ void __launch_bounds__(128) sg_attention_kernel(const float* __restri
   const int q0 = blockIdx.x * kAtQ;
   if (q0 >= nq) return;
   const int t = threadIdx.x, qi = t >> 3, sub = t & 7;
-  const int q = q0 + qi;
-  const bool q_ok = q < nq;
-  float qr[64];
-  {
-    const float* qp = qkv + (static_cast<size_t>(img) * max_kp + (q_ok ? q : q0)) * ld + head * 64;
+  const int qa = q0 + qi, qb = q0 + qi + 16;
+  float qr[2][64];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int q = u == 0 ? qa : qb;
+    const float* qp = qkv + (static_cast<size_t>(img) * max_kp + (q < nq ? q : q0)) * ld + head * 64;
 #pragma unroll
     for (int d4 = 0; d4 < 16; ++d4) {
       const float4 f = *reinterpret_cast<const float4*>(qp + 4 * d4);
-      qr[4 * d4] = f.x * 0.125f; qr[4 * d4 + 1] = f.y * 0.125f; qr[4 * d4 + 2] = f.z * 0.125f; qr[4 * d4 + 3] = f.w * 0.125f;
+      qr[u][4 * d4] = f.x * 0.125f; qr[u][4 * d4 + 1] = f.y * 0.125f; qr[u][4 * d4 + 2] = f.z * 0.125f; qr[u][4 * d4 + 3] = f.w * 0.125f;
     }
   }
-  float m_run = -INFINITY, l_run = 0.f;
-  float o[8];
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float o[2][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = 0.f;
+  for (int j = 0; j < 8; ++j) { o[0][j] = 0.f; o[1][j] = 0.f; }
   const float* kbase = qkv + static_cast<size_t>(src) * max_kp * ld + 256 + head * 64;
   const float* vbase = qkv + static_cast<size_t>(src) * max_kp * ld + 512 + head * 64;
   for (int k0 = 0; k0 < nk; k0 += kAtK) {
@@ -345,53 +349,74 @@ __global__ void __launch_bounds__(128) sg_attention_kernel(const float* __restri
         kk = *reinterpret_cast<const float4*>(kbase + static_cast<size_t>(k0 + r) * ld + 4 * c4);
         vv = *reinterpret_cast<const float4*>(vbase + static_cast<size_t>(k0 + r) * ld + 4 * c4);
       }
-      sK[r][4 * c4] = kk.x; sK[r][4 * c4 + 1] = kk.y; sK[r][4 * c4 + 2] = kk.z; sK[r][4 * c4 + 3] = kk.w;
-      sV[r][4 * c4] = vv.x; sV[r][4 * c4 + 1] = vv.y; sV[r][4 * c4 + 2] = vv.z; sV[r][4 * c4 + 3] = vv.w;
+      *reinterpret_cast<float4*>(&sK[r][4 * c4]) = kk;
+      *reinterpret_cast<float4*>(&sV[r][4 * c4]) = vv;
     }
     __syncthreads();
-    float s[8];
-    float mx = -INFINITY;
+    float s[2][8];
+    float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int kk = sub + 8 * j;
-      float a = 0.f;
+      float a0 = 0.f, a1 = 0.f;
+      const float4* kr = reinterpret_cast<const float4*>(&sK[kk][0]);
 #pragma unroll
-      for (int d = 0; d < 64; ++d) a = fmaf(qr[d], sK[kk][d], a);
-      s[j] = (k0 + kk < nk) ? a : -INFINITY;
-      mx = fmaxf(mx, s[j]);
+      for (int d4 = 0; d4 < 16; ++d4) {            // same accumulation order as a scalar loop over d
+        const float4 kv = kr[d4];
+        a0 = fmaf(qr[0][4 * d4], kv.x, a0); a0 = fmaf(qr[0][4 * d4 + 1], kv.y, a0);
+        a0 = fmaf(qr[0][4 * d4 + 2], kv.z, a0); a0 = fmaf(qr[0][4 * d4 + 3], kv.w, a0);
+        a1 = fmaf(qr[1][4 * d4], kv.x, a1); a1 = fmaf(qr[1][4 * d4 + 1], kv.y, a1);
+        a1 = fmaf(qr[1][4 * d4 + 2], kv.z, a1); a1 = fmaf(qr[1][4 * d4 + 3], kv.w, a1);
+      }
+      const bool ok = k0 + kk < nk;
+      s[0][j] = ok ? a0 : -INFINITY; s[1][j] = ok ? a1 : -INFINITY;
+      mx[0] = fmaxf(mx[0], s[0][j]); mx[1] = fmaxf(mx[1], s[1][j]);
     }
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-    const float m_new = fmaxf(m_run, mx);
-    const float corr = __expf(m_run - m_new);
-    float ps = 0.f;
+    float corr[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float p = __expf(s[j] - m_new);
-      sP[qi][sub + 8 * j] = p;
-      ps += p;
+    for (int u = 0; u < 2; ++u) {
+      float m = mx[u];
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+      const float m_new = fmaxf(m_run[u], m);
+      corr[u] = __expf(m_run[u] - m_new);
+      float ps = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pv = __expf(s[u][j] - m_new);
+        sP[qi + 16 * u][sub + 8 * j] = pv;
+        ps += pv;
+      }
+      ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+      ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+      ps += __shfl_xor_sync(0xffffffffu, ps, 4);
+      l_run[u] = l_run[u] * corr[u] + ps;
+      m_run[u] = m_new;
     }
-    ps += __shfl_xor_sync(0xffffffffu, ps, 1);
-    ps += __shfl_xor_sync(0xffffffffu, ps, 2);
-    ps += __shfl_xor_sync(0xffffffffu, ps, 4);
-    l_run = l_run * corr + ps;
-    m_run = m_new;
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] *= corr;
+    for (int j = 0; j < 8; ++j) { o[0][j] *= corr[0]; o[1][j] *= corr[1]; }
     for (int kk = 0; kk < kAtK; ++kk) {
-      const float p = sP[qi][kk];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(p, sV[kk][sub * 8 + j], o[j]);
+      const float p0 = sP[qi][kk], p1 = sP[qi + 16][kk];
+      const float4 v0 = *reinterpret_cast<const float4*>(&sV[kk][sub * 8]);
+      const float4 v1 = *reinterpret_cast<const float4*>(&sV[kk][sub * 8 + 4]);
+      o[0][0] = fmaf(p0, v0.x, o[0][0]); o[0][1] = fmaf(p0, v0.y, o[0][1]); o[0][2] = fmaf(p0, v0.z, o[0][2]); o[0][3] = fmaf(p0, v0.w, o[0][3]);
+      o[0][4] = fmaf(p0, v1.x, o[0][4]); o[0][5] = fmaf(p0, v1.y, o[0][5]); o[0][6] = fmaf(p0, v1.z, o[0][6]); o[0][7] = fmaf(p0, v1.w, o[0][7]);
+      o[1][0] = fmaf(p1, v0.x, o[1][0]); o[1][1] = fmaf(p1, v0.y, o[1][1]); o[1][2] = fmaf(p1, v0.z, o[1][2]); o[1][3] = fmaf(p1, v0.w, o[1][3]);
+      o[1][4] = fmaf(p1, v1.x, o[1][4]); o[1][5] = fmaf(p1, v1.y, o[1][5]); o[1][6] = fmaf(p1, v1.z, o[1][6]); o[1][7] = fmaf(p1, v1.w, o[1][7]);
     }
     __syncwarp();
   }
-  if (q_ok) {
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    float* op = out + (static_cast<size_t>(img) * max_kp + q) * ldo + head * 64 + sub * 8;
-    *reinterpret_cast<float4*>(op) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
-    *reinterpret_cast<float4*>(op + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int q = u == 0 ? qa : qb;
+    if (q < nq) {
+      const float inv = l_run[u] > 0.f ? 1.f / l_run[u] : 0.f;
+      float* op = out + (static_cast<size_t>(img) * max_kp + q) * ldo + head * 64 + sub * 8;
+      *reinterpret_cast<float4*>(op) = make_float4(o[u][0] * inv, o[u][1] * inv, o[u][2] * inv, o[u][3] * inv);
+      *reinterpret_cast<float4*>(op + 4) = make_float4(o[u][4] * inv, o[u][5] * inv, o[u][6] * inv, o[u][7] * inv);
+    }
   }
 }
 
