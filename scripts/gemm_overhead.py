@@ -14,5 +14,5 @@ for rows in (128, 6120, 12240, 6120 * 8):
     for (cin, cout) in ((256, 256), (512, 512), (256, 768)):
         x = torch.randn(1, 1, rows, cin, device="cuda"); w = torch.randn(cout, 1, cin, device="cuda") * 0.05
         out = torch.empty(1, 1, rows, cout, device="cuda")
-        us = lib.mfr_debug_time_conv(mfr.ptr(x), 1, 1, rows, cin, mfr.ptr(w), cout, 1, 1, mfr.ptr(out), 100)
+        us = lib.mfr_debug_time_conv(mfr.ptr(x), 1, 1, rows, cin, mfr.ptr(w), cout, 1, 1, mfr.ptr(out), 100, 0, None)
         print(f"prebuilt rows {rows} {cin}->{cout}: {us:.1f} us/launch ({2.0*rows*cin*cout/us/1e6:.1f} TF/s)")
