@@ -275,6 +275,9 @@ __global__ void __launch_bounds__(256) kv_partial_kernel(const void* __restrict_
   constexpr int kSlabBytes = kSlab * 256 * (BF ? 2 : 4);
   char* sK = reinterpret_cast<char*>(att_smem);                          // [stages][kSlab][256]
   char* sV = reinterpret_cast<char*>(att_smem) + kAttStages * kSlabBytes;
+  // bf16 operands: every K element is read by the 32 lanes of its head's warp, so it is widened to fp32 ONCE per slab
+  // into this buffer instead of 32 times in the inner loop (the kernel is ALU-bound)
+  float* sKf = reinterpret_cast<float*>(reinterpret_cast<char*>(att_smem) + 2 * kAttStages * kSlabBytes);   // [kSlab][256], BF only
   const int split = blockIdx.x, n = blockIdx.y;
   const int chunk = (S + splits - 1) / splits;
   const int s_beg = split * chunk, s_end = min(S, s_beg + chunk);
@@ -308,14 +311,32 @@ __global__ void __launch_bounds__(256) kv_partial_kernel(const void* __restrict_
     }
     const char* k0 = sK + (i % kAttStages) * kSlabBytes;
     const char* v0 = sV + (i % kAttStages) * kSlabBytes;
+    const void* kc = k0;                       // what the inner loop reads K from
+    if constexpr (BF) {
+#pragma unroll
+      for (int e = 0; e < kSlab * 256 / 256 / 8; ++e) {           // 8 elements (16 bytes) per thread per step
+        const int idx = (t + 256 * e) * 8;
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(k0) + idx);
+        const unsigned w[4] = {u.x, u.y, u.z, u.w};
+        float4 lo, hi;
+        lo.x = __uint_as_float(w[0] << 16); lo.y = __uint_as_float(w[0] & 0xffff0000u);
+        lo.z = __uint_as_float(w[1] << 16); lo.w = __uint_as_float(w[1] & 0xffff0000u);
+        hi.x = __uint_as_float(w[2] << 16); hi.y = __uint_as_float(w[2] & 0xffff0000u);
+        hi.z = __uint_as_float(w[3] << 16); hi.w = __uint_as_float(w[3] & 0xffff0000u);
+        *reinterpret_cast<float4*>(sKf + idx) = lo;
+        *reinterpret_cast<float4*>(sKf + idx + 4) = hi;
+      }
+      __syncthreads();
+      kc = sKf;
+    }
 #pragma unroll 4
     for (int r = 0; r < kSlab; ++r) {
       const float vv = __fdiv_rn(slab_elem<BF>(v0, r, t), fS);     // values / v_length (linear_attention.py:40)
       float kk[32];
-      slab_head<BF>(k0, r, h, kk);
+      slab_head<false>(kc, r, h, kk);
 #pragma unroll
       for (int d = 0; d < 32; ++d) acc[d] = fmaf(kk[d], vv, acc[d]);
-      ks += slab_elem<BF>(k0, r, t);
+      ks += slab_elem<false>(kc, r, t);
     }
   }
   float* o = kv_part + ((static_cast<size_t>(n) * splits + split) * 8 + h) * 1056;
@@ -343,6 +364,7 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const void* __restrict_
   extern __shared__ __align__(16) float att_smem[];
   constexpr int kSlabBytes = kSlab * 256 * (BF ? 2 : 4);
   char* sQ = reinterpret_cast<char*>(att_smem);                           // [stages][kSlab][256]
+  float* sQf = reinterpret_cast<float*>(reinterpret_cast<char*>(att_smem) + kAttStages * kSlabBytes);   // [kSlab][256], BF only
   const int n = blockIdx.y;
   const int chunk = (L + splits - 1) / splits;
   const int l_beg = blockIdx.x * chunk, l_end = min(L, l_beg + chunk);
@@ -370,14 +392,32 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const void* __restrict_
     }
     const char* q0 = sQ + (i % kAttStages) * kSlabBytes;
     const int cnt = min(kSlab, l_end - l_beg - i * kSlab);
+    const void* qc = q0;
+    if constexpr (BF) {                        // widen the slab once (every q element is read by a whole warp)
+#pragma unroll
+      for (int e = 0; e < kSlab * 256 / 256 / 8; ++e) {
+        const int idx = (t + 256 * e) * 8;
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(q0) + idx);
+        const unsigned w[4] = {u.x, u.y, u.z, u.w};
+        float4 lo, hi;
+        lo.x = __uint_as_float(w[0] << 16); lo.y = __uint_as_float(w[0] & 0xffff0000u);
+        lo.z = __uint_as_float(w[1] << 16); lo.w = __uint_as_float(w[1] & 0xffff0000u);
+        hi.x = __uint_as_float(w[2] << 16); hi.y = __uint_as_float(w[2] & 0xffff0000u);
+        hi.z = __uint_as_float(w[3] << 16); hi.w = __uint_as_float(w[3] & 0xffff0000u);
+        *reinterpret_cast<float4*>(sQf + idx) = lo;
+        *reinterpret_cast<float4*>(sQf + idx + 4) = hi;
+      }
+      __syncthreads();
+      qc = sQf;
+    }
 #pragma unroll 4
     for (int r = 0; r < cnt; ++r) {
       float qq[32];
-      slab_head<BF>(q0, r, h, qq);
+      slab_head<false>(qc, r, h, qq);
       float a = 0.f;
 #pragma unroll
       for (int d = 0; d < 32; ++d) a = fmaf(qq[d], kvr[d], a);
-      const float den = warp_sum(slab_elem<BF>(q0, r, t) * ksum);
+      const float den = warp_sum(slab_elem<false>(qc, r, t) * ksum);
       const float o = a * (1.f / (den + eps)) * fS;
       const long long oi = (base + l_beg + i * kSlab + r) * ldm + t;
       if constexpr (BF) static_cast<unsigned short*>(msg)[oi] = f2bf(o);
@@ -1147,19 +1187,21 @@ int linear_attention_long(const void* Q, long long ldq, const void* K, long long
   if (dim != 32 || heads != 8) return MFR_ERR_UNSUPPORTED;
   if ((ldq | ldk | ldv) & (bf16 ? 7 : 3)) return MFR_ERR_ARG;                    // 16-byte cp.async chunks
   constexpr int kKvSmem = 2 * kAttStages * kSlab * 256 * 4, kApSmem = kAttStages * kSlab * 256 * 4;
+  constexpr int kWide = kSlab * 256 * 4;   // bf16 variants: one fp32 slab the K / Q rows are widened into
+  constexpr int kKvSmemBf = kKvSmem / 2 + kWide, kApSmemBf = kApSmem / 2 + kWide;
   static bool attr_set = false;
   if (!attr_set) {
     MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem));
     MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmem));
-    MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem / 2));
-    MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmem / 2));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmemBf));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmemBf));
     attr_set = true;
   }
   const int asplits = std::max(1, std::min((L + kSlab - 1) / kSlab, (4 * 148 + n - 1) / n));
   if (bf16) {
-    kv_partial_kernel<true><<<dim3(splits, n), 256, kKvSmem / 2, st>>>(K, ldk, V, ldv, kv_part, S, splits);
+    kv_partial_kernel<true><<<dim3(splits, n), 256, kKvSmemBf, st>>>(K, ldk, V, ldv, kv_part, S, splits);
     kv_reduce_kernel<<<dim3((8 * 1056 + 255) / 256, n), 256, 0, st>>>(kv_part, kv, splits);
-    attn_apply_kernel<true><<<dim3(asplits, n), 256, kApSmem / 2, st>>>(Q, ldq, kv, msg, ldm, L, S, 1e-6f, asplits);
+    attn_apply_kernel<true><<<dim3(asplits, n), 256, kApSmemBf, st>>>(Q, ldq, kv, msg, ldm, L, S, 1e-6f, asplits);
   } else {
     kv_partial_kernel<false><<<dim3(splits, n), 256, kKvSmem, st>>>(K, ldk, V, ldv, kv_part, S, splits);
     kv_reduce_kernel<<<dim3((8 * 1056 + 255) / 256, n), 256, 0, st>>>(kv_part, kv, splits);
