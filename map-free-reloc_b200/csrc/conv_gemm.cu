@@ -470,8 +470,13 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
               mbar_wait(a_empty(sa), pa ^ 1u, 1);
               if (elect_one_sync()) {
                 mbar_arrive_expect_tx(a_full(sa), ab);
-                tma_load_4d(smem_a + sa * a_slot_bytes, tmA, a_full(sa), c0, x_in0 + kx, y_in0 + ky, img);
-                tma_load_3d(smem_b + sa * b_bytes, tmB, a_full(sa), c0, bz >= 0 ? bz : tap, n0);
+                if (p.a_yx) tma_load_4d(smem_a + sa * a_slot_bytes, tmA, a_full(sa), c0, y_in0 + ky, x_in0 + kx, img);
+                else tma_load_4d(smem_a + sa * a_slot_bytes, tmA, a_full(sa), c0, x_in0 + kx, y_in0 + ky, img);
+                if (p.b_batched == 2) {
+                  if (p.b_yx) tma_load_4d(smem_b + sa * b_bytes, tmB, a_full(sa), c0, ty, n0, img ^ p.b_xor);
+                  else tma_load_4d(smem_b + sa * b_bytes, tmB, a_full(sa), c0, n0, ty, img ^ p.b_xor);
+                }
+                else tma_load_3d(smem_b + sa * b_bytes, tmB, a_full(sa), c0, bz >= 0 ? bz : tap, n0);
               }
               if (++sa == a_slots) { sa = 0; pa ^= 1u; }
             }
@@ -687,6 +692,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
         const int y = ty * tile_rows + m * p.TH + ly0, x = tx * p.TW + lx;
         const bool row_ok = (row < p.TW * p.TH) && (y < p.Ho) && (x < w_lim);
         const long long pix = static_cast<long long>(y) * p.Wo + x;   // pixel inside the image
+        const long long opix = static_cast<long long>(y) * p.out_y_stride + static_cast<long long>(x) * p.ldo;   // its output offset
         const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxBN + m * 128) +
                                (static_cast<uint32_t>(q * 32) << 16);
         const bool do_wait = m == 0;
@@ -711,7 +717,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
             const int rr = k * 4 + sub_r;
             const long long pr = __shfl_sync(0xffffffffu, pix, rr);
             okmask |= (__shfl_sync(0xffffffffu, row_ok ? 1 : 0, rr) != 0 ? 1u : 0u) << k;
-            off_o[k] = img * p.out_img_stride + pr * p.ldo;
+            off_o[k] = img * p.out_img_stride + __shfl_sync(0xffffffffu, opix, rr);
             off_r[k] = img * p.res_img_stride + pr * p.ldr;
           }
 #define MFR_EPI(ACTV)                                                                                               \
@@ -736,7 +742,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
             mbar_wait(tfull_bar(acc), acc_phase, 4);
             tc_fence_after();
           }
-          epilogue_subtile_scalar(p, taddr, n0, row_ok, img * p.out_img_stride + pix * p.ldo,
+          epilogue_subtile_scalar(p, taddr, n0, row_ok, img * p.out_img_stride + opix,
                                   img * p.res_img_stride + pix * p.ldr, c_begin);
         }
         if (it == 0 && m == 0 && threadIdx.x == 64) MFR_STAMP(6);
@@ -820,7 +826,8 @@ RingCfg ring_cfg(int halo, int MT, int TW, int TH, int BN) {
 }
 
 TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, int pad, int kb_per_tap,
-                   int ksteps_last, bool allow_mt2, bool tma_store_ok, bool allow_swap, bool allow_mcast) {
+                   int ksteps_last, bool allow_mt2, bool tma_store_ok, bool allow_swap, bool allow_mcast,
+                   bool single_row_tiles = false) {
   const int sms = conv_gemm_num_sms();
   const int c16 = (Cout + 15) / 16 * 16;
   const int taps = R * S;
@@ -847,6 +854,7 @@ TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, in
           if (tw * stride > 256) break;
           int th = 128 / tw;
           if (!halo && th > Ho) th = Ho;
+          if (single_row_tiles) th = 1;                 // every output row has its own B operand
           if (MT == 2 && (tw * th) % 8 != 0) continue;
           const int box_rows = halo ? MT * th + 2 : MT * th * stride;
           if (box_rows > 256) continue;
@@ -939,16 +947,18 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
     p->ksteps_last = (tail + ummak - 1) / ummak;
     // a tail of one k-step (<= 32 bytes of channels) is moved as 32-byte-wide tiles (32B swizzle) instead of zero-filled
     // 128-byte ones: Cin = 196 otherwise spends a quarter of its operand traffic on 4 channels
-    p->tail32 = (p->ksteps_last == 1 && tail * es <= 32 && p->kb_per_tap > 1 && getenv("MFR_CONV_NO_TAIL32") == nullptr) ? 1 : 0;
+    p->tail32 = (p->ksteps_last == 1 && tail * es <= 32 && p->kb_per_tap > 1 && d.b_batched != 2 &&
+                 getenv("MFR_CONV_NO_TAIL32") == nullptr) ? 1 : 0;
   }
   const TileCfg cfg = choose_cfg(d.N, p->Ho, p->Wo, d.Cout, d.R, d.S, d.stride, d.pad, p->kb_per_tap, p->ksteps_last,
-                                 d.dyn_w == nullptr, !d.out_bf16 && d.residual == nullptr,
+                                 d.dyn_w == nullptr && d.b_batched != 2, !d.out_bf16 && d.residual == nullptr,
                                  // swapped operands: not with a residual (measured: its transposed epilogue then becomes the bottleneck)
                                  (d.Cout % 4 == 0) && (d.ldo % 4 == 0) && !d.b_batched &&
                                      (d.residual == nullptr || (getenv("MFR_CONV_FORCE") != nullptr && d.ldr % 4 == 0)),
                                  // CTA-pair weight multicast: measured no gain on B200 for these shapes (the layers are not L2-bound once the
                                  // channel tail is narrow), so it is opt-in (MFR_CONV_MCAST=1 or the test hook)
-                                 !d.b_batched && d.dyn_w == nullptr && (getenv("MFR_CONV_MCAST") != nullptr || getenv("MFR_CONV_FORCE") != nullptr));
+                                 !d.b_batched && d.dyn_w == nullptr && (getenv("MFR_CONV_MCAST") != nullptr || getenv("MFR_CONV_FORCE") != nullptr),
+                                 d.b_batched == 2);
   p->TW = cfg.TW; p->TH = cfg.TH; p->MT = cfg.MT; p->halo = cfg.halo; p->swap = cfg.swap; p->mcast = cfg.mcast;
   p->BN = cfg.BN; p->n_tiles = cfg.n_tiles;
   p->tiles_x = (p->Wo + p->TW - 1) / p->TW;
@@ -974,17 +984,25 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
   p->ldr = d.ldr;
   p->out = d.out;
   p->ldo = d.ldo;
+  p->out_y_stride = d.out_y_stride > 0 ? d.out_y_stride : static_cast<long long>(p->Wo) * d.ldo;
   p->out_img_stride = d.out_img_stride > 0 ? d.out_img_stride : static_cast<long long>(p->Ho) * p->Wo * d.ldo;
+  p->b_xor = d.b_xor;
   p->res_img_stride = static_cast<long long>(p->Ho) * p->Wo * d.ldr;
   p->dbg = nullptr;
 
   {  // activations: {C, W, H, N}
     cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};
-    cuuint64_t strides[3] = {(cuuint64_t)d.ldx * es, (cuuint64_t)d.ldx * es * d.W,
+    cuuint64_t strides[3] = {(cuuint64_t)d.ldx * es, d.x_y_stride > 0 ? (cuuint64_t)d.x_y_stride * es : (cuuint64_t)d.ldx * es * d.W,
                              d.x_img_stride > 0 ? (cuuint64_t)d.x_img_stride * es : (cuuint64_t)d.ldx * es * d.W * d.H};
     cuuint32_t box[4] = {(cuuint32_t)kblk, (cuuint32_t)(p->TW * d.stride),
                          (cuuint32_t)(p->halo ? p->MT * p->TH + 2 : p->MT * p->TH * d.stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
+    p->a_yx = 0;
+    if (d.x_y_stride > 0 && d.x_y_stride < d.ldx) {   // rows interleaved inside a pixel: tensor-map strides must not decrease
+      if (p->halo || d.stride != 1 || p->tail32) return MFR_ERR_ARG;
+      p->a_yx = 1;
+      std::swap(dims[1], dims[2]); std::swap(strides[0], strides[1]); std::swap(box[1], box[2]);
+    }
     CUresult r = enc(&p->tmA, d.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                      const_cast<float*>(d.x), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1007,13 +1025,13 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
     const bool ok = !p->swap && !d.out_bf16 && d.residual == nullptr && pow2 && p->TW >= 8 && p->TW * p->TH == 128 &&
                     (p->BN % 32 == 0 || p->n_tiles == 1) && (p->act_cols % 32 == 0 || p->act_cols >= d.Cout) &&
                     (d.ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && (d.Cout % 4 == 0) &&
-                    (p->out_img_stride % 4 == 0) && (d.bias == nullptr || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0) &&
+                    (p->out_img_stride % 4 == 0) && (p->out_y_stride % 4 == 0) && (d.bias == nullptr || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0) &&
                     getenv("MFR_CONV_NO_TMA_STORE") == nullptr;
     p->tma_store = ok ? 1 : 0;
     if (ok) {
       const int bw = std::min(p->TW, 32);
       cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)p->Wo, (cuuint64_t)p->Ho, (cuuint64_t)d.N};
-      cuuint64_t strides[3] = {(cuuint64_t)d.ldo * 4, (cuuint64_t)d.ldo * 4 * p->Wo, (cuuint64_t)p->out_img_stride * 4};
+      cuuint64_t strides[3] = {(cuuint64_t)d.ldo * 4, (cuuint64_t)p->out_y_stride * 4, (cuuint64_t)p->out_img_stride * 4};
       cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)(32 / bw), 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = enc(&p->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out, dims, strides, box, estr,
@@ -1026,6 +1044,26 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
     const int taps = d.R * d.S;
     cuuint64_t dims[3];
     cuuint64_t strides[2];
+    if (d.b_batched == 2) {   // per-(image, row) B operand: rank-4 map {Cin, Cout rows, y, image}
+      cuuint64_t dims4[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.Cout, (cuuint64_t)p->Ho, (cuuint64_t)d.N};
+      cuuint64_t strides4[3] = {(cuuint64_t)ldw_e * es, (cuuint64_t)d.w_y_stride * es, (cuuint64_t)d.w_img_stride * es};
+      cuuint32_t box4[4] = {(cuuint32_t)kblk, (cuuint32_t)p->BN, 1, 1};
+      cuuint32_t estr4[4] = {1, 1, 1, 1};
+      p->b_yx = 0;
+      if (d.w_y_stride < ldw_e) {
+        p->b_yx = 1;
+        std::swap(dims4[1], dims4[2]); std::swap(strides4[0], strides4[1]); std::swap(box4[1], box4[2]);
+      }
+      if (d.w_y_stride <= 0 || d.w_img_stride <= 0 || p->TH != 1 || p->MT != 1) return MFR_ERR_ARG;
+      CUresult r4 = enc(&p->tmB, d.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                        const_cast<float*>(d.w), dims4, strides4, box4, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r4 != CUDA_SUCCESS) {
+        fprintf(stderr, "[mfr_b200] cuTensorMapEncodeTiled(B, per-row) failed: %d\n", (int)r4);
+        return MFR_ERR_CUDA;
+      }
+      return MFR_OK;
+    }
     if (d.b_batched) {
       const long long ldw = ldw_e;
       dims[0] = d.Cin; dims[1] = d.N; dims[2] = d.Cout;

@@ -49,6 +49,10 @@ struct alignas(64) ConvGemmParams {
   float* out;
   long long ldr, ldo;
   long long out_img_stride, res_img_stride;  // elements between images of out / residual
+  long long out_y_stride;                    // elements between output rows (Wo * ldo when dense)
+  int b_xor;
+  int a_yx, b_yx;                            // tensor map dims 1 and 2 swapped (row stride smaller than the pixel / filter-row stride:
+                                             // attention heads interleaved inside a token row) -> coordinate order (c, y, x|n, img)
   long long* dbg;       // optional: block 0 writes globaltimer stamps (ns) at pipeline milestones
 };
 
@@ -59,11 +63,14 @@ struct ConvGemmDesc {
   long long ldx;
   const float* w;      // [Cout][R*S][Cin] (Cin fastest); for batched GEMM: [N][Cout][ldw]
   int Cout, R, S, stride, pad;
-  int b_batched;       // 0: shared weights; 1: per-image B operand
+  int b_batched;       // 0: shared weights; 1: per-image B operand; 2: per-(image, output row y) B operand (H = e.g. attention
+                       //    heads): w[(img ^ b_xor)][y][Cout rows][Cin] with strides w_img_stride / w_y_stride / ldw
   long long ldw;       // row stride of w in elements (0 = Cin): per tap for shared weights, per row if batched
   int act_cols;        // 0 = all output channels
   const int* dyn_w;    // optional device row count (token GEMMs with data-dependent length)
   long long x_img_stride, w_img_stride, out_img_stride;  // elements between images; 0 = dense
+  long long x_y_stride, w_y_stride, out_y_stride;        // elements between rows y of x / of w (b_batched 2) / of out; 0 = dense
+  int b_xor;                                             // b_batched 2: the B operand of image i is taken from image i ^ b_xor
   int in_bf16, out_bf16;  // x / w are bf16 ; out / residual are bf16 (pointers reinterpret the storage)
   const float* bias;   // [Cout] or null
   const float* residual;  // NHWC like out (pixel stride ldr) or null

@@ -112,6 +112,9 @@ struct SpsgEngine {
     float* k3 = alloc<float>(rows * 128); float* k4 = alloc<float>(rows * 256);
     float* qkv = alloc<float>(rows * 768, "qkv"); float* msg = alloc<float>(rows * 256, "msg"); float* h1 = alloc<float>(rows * 512);
     float* Mb = alloc<float>(rows * 256, "mdesc");
+    // tensor-core attention: scores / probabilities [NI][4 heads][K][K] and V transposed [NI][256][K]
+    float* Sat = alloc<float>(static_cast<size_t>(NI) * 4 * K * K, "attn_scores");
+    float* Vt = alloc<float>(static_cast<size_t>(NI) * 256 * K, "attn_vt");
     float* S = alloc<float>(static_cast<size_t>(B) * K * K, "sg_scores");
     float* u = alloc<float>(static_cast<size_t>(B) * (K + 1), "sk_u"); float* v = alloc<float>(static_cast<size_t>(B) * (K + 1), "sk_v");
     float* rmax = alloc<float>(static_cast<size_t>(B) * K); int* rarg = alloc<int>(static_cast<size_t>(B) * K); int* carg = alloc<int>(static_cast<size_t>(B) * K);
@@ -171,8 +174,32 @@ struct SpsgEngine {
       const std::string p = "gnn." + std::to_string(i);
       gemm(p + ".qkv", X, NI, 1, K, 256, 512, 768, 1, ACT_NONE, nullptr, qkv, 768);
       {
+        // multi-head softmax attention (superglue.py:85-89) as two tcgen05 GEMMs with the heads as the H dimension:
+        //   S[img][h][q][k] = Q_h K_h^T / 8   (B operand = keys of image img ^ cross, head h)
+        //   P = softmax_k(S) in place, masked to the source image's keypoint count
+        //   msg[img][q][64 h + d] = sum_k P[img][h][q][k] V[img ^ cross][k][64 h + d]   (B operand = V^T of that image / head)
         const int cross = i % 2, kk = K, n = NI; int* cn = counts;
-        push([=](cudaStream_t st) { return sg_attention(qkv, 768, cn, cross, kk, n, msg, 256, st); });
+        ConvGemmDesc d{};
+        d.x = qkv; d.N = NI; d.H = 4; d.W = K; d.Cin = 64; d.ldx = 768; d.x_y_stride = 64; d.x_img_stride = static_cast<long long>(K) * 768;
+        d.w = qkv + 256; d.Cout = K; d.R = 1; d.S = 1; d.stride = 1; d.pad = 0;
+        d.b_batched = 2; d.ldw = 768; d.w_y_stride = 64; d.w_img_stride = static_cast<long long>(K) * 768; d.b_xor = cross;
+        d.act = ACT_NONE; d.alpha = 0.125f; d.out = Sat; d.ldo = K; d.ldr = K;
+        ConvGemmParams pq;
+        int r = conv_gemm_build(d, &pq);
+        if (r != MFR_OK) return r;
+        push([pq](cudaStream_t st) { return conv_gemm_launch(pq, st); });
+        push([=](cudaStream_t st) { return sg_softmax_rows(Sat, cn, cross, kk, n, st); });
+        push([=](cudaStream_t st) { return sg_transpose_v(qkv, 768, Vt, kk, n, st); });
+        ConvGemmDesc e{};
+        e.x = Sat; e.N = NI; e.H = 4; e.W = K; e.Cin = K; e.ldx = K;
+        e.w = Vt; e.Cout = 64; e.R = 1; e.S = 1; e.stride = 1; e.pad = 0;
+        e.b_batched = 2; e.ldw = K; e.w_y_stride = 64LL * K; e.w_img_stride = 256LL * K; e.b_xor = cross;
+        e.act = ACT_NONE; e.alpha = 1.f; e.out = msg; e.ldo = 256; e.ldr = 256; e.out_y_stride = 64;
+        e.out_img_stride = static_cast<long long>(K) * 256;
+        ConvGemmParams pv;
+        r = conv_gemm_build(e, &pv);
+        if (r != MFR_OK) return r;
+        push([pv](cudaStream_t st) { return conv_gemm_launch(pv, st); });
       }
       gemm(p + ".merge", msg, NI, 1, K, 256, 256, 256, 1, ACT_NONE, nullptr, X + 256, 512);
       gemm(p + ".mlp0", X, NI, 1, K, 512, 512, 512, 1, ACT_RELU, nullptr, h1, 512);

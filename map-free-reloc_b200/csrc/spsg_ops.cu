@@ -420,6 +420,77 @@ __global__ void __launch_bounds__(128) sg_attention_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------ softmax attention on the tensor cores
+// The scores Q_h K_h^T / 8 and the product P V_h are tcgen05 GEMMs (conv_gemm, per-(image, head) B operand); in between:
+//   sg_softmax_rows : P[img][h][q][:] = softmax over the source image's nk keys (0 beyond them), in place
+//   sg_transpose_v  : Vt[img][h][d][k] = qkv[img][k][512 + 64 h + d]  (the P V GEMM needs V K-major along the keys)
+__global__ void __launch_bounds__(256) sg_softmax_rows_kernel(float* __restrict__ S, const int* __restrict__ counts,
+                                                              int src_xor, int max_kp) {
+  __shared__ float sh[8];
+  const int q = blockIdx.x, h = blockIdx.y, img = blockIdx.z;
+  const int nq = counts[img], nk = counts[img ^ src_xor];
+  float* row = S + ((static_cast<size_t>(img) * 4 + h) * max_kp + q) * max_kp;
+  const int t = threadIdx.x;
+  if (q >= nq) {                             // absent keypoints: zero message, so that padded rows stay bounded through the layers
+    for (int k = t; k < max_kp; k += 256) row[k] = 0.f;
+    return;
+  }
+  float v[4];
+  float m = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int k = t + 256 * e;
+    v[e] = (k < nk) ? row[k] : -INFINITY;
+    m = fmaxf(m, v[e]);
+  }
+  for (int k = t + 1024; k < nk; k += 256) m = fmaxf(m, row[k]);    // max_kp > 1024 (not used by the reference config)
+  m = warp_max(m);
+  if ((t & 31) == 0) sh[t >> 5] = m;
+  __syncthreads();
+  m = sh[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, sh[w]);
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[e] = (t + 256 * e < nk) ? __expf(v[e] - m) : 0.f;
+    s += v[e];
+  }
+  for (int k = t + 1024; k < nk; k += 256) s += __expf(row[k] - m);
+  s = warp_sum(s);
+  if ((t & 31) == 0) sh[t >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += sh[w];
+  const float inv = s > 0.f ? 1.f / s : 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int k = t + 256 * e;
+    if (k < max_kp) row[k] = v[e] * inv;
+  }
+  for (int k = t + 1024; k < max_kp; k += 256) row[k] = (k < nk) ? __expf(row[k] - m) * inv : 0.f;
+}
+
+__global__ void __launch_bounds__(256) sg_transpose_v_kernel(const float* __restrict__ qkv, long long ld,
+                                                             float* __restrict__ vt, int max_kp) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z, c0 = blockIdx.y * 32, k0 = blockIdx.x * 32;   // c = 64 h + d in [0, 256)
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                   // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = k0 + ty + 8 * j;
+    tile[ty + 8 * j][tx] = k < max_kp ? qkv[(static_cast<size_t>(img) * max_kp + k) * ld + 512 + c0 + tx] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + ty + 8 * j, k = k0 + tx;
+    if (k < max_kp) vt[(static_cast<size_t>(img) * 256 + c) * max_kp + k] = tile[tx][ty + 8 * j];
+  }
+}
+
 // ------------------------------------------------------------------------------------------ Sinkhorn (superglue.py:141-170)
 // couplings Z[(n0+1) x (n1+1)]: Z[i][j] = S[i][j] (i < n0, j < n1), bin score alpha otherwise.
 __device__ __forceinline__ void lse_push(float& m, float& s, float x) {
@@ -706,6 +777,16 @@ int sg_kenc_input(const float* kpts, const float* kscores, float* out, int total
 int sg_attention(const float* qkv, long long ld, const int* counts, int cross, int max_kp, int n_img, float* out,
                  long long ldo, cudaStream_t st) {
   sg_attention_kernel<<<dim3((max_kp + kAtQ - 1) / kAtQ, 4, n_img), 128, 0, st>>>(qkv, ld, counts, cross ? 1 : 0, max_kp, out, ldo);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+int sg_softmax_rows(float* S, const int* counts, int cross, int max_kp, int n_img, cudaStream_t st) {
+  sg_softmax_rows_kernel<<<dim3(max_kp, 4, n_img), 256, 0, st>>>(S, counts, cross ? 1 : 0, max_kp);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+int sg_transpose_v(const float* qkv, long long ld, float* vt, int max_kp, int n_img, cudaStream_t st) {
+  sg_transpose_v_kernel<<<dim3((max_kp + 31) / 32, 8, n_img), 256, 0, st>>>(qkv, ld, vt, max_kp);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }

@@ -23,6 +23,9 @@ int sg_kenc_input(const float* kpts, const float* kscores, float* out, int total
 // images are stored pair-interleaved (2p, 2p+1); cross != 0: image i attends to image i^1
 int sg_attention(const float* qkv, long long ld, const int* counts, int cross, int max_kp, int n_img, float* out,
                  long long ldo, cudaStream_t st);
+// tensor-core attention helpers (see spsg_ops.cu): in-place row softmax of the [img][4][K][K] scores, V transpose
+int sg_softmax_rows(float* S, const int* counts, int cross, int max_kp, int n_img, cudaStream_t st);
+int sg_transpose_v(const float* qkv, long long ld, float* vt, int max_kp, int n_img, cudaStream_t st);
 int sg_sinkhorn(const float* S, int ldS, const int* counts, float alpha, int iters, int max_kp, int n_pairs,
                 float* u, float* v, cudaStream_t st);
 int sg_extract_matches(const float* S, int ldS, const int* counts, const float* u, const float* v, float thr,
