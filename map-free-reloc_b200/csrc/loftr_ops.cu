@@ -210,6 +210,7 @@ __global__ void posenc_kernel(const float* __restrict__ feat, const float* __res
 // Both streaming kernels move their token rows with a 3-stage cp.async pipeline (16 tokens x 1 KB per
 // operand per stage), so the HBM latency is paid once per block, not once per slab.
 constexpr int kSlab = 16;     // tokens per pipeline stage
+constexpr bool kUseMmaAttention = true;   // bf16 mode: warp-level tensor-core linear attention (false: the SIMT kernels)
 constexpr int kAttStages = 3;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
@@ -426,6 +427,201 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const void* __restrict_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ linear attention on mma.sync (bf16 operands)
+// bf16 mode: q' = elu(q)+1, k' and v are already bf16 in HBM, so K'^T V (32 x 32 per head, reduction over the tokens)
+// and Q' (KV) are warp-level m16n8k16 tensor-core products with fp32 accumulation; the SIMT kernels above are
+// issue-bound on shared-memory reads and fp32 FMAs. Slabs land by cp.async with the 16-byte chunk index XOR-ed by
+// (row & 7), which makes every ldmatrix phase (8 rows, one chunk column) bank-conflict free. The reference's
+// values / v_length ... * v_length pair (linear_attention.py:40-45) cancels and is not applied here.
+constexpr int kMS = 32;          // tokens per pipeline stage
+constexpr int kMStages = 3;
+constexpr int kMSlabBytes = kMS * 512;
+
+__device__ __forceinline__ void ldsm_x4(unsigned (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(static_cast<unsigned>(__cvta_generic_to_shared(p))));
+}
+__device__ __forceinline__ void ldsm_x4_t(unsigned (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(static_cast<unsigned>(__cvta_generic_to_shared(p))));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
+  return static_cast<unsigned>(f2bf(lo)) | (static_cast<unsigned>(f2bf(hi)) << 16);
+}
+// rows [r0, r0+kMS) of a bf16 [rows][256] matrix -> dst[kMS][512 B], chunk-swizzled; rows >= r_end are zero-filled
+__device__ __forceinline__ void slab_load_sw(char* dst, const void* __restrict__ src, long long ld, long long r0,
+                                             long long r_end, int t) {
+#pragma unroll
+  for (int i = 0; i < kMS * 32 / 256; ++i) {
+    const int c = t + 256 * i;
+    const int r = c >> 5, ch = c & 31;
+    const bool ok = r0 + r < r_end;
+    cp_async16(dst + r * 512 + ((ch ^ (r & 7)) << 4),
+               static_cast<const char*>(src) + ((ok ? (r0 + r) : r0) * ld) * 2 + ch * 16, ok);
+  }
+}
+__device__ __forceinline__ const char* sw_addr(const char* slab, int row, int chunk) {
+  return slab + row * 512 + ((chunk ^ (row & 7)) << 4);
+}
+
+// kv_part[n][split][h][d*32 + v] = sum_s K'[s][32h+d] V[s][32h+v],  [..][1024 + d] = sum_s K'[s][32h+d]; warp = head
+__global__ void __launch_bounds__(256) kv_partial_mma_kernel(const void* __restrict__ K, long long ldk,
+                                                             const void* __restrict__ V, long long ldv,
+                                                             float* __restrict__ kv_part, int S, int splits) {
+  extern __shared__ __align__(128) float att_smem[];
+  char* sK = reinterpret_cast<char*>(att_smem);
+  char* sV = sK + kMStages * kMSlabBytes;
+  const int split = blockIdx.x, n = blockIdx.y;
+  const int chunk = (S + splits - 1) / splits;
+  const int s_beg = split * chunk, s_end = min(S, s_beg + chunk);
+  const int t = threadIdx.x, h = t >> 5, lane = t & 31;
+  const int j = lane >> 3, r = lane & 7, g = lane >> 2, tq = lane & 3;
+  const long long base = static_cast<long long>(n) * S;
+  const int nslab = s_end > s_beg ? (s_end - s_beg + kMS - 1) / kMS : 0;
+  float acc[2][4][4], accs[2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      accs[a][b] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+    }
+  }
+  const unsigned ones = (g == 0) ? 0x3F803F80u : 0u;      // B tile whose column 0 is all ones -> sum of K' over the tokens
+#pragma unroll
+  for (int st = 0; st < kMStages - 1; ++st) {
+    if (st < nslab) {
+      slab_load_sw(sK + st * kMSlabBytes, K, ldk, base + s_beg + st * kMS, base + s_end, t);
+      slab_load_sw(sV + st * kMSlabBytes, V, ldv, base + s_beg + st * kMS, base + s_end, t);
+    }
+    cp_async_commit();
+  }
+  for (int i = 0; i < nslab; ++i) {
+    cp_async_wait<kMStages - 2>();
+    __syncthreads();
+    {
+      const int nx = i + kMStages - 1;
+      if (nx < nslab) {
+        const int st = nx % kMStages;
+        slab_load_sw(sK + st * kMSlabBytes, K, ldk, base + s_beg + nx * kMS, base + s_end, t);
+        slab_load_sw(sV + st * kMSlabBytes, V, ldv, base + s_beg + nx * kMS, base + s_end, t);
+      }
+      cp_async_commit();
+    }
+    const char* k0 = sK + (i % kMStages) * kMSlabBytes;
+    const char* v0 = sV + (i % kMStages) * kMSlabBytes;
+#pragma unroll
+    for (int ks = 0; ks < kMS / 16; ++ks) {
+      unsigned a[2][4], b[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)      // A = K'^T: m = channel d, k = token
+        ldsm_x4_t(a[mt], sw_addr(k0, 16 * ks + r + 8 * (j >> 1), 4 * h + 2 * mt + (j & 1)));
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp)      // B = V: k = token, n = channel v (two 8-wide tiles per ldmatrix)
+        ldsm_x4_t(b[pp], sw_addr(v0, 16 * ks + r + 8 * (j & 1), 4 * h + 2 * pp + (j >> 1)));
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[mt][nt], a[mt], b[nt >> 1][2 * (nt & 1)], b[nt >> 1][2 * (nt & 1) + 1]);
+        mma_bf16(accs[mt], a[mt], ones, ones);
+      }
+    }
+  }
+  float* o = kv_part + ((static_cast<size_t>(n) * splits + split) * 8 + h) * 1056;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      *reinterpret_cast<float2*>(o + (16 * mt + g) * 32 + 8 * nt + 2 * tq) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+      *reinterpret_cast<float2*>(o + (16 * mt + g + 8) * 32 + 8 * nt + 2 * tq) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+    }
+    if (tq == 0) {
+      o[1024 + 16 * mt + g] = accs[mt][0];
+      o[1024 + 16 * mt + g + 8] = accs[mt][2];
+    }
+  }
+}
+
+// msg[l][32h+v] = (Q'[l] . KV[:, v]) / (Q'[l] . Ksum + eps), KV / Ksum rounded to bf16 as the B operand; warp = head
+__global__ void __launch_bounds__(256) attn_apply_mma_kernel(const void* __restrict__ Q, long long ldq,
+                                                             const float* __restrict__ kv,
+                                                             unsigned short* __restrict__ msg, long long ldm, int L,
+                                                             float eps, int splits) {
+  extern __shared__ __align__(128) float att_smem[];
+  char* sQ = reinterpret_cast<char*>(att_smem);
+  const int n = blockIdx.y;
+  const int chunk = (L + splits - 1) / splits;
+  const int l_beg = blockIdx.x * chunk, l_end = min(L, l_beg + chunk);
+  const int nslab = l_end > l_beg ? (l_end - l_beg + kMS - 1) / kMS : 0;
+  const int t = threadIdx.x, h = t >> 5, lane = t & 31;
+  const int j = lane >> 3, r = lane & 7, g = lane >> 2, tq = lane & 3;
+  const long long base = static_cast<long long>(n) * L;
+#pragma unroll
+  for (int st = 0; st < kMStages - 1; ++st) {
+    if (st < nslab) slab_load_sw(sQ + st * kMSlabBytes, Q, ldq, base + l_beg + st * kMS, base + l_end, t);
+    cp_async_commit();
+  }
+  const float* kvh = kv + (static_cast<size_t>(n) * 8 + h) * 1056;
+  unsigned bkv[2][4][2], bden[2][2];      // B fragments: k = channel d (two 16-steps), n = channel v (four tiles) / the Ksum column
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const int d0 = 16 * ks + 2 * tq;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int v = 8 * nt + g;
+      bkv[ks][nt][0] = pack_bf16(kvh[d0 * 32 + v], kvh[(d0 + 1) * 32 + v]);
+      bkv[ks][nt][1] = pack_bf16(kvh[(d0 + 8) * 32 + v], kvh[(d0 + 9) * 32 + v]);
+    }
+    bden[ks][0] = g == 0 ? pack_bf16(kvh[1024 + d0], kvh[1024 + d0 + 1]) : 0u;
+    bden[ks][1] = g == 0 ? pack_bf16(kvh[1024 + d0 + 8], kvh[1024 + d0 + 9]) : 0u;
+  }
+  for (int i = 0; i < nslab; ++i) {
+    cp_async_wait<kMStages - 2>();
+    __syncthreads();
+    {
+      const int nx = i + kMStages - 1;
+      if (nx < nslab) slab_load_sw(sQ + (nx % kMStages) * kMSlabBytes, Q, ldq, base + l_beg + nx * kMS, base + l_end, t);
+      cp_async_commit();
+    }
+    const char* q0 = sQ + (i % kMStages) * kMSlabBytes;
+#pragma unroll
+    for (int mt = 0; mt < kMS / 16; ++mt) {
+      float c[4][4], cd[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        cd[b] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[b][e] = 0.f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        unsigned a[4];                      // A = Q': m = token, k = channel d
+        ldsm_x4(a, sw_addr(q0, 16 * mt + r + 8 * (j & 1), 4 * h + 2 * ks + (j >> 1)));
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_bf16(c[nt], a, bkv[ks][nt][0], bkv[ks][nt][1]);
+        mma_bf16(cd, a, bden[ks][0], bden[ks][1]);
+      }
+      const float den_lo = __shfl_sync(0xffffffffu, cd[0], lane & ~3), den_hi = __shfl_sync(0xffffffffu, cd[2], lane & ~3);
+      const float z_lo = 1.f / (den_lo + eps), z_hi = 1.f / (den_hi + eps);
+      const int l0 = l_beg + i * kMS + 16 * mt + g;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (l0 < l_end)
+          *reinterpret_cast<unsigned*>(msg + (base + l0) * ldm + 32 * h + 8 * nt + 2 * tq) = pack_bf16(c[nt][0] * z_lo, c[nt][1] * z_lo);
+        if (l0 + 8 < l_end)
+          *reinterpret_cast<unsigned*>(msg + (base + l0 + 8) * ldm + 32 * h + 8 * nt + 2 * tq) = pack_bf16(c[nt][2] * z_hi, c[nt][3] * z_hi);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ linear attention (windows)
 // C = 128 (8 heads x 16), T tokens per item (T <= 32). One block (128 threads) per item.
 template <int T, bool BF>
@@ -521,6 +717,84 @@ __global__ void __launch_bounds__(128) attn_windows_kernel(const void* __restric
     } else {
       *reinterpret_cast<float4*>(static_cast<float*>(msgv) + (row0 + r) * ldm + e0) =
           make_float4(sK[r][e0], sK[r][e0 + 1], sK[r][e0 + 2], sK[r][e0 + 3]);
+    }
+  }
+}
+
+
+// bf16 variant on mma.sync: block = window (8 warps = 8 heads of 16 channels), tokens padded 25 -> 32 with zero K' / V
+// rows. Per head: KV^T[v][d] = sum_s V[s][v] K'[s][d] (A = V^T, B = K') and Ksum through an A tile whose row 0 is all
+// ones; the accumulator fragments ARE the B fragments of the second product out[l][v] = Q'[l][d] KV[d][v] (transposed
+// accumulation puts (d pair, v) in the right lanes), so nothing goes back through shared memory.
+template <int T>
+__global__ void __launch_bounds__(256) attn_windows_mma_kernel(const unsigned short* __restrict__ Q, long long ldq,
+                                                               const unsigned short* __restrict__ K, long long ldk,
+                                                               const unsigned short* __restrict__ V, long long ldv,
+                                                               unsigned short* __restrict__ msg, long long ldm,
+                                                               const int* __restrict__ n_items_dev, float eps) {
+  static_assert(T <= 32, "window tokens are padded to 32");
+  const int item = blockIdx.x;
+  if (item >= *n_items_dev) return;
+  __shared__ __align__(128) char sm[3][32 * 256];        // Q', K', V: [32 rows][128 ch] bf16, 16-byte chunks XOR (row & 7)
+  const int t = threadIdx.x;
+  const size_t row0 = static_cast<size_t>(item) * T;
+  for (int c = t; c < 3 * T * 16; c += 256) {
+    const int which = c / (T * 16), rc = c % (T * 16), r = rc >> 4, ch = rc & 15;
+    const unsigned short* src = which == 0 ? Q + (row0 + r) * ldq : which == 1 ? K + (row0 + r) * ldk : V + (row0 + r) * ldv;
+    cp_async16(sm[which] + r * 256 + ((ch ^ (r & 7)) << 4), src + ch * 8, true);
+  }
+  cp_async_commit();
+  for (int c = t; c < 2 * (32 - T) * 16; c += 256) {     // zero padding rows of K' and V
+    const int which = 1 + c / ((32 - T) * 16), rc = c % ((32 - T) * 16), r = T + (rc >> 4), ch = rc & 15;
+    *reinterpret_cast<uint4*>(sm[which] + r * 256 + (ch << 4)) = make_uint4(0, 0, 0, 0);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  const int h = t >> 5, lane = t & 31;
+  const int j = lane >> 3, r = lane & 7, g = lane >> 2, tq = lane & 3;
+  auto addr = [&](int which, int row, int chunk) { return sm[which] + row * 256 + ((chunk ^ (row & 7)) << 4); };
+  float ckv[2][4], cks[2][4];                            // [d tile]: KV^T rows v = g / g+8, cols d = 8 j' + 2 tq (+1)
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { ckv[a][e] = 0.f; cks[a][e] = 0.f; }
+  }
+  const unsigned one = (g == 0) ? 0x3F803F80u : 0u;
+  const unsigned aones[4] = {one, 0u, one, 0u};
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    unsigned a[4], b[4];
+    ldsm_x4_t(a, addr(2, 16 * ks + r + 8 * (j >> 1), 2 * h + (j & 1)));     // A = V^T: m = v, k = token
+    ldsm_x4_t(b, addr(1, 16 * ks + r + 8 * (j & 1), 2 * h + (j >> 1)));     // B = K': k = token, n = d
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      mma_bf16(ckv[nt], a, b[2 * nt], b[2 * nt + 1]);
+      mma_bf16(cks[nt], aones, b[2 * nt], b[2 * nt + 1]);
+    }
+  }
+  const unsigned bv0[2] = {pack_bf16(ckv[0][0], ckv[0][1]), pack_bf16(ckv[1][0], ckv[1][1])};   // n tile v 0-7
+  const unsigned bv1[2] = {pack_bf16(ckv[0][2], ckv[0][3]), pack_bf16(ckv[1][2], ckv[1][3])};   // n tile v 8-15
+  const unsigned bd[2] = {pack_bf16(cks[0][0], cks[0][1]), pack_bf16(cks[1][0], cks[1][1])};    // column 0 = Ksum
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    unsigned a[4];
+    ldsm_x4(a, addr(0, 16 * mt + r + 8 * (j & 1), 2 * h + (j >> 1)));       // A = Q': m = token, k = d
+    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, cd[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_bf16(c0, a, bv0[0], bv0[1]);
+    mma_bf16(c1, a, bv1[0], bv1[1]);
+    mma_bf16(cd, a, bd[0], bd[1]);
+    const float den_lo = __shfl_sync(0xffffffffu, cd[0], lane & ~3), den_hi = __shfl_sync(0xffffffffu, cd[2], lane & ~3);
+    const float z_lo = 1.f / (den_lo + eps), z_hi = 1.f / (den_hi + eps);
+    const int l0 = 16 * mt + g;
+    if (l0 < T) {
+      unsigned short* o = msg + (row0 + l0) * ldm + 16 * h + 2 * tq;
+      *reinterpret_cast<unsigned*>(o) = pack_bf16(c0[0] * z_lo, c0[1] * z_lo);
+      *reinterpret_cast<unsigned*>(o + 8) = pack_bf16(c1[0] * z_lo, c1[1] * z_lo);
+    }
+    if (l0 + 8 < T) {
+      unsigned short* o = msg + (row0 + l0 + 8) * ldm + 16 * h + 2 * tq;
+      *reinterpret_cast<unsigned*>(o) = pack_bf16(c0[2] * z_hi, c0[3] * z_hi);
+      *reinterpret_cast<unsigned*>(o + 8) = pack_bf16(c1[2] * z_hi, c1[3] * z_hi);
     }
   }
 }
@@ -1195,13 +1469,23 @@ int linear_attention_long(const void* Q, long long ldq, const void* K, long long
     MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmem));
     MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmemBf));
     MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmemBf));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMStages * kMSlabBytes));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMStages * kMSlabBytes));
     attr_set = true;
   }
   const int asplits = std::max(1, std::min((L + kSlab - 1) / kSlab, (4 * 148 + n - 1) / n));
   if (bf16) {
-    kv_partial_kernel<true><<<dim3(splits, n), 256, kKvSmemBf, st>>>(K, ldk, V, ldv, kv_part, S, splits);
-    kv_reduce_kernel<<<dim3((8 * 1056 + 255) / 256, n), 256, 0, st>>>(kv_part, kv, splits);
-    attn_apply_kernel<true><<<dim3(asplits, n), 256, kApSmemBf, st>>>(Q, ldq, kv, msg, ldm, L, S, 1e-6f, asplits);
+    if (kUseMmaAttention) {
+      const int msplits = std::max(1, std::min((L + kMS - 1) / kMS, (4 * 148 + n - 1) / n));
+      kv_partial_mma_kernel<<<dim3(splits, n), 256, 2 * kMStages * kMSlabBytes, st>>>(K, ldk, V, ldv, kv_part, S, splits);
+      kv_reduce_kernel<<<dim3((8 * 1056 + 255) / 256, n), 256, 0, st>>>(kv_part, kv, splits);
+      attn_apply_mma_kernel<<<dim3(msplits, n), 256, kMStages * kMSlabBytes, st>>>(Q, ldq, kv, static_cast<unsigned short*>(msg), ldm,
+                                                                                  L, 1e-6f, msplits);
+    } else {
+      kv_partial_kernel<true><<<dim3(splits, n), 256, kKvSmemBf, st>>>(K, ldk, V, ldv, kv_part, S, splits);
+      kv_reduce_kernel<<<dim3((8 * 1056 + 255) / 256, n), 256, 0, st>>>(kv_part, kv, splits);
+      attn_apply_kernel<true><<<dim3(asplits, n), 256, kApSmemBf, st>>>(Q, ldq, kv, msg, ldm, L, S, 1e-6f, asplits);
+    }
   } else {
     kv_partial_kernel<false><<<dim3(splits, n), 256, kKvSmem, st>>>(K, ldk, V, ldv, kv_part, S, splits);
     kv_reduce_kernel<<<dim3((8 * 1056 + 255) / 256, n), 256, 0, st>>>(kv_part, kv, splits);
@@ -1215,7 +1499,12 @@ int linear_attention_windows(const void* Q, long long ldq, const void* K, long l
                              long long ldv, void* msg, long long ldm, const int* n_items_dev,
                              int max_items, int T, cudaStream_t st, int bf16) {
   if (T != 25 || max_items <= 0) return MFR_ERR_UNSUPPORTED;
-  if (bf16) attn_windows_kernel<25, true><<<max_items, 128, 0, st>>>(Q, ldq, K, ldk, V, ldv, msg, ldm, n_items_dev, 1e-6f);
+  if (bf16 && kUseMmaAttention) {
+    if ((ldq | ldk | ldv) & 7) return MFR_ERR_ARG;
+    attn_windows_mma_kernel<25><<<max_items, 256, 0, st>>>(static_cast<const unsigned short*>(Q), ldq, static_cast<const unsigned short*>(K), ldk,
+                                                          static_cast<const unsigned short*>(V), ldv, static_cast<unsigned short*>(msg), ldm,
+                                                          n_items_dev, 1e-6f);
+  } else if (bf16) attn_windows_kernel<25, true><<<max_items, 128, 0, st>>>(Q, ldq, K, ldk, V, ldv, msg, ldm, n_items_dev, 1e-6f);
   else attn_windows_kernel<25, false><<<max_items, 128, 0, st>>>(Q, ldq, K, ldk, V, ldv, msg, ldm, n_items_dev, 1e-6f);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
