@@ -1,6 +1,7 @@
 // C ABI of libmfr_b200.so (declared in include/mfr_b200.h).
 #include "../../include/mfr_b200.h"
 
+#include <algorithm>
 #include "common.cuh"
 #include "conv_gemm.cuh"
 #include "loftr_engine.cuh"
@@ -248,6 +249,30 @@ float mfr_debug_time_conv(const float* x, int N, int H, int W, int Cin, const fl
   mfr::ConvGemmParams p;
   if (mfr::conv_gemm_build(d, &p) != MFR_OK) return -1.f;
   return mfr::conv_gemm_time_prebuilt(p, iters, nullptr);
+}
+
+int mfr_linear_attention(const void* q, const void* k, const void* v, void* msg, int n, int L, int S, int windows,
+                         int bf16, void* stream) {
+  if (!q || !k || !v || !msg || n <= 0) return MFR_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (windows) {
+    int* cnt = nullptr;
+    if (cudaMalloc(&cnt, sizeof(int)) != cudaSuccess) return MFR_ERR_CUDA;
+    cudaMemcpyAsync(cnt, &n, sizeof(int), cudaMemcpyHostToDevice, st);
+    const int r = mfr::linear_attention_windows(q, 128, k, 128, v, 128, msg, 128, cnt, n, 25, st, bf16);
+    cudaStreamSynchronize(st);
+    cudaFree(cnt);
+    return r;
+  }
+  if (L <= 0 || S <= 0) return MFR_ERR_ARG;
+  const int splits = std::max(1, std::min((S + 63) / 64, (2 * 148 + n - 1) / n));
+  float *kv_part = nullptr, *kv = nullptr;
+  if (cudaMalloc(&kv_part, static_cast<size_t>(n) * splits * 8448 * sizeof(float)) != cudaSuccess) return MFR_ERR_CUDA;
+  if (cudaMalloc(&kv, static_cast<size_t>(n) * 8448 * sizeof(float)) != cudaSuccess) { cudaFree(kv_part); return MFR_ERR_CUDA; }
+  const int r = mfr::linear_attention_long(q, 256, k, 256, v, 256, msg, 256, kv_part, kv, n, L, S, 8, 32, splits, st, bf16);
+  cudaStreamSynchronize(st);
+  cudaFree(kv_part); cudaFree(kv);
+  return r;
 }
 
 }  // extern "C"

@@ -1402,6 +1402,105 @@ __global__ void __launch_bounds__(128) fine_match_kernel(const float* __restrict
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ stem on mma.sync (bf16 x 3)
+// The 7x7 stride-2 stem (1 -> 128 channels, resnet_fpn.py:52-54) as an implicit GEMM on warp-level tensor cores:
+// M = 16 output pixels of one row, N = 32 channels per warp, K = 8 ky x 8 kx (row ky = 7 and tap kx = 7 carry zero
+// weights, so two consecutive K elements are two consecutive image pixels and every A register is one aligned 32-bit
+// shared-memory load). fp32 accuracy is kept by splitting image and weights into bf16 hi + lo parts and accumulating
+// hi*hi + hi*lo + lo*hi in fp32 (error ~2^-16 relative, below TF32). Block = one output row of one image.
+constexpr bool kUseMmaStem = true;
+template <bool OBF>
+__global__ void __launch_bounds__(128) stem_mma_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, void* __restrict__ out,
+                                                       int H, int W, int Ho, int Wo, int PW) {
+  extern __shared__ __align__(16) unsigned short stem_sm[];       // [2 (hi, lo)][8 rows][PW]
+  const int n = blockIdx.y, y = blockIdx.x;
+  const int t = threadIdx.x, wid = t >> 5, lane = t & 31, g = lane >> 2, tq = lane & 3;
+  unsigned short* p_hi = stem_sm;
+  unsigned short* p_lo = stem_sm + 8 * PW;
+  for (int idx = t; idx < 8 * PW; idx += 128) {
+    const int ky = idx / PW, col = idx - ky * PW;
+    const int iy = 2 * y - 3 + ky, ix = col - 3;
+    float v = 0.f;
+    if (ky < 7 && iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[(static_cast<size_t>(n) * H + iy) * W + ix];
+    const unsigned short hi = f2bf(v);
+    p_hi[idx] = hi;
+    p_lo[idx] = f2bf(v - bf2f(hi));
+  }
+  // B fragments of this warp's 32 channels: k = 16 ks + {2 tq, 2 tq + 1} -> (ky = 2 ks, kx = 2 tq + {0, 1}); + 8 -> ky = 2 ks + 1
+  unsigned bh[4][4][2], bl[4][4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const float* wc = w + (32 * wid + 8 * nt + g) * 49;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int ky = 2 * ks + half, kx = 2 * tq;
+        const float w0 = ky < 7 ? wc[ky * 7 + kx] : 0.f;
+        const float w1 = (ky < 7 && kx + 1 < 7) ? wc[ky * 7 + kx + 1] : 0.f;
+        const unsigned short h0 = f2bf(w0), h1 = f2bf(w1);
+        bh[nt][ks][half] = static_cast<unsigned>(h0) | (static_cast<unsigned>(h1) << 16);
+        bl[nt][ks][half] = pack_bf16(w0 - bf2f(h0), w1 - bf2f(h1));
+      }
+    }
+  }
+  float bia[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    bia[nt][0] = bias[32 * wid + 8 * nt + 2 * tq];
+    bia[nt][1] = bias[32 * wid + 8 * nt + 2 * tq + 1];
+  }
+  __syncthreads();
+  const int mtiles = (Wo + 15) / 16;
+  for (int mt = 0; mt < mtiles; ++mt) {
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+    }
+    const int c_lo = 2 * (16 * mt + g) + 2 * tq;        // patch column of (pixel row g, kx = 2 tq)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      unsigned ah[4], al[4];
+      const int r0 = (2 * ks) * PW, r1 = (2 * ks + 1) * PW;
+      ah[0] = *reinterpret_cast<const unsigned*>(p_hi + r0 + c_lo);
+      ah[1] = *reinterpret_cast<const unsigned*>(p_hi + r0 + c_lo + 16);
+      ah[2] = *reinterpret_cast<const unsigned*>(p_hi + r1 + c_lo);
+      ah[3] = *reinterpret_cast<const unsigned*>(p_hi + r1 + c_lo + 16);
+      al[0] = *reinterpret_cast<const unsigned*>(p_lo + r0 + c_lo);
+      al[1] = *reinterpret_cast<const unsigned*>(p_lo + r0 + c_lo + 16);
+      al[2] = *reinterpret_cast<const unsigned*>(p_lo + r1 + c_lo);
+      al[3] = *reinterpret_cast<const unsigned*>(p_lo + r1 + c_lo + 16);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        mma_bf16(acc[nt], al, bh[nt][ks][0], bh[nt][ks][1]);
+        mma_bf16(acc[nt], ah, bl[nt][ks][0], bl[nt][ks][1]);
+        mma_bf16(acc[nt], ah, bh[nt][ks][0], bh[nt][ks][1]);
+      }
+    }
+    const int x_lo = 16 * mt + g;
+    const size_t row = (static_cast<size_t>(n) * Ho + y) * Wo;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int c = 32 * wid + 8 * nt + 2 * tq;
+      const float o0 = fmaxf(acc[nt][0] + bia[nt][0], 0.f), o1 = fmaxf(acc[nt][1] + bia[nt][1], 0.f);
+      const float o2 = fmaxf(acc[nt][2] + bia[nt][0], 0.f), o3 = fmaxf(acc[nt][3] + bia[nt][1], 0.f);
+      if constexpr (OBF) {
+        unsigned short* o = static_cast<unsigned short*>(out);
+        if (x_lo < Wo) *reinterpret_cast<unsigned*>(o + (row + x_lo) * 128 + c) = pack_bf16(o0, o1);
+        if (x_lo + 8 < Wo) *reinterpret_cast<unsigned*>(o + (row + x_lo + 8) * 128 + c) = pack_bf16(o2, o3);
+      } else {
+        float* o = static_cast<float*>(out);
+        if (x_lo < Wo) *reinterpret_cast<float2*>(o + (row + x_lo) * 128 + c) = make_float2(o0, o1);
+        if (x_lo + 8 < Wo) *reinterpret_cast<float2*>(o + (row + x_lo + 8) * 128 + c) = make_float2(o2, o3);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -1410,6 +1509,16 @@ __global__ void __launch_bounds__(128) fine_match_kernel(const float* __restrict
 int stem_conv7x7(const float* img, const float* w, const float* bias, float* out, int NI, int H, int W,
                  cudaStream_t st, int out_bf16) {
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  if (kUseMmaStem) {
+    const int PW = 32 * ((Wo + 15) / 16) + 8;                 // patch columns: 2 px + kx for every pixel of the padded row
+    const int smem = 2 * 8 * PW * 2;
+    if (smem <= 48 * 1024) {
+      if (out_bf16) stem_mma_kernel<true><<<dim3(Ho, NI), 128, smem, st>>>(img, w, bias, out, H, W, Ho, Wo, PW);
+      else stem_mma_kernel<false><<<dim3(Ho, NI), 128, smem, st>>>(img, w, bias, out, H, W, Ho, Wo, PW);
+      MFR_CUDA_CHECK(cudaGetLastError());
+      return MFR_OK;
+    }
+  }
   dim3 grid((Wo + kStemPx - 1) / kStemPx, Ho, NI);
   if (out_bf16) stem_kernel<true><<<grid, 128, 0, st>>>(img, w, bias, out, H, W, Ho, Wo);
   else stem_kernel<false><<<grid, 128, 0, st>>>(img, w, bias, out, H, W, Ho, Wo);

@@ -182,3 +182,38 @@ def test_empty_match_set(sd):
     pts = m.match_arrays(i0[0, 0].numpy(), i1[0, 0].numpy())
     assert pts.shape == (1, 4) and np.isnan(pts).all()      # matchers.py:58-59 NaN row
     eng.close()
+
+
+def _lin_att_ref(q, k, v, heads, eps=1e-6):
+    """linear_attention.py:31-45 on already feature-mapped q', k' (fp64 restatement; the v / S ... * S pair cancels)."""
+    n, L, C = q.shape
+    d = C // heads
+    Q = q.double().view(n, L, heads, d); K = k.double().view(n, -1, heads, d); V = v.double().view(n, -1, heads, d)
+    KV = torch.einsum("nshd,nshv->nhdv", K, V)
+    Z = 1 / (torch.einsum("nlhd,nhd->nlh", Q, K.sum(dim=1)) + eps)
+    return torch.einsum("nlhd,nhdv,nlh->nlhv", Q, KV, Z).reshape(n, L, C)
+
+
+@pytest.mark.parametrize("windows,n,L,S", [(0, 3, 301, 417), (0, 2, 64, 4800), (1, 37, 25, 25)])
+@pytest.mark.parametrize("bf16", [0, 1])
+def test_linear_attention_stage(mfr, windows, n, L, S, bf16):
+    """Coarse (8 x 32) and fine-window (8 x 16) linear attention, fp32 SIMT kernels and the bf16 tensor-core kernels,
+    against an fp64 restatement. Ragged L / S exercise the zero-filled slab tails. Tolerance: fp32 1e-4 of the output
+    range; bf16 operands and bf16-rounded KV 2e-2 (8-bit mantissas, sums of <= 4800 positive terms in fp32)."""
+    lib = mfr.load()
+    g = torch.Generator().manual_seed(11 + windows)
+    C = 128 if windows else 256
+    q = torch.nn.functional.elu(torch.randn(n, L, C, generator=g)) + 1
+    k = torch.nn.functional.elu(torch.randn(n, S, C, generator=g)) + 1
+    v = torch.randn(n, S, C, generator=g)
+    dt = torch.bfloat16 if bf16 else torch.float32
+    qd, kd, vd = (x.to(dt).cuda().contiguous() for x in (q, k, v))
+    out = torch.full((n, L, C), float("nan"), dtype=dt, device="cuda")
+    mfr.check(lib.mfr_linear_attention(mfr.ptr(qd), mfr.ptr(kd), mfr.ptr(vd), mfr.ptr(out), n, L, S, windows, bf16,
+                                       mfr.cur_stream()))
+    torch.cuda.synchronize()
+    ref = _lin_att_ref(qd.cpu().float(), kd.cpu().float(), vd.cpu().float(), 8)
+    got = out.cpu().double()
+    assert torch.isfinite(got).all()
+    tol = 2e-2 if bf16 else 1e-4
+    assert ((got - ref).abs().max() / ref.abs().max()).item() < tol
