@@ -36,6 +36,10 @@ struct StepInfo {
   int launches = 1;     // kernels this step launches
 };
 
+// bf16 mode: the coarse correlation reads the bf16 shadow of the final tokens (kind::f16, half the operand bytes)
+constexpr bool kCorrelationBf16 = true;
+constexpr size_t kW16Capacity = static_cast<size_t>(16) * 1024 * 1024;   // bf16 weight copies (elements): ~11.5 M used
+
 struct LoftrEngine {
   int B, H, W, NI;
   int H2, W2, H4, W4, H8, W8, L, Mcap;
@@ -69,6 +73,12 @@ struct LoftrEngine {
   float* img = nullptr;
   float *a0, *a1, *a2, *b0, *b1, *b2, *c0, *c1, *c2, *fc, *p4a, *p4b, *p4c, *p2a, *p2b;
   float *tok, *qkv, *msg, *mrg, *h1, *h2, *kvp, *kv, *S;
+  float *tokb = nullptr, *ftokb = nullptr;   // bf16 mode: bf16 shadows of tok / ftok (same shape; float-typed like the other bf16 buffers)
+  size_t ftok_elems = 0;
+  float* shadow(float* x) const {            // same element offset inside the shadow buffer
+    if (x >= ftok && x < ftok + ftok_elems) return ftokb + (x - ftok) / 2;
+    return tokb + (x - tok) / 2;
+  }
   CoarseMatchBuffers cm;
   float *cin, *cproj, *win, *ftok, *fqkv, *fmsg, *fmrg, *fh1, *fh2, *mk1f, *expec;
   // graph
@@ -109,7 +119,8 @@ struct LoftrEngine {
   void conv(const std::string& wname, const float* x, int N, int Hh, int Ww, int Cin, long long ldx,
             int Cout, int R, int stride, bool bias, const float* residual, int act, float* out,
             long long ldo, int act_cols = 0, const int* dyn_w = nullptr, const float* w_override = nullptr,
-            const float* bias_override = nullptr, int in_bf16 = 0, int out_bf16 = 0) {
+            const float* bias_override = nullptr, int in_bf16 = 0, int out_bf16 = 0, int w_rows_total = 0,
+            int w_row_off = 0) {
     ConvGemmDesc d{};
     d.x = x; d.N = N; d.H = Hh; d.W = Ww; d.Cin = Cin; d.ldx = ldx;
     d.in_bf16 = in_bf16; d.out_bf16 = out_bf16;
@@ -120,11 +131,13 @@ struct LoftrEngine {
       for (const auto& e : bf16_convs)
         if (e.name == wname) { off = e.off; found = true; }     // cross layers build the same weights twice
       if (!found) {
-        bf16_convs.push_back(Bf16Conv{wname, Cout, R * R, Cin, cin_pad, off});
-        w16_total += (static_cast<size_t>(Cout) * R * R * cin_pad + 63) / 64 * 64;
+        // a GEMM may use a row window [w_row_off, w_row_off + Cout) of a larger weight (q / k|v parts of qkv)
+        const int rows_total = w_rows_total > 0 ? w_rows_total : Cout;
+        bf16_convs.push_back(Bf16Conv{wname, rows_total, R * R, Cin, cin_pad, off});
+        w16_total += (static_cast<size_t>(rows_total) * R * R * cin_pad + 63) / 64 * 64;
       }
       d.ldw = cin_pad;
-      w_override = reinterpret_cast<const float*>(wblob16 + off);
+      w_override = reinterpret_cast<const float*>(wblob16 + off + static_cast<size_t>(w_row_off) * R * R * cin_pad);
     }
     d.w = w_override ? w_override : W_(wname + ".w");
     d.Cout = Cout; d.R = R; d.S = R; d.stride = stride; d.pad = R / 2;
@@ -201,12 +214,18 @@ struct LoftrEngine {
     // The buffers are float-typed: `tb` bf16 elements per float when converting element offsets.
     const int tbf = precision == 1 ? 1 : 0, tb = tbf ? 2 : 1;
     auto E = [tb](float* ptr, size_t elems) { return ptr + elems / tb; };
+    // bf16 mode: the GEMMs that read the token stream (q|k|v, mlp0) take their A operand from its bf16 shadow
+    // (written by the LayerNorms below): half the operand bytes and kind::f16 MMAs instead of kind::tf32.
+    float* xb = tbf ? shadow(x) : x;
+    float* srcb = tbf ? shadow(src) : src;
+    const std::string qn = p + ".qkv";
     if (x == src) {
-      conv("", x, n, 1, rows, C, ld2, 3 * C, 1, 1, false, nullptr, ACT_ELU1, qkv_x, ld3, 2 * C, dyn_rows, wq, nullptr, 0, tbf);
+      conv(qn, xb, n, 1, rows, C, ld2, 3 * C, 1, 1, false, nullptr, ACT_ELU1, qkv_x, ld3, 2 * C, dyn_rows, wq, nullptr, tbf, tbf,
+           3 * C, 0);
     } else {
-      conv("", x, n, 1, rows, C, ld2, C, 1, 1, false, nullptr, ACT_ELU1, qkv_x, ld3, C, dyn_rows, wq, nullptr, 0, tbf);
-      conv("", src, n, 1, rows, C, ld2, 2 * C, 1, 1, false, nullptr, ACT_ELU1, E(qkv_s, C), ld3, C, dyn_rows,
-           wq + static_cast<size_t>(C) * C, nullptr, 0, tbf);
+      conv(qn, xb, n, 1, rows, C, ld2, C, 1, 1, false, nullptr, ACT_ELU1, qkv_x, ld3, C, dyn_rows, wq, nullptr, tbf, tbf, 3 * C, 0);
+      conv(qn, srcb, n, 1, rows, C, ld2, 2 * C, 1, 1, false, nullptr, ACT_ELU1, E(qkv_s, C), ld3, C, dyn_rows,
+           wq + static_cast<size_t>(C) * C, nullptr, tbf, tbf, 3 * C, C);
     }
     if (!windows) {
       float* kvp_ = kvp; float* kv_ = kv;
@@ -231,31 +250,35 @@ struct LoftrEngine {
     const float *g1 = W_(p + ".norm1.g"), *b1 = W_(p + ".norm1.b");
     const float *g2 = W_(p + ".norm2.g"), *b2 = W_(p + ".norm2.b");
     const long long tot = static_cast<long long>(n) * rows;
+    // norm1(message) is only read by mlp0: in bf16 mode it goes straight to the shadow's message half
     if (dyn_rows == nullptr) {
       push("layernorm", [=](cudaStream_t st) {
+        if (tbf) return layernorm_rows(mrg_x, C, g1, b1, nullptr, 0, nullptr, 0, tot, C, nullptr, st, E(xb, C), ld2);
         return layernorm_rows(mrg_x, C, g1, b1, nullptr, 0, x + C, ld2, tot, C, nullptr, st);
       });
     } else {
       for (int side = 0; side < n; ++side) {
         const size_t o1 = static_cast<size_t>(side) * rows * C, o2 = static_cast<size_t>(side) * rows * ld2;
         push("layernorm", [=](cudaStream_t st) {
+          if (tbf) return layernorm_rows(mrg_x + o1, C, g1, b1, nullptr, 0, nullptr, 0, rows, C, dyn_rows, st, E(xb, o2 + C), ld2);
           return layernorm_rows(mrg_x + o1, C, g1, b1, nullptr, 0, x + o2 + C, ld2, rows, C, dyn_rows, st);
         });
       }
     }
-    conv(p + ".mlp0", x, n, 1, rows, 2 * C, ld2, 2 * C, 1, 1, false, nullptr, ACT_RELU, h1_x, ld2, 0, dyn_rows, nullptr,
-         nullptr, 0, tbf);
+    conv(p + ".mlp0", xb, n, 1, rows, 2 * C, ld2, 2 * C, 1, 1, false, nullptr, ACT_RELU, h1_x, ld2, 0, dyn_rows, nullptr,
+         nullptr, tbf, tbf);
     conv(p + ".mlp2", h1_x, n, 1, rows, 2 * C, ld2, C, 1, 1, false, nullptr, ACT_NONE, h2_x, C, 0, dyn_rows, nullptr,
          nullptr, tbf, 0);
     if (dyn_rows == nullptr) {
       push("layernorm", [=](cudaStream_t st) {
-        return layernorm_rows(h2_x, C, g2, b2, x, ld2, x, ld2, tot, C, nullptr, st);
+        return layernorm_rows(h2_x, C, g2, b2, x, ld2, x, ld2, tot, C, nullptr, st, tbf ? xb : nullptr, ld2);
       });
     } else {
       for (int side = 0; side < n; ++side) {
         const size_t o1 = static_cast<size_t>(side) * rows * C, o2 = static_cast<size_t>(side) * rows * ld2;
         push("layernorm", [=](cudaStream_t st) {
-          return layernorm_rows(h2_x + o1, C, g2, b2, x + o2, ld2, x + o2, ld2, rows, C, dyn_rows, st);
+          return layernorm_rows(h2_x + o1, C, g2, b2, x + o2, ld2, x + o2, ld2, rows, C, dyn_rows, st,
+                                tbf ? E(xb, o2) : nullptr, ld2);
         });
       }
     }
@@ -286,7 +309,7 @@ struct LoftrEngine {
     };
     // the bf16 weight blob must exist before the conv steps are built (its size is known only afterwards:
     // reserve the upper bound = all backbone conv weights)
-    if (bf) wblob16 = alloc<unsigned short>(static_cast<size_t>(12) * 1024 * 1024, "weights_bf16");
+    if (bf) wblob16 = alloc<unsigned short>(kW16Capacity, "weights_bf16");
     a0 = balloc(px2 * 128, "a0"); a1 = balloc(px2 * 128, "a1"); a2 = balloc(px2 * 128, "a2");
     b0 = balloc(px4 * c196, "b0"); b1 = balloc(px4 * c196, "b1"); b2 = balloc(px4 * c196, "b2");
     c0 = balloc(px8 * 256, "c0"); c1 = balloc(px8 * 256, "c1"); c2 = balloc(px8 * 256, "c2");
@@ -295,6 +318,7 @@ struct LoftrEngine {
     p2a = balloc(px2 * c196, "p2a"); p2b = balloc(px2 * c196, "p2b");
     float* featf = alloc<float>(px2 * 128, "feat_f");
     tok = alloc<float>(px8 * 512, "tok");
+    if (bf) tokb = reinterpret_cast<float*>(alloc<unsigned short>(px8 * 512, "tok_bf16"));
     qkv = alloc<float>(px8 * 768, "qkv"); msg = alloc<float>(px8 * 256, "msg"); mrg = alloc<float>(px8 * 256, "mrg");
     h1 = alloc<float>(px8 * 512, "h1"); h2 = alloc<float>(px8 * 256, "h2");
     splits_kv = std::max(1, std::min(L / 16, (2 * 148 + NI - 1) / NI));   // ~2 blocks per SM when all images run
@@ -317,6 +341,8 @@ struct LoftrEngine {
     cproj = alloc<float>(static_cast<size_t>(2) * Mcap * 128, "fine_cproj");
     win = alloc<float>(frows * 256, "fine_win");
     ftok = alloc<float>(frows * 256, "fine_tok");
+    ftok_elems = frows * 256;
+    if (bf) ftokb = reinterpret_cast<float*>(alloc<unsigned short>(frows * 256, "fine_tok_bf16"));
     fqkv = alloc<float>(frows * 384, "fine_qkv"); fmsg = alloc<float>(frows * 128); fmrg = alloc<float>(frows * 128);
     fh1 = alloc<float>(frows * 256); fh2 = alloc<float>(frows * 128);
     mk1f = alloc<float>(BL * 2, "mkpts1_f"); expec = alloc<float>(BL * 3, "expec_f");
@@ -363,15 +389,15 @@ struct LoftrEngine {
     }
     bconv("layer1_outconv2.0", p2a, H2, W2, 196, c196, 196, 3, 1, true, nullptr, ACT_LEAKY, p2b, c196, B16);
     bconv("layer1_outconv2.3", p2b, H2, W2, 196, c196, 128, 3, 1, false, nullptr, ACT_NONE, featf, 128, 0);   // fp32 out
-    if (bf && w16_total > static_cast<size_t>(12) * 1024 * 1024) {
-      fprintf(stderr, "[mfr_b200] bf16 weight blob too small\n");
-      return MFR_ERR_ARG;
-    }
 
     // ---------------------------------------------------------------- pos-enc + coarse transformer
     {
       float *f = fc, *t = tok; float* pe = W_("pos_enc"); const int n = NI, l = L;
       push("posenc", [=](cudaStream_t st) { return posenc_tokens(f, pe, t, 512, n, l, 256, st); });
+      if (bf) {
+        float* tb_ = tokb;
+        push("to_bf16", [=](cudaStream_t st) { return rows_to_bf16(t, 512, tb_, 512, static_cast<long long>(n) * l, 256, nullptr, st); });
+      }
     }
     const size_t half_tok = static_cast<size_t>(B) * L * 512, half_qkv = static_cast<size_t>(B) * L * 768;
     const size_t half_c = static_cast<size_t>(B) * L * 256, half_2c = static_cast<size_t>(B) * L * 512;
@@ -393,6 +419,7 @@ struct LoftrEngine {
       ConvGemmDesc d{};
       d.x = tok; d.N = B; d.H = 1; d.W = L; d.Cin = 256; d.ldx = 512;
       d.w = tok + half_tok; d.Cout = L; d.R = 1; d.S = 1; d.stride = 1; d.pad = 0;
+      if (kCorrelationBf16 && precision == 1) { d.x = tokb; d.w = tokb + half_tok / 2; d.in_bf16 = 1; }
       d.b_batched = 1; d.ldw = 512; d.act = ACT_NONE; d.alpha = 1.f / (256.f * temperature);
       d.out = S; d.ldo = L; d.ldr = L;
       ConvGemmParams p;
@@ -426,6 +453,14 @@ struct LoftrEngine {
     }
     {
       const int rows = Mcap * 25;
+      if (precision == 1) {   // bf16 shadow of the fine tokens (the encoder layers keep it current from here on)
+        for (int side = 0; side < 2; ++side) {
+          const float* src = ftok + static_cast<size_t>(side) * rows * 256;
+          float* dst = ftokb + static_cast<size_t>(side) * rows * 256 / 2;
+          const int* dr = cm.m_total + 2;
+          push("to_bf16", [=](cudaStream_t st) { return rows_to_bf16(src, 256, dst, 256, rows, 128, dr, st); });
+        }
+      }
       const size_t s_tok = static_cast<size_t>(rows) * 256, s_qkv = static_cast<size_t>(rows) * 384,
                    s_c = static_cast<size_t>(rows) * 128, s_2c = static_cast<size_t>(rows) * 256;
       encoder_layer("fine.0", 128, ftok, ftok, fqkv, fqkv, fmsg, fmrg, fh1, fh2, 2, rows, cm.m_total + 2,
@@ -440,6 +475,10 @@ struct LoftrEngine {
       push("fine_match", [=](cudaStream_t st) {
         return fine_match(f0, f1, 256, cmb.mkpts1_c, cmb.m_total, Mc, scale_f, mk, ex, st);
       });
+    }
+    if (bf && w16_total > kW16Capacity) {
+      fprintf(stderr, "[mfr_b200] bf16 weight blob too small\n");
+      return MFR_ERR_ARG;
     }
     return build_rc;
   }

@@ -806,7 +806,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta,
                                                         const float* __restrict__ res, long long ldr,
                                                         float* __restrict__ out, long long ldo,
-                                                        long long rows, const int* __restrict__ dyn_rows) {
+                                                        long long rows, const int* __restrict__ dyn_rows,
+                                                        unsigned short* __restrict__ out16, long long ldo16) {
   constexpr int V = C / 128;  // float4 per lane
   long long lim = rows;
   if (dyn_rows) lim = min(lim, static_cast<long long>(*dyn_rows));
@@ -844,8 +845,32 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       const float4 r = *reinterpret_cast<const float4*>(res + row * ldr + c);
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
-    *reinterpret_cast<float4*>(out + row * ldo + c) = o;
+    if (out) *reinterpret_cast<float4*>(out + row * ldo + c) = o;
+    if (out16) {     // bf16 shadow of the row (A operand of the next token GEMMs in bf16 mode)
+      uint2 u;
+      u.x = static_cast<unsigned>(f2bf(o.x)) | (static_cast<unsigned>(f2bf(o.y)) << 16);
+      u.y = static_cast<unsigned>(f2bf(o.z)) | (static_cast<unsigned>(f2bf(o.w)) << 16);
+      *reinterpret_cast<uint2*>(out16 + row * ldo16 + c) = u;
+    }
   }
+  }
+}
+
+// dst16[row][0..C) = bf16(src[row][0..C)), 4 channels per thread
+__global__ void rows_to_bf16_kernel(const float* __restrict__ src, long long lds, unsigned short* __restrict__ dst,
+                                    long long ldd, long long rows, int C4, const int* __restrict__ dyn_rows) {
+  long long lim = rows;
+  if (dyn_rows) lim = min(lim, static_cast<long long>(*dyn_rows));
+  const long long total = lim * C4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / C4;
+    const int c = static_cast<int>(i - row * C4) * 4;
+    const float4 f = *reinterpret_cast<const float4*>(src + row * lds + c);
+    uint2 u;
+    u.x = static_cast<unsigned>(f2bf(f.x)) | (static_cast<unsigned>(f2bf(f.y)) << 16);
+    u.y = static_cast<unsigned>(f2bf(f.z)) | (static_cast<unsigned>(f2bf(f.w)) << 16);
+    *reinterpret_cast<uint2*>(dst + row * ldd + c) = u;
   }
 }
 
@@ -1621,15 +1646,28 @@ int linear_attention_windows(const void* Q, long long ldq, const void* K, long l
 
 int layernorm_rows(const float* in, long long ldi, const float* gamma, const float* beta,
                    const float* res, long long ldr, float* out, long long ldo, long long rows, int C,
-                   const int* dyn_rows, cudaStream_t st) {
+                   const int* dyn_rows, cudaStream_t st, void* out16, long long ldo16) {
   unsigned grid = static_cast<unsigned>(std::min<long long>((rows + 7) / 8, 148LL * 16));
   if (grid == 0) return MFR_OK;
+  if (out == nullptr && out16 == nullptr) return MFR_ERR_ARG;
+  if (out16 != nullptr && ((ldo16 & 3) || (reinterpret_cast<uintptr_t>(out16) & 7))) return MFR_ERR_ARG;
+  unsigned short* o16 = static_cast<unsigned short*>(out16);
   if (C == 256)
-    layernorm_kernel<256><<<grid, 256, 0, st>>>(in, ldi, gamma, beta, res, ldr, out, ldo, rows, dyn_rows);
+    layernorm_kernel<256><<<grid, 256, 0, st>>>(in, ldi, gamma, beta, res, ldr, out, ldo, rows, dyn_rows, o16, ldo16);
   else if (C == 128)
-    layernorm_kernel<128><<<grid, 256, 0, st>>>(in, ldi, gamma, beta, res, ldr, out, ldo, rows, dyn_rows);
+    layernorm_kernel<128><<<grid, 256, 0, st>>>(in, ldi, gamma, beta, res, ldr, out, ldo, rows, dyn_rows, o16, ldo16);
   else
     return MFR_ERR_UNSUPPORTED;
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int rows_to_bf16(const float* src, long long lds, void* dst, long long ldd, long long rows, int C, const int* dyn_rows,
+                 cudaStream_t st) {
+  if ((C & 3) || (lds & 3) || (ldd & 3) || rows <= 0) return MFR_ERR_ARG;
+  const long long total = rows * (C / 4);
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((total + 255) / 256, 148LL * 16));
+  rows_to_bf16_kernel<<<grid, 256, 0, st>>>(src, lds, static_cast<unsigned short*>(dst), ldd, rows, C / 4, dyn_rows);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }

@@ -39,7 +39,11 @@ int linear_attention_windows(const void* Q, long long ldq, const void* K, long l
 // limited by *dyn_rows (device) when non-null.
 int layernorm_rows(const float* in, long long ldi, const float* gamma, const float* beta,
                    const float* res, long long ldr, float* out, long long ldo, long long rows, int C,
-                   const int* dyn_rows, cudaStream_t st);
+                   const int* dyn_rows, cudaStream_t st, void* out16 = nullptr, long long ldo16 = 0);
+// out may be NULL when only the bf16 copy out16 (row stride ldo16 elements) is wanted.
+// dst16[row][0..C) = bf16(src[row][0..C)); rows optionally capped by *dyn_rows
+int rows_to_bf16(const float* src, long long lds, void* dst, long long ldd, long long rows, int C, const int* dyn_rows,
+                 cudaStream_t st);
 
 // ---- coarse matching on the materialised similarity matrix S [B][L][L] (coarse_matching.py) ----
 struct CoarseMatchBuffers {
