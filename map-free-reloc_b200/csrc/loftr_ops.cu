@@ -1064,6 +1064,23 @@ __device__ __forceinline__ void block_reduce_n(float (&v)[NV], float* sh /* [NV]
   __syncthreads();
 }
 
+// The rows of S stream through a thread-private multi-stage cp.async ring in shared memory (every thread copies and
+// later reads exactly its own 16-byte chunks, so no block barrier is involved): ~150 KB of loads stay in flight per SM
+// while the previous rows are reduced, instead of a load phase and a compute phase taking turns.
+constexpr int kCmStageBytes = 196608;   // stats: 2 stages x 4 rows, conf: 4 stages x 2 rows, of kF4 * kCmThreads float4
+template <int R>
+__device__ __forceinline__ void cm_issue(float4* stage, const float4* __restrict__ Sb, int i, int i1, int L4, int t) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+#pragma unroll
+    for (int k = 0; k < kF4; ++k) {
+      const int f = t + kCmThreads * k;
+      if (i + r < i1 && f < L4) cp_async16(stage + (r * kF4 + k) * kCmThreads + t, Sb + static_cast<size_t>(i + r) * L4 + f, true);
+    }
+  }
+  cp_async_commit();
+}
+
 __global__ void __launch_bounds__(kCmThreads) stats_fused_kernel(const float* __restrict__ S, float* __restrict__ row_max,
                                                           float* __restrict__ row_rsum, float* __restrict__ part,
                                                           int L, int rows_per_block, int splits) {
@@ -1077,14 +1094,24 @@ __global__ void __launch_bounds__(kCmThreads) stats_fused_kernel(const float* __
 #pragma unroll
   for (int c = 0; c < kF4 * 4; ++c) { cm[c] = -INFINITY; cs[c] = 0.f; }
   const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  extern __shared__ float4 cm_stage[];
+  constexpr int STAGES = 2, kStageF4 = R * kF4 * kCmThreads;
+  static_assert(STAGES * kStageF4 * 16 == kCmStageBytes, "ring size");
+#pragma unroll
+  for (int s_ = 0; s_ < STAGES - 1; ++s_) cm_issue<R>(cm_stage + s_ * kStageF4, Sb, i0 + s_ * R, i1, L4, t);
+  int stg = 0;
   for (int i = i0; i < i1; i += R) {
+    cm_issue<R>(cm_stage + ((stg + STAGES - 1) % STAGES) * kStageF4, Sb, i + (STAGES - 1) * R, i1, L4, t);
+    cp_async_wait<STAGES - 1>();
+    const float4* cur = cm_stage + stg * kStageF4;
+    stg = (stg + 1) % STAGES;
     float4 v[R][kF4];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int k = 0; k < kF4; ++k) {
         const int f = t + kCmThreads * k;
-        v[r][k] = (i + r < i1 && f < L4) ? __ldg(Sb + static_cast<size_t>(i + r) * L4 + f) : ninf;
+        v[r][k] = (i + r < i1 && f < L4) ? cur[(r * kF4 + k) * kCmThreads + t] : ninf;
       }
     float rm[R], rs[R];
 #pragma unroll
@@ -1170,14 +1197,24 @@ __global__ void __launch_bounds__(kCmThreads) conf_fused_kernel(const float* __r
 #pragma unroll
     for (int e = 0; e < 4; ++e) cbest[k * 4 + e] = -1.f;
   }
+  extern __shared__ float4 cm_stage[];
+  constexpr int STAGES = 4, kStageF4 = R * kF4 * kCmThreads;
+  static_assert(STAGES * kStageF4 * 16 == kCmStageBytes, "ring size");
+#pragma unroll
+  for (int s_ = 0; s_ < STAGES - 1; ++s_) cm_issue<R>(cm_stage + s_ * kStageF4, Sb, i0 + s_ * R, i1, L4, t);
+  int stg = 0;
   for (int i = i0; i < i1; i += R) {
+    cm_issue<R>(cm_stage + ((stg + STAGES - 1) % STAGES) * kStageF4, Sb, i + (STAGES - 1) * R, i1, L4, t);
+    cp_async_wait<STAGES - 1>();
+    const float4* cur = cm_stage + stg * kStageF4;
+    stg = (stg + 1) % STAGES;
     float4 v[R][kF4];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int k = 0; k < kF4; ++k) {
         const int f = t + kCmThreads * k;
-        v[r][k] = (i + r < i1 && f < L4) ? __ldg(Sb + static_cast<size_t>(i + r) * L4 + f) : make_float4(0, 0, 0, 0);
+        v[r][k] = (i + r < i1 && f < L4) ? cur[(r * kF4 + k) * kCmThreads + t] : make_float4(0, 0, 0, 0);
       }
     float best[R];
     int arg[R];
@@ -1678,14 +1715,20 @@ int coarse_match(const float* S, CoarseMatchBuffers f, int B, int L, int h_c, in
   const bool raw = input_is_conf;
   const bool fused = (L % 4 == 0) && L <= kCmThreads * 4 * kF4 && (reinterpret_cast<uintptr_t>(S) & 15) == 0;
   if (fused) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      MFR_CUDA_CHECK(cudaFuncSetAttribute(stats_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCmStageBytes));
+      MFR_CUDA_CHECK(cudaFuncSetAttribute(conf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCmStageBytes));
+      attr_set = true;
+    }
     // a block owns ceil(L / splits) rows (rounded to the row batch) and all columns
     const int rpb = ((L + splits - 1) / splits + 3) / 4 * 4;
     const int nblk = (L + rpb - 1) / rpb;
     if (!raw) {
-      stats_fused_kernel<<<dim3(nblk, B), kCmThreads, 0, st>>>(S, f.row_max, f.row_rsum, f.col_part, L, rpb, nblk);
+      stats_fused_kernel<<<dim3(nblk, B), kCmThreads, kCmStageBytes, st>>>(S, f.row_max, f.row_rsum, f.col_part, L, rpb, nblk);
       col_stats_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.col_max, f.col_rsum, L, nblk);
     }
-    conf_fused_kernel<<<dim3(nblk, B), kCmThreads, 0, st>>>(S, f.row_max, f.row_rsum, f.col_max, f.col_rsum, f.rconf_max,
+    conf_fused_kernel<<<dim3(nblk, B), kCmThreads, kCmStageBytes, st>>>(S, f.row_max, f.row_rsum, f.col_max, f.col_rsum, f.rconf_max,
                                                      f.rconf_arg, f.rconf_ties, f.col_part, L, rpb, nblk, raw);
     col_conf_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.cconf_max, L, nblk);
   } else {
@@ -1709,7 +1752,9 @@ int coarse_match(const float* S, CoarseMatchBuffers f, int B, int L, int h_c, in
   return MFR_OK;
 }
 
-int coarse_match_splits(int B, int L) { return std::max(1, std::min((L + 3) / 4, (2 * 148 + B - 1) / B)); }
+// row slabs per pair: the fused kernels run one block per SM (their cp.async ring fills the shared memory), so B * splits
+// is kept at or just under two full waves of the 148 SMs (rounding up would add a nearly empty third wave)
+int coarse_match_splits(int B, int L) { return std::max(1, std::min((L + 3) / 4, (2 * 148) / B)); }
 
 int coarse_match_alloc(int B, int L, int splits, CoarseMatchBuffers* o) {
   const size_t BL = static_cast<size_t>(B) * L;
