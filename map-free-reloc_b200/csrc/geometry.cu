@@ -111,12 +111,30 @@ __device__ __forceinline__ float sampson_sq_f(const float* E, float4 p) {
 // ================================================================================================
 // essential matrix: hypothesis generation + scoring
 // ================================================================================================
-__global__ void __launch_bounds__(kHypPerBlock) emat_hyp_kernel(
-    const float* __restrict__ kpts0, const float* __restrict__ kpts1, const int* __restrict__ offsets,
+// normalised correspondences of every pair, once, for the hypothesis kernel: pts[pair][i] = (K0^-1 x0, K1^-1 x1)
+__global__ void __launch_bounds__(256) emat_normalise_kernel(const float* __restrict__ kpts0, const float* __restrict__ kpts1,
+                                                             const int* __restrict__ offsets, const float* __restrict__ K0s,
+                                                             const float* __restrict__ K1s, int max_pts,
+                                                             float4* __restrict__ pts) {
+  const int pair = blockIdx.y;
+  const int n0 = offsets[pair];
+  const int N = min(offsets[pair + 1] - n0, max_pts);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  pts[static_cast<size_t>(pair) * max_pts + i] = normalise_pt(kpts0 + 2 * static_cast<size_t>(n0), kpts1 + 2 * static_cast<size_t>(n0), i,
+                                                              K0s + 9 * pair, K1s + 9 * pair);
+}
+
+// The hypothesis kernel is the long one of the back end (a 5-point solve is ~1.8 ms of dependent fp64 work) and runs on
+// the solver stream under the next batch's matcher, whose persistent GEMM CTAs hold all but 2 KB of an SM's shared
+// memory and all but ~21 K of its registers. It therefore keeps out of shared memory (the points come through L1 / L2,
+// 32 bytes of block-reduction scratch) and under 160 registers, so that one of its blocks fits NEXT to a GEMM CTA
+// instead of making that CTA (and, with static tile assignment, the whole GEMM kernel) wait for it.
+__global__ void __maxnreg__(160) emat_hyp_kernel(   // launched with <= kHypPerBlock threads
+    const float4* __restrict__ pts_all, const int* __restrict__ offsets,
     const float* __restrict__ K0s, const float* __restrict__ K1s, float pix_thr, int num_hyp,
     unsigned long long seed, int max_pts, HypResult* __restrict__ results) {
-  extern __shared__ float4 s_pts[];
-  __shared__ HypResult s_best[kHypPerBlock / 32];
+  __shared__ double s_cost[kHypPerBlock / 32];
   const int pair = blockIdx.y;
   const int n0 = offsets[pair];
   const int N = min(offsets[pair + 1] - n0, max_pts);
@@ -127,10 +145,7 @@ __global__ void __launch_bounds__(kHypPerBlock) emat_hyp_kernel(
   }
   const float* K0 = K0s + 9 * pair;
   const float* K1 = K1s + 9 * pair;
-  const float* k0 = kpts0 + 2 * static_cast<size_t>(n0);
-  const float* k1 = kpts1 + 2 * static_cast<size_t>(n0);
-  for (int i = threadIdx.x; i < N; i += blockDim.x) s_pts[i] = normalise_pt(k0, k1, i, K0, K1);
-  __syncthreads();
+  const float4* s_pts = pts_all + static_cast<size_t>(pair) * max_pts;
   const float thr = emat_threshold(pix_thr, K0, K1);
   const float thr2 = thr * thr;
 
@@ -145,7 +160,7 @@ __global__ void __launch_bounds__(kHypPerBlock) emat_hyp_kernel(
     sample_distinct<5>(st, N, idx);
     double x0[5][2], x1[5][2];
     for (int k = 0; k < 5; ++k) {
-      const float4 p = s_pts[idx[k]];
+      const float4 p = __ldg(s_pts + idx[k]);
       x0[k][0] = p.x; x0[k][1] = p.y; x1[k][0] = p.z; x1[k][1] = p.w;
     }
     ncand = five_point(x0, x1, Ec);
@@ -169,7 +184,7 @@ __global__ void __launch_bounds__(kHypPerBlock) emat_hyp_kernel(
           float d2 = thr2;
           bool ok = false;
           if (i < N) {
-            d2 = sampson_sq_f(E, s_pts[i]);
+            d2 = sampson_sq_f(E, __ldg(s_pts + i));
             ok = d2 < thr2;
             cost += fminf(d2, thr2);
           }
@@ -189,20 +204,20 @@ __global__ void __launch_bounds__(kHypPerBlock) emat_hyp_kernel(
       }
     }
   }
+  // block winner = the warp with the lowest cost (first one on ties); that warp writes the record itself
+  if (lane == 0) s_cost[warp] = best_src >= 0 ? static_cast<double>(best_cost) : 1e300;
+  __syncthreads();
+  int bw = 0;
+  for (int w = 1; w < static_cast<int>(blockDim.x) / 32; ++w)
+    if (s_cost[w] < s_cost[bw]) bw = w;
+  if (warp != bw) return;
   if (lane == 0) {
-    s_best[warp].valid = best_src >= 0 ? 1 : 0;
-    s_best[warp].cost = best_src >= 0 ? static_cast<double>(best_cost) : 1e300;
-    s_best[warp].count = best_cnt;
+    out->valid = best_src >= 0 ? 1 : 0;
+    out->cost = best_src >= 0 ? static_cast<double>(best_cost) : 1e300;
+    out->count = best_cnt;
   }
   if (best_src >= 0 && lane == best_src)
-    for (int k = 0; k < 9; ++k) s_best[warp].model[k] = Ec[best_c][k];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int bw = 0;
-    for (int w = 1; w < static_cast<int>(blockDim.x) / 32; ++w)
-      if (s_best[w].cost < s_best[bw].cost) bw = w;
-    *out = s_best[bw];
-  }
+    for (int k = 0; k < 9; ++k) out->model[k] = Ec[best_c][k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1296,6 +1311,7 @@ struct PoseSolver {
   int max_pairs, max_pts, max_hyp;
   HypResult* results = nullptr;
   void* lo_out = nullptr;   // LoResult[max_pairs][kLoTopK]
+  void* pts_norm = nullptr; // float4[max_pairs][max_pts]: normalised correspondences for the hypothesis kernel
   double *Rd = nullptr, *td = nullptr, *Xw = nullptr, *X1w = nullptr;
   float* uv = nullptr;
   int *vidx = nullptr, *nvalid = nullptr;
@@ -1313,6 +1329,7 @@ int pose_solver_create(int max_pairs, int max_pts, int max_hyp, PoseSolver** out
   bool ok = true;
   ok &= cudaMalloc(&s->results, sizeof(HypResult) * max_pairs * blocks) == cudaSuccess;
   ok &= cudaMalloc(&s->lo_out, sizeof(LoResult) * max_pairs * kLoTopK) == cudaSuccess;
+  ok &= cudaMalloc(&s->pts_norm, sizeof(float4) * static_cast<size_t>(max_pairs) * s->max_pts) == cudaSuccess;
   ok &= cudaMalloc(&s->Rd, sizeof(double) * 9 * max_pairs) == cudaSuccess;
   ok &= cudaMalloc(&s->td, sizeof(double) * 3 * max_pairs) == cudaSuccess;
   ok &= cudaMalloc(&s->Xw, sizeof(double) * 3 * s->total_pts) == cudaSuccess;
@@ -1339,7 +1356,7 @@ int pose_solver_create(int max_pairs, int max_pts, int max_hyp, PoseSolver** out
 
 void pose_solver_destroy(PoseSolver* s) {
   if (!s) return;
-  cudaFree(s->results); cudaFree(s->lo_out); cudaFree(s->Rd); cudaFree(s->td); cudaFree(s->Xw); cudaFree(s->uv);
+  cudaFree(s->results); cudaFree(s->lo_out); cudaFree(s->pts_norm); cudaFree(s->Rd); cudaFree(s->td); cudaFree(s->Xw); cudaFree(s->uv);
   cudaFree(s->vidx); cudaFree(s->nvalid); cudaFree(s->dmin); cudaFree(s->dmin1); cudaFree(s->X1w);
   delete s;
 }
@@ -1353,12 +1370,15 @@ int emat_ransac(PoseSolver* s, const float* kpts0, const float* kpts1, const int
   if (P < 1 || P > s->max_pairs || num_hyp < 1) return MFR_ERR_ARG;
   num_hyp = std::min(num_hyp, s->max_hyp);
   // hypotheses per block: 128 when that already gives >= 2 blocks per SM, else down to one warp per block
+  // (enough pairs: full 128-thread blocks, one per SM beside the matcher's GEMM CTAs — see emat_hyp_kernel)
   int hpb = kHypPerBlock;
-  while (hpb > 32 && static_cast<long long>(P) * ((num_hyp + hpb - 1) / hpb) < 2LL * 148) hpb /= 2;
+  while (hpb > 32 && static_cast<long long>(P) * ((num_hyp + hpb - 1) / hpb) < 148 / 2) hpb /= 2;
   const int blocks = (num_hyp + hpb - 1) / hpb;
   const size_t smem = static_cast<size_t>(s->max_pts) * 16;
-  emat_hyp_kernel<<<dim3(blocks, P), hpb, smem, st>>>(kpts0, kpts1, offsets, K0, K1, pix_thr, num_hyp,
-                                                      seed, s->max_pts, s->results);
+  emat_normalise_kernel<<<dim3((s->max_pts + 255) / 256, P), 256, 0, st>>>(kpts0, kpts1, offsets, K0, K1, s->max_pts,
+                                                                          static_cast<float4*>(s->pts_norm));
+  emat_hyp_kernel<<<dim3(blocks, P), hpb, 0, st>>>(static_cast<const float4*>(s->pts_norm), offsets, K0, K1, pix_thr, num_hyp,
+                                                   seed, s->max_pts, s->results);
   emat_lo_kernel<<<dim3(P, kLoTopK), kLoThreads, smem, st>>>(kpts0, kpts1, offsets, K0, K1, pix_thr, blocks, s->max_pts,
                                                       s->results, static_cast<LoResult*>(s->lo_out), lo_enabled);
   emat_final_kernel<<<P, kLoThreads, smem, st>>>(kpts0, kpts1, offsets, K0, K1, pix_thr, blocks, s->max_pts,
