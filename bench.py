@@ -308,8 +308,8 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 2), "unit": "pairs/s", "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": out_bytes, "ms_per_step": round(ms_e2e / K, 3),
                     "api": "mfr_b200.pipeline.RelocPipeline.submit_host (copy / matcher / RANSAC stages of consecutive batches overlap)"},
-            "gpu_launches": int((eng.num_launches() + 4) * K),   # + emat_hyp, emat_lo, emat_final, scale_consensus
-            "kernels_per_step": eng.num_launches() + 4,
+            "gpu_launches": int((eng.num_launches() + 5) * K),   # + emat_normalise, emat_hyp, emat_lo, emat_final, scale_consensus
+            "kernels_per_step": eng.num_launches() + 5,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "accuracy": accuracy,
         }
     if world > 1:
