@@ -25,6 +25,16 @@
     }                                                                                \
   } while (0)
 
+// Kernel attributes (dynamic shared-memory opt-in) are per device: true the first time a call site runs on the
+// current device. `seen` is the call site's own static table.
+inline bool first_call_on_device(bool (&seen)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (seen[dev]) return false;
+  seen[dev] = true;
+  return true;
+}
+
 namespace mfr {
 
 // ---------------------------------------------------------------------------------------------

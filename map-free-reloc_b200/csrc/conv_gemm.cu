@@ -1100,11 +1100,10 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
 }
 
 int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_seen[64] = {};
+  if (first_call_on_device(attr_seen)) {
     MFR_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tf32_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
   }
   const int total = p.N * p.tiles_y * p.tiles_x * p.n_tiles;
   if (total <= 0) return MFR_OK;

@@ -1340,15 +1340,13 @@ int pose_solver_create(int max_pairs, int max_pts, int max_hyp, PoseSolver** out
   ok &= cudaMalloc(&s->dmin, sizeof(unsigned int) * max_pairs) == cudaSuccess;
   ok &= cudaMalloc(&s->dmin1, sizeof(unsigned int) * max_pairs) == cudaSuccess;
   if (!ok) { pose_solver_destroy(s); return MFR_ERR_CUDA; }
-  static bool attrs = false;
-  if (!attrs) {
-    cudaFuncSetAttribute(emat_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
+  static bool attr_seen[64] = {};
+  if (first_call_on_device(attr_seen)) {
     cudaFuncSetAttribute(emat_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
     cudaFuncSetAttribute(emat_lo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
     cudaFuncSetAttribute(scale_consensus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
     cudaFuncSetAttribute(pnp_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 20);
     cudaFuncSetAttribute(procrustes_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 24);
-    attrs = true;
   }
   *out = s;
   return MFR_OK;

@@ -1634,15 +1634,14 @@ int linear_attention_long(const void* Q, long long ldq, const void* K, long long
   constexpr int kKvSmem = 2 * kAttStages * kSlab * 256 * 4, kApSmem = kAttStages * kSlab * 256 * 4;
   constexpr int kWide = kSlab * 256 * 4;   // bf16 variants: one fp32 slab the K / Q rows are widened into
   constexpr int kKvSmemBf = kKvSmem / 2 + kWide, kApSmemBf = kApSmem / 2 + kWide;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_seen[64] = {};
+  if (first_call_on_device(attr_seen)) {
     MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem));
     MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmem));
     MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmemBf));
     MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmemBf));
     MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMStages * kMSlabBytes));
     MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMStages * kMSlabBytes));
-    attr_set = true;
   }
   const int asplits = std::max(1, std::min((L + kSlab - 1) / kSlab, (4 * 148 + n - 1) / n));
   if (bf16) {
@@ -1715,11 +1714,10 @@ int coarse_match(const float* S, CoarseMatchBuffers f, int B, int L, int h_c, in
   const bool raw = input_is_conf;
   const bool fused = (L % 4 == 0) && L <= kCmThreads * 4 * kF4 && (reinterpret_cast<uintptr_t>(S) & 15) == 0;
   if (fused) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_seen[64] = {};
+    if (first_call_on_device(attr_seen)) {
       MFR_CUDA_CHECK(cudaFuncSetAttribute(stats_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCmStageBytes));
       MFR_CUDA_CHECK(cudaFuncSetAttribute(conf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCmStageBytes));
-      attr_set = true;
     }
     // a block owns ceil(L / splits) rows (rounded to the row batch) and all columns
     const int rpb = ((L + splits - 1) / splits + 3) / 4 * 4;

@@ -748,11 +748,9 @@ int sp_nms(const float* scores, float* mask, float* t0, float* t1, float* t2, fl
 }
 int sp_select_keypoints(const float* scores, const float* mask, int N, int H, int W, float thr, int border,
                         int max_kp, float* kpts, float* kscores, int* counts, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static bool attr_seen[64] = {};
+  if (first_call_on_device(attr_seen))
     cudaFuncSetAttribute(select_keypoints_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxCand * 8);
-    attr = true;
-  }
   select_keypoints_kernel<<<N, 1024, kMaxCand * 8, st>>>(scores, mask, H, W, thr, border, max_kp, kpts, kscores, counts);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
