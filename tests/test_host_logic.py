@@ -96,3 +96,30 @@ def test_model_rejects_unknown_plugins():
     cfg.MODEL = "Regression"
     with pytest.raises(NotImplementedError):
         model.build_model(cfg)
+
+
+def test_linear_attention_stage_reference_matches_oracle():
+    """The fp64 restatement the GPU stage test (tests/test_loftr_gpu.py::test_linear_attention_stage) checks the kernels
+    against is the oracle's LinearAttention (linear_attention.py:31-45) with the feature map applied outside and the
+    v / S ... * S pair cancelled."""
+    import torch
+    from oracle import loftr_oracle as lo
+    from test_loftr_gpu import _lin_att_ref
+    g = torch.Generator().manual_seed(5)
+    n, L, S, H, D = 2, 37, 53, 8, 32
+    q = torch.randn(n, L, H * D, generator=g); k = torch.randn(n, S, H * D, generator=g); v = torch.randn(n, S, H * D, generator=g)
+    want = lo.linear_attention(q.view(n, L, H, D), k.view(n, S, H, D), v.view(n, S, H, D)).reshape(n, L, H * D)
+    got = _lin_att_ref(torch.nn.functional.elu(q) + 1, torch.nn.functional.elu(k) + 1, v, H)
+    assert torch.allclose(got.float(), want, rtol=1e-4, atol=1e-5)
+
+
+def test_launch_summary_of_committed_profile():
+    """profiles/ tooling: the committed launch list of one bench step summarises to the table quoted in profiles/README.md."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "summarize_launches.py"),
+                          os.path.join(root, "profiles", "r01_launches_bf16_B16.csv")], capture_output=True, text=True, check=True).stdout
+    first = out.splitlines()[0]
+    assert first.startswith("186 launches"), first
+    conv = next(l for l in out.splitlines() if l.startswith("conv_gemm_tf32_kernel"))
+    assert int(conv.split("x")[1].split()[0]) == 94
