@@ -71,11 +71,21 @@ typedef struct {
   int capacity;
 } mfr_loftr_outputs;
 
-/* precision: 0 = fp32 storage, TF32 tensor-core inputs everywhere (parity mode; what torch+cuDNN do
- * by default for the convs); 1 = bf16 storage and bf16 tensor-core inputs in the ResNet-FPN backbone
- * (fp32 accumulate, fp32 feature maps out), everything after the backbone as in mode 0. */
+/* precision:
+ *  0 TF32   fp32 storage everywhere, TF32 tensor-core inputs in every conv / linear / correlation GEMM (what
+ *           torch + cuDNN do by default for the reference's convs on a GPU); attention, LayerNorm, softmax fp32.
+ *  1 BF16   throughput mode. bf16 storage + kind::f16 MMAs (fp32 accumulate) for the ResNet-FPN maps, the token
+ *           GEMM operands (q|k|v, mlp0 read a bf16 shadow of the token stream; q|k|v, attention message and MLP
+ *           hidden tensors are stored in bf16), the linear attention and the coarse correlation operands. The two
+ *           backbone outputs, the token residual stream, LayerNorm arithmetic, the similarity matrix S, dual
+ *           softmax and fine matching stay fp32.
+ *  2 FP32X3 fp32-faithful parity mode. fp32 storage; every GEMM (convs, linears, correlation) runs as a 3xTF32
+ *           split product  A.B ~= Ahi.Bhi + Alo.Bhi + Ahi.Blo  (one tensor-core GEMM over 3x the K extent,
+ *           ~2^-21 relative per product instead of TF32's 2^-11); stem, attention, LayerNorm in plain fp32. This
+ *           is the mode whose match indices are compared with the reference's fp32 arithmetic. */
 #define MFR_PRECISION_TF32 0
 #define MFR_PRECISION_BF16 1
+#define MFR_PRECISION_FP32X3 2
 int mfr_loftr_create(int B, int H, int W, float thr, int border_rm, float temperature, int precision,
                      mfr_loftr** out);
 void mfr_loftr_destroy(mfr_loftr* h);
@@ -119,6 +129,11 @@ typedef struct {
 } mfr_spsg_outputs;
 int mfr_spsg_create(int B, int H, int W, int max_keypoints, int nms_radius, float keypoint_threshold,
                     int remove_borders, int sinkhorn_iterations, float match_threshold, mfr_spsg** out);
+/* same with the GEMM precision: MFR_PRECISION_TF32 (what mfr_spsg_create uses) or MFR_PRECISION_FP32X3 (every conv /
+ * linear / attention / score GEMM as a 3xTF32 split product: the fp32-faithful parity mode) */
+int mfr_spsg_create_ex(int B, int H, int W, int max_keypoints, int nms_radius, float keypoint_threshold,
+                       int remove_borders, int sinkhorn_iterations, float match_threshold, int precision,
+                       mfr_spsg** out);
 void mfr_spsg_destroy(mfr_spsg* h);
 int mfr_spsg_num_weights(const mfr_spsg* h);
 const char* mfr_spsg_weight_name(const mfr_spsg* h, int i);
@@ -170,9 +185,14 @@ int mfr_pose_solver_create(int max_pairs, int max_pts_per_pair, int max_hypothes
 void mfr_pose_solver_destroy(mfr_pose_solver* s);
 
 /* EssentialMatrixSolver.estimate_pose (pose_solver.py:29-61): cv.findEssentialMat(USAC_MAGSAC) +
- * cv.recoverPose. `num_hyp` 5-point hypotheses per pair (MSAC-scored), then local optimisation
- * (LM on the Sampson error over the inliers) when lo_enabled != 0. t has unit norm. The final
- * (R, t) is also kept in fp64 inside the handle for mfr_scale_from_depth. */
+ * cv.recoverPose. `num_hyp` 5-point hypotheses per pair (MSAC-scored). lo_enabled is a bit set:
+ *   bit 0 (1): local optimisation of the 4 best block winners (LM on a Tukey M-estimator of the Sampson distance,
+ *              cut-off 3x -> 1x the threshold) + noise-adaptive tightening;
+ *   bit 1 (2): final truncated least-squares refit at the threshold (LM on the MSAC cost): the result is the Sampson
+ *              least-squares optimum of its OWN inlier set — the point the reference's output polished by LM on its
+ *              own mask sits at (SURVEY §7 hard part 1(b)); needs bit 0.
+ * t has unit norm; max_pts_per_pair <= 8192 (more correspondences of a pair are ignored). The final (R, t) is also
+ * kept in fp64 inside the handle for mfr_scale_from_depth. */
 int mfr_emat_ransac(mfr_pose_solver* s, const float* kpts0, const float* kpts1, const int* offsets,
                     int P, const float* K0, const float* K1, float pix_threshold, int num_hyp,
                     unsigned long long seed, int lo_enabled, float* R, float* t, int* n_inliers,

@@ -51,7 +51,7 @@ def build(force=False, verbose=True):
             sys.stderr.write(out)
         elif verbose:
             for line in out.splitlines():
-                if "registers" in line or "spill" in line and "0 bytes spill" not in line:
+                if "registers" in line or ("spill" in line and "0 bytes spill" not in line):
                     print(os.path.basename(src), line.strip())
     if not ok:
         raise RuntimeError("nvcc failed")

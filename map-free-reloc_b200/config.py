@@ -5,8 +5,8 @@ this is a small attribute-dict with the same keys, the same layered ``merge_from
 pre-declared keys may be set. The reference's yaml files load unchanged.
 
 Additive keys (not in the reference): FEATURE_MATCHING may also be 'LoFTR' (fused on-GPU matcher),
-LOFTR.{WEIGHTS, THR, BORDER_RM, TEMPERATURE, BATCH}, GPU_RANSAC.{NUM_HYPOTHESES, SEED,
-LOCAL_OPTIMISATION}.
+LOFTR.{WEIGHTS, THR, BORDER_RM, TEMPERATURE, BATCH}, GPU_RANSAC.{NUM_HYPOTHESES, MAX_HYPOTHESES, SEED,
+LOCAL_OPTIMISATION, FINAL_REFIT}.
 """
 import copy
 
@@ -81,7 +81,10 @@ def get_default_cfg():
         "BACKPROJECT_ANCHORS": None,
         # additive
         "LOFTR": {"WEIGHTS": None, "THR": 0.2, "BORDER_RM": 2, "TEMPERATURE": 0.1, "BATCH": 1},
-        "GPU_RANSAC": {"NUM_HYPOTHESES": 2048, "SEED": 0x5EED, "LOCAL_OPTIMISATION": True},
+        # NUM_HYPOTHESES None = the solver's default (E-mat 2048; PnP: PNP.RANSAC_ITER rounded up to 128);
+        # MAX_HYPOTHESES bounds the CONFIDENCE-driven escalation (pose_solver._SolverBase)
+        "GPU_RANSAC": {"NUM_HYPOTHESES": None, "MAX_HYPOTHESES": 32768, "SEED": 0x5EED, "LOCAL_OPTIMISATION": True,
+                       "FINAL_REFIT": "lsq"},
     })
 
 

@@ -98,15 +98,21 @@ int mfr_loftr_profile(mfr_loftr* h, const float* img0, const float* img1, int sr
 
 // ------------------------------------------------------------------------------------------ SuperPoint + SuperGlue
 struct mfr_spsg { mfr::SpsgEngine* e; };
-int mfr_spsg_create(int B, int H, int W, int max_keypoints, int nms_radius, float keypoint_threshold,
-                    int remove_borders, int sinkhorn_iterations, float match_threshold, mfr_spsg** out) {
+int mfr_spsg_create_ex(int B, int H, int W, int max_keypoints, int nms_radius, float keypoint_threshold,
+                       int remove_borders, int sinkhorn_iterations, float match_threshold, int precision,
+                       mfr_spsg** out) {
   if (!out) return MFR_ERR_ARG;
   mfr::SpsgEngine* e = nullptr;
   int rc = mfr::spsg_create(B, H, W, max_keypoints, nms_radius, keypoint_threshold, remove_borders,
-                            sinkhorn_iterations, match_threshold, &e);
+                            sinkhorn_iterations, match_threshold, precision, &e);
   if (rc != MFR_OK) return rc;
   *out = new mfr_spsg{e};
   return MFR_OK;
+}
+int mfr_spsg_create(int B, int H, int W, int max_keypoints, int nms_radius, float keypoint_threshold,
+                    int remove_borders, int sinkhorn_iterations, float match_threshold, mfr_spsg** out) {
+  return mfr_spsg_create_ex(B, H, W, max_keypoints, nms_radius, keypoint_threshold, remove_borders,
+                            sinkhorn_iterations, match_threshold, MFR_PRECISION_TF32, out);
 }
 void mfr_spsg_destroy(mfr_spsg* h) { if (h) { mfr::spsg_destroy(h->e); delete h; } }
 int mfr_spsg_num_weights(const mfr_spsg* h) { return mfr::spsg_num_weights(h->e); }

@@ -333,10 +333,13 @@ struct LoResult {
 
 // LM rounds on the Tukey-biweight M-estimator of the Sampson distance with cut-off sqrt(T2),
 // starting from (S.R, S.t); leaves the last accepted parameters there. All threads must call it.
-__device__ void emat_lm_round(EmatShared& S, const float4* pts, int N, double T2, int step = 1) {
+// hard = true: truncated least squares instead (weight 1 inside the cut-off, cost sum min(r^2, T2) / T2 = the MSAC cost):
+// its fixed point is the least-squares optimum of the model's own inlier set.
+__device__ void emat_lm_round(EmatShared& S, const float4* pts, int N, double T2, int step = 1, bool hard = false,
+                              int max_it = kLoInner) {
   if (threadIdx.x == 0) { S.lambda = 1e-6; S.prev_cost = 1e300; S.done = 0; }
   __syncthreads();
-  for (int it = 0; it <= kLoInner; ++it) {
+  for (int it = 0; it <= max_it; ++it) {
     if (S.done) break;   // converged: the accepted parameters are already in (prevR, prevt)
     double R[9], t[3], b1[3], b2[3];
     for (int k = 0; k < 9; ++k) R[k] = S.R[k];
@@ -349,12 +352,12 @@ __device__ void emat_lm_round(EmatShared& S, const float4* pts, int N, double T2
       const double r = sampson_res_jac(R, t, b1, b2, pts[i], J);
       const double q = r * r / T2;
       if (q < 1.0) {
-        const double u = 1.0 - q, w = u * u;
+        const double u = 1.0 - q, w = hard ? 1.0 : u * u;
         int qq = 0;
         for (int a = 0; a < 5; ++a)
           for (int b = a; b < 5; ++b) acc[qq++] += w * J[a] * J[b];
         for (int a = 0; a < 5; ++a) acc[15 + a] += w * J[a] * r;
-        acc[20] += (1.0 - u * u * u);
+        acc[20] += hard ? q : (1.0 - u * u * u);
       } else {
         acc[20] += 1.0;
       }
@@ -377,7 +380,7 @@ __device__ void emat_lm_round(EmatShared& S, const float4* pts, int N, double T2
       }
       double d[5], pb1[3], pb2[3];
       tangent_basis(S.prevt, pb1, pb2);
-      if (it < kLoInner && solve_damped(S.H, S.g, S.lambda, 5, d)) {
+      if (it < max_it && solve_damped(S.H, S.g, S.lambda, 5, d)) {
         double dR[9], Rn[9], tn[3];
         so3_exp(d, dR);
         mat3_mul(dR, S.prevR, Rn);
@@ -596,6 +599,12 @@ __global__ void __launch_bounds__(kLoThreads) emat_final_kernel(
       for (int k = 0; k < 3; ++k) S.t[k] = S.bestt[k];
     }
     __syncthreads();
+    if (lo_enabled & 2) {
+      // reference-equivalent refit (SURVEY §7 hard part 1(b)): truncated least squares at the RANSAC threshold, i.e. LM
+      // on the MSAC cost, whose fixed point is the Sampson least-squares optimum of the model's OWN inlier set — the
+      // point the "polished oracle" (OpenCV's mask -> Sampson LM, oracle/pose_solver_oracle.py) sits at.
+      for (int round = 0; round < 2; ++round) emat_lm_round(S, s_pts, N, thr2, 1, true, 8);
+    }
   }
   if (threadIdx.x == 0) essential_from_rt(S.R, S.t, S.E);
   __syncthreads();
@@ -776,7 +785,7 @@ __global__ void __launch_bounds__(1024) pnp_prepare_kernel(
     }
     __syncthreads();
     if (flag) {
-      const int slot = n0 + base + (wid > 0 ? wsum[wid - 1] : 0) + inc - 1;
+      const int slot = pair * max_pts + base + (wid > 0 ? wsum[wid - 1] : 0) + inc - 1;
       double X[3];
       backproject(s_Ki, u, v, z, X);
       Xw[3 * slot] = X[0]; Xw[3 * slot + 1] = X[1]; Xw[3 * slot + 2] = X[2];
@@ -796,11 +805,11 @@ struct PnpPt { float X, Y, Z, u, v; };
 __global__ void __launch_bounds__(kHypPerBlock) pnp_hyp_kernel(
     const double* __restrict__ Xw, const float* __restrict__ uv, const int* __restrict__ offsets,
     const int* __restrict__ nvalid, const float* __restrict__ K1s, float reproj_thr, int num_hyp,
-    unsigned long long seed, HypResult* __restrict__ results) {
+    unsigned long long seed, int max_pts, HypResult* __restrict__ results) {
   extern __shared__ float s_raw[];
   __shared__ HypResult s_best[kHypPerBlock / 32];
   const int pair = blockIdx.y;
-  const int n0 = offsets[pair];
+  const int s0 = pair * max_pts;   // scratch rows of this pair (compacted, at most max_pts)
   const int N = nvalid[pair];
   HypResult* out = results + static_cast<size_t>(pair) * gridDim.x + blockIdx.x;
   if (N < 4) {
@@ -810,11 +819,11 @@ __global__ void __launch_bounds__(kHypPerBlock) pnp_hyp_kernel(
   float* sX = s_raw;            // [N][3]
   float* sU = s_raw + 3 * N;    // [N][2]
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    sX[3 * i] = static_cast<float>(Xw[3 * (n0 + i)]);
-    sX[3 * i + 1] = static_cast<float>(Xw[3 * (n0 + i) + 1]);
-    sX[3 * i + 2] = static_cast<float>(Xw[3 * (n0 + i) + 2]);
-    sU[2 * i] = uv[2 * (n0 + i)];
-    sU[2 * i + 1] = uv[2 * (n0 + i) + 1];
+    sX[3 * i] = static_cast<float>(Xw[3 * (s0 + i)]);
+    sX[3 * i + 1] = static_cast<float>(Xw[3 * (s0 + i) + 1]);
+    sX[3 * i + 2] = static_cast<float>(Xw[3 * (s0 + i) + 2]);
+    sU[2 * i] = uv[2 * (s0 + i)];
+    sU[2 * i + 1] = uv[2 * (s0 + i) + 1];
   }
   __syncthreads();
   const float* K1 = K1s + 9 * pair;
@@ -831,9 +840,9 @@ __global__ void __launch_bounds__(kHypPerBlock) pnp_hyp_kernel(
     sample_distinct<4>(st, N, idx);
     double X[3][3], f[3][3];
     for (int k = 0; k < 3; ++k) {
-      for (int c = 0; c < 3; ++c) X[k][c] = Xw[3 * (n0 + idx[k]) + c];
-      const double bx = (static_cast<double>(uv[2 * (n0 + idx[k])]) - cx) / fx;
-      const double by = (static_cast<double>(uv[2 * (n0 + idx[k]) + 1]) - cy) / fy;
+      for (int c = 0; c < 3; ++c) X[k][c] = Xw[3 * (s0 + idx[k]) + c];
+      const double bx = (static_cast<double>(uv[2 * (s0 + idx[k])]) - cx) / fx;
+      const double by = (static_cast<double>(uv[2 * (s0 + idx[k]) + 1]) - cy) / fy;
       const double nn = 1.0 / sqrt(bx * bx + by * by + 1.0);
       f[k][0] = bx * nn; f[k][1] = by * nn; f[k][2] = nn;
     }
@@ -841,8 +850,8 @@ __global__ void __launch_bounds__(kHypPerBlock) pnp_hyp_kernel(
     const int ns = p3p(X, f, Rs, ts);
     // disambiguate with the 4th point (what cv's P3P does with 4 input points)
     double best = 1e300;
-    const double X4[3] = {Xw[3 * (n0 + idx[3])], Xw[3 * (n0 + idx[3]) + 1], Xw[3 * (n0 + idx[3]) + 2]};
-    const double u4 = uv[2 * (n0 + idx[3])], v4 = uv[2 * (n0 + idx[3]) + 1];
+    const double X4[3] = {Xw[3 * (s0 + idx[3])], Xw[3 * (s0 + idx[3]) + 1], Xw[3 * (s0 + idx[3]) + 2]};
+    const double u4 = uv[2 * (s0 + idx[3])], v4 = uv[2 * (s0 + idx[3]) + 1];
     for (int s = 0; s < ns; ++s) {
       double Xc[3];
       mat3_vec(Rs[s], X4, Xc);
@@ -908,7 +917,7 @@ constexpr int kPnpIters = 20;
 __global__ void __launch_bounds__(256) pnp_final_kernel(
     const double* __restrict__ Xw, const float* __restrict__ uv, const int* __restrict__ vidx,
     const int* __restrict__ offsets, const int* __restrict__ nvalid, const float* __restrict__ K1s,
-    float reproj_thr, int blocks_per_pair, const HypResult* __restrict__ results, float* __restrict__ Rf,
+    float reproj_thr, int blocks_per_pair, int max_pts, const HypResult* __restrict__ results, float* __restrict__ Rf,
     float* __restrict__ tf, int* __restrict__ n_inl, unsigned char* __restrict__ mask) {
   __shared__ double sh_red[8 * 28];
   __shared__ double s_R[9], s_t[3], s_R0[9], s_t0[3], s_prevR[9], s_prevt[3], s_H[36], s_g[6];
@@ -917,6 +926,7 @@ __global__ void __launch_bounds__(256) pnp_final_kernel(
   const int pair = blockIdx.x;
   const int n0 = offsets[pair];
   const int Nall = offsets[pair + 1] - n0;
+  const int s0 = pair * max_pts;
   const int N = nvalid[pair];
   for (int i = threadIdx.x; i < Nall; i += blockDim.x) mask[n0 + i] = 0;
   auto fail = [&]() {
@@ -945,17 +955,17 @@ __global__ void __launch_bounds__(256) pnp_final_kernel(
   __syncthreads();
   // inlier set of the RANSAC model (fixed during the refinement, like cv.solvePnPRansac's)
   auto is_inlier = [&](int i) {
-    const double* X = Xw + 3 * (n0 + i);
+    const double* X = Xw + 3 * (s0 + i);
     double Xc[3];
     mat3_vec(s_R0, X, Xc);
     for (int c = 0; c < 3; ++c) Xc[c] += s_t0[c];
     if (!(Xc[2] > 1e-9)) return false;
-    const double du = fx * Xc[0] / Xc[2] + cx - uv[2 * (n0 + i)], dv = fy * Xc[1] / Xc[2] + cy - uv[2 * (n0 + i) + 1];
+    const double du = fx * Xc[0] / Xc[2] + cx - uv[2 * (s0 + i)], dv = fy * Xc[1] / Xc[2] + cy - uv[2 * (s0 + i) + 1];
     return du * du + dv * dv < thr2;
   };
   double cnt[1] = {0.0};
   for (int i = threadIdx.x; i < N; i += blockDim.x)
-    if (is_inlier(i)) { cnt[0] += 1.0; mask[n0 + vidx[n0 + i]] = 1; }
+    if (is_inlier(i)) { cnt[0] += 1.0; mask[n0 + vidx[s0 + i]] = 1; }
   block_sum_256<1>(cnt, sh_red);
   if (threadIdx.x == 0) { s_n = static_cast<int>(cnt[0] + 0.5); s_lambda = 1e-6; s_prev_cost = 1e300; }
   __syncthreads();
@@ -970,13 +980,13 @@ __global__ void __launch_bounds__(256) pnp_final_kernel(
       for (int k = 0; k < 28; ++k) acc[k] = 0.0;
       for (int i = threadIdx.x; i < N; i += blockDim.x) {
         if (!is_inlier(i)) continue;
-        const double* X = Xw + 3 * (n0 + i);
+        const double* X = Xw + 3 * (s0 + i);
         double RX[3], Xc[3];
         mat3_vec(R, X, RX);
         for (int c = 0; c < 3; ++c) Xc[c] = RX[c] + t[c];
         const double iz = 1.0 / Xc[2];
-        const double ru = fx * Xc[0] * iz + cx - uv[2 * (n0 + i)];
-        const double rv = fy * Xc[1] * iz + cy - uv[2 * (n0 + i) + 1];
+        const double ru = fx * Xc[0] * iz + cx - uv[2 * (s0 + i)];
+        const double rv = fy * Xc[1] * iz + cy - uv[2 * (s0 + i) + 1];
         // d(u,v)/dXc
         const double a0 = fx * iz, a2 = -fx * Xc[0] * iz * iz, b1 = fy * iz, b2 = -fy * Xc[1] * iz * iz;
         // dXc/d(omega) = -[RX]x ; dXc/dt = I
@@ -1133,7 +1143,7 @@ __global__ void __launch_bounds__(1024) procrustes_prepare_kernel(
     }
     __syncthreads();
     if (flag) {
-      const int slot = n0 + base + (wid > 0 ? wsum[wid - 1] : 0) + inc - 1;
+      const int slot = pair * max_pts + base + (wid > 0 ? wsum[wid - 1] : 0) + inc - 1;
       double A[3], Bq[3];
       backproject(s_Ki0, u0, v0, z0, A);
       backproject(s_Ki1, u1, v1, z1, Bq);
@@ -1148,12 +1158,12 @@ __global__ void __launch_bounds__(1024) procrustes_prepare_kernel(
 
 __global__ void __launch_bounds__(kHypPerBlock) procrustes_hyp_kernel(
     const double* __restrict__ X0, const double* __restrict__ X1, const int* __restrict__ offsets,
-    const int* __restrict__ nvalid, float max_dist, int num_hyp, unsigned long long seed,
+    const int* __restrict__ nvalid, float max_dist, int num_hyp, unsigned long long seed, int max_pts,
     HypResult* __restrict__ results) {
   extern __shared__ float s_raw[];
   __shared__ HypResult s_best[kHypPerBlock / 32];
   const int pair = blockIdx.y;
-  const int n0 = offsets[pair];
+  const size_t n0 = static_cast<size_t>(pair) * max_pts;   // scratch rows of this pair
   const int N = nvalid[pair];
   HypResult* out = results + static_cast<size_t>(pair) * gridDim.x + blockIdx.x;
   if (N < 3) {
@@ -1236,13 +1246,13 @@ __global__ void __launch_bounds__(kHypPerBlock) procrustes_hyp_kernel(
 
 __global__ void __launch_bounds__(256) procrustes_final_kernel(
     const double* __restrict__ X0, const double* __restrict__ X1, const int* __restrict__ offsets,
-    const int* __restrict__ nvalid, float max_dist, int blocks_per_pair, const HypResult* __restrict__ results,
+    const int* __restrict__ nvalid, float max_dist, int blocks_per_pair, int max_pts, const HypResult* __restrict__ results,
     float* __restrict__ Rf, float* __restrict__ tf, int* __restrict__ n_inl) {
   __shared__ double sh_red[8 * 16];
   __shared__ double s_R[9], s_t[3];
   __shared__ int s_flag, s_cnt;
   const int pair = blockIdx.x;
-  const int n0 = offsets[pair];
+  const size_t n0 = static_cast<size_t>(pair) * max_pts;   // scratch rows of this pair
   const int N = nvalid[pair];
   auto fail = [&]() {
     if (threadIdx.x < 9) Rf[9 * pair + threadIdx.x] = NAN;
@@ -1320,8 +1330,8 @@ struct PoseSolver {
 };
 
 int pose_solver_create(int max_pairs, int max_pts, int max_hyp, PoseSolver** out) {
-  if (max_pairs < 1 || max_pts < 8 || max_hyp < kHypPerBlock) return MFR_ERR_ARG;
-  if (max_pts > 8192) max_pts = 8192;  // correspondences live in shared memory (16 B each)
+  // correspondences of a pair live in shared memory in the LO / final / consensus kernels (16 B each): 8192 is the hard limit
+  if (max_pairs < 1 || max_pts < 8 || max_pts > 8192 || max_hyp < kHypPerBlock) return MFR_ERR_ARG;
   auto* s = new PoseSolver();
   s->max_pairs = max_pairs; s->max_pts = max_pts; s->max_hyp = max_hyp;
   s->total_pts = static_cast<size_t>(max_pairs) * max_pts;
@@ -1412,9 +1422,9 @@ int pnp_ransac(PoseSolver* s, const float* kpts0, const float* kpts1, const int*
   pnp_prepare_kernel<<<P, 1024, 0, st>>>(kpts0, kpts1, offsets, K0, depth0, H, W, s->dmin, s->max_pts, s->Xw,
                                          s->uv, s->vidx, s->nvalid);
   pnp_hyp_kernel<<<dim3(blocks, P), kHypPerBlock, static_cast<size_t>(s->max_pts) * 20, st>>>(
-      s->Xw, s->uv, offsets, s->nvalid, K1, reproj_thr, num_hyp, seed, s->results);
+      s->Xw, s->uv, offsets, s->nvalid, K1, reproj_thr, num_hyp, seed, s->max_pts, s->results);
   pnp_final_kernel<<<P, 256, 0, st>>>(s->Xw, s->uv, s->vidx, offsets, s->nvalid, K1, reproj_thr, blocks,
-                                      s->results, R, t, n_inl, mask);
+                                      s->max_pts, s->results, R, t, n_inl, mask);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }
@@ -1433,8 +1443,8 @@ int procrustes_ransac(PoseSolver* s, const float* kpts0, const float* kpts1, con
   procrustes_prepare_kernel<<<P, 1024, 0, st>>>(kpts0, kpts1, offsets, K0, K1, depth0, depth1, H, W, s->dmin,
                                                 s->dmin1, s->max_pts, s->Xw, s->X1w, s->nvalid);
   procrustes_hyp_kernel<<<dim3(blocks, P), kHypPerBlock, static_cast<size_t>(s->max_pts) * 24, st>>>(
-      s->Xw, s->X1w, offsets, s->nvalid, max_corr_dist, num_hyp, seed, s->results);
-  procrustes_final_kernel<<<P, 256, 0, st>>>(s->Xw, s->X1w, offsets, s->nvalid, max_corr_dist, blocks, s->results, R,
+      s->Xw, s->X1w, offsets, s->nvalid, max_corr_dist, num_hyp, seed, s->max_pts, s->results);
+  procrustes_final_kernel<<<P, 256, 0, st>>>(s->Xw, s->X1w, offsets, s->nvalid, max_corr_dist, blocks, s->max_pts, s->results, R,
                                              t, n_inl);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;

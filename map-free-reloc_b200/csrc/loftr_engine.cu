@@ -50,6 +50,9 @@ struct LoftrEngine {
   struct Bf16Conv { std::string name; int cout, taps, cin, cin_pad; size_t off; };
   std::vector<Bf16Conv> bf16_convs;
   unsigned short* wblob16 = nullptr;
+  float* wblob3 = nullptr;     // precision 2: [hi | hi | lo] split of every GEMM weight (3 * Cin per row)
+  float* x3 = nullptr;         // precision 2: scratch for the [hi | lo | hi] split of a GEMM's activations
+  size_t x3_cap = 0;
   size_t w16_total = 0;
   bool w16_ready = false;
 
@@ -58,6 +61,8 @@ struct LoftrEngine {
   float* wblob = nullptr;
   size_t wtotal = 0;
   bool weights_loaded = false;
+  std::vector<char> weight_set;   // per weight tensor: uploaded at least once
+  int last_src_h = -1, last_src_w = -1;
 
   std::vector<void*> allocs;
   std::map<std::string, DebugTensor> dbg;
@@ -122,7 +127,31 @@ struct LoftrEngine {
             const float* bias_override = nullptr, int in_bf16 = 0, int out_bf16 = 0, int w_rows_total = 0,
             int w_row_off = 0) {
     ConvGemmDesc d{};
-    d.x = x; d.N = N; d.H = Hh; d.W = Ww; d.Cin = Cin; d.ldx = ldx;
+    int cin_gemm = Cin;                       // K of the GEMM per tap (3 * Cin in the 3xTF32 mode)
+    if (precision == 2 && !in_bf16) {
+      // fp32-faithful mode: A = [hi | lo | hi] of the activations (split into the scratch x3 right before the GEMM),
+      // B = [hi | hi | lo] of the weights (wblob3, built once per weight upload) -> one TF32 GEMM over 3 * Cin
+      const long long rows_img = static_cast<long long>(Hh) * Ww;
+      if (static_cast<size_t>(N) * rows_img * 3 * Cin > x3_cap) {
+        fprintf(stderr, "[mfr_b200] split scratch too small for %s\n", wname.c_str());
+        build_rc = MFR_ERR_ARG;
+        return;
+      }
+      float* x3_ = x3; const float* xs = x; const int N_ = N, C_ = Cin; const long long ldx_ = ldx;
+      push("split3", [=](cudaStream_t st) { return rows_split3(xs, ldx_, rows_img * ldx_, x3_, rows_img, N_, C_, 0, dyn_w, st); });
+      size_t off = w16_total;
+      bool found = false;
+      for (const auto& e : bf16_convs)
+        if (e.name == wname) { off = e.off; found = true; }
+      if (!found) {
+        const int rows_total = w_rows_total > 0 ? w_rows_total : Cout;
+        bf16_convs.push_back(Bf16Conv{wname, rows_total, R * R, Cin, 3 * Cin, off});
+        w16_total += (static_cast<size_t>(rows_total) * R * R * 3 * Cin + 63) / 64 * 64;
+      }
+      w_override = wblob3 + off + static_cast<size_t>(w_row_off) * R * R * 3 * Cin;
+      x = x3; ldx = 3 * Cin; cin_gemm = 3 * Cin;
+    }
+    d.x = x; d.N = N; d.H = Hh; d.W = Ww; d.Cin = cin_gemm; d.ldx = ldx;
     d.in_bf16 = in_bf16; d.out_bf16 = out_bf16;
     if (in_bf16) {   // bf16 copy of the weights, Cin padded to a multiple of 8 (16-byte TMA strides)
       const int cin_pad = (Cin + 7) / 8 * 8;
@@ -310,6 +339,12 @@ struct LoftrEngine {
     // the bf16 weight blob must exist before the conv steps are built (its size is known only afterwards:
     // reserve the upper bound = all backbone conv weights)
     if (bf) wblob16 = alloc<unsigned short>(kW16Capacity, "weights_bf16");
+    if (precision == 2) {
+      wblob3 = alloc<float>(wtotal * 3 + 64 * specs.size(), "weights_split3");
+      const size_t frows_ = static_cast<size_t>(2) * Mcap * 25;
+      x3_cap = 3 * std::max(std::max(px2 * 196, px4 * 256), std::max(px8 * 512, frows_ * 256));
+      x3 = alloc<float>(x3_cap, "split3_scratch");
+    }
     a0 = balloc(px2 * 128, "a0"); a1 = balloc(px2 * 128, "a1"); a2 = balloc(px2 * 128, "a2");
     b0 = balloc(px4 * c196, "b0"); b1 = balloc(px4 * c196, "b1"); b2 = balloc(px4 * c196, "b2");
     c0 = balloc(px8 * 256, "c0"); c1 = balloc(px8 * 256, "c1"); c2 = balloc(px8 * 256, "c2");
@@ -352,8 +387,8 @@ struct LoftrEngine {
     const int B16 = bf ? 1 : 0;
     {
       float *img_ = img, *a0_ = a0; float* ws = W_("stem.w"); float* bs = W_("stem.b");
-      const int NI_ = NI, H_ = H, W_w = W, ob = B16;
-      push("stem", [=](cudaStream_t st) { return stem_conv7x7(img_, ws, bs, a0_, NI_, H_, W_w, st, ob); });
+      const int NI_ = NI, H_ = H, W_w = W, ob = B16, exact = precision == 2 ? 1 : 0;
+      push("stem", [=](cudaStream_t st) { return stem_conv7x7(img_, ws, bs, a0_, NI_, H_, W_w, st, ob, exact); });
     }
     auto bconv = [&](const std::string& name, const float* x, int Hh, int Ww, int Cin, int ldx, int Cout, int R,
                      int stride, bool bias, const float* res, int act, float* out, int ldo, int out16) {
@@ -420,7 +455,14 @@ struct LoftrEngine {
       d.x = tok; d.N = B; d.H = 1; d.W = L; d.Cin = 256; d.ldx = 512;
       d.w = tok + half_tok; d.Cout = L; d.R = 1; d.S = 1; d.stride = 1; d.pad = 0;
       if (kCorrelationBf16 && precision == 1) { d.x = tokb; d.w = tokb + half_tok / 2; d.in_bf16 = 1; }
-      d.b_batched = 1; d.ldw = 512; d.act = ACT_NONE; d.alpha = 1.f / (256.f * temperature);
+      if (precision == 2) {   // 3xTF32: X -> [hi | lo | hi], Y -> [hi | hi | lo], one GEMM over K = 768
+        const size_t BLr = static_cast<size_t>(B) * L;
+        float *xa = x3, *xb = x3 + BLr * 768; const float *t0 = tok, *t1 = tok + half_tok; const int B_ = B, L_ = L;
+        push("split3", [=](cudaStream_t st) { return rows_split3(t0, 512, static_cast<long long>(L_) * 512, xa, L_, B_, 256, 0, nullptr, st); });
+        push("split3", [=](cudaStream_t st) { return rows_split3(t1, 512, static_cast<long long>(L_) * 512, xb, L_, B_, 256, 1, nullptr, st); });
+        d.x = xa; d.w = xb; d.Cin = 768; d.ldx = 768; d.ldw = 768;
+      }
+      d.b_batched = 1; if (precision != 2) d.ldw = 512; d.act = ACT_NONE; d.alpha = 1.f / (256.f * temperature);
       d.out = S; d.ldo = L; d.ldr = L;
       ConvGemmParams p;
       int rc = conv_gemm_build(d, &p);
@@ -476,6 +518,10 @@ struct LoftrEngine {
         return fine_match(f0, f1, 256, cmb.mkpts1_c, cmb.m_total, Mc, scale_f, mk, ex, st);
       });
     }
+    if (precision == 2 && w16_total > wtotal * 3 + 64 * specs.size()) {
+      fprintf(stderr, "[mfr_b200] split weight blob too small\n");
+      return MFR_ERR_ARG;
+    }
     if (bf && w16_total > kW16Capacity) {
       fprintf(stderr, "[mfr_b200] bf16 weight blob too small\n");
       return MFR_ERR_ARG;
@@ -507,7 +553,18 @@ struct LoftrEngine {
       }
       w16_ready = true;
     }
+    if (precision == 2 && !w16_ready) {   // [hi | hi | lo] split of every GEMM weight
+      for (const auto& bc : bf16_convs) {
+        int rc = rows_split3(W_(bc.name + ".w"), bc.cin, 0, wblob3 + bc.off, static_cast<long long>(bc.cout) * bc.taps, 1, bc.cin,
+                             1, nullptr, st);
+        if (rc != MFR_OK) return rc;
+      }
+      w16_ready = true;
+    }
     const size_t half = static_cast<size_t>(B) * H * W;
+    if ((src_h != H || src_w != W) && (src_h != last_src_h || src_w != last_src_w) && last_src_h > 0)
+      MFR_CUDA_CHECK(cudaMemsetAsync(img, 0, 2 * half * 4, st));   // a smaller source than last time: clear the old pixels of the pad
+    last_src_h = src_h; last_src_w = src_w;
     if (src_h == H && src_w == W) {
       MFR_CUDA_CHECK(cudaMemcpyAsync(img, img0, half * 4, cudaMemcpyDeviceToDevice, st));
       MFR_CUDA_CHECK(cudaMemcpyAsync(img + half, img1, half * 4, cudaMemcpyDeviceToDevice, st));
@@ -589,7 +646,7 @@ struct LoftrEngine {
 
 // ---------------------------------------------------------------------------------------------
 int loftr_create(int B, int H, int W, float thr, int border, float temperature, int precision, LoftrEngine** out) {
-  if (B < 1 || H % 8 || W % 8 || H < 32 || W < 32 || precision < 0 || precision > 1) return MFR_ERR_ARG;
+  if (B < 1 || H % 8 || W % 8 || H < 32 || W < 32 || precision < 0 || precision > 2) return MFR_ERR_ARG;
   auto* e = new LoftrEngine();
   e->B = B; e->H = H; e->W = W; e->thr = thr; e->border = border; e->temperature = temperature;
   e->precision = precision;
@@ -607,7 +664,12 @@ int loftr_set_weight(LoftrEngine* e, int i, const float* host, long long numel, 
     return MFR_ERR_ARG;
   MFR_CUDA_CHECK(cudaMemcpyAsync(e->wblob + e->specs[i].offset, host, numel * 4, cudaMemcpyHostToDevice, st));
   MFR_CUDA_CHECK(cudaStreamSynchronize(st));
-  if (i == static_cast<int>(e->specs.size()) - 1) e->weights_loaded = true;
+  e->w16_ready = false;                       // derived copies (bf16 / split operands) are rebuilt by the next forward
+  if (e->weight_set.size() != e->specs.size()) e->weight_set.assign(e->specs.size(), 0);
+  e->weight_set[i] = 1;
+  bool all = true;
+  for (char c : e->weight_set) all = all && c;
+  e->weights_loaded = all;                    // every tensor of the state dict has arrived
   return MFR_OK;
 }
 void loftr_mark_weights_loaded(LoftrEngine* e) { e->weights_loaded = true; }

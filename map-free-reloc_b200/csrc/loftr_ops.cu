@@ -874,6 +874,41 @@ __global__ void rows_to_bf16_kernel(const float* __restrict__ src, long long lds
   }
 }
 
+// fp32-faithful GEMM operands (precision mode 2, "3xTF32"): x = hi + lo with hi = tf32(x), lo = tf32(x - hi), so that
+//   A.B ~= Ahi.Bhi + Alo.Bhi + Ahi.Blo   (the dropped lo.lo term and the rounding of lo are ~2^-22 relative)
+// is ONE tensor-core GEMM over a three times longer K: dst row = [hi | lo | hi] (pattern 0, the A operand) or
+// [hi | hi | lo] (pattern 1, the B operand). Both halves are exact TF32 values, so the tensor core's own
+// fp32 -> tf32 conversion of the operands is the identity.
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__global__ void rows_split3_kernel(const float* __restrict__ src, long long lds, long long src_img_stride,
+                                   float* __restrict__ dst, long long rows_per_img, int C4, int pattern,
+                                   const int* __restrict__ dyn_rows) {
+  long long lim = rows_per_img;
+  if (dyn_rows) lim = min(lim, static_cast<long long>(*dyn_rows));
+  const int img = blockIdx.y;
+  const long long total = lim * C4;
+  const int C = C4 * 4;
+  const float* s = src + img * src_img_stride;
+  float* d0 = dst + img * rows_per_img * 3 * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / C4;
+    const int c = static_cast<int>(i - row * C4) * 4;
+    const float4 f = *reinterpret_cast<const float4*>(s + row * lds + c);
+    float4 hi, lo;
+    hi.x = tf32_rn(f.x); hi.y = tf32_rn(f.y); hi.z = tf32_rn(f.z); hi.w = tf32_rn(f.w);
+    lo.x = tf32_rn(f.x - hi.x); lo.y = tf32_rn(f.y - hi.y); lo.z = tf32_rn(f.z - hi.z); lo.w = tf32_rn(f.w - hi.w);
+    float* d = d0 + row * 3 * C + c;
+    *reinterpret_cast<float4*>(d) = hi;
+    *reinterpret_cast<float4*>(d + C) = pattern == 0 ? lo : hi;
+    *reinterpret_cast<float4*>(d + 2 * C) = pattern == 0 ? hi : lo;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ coarse matching
 // conf = softmax_col(S) * softmax_row(S); the expression is written with explicit rounding
 // intrinsics so that every pass reproduces the identical fp32 value (the mutual-NN test compares
@@ -1569,9 +1604,9 @@ __global__ void __launch_bounds__(128) stem_mma_kernel(const float* __restrict__
 // launch wrappers
 // ================================================================================================
 int stem_conv7x7(const float* img, const float* w, const float* bias, float* out, int NI, int H, int W,
-                 cudaStream_t st, int out_bf16) {
+                 cudaStream_t st, int out_bf16, int exact_fp32) {
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
-  if (kUseMmaStem) {
+  if (kUseMmaStem && !exact_fp32) {
     const int PW = 32 * ((Wo + 15) / 16) + 8;                 // patch columns: 2 px + kx for every pixel of the padded row
     const int smem = 2 * 8 * PW * 2;
     if (smem <= 48 * 1024) {
@@ -1704,6 +1739,17 @@ int rows_to_bf16(const float* src, long long lds, void* dst, long long ldd, long
   const long long total = rows * (C / 4);
   const unsigned grid = static_cast<unsigned>(std::min<long long>((total + 255) / 256, 148LL * 16));
   rows_to_bf16_kernel<<<grid, 256, 0, st>>>(src, lds, static_cast<unsigned short*>(dst), ldd, rows, C / 4, dyn_rows);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int rows_split3(const float* src, long long lds, long long src_img_stride, float* dst, long long rows_per_img,
+                int images, int C, int pattern, const int* dyn_rows, cudaStream_t st) {
+  if ((C & 3) || (lds & 3) || (src_img_stride & 3) || rows_per_img <= 0 || images <= 0 || images > 65535) return MFR_ERR_ARG;
+  const long long total = rows_per_img * (C / 4);
+  const unsigned gx = static_cast<unsigned>(std::min<long long>((total + 255) / 256, std::max(1LL, 148LL * 16 / images)));
+  rows_split3_kernel<<<dim3(gx, static_cast<unsigned>(images)), 256, 0, st>>>(src, lds, src_img_stride, dst, rows_per_img,
+                                                                             C / 4, pattern, dyn_rows);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }

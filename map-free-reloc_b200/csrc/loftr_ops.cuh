@@ -6,8 +6,9 @@
 namespace mfr {
 
 // stem: conv7x7 stride 2 pad 3, 1 -> 128 channels, folded BN bias, ReLU (resnet_fpn.py:60-62,102)
+// exact_fp32: plain fp32 FMA kernel instead of the tensor-core one (bf16 hi/lo split, ~2^-16 relative)
 int stem_conv7x7(const float* img, const float* w /*[128][49]*/, const float* bias, float* out,
-                 int NI, int H, int W, cudaStream_t st, int out_bf16 = 0);
+                 int NI, int H, int W, cudaStream_t st, int out_bf16 = 0, int exact_fp32 = 0);
 
 // dst[n,y,x,:] += bilinear_x2_align_corners(src)[n,y,x,:]   (resnet_fpn.py:110,114)
 // pixel strides lds / ldd in elements; src / dst fp32 or bf16
@@ -44,6 +45,11 @@ int layernorm_rows(const float* in, long long ldi, const float* gamma, const flo
 // dst16[row][0..C) = bf16(src[row][0..C)); rows optionally capped by *dyn_rows
 int rows_to_bf16(const float* src, long long lds, void* dst, long long ldd, long long rows, int C, const int* dyn_rows,
                  cudaStream_t st);
+
+// 3xTF32 operand split: dst[img][row][0:3C] = [hi | lo | hi] (pattern 0) or [hi | hi | lo] (pattern 1) of
+// src[img][row][0:C]; hi = tf32(x), lo = tf32(x - hi). Rows per image optionally capped by *dyn_rows.
+int rows_split3(const float* src, long long lds, long long src_img_stride, float* dst, long long rows_per_img,
+                int images, int C, int pattern, const int* dyn_rows, cudaStream_t st);
 
 // ---- coarse matching on the materialised similarity matrix S [B][L][L] (coarse_matching.py) ----
 struct CoarseMatchBuffers {

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "conv_gemm.cuh"
+#include "loftr_ops.cuh"   // rows_split3 (3xTF32 operand split of the fp32-faithful mode)
 #include "spsg_ops.cuh"
 
 namespace mfr {
@@ -40,6 +41,15 @@ struct SpsgEngine {
   float* img;
   float *kpts, *kscores, *X, *D, *mk0, *mk1, *mscores0;
   int *counts, *matches0, *m_offsets;
+  // precision 2 (fp32-faithful, MFR_PRECISION_FP32X3): every tensor-core GEMM runs as a 3xTF32 split product over 3x the
+  // K extent; A operands are split [hi | lo | hi] into the scratch x3 right before the GEMM, weights [hi | hi | lo] into
+  // wblob3 once per upload (see loftr_ops.cu: rows_split3)
+  int precision = 0;
+  float* x3 = nullptr; size_t x3_cap = 0;
+  float* wblob3 = nullptr;
+  bool w3_ready = false;
+  struct W3 { std::string name; long long rows; int cin; };
+  std::vector<W3> w3_list;
 
   void add(const std::string& n, size_t numel) {
     idx[n] = specs.size();
@@ -66,7 +76,19 @@ struct SpsgEngine {
             int act, const float* residual, float* out, long long ldo, long long ldr = 0) {
     ConvGemmDesc d{};
     d.x = x; d.N = N; d.H = Hh; d.W = Ww; d.Cin = Cin; d.ldx = ldx;
-    d.w = Wp(w + ".w"); d.Cout = Cout; d.R = R; d.S = R; d.stride = 1; d.pad = R / 2;
+    d.w = Wp(w + ".w");
+    if (precision == 2) {
+      const long long rows_img = static_cast<long long>(Hh) * Ww;
+      if (static_cast<size_t>(N) * rows_img * 3 * Cin > x3_cap || (Cin & 3)) { rc = MFR_ERR_ARG; return; }
+      float* x3_ = x3; const int N_ = N, C_ = Cin;
+      push([=](cudaStream_t st) { return rows_split3(x, ldx, rows_img * ldx, x3_, rows_img, N_, C_, 0, nullptr, st); });
+      bool found = false;
+      for (const auto& e : w3_list) found = found || e.name == w;
+      if (!found) w3_list.push_back(W3{w, static_cast<long long>(Cout) * R * R, Cin});
+      d.x = x3; d.Cin = 3 * Cin; d.ldx = 3 * Cin;
+      d.w = wblob3 + 3 * specs[idx[w + ".w"]].offset;
+    }
+    d.Cout = Cout; d.R = R; d.S = R; d.stride = 1; d.pad = R / 2;
     d.bias = Wp(w + ".b"); d.residual = residual; d.ldr = ldr > 0 ? ldr : ldo; d.act = act; d.alpha = 1.f; d.out = out; d.ldo = ldo;
     ConvGemmParams p;
     int r = conv_gemm_build(d, &p);
@@ -90,6 +112,13 @@ struct SpsgEngine {
     cv("final_proj", 256, 256, 1);
     add("bin_score", 1);
     wblob = alloc<float>(wtotal, "weights");
+    if (precision == 2) {
+      wblob3 = alloc<float>(3 * wtotal, "weights_split3");
+      const size_t act = static_cast<size_t>(2) * B * H * W * 64;                         // largest conv input (conv1b)
+      const size_t att = static_cast<size_t>(2) * B * (4 * static_cast<size_t>(K) * K + 256 * static_cast<size_t>(K));   // P + V^T
+      x3_cap = 3 * std::max(act, std::max(att, static_cast<size_t>(2) * B * K * 768));
+      x3 = alloc<float>(x3_cap, "split3_scratch");
+    }
 
     const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2, h8 = H4 / 2, w8 = W4 / 2;
     const int Hs = h8 * 8, Ws = w8 * 8;
@@ -184,6 +213,14 @@ struct SpsgEngine {
         d.w = qkv + 256; d.Cout = K; d.R = 1; d.S = 1; d.stride = 1; d.pad = 0;
         d.b_batched = 2; d.ldw = 768; d.w_y_stride = 64; d.w_img_stride = static_cast<long long>(K) * 768; d.b_xor = cross;
         d.act = ACT_NONE; d.alpha = 0.125f; d.out = Sat; d.ldo = K; d.ldr = K;
+        if (precision == 2) {   // q / k heads (64 channels each) -> [hi | lo | hi] / [hi | hi | lo] of 192, rows keep a stride of 768
+          float *q3 = x3, *k3 = x3 + static_cast<size_t>(NI) * K * 768; const int rows = NI * K;
+          if (rows > 65535) return MFR_ERR_ARG;
+          push([=](cudaStream_t st) { return rows_split3(qkv, 64, 768, q3, 4, rows, 64, 0, nullptr, st); });
+          push([=](cudaStream_t st) { return rows_split3(qkv + 256, 64, 768, k3, 4, rows, 64, 1, nullptr, st); });
+          d.x = q3; d.Cin = 192; d.x_y_stride = 192;
+          d.w = k3; d.w_y_stride = 192;
+        }
         ConvGemmParams pq;
         int r = conv_gemm_build(d, &pq);
         if (r != MFR_OK) return r;
@@ -196,6 +233,14 @@ struct SpsgEngine {
         e.b_batched = 2; e.ldw = K; e.w_y_stride = 64LL * K; e.w_img_stride = 256LL * K; e.b_xor = cross;
         e.act = ACT_NONE; e.alpha = 1.f; e.out = msg; e.ldo = 256; e.ldr = 256; e.out_y_stride = 64;
         e.out_img_stride = static_cast<long long>(K) * 256;
+        if (precision == 2) {   // P rows [K] -> [3K] (A pattern), V^T rows [K] -> [3K] (B pattern)
+          float *p3 = x3, *v3 = x3 + static_cast<size_t>(NI) * 4 * K * 3 * K;
+          const long long prow = static_cast<long long>(NI) * 4 * K, vrow = static_cast<long long>(NI) * 256;
+          push([=](cudaStream_t st) { return rows_split3(Sat, kk, 0, p3, prow, 1, kk, 0, nullptr, st); });
+          push([=](cudaStream_t st) { return rows_split3(Vt, kk, 0, v3, vrow, 1, kk, 1, nullptr, st); });
+          e.x = p3; e.Cin = 3 * K; e.ldx = 3 * K;
+          e.w = v3; e.ldw = 3 * K; e.w_y_stride = 64LL * 3 * K; e.w_img_stride = 256LL * 3 * K;
+        }
         ConvGemmParams pv;
         r = conv_gemm_build(e, &pv);
         if (r != MFR_OK) return r;
@@ -212,6 +257,14 @@ struct SpsgEngine {
       d.w = Mb + static_cast<size_t>(K) * 256; d.Cout = K; d.R = 1; d.S = 1; d.stride = 1; d.pad = 0;
       d.b_batched = 1; d.ldw = 256; d.w_img_stride = 2LL * K * 256; d.act = ACT_NONE; d.alpha = 1.f / 16.f;
       d.out = S; d.ldo = K; d.ldr = K;
+      if (precision == 2) {   // matching descriptors of all images, once in the A pattern and once in the B pattern
+        const long long rows = static_cast<long long>(NI) * K;
+        float *ma = x3, *mb = x3 + static_cast<size_t>(rows) * 768;
+        push([=](cudaStream_t st) { return rows_split3(Mb, 256, 0, ma, rows, 1, 256, 0, nullptr, st); });
+        push([=](cudaStream_t st) { return rows_split3(Mb, 256, 0, mb, rows, 1, 256, 1, nullptr, st); });
+        d.x = ma; d.Cin = 768; d.ldx = 768; d.x_img_stride = 2LL * K * 768;
+        d.w = mb + static_cast<size_t>(K) * 768; d.ldw = 768; d.w_img_stride = 2LL * K * 768;
+      }
       ConvGemmParams p;
       int r = conv_gemm_build(d, &p);
       if (r != MFR_OK) return r;
@@ -230,7 +283,19 @@ struct SpsgEngine {
   }
 
   int run(cudaStream_t st) {
-    for (auto& s : steps) { int r = s(st); if (r != MFR_OK) return r; }
+    int r = prepare_weights(st);
+    if (r != MFR_OK) return r;
+    for (auto& s : steps) { r = s(st); if (r != MFR_OK) return r; }
+    return MFR_OK;
+  }
+  int prepare_weights(cudaStream_t st) {
+    if (precision != 2 || w3_ready) return MFR_OK;
+    for (const auto& e : w3_list) {
+      const size_t off = specs[idx[e.name + ".w"]].offset;
+      int r = rows_split3(wblob + off, e.cin, 0, wblob3 + 3 * off, e.rows, 1, e.cin, 1, nullptr, st);
+      if (r != MFR_OK) return r;
+    }
+    w3_ready = true;
     return MFR_OK;
   }
 
@@ -240,6 +305,7 @@ struct SpsgEngine {
     const size_t hw = static_cast<size_t>(H) * W;
     MFR_CUDA_CHECK(cudaMemcpy2DAsync(img, 2 * hw * 4, img0, hw * 4, hw * 4, B, cudaMemcpyDeviceToDevice, st));
     MFR_CUDA_CHECK(cudaMemcpy2DAsync(img + hw, 2 * hw * 4, img1, hw * 4, hw * 4, B, cudaMemcpyDeviceToDevice, st));
+    { int r0 = prepare_weights(st); if (r0 != MFR_OK) return r0; }   // outside any capture
     if (!use_graph) return run(st);
     if (!graph) {
       int r = run(st);
@@ -272,6 +338,7 @@ struct SpsgEngine {
     MFR_CUDA_CHECK(cudaMemcpyAsync(kpts, h_kpts, sizeof(float) * NI * K * 2, cudaMemcpyHostToDevice, st));
     MFR_CUDA_CHECK(cudaMemcpyAsync(kscores, h_scores, sizeof(float) * NI * K, cudaMemcpyHostToDevice, st));
     MFR_CUDA_CHECK(cudaMemcpyAsync(D, h_desc, sizeof(float) * NI * K * 256, cudaMemcpyHostToDevice, st));
+    { int r0 = prepare_weights(st); if (r0 != MFR_OK) return r0; }
     for (size_t i = sg_begin; i < steps.size(); ++i) {
       int r = steps[i](st);
       if (r != MFR_OK) return r;
@@ -286,9 +353,11 @@ struct SpsgEngine {
 };
 
 int spsg_create(int B, int H, int W, int max_kp, int nms_radius, float kp_thr, int border, int sinkhorn_iters,
-                float match_thr, SpsgEngine** out) {
+                float match_thr, int precision, SpsgEngine** out) {
   if (B < 1 || H < 64 || W < 64 || max_kp < 16 || max_kp > 2048 || (max_kp % 16)) return MFR_ERR_ARG;
+  if (precision != 0 && precision != 2) return MFR_ERR_ARG;   // 0 = TF32 GEMM inputs, 2 = 3xTF32 split (fp32-faithful)
   auto* e = new SpsgEngine();
+  e->precision = precision;
   e->B = B; e->H = H; e->W = W; e->K = max_kp; e->nms_r = nms_radius; e->kp_thr = kp_thr; e->border = border;
   e->sk_iters = sinkhorn_iters; e->match_thr = match_thr;
   int rc = e->build();
@@ -304,6 +373,7 @@ int spsg_set_weight(SpsgEngine* e, int i, const float* host, long long numel, cu
   if (i < 0 || i >= static_cast<int>(e->specs.size()) || numel != static_cast<long long>(e->specs[i].numel)) return MFR_ERR_ARG;
   MFR_CUDA_CHECK(cudaMemcpyAsync(e->wblob + e->specs[i].offset, host, numel * 4, cudaMemcpyHostToDevice, st));
   MFR_CUDA_CHECK(cudaStreamSynchronize(st));
+  e->w3_ready = false;
   if (e->specs[i].name == "bin_score") e->bin_score = host[0];
   if (i == static_cast<int>(e->specs.size()) - 1) e->loaded = true;
   return MFR_OK;

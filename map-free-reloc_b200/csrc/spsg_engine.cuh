@@ -20,7 +20,7 @@ struct SpsgOutputs {
 };
 
 int spsg_create(int B, int H, int W, int max_kp, int nms_radius, float kp_thr, int border, int sinkhorn_iters,
-                float match_thr, SpsgEngine** out);
+                float match_thr, int precision, SpsgEngine** out);
 void spsg_destroy(SpsgEngine* e);
 int spsg_num_weights(const SpsgEngine* e);
 const char* spsg_weight_name(const SpsgEngine* e, int i);

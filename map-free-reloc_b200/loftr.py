@@ -173,7 +173,7 @@ def synthetic_state_dict(seed=0):
     return sd
 
 
-def functional_state_dict(coarse_scale=200.0, fine_scale=30.0, ln_gain=40.0):
+def functional_state_dict(coarse_scale=200.0, fine_scale=30.0, ln_gain=40.0, noise=0.0, noise_seed=0):
     """Hand-constructed LoFTR weights (reference state_dict names / shapes) that make the network a
     working matcher on textured scenes, for benchmarking without the real checkpoints (which the
     reference does not ship): every layer runs with its full shape and FLOPs, but the convolutions
@@ -191,6 +191,12 @@ def functional_state_dict(coarse_scale=200.0, fine_scale=30.0, ln_gain=40.0):
       norm2 gain ``ln_gain`` -> x + g * LayerNorm(x): tokens get (almost) unit norm, so the dual
       softmax matches by normalised cross-correlation; the other layers are identities;
     * fine level: merge_feat passes the window features through, transformer identity.
+
+    ``noise`` > 0 adds seeded Gaussian noise of that standard deviation to EVERY conv / linear weight, so that no
+    tensor-core operand is structurally zero: the constructed weights above are 99.8 % zeros, and a chip multiplying
+    zeros draws far less power (and clocks higher) than one running a trained checkpoint. The perturbed network is
+    still a working matcher (the descriptor is a few hundred times larger than the perturbation), which is what the
+    throughput benchmark needs: dense operands AND a few thousand matches per pair for the fine level and RANSAC.
     """
     sd = {k: torch.zeros(shp) for k, shp in _state_dict_shapes().items()}
     for k in sd:                                                       # identity BatchNorms / LayerNorm gains off
@@ -259,6 +265,11 @@ def functional_state_dict(coarse_scale=200.0, fine_scale=30.0, ln_gain=40.0):
                 sd[f"{p}.{nme}.weight"] = torch.eye(c)
     sd["loftr_coarse.layers.0.norm2.weight"] = torch.full((256,), float(ln_gain))
     sd["fine_preprocess.merge_feat.weight"] = torch.cat([torch.eye(128), torch.zeros(128, 128)], 1)
+    if noise > 0:
+        g = torch.Generator().manual_seed(int(noise_seed))
+        for k in sorted(sd):
+            if k.endswith(".weight") and sd[k].dim() in (2, 4):
+                sd[k] = sd[k] + float(noise) * torch.randn(sd[k].shape, generator=g)
     return {k: v.float().contiguous() for k, v in sd.items()}
 
 
@@ -276,7 +287,10 @@ class LoFTR:
         torch.cuda.set_device(self.device)
         self.stream = torch.cuda.Stream(device=self.device)
         h = ctypes.c_void_p()
-        self.precision = {"tf32": 0, "bf16": 1}[precision]
+        # tf32: fp32 storage, TF32 tensor-core inputs; bf16: bf16 storage + kind::f16 MMAs (backbone, token GEMMs,
+        # correlation, attention); fp32x3: fp32 storage, every GEMM as a 3xTF32 split product (fp32-faithful)
+        self.precision = {"tf32": 0, "bf16": 1, "fp32x3": 2, "fp32": 2}[precision]
+        self.precision_name = {0: "tf32", 1: "bf16", 2: "fp32x3"}[self.precision]
         _lib.check(self._l.mfr_loftr_create(self.B, self.H, self.W, float(self.cfg["thr"]),
                                             int(self.cfg["border_rm"]), float(self.cfg["temperature"]),
                                             self.precision, ctypes.byref(h)), "mfr_loftr_create")

@@ -48,14 +48,17 @@ class RelocPipeline:
             h, w = depth_hw
             self.stage = [{"g0": torch.empty(B, h, w, device=dev), "g1": torch.empty(B, h, w, device=dev),
                            "d0": torch.empty(B, h, w, device=dev), "d1": torch.empty(B, h, w, device=dev),
-                           "K": torch.empty(B, 3, 3, device=dev)} for _ in range(2)]
+                           "K0": torch.empty(B, 3, 3, device=dev), "K1": torch.empty(B, 3, 3, device=dev)}
+                          for _ in range(2)]
         self.i = 0
         self._outs_all = [e.device_outputs() for e in self.engines]
 
     # ---------------------------------------------------------------- stages
-    def _enqueue(self, g0, g1, d0, d1, K):
-        """g0/g1/d0/d1/K: device tensors of this batch (already ordered after whatever produced them on the
-        current stream or on self.s_copy via slot['ev_in'])."""
+    def _enqueue(self, g0, g1, d0, d1, K0, K1):
+        """g0/g1/d0/d1/K0/K1: device tensors of this batch (already ordered after whatever produced them on the
+        current stream or on self.s_copy via slot['ev_in']). K0 / K1 are the intrinsics of the reference and the
+        query frame: Map-free frames have per-frame intrinsics (lib/datasets/mapfree.py:39-54) and the solver
+        normalises each image's points with its own K (pose_solver.py:39-43, 150-151)."""
         eng, slot = self.engines[self.i % len(self.engines)], self.slots[self.i % 2]
         outs = self._outs_all[self.i % len(self.engines)]
         if slot["busy"]:                              # the solver of batch i-2 must be done with this slot
@@ -68,7 +71,7 @@ class RelocPipeline:
             slot["ev_fwd"].record(eng.stream)
         with torch.cuda.stream(self.s_solve):
             self.s_solve.wait_event(slot["ev_fwd"])
-            R, t, n = self.be.emat_metric(slot["k0"], slot["k1"], slot["off"], K, K, d0, d1, self.pix_thr,
+            R, t, n = self.be.emat_metric(slot["k0"], slot["k1"], slot["off"], K0, K1, d0, d1, self.pix_thr,
                                           self.scale_thr, self.num_hyp)
             B = eng.B
             slot["rec"][:, :9] = R.reshape(B, 9)
@@ -76,9 +79,9 @@ class RelocPipeline:
             slot["rec"][:, 12] = n.to(torch.float32)
             slot["rec_host"].copy_(slot["rec"], non_blocking=True)
             slot["ev_solved"].record(self.s_solve)
-        for x in (d0, d1, K):
+        for x in (d0, d1, K0, K1):
             x.record_stream(self.s_solve)
-        slot["inputs"] = (g0, g1, d0, d1, K)          # keep alive until the slot is reused
+        slot["inputs"] = (g0, g1, d0, d1, K0, K1)     # keep alive until the slot is reused
         slot["busy"] = True
 
     def _collect(self, j):
@@ -89,21 +92,23 @@ class RelocPipeline:
         return rec[:, :9].reshape(B, 3, 3).clone(), rec[:, 9:12].clone(), rec[:, 12].to(torch.int32)
 
     # ---------------------------------------------------------------- public
-    def submit_device(self, g0, g1, d0, d1, K):
-        """Batch already resident on the device. Returns the result of the previous batch (or None)."""
-        self._enqueue(g0, g1, d0, d1, K)
+    def submit_device(self, g0, g1, d0, d1, K0, K1=None):
+        """Batch already resident on the device ([B,3,3] float32 intrinsics per image; K1=None: both frames share
+        K0). Returns the result of the previous batch (or None)."""
+        self._enqueue(g0, g1, d0, d1, K0, K0 if K1 is None else K1)
         self.i += 1
         return self._collect(self.i - 2) if self.i >= 2 else None
 
-    def submit_host(self, g0, g1, d0, d1, K):
-        """Batch in pinned host memory ([B,h,w] float32 images / depths, [B,3,3] intrinsics): the copy to the
-        device runs on its own stream, overlapping the forward of the previous batch."""
+    def submit_host(self, g0, g1, d0, d1, K0, K1=None):
+        """Batch in pinned host memory ([B,h,w] float32 images / depths, [B,3,3] intrinsics of each frame; K1=None:
+        both frames share K0): the copy to the device runs on its own stream, overlapping the forward of the
+        previous batch."""
         assert self.stage is not None, "construct the pipeline with depth_hw=(h, w) to feed host batches"
         st, slot = self.stage[self.i % 2], self.slots[self.i % 2]
         with torch.cuda.stream(self.s_copy):
             if slot["busy"]:                          # staging tensors of batch i-2 are read by its solver
                 self.s_copy.wait_event(slot["ev_solved"])
-            for k, src in (("g0", g0), ("g1", g1), ("d0", d0), ("d1", d1), ("K", K)):
+            for k, src in (("g0", g0), ("g1", g1), ("d0", d0), ("d1", d1), ("K0", K0), ("K1", K0 if K1 is None else K1)):
                 if isinstance(src, (list, tuple)):    # one pinned tensor per pair
                     for j, row in enumerate(src):
                         st[k][j].copy_(row, non_blocking=True)
@@ -112,7 +117,7 @@ class RelocPipeline:
             slot["ev_in"].record(self.s_copy)
         self.engines[self.i % len(self.engines)].stream.wait_event(slot["ev_in"])
         self.s_solve.wait_event(slot["ev_in"])
-        return self.submit_device(st["g0"], st["g1"], st["d0"], st["d1"], st["K"])
+        return self.submit_device(st["g0"], st["g1"], st["d0"], st["d1"], st["K0"], st["K1"])
 
     def drain(self):
         """Result of the last submitted batch (blocks until it is done)."""

@@ -5,6 +5,8 @@ arithmetic runs in the batched-hypothesis CUDA kernels of libmfr_b200.so. ``Pose
 batched device-resident interface the fused matcher+solver pipeline and the benchmark use.
 """
 import ctypes
+import math
+import warnings
 
 import numpy as np
 import torch
@@ -13,6 +15,9 @@ from . import lib as _lib
 
 DEFAULT_NUM_HYP = 2048
 DEFAULT_SEED = 0x5EED
+LO_TUKEY, LO_LSQ = 1, 3       # mfr_emat_ransac lo_enabled flags: bit 0 local optimisation, bit 1 final least-squares refit
+DEFAULT_FINAL_REFIT = "lsq"
+MAX_PTS_LIMIT = 8192          # correspondences per pair the RANSAC kernels can hold (shared memory)
 
 
 def _cfg_get(cfg, path, default=None):
@@ -34,11 +39,14 @@ class PoseBackend:
         self._l = _lib.load()
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
+        if not 8 <= int(max_pts) <= MAX_PTS_LIMIT:
+            raise ValueError(f"PoseBackend: max_pts must be in [8, {MAX_PTS_LIMIT}] (correspondences of a pair are staged "
+                             f"in shared memory), got {max_pts}")
         h = ctypes.c_void_p()
         _lib.check(self._l.mfr_pose_solver_create(int(max_pairs), int(max_pts), int(max_hyp), ctypes.byref(h)),
                    "mfr_pose_solver_create")
         self._h = h
-        self.max_pairs, self.max_pts, self.max_hyp = max_pairs, min(max_pts, 8192), max_hyp
+        self.max_pairs, self.max_pts, self.max_hyp = int(max_pairs), int(max_pts), int(max_hyp)
 
     def _outs(self, P, total):
         dev = self.device
@@ -56,13 +64,15 @@ class PoseBackend:
 
     def emat(self, kpts0, kpts1, offsets, K0, K1, pix_thr, num_hyp=DEFAULT_NUM_HYP, seed=DEFAULT_SEED,
              lo=True, total=None):
-        """EssentialMatrixSolver for P pairs. Returns R [P,3,3], t [P,3] (unit), n [P], mask [total]."""
+        """EssentialMatrixSolver for P pairs. Returns R [P,3,3], t [P,3] (unit), n [P], mask [total].
+        lo: False / 0 = raw RANSAC winner; True / 1 = local optimisation (LO_TUKEY); 3 = LO + the final truncated
+        least-squares refit on the model's own inlier set (LO_LSQ, the reference-equivalent optimum)."""
         P = self._prep(kpts0, kpts1, offsets, K0, K1)
         total = kpts0.shape[0] if total is None else total
         R, t, n, mask = self._outs(P, total)
         _lib.check(self._l.mfr_emat_ransac(self._h, _lib.ptr(kpts0), _lib.ptr(kpts1), _lib.ptr(offsets), P,
                                            _lib.ptr(K0), _lib.ptr(K1), float(pix_thr), int(num_hyp),
-                                           ctypes.c_ulonglong(seed), int(bool(lo)), _lib.ptr(R), _lib.ptr(t),
+                                           ctypes.c_ulonglong(seed), int(lo), _lib.ptr(R), _lib.ptr(t),
                                            _lib.ptr(n), _lib.ptr(mask), _lib.cur_stream()), "mfr_emat_ransac")
         return R, t, n, mask
 
@@ -129,15 +139,56 @@ class PoseBackend:
 # ------------------------------------------------------------------------------------------------
 # reference-shaped plugins (one pair per call, host arrays in / host arrays out)
 # ------------------------------------------------------------------------------------------------
+def required_hypotheses(confidence, inlier_ratio, sample_size):
+    """RANSAC stopping rule (what cv2's `confidence` / `prob` argument drives): the number of minimal samples after
+    which an all-inlier sample has been drawn with probability `confidence`, given the inlier ratio found."""
+    w = min(max(float(inlier_ratio), 1e-9), 1.0) ** sample_size
+    if w >= 1.0 - 1e-12:
+        return 1
+    c = min(max(float(confidence), 0.0), 1.0 - 1e-12)
+    return int(math.ceil(math.log(1.0 - c) / math.log(1.0 - w)))
+
+
 class _SolverBase:
-    def __init__(self, cfg):
-        self.num_hyp = int(_cfg_get(cfg, "GPU_RANSAC.NUM_HYPOTHESES", DEFAULT_NUM_HYP))
+    """The GPU solvers run a fixed hypothesis budget per launch instead of OpenCV's sequential loop with an early
+    exit. The reference's `CONFIDENCE` is honoured as an escalation rule: when the inlier ratio a launch found says
+    that its budget was too small for the requested confidence (``required_hypotheses``), the launch is repeated with
+    a larger budget (x4 per round, up to ``GPU_RANSAC.MAX_HYPOTHESES``)."""
+    SAMPLE_SIZE = 5
+
+    def __init__(self, cfg, default_hyp=DEFAULT_NUM_HYP):
+        self.num_hyp = int(_cfg_get(cfg, "GPU_RANSAC.NUM_HYPOTHESES", default_hyp))
+        self.max_hyp = max(self.num_hyp, int(_cfg_get(cfg, "GPU_RANSAC.MAX_HYPOTHESES", 32768)))
         self.seed = int(_cfg_get(cfg, "GPU_RANSAC.SEED", DEFAULT_SEED))
-        self.lo = bool(_cfg_get(cfg, "GPU_RANSAC.LOCAL_OPTIMISATION", True))
-        self.backend = PoseBackend(max_pairs=1, max_hyp=max(self.num_hyp, 128))
+        lo = bool(_cfg_get(cfg, "GPU_RANSAC.LOCAL_OPTIMISATION", True))
+        refit = str(_cfg_get(cfg, "GPU_RANSAC.FINAL_REFIT", DEFAULT_FINAL_REFIT)).lower()
+        if refit not in ("lsq", "tukey"):
+            raise ValueError("GPU_RANSAC.FINAL_REFIT must be 'lsq' or 'tukey'")
+        self.lo = (LO_LSQ if refit == "lsq" else LO_TUKEY) if lo else 0
+        self.backend = PoseBackend(max_pairs=1, max_hyp=max(self.max_hyp, 128))
         self.dev = self.backend.device
+        self.last_num_hyp = 0       # budget of the launch whose result was returned
+
+    def _budgets(self, confidence):
+        """Hypothesis budgets to try in order; the caller stops at the first one that satisfies `confidence`."""
+        h = self.num_hyp
+        yield h
+        if confidence is None:
+            return
+        while h < self.max_hyp:
+            h = min(self.max_hyp, 4 * h)
+            yield h
+
+    def _satisfied(self, confidence, n_inliers, n_points, budget):
+        if confidence is None or n_points <= 0:
+            return True
+        return budget >= required_hypotheses(confidence, n_inliers / float(n_points), self.SAMPLE_SIZE)
 
     def _upload(self, kpts0, kpts1, data):
+        if len(kpts0) > MAX_PTS_LIMIT:    # the reference has no limit; no matcher on this path produces this many
+            warnings.warn(f"{type(self).__name__}: {len(kpts0)} correspondences, the GPU solver takes the first "
+                          f"{MAX_PTS_LIMIT}", RuntimeWarning, stacklevel=3)
+            kpts0, kpts1 = kpts0[:MAX_PTS_LIMIT], kpts1[:MAX_PTS_LIMIT]
         k0 = torch.as_tensor(np.ascontiguousarray(kpts0, dtype=np.float32)).to(self.dev).reshape(-1, 2)
         k1 = torch.as_tensor(np.ascontiguousarray(kpts1, dtype=np.float32)).to(self.dev).reshape(-1, 2)
         off = torch.tensor([0, k0.shape[0]], dtype=torch.int32, device=self.dev)
@@ -156,17 +207,20 @@ class EssentialMatrixSolver(_SolverBase):
     def __init__(self, cfg):
         super().__init__(cfg)
         self.ransac_pix_threshold = float(_cfg_get(cfg, "EMAT_RANSAC.PIX_THRESHOLD"))
-        self.ransac_confidence = _cfg_get(cfg, "EMAT_RANSAC.CONFIDENCE")  # kept for the surface; the
-        # GPU solver runs a fixed hypothesis budget instead of a confidence-driven early exit
+        self.ransac_confidence = _cfg_get(cfg, "EMAT_RANSAC.CONFIDENCE")  # escalation rule, see _SolverBase
         self.mask = None
 
     def estimate_pose(self, kpts0, kpts1, data):
         if len(kpts0) < 5:
             return self._nan()
         k0, k1, off, K0, K1 = self._upload(kpts0, kpts1, data)
-        R, t, n, mask = self.backend.emat(k0, k1, off, K0, K1, self.ransac_pix_threshold, self.num_hyp,
-                                          self.seed, self.lo)
-        n = int(n.item())
+        for budget in self._budgets(self.ransac_confidence):
+            R, t, n, mask = self.backend.emat(k0, k1, off, K0, K1, self.ransac_pix_threshold, budget,
+                                              self.seed, self.lo)
+            n = int(n.item())
+            self.last_num_hyp = budget
+            if self._satisfied(self.ransac_confidence, n, k0.shape[0], budget):
+                break
         self.mask = mask.cpu().numpy().reshape(-1, 1)
         self._dev = (k0, k1, off, K0, K1, mask)
         if n == 0:
@@ -198,9 +252,14 @@ class EssentialMatrixMetricSolver(EssentialMatrixSolver):
 class PnPSolver(_SolverBase):
     """Metric relative pose from 2D-3D correspondences (pose_solver.py:175-235)."""
 
+    SAMPLE_SIZE = 4   # P3P + the disambiguating 4th point
+
     def __init__(self, cfg):
-        super().__init__(cfg)
-        self.ransac_iterations = _cfg_get(cfg, "PNP.RANSAC_ITER")   # surface only (fixed GPU budget)
+        # PNP.RANSAC_ITER (reference: the iteration cap of cv2.solvePnPRansac) is the first launch's hypothesis
+        # budget unless GPU_RANSAC.NUM_HYPOTHESES overrides it; PNP.CONFIDENCE escalates it (see _SolverBase)
+        self.ransac_iterations = _cfg_get(cfg, "PNP.RANSAC_ITER")
+        iters = int(self.ransac_iterations) if self.ransac_iterations else DEFAULT_NUM_HYP
+        super().__init__(cfg, default_hyp=max(128, (iters + 127) // 128 * 128))
         self.reprojection_inlier_threshold = float(_cfg_get(cfg, "PNP.REPROJECTION_INLIER_THRESHOLD"))
         self.confidence = _cfg_get(cfg, "PNP.CONFIDENCE")
 
@@ -210,9 +269,13 @@ class PnPSolver(_SolverBase):
         k0, k1, off, K0, K1 = self._upload(pts0, pts1, data)
         d0 = torch.as_tensor(data["depth0"]).float()
         d0 = d0.reshape(1, *d0.shape[-2:]).to(self.dev)
-        R, t, n, _ = self.backend.pnp(k0, k1, off, K0, K1, d0, self.reprojection_inlier_threshold,
-                                      self.num_hyp, self.seed)
-        n = int(n.item())
+        for budget in self._budgets(self.confidence):
+            R, t, n, _ = self.backend.pnp(k0, k1, off, K0, K1, d0, self.reprojection_inlier_threshold,
+                                          budget, self.seed)
+            n = int(n.item())
+            self.last_num_hyp = budget
+            if self._satisfied(self.confidence, n, k0.shape[0], budget):
+                break
         if n == 0:
             return self._nan()
         return R[0].double().cpu().numpy(), t[0].double().cpu().numpy().reshape(3, 1), n
@@ -221,6 +284,7 @@ class PnPSolver(_SolverBase):
 class ProcrustesSolver(_SolverBase):
     """Metric relative pose from 3D-3D correspondences (pose_solver.py:238-320). The ICP refinement
     over the full point clouds (PROCRUSTES.REFINE, Open3D registration_icp) is not built."""
+    SAMPLE_SIZE = 3
 
     def __init__(self, cfg):
         super().__init__(cfg)

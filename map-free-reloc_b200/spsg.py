@@ -131,7 +131,7 @@ def synthetic_state_dicts(seed=0):
 class SuperPointSuperGlue:
     """CUDA SuperPoint+SuperGlue engine for ``batch`` pairs of [H, W] gray images."""
 
-    def __init__(self, sp_sd, sg_sd, batch=1, height=720, width=540, cfg=None, device=0, graph=True):
+    def __init__(self, sp_sd, sg_sd, batch=1, height=720, width=540, cfg=None, device=0, graph=True, precision="tf32"):
         if not torch.cuda.is_available():
             raise _lib.MfrError("mfr_b200.SuperPointSuperGlue needs a CUDA device (no CPU fallback)")
         self._l = _lib.load()
@@ -142,10 +142,11 @@ class SuperPointSuperGlue:
         self.stream = torch.cuda.Stream(device=self.device)
         h = ctypes.c_void_p()
         c = self.cfg
-        _lib.check(self._l.mfr_spsg_create(self.B, self.H, self.W, self.K, int(c["nms_radius"]),
-                                           float(c["keypoint_threshold"]), int(c["remove_borders"]),
-                                           int(c["sinkhorn_iterations"]), float(c["match_threshold"]), ctypes.byref(h)),
-                   "mfr_spsg_create")
+        self.precision = {"tf32": 0, "fp32x3": 2, "fp32": 2}[precision]
+        _lib.check(self._l.mfr_spsg_create_ex(self.B, self.H, self.W, self.K, int(c["nms_radius"]),
+                                              float(c["keypoint_threshold"]), int(c["remove_borders"]),
+                                              int(c["sinkhorn_iterations"]), float(c["match_threshold"]),
+                                              self.precision, ctypes.byref(h)), "mfr_spsg_create_ex")
         self._h = h
         self._l.mfr_spsg_set_graph(self._h, int(bool(graph)))
         w = prepare_weights(sp_sd, sg_sd)

@@ -64,6 +64,52 @@ def essential_matrix_solver(kpts0, kpts1, K0, K1, pix_threshold, confidence):
     return ret[0], ret[1], ret[2], mask
 
 
+def sampson_residuals(R, t, k0, k1):
+    """Signed Sampson distance of normalised correspondences under E = [t]x R:
+    r = x1^T E x0 / sqrt((E x0)_0^2 + (E x0)_1^2 + (E^T x1)_0^2 + (E^T x1)_1^2); OpenCV's inlier test is r^2 < thr^2."""
+    t = np.asarray(t, dtype=np.float64).ravel()
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    E = tx @ np.asarray(R, dtype=np.float64)
+    x0 = np.concatenate([k0, np.ones((len(k0), 1))], 1)
+    x1 = np.concatenate([k1, np.ones((len(k1), 1))], 1)
+    Ex0 = x0 @ E.T
+    Etx1 = x1 @ E
+    num = np.sum(x1 * Ex0, axis=1)
+    den = np.sqrt(Ex0[:, 0] ** 2 + Ex0[:, 1] ** 2 + Etx1[:, 0] ** 2 + Etx1[:, 1] ** 2)
+    return num / den
+
+
+def polish_essential(R, t, mask, kpts0, kpts1, K0, K1):
+    """The "polished oracle" of SURVEY.md §7 hard part 1(b): the reference solver's output (R, unit t, cheirality
+    mask of pose_solver.py:46-60) -> deterministic Levenberg-Marquardt on the Sampson residuals of the reference's
+    OWN inlier set (fixed), parameters = rotation vector increment (left-multiplied) + 2 tangent coordinates of t on
+    the unit sphere. cv.findEssentialMat(USAC_MAGSAC) does not return the least-squares optimum of its inlier set;
+    this does, and an independent solver can be compared with it at 1e-3 rad."""
+    from scipy.optimize import least_squares
+    K0 = np.asarray(K0, dtype=np.float64); K1 = np.asarray(K1, dtype=np.float64)
+    k0, k1 = normalise_kpts(np.asarray(kpts0, np.float64), np.asarray(kpts1, np.float64), K0, K1)
+    m = np.asarray(mask).ravel() == 1
+    k0, k1 = k0[m], k1[m]
+    R0 = np.asarray(R, dtype=np.float64)
+    t0 = np.asarray(t, dtype=np.float64).ravel()
+    t0 = t0 / np.linalg.norm(t0)
+    a = np.eye(3)[np.argmin(np.abs(t0))]
+    b1 = np.cross(t0, a); b1 /= np.linalg.norm(b1)
+    b2 = np.cross(t0, b1)
+
+    def unpack(p):
+        dR, _ = cv.Rodrigues(p[:3].reshape(3, 1))
+        tt = t0 + p[3] * b1 + p[4] * b2
+        return dR @ R0, tt / np.linalg.norm(tt)
+
+    def fun(p):
+        Rp, tp = unpack(p)
+        return sampson_residuals(Rp, tp, k0, k1)
+
+    sol = least_squares(fun, np.zeros(5), method="lm", xtol=1e-15, ftol=1e-15, gtol=1e-15, max_nfev=2000)
+    return unpack(sol.x)
+
+
 def scale_from_depth(R, t, mask, kpts0, kpts1, depth0, depth1, K0, K1, scale_threshold):
     """EssentialMatrixMetricSolver.estimate_pose, pose_solver.py:132-172, the part after the
     scale-free solve. depth0/depth1 are [H,W] float32 (the reference indexes data['depth0'][0])."""

@@ -12,7 +12,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import mfr_b200  # noqa: E402,F401
+from helpers import spsg_real_cases  # noqa: E402
 from mfr_b200 import synth  # noqa: E402
 from oracle import ref_import, loftr_oracle  # noqa: E402
 
@@ -90,6 +92,60 @@ def make_loftr_golden():
     print("loftr golden:", len(out), "arrays; M =", [len(out[f'c{i}_i_ids']) for i in range(2)])
 
 
+FULLRES_CASES = [("dense", 0.0), ("functional", 0.2), ("functional_dense", 0.2)]   # weights, coarse threshold
+FUNCTIONAL_DENSE_NOISE = 1e-3                            # bench.py's throughput weights (loftr.functional_state_dict(noise=...))
+FULLRES_SEEDS = (1000, 1001)                             # the first two pairs of bench.py's pool
+
+
+def fullres_inputs():
+    """Two 720x540 synthetic pairs exactly as bench.py feeds them (gray float32 / 255), [2,1,720,540] each."""
+    g0, g1 = [], []
+    for sd_ in FULLRES_SEEDS:
+        p = synth.make_pair(sd_)
+        g0.append(synth.rgb_to_gray_u8(p["image0"]).astype(np.float32) / 255.0)
+        g1.append(synth.rgb_to_gray_u8(p["image1"]).astype(np.float32) / 255.0)
+    return torch.from_numpy(np.stack(g0))[:, None], torch.from_numpy(np.stack(g1))[:, None]
+
+
+def fullres_state_dict(kind):
+    from mfr_b200 import loftr
+    if kind == "dense":
+        return loftr_oracle.make_state_dict(0)
+    return loftr.functional_state_dict(noise=FUNCTIONAL_DENSE_NOISE if kind == "functional_dense" else 0.0)
+
+
+def make_loftr_fullres_golden():
+    """BASELINE configuration (540x720 -> 720x544 after the reference's pad, L = 6120 coarse cells), the UNMODIFIED
+    reference LoFTR on CPU fp32, one pair per forward (the reference's batch size). Two weight sets: dense seeded
+    random weights (coarse threshold 0: every mutual nearest neighbour is a match) and the functional weights the
+    benchmark's accuracy block uses (reference threshold 0.2), plain and with the dense perturbation of the throughput run."""
+    from mfr_b200 import loftr
+    LoFTR, default_cfg = ref_import.load_loftr()
+    i0, i1 = fullres_inputs()
+    out = {"checksum": checksum(i0.numpy(), i1.numpy())}
+    for kind, thr in FULLRES_CASES:
+        sd = fullres_state_dict(kind)
+        m = LoFTR(config=default_cfg).eval()
+        m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=False)
+        m.coarse_matching.thr = thr
+        cap = {}
+        m.loftr_coarse.register_forward_hook(lambda mod, inp, outp: cap.__setitem__("c", outp))   # (feat_c0, feat_c1)
+        for b in range(i0.shape[0]):
+            d = {"image0": loftr.pad_to_8(i0[b:b + 1]), "image1": loftr.pad_to_8(i1[b:b + 1])}
+            with torch.no_grad():
+                m(d)
+            pre = f"{kind}_p{b}_"
+            out[pre + "i_ids"] = d["i_ids"].numpy().astype(np.int32)
+            out[pre + "j_ids"] = d["j_ids"].numpy().astype(np.int32)
+            out[pre + "mconf"] = d["mconf"].numpy()
+            out[pre + "mkpts1_f"] = d["mkpts1_f"].numpy()
+            out[pre + "conf_sample"] = d["conf_matrix"][0, ::97, ::89].numpy()
+            out[pre + "feat_c0_sample"] = cap["c"][0][0, ::61, ::8].numpy()       # coarse tokens after the transformer
+            out[pre + "feat_c1_sample"] = cap["c"][1][0, ::61, ::8].numpy()
+            print(f"fullres golden {kind} pair {b}: M = {len(d['i_ids'])}, conf max {d['conf_matrix'].max().item():.4g}")
+    np.savez_compressed(os.path.join(HERE, "loftr_fullres_reference.npz"), **out)
+
+
 def spsg_case():
     p = synth.make_pair(5)
     g0 = synth.rgb_to_gray_u8(p["image0"]).astype(np.float32) / 255.0
@@ -118,8 +174,37 @@ def make_spsg_golden():
     print("spsg golden: kpts", out["keypoints0"].shape, out["keypoints1"].shape, "matches", int((out["matches0"] > -1).sum()))
 
 
+def make_spsg_real_golden():
+    """UNMODIFIED reference Matching (SuperPoint + SuperGlue) with the in-tree weights and the settings of
+    etc/feature_matching_baselines/matchers.py:65-71."""
+    from oracle import build_ref
+    assert build_ref.build(verbose=False)
+    SuperPoint, SuperGlue, Matching = ref_import.load_superglue()
+    m = Matching({"superpoint": {"nms_radius": 4, "keypoint_threshold": 0.005, "max_keypoints": 1024},
+                  "superglue": {"weights": "indoor", "sinkhorn_iterations": 20, "match_threshold": 0.2}}).eval()
+    out = {}
+    for name, i0, i1 in spsg_real_cases():
+        with torch.no_grad():
+            pred = m({"image0": i0, "image1": i1})
+        out[name + "_checksum"] = checksum(i0.numpy(), i1.numpy())
+        for k in ("keypoints0", "keypoints1", "scores0", "scores1", "matches0", "matching_scores0"):
+            out[f"{name}_{k}"] = pred[k][0].numpy()
+        out[f"{name}_descriptors0_sample"] = pred["descriptors0"][0][::8, ::4].numpy()
+        print(f"spsg real-weights golden {name}: keypoints {len(out[name + '_keypoints0'])} / {len(out[name + '_keypoints1'])},"
+              f" matches {int((out[name + '_matches0'] > -1).sum())}")
+    np.savez_compressed(os.path.join(HERE, "spsg_real_reference.npz"), **out)
+
+
 if __name__ == "__main__":
     assert ref_import.available(), "needs /root/reference"
-    make_pose_golden()
-    make_loftr_golden()
-    make_spsg_golden()
+    which = sys.argv[1:] or ["pose", "loftr", "fullres", "spsg", "spsg_real"]
+    if "pose" in which:
+        make_pose_golden()
+    if "loftr" in which:
+        make_loftr_golden()
+    if "fullres" in which:
+        make_loftr_fullres_golden()
+    if "spsg" in which:
+        make_spsg_golden()
+    if "spsg_real" in which:
+        make_spsg_real_golden()

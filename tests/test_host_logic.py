@@ -48,7 +48,7 @@ def test_config_loads_reference_yaml_layers(tmp_path):
                   "PNP:\n  RANSAC_ITER: 1000\n  REPROJECTION_INLIER_THRESHOLD: 3\n  CONFIDENCE: 0.9999\n")
     cfg = config.load_cfg(str(ds), str(me))
     assert cfg.POSE_SOLVER == "PNP" and cfg.PNP.RANSAC_ITER == 1000 and cfg.DATASET.SCENES is None
-    assert cfg.DATASET.HEIGHT == 720 and cfg.GPU_RANSAC.NUM_HYPOTHESES == 2048
+    assert cfg.DATASET.HEIGHT == 720 and cfg.GPU_RANSAC.NUM_HYPOTHESES is None and cfg.GPU_RANSAC.FINAL_REFIT == "lsq"
     bad = tmp_path / "bad.yaml"
     bad.write_text("NOT_A_KEY: 1\n")
     with pytest.raises(KeyError):
