@@ -256,6 +256,23 @@ float mfr_debug_time_conv(const float* x, int N, int H, int W, int Cin, const fl
 int mfr_linear_attention(const void* q, const void* k, const void* v, void* msg, int n, int L, int S, int windows,
                          int bf16, void* stream);
 
+/* Leaderboard metrics of the Map-free benchmark for n poses (benchmark/metrics.py:40-67, benchmark/utils.py:95-129 sine
+ * variant, benchmark/reprojection.py:7-86): device double arrays q_gt/q_est [n][4] (w, x, y, z), t_gt/t_est [n][3],
+ * K [n][9]; image size W x H. Out: trans_err [n] (m), rot_err [n] (degrees), reproj_err [n] (VCRE, pixels). */
+int mfr_pose_metrics(const double* q_gt, const double* t_gt, const double* q_est, const double* t_est, const double* K, int W,
+                     int H, int n, double* trans_err, double* rot_err, double* reproj_err, void* stream);
+
+/* Stage entry: the fused tail of one LoFTREncoderLayer (loftr_module/transformer.py:52-58),
+ *   x += norm2(mlp2(relu(mlp0([x | norm1(merge(msg))])))),  bf16 tensor-core operands, fp32 accumulate / LayerNorm / residual,
+ * for n_blocks row blocks of rows_cap token rows (live rows per block: *dyn_rows when non-null). Device pointers:
+ * msg bf16 [rows][C]; xb bf16 [rows][2C] (columns [0, C) = shadow of x: read, then rewritten with the new x);
+ * x fp32 [rows][2C] (columns [0, C) in / out); w_merge [C][C], w_mlp0 [2C][2C], w_mlp2 [C][2C] bf16 row-major
+ * ([out][in], the reference's nn.Linear layout); g1 / b1 / g2 / b2 fp32 [C]. C = 256 or 128. `iters` launches back to
+ * back (timing); note that every launch applies the residual update again. */
+int mfr_encoder_tail(const void* msg, void* xb, float* x, const void* w_merge, const void* w_mlp0, const void* w_mlp2,
+                     const float* g1, const float* b1, const float* g2, const float* b2, int C, int n_blocks,
+                     long long rows_cap, const int* dyn_rows, int iters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

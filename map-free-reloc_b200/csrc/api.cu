@@ -6,10 +6,16 @@
 #include "conv_gemm.cuh"
 #include "loftr_engine.cuh"
 #include "loftr_ops.cuh"
+#include "encoder_tail.cuh"
 #include "spsg_engine.cuh"
 #include "geometry_solvers.cuh"
 #include "geometry.cuh"
 #include "descriptor_match.cuh"
+
+namespace mfr {   // metrics.cu
+int pose_metrics(const double* q_gt, const double* t_gt, const double* q_est, const double* t_est, const double* K, int W, int H,
+                 int n, double* trans_err, double* rot_err, double* reproj_err, cudaStream_t st);
+}
 
 extern "C" {
 
@@ -279,6 +285,27 @@ int mfr_linear_attention(const void* q, const void* k, const void* v, void* msg,
   cudaStreamSynchronize(st);
   cudaFree(kv_part); cudaFree(kv);
   return r;
+}
+
+int mfr_pose_metrics(const double* q_gt, const double* t_gt, const double* q_est, const double* t_est, const double* K, int W,
+                     int H, int n, double* trans_err, double* rot_err, double* reproj_err, void* stream) {
+  if (n < 0 || (n > 0 && (!q_gt || !t_gt || !q_est || !t_est || !K || !trans_err || !rot_err || !reproj_err))) return MFR_ERR_ARG;
+  return mfr::pose_metrics(q_gt, t_gt, q_est, t_est, K, W, H, n, trans_err, rot_err, reproj_err, static_cast<cudaStream_t>(stream));
+}
+
+int mfr_encoder_tail(const void* msg, void* xb, float* x, const void* w_merge, const void* w_mlp0, const void* w_mlp2,
+                     const float* g1, const float* b1, const float* g2, const float* b2, int C, int n_blocks,
+                     long long rows_cap, const int* dyn_rows, int iters, void* stream) {
+  if (!msg || !xb || !x || !w_merge || !w_mlp0 || !w_mlp2 || !g1 || !b1 || !g2 || !b2 || iters < 1) return MFR_ERR_ARG;
+  mfr::EncoderTailDesc d{};
+  d.msg = msg; d.ld_msg = C; d.xb_in = xb; d.ld_xb = 2 * C; d.w_merge = w_merge; d.w_mlp0 = w_mlp0; d.w_mlp2 = w_mlp2;
+  d.g1 = g1; d.b1 = b1; d.g2 = g2; d.b2 = b2; d.x = x; d.ldx = 2 * C; d.C = C; d.n_img = n_blocks; d.rows_cap = rows_cap;
+  d.dyn_rows = dyn_rows;
+  mfr::EncoderTailParams p;
+  int rc = mfr::encoder_tail_build(d, &p);
+  if (rc != MFR_OK) return rc;
+  for (int i = 0; i < iters && rc == MFR_OK; ++i) rc = mfr::encoder_tail_launch(p, static_cast<cudaStream_t>(stream));
+  return rc;
 }
 
 }  // extern "C"

@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(kLoThreads) emat_final_kernel(
       // reference-equivalent refit (SURVEY §7 hard part 1(b)): truncated least squares at the RANSAC threshold, i.e. LM
       // on the MSAC cost, whose fixed point is the Sampson least-squares optimum of the model's OWN inlier set — the
       // point the "polished oracle" (OpenCV's mask -> Sampson LM, oracle/pose_solver_oracle.py) sits at.
-      for (int round = 0; round < 2; ++round) emat_lm_round(S, s_pts, N, thr2, 1, true, 8);
+      for (int round = 0; round < 4; ++round) emat_lm_round(S, s_pts, N, thr2, 1, true, 8);
     }
   }
   if (threadIdx.x == 0) essential_from_rt(S.R, S.t, S.E);

@@ -5,6 +5,7 @@
 // transformer -> expectation), for B image pairs per call, channel-last fp32 activations.
 #include "loftr_engine.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -12,6 +13,7 @@
 #include <vector>
 
 #include "conv_gemm.cuh"
+#include "encoder_tail.cuh"
 #include "loftr_ops.cuh"
 
 namespace mfr {
@@ -46,7 +48,8 @@ struct LoftrEngine {
   float thr, temperature;
   int border;
   int splits_kv = 96, splits_col = 32;   // splits_kv is set from the image count in build()
-  int precision = 0;   // 0: fp32 storage / TF32 MMA everywhere; 1: bf16 storage + bf16 MMA in the ResNet-FPN backbone
+  int precision = 0;   // MFR_PRECISION_* (include/mfr_b200.h)
+  bool fused_tail = getenv("MFR_FUSED_TAIL") == nullptr || atoi(getenv("MFR_FUSED_TAIL")) != 0;   // bf16 mode: encoder_tail.cu
   struct Bf16Conv { std::string name; int cout, taps, cin, cin_pad; size_t off; };
   std::vector<Bf16Conv> bf16_convs;
   unsigned short* wblob16 = nullptr;
@@ -188,6 +191,16 @@ struct LoftrEngine {
     infos.push_back(inf);
   }
 
+  // bf16 copy of a GEMM weight [rows][cin] in wblob16 (converted from the fp32 blob by the next forward)
+  const unsigned short* w16(const std::string& wname, int rows, int cin) {
+    for (const auto& e : bf16_convs)
+      if (e.name == wname) return wblob16 + e.off;
+    const size_t off = w16_total;
+    bf16_convs.push_back(Bf16Conv{wname, rows, 1, cin, cin, off});
+    w16_total += (static_cast<size_t>(rows) * cin + 63) / 64 * 64;
+    return wblob16 + off;
+  }
+
   void specs_backbone() {
     add_spec("stem.w", 128 * 49);
     add_spec("stem.b", 128);
@@ -274,10 +287,33 @@ struct LoftrEngine {
         });
       }
     }
-    conv(p + ".merge", msg_x, n, 1, rows, C, C, C, 1, 1, false, nullptr, ACT_NONE, mrg_x, C, 0, dyn_rows, nullptr, nullptr,
-         tbf, 0);
     const float *g1 = W_(p + ".norm1.g"), *b1 = W_(p + ".norm1.b");
     const float *g2 = W_(p + ".norm2.g"), *b2 = W_(p + ".norm2.b");
+    if (tbf && fused_tail) {
+      // merge -> norm1 -> mlp([x | message]) -> norm2 -> residual as ONE kernel: the merge output, the norm1 output, the
+      // 2C-wide hidden tensor and the mlp output never leave the SM (encoder_tail.cu)
+      EncoderTailDesc d{};
+      d.msg = msg_x; d.ld_msg = C; d.xb_in = xb; d.ld_xb = ld2;
+      d.w_merge = w16(p + ".merge", C, C); d.w_mlp0 = w16(p + ".mlp0", 2 * C, 2 * C); d.w_mlp2 = w16(p + ".mlp2", C, 2 * C);
+      d.g1 = g1; d.b1 = b1; d.g2 = g2; d.b2 = b2; d.x = x; d.ldx = ld2; d.C = C;
+      if (dyn_rows) { d.n_img = n; d.rows_cap = rows; d.dyn_rows = dyn_rows; }
+      else { d.n_img = 1; d.rows_cap = static_cast<long long>(n) * rows; d.dyn_rows = nullptr; }
+      EncoderTailParams tp;
+      int rc = encoder_tail_build(d, &tp);
+      if (rc != MFR_OK) { build_rc = rc; return; }
+      steps.push_back([tp](cudaStream_t st) { return encoder_tail_launch(tp, st); });
+      StepInfo inf;
+      inf.name = p + ".tail";
+      inf.kind = 1;
+      inf.dyn_rows = dyn_rows;
+      inf.dyn_images = n;
+      const double per_row = 14.0 * C * C;      // 2 * (C*C + 2C*2C + 2C*C)
+      inf.flops = dyn_rows ? per_row : per_row * n * rows;
+      infos.push_back(inf);
+      return;
+    }
+    conv(p + ".merge", msg_x, n, 1, rows, C, C, C, 1, 1, false, nullptr, ACT_NONE, mrg_x, C, 0, dyn_rows, nullptr, nullptr,
+         tbf, 0);
     const long long tot = static_cast<long long>(n) * rows;
     // norm1(message) is only read by mlp0: in bf16 mode it goes straight to the shadow's message half
     if (dyn_rows == nullptr) {

@@ -57,3 +57,33 @@ def median_pose_errors(table, R_ref, t_ref):
     ang = torch.acos(c.clamp(-1.0, 1.0))
     dt = (t[ok] - tr).norm(dim=1)
     return float(ang.median()), float(dt.median()), int(ok.sum())
+
+
+def run_stream(n_pairs, batch, submit, drain, rank=0, world=1, device="cpu"):
+    """Drives one rank's contiguous block of a stream of ``n_pairs`` pairs through a one-deep pipeline and returns the
+    complete, pair-ordered record table [n_pairs, 14] on every rank (the multi-GPU replacement of the reference's
+    sequential loop, submission.py:36-56 — pairs are independent, so the only collective is the final gather).
+
+    ``submit(ids)`` enqueues one engine batch of exactly ``batch`` pair ids and returns the finished result of the batch
+    submitted one call earlier (``None`` on the first call), ``drain()`` returns the last one; a result is
+    ``(R [batch,3,3], t [batch,3], inliers [batch])`` (``mfr_b200.pipeline.RelocPipeline.submit_host`` / ``drain``).
+    A ragged last batch is padded by repeating its final pair id; the padding rows are dropped again."""
+    a, b = shard_range(n_pairs, rank, world)
+    ids = list(range(a, b))
+    chunks = [ids[k:k + batch] for k in range(0, len(ids), batch)]
+    done, pending = [], []
+    for chunk in chunks:
+        prev = submit(chunk + [chunk[-1]] * (batch - len(chunk)))
+        pending.append(chunk)
+        if prev is not None:
+            done.append((pending.pop(0), prev))
+    if pending:
+        done.append((pending.pop(0), drain()))
+    assert not pending and sum(len(c) for c, _ in done) == len(ids)
+    if done:
+        R = torch.cat([torch.as_tensor(r[0])[: len(c)] for c, r in done]).to(device)
+        t = torch.cat([torch.as_tensor(r[1])[: len(c)] for c, r in done]).to(device)
+        n = torch.cat([torch.as_tensor(r[2])[: len(c)] for c, r in done]).to(device)
+    else:
+        R, t, n = torch.zeros(0, 3, 3, device=device), torch.zeros(0, 3, device=device), torch.zeros(0, dtype=torch.int32, device=device)
+    return gather_records(pack_records(ids, R, t, n), n_pairs)

@@ -122,3 +122,13 @@ class RelocPipeline:
     def drain(self):
         """Result of the last submitted batch (blocks until it is done)."""
         return self._collect(self.i - 1) if self.i >= 1 else None
+
+    def reset(self):
+        """Waits for everything in flight and forgets it: the next submit starts a new stream (returns None)."""
+        for e in self.engines:
+            e.stream.synchronize()
+        self.s_copy.synchronize(); self.s_solve.synchronize()
+        for slot in self.slots:
+            slot["busy"] = False
+            slot["inputs"] = None
+        self.i = 0

@@ -142,11 +142,13 @@ class PoseBackend:
 def required_hypotheses(confidence, inlier_ratio, sample_size):
     """RANSAC stopping rule (what cv2's `confidence` / `prob` argument drives): the number of minimal samples after
     which an all-inlier sample has been drawn with probability `confidence`, given the inlier ratio found."""
-    w = min(max(float(inlier_ratio), 1e-9), 1.0) ** sample_size
+    w = min(max(float(inlier_ratio), 0.0), 1.0) ** sample_size
     if w >= 1.0 - 1e-12:
         return 1
     c = min(max(float(confidence), 0.0), 1.0 - 1e-12)
-    return int(math.ceil(math.log(1.0 - c) / math.log(1.0 - w)))
+    if w < 1e-15:                      # no consensus at all: no finite budget reaches the confidence
+        return 2 ** 31 - 1
+    return int(min(2 ** 31 - 1, math.ceil(math.log(1.0 - c) / -w if w < 1e-8 else math.log(1.0 - c) / math.log1p(-w))))
 
 
 class _SolverBase:
@@ -180,8 +182,8 @@ class _SolverBase:
             yield h
 
     def _satisfied(self, confidence, n_inliers, n_points, budget):
-        if confidence is None or n_points <= 0:
-            return True
+        if confidence is None or n_points <= 0 or n_inliers <= 0:    # nothing found: a larger budget is tried only when
+            return confidence is None or n_points <= 0 or budget >= self.max_hyp   # some remains (and then the NaN pose stands)
         return budget >= required_hypotheses(confidence, n_inliers / float(n_points), self.SAMPLE_SIZE)
 
     def _upload(self, kpts0, kpts1, data):

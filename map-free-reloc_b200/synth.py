@@ -178,3 +178,43 @@ def make_correspondences(seed, n=2000, inlier_ratio=0.5, noise_px=0.5, h=H, w=W,
             depth1[kk1[new_i, 1], kk1[new_i, 0]] = zq[old_i]
         out["depth1"] = depth1
     return out
+
+
+def make_correspondence_points(seed, n=2000, inlier_ratio=0.5, noise_px=0.5, h=H, w=W, K=None):
+    """Correspondence set without images AND without depth maps (BASELINE config C5, essential-matrix cells): the same
+    construction as ``make_correspondences`` — inliers are projections of 3-D points at a smooth depth field, Gaussian
+    pixel noise in image 1, outliers uniform in both images — but the depth field is evaluated only at the sampled
+    pixels, so a cell of 256 sets costs milliseconds. Returns kpts0/kpts1 float32 [n,2], inlier_gt, R_gt, t_gt, K."""
+    rng = np.random.default_rng(seed)
+    K = (K_DEFAULT if K is None else np.asarray(K, dtype=np.float64)).copy()
+    R, t = random_pose(rng)
+    amp = rng.uniform(0.2, 0.8, 4); om = rng.uniform(0.004, 0.02, 4); nu = rng.uniform(0.004, 0.02, 4)
+    ph = rng.uniform(0, 2 * np.pi, 4); ps = rng.uniform(0, 2 * np.pi, 4)
+
+    def depth_at(u, v):
+        d = np.full(u.shape, 3.0)
+        for k in range(4):
+            d += amp[k] * np.sin(om[k] * np.floor(u) + ph[k]) * np.cos(nu[k] * np.floor(v) + ps[k])
+        return np.round(np.clip(d, 1.0, 8.0) * 1000.0) / 1000.0
+
+    n_in = int(round(n * inlier_ratio))
+    Kinv = np.linalg.inv(K)
+    k0 = np.zeros((0, 2)); k1 = np.zeros((0, 2))
+    while len(k0) < n_in:
+        m = 2 * (n_in - len(k0)) + 16
+        u = rng.uniform(2, w - 3, m); v = rng.uniform(2, h - 3, m)
+        X0 = depth_at(u, v)[None] * (Kinv @ np.stack([u, v, np.ones(m)]))
+        X1 = R @ X0 + t[:, None]
+        p = K @ X1
+        u1, v1 = p[0] / p[2], p[1] / p[2]
+        ok = (X1[2] > 0.1) & (u1 >= 2) & (u1 < w - 3) & (v1 >= 2) & (v1 < h - 3)
+        k0 = np.concatenate([k0, np.stack([u, v], 1)[ok]]); k1 = np.concatenate([k1, np.stack([u1, v1], 1)[ok]])
+    k0, k1 = k0[:n_in], k1[:n_in]
+    k1 = k1 + rng.normal(0, noise_px, k1.shape)
+    n_out = n - n_in
+    o0 = np.stack([rng.uniform(0, w - 1, n_out), rng.uniform(0, h - 1, n_out)], 1)
+    o1 = np.stack([rng.uniform(0, w - 1, n_out), rng.uniform(0, h - 1, n_out)], 1)
+    perm = rng.permutation(n)
+    gt = np.concatenate([np.ones(n_in, bool), np.zeros(n_out, bool)])[perm]
+    return {"kpts0": np.concatenate([k0, o0]).astype(np.float32)[perm], "kpts1": np.concatenate([k1, o1]).astype(np.float32)[perm],
+            "inlier_gt": gt, "R_gt": R, "t_gt": t, "K_color0": K.astype(np.float32), "K_color1": K.astype(np.float32)}

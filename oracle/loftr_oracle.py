@@ -154,7 +154,7 @@ def fine_preprocess(ff0, ff1, fc0, fc1, b_ids, i_ids, j_ids, sd, stride, W=5):
     """FinePreprocess.forward, loftr_module/fine_preprocess.py:29-59."""
     cf = ff0.shape[1]
     if b_ids.numel() == 0:
-        e = torch.empty(0, W * W, cf)
+        e = torch.empty(0, W * W, cf, device=ff0.device)
         return e, e
     def unfold(f):
         u = F.unfold(f, kernel_size=(W, W), stride=stride, padding=W // 2)      # [n, c*ww, l]
@@ -174,10 +174,10 @@ def fine_matching(f0, f1, mkpts0_c, mkpts1_c, scale, W=5):
     spatial_expectation2d over a normalised [-1,1] grid restated inline)."""
     M, WW, C = f0.shape
     if M == 0:
-        return mkpts0_c, mkpts1_c, torch.empty(0, 3)
+        return mkpts0_c, mkpts1_c, torch.empty(0, 3, device=f0.device)
     sim = torch.einsum("mc,mrc->mr", f0[:, WW // 2, :], f1)
     heat = torch.softmax(sim / C ** 0.5, dim=1)                                # [M, WW]
-    lin = torch.linspace(-1, 1, W)
+    lin = torch.linspace(-1, 1, W, device=f0.device)
     gx = lin[None, :].expand(W, W).reshape(-1)                                 # x varies fastest
     gy = lin[:, None].expand(W, W).reshape(-1)
     ex = (heat * gx).sum(1)
@@ -199,7 +199,7 @@ def loftr_forward(img0, img1, sd, cfg=None, return_intermediates=False):
     fc, ff = backbone(torch.cat([img0, img1], 0), sd)
     h_c, w_c = fc.shape[2:]
     h_f = ff.shape[2]
-    pe = position_encoding(fc.shape[1], h_c, w_c)
+    pe = position_encoding(fc.shape[1], h_c, w_c).to(fc.device)     # device-agnostic: bench.py also times it on the GPU
     fc = (fc + pe[None]).flatten(2).transpose(1, 2)                            # n (h w) c
     fc0, fc1 = fc[:n], fc[n:]
     ff0, ff1 = ff[:n], ff[n:]

@@ -79,6 +79,38 @@ def sampson_residuals(R, t, k0, k1):
     return num / den
 
 
+def msac_cost(R, t, kpts0, kpts1, K0, K1, pix_threshold):
+    """sum min(Sampson^2, thr^2) / thr^2 over all correspondences: the objective the LO stages minimise."""
+    K0 = np.asarray(K0, dtype=np.float64); K1 = np.asarray(K1, dtype=np.float64)
+    k0, k1 = normalise_kpts(np.asarray(kpts0, np.float64), np.asarray(kpts1, np.float64), K0, K1)
+    thr = ransac_threshold(pix_threshold, K0, K1)
+    r2 = sampson_residuals(R, t, k0, k1) ** 2
+    return float(np.minimum(r2, thr * thr).sum() / (thr * thr))
+
+
+def polish_essential_fixed_point(R, t, kpts0, kpts1, K0, K1, pix_threshold, max_rounds=50):
+    """Extension of ``polish_essential``: alternate (inlier set = Sampson^2 < thr^2 under the current model, the test that
+    produces OpenCV's mask) and (Sampson least squares on that set) from the reference's output until the set stops
+    changing. The fixed point is the model that is the least-squares optimum of its OWN inlier set, i.e. a local minimum
+    of the MSAC cost sum min(r^2, thr^2); which one is reached is decided by the reference's output (the basin it lies
+    in). An independent RANSAC whose final stage minimises the same cost (mfr_emat_ransac with lo_enabled = 3) must land
+    on the same point whenever it ends up in the same basin. Returns (R, t, mask, rounds)."""
+    K0 = np.asarray(K0, dtype=np.float64); K1 = np.asarray(K1, dtype=np.float64)
+    k0, k1 = normalise_kpts(np.asarray(kpts0, np.float64), np.asarray(kpts1, np.float64), K0, K1)
+    thr = ransac_threshold(pix_threshold, K0, K1)
+    Rc, tc = np.asarray(R, np.float64), np.asarray(t, np.float64).ravel()
+    prev = None
+    for rounds in range(1, max_rounds + 1):
+        m = sampson_residuals(Rc, tc, k0, k1) ** 2 < thr * thr
+        if prev is not None and np.array_equal(m, prev):
+            break
+        prev = m
+        if m.sum() < 5:
+            break
+        Rc, tc = polish_essential(Rc, tc, m.astype(np.uint8), kpts0, kpts1, K0, K1)
+    return Rc, tc, prev, rounds
+
+
 def polish_essential(R, t, mask, kpts0, kpts1, K0, K1):
     """The "polished oracle" of SURVEY.md §7 hard part 1(b): the reference solver's output (R, unit t, cheirality
     mask of pose_solver.py:46-60) -> deterministic Levenberg-Marquardt on the Sampson residuals of the reference's

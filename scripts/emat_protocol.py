@@ -25,6 +25,7 @@ if __name__ == "__main__":
         c = synth.make_correspondences(seed, n=n, inlier_ratio=ratio, noise_px=noise)
         Ro, to, no, mo = po.essential_matrix_solver(c["kpts0"], c["kpts1"], c["K_color0"], c["K_color1"], 2.0, 0.9999)
         Rp, tp = po.polish_essential(Ro, to, mo, c["kpts0"], c["kpts1"], c["K_color0"], c["K_color1"])
+        Rf, tf, mf, rounds = po.polish_essential_fixed_point(Ro, to, c["kpts0"], c["kpts1"], c["K_color0"], c["K_color1"], 2.0)
         data = {k: c[k] for k in ("K_color0", "K_color1", "depth0", "depth1")}
         for name, s in solvers.items():
             R, t, ninl = ps.EssentialMatrixSolver.estimate_pose(s, c["kpts0"], c["kpts1"], data)
@@ -32,6 +33,11 @@ if __name__ == "__main__":
             row = {"seed": seed, "n": n, "inlier_ratio": ratio, "noise_px": noise, "refit": name, "hyp": s.last_num_hyp,
                    "mask_iou": round(float((m & mo_).sum() / max(1, (m | mo_).sum())), 4), "inliers": int(ninl), "cv_inliers": int(no),
                    "R_vs_polished_rad": rot_angle(R, Rp), "t_vs_polished_rad": vec_angle(t, tp),
+                   "R_vs_fixed_point_rad": rot_angle(R, Rf), "t_vs_fixed_point_rad": vec_angle(t, tf), "fixed_point_rounds": rounds,
+                   "fixed_point_R_err_gt": rot_angle(Rf, c["R_gt"]), "fixed_point_t_err_gt": vec_angle(tf, c["t_gt"]),
+                   "msac_cost": po.msac_cost(R, t, c["kpts0"], c["kpts1"], c["K_color0"], c["K_color1"], 2.0),
+                   "fixed_point_msac_cost": po.msac_cost(Rf, tf, c["kpts0"], c["kpts1"], c["K_color0"], c["K_color1"], 2.0),
+                   "cv_msac_cost": po.msac_cost(Ro, to, c["kpts0"], c["kpts1"], c["K_color0"], c["K_color1"], 2.0),
                    "R_vs_raw_rad": rot_angle(R, Ro), "t_vs_raw_rad": vec_angle(t, to),
                    "R_err_gt": rot_angle(R, c["R_gt"]), "t_err_gt": vec_angle(t, c["t_gt"]),
                    "cv_R_err_gt": rot_angle(Ro, c["R_gt"]), "cv_t_err_gt": vec_angle(to, c["t_gt"]),

@@ -71,7 +71,12 @@ def test_emat_vs_oracle_and_ground_truth(solvers, seed, n, ratio, noise):
     R, t, ninl = solvers[0].estimate_pose(c["kpts0"], c["kpts1"], _data(c))
     assert t.shape == (3,) and abs(np.linalg.norm(t) - 1) < 1e-5
     m = solvers[0].mask.ravel().astype(bool); mo = mo.ravel().astype(bool)
-    assert (m & mo).sum() / (m | mo).sum() >= 0.9                  # inlier-mask IoU
+    # leg (a) of the protocol, SURVEY target 0.98 (measured 0.996-0.998, profiles/r02_emat_protocol.txt). Seed 44 (40 %
+    # inliers): OpenCV stops at 1172 of the ~1210 inliers its own threshold admits, so there the bar is on its recall
+    if seed == 44:
+        assert (m & mo).sum() / mo.sum() >= 0.98 and m.sum() >= mo.sum()
+    else:
+        assert (m & mo).sum() / (m | mo).sum() >= 0.98             # inlier-mask IoU
     assert rot_angle(R, c["R_gt"]) <= rot_angle(Ro, c["R_gt"]) + 1e-3
     assert vec_angle(t, c["t_gt"]) <= vec_angle(to, c["t_gt"]) + 1e-3
     Rm, tm, nm = solvers[1].estimate_pose(c["kpts0"], c["kpts1"], _data(c))
@@ -79,6 +84,27 @@ def test_emat_vs_oracle_and_ground_truth(solvers, seed, n, ratio, noise):
                                                       c["K_color0"], c["K_color1"], 2.0, 0.9999, 0.1)
     assert tm.shape == (3, 1)
     assert np.linalg.norm(tm.ravel() - c["t_gt"]) <= np.linalg.norm(tmo.ravel() - c["t_gt"]) + 1e-3
+
+
+@pytest.mark.parametrize("seed,n,ratio,noise", [(41, 1000, 0.6, 0.3), (42, 2000, 0.5, 0.5), (43, 800, 0.7, 0.2), (44, 3000, 0.4, 0.5),
+                                                (45, 5000, 0.5, 0.5), (46, 1500, 0.8, 0.1), (47, 600, 0.5, 1.0)])
+def test_emat_polished_oracle_leg(solvers, seed, n, ratio, noise):
+    """Leg (b) of the protocol (SURVEY §7 hard part 1): the reference's output polished to the least-squares optimum of
+    its own inlier set, iterated to the fixed point (oracle.polish_essential_fixed_point = a local minimum of the MSAC
+    cost in the basin of OpenCV's output). The GPU solver's final stage minimises the same cost; it must either sit on
+    that fixed point (1e-3 rad in R and in the direction of t) or on another local minimum of (nearly) the same or lower
+    cost — the truncated least-squares cost is not convex and the two RANSACs do not always end in the same basin."""
+    c = synth.make_correspondences(seed, n=n, inlier_ratio=ratio, noise_px=noise)
+    Ro, to, no, mo = po.essential_matrix_solver(c["kpts0"], c["kpts1"], c["K_color0"], c["K_color1"], 2.0, 0.9999)
+    Rf, tf, mf, rounds = po.polish_essential_fixed_point(Ro, to, c["kpts0"], c["kpts1"], c["K_color0"], c["K_color1"], 2.0)
+    R, t, ninl = solvers[0].estimate_pose(c["kpts0"], c["kpts1"], _data(c))
+    cost = po.msac_cost(R, t, c["kpts0"], c["kpts1"], c["K_color0"], c["K_color1"], 2.0)
+    cost_f = po.msac_cost(Rf, tf, c["kpts0"], c["kpts1"], c["K_color0"], c["K_color1"], 2.0)
+    same_point = rot_angle(R, Rf) < 1e-3 and vec_angle(t, tf) < 1e-3
+    # measured (profiles/r02_emat_protocol.txt): 3 of 7 cases sit on the polished reference's fixed point (< 3e-5 rad), 3 on
+    # a lower local minimum, and seed 43 on one whose cost is 0.45 % higher (while 10x closer to ground truth)
+    assert same_point or cost < cost_f * 1.01, (rot_angle(R, Rf), vec_angle(t, tf), cost, cost_f)
+    assert cost < po.msac_cost(Ro, to, c["kpts0"], c["kpts1"], c["K_color0"], c["K_color1"], 2.0)   # always better than raw OpenCV
 
 
 @pytest.mark.parametrize("seed,n,ratio", [(51, 600, 0.8), (52, 1500, 0.6)])
