@@ -256,6 +256,19 @@ float mfr_debug_time_conv(const float* x, int N, int H, int W, int Cin, const fl
 int mfr_linear_attention(const void* q, const void* k, const void* v, void* msg, int n, int L, int S, int windows,
                          int bf16, void* stream);
 
+/* Input path on the GPU. mfr_jpeg_info / mfr_jpeg_decode: nvJPEG decode of a JPEG held in HOST
+ * memory into a DEVICE uint8 image — rgb = 0: the luma plane [h][w] (cv2.imread(IMREAD_GRAYSCALE) of a JPEG,
+ * SuperGlue/models/utils.py:264), rgb = 1: interleaved RGB [h][w][3] (lib/datasets/utils.py:67 imread).
+ * mfr_resize_linear: cv2.resize(INTER_LINEAR) + scale on the device, dst fp32 [dst_h][dst_w][channels] (chw = 0) or
+ * [channels][dst_h][dst_w] (chw = 1) = resized * out_scale. mode 0: float source, float arithmetic; mode 1: uint8 source
+ * converted to float first (read_image with resize_float = True, utils.py:272-273: the FMB matcher plugins);
+ * mode 2: uint8 source, OpenCV's 11-bit fixed-point uint8 path, rounded to uint8 before the scale (utils.py:275,
+ * lib/datasets/utils.py:68). src_row_stride in elements. */
+int mfr_jpeg_info(const unsigned char* data, long long length, int* width, int* height, int* components);
+int mfr_jpeg_decode(const unsigned char* data, long long length, int rgb, unsigned char* dst, int width, int height, void* stream);
+int mfr_resize_linear(const void* src, int src_is_u8, int src_w, int src_h, long long src_row_stride, int channels, float* dst,
+                      int dst_w, int dst_h, int mode, float out_scale, int chw, void* stream);
+
 /* Leaderboard metrics of the Map-free benchmark for n poses (benchmark/metrics.py:40-67, benchmark/utils.py:95-129 sine
  * variant, benchmark/reprojection.py:7-86): device double arrays q_gt/q_est [n][4] (w, x, y, z), t_gt/t_est [n][3],
  * K [n][9]; image size W x H. Out: trans_err [n] (m), rot_err [n] (degrees), reproj_err [n] (VCRE, pixels). */

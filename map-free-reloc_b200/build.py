@@ -55,7 +55,7 @@ def build(force=False, verbose=True):
                     print(os.path.basename(src), line.strip())
     if not ok:
         raise RuntimeError("nvcc failed")
-    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT, *objs, "-lcudart"]
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT, *objs, "-lcudart", "-lnvjpeg"]
     subprocess.check_call(cmd)
     return OUT
 

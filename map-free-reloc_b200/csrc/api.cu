@@ -2,6 +2,7 @@
 #include "../../include/mfr_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "conv_gemm.cuh"
 #include "loftr_engine.cuh"
@@ -12,6 +13,12 @@
 #include "geometry.cuh"
 #include "descriptor_match.cuh"
 
+namespace mfr {   // image_io.cu
+int resize_linear(const void* src, int src_is_u8, int sw, int sh, long long src_stride, int channels, float* dst, int dw, int dh,
+                  int mode, float out_scale, int chw, cudaStream_t st);
+int jpeg_info(const unsigned char* data, size_t length, int* width, int* height, int* components);
+int jpeg_decode(const unsigned char* data, size_t length, int rgb, unsigned char* dst, int width, int height, cudaStream_t st);
+}
 namespace mfr {   // metrics.cu
 int pose_metrics(const double* q_gt, const double* t_gt, const double* q_est, const double* t_est, const double* K, int W, int H,
                  int n, double* trans_err, double* rot_err, double* reproj_err, cudaStream_t st);
@@ -287,6 +294,20 @@ int mfr_linear_attention(const void* q, const void* k, const void* v, void* msg,
   return r;
 }
 
+int mfr_resize_linear(const void* src, int src_is_u8, int src_w, int src_h, long long src_row_stride, int channels, float* dst,
+                      int dst_w, int dst_h, int mode, float out_scale, int chw, void* stream) {
+  return mfr::resize_linear(src, src_is_u8, src_w, src_h, src_row_stride, channels, dst, dst_w, dst_h, mode, out_scale, chw,
+                            static_cast<cudaStream_t>(stream));
+}
+int mfr_jpeg_info(const unsigned char* data, long long length, int* width, int* height, int* components) {
+  if (!data || length <= 0 || !width || !height || !components) return MFR_ERR_ARG;
+  return mfr::jpeg_info(data, static_cast<size_t>(length), width, height, components);
+}
+int mfr_jpeg_decode(const unsigned char* data, long long length, int rgb, unsigned char* dst, int width, int height, void* stream) {
+  if (!data || length <= 0 || !dst) return MFR_ERR_ARG;
+  return mfr::jpeg_decode(data, static_cast<size_t>(length), rgb, dst, width, height, static_cast<cudaStream_t>(stream));
+}
+
 int mfr_pose_metrics(const double* q_gt, const double* t_gt, const double* q_est, const double* t_est, const double* K, int W,
                      int H, int n, double* trans_err, double* rot_err, double* reproj_err, void* stream) {
   if (n < 0 || (n > 0 && (!q_gt || !t_gt || !q_est || !t_est || !K || !trans_err || !rot_err || !reproj_err))) return MFR_ERR_ARG;
@@ -305,6 +326,26 @@ int mfr_encoder_tail(const void* msg, void* xb, float* x, const void* w_merge, c
   int rc = mfr::encoder_tail_build(d, &p);
   if (rc != MFR_OK) return rc;
   for (int i = 0; i < iters && rc == MFR_OK; ++i) rc = mfr::encoder_tail_launch(p, static_cast<cudaStream_t>(stream));
+  if (rc == MFR_OK && getenv("MFR_TAIL_DEBUG") != nullptr) {   // timeline of block 0 (one extra launch)
+    long long* d = nullptr;
+    cudaMalloc(&d, 192 * sizeof(long long));
+    cudaMemset(d, 0, 192 * sizeof(long long));
+    p.dbg = d;
+    mfr::encoder_tail_launch(p, static_cast<cudaStream_t>(stream));
+    cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    long long h[192];
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    long long t0 = 0;
+    for (int r = 0; r < 3; ++r)
+      if (h[r * 64 + 1] && (t0 == 0 || h[r * 64 + 1] < t0)) t0 = h[r * 64 + 1];
+    const char* names[3] = {"mma", "epi", "tma"};
+    for (int r = 0; r < 3; ++r) {
+      fprintf(stderr, "[encoder_tail C=%d %s]", C, names[r]);
+      for (int k = 0; k < 32 && h[r * 64 + 2 * k + 1]; ++k) fprintf(stderr, " %lld@%lld", h[r * 64 + 2 * k], h[r * 64 + 2 * k + 1] - t0);
+      fprintf(stderr, "\n");
+    }
+  }
   return rc;
 }
 

@@ -20,8 +20,9 @@
 //   warp 0     TMA producer: the ring items in exactly the order the MMA warp consumes them
 //   warp 1     MMA issuer  : GEMM1; then GEMM2 chunk q+1 is issued BEFORE GEMM3 chunk q, so the tensor pipe runs the
 //                            next chunk while the epilogue warps turn chunk q into the bf16 A operand of GEMM3
-//   warps 2-5  epilogue, thread = row: LayerNorm1 (TMEM -> registers -> swizzled smem), relu + bf16 (TMEM -> smem),
-//              LayerNorm2 + residual (TMEM -> staging -> coalesced fp32 store of x and its bf16 shadow)
+//   warps 2-9  epilogue, thread = row, two warps per TMEM lane quadrant splitting the 32-column chunks: LayerNorm1
+//              (TMEM -> registers -> swizzled smem), relu + bf16 (TMEM -> smem), LayerNorm2 + residual (TMEM -> staging ->
+//              coalesced fp32 store of x and its bf16 shadow; the residual rows are prefetched a chunk ahead)
 //
 // The hidden layer is produced and consumed in 128-column chunks because GEMM3 accumulates over exactly those
 // columns: D3 += relu(D2_q) @ W2[:, q]^T can start as soon as chunk q exists, and 2C-wide rows never exist anywhere.
@@ -38,7 +39,8 @@ namespace mfr {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;          // two per TMEM lane quadrant: the pair splits the 32-column chunks of a phase (even / odd)
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kRelBatch = 3;        // ring slots handed back per tcgen05.commit batch
 constexpr int kKbBytes = 16384;     // one k-block of an A operand: [128 rows x 64 bf16], 128B-swizzled
 constexpr int kTmemCols = 512;
@@ -83,12 +85,22 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
   auto d13_empty = [&](int b) { return m_full + 80 + 8u * b; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int dbg_n = 0;
+  auto stamp = [&](int role, int id) {           // debug timeline of block 0 (first 32 events per role)
+    if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && dbg_n < 32) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.dbg[role * 64 + 2 * dbg_n] = id;
+      p.dbg[role * 64 + 2 * dbg_n + 1] = t;
+      ++dbg_n;
+    }
+  };
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmMsg); tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmWm); tma_prefetch_desc(&p.tmW0); tma_prefetch_desc(&p.tmW2);
     for (int s = 0; s < 2 * NS; ++s) mbar_init(bb + 8u * s, 1);
-    mbar_init(m_full, 1); mbar_init(d1_full, 1); mbar_init(ln1_ready, 4); mbar_init(d3_full, 1);
+    mbar_init(m_full, 1); mbar_init(d1_full, 1); mbar_init(ln1_ready, kEpiWarps); mbar_init(d3_full, 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(d2_full(b), 1); mbar_init(h1_full(b), 4); mbar_init(h1_empty(b), 1); mbar_init(d13_empty(b), 4);
+      mbar_init(d2_full(b), 1); mbar_init(h1_full(b), kEpiWarps); mbar_init(h1_empty(b), 1); mbar_init(d13_empty(b), kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -128,6 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       int rin;
       const int row0 = static_cast<int>(tile_row0(tile, rin));
+      stamp(2, tile);
       for (int kb = 0; kb < KB; ++kb) {                         // GEMM1: message k-block + merge weights
         put(&p.tmMsg, kb * 64, row0);
         for (int h = 0; h < NH; ++h) put(&p.tmWm, kb * 64, h * 128);
@@ -187,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
       const uint32_t d13 = tmem_base + static_cast<uint32_t>(par * G::D13_STRIDE);
       const uint32_t d2b = tmem_base + static_cast<uint32_t>(C == 256 ? (1 - par) * 256 : 256);
       if (it >= 2) mbar_wait(d13_empty(par), ((it >> 1) - 1) & 1, 21);   // LayerNorm2 of tile it-2 has read these columns
+      stamp(0, 100 * it);
       // ---- GEMM1: D13 = message @ Wm^T
       for (int kb = 0; kb < KB; ++kb) {
         const uint32_t a = take();
@@ -199,6 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
         if (n_unrel >= kRelBatch) flush(0);
       }
       flush(d1_full);
+      stamp(0, 100 * it + 1);
       if (C == 256 && it >= 1) mbar_wait(d13_empty(1 - par), ((it - 1) >> 1) & 1, 24);   // D2 columns = D13 of the previous tile
       bool ln_ok = false;
       auto g2 = [&](int q) {
@@ -217,6 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
           if (n_unrel >= kRelBatch && kb != 2 * KB - 1) flush(0);
         }
         flush(d2_full(q & 1));
+        stamp(0, 100 * it + 10 + q);
       };
       auto g3 = [&](int q) {
         const int u = it * (NQ / 2) + (q >> 1);                  // use index of H1 buffer q & 1
@@ -230,6 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
           }
         flush(q == NQ - 1 ? 0u : h1_empty(q & 1));
         if (q == NQ - 1 && elect_one_sync()) { tc_commit(h1_empty(q & 1)); tc_commit(d3_full); }
+        stamp(0, 100 * it + 20 + q);
       };
       g2(0);
       for (int q = 1; q < NQ; ++q) { g2(q); g3(q - 1); }
@@ -245,9 +262,17 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
     // part of L no other warp writes (a faster warp may already be in LayerNorm1 of the next tile). 32 rows x 32 floats,
     // 16-byte chunk j of row i stored at chunk position j ^ (i & 7): conflict-free for the row-wise writes and the
     // transposed reads alike.
-    float* stg = reinterpret_cast<float*>(smem_raw + (sL - smem_u32(smem_raw))) + q4 * 1024;
+    // The two warps of a quadrant (half = 0 / 1) own the same 32 rows and alternate the 32-column chunks. Their private
+    // scratch lives in the rows of region L that only this pair ever writes: the staging tile of warp `half` in its rows
+    // of k-block `half`, the statistics exchange (8 bytes per row and half) at the start of its rows of k-block 0 — read
+    // and overwritten only between two pair barriers.
+    const int half = (warp - 2) >> 2;
+    float* stg = reinterpret_cast<float*>(smem_raw + (sL - smem_u32(smem_raw))) + half * (kKbBytes / 4) + q4 * 1024;
+    float* exch = reinterpret_cast<float*>(smem_raw + (sL - smem_u32(smem_raw))) + q4 * 1024 + lane * 32;   // this row's 128 bytes in k-block 0
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q4) : "memory"); };
     const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
-    const float inv_c = 1.f / static_cast<float>(C);
+    constexpr int kHalfCols = C / 2;
+    const float inv_h = 1.f / static_cast<float>(kHalfCols);
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int par = it & 1;
@@ -256,13 +281,15 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
       const uint32_t d13 = tmem_base + static_cast<uint32_t>(par * G::D13_STRIDE) + lane_off;
       const uint32_t d2b = tmem_base + static_cast<uint32_t>(C == 256 ? (1 - par) * 256 : 256) + lane_off;
       // row statistics of a [128 x C] accumulator in one pass: sums of (v - v0), v0 = the row's first element
+      // (v - v0 with v0 = the first element this warp sees), over this warp's chunks; the two halves are merged with the
+      // pairwise-variance formula (equal counts): mean = (m0 + m1) / 2, M2 = M2_0 + M2_1 + (m0 - m1)^2 * n / 2, n = C / 2
       auto row_stats = [&](uint32_t acc, float& mean, float& rstd) {
         float v0 = 0.f, s1 = 0.f, s2 = 0.f;
-        for (int c0 = 0; c0 < C; c0 += 32) {
+        for (int c0 = 32 * half; c0 < C; c0 += 64) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(acc + static_cast<uint32_t>(c0), v);
           tmem_ld_wait();
-          if (c0 == 0) v0 = __uint_as_float(v[0]);
+          if (c0 == 32 * half) v0 = __uint_as_float(v[0]);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float d = __uint_as_float(v[j]) - v0;
@@ -270,26 +297,37 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
             s2 = fmaf(d, d, s2);
           }
         }
-        const float md = s1 * inv_c;
-        mean = v0 + md;
-        rstd = rsqrtf(fmaxf(fmaf(-md, md, s2 * inv_c), 0.f) + 1e-5f);
+        const float md = s1 * inv_h;
+        const float m_own = v0 + md, M2_own = fmaxf(fmaf(-md, s1, s2), 0.f);      // sum (v - m_own)^2 = s2 - s1^2 / n
+        exch[2 * half] = m_own;
+        exch[2 * half + 1] = M2_own;
+        pair_sync();
+        const float m_oth = exch[2 * (1 - half)], M2_oth = exch[2 * (1 - half) + 1];
+        pair_sync();                                   // both have read: the rows may be overwritten from here on
+        const float dm = m_own - m_oth;
+        mean = 0.5f * (m_own + m_oth);
+        rstd = rsqrtf((M2_own + M2_oth + dm * dm * (0.5f * kHalfCols)) * (1.f / static_cast<float>(C)) + 1e-5f);
       };
       // ---- E1: LayerNorm1 of the merge output -> bf16 A operand (region L)
       mbar_wait(d1_full, it & 1, 31);
       tc_fence_after();
+      if (warp == 2) stamp(1, 100 * it + 1);
       {
         float mean, rstd;
         row_stats(d13, mean, rstd);
-        for (int c0 = 0; c0 < C; c0 += 32) {
+        for (int c0 = 32 * half; c0 < C; c0 += 64) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(d13 + static_cast<uint32_t>(c0), v);
           tmem_ld_wait();
           uint32_t o[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = fmaf((__uint_as_float(v[2 * j]) - mean) * rstd, __ldg(p.g1 + c0 + 2 * j), __ldg(p.b1 + c0 + 2 * j));
-            const float b = fmaf((__uint_as_float(v[2 * j + 1]) - mean) * rstd, __ldg(p.g1 + c0 + 2 * j + 1), __ldg(p.b1 + c0 + 2 * j + 1));
-            o[j] = pack_bf16x2(a, b);
+          for (int j = 0; j < 8; ++j) {                           // the same 4 gammas / betas for every lane: broadcast 16-byte loads
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.g1 + c0) + j);
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.b1 + c0) + j);
+            o[2 * j] = pack_bf16x2(fmaf((__uint_as_float(v[4 * j]) - mean) * rstd, g.x, bt.x),
+                                   fmaf((__uint_as_float(v[4 * j + 1]) - mean) * rstd, g.y, bt.y));
+            o[2 * j + 1] = pack_bf16x2(fmaf((__uint_as_float(v[4 * j + 2]) - mean) * rstd, g.z, bt.z),
+                                       fmaf((__uint_as_float(v[4 * j + 3]) - mean) * rstd, g.w, bt.w));
           }
           const uint32_t rowa = sL + (c0 >> 6) * kKbBytes + r * 128;
           const uint32_t cc0 = static_cast<uint32_t>((c0 & 63) >> 3);
@@ -302,6 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(ln1_ready);
+        if (warp == 2) stamp(1, 100 * it + 2);
       }
       // ---- E2: relu + bf16 of hidden chunk q -> H1 buffer q & 1 (A operand of GEMM3)
       for (int q = 0; q < NQ; ++q) {
@@ -310,8 +349,9 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
         mbar_wait(d2_full(b), u & 1, 32);
         tc_fence_after();
         if (u >= 1) mbar_wait(h1_empty(b), (u - 1) & 1, 33);   // GEMM3 of the previous use of this buffer has read it
+        if (warp == 2) stamp(1, 100 * it + 10 + q);
         const uint32_t acc = d2b + static_cast<uint32_t>(b * 128);
-        for (int c0 = 0; c0 < 128; c0 += 32) {
+        for (int c0 = 32 * half; c0 < 128; c0 += 64) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(acc + static_cast<uint32_t>(c0), v);
           tmem_ld_wait();
@@ -330,25 +370,39 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(h1_full(b));
+        if (warp == 2) stamp(1, 100 * it + 20 + q);
       }
       // ---- E3: x += LayerNorm2(mlp.2 output); fp32 x and its bf16 shadow, coalesced through a per-warp staging tile
       mbar_wait(d3_full, it & 1, 34);
       tc_fence_after();
+      if (warp == 2) stamp(1, 100 * it + 30);
       {
+        // the residual rows of a chunk are requested one chunk ahead of their use (the first before the statistics pass):
+        // 8 independent 16-byte loads in flight per lane instead of one DRAM round trip per store
+        const long long grow0 = row0 + q4 * 32;                  // first row of this warp
+        const bool ok = rin + r < live;
+        uint32_t okm = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) okm |= (__shfl_sync(0xffffffffu, ok ? 1 : 0, k * 4 + sub_r) ? 1u : 0u) << k;
+        float4 xn[8];
+        auto load_res = [&](int c0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            xn[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((okm >> k) & 1u) xn[k] = *reinterpret_cast<const float4*>(p.x + (grow0 + k * 4 + sub_r) * p.ldx + c0 + sub_c);
+          }
+        };
+        load_res(32 * half);
         float mean, rstd;
         row_stats(d13, mean, rstd);
-        const bool ok = rin + r < live;
         float mk[8], rk[8];
-        uint32_t okm = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int rr = k * 4 + sub_r;
           mk[k] = __shfl_sync(0xffffffffu, mean, rr);
           rk[k] = __shfl_sync(0xffffffffu, rstd, rr);
-          okm |= (__shfl_sync(0xffffffffu, ok ? 1 : 0, rr) ? 1u : 0u) << k;
         }
-        const long long grow0 = row0 + q4 * 32;                  // first row of this warp
-        for (int c0 = 0; c0 < C; c0 += 32) {
+        for (int c0 = 32 * half; c0 < C; c0 += 64) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(d13 + static_cast<uint32_t>(c0), v);
           tmem_ld_wait();
@@ -358,13 +412,17 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
           __syncwarp();
           const float4 g = __ldg(reinterpret_cast<const float4*>(p.g2 + c0 + sub_c));
           const float4 bt = __ldg(reinterpret_cast<const float4*>(p.b2 + c0 + sub_c));
+          float4 xc[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) xc[k] = xn[k];
+          if (c0 + 64 < C) load_res(c0 + 64);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             if (!((okm >> k) & 1u)) continue;
             const int rr = k * 4 + sub_r;
             const float4 a = *reinterpret_cast<const float4*>(stg + rr * 32 + (((sub_c >> 2) ^ (rr & 7)) << 2));
             float* xr = p.x + (grow0 + rr) * p.ldx + c0 + sub_c;
-            const float4 xo = *reinterpret_cast<const float4*>(xr);
+            const float4 xo = xc[k];
             float4 o;
             o.x = xo.x + fmaf((a.x - mk[k]) * rk[k], g.x, bt.x);
             o.y = xo.y + fmaf((a.y - mk[k]) * rk[k], g.y, bt.y);
@@ -378,6 +436,8 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(d13_empty(par));
+        pair_sync();      // the partner's staging tile / this pair's exchange rows are rewritten by the next tile's LayerNorm1
+        if (warp == 2) stamp(1, 100 * it + 31);
       }
     }
   }
@@ -441,6 +501,7 @@ int encoder_tail_build(const EncoderTailDesc& d, EncoderTailParams* p) {
   p->x = d.x; p->xb = static_cast<unsigned short*>(const_cast<void*>(d.xb_in));
   p->ldx = d.ldx; p->ld_xb = d.ld_xb;
   p->C = d.C; p->n_img = d.n_img; p->rows_cap = d.rows_cap; p->dyn_rows = d.dyn_rows;
+  p->dbg = nullptr;
   return MFR_OK;
 }
 

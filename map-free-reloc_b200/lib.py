@@ -78,6 +78,9 @@ SIGNATURES = {
     "mfr_pnp_ransac": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int,
                                c_float, ctypes.c_ulonglong, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mfr_linear_attention": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "mfr_jpeg_info": (c_int, [c_vp, c_ll, c_vp, c_vp, c_vp]),
+    "mfr_jpeg_decode": (c_int, [c_vp, c_ll, c_int, c_vp, c_int, c_int, c_vp]),
+    "mfr_resize_linear": (c_int, [c_vp, c_int, c_int, c_int, c_ll, c_int, c_vp, c_int, c_int, c_int, c_float, c_int, c_vp]),
     "mfr_pose_metrics": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "mfr_encoder_tail": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_vp, c_int, c_vp]),
     "mfr_debug_probe_overhead": (c_float, [c_int, c_int, c_int, c_int]),

@@ -460,9 +460,15 @@ class LoFTR_matcher:
         self.engine = LoFTR(weights, batch=1, height=self.hp, width=self.wp, cfg=cfg)
 
     def match(self, pair_path):
-        im0 = read_image_gray(pair_path[0], self.resize)
-        im1 = read_image_gray(pair_path[1], self.resize)
-        return self.match_arrays(im0, im1)
+        """matchers.py:24-59: both images through read_image(path, device, resize, 0, True) — here decoded (JPEG: nvJPEG)
+        and resized on the GPU (mfr_b200.image_io)."""
+        from . import image_io
+        im0 = image_io.read_image(pair_path[0], self.resize, True, self.engine.device)
+        im1 = image_io.read_image(pair_path[1], self.resize, True, self.engine.device)
+        out = self.engine.forward(im0[None], im1[None])
+        if out["M"] > 0:
+            return torch.cat([out["mkpts0_f"], out["mkpts1_f"]], 1).cpu().numpy()
+        return np.full((1, 4), np.nan)
 
     def match_arrays(self, im0, im1):
         dev = self.engine.device

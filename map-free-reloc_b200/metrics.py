@@ -40,13 +40,13 @@ def precision_recall(inliers, tp, failures):
     thr = torch.cat([distinct, torch.tensor([N - 1], device=inl.device)])
     rec_all = torch.arange(1, N + 1, dtype=torch.float32, device=inl.device)
     prec = (torch.cumsum(tp, 0)[thr] / rec_all[thr].to(torch.float64))
-    rec = (rec_all[thr] / (float(N) + float(failures))).to(torch.float64)
+    rec = rec_all[thr] / torch.tensor(float(N) + float(failures), dtype=torch.float32, device=inl.device)   # float32, like numpy's
     last = int(torch.searchsorted(rec, rec[-1:].contiguous()).item())
     idx = torch.arange(last, -1, -1, device=inl.device)
     prec = torch.cat([prec[idx], torch.ones(1, dtype=torch.float64, device=inl.device)])
-    rec = torch.cat([rec[idx], torch.zeros(1, dtype=torch.float64, device=inl.device)])
-    ap = float(torch.abs(torch.sum((rec[1:] - rec[:-1]) * prec[:-1])).item())
-    return prec, rec, ap
+    rec = torch.cat([rec[idx], torch.zeros(1, dtype=torch.float32, device=inl.device)])
+    ap = float(torch.abs(torch.sum((rec[1:] - rec[:-1]).to(torch.float64) * prec[:-1])).item())    # np.diff in float32
+    return prec, rec.to(torch.float64), ap
 
 
 def aggregate_results(all_results, all_failures):

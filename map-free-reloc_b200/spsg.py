@@ -247,13 +247,19 @@ class SuperGlue_matcher:
         self.engine = SuperPointSuperGlue(sp, sg, batch=1, height=int(resize[1]), width=int(resize[0]))
 
     def match(self, pair_path):
-        from .loftr import read_image_gray
-        return self.match_arrays(read_image_gray(pair_path[0], self.resize), read_image_gray(pair_path[1], self.resize))
+        """matchers.py:93-120; images decoded (JPEG: nvJPEG) and resized on the GPU (mfr_b200.image_io)."""
+        from . import image_io
+        dev = self.engine.device
+        return self._result(self.engine.forward(image_io.read_image(pair_path[0], self.resize, True, dev)[None],
+                                                image_io.read_image(pair_path[1], self.resize, True, dev)[None]))
 
     def match_arrays(self, im0, im1):
         dev = self.engine.device
-        o = self.engine.forward(torch.from_numpy(np.ascontiguousarray(im0, dtype=np.float32))[None].to(dev),
-                                torch.from_numpy(np.ascontiguousarray(im1, dtype=np.float32))[None].to(dev))
+        return self._result(self.engine.forward(torch.from_numpy(np.ascontiguousarray(im0, dtype=np.float32))[None].to(dev),
+                                                torch.from_numpy(np.ascontiguousarray(im1, dtype=np.float32))[None].to(dev)))
+
+    @staticmethod
+    def _result(o):
         m = int(o["m_offsets"][1].item())
         if m > 0:
             return torch.cat([o["mkpts0"][:m], o["mkpts1"][:m]], 1).cpu().numpy()
