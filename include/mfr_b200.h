@@ -220,7 +220,7 @@ int mfr_pnp_ransac(mfr_pose_solver* s, const float* kpts0, const float* kpts1, c
 /* ProcrustesSolver.estimate_pose with REFINE = False (pose_solver.py:247-320): lift both keypoint sets
  * through their depth maps (valid iff depth > depth.min() on both sides), RANSAC over 3-point Kabsch
  * alignments with inlier distance max_corr_dist (metres), refit on the inliers. The reference calls
- * Open3D's registration_ransac_based_on_correspondence for this step. */
+ * Open3D's registration_ransac_based_on_correspondence for this step; REFINE = True continues with mfr_icp_refine. */
 int mfr_procrustes_ransac(mfr_pose_solver* s, const float* kpts0, const float* kpts1, const int* offsets,
                           int P, const float* K0, const float* K1, const float* depth0,
                           const float* depth1, int H, int W, int num_hyp, float max_corr_dist,
@@ -255,6 +255,15 @@ float mfr_debug_time_conv(const float* x, int N, int H, int W, int Cin, const fl
  * bf16 = 1: all four tensors are bf16 (the tensor-core kernels), else fp32. Device pointers, dense rows. */
 int mfr_linear_attention(const void* q, const void* k, const void* v, void* msg, int n, int L, int S, int windows,
                          int bf16, void* stream);
+
+/* ProcrustesSolver's ICP refinement (PROCRUSTES.REFINE, pose_solver.py:289-315: Open3D registration_icp, point-to-point,
+ * correspondence radius max_corr_dist, criteria relative_fitness / relative_rmse / max_iterations = 1e-4 / 1e-4 / 30 in the
+ * reference) of the poses (R_in, t_in) [P][9] / [P][3] over the FULL clouds of both depth maps (every pixel with depth > 0),
+ * device float [P][H][W]. Nearest neighbours are exact within the radius (bounded window search in the organised target
+ * cloud). n_inliers = int(fitness * valid target points), the reference's return value (pose_solver.py:319). */
+int mfr_icp_refine(mfr_pose_solver* s, const float* depth0, const float* depth1, int H, int W, int P, const float* K0,
+                   const float* K1, const float* R_in, const float* t_in, float max_corr_dist, int max_iterations,
+                   float relative_fitness, float relative_rmse, float* R, float* t, int* n_inliers, void* stream);
 
 /* Input path on the GPU. mfr_jpeg_info / mfr_jpeg_decode: nvJPEG decode of a JPEG held in HOST
  * memory into a DEVICE uint8 image — rgb = 0: the luma plane [h][w] (cv2.imread(IMREAD_GRAYSCALE) of a JPEG,

@@ -294,6 +294,14 @@ int mfr_linear_attention(const void* q, const void* k, const void* v, void* msg,
   return r;
 }
 
+int mfr_icp_refine(mfr_pose_solver* s, const float* depth0, const float* depth1, int H, int W, int P, const float* K0,
+                   const float* K1, const float* R_in, const float* t_in, float max_corr_dist, int max_iterations,
+                   float relative_fitness, float relative_rmse, float* R, float* t, int* n_inliers, void* stream) {
+  if (!s || !depth0 || !depth1 || !K0 || !K1 || !R_in || !t_in || !R || !t || !n_inliers) return MFR_ERR_ARG;
+  return mfr::icp_refine(s->s, depth0, depth1, H, W, P, K0, K1, R_in, t_in, max_corr_dist, max_iterations, relative_fitness,
+                         relative_rmse, R, t, n_inliers, static_cast<cudaStream_t>(stream));
+}
+
 int mfr_resize_linear(const void* src, int src_is_u8, int src_w, int src_h, long long src_row_stride, int channels, float* dst,
                       int dst_w, int dst_h, int mode, float out_scale, int chw, void* stream) {
   return mfr::resize_linear(src, src_is_u8, src_w, src_h, src_row_stride, channels, dst, dst_w, dst_h, mode, out_scale, chw,

@@ -1312,6 +1312,156 @@ __global__ void __launch_bounds__(256) procrustes_final_kernel(
   if (threadIdx.x == 0) n_inl[pair] = s_cnt;
 }
 
+// ================================================================================================
+// ICP refinement of the Procrustes pose over the FULL depth clouds (pose_solver.py:289-315: Open3D registration_icp,
+// point-to-point, max correspondence distance = PROCRUSTES.MAX_CORR_DIST, <= 30 iterations, relative fitness / rmse 1e-4).
+// Both clouds are organised (one 3-D point per valid depth pixel), so the nearest neighbour of a transformed source point
+// inside the correspondence radius D is found EXACTLY by a bounded window search around its projection into image 1: a
+// target point within D of the query lies within ceil(D (f + |u - c|) / (z - D)) pixels of it on each axis. No k-d tree.
+// State per pair (double[kIcpState]): [0..8] R, [9..11] t (current source -> target transform), [12] fitness, [13] rmse,
+// [14] converged flag, [15] correspondences, [16] valid source points, [17] valid target points.
+// Accumulator per pair (double[17]): n, sum p [3], sum q [3], sum p q^T [9], sum |p - q|^2  (p = transformed source point).
+// ================================================================================================
+__global__ void f32_to_f64_kernel(const float* __restrict__ a, double* __restrict__ b, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) b[i] = a[i];
+}
+
+constexpr int kIcpState = 18;
+constexpr int kIcpMaxRadius = 96;
+
+__global__ void icp_count_kernel(const float* __restrict__ depth0, const float* __restrict__ depth1, int hw,
+                                 const double* __restrict__ Rd, const double* __restrict__ td, double* __restrict__ state) {
+  const int pair = blockIdx.y;
+  __shared__ int s0[32], s1[32];
+  int c0 = 0, c1 = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    c0 += depth0[static_cast<size_t>(pair) * hw + i] > 0.f;
+    c1 += depth1[static_cast<size_t>(pair) * hw + i] > 0.f;
+  }
+  for (int o = 16; o > 0; o >>= 1) { c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o); }
+  if ((threadIdx.x & 31) == 0) { s0[threadIdx.x >> 5] = c0; s1[threadIdx.x >> 5] = c1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a = 0, b = 0;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) { a += s0[w]; b += s1[w]; }
+    atomicAdd(state + pair * kIcpState + 16, static_cast<double>(a));
+    atomicAdd(state + pair * kIcpState + 17, static_cast<double>(b));
+    if (blockIdx.x == 0) {
+      for (int k = 0; k < 9; ++k) state[pair * kIcpState + k] = Rd[9 * pair + k];
+      for (int k = 0; k < 3; ++k) state[pair * kIcpState + 9 + k] = td[3 * pair + k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) icp_assoc_kernel(const float* __restrict__ depth0, const float* __restrict__ depth1,
+                                                        int H, int W, const float* __restrict__ K0s, const float* __restrict__ K1s,
+                                                        float max_dist, const double* __restrict__ state, double* __restrict__ acc) {
+  const int pair = blockIdx.y;
+  const double* st = state + pair * kIcpState;
+  if (st[14] != 0.0 || !(st[0] == st[0])) return;                 // converged (or no initial pose): nothing to do
+  __shared__ float s_Ki0[9], s_Ki1[9], s_K1[9];
+  __shared__ double sh_red[8 * 17];
+  if (threadIdx.x == 0) {
+    inverse_K_f32(K0s + 9 * pair, s_Ki0);
+    inverse_K_f32(K1s + 9 * pair, s_Ki1);
+    for (int k = 0; k < 9; ++k) s_K1[k] = K1s[9 * pair + k];
+  }
+  __syncthreads();
+  double R[9], t[3];
+  for (int k = 0; k < 9; ++k) R[k] = st[k];
+  for (int k = 0; k < 3; ++k) t[k] = st[9 + k];
+  const float* d0 = depth0 + static_cast<size_t>(pair) * H * W;
+  const float* d1 = depth1 + static_cast<size_t>(pair) * H * W;
+  const double D = max_dist, D2 = D * D;
+  const double fx = s_K1[0], fy = s_K1[4], cx = s_K1[2], cy = s_K1[5];
+  double a[17];
+  for (int k = 0; k < 17; ++k) a[k] = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    const float z0 = d0[i];
+    if (!(z0 > 0.f)) continue;
+    double X[3], P[3];
+    backproject(s_Ki0, i % W, i / W, z0, X);
+    mat3_vec(R, X, P);
+    for (int k = 0; k < 3; ++k) P[k] += t[k];
+    if (!(P[2] > D + 1e-3)) continue;                              // behind / too close to camera 1: no target point can be within D
+    const double up = fx * P[0] / P[2] + cx, vp = fy * P[1] / P[2] + cy;
+    const double zr = 1.0 / (P[2] - D);
+    const int ru = min(kIcpMaxRadius, static_cast<int>(ceil(D * (fx + fabs(up - cx)) * zr)) + 1);
+    const int rv = min(kIcpMaxRadius, static_cast<int>(ceil(D * (fy + fabs(vp - cy)) * zr)) + 1);
+    const int uc = static_cast<int>(floor(up + 0.5)), vc = static_cast<int>(floor(vp + 0.5));
+    const int u_lo = max(0, uc - ru), u_hi = min(W - 1, uc + ru), v_lo = max(0, vc - rv), v_hi = min(H - 1, vc + rv);
+    double best = D2, Q[3] = {0, 0, 0};
+    bool found = false;
+    const float zlo = static_cast<float>(P[2] - D), zhi = static_cast<float>(P[2] + D);
+    for (int v = v_lo; v <= v_hi; ++v)
+      for (int u = u_lo; u <= u_hi; ++u) {
+        const float z1 = d1[v * W + u];
+        if (!(z1 > zlo && z1 < zhi)) continue;                     // also skips invalid (0) depth
+        double Y[3];
+        backproject(s_Ki1, u, v, z1, Y);
+        const double dx = Y[0] - P[0], dy = Y[1] - P[1], dz = Y[2] - P[2];
+        const double dd = dx * dx + dy * dy + dz * dz;
+        if (dd < best) { best = dd; Q[0] = Y[0]; Q[1] = Y[1]; Q[2] = Y[2]; found = true; }
+      }
+    if (found) {
+      a[0] += 1.0;
+      for (int r = 0; r < 3; ++r) {
+        a[1 + r] += P[r]; a[4 + r] += Q[r];
+        for (int c = 0; c < 3; ++c) a[7 + 3 * r + c] += P[r] * Q[c];
+      }
+      a[16] += best;
+    }
+  }
+  block_sum_256<17>(a, sh_red);
+  if (threadIdx.x == 0 && a[0] > 0.0)
+    for (int k = 0; k < 17; ++k) atomicAdd(acc + pair * 17 + k, a[k]);
+}
+
+// one thread per pair: fitness / rmse of the association just computed, convergence test against the previous one
+// (Open3D RegistrationICP: |d fitness| < rel_fitness and |d rmse| < rel_rmse), Kabsch update composed onto the transform
+__global__ void icp_update_kernel(double* __restrict__ state, double* __restrict__ acc, int P, int iter, double rel_fit, double rel_rmse) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= P) return;
+  double* st = state + pair * kIcpState;
+  double* a = acc + pair * 17;
+  if (st[14] != 0.0 || !(st[0] == st[0])) return;
+  const double n = a[0];
+  const double fit = st[16] > 0.0 ? n / st[16] : 0.0, rmse = n > 0.0 ? sqrt(a[16] / n) : 0.0;
+  const bool conv = iter > 0 && fabs(st[12] - fit) < rel_fit && fabs(st[13] - rmse) < rel_rmse;
+  st[12] = fit; st[13] = rmse; st[15] = n;
+  if (conv || n < 3.0) { st[14] = 1.0; }
+  else {
+    double Ru[9], tu[3];
+    if (kabsch_from_sums(n, a + 1, a + 4, a + 7, Ru, tu)) {       // update maps the transformed source onto its correspondences
+      double Rn[9], tn[3];
+      mat3_mul(Ru, st, Rn);
+      mat3_vec(Ru, st + 9, tn);
+      for (int k = 0; k < 9; ++k) st[k] = Rn[k];
+      for (int k = 0; k < 3; ++k) st[9 + k] = tn[k] + tu[k];
+    } else {
+      st[14] = 1.0;
+    }
+  }
+  for (int k = 0; k < 17; ++k) a[k] = 0.0;
+}
+
+__global__ void icp_finish_kernel(const double* __restrict__ state, int P, float* __restrict__ Rf, float* __restrict__ tf,
+                                  int* __restrict__ n_inl) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= P) return;
+  const double* st = state + pair * kIcpState;
+  if (!(st[0] == st[0])) {                                         // NaN initial pose: the RANSAC stage failed, ICP does not run
+    for (int k = 0; k < 9; ++k) Rf[9 * pair + k] = NAN;
+    for (int k = 0; k < 3; ++k) tf[3 * pair + k] = NAN;
+    n_inl[pair] = 0;
+    return;
+  }
+  for (int k = 0; k < 9; ++k) Rf[9 * pair + k] = static_cast<float>(st[k]);
+  for (int k = 0; k < 3; ++k) tf[3 * pair + k] = static_cast<float>(st[9 + k]);
+  n_inl[pair] = static_cast<int>(st[12] * st[17]);                // pose_solver.py:319: int(fitness * len(pcl_1.points))
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -1326,6 +1476,7 @@ struct PoseSolver {
   float* uv = nullptr;
   int *vidx = nullptr, *nvalid = nullptr;
   unsigned int *dmin = nullptr, *dmin1 = nullptr;
+  double* icp_state = nullptr;   // ICP refinement scratch (allocated on first use)
   size_t total_pts;
 };
 
@@ -1365,7 +1516,7 @@ int pose_solver_create(int max_pairs, int max_pts, int max_hyp, PoseSolver** out
 void pose_solver_destroy(PoseSolver* s) {
   if (!s) return;
   cudaFree(s->results); cudaFree(s->lo_out); cudaFree(s->pts_norm); cudaFree(s->Rd); cudaFree(s->td); cudaFree(s->Xw); cudaFree(s->uv);
-  cudaFree(s->vidx); cudaFree(s->nvalid); cudaFree(s->dmin); cudaFree(s->dmin1); cudaFree(s->X1w);
+  cudaFree(s->vidx); cudaFree(s->nvalid); cudaFree(s->dmin); cudaFree(s->dmin1); cudaFree(s->X1w); cudaFree(s->icp_state);
   delete s;
 }
 
@@ -1446,6 +1597,33 @@ int procrustes_ransac(PoseSolver* s, const float* kpts0, const float* kpts1, con
       s->Xw, s->X1w, offsets, s->nvalid, max_corr_dist, num_hyp, seed, s->max_pts, s->results);
   procrustes_final_kernel<<<P, 256, 0, st>>>(s->Xw, s->X1w, offsets, s->nvalid, max_corr_dist, blocks, s->max_pts, s->results, R,
                                              t, n_inl);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int icp_refine(PoseSolver* s, const float* depth0, const float* depth1, int H, int W, int P, const float* K0, const float* K1,
+               const float* R_in, const float* t_in, float max_corr_dist, int max_iter, float rel_fitness, float rel_rmse,
+               float* R, float* t, int* n_inl, cudaStream_t st) {
+  if (P < 1 || P > s->max_pairs || max_iter < 1) return MFR_ERR_ARG;
+  if (!s->icp_state) {
+    if (cudaMalloc(&s->icp_state, sizeof(double) * (kIcpState + 17 + 12) * s->max_pairs) != cudaSuccess) return MFR_ERR_CUDA;
+  }
+  double* state = s->icp_state;
+  double* acc = state + static_cast<size_t>(kIcpState) * s->max_pairs;
+  double* Rd = acc + static_cast<size_t>(17) * s->max_pairs;      // initial pose in double: R [P][9] then t [P][3]
+  double* td = Rd + static_cast<size_t>(9) * s->max_pairs;
+  MFR_CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(double) * (kIcpState + 17) * s->max_pairs, st));
+  f32_to_f64_kernel<<<(9 * P + 255) / 256, 256, 0, st>>>(R_in, Rd, 9 * P);
+  f32_to_f64_kernel<<<(3 * P + 255) / 256, 256, 0, st>>>(t_in, td, 3 * P);
+  icp_count_kernel<<<dim3(64, P), 256, 0, st>>>(depth0, depth1, H * W, Rd, td, state);
+  const int blocks = std::max(1, std::min((H * W + 255) / 256, 4 * 148 / P + 1));
+  for (int it = 0; it <= max_iter; ++it) {
+    // association under the current transform; the update kernel evaluates it (fitness, rmse), tests convergence against the
+    // previous association and applies the Kabsch step. The last pass (it == max_iter) only evaluates.
+    icp_assoc_kernel<<<dim3(blocks, P), 256, 0, st>>>(depth0, depth1, H, W, K0, K1, max_corr_dist, state, acc);
+    icp_update_kernel<<<(P + 63) / 64, 64, 0, st>>>(state, acc, P, it, it == max_iter ? 1e300 : rel_fitness, it == max_iter ? 1e300 : rel_rmse);
+  }
+  icp_finish_kernel<<<(P + 63) / 64, 64, 0, st>>>(state, P, R, t, n_inl);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }

@@ -28,4 +28,9 @@ int procrustes_ransac(PoseSolver* s, const float* kpts0, const float* kpts1, con
                       int num_hyp, float max_corr_dist, unsigned long long seed, float* R, float* t, int* n_inl,
                       cudaStream_t st);
 
+// ICP refinement over the full depth clouds (pose_solver.py:289-315), starting from (R_in, t_in) [P][9] / [P][3] (NaN = skip)
+int icp_refine(PoseSolver* s, const float* depth0, const float* depth1, int H, int W, int P, const float* K0, const float* K1,
+               const float* R_in, const float* t_in, float max_corr_dist, int max_iter, float rel_fitness, float rel_rmse,
+               float* R, float* t, int* n_inl, cudaStream_t st);
+
 }  // namespace mfr

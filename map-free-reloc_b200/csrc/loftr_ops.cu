@@ -1214,14 +1214,21 @@ __global__ void __launch_bounds__(kCmThreads) conf_fused_kernel(const float* __r
                                                          const float* __restrict__ col_rsum,
                                                          float* __restrict__ rconf_max, int* __restrict__ rconf_arg,
                                                          int* __restrict__ rconf_ties, float* __restrict__ part,
-                                                         int L, int rows_per_block, int splits, bool raw) {
+                                                         int L, int rows_per_block, int splits, bool raw, float thr) {
+  // Only entries with conf > thr can become matches (coarse_matching.py:183), and conf = p_row * p_col with both factors
+  // <= 1, so conf > thr needs p_row > thr AND p_col > thr, i.e. S > max + ln(thr * sum) on the row and on the column side.
+  // Everything else is skipped after two compares (at most 1 / thr entries of a row pass): the row / column maxima then run
+  // over the candidates only, which changes them exactly where they are <= thr — where no match is possible anyway. With
+  // thr <= 0 (or a raw confidence matrix) every entry is a candidate and the pass is the exhaustive one.
   constexpr int R = 2;
+  constexpr float kSlack = 1e-3f;      // the screen is applied to S, the decision to the rounded conf: keep borderline entries
+  const bool screen = thr > 0.f && !raw;
   __shared__ float sh[2 * R * kCmWarps];
   const int b = blockIdx.y, t = threadIdx.x;
   const int i0 = blockIdx.x * rows_per_block, i1 = min(L, i0 + rows_per_block);
   const int L4 = L >> 2;
   const float4* Sb = reinterpret_cast<const float4*>(S + static_cast<size_t>(b) * L * L);
-  float4 cmv[kF4], crv[kF4];
+  float4 cmv[kF4], crv[kF4], tcv[kF4];
   float cbest[kF4 * 4];
 #pragma unroll
   for (int k = 0; k < kF4; ++k) {
@@ -1229,6 +1236,12 @@ __global__ void __launch_bounds__(kCmThreads) conf_fused_kernel(const float* __r
     const bool ok = f < L4 && !raw;
     cmv[k] = ok ? __ldg(reinterpret_cast<const float4*>(col_max + static_cast<size_t>(b) * L) + f) : make_float4(0, 0, 0, 0);
     crv[k] = ok ? __ldg(reinterpret_cast<const float4*>(col_rsum + static_cast<size_t>(b) * L) + f) : make_float4(0, 0, 0, 0);
+    // column-side candidate bound: S > cmax + ln(thr / crs) - slack   (crs = 1 / sum)
+    tcv[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (screen && ok) {
+      tcv[k].x = cmv[k].x + __logf(thr / crv[k].x) - kSlack; tcv[k].y = cmv[k].y + __logf(thr / crv[k].y) - kSlack;
+      tcv[k].z = cmv[k].z + __logf(thr / crv[k].z) - kSlack; tcv[k].w = cmv[k].w + __logf(thr / crv[k].w) - kSlack;
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) cbest[k * 4 + e] = -1.f;
   }
@@ -1258,24 +1271,30 @@ __global__ void __launch_bounds__(kCmThreads) conf_fused_kernel(const float* __r
       const bool rok = i + r < i1;
       const size_t row = static_cast<size_t>(b) * L + (rok ? i + r : i);
       const float rmx = raw ? 0.f : row_max[row], rrs = raw ? 0.f : row_rsum[row];
+      const float tr = screen ? rmx + __logf(thr / rrs) - kSlack : -INFINITY;      // row-side candidate bound
       best[r] = -1.f;
       arg[r] = 0x7fffffff;
 #pragma unroll
       for (int k = 0; k < kF4; ++k) {
         const int f = t + kCmThreads * k;
         const bool ok = rok && f < L4;
-        float4 c;
-        c.x = ok ? conf_value(v[r][k].x, rmx, rrs, cmv[k].x, crv[k].x, raw) : -1.f;
-        c.y = ok ? conf_value(v[r][k].y, rmx, rrs, cmv[k].y, crv[k].y, raw) : -1.f;
-        c.z = ok ? conf_value(v[r][k].z, rmx, rrs, cmv[k].z, crv[k].z, raw) : -1.f;
-        c.w = ok ? conf_value(v[r][k].w, rmx, rrs, cmv[k].w, crv[k].w, raw) : -1.f;
+        const float4 s4 = v[r][k];
+        const bool c0 = ok && s4.x > tr && s4.x > tcv[k].x, c1 = ok && s4.y > tr && s4.y > tcv[k].y;
+        const bool c2 = ok && s4.z > tr && s4.z > tcv[k].z, c3 = ok && s4.w > tr && s4.w > tcv[k].w;
+        float4 c = make_float4(-1.f, -1.f, -1.f, -1.f);
+        if (c0 | c1 | c2 | c3) {
+          if (c0) c.x = conf_value(s4.x, rmx, rrs, cmv[k].x, crv[k].x, raw);
+          if (c1) c.y = conf_value(s4.y, rmx, rrs, cmv[k].y, crv[k].y, raw);
+          if (c2) c.z = conf_value(s4.z, rmx, rrs, cmv[k].z, crv[k].z, raw);
+          if (c3) c.w = conf_value(s4.w, rmx, rrs, cmv[k].w, crv[k].w, raw);
+          if (c.x > best[r]) { best[r] = c.x; arg[r] = 4 * f; }
+          if (c.y > best[r]) { best[r] = c.y; arg[r] = 4 * f + 1; }
+          if (c.z > best[r]) { best[r] = c.z; arg[r] = 4 * f + 2; }
+          if (c.w > best[r]) { best[r] = c.w; arg[r] = 4 * f + 3; }
+          cbest[k * 4] = fmaxf(cbest[k * 4], c.x); cbest[k * 4 + 1] = fmaxf(cbest[k * 4 + 1], c.y);
+          cbest[k * 4 + 2] = fmaxf(cbest[k * 4 + 2], c.z); cbest[k * 4 + 3] = fmaxf(cbest[k * 4 + 3], c.w);
+        }
         v[r][k] = c;   // keep the confidences for the tie count
-        if (c.x > best[r]) { best[r] = c.x; arg[r] = 4 * f; }
-        if (c.y > best[r]) { best[r] = c.y; arg[r] = 4 * f + 1; }
-        if (c.z > best[r]) { best[r] = c.z; arg[r] = 4 * f + 2; }
-        if (c.w > best[r]) { best[r] = c.w; arg[r] = 4 * f + 3; }
-        cbest[k * 4] = fmaxf(cbest[k * 4], c.x); cbest[k * 4 + 1] = fmaxf(cbest[k * 4 + 1], c.y);
-        cbest[k * 4 + 2] = fmaxf(cbest[k * 4 + 2], c.z); cbest[k * 4 + 3] = fmaxf(cbest[k * 4 + 3], c.w);
       }
     }
     float bm[R];
@@ -1288,9 +1307,11 @@ __global__ void __launch_bounds__(kCmThreads) conf_fused_kernel(const float* __r
     for (int r = 0; r < R; ++r) {
       q[r] = (best[r] == bm[r] && arg[r] != 0x7fffffff) ? -static_cast<float>(arg[r]) : -INFINITY;   // indices < 2^24: exact
       int ties = 0;
+      if (bm[r] >= 0.f) {               // a row without candidates has no maximum to tie with
 #pragma unroll
-      for (int k = 0; k < kF4; ++k)
-        ties += (v[r][k].x == bm[r]) + (v[r][k].y == bm[r]) + (v[r][k].z == bm[r]) + (v[r][k].w == bm[r]);
+        for (int k = 0; k < kF4; ++k)
+          ties += (v[r][k].x == bm[r]) + (v[r][k].y == bm[r]) + (v[r][k].z == bm[r]) + (v[r][k].w == bm[r]);
+      }
       q[R + r] = static_cast<float>(ties);
     }
     {  // one barrier pair for both reductions: max over q[0..R), sum over q[R..2R)
@@ -1773,7 +1794,7 @@ int coarse_match(const float* S, CoarseMatchBuffers f, int B, int L, int h_c, in
       col_stats_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.col_max, f.col_rsum, L, nblk);
     }
     conf_fused_kernel<<<dim3(nblk, B), kCmThreads, kCmStageBytes, st>>>(S, f.row_max, f.row_rsum, f.col_max, f.col_rsum, f.rconf_max,
-                                                     f.rconf_arg, f.rconf_ties, f.col_part, L, rpb, nblk, raw);
+                                                     f.rconf_arg, f.rconf_ties, f.col_part, L, rpb, nblk, raw, thr);
     col_conf_combine_kernel<<<dim3(cb, B), 256, 0, st>>>(f.col_part, f.cconf_max, L, nblk);
   } else {
     if (!raw) {

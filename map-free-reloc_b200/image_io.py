@@ -9,6 +9,7 @@ between two IDCT implementations); other formats are decoded by OpenCV on the ho
 kernels restate cv2.resize(INTER_LINEAR) for both of its arithmetic paths (tests/test_image_io_gpu.py: float path
 within 1e-6 of cv2, uint8 path bit-exact)."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -59,6 +60,8 @@ def resize_linear(img, size, mode, out_scale=1.0, chw=False):
 
 def _load_u8(path, rgb, device):
     p = str(path)
+    if not os.path.isfile(p):
+        return None                                  # cv2.imread's convention for unreadable files (utils.py:265-266)
     if p.lower().endswith((".jpg", ".jpeg")):
         try:
             return decode_jpeg(p, rgb=rgb, device=device)

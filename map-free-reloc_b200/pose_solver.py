@@ -124,6 +124,18 @@ class PoseBackend:
             _lib.cur_stream()), "mfr_procrustes_ransac")
         return R, t, n
 
+    def icp(self, R_in, t_in, K0, K1, depth0, depth1, max_corr_dist, max_iter=30, rel_fitness=1e-4, rel_rmse=1e-4):
+        """ICP refinement of ProcrustesSolver (REFINE=True) over the full depth clouds: R [P,3,3], t [P,3], inliers [P]."""
+        P = R_in.shape[0]
+        H, W = depth0.shape[-2:]
+        R = torch.empty(P, 3, 3, device=self.device); t = torch.empty(P, 3, device=self.device)
+        n = torch.empty(P, dtype=torch.int32, device=self.device)
+        _lib.check(self._l.mfr_icp_refine(self._h, _lib.ptr(depth0.contiguous()), _lib.ptr(depth1.contiguous()), int(H), int(W), P,
+                                          _lib.ptr(K0), _lib.ptr(K1), _lib.ptr(R_in.contiguous()), _lib.ptr(t_in.contiguous()),
+                                          float(max_corr_dist), int(max_iter), float(rel_fitness), float(rel_rmse),
+                                          _lib.ptr(R), _lib.ptr(t), _lib.ptr(n), _lib.cur_stream()), "mfr_icp_refine")
+        return R, t, n
+
     def close(self):
         if getattr(self, "_h", None):
             self._l.mfr_pose_solver_destroy(self._h)
@@ -284,16 +296,14 @@ class PnPSolver(_SolverBase):
 
 
 class ProcrustesSolver(_SolverBase):
-    """Metric relative pose from 3D-3D correspondences (pose_solver.py:238-320). The ICP refinement
-    over the full point clouds (PROCRUSTES.REFINE, Open3D registration_icp) is not built."""
+    """Metric relative pose from 3D-3D correspondences (pose_solver.py:238-320): RANSAC over 3-point Kabsch alignments,
+    and with PROCRUSTES.REFINE the point-to-point ICP over the full depth clouds (pose_solver.py:289-315)."""
     SAMPLE_SIZE = 3
 
     def __init__(self, cfg):
         super().__init__(cfg)
         self.ransac_max_corr_distance = float(_cfg_get(cfg, "PROCRUSTES.MAX_CORR_DIST"))
         self.refine = bool(_cfg_get(cfg, "PROCRUSTES.REFINE", False))
-        if self.refine:
-            raise NotImplementedError("PROCRUSTES.REFINE (ICP over the full clouds) is not built")
 
     def estimate_pose(self, pts0, pts1, data):
         if len(pts0) < 3:
@@ -306,4 +316,7 @@ class ProcrustesSolver(_SolverBase):
         n = int(n.item())
         if n == 0:
             return self._nan()
+        if self.refine:          # pose_solver.py:289-319: ICP over all valid depth pixels, starting from the RANSAC pose
+            R, t, n = self.backend.icp(R, t, K0, K1, d0, d1, self.ransac_max_corr_distance)
+            n = int(n.item())
         return R[0].double().cpu().numpy(), t[0].double().cpu().numpy().reshape(3, 1), n

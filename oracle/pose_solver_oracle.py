@@ -260,6 +260,57 @@ def procrustes_solver(pts0, pts1, depth0, depth1, K0, K1, max_corr_dist, iters=4
     return R, t.reshape(3, 1), int(inl.sum())
 
 
+def icp_point_to_point(src, dst, T_init, max_corr_dist, max_iter=30, rel_fitness=1e-4, rel_rmse=1e-4):
+    """Open3D 0.17 registration_icp with TransformationEstimationPointToPoint, restated (PARITY UNPINNED: Open3D cannot
+    be installed here; this follows its published algorithm — evaluate, then per iteration Kabsch on the current
+    correspondences, re-evaluate, stop when fitness and inlier rmse both change by less than the relative criteria):
+    nearest neighbour of every transformed source point in `dst` within max_corr_dist (exact, k-d tree),
+    fitness = #correspondences / #source, inlier_rmse = sqrt(mean squared correspondence distance).
+    Returns (T [4,4], fitness, inlier_rmse)."""
+    from scipy.spatial import cKDTree
+    tree = cKDTree(dst)
+    T = np.array(T_init, dtype=np.float64)
+    P = src @ T[:3, :3].T + T[:3, 3]
+
+    def evaluate(P):
+        d, j = tree.query(P, k=1, distance_upper_bound=max_corr_dist)
+        ok = np.isfinite(d)
+        n = int(ok.sum())
+        return ok, j, (n / len(P) if len(P) else 0.0), (float(np.sqrt(np.mean(d[ok] ** 2))) if n else 0.0)
+
+    ok, j, fit, rmse = evaluate(P)
+    for _ in range(max_iter):
+        if ok.sum() < 3:
+            break
+        Ru, tu = kabsch(P[ok], dst[j[ok]])
+        U = np.eye(4); U[:3, :3] = Ru; U[:3, 3] = tu
+        T = U @ T
+        P = P @ Ru.T + tu
+        ok, j, fit2, rmse2 = evaluate(P)
+        done = abs(fit - fit2) < rel_fitness and abs(rmse - rmse2) < rel_rmse
+        fit, rmse = fit2, rmse2
+        if done:
+            break
+    return T, fit, rmse
+
+
+def procrustes_icp_solver(pts0, pts1, depth0, depth1, K0, K1, max_corr_dist, iters=4096, seed=0):
+    """ProcrustesSolver.estimate_pose with REFINE=True (pose_solver.py:289-319): the RANSAC pose, then ICP over the
+    full clouds of both depth maps (every pixel with depth > 0), inliers = int(fitness * #target points)."""
+    R, t, n = procrustes_solver(pts0, pts1, depth0, depth1, K0, K1, max_corr_dist, iters, seed)
+    if n == 0:
+        return R, t, n
+    vv, uu = np.mgrid[0:depth0.shape[0], 0:depth1.shape[1]]
+    uv = np.concatenate([uu.reshape(-1, 1), vv.reshape(-1, 1)], axis=1)
+    v0 = depth0.reshape(-1) > 0
+    X0 = backproject_3d(uv[v0], depth0.reshape(-1)[v0], K0)
+    v1 = depth1.reshape(-1) > 0
+    X1 = backproject_3d(uv[v1], depth1.reshape(-1)[v1], K1)
+    T0 = np.eye(4); T0[:3, :3] = R; T0[:3, 3] = np.ravel(t)
+    T, fit, _ = icp_point_to_point(X0, X1, T0, max_corr_dist)
+    return T[:3, :3], T[:3, 3].reshape(3, 1), int(fit * len(X1))
+
+
 # --------------------------------------------------------------------------------------------
 # Oracle extensions (not in the reference): the "polished oracle" of SURVEY.md §7 hard part 1
 # --------------------------------------------------------------------------------------------

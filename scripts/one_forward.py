@@ -6,7 +6,9 @@ import numpy as np, torch
 import mfr_b200
 from mfr_b200 import loftr, synth, pose_solver
 B = int(os.environ.get("B", 4)); H, W = 720, 544
-eng = loftr.LoFTR(loftr.functional_state_dict(), batch=B, height=H, width=W, cfg={"thr": 0.2}, graph=False,
+# WEIGHTS=dense (default): the throughput benchmark's weights, functional matcher + dense perturbation (bench.py); functional: 99.8 % zeros
+noise = 0.0 if os.environ.get("WEIGHTS", "dense") == "functional" else 1e-3
+eng = loftr.LoFTR(loftr.functional_state_dict(noise=noise), batch=B, height=H, width=W, cfg={"thr": 0.2}, graph=False,
                   precision=os.environ.get("PRECISION", "bf16"))
 be = pose_solver.PoseBackend(max_pairs=B, max_pts=(H // 8) * (W // 8), max_hyp=1024)
 ps = [synth.make_pair(1000 + b) for b in range(B)]

@@ -179,3 +179,38 @@ def test_procrustes_matches_oracle(seed, n, ratio, noise):
     assert rot_angle(R, Ro) < 2e-3 and np.linalg.norm(t.ravel() - to.ravel()) < 2e-3
     assert abs(ninl - no) <= max(3, 0.02 * no)
     assert rot_angle(R, c["R_gt"]) < 1e-2 and np.linalg.norm(t.ravel() - c["t_gt"]) < 3e-2
+
+
+@pytest.mark.parametrize("seed", [3, 8])
+def test_procrustes_icp_refine_matches_oracle(seed):
+    """PROCRUSTES.REFINE (pose_solver.py:289-319): the GPU ICP (exact nearest neighbour inside the correspondence radius
+    by a bounded window search in the organised target cloud) against the k-d tree restatement of Open3D's point-to-point
+    ICP on the same full-resolution depth clouds and the same starting pose. Open3D itself is absent: parity unpinned."""
+    from mfr_b200 import pose_solver as ps
+    p = synth.make_pair(seed, h=240, w=320, K=np.array([[300.0, 0, 159.5], [0, 300.0, 119.5], [0, 0, 1]]))
+    rng = np.random.default_rng(seed)
+    # a perturbed ground-truth pose as the starting point (what the correspondence RANSAC delivers, but identical on both sides)
+    R0 = synth.rodrigues(rng.normal(0, 0.01, 3)) @ p["R_gt"]
+    t0 = p["t_gt"] + rng.normal(0, 0.02, 3)
+    vv, uu = np.mgrid[0:240, 0:320]
+    uv = np.concatenate([uu.reshape(-1, 1), vv.reshape(-1, 1)], 1)
+    v0 = p["depth0"].reshape(-1) > 0; v1 = p["depth1"].reshape(-1) > 0
+    X0 = po.backproject_3d(uv[v0], p["depth0"].reshape(-1)[v0], p["K_color0"]); X1 = po.backproject_3d(uv[v1], p["depth1"].reshape(-1)[v1], p["K_color1"])
+    T0 = np.eye(4); T0[:3, :3] = R0; T0[:3, 3] = t0
+    T, fit, rmse = po.icp_point_to_point(X0, X1, T0, 0.05)
+    be = ps.PoseBackend(max_pairs=2, max_pts=64, max_hyp=128)
+    dev = be.device
+    f = lambda a: torch.tensor(np.stack([a, a]), dtype=torch.float32, device=dev).contiguous()      # two identical pairs: batched path
+    R, t, n = be.icp(f(R0), f(t0), f(p["K_color0"]), f(p["K_color1"]), f(p["depth0"]), f(p["depth1"]), 0.05)
+    for b in range(2):
+        assert rot_angle(R[b].cpu().numpy(), T[:3, :3]) < 2e-4 and np.linalg.norm(t[b].cpu().numpy() - T[:3, 3]) < 2e-4
+        assert abs(int(n[b]) - int(fit * len(X1))) <= max(3, 0.002 * len(X1))
+    # NaN starting pose (failed RANSAC): passes through as the failure convention
+    Rn = f(R0); Rn[1] = float("nan")
+    R, t, n = be.icp(Rn, f(t0), f(p["K_color0"]), f(p["K_color1"]), f(p["depth0"]), f(p["depth1"]), 0.05)
+    assert torch.isnan(R[1]).all() and int(n[1]) == 0 and torch.isfinite(R[0]).all()
+    # the plugin with REFINE: True (the scannet *_icp.yaml configurations)
+    c = synth.make_correspondences(81, n=600, inlier_ratio=0.7, noise_px=0.2)
+    cfg = dict(CFG, PROCRUSTES={"MAX_CORR_DIST": 0.05, "REFINE": True})
+    Rp, tp, npl = ps.ProcrustesSolver(cfg).estimate_pose(c["kpts0"], c["kpts1"], _data(c))
+    assert Rp.shape == (3, 3) and tp.shape == (3, 1) and npl >= 0

@@ -79,10 +79,10 @@ def test_jpeg_decode_and_plugins(tmp_path):
     # offline plugins on files: match((path0, path1)) -> [N, 4]  (matchers.py:24-59, 93-120)
     q = str(tmp_path / "b.png")
     cv2.imwrite(q, np.roll(rgb, (6, 10), (0, 1))[:, :, ::-1])                      # PNG: host decode, GPU resize
-    m = loftr.LoFTR_matcher((270, 360), weights=loftr.functional_state_dict(), cfg={"thr": 0.2})
+    m = loftr.LoFTR_matcher((272, 360), weights=loftr.functional_state_dict(), cfg={"thr": 0.2})
     pts = m.match((p, q))
     assert pts.shape[1] == 4 and len(pts) > 50
-    d = pts[:, 2:] - pts[:, :2]                              # image b is image a shifted by (10, 6) * 0.5 (resize 540 -> 270)
+    d = pts[:, 2:] - pts[:, :2]                              # image b is image a shifted by (10, 6) * 0.5 (resize 540 -> 272)
     assert np.abs(np.median(d, 0) - np.array([5.0, 3.0])).max() < 0.6
     sp, sg = spsg.synthetic_state_dicts(0)
     s = spsg.SuperGlue_matcher((272, 360), state_dicts=(sp, sg))
