@@ -58,11 +58,21 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_ELU1) return v > 0.f ? v + 1.f : __expf(v);
   return v;
 }
-template <int ACT>
+// FAST (bf16 outputs only): elu(x) + 1 for x <= 0 is exp(x) in (0, 1] — a bare ex2.approx on the pre-scaled argument (2
+// instructions) instead of __expf with its range fix-ups (~9); its 2-ulp error is far below the bf16 rounding that follows.
+template <int ACT, bool FAST = false>
 __device__ __forceinline__ float act_fn(float v) {
   if constexpr (ACT == ACT_RELU) return fmaxf(v, 0.f);
   if constexpr (ACT == ACT_LEAKY) return v > 0.f ? v : 0.01f * v;
-  if constexpr (ACT == ACT_ELU1) return v > 0.f ? v + 1.f : __expf(v);
+  if constexpr (ACT == ACT_ELU1) {
+    if constexpr (FAST) {
+      float e;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 0.f) * 1.4426950408889634f));
+      return v > 0.f ? v + 1.f : e;
+    } else {
+      return v > 0.f ? v + 1.f : __expf(v);
+    }
+  }
   return v;
 }
 
@@ -151,7 +161,7 @@ __device__ __forceinline__ void epilogue_subtile(const ConvGemmParams& p, uint32
           v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
         }
         if (do_act) {
-          v.x = act_fn<ACT>(v.x); v.y = act_fn<ACT>(v.y); v.z = act_fn<ACT>(v.z); v.w = act_fn<ACT>(v.w);
+          v.x = act_fn<ACT, OBF>(v.x); v.y = act_fn<ACT, OBF>(v.y); v.z = act_fn<ACT, OBF>(v.z); v.w = act_fn<ACT, OBF>(v.w);
         }
         if constexpr (OBF)
           *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + off_o[k] + n) =
@@ -294,7 +304,7 @@ __device__ __forceinline__ void epilogue_tile_swap(const ConvGemmParams& p, uint
         else r4 = rcur[k];
         v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
       }
-      v.x = act_fn<ACT>(v.x); v.y = act_fn<ACT>(v.y); v.z = act_fn<ACT>(v.z); v.w = act_fn<ACT>(v.w);
+      v.x = act_fn<ACT, OBF>(v.x); v.y = act_fn<ACT, OBF>(v.y); v.z = act_fn<ACT, OBF>(v.z); v.w = act_fn<ACT, OBF>(v.w);
       if constexpr (OBF)
         *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out_img) + pcur[k] * ldo) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
       else

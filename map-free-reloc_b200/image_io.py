@@ -22,7 +22,9 @@ MODE_F32, MODE_U8_AS_F32, MODE_U8_FIXED = 0, 1, 2
 def _device(device):
     if not torch.cuda.is_available():
         raise _lib.MfrError("mfr_b200.image_io needs a CUDA device (no CPU fallback)")
-    return torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    if isinstance(device, torch.device):
+        return device
+    return torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
 
 
 def decode_jpeg(data, rgb=False, device=None):
