@@ -32,17 +32,17 @@ constexpr int kMaxBN = 256;
 constexpr int kAStage = kTileM * kBlockK * 4;   // 16 KB
 constexpr int kRingBytes = 204 * 1024;          // operand rings (A slots + B slots)
 constexpr int kStgStride = 36;                  // floats per staged row (144 B: conflict-free 128-bit access)
-constexpr int kEpiWarps = 4;                    // 4 or 8 (two per TMEM lane quarter, alternating 32-channel chunks);
-                                                // 8 measured no faster: the store phase is bound by the memory system
-constexpr int kStgBytes = kEpiWarps * 32 * kStgStride * 4;  // epilogue transpose buffers, one per epilogue warp
-constexpr int kSmemBytes = kRingBytes + kStgBytes + 1024 /*align slack*/;
+constexpr int kStgBytes4 = 4 * 32 * kStgStride * 4;  // epilogue transpose buffers, one per epilogue warp (18 KB with 4 warps)
+constexpr int kSmemBytes = kRingBytes + kStgBytes4 + 1024 /*align slack*/;
+// with 8 epilogue warps the second 18 KB of staging comes out of the ring (token GEMMs with K <= 512 do not need its depth)
+constexpr int kRingBytes8 = kRingBytes - kStgBytes4;
 // Two MMA-issuing warps that alternate commit groups hide the commit stall (profiles/r01_mma_probe2.txt) and were
 // measured 3 % faster on the backbone, but the two instruction streams interleave in the pipe in a timing-dependent
 // order, so the fp32 accumulation order — and with it the last bits of the result — changes from run to run. The
 // engine promises bit-identical replays (tests/test_loftr_gpu.py), so the second issuer is compiled out.
 constexpr bool kDualIssue = false;
-constexpr int kThreads = 64 + 32 * kEpiWarps + (kDualIssue ? 32 : 0);   // TMA producer, MMA issuer, epilogue warps[, MMA issuer 1]
-constexpr int kMma2Warp = kDualIssue ? 2 + kEpiWarps : -1;
+constexpr int kThreads = 64 + 32 * 4;   // TMA producer, MMA issuer, 4 epilogue warps (the 8-warp instantiation: 64 + 32 * 8)
+static_assert(!kDualIssue, "the second MMA issuer was removed from the warp layout");
 constexpr int kTmemCols = 512;
 
 __device__ __forceinline__ long long gtime() {
@@ -95,7 +95,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // (LDS.128 -> alpha/bias/residual/act -> coalesced STG); lane (sub_r, sub_c) handles staged rows
 // k*4+sub_r, channels sub_c..sub_c+3. The residual of chunk c+1 is fetched before chunk c is stored
 // (and the first one before the accumulator wait), so its HBM latency never sits in front of a store.
-template <int ACT, bool RES, bool OBF>
+template <int ACT, bool RES, bool OBF, int EPI>
 __device__ __forceinline__ void epilogue_subtile(const ConvGemmParams& p, uint32_t taddr, float* stg, int lane,
                                                  int n0, const long long (&off_o)[8], const long long (&off_r)[8],
                                                  uint32_t okmask, uint32_t wait_bar, uint32_t wait_phase,
@@ -117,7 +117,7 @@ __device__ __forceinline__ void epilogue_subtile(const ConvGemmParams& p, uint32
       }
     }
   };
-  constexpr int kStep = 32 * (kEpiWarps / 4);   // this warp's chunks: c_begin, c_begin + kStep, ...
+  constexpr int kStep = 32 * (EPI / 4);   // this warp's chunks: c_begin, c_begin + kStep, ...
   if constexpr (RES) issue_res(c_begin);
   if (do_wait) {
     mbar_wait(wait_bar, wait_phase, 4);
@@ -315,9 +315,10 @@ __device__ __forceinline__ void epilogue_tile_swap(const ConvGemmParams& p, uint
 }
 
 // Scalar epilogue for shapes the vector path cannot take (Cout or strides not multiples of 4); fp32 only.
+template <int EPI>
 __device__ __forceinline__ void epilogue_subtile_scalar(const ConvGemmParams& p, uint32_t taddr, int n0, bool row_ok,
                                                         long long o_off, long long r_off, int c_begin) {
-  for (int c0 = c_begin; c0 < p.BN; c0 += 32 * (kEpiWarps / 4)) {
+  for (int c0 = c_begin; c0 < p.BN; c0 += 32 * (EPI / 4)) {
     uint32_t r[32];
     tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), r);
     tmem_ld_wait();
@@ -345,15 +346,20 @@ __device__ __forceinline__ uint64_t desc_at(uint32_t addr) { return kDescHi | ((
 constexpr uint64_t kDescHi32 = (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);
 __device__ __forceinline__ uint64_t desc32_at(uint32_t addr) { return kDescHi32 | ((addr >> 4) & 0x3fffu); }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// EPI = number of epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, alternating 32-column chunks; only the
+// generic vector-store epilogue: token GEMMs with wide bf16 outputs, whose per-chunk latency is what bounds them)
+template <int EPI>
+__global__ void __launch_bounds__(64 + 32 * EPI, 1)
 conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
+  constexpr int kEpiWarps = EPI;
+  constexpr int kMma2Warp = -1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_bars[4 * kMaxSlots + 6];
   __shared__ uint32_t s_tmem_base;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + p.a_slots * p.a_slot_bytes;
-  const uint32_t smem_stg = smem_base + kRingBytes;
+  const uint32_t smem_stg = smem_base + static_cast<uint32_t>(p.ring_bytes);
   const uint32_t bar_base = smem_u32(s_bars);
   // barriers: a_full[8], a_empty[8], b_full[8], b_empty[8], tmem_full[2], tmem_empty[2].
   // Generic mode uses one ring (A and B tile of a k-block share slot and barriers: the "a" set);
@@ -733,11 +739,11 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
 #define MFR_EPI(ACTV)                                                                                               \
   do {                                                                                                              \
     if (p.residual != nullptr) {                                                                                    \
-      if (obf) epilogue_subtile<ACTV, true, true>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait, c_begin);   \
-      else epilogue_subtile<ACTV, true, false>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait, c_begin);      \
+      if (obf) epilogue_subtile<ACTV, true, true, EPI>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait, c_begin);   \
+      else epilogue_subtile<ACTV, true, false, EPI>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait, c_begin);      \
     } else {                                                                                                        \
-      if (obf) epilogue_subtile<ACTV, false, true>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait, c_begin);  \
-      else epilogue_subtile<ACTV, false, false>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait, c_begin);     \
+      if (obf) epilogue_subtile<ACTV, false, true, EPI>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait, c_begin);  \
+      else epilogue_subtile<ACTV, false, false, EPI>(p, taddr, stg, lane, n0, off_o, off_r, okmask, tfull_bar(acc), acc_phase, do_wait, c_begin);     \
     }                                                                                                               \
   } while (0)
           switch (p.act) {
@@ -752,7 +758,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
             mbar_wait(tfull_bar(acc), acc_phase, 4);
             tc_fence_after();
           }
-          epilogue_subtile_scalar(p, taddr, n0, row_ok, img * p.out_img_stride + opix,
+          epilogue_subtile_scalar<EPI>(p, taddr, n0, row_ok, img * p.out_img_stride + opix,
                                   img * p.res_img_stride + pix * p.ldr, c_begin);
         }
         if (it == 0 && m == 0 && threadIdx.x == 64) MFR_STAMP(6);
@@ -813,7 +819,8 @@ struct TileCfg {
 //   epilogue : ~500 ns per 32-channel chunk of a 128-pixel sub-tile (4 epilogue warps)
 // times the number of waves of tiles over the SMs.
 struct RingCfg { int a_slots, b_slots, cbatch, a_slot_bytes; };
-RingCfg ring_cfg(int halo, int MT, int TW, int TH, int BN) {
+RingCfg ring_cfg(int halo, int MT, int TW, int TH, int BN, int ring_bytes = kRingBytes) {
+  const int kRingBytes = ring_bytes;      // shadows the constant: the 8-epilogue-warp launches have an 18 KB smaller ring
   RingCfg r{};
   const int b_bytes = BN * 128;
   if (halo) {
@@ -837,7 +844,7 @@ RingCfg ring_cfg(int halo, int MT, int TW, int TH, int BN) {
 
 TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, int pad, int kb_per_tap,
                    int ksteps_last, bool allow_mt2, bool tma_store_ok, bool allow_swap, bool allow_mcast,
-                   bool single_row_tiles = false) {
+                   bool single_row_tiles = false, int ring_bytes = kRingBytes) {
   const int sms = conv_gemm_num_sms();
   const int c16 = (Cout + 15) / 16 * 16;
   const int taps = R * S;
@@ -869,7 +876,7 @@ TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, in
           const int box_rows = halo ? MT * th + 2 : MT * th * stride;
           if (box_rows > 256) continue;
           const long long tiles = static_cast<long long>(N) * ((Wo + tw - 1) / tw) * ((Ho + MT * th - 1) / (MT * th)) * nt;
-          const RingCfg rc = ring_cfg(halo, MT, tw, th, BN);
+          const RingCfg rc = ring_cfg(halo, MT, tw, th, BN, ring_bytes);
           if (rc.a_slots < 2 || rc.b_slots < (halo ? 4 : 2)) continue;
           const double commits = halo ? 3.0 * kb_per_tap : std::ceil(static_cast<double>(taps) * kb_per_tap / rc.cbatch);
           const double mma = static_cast<double>(MT) * taps * ksteps_tap * (30.5 + 0.2415 * BN) + commits * 215.0;
@@ -960,6 +967,12 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
     p->tail32 = (p->ksteps_last == 1 && tail * es <= 32 && p->kb_per_tap > 1 && d.b_batched != 2 &&
                  getenv("MFR_CONV_NO_TAIL32") == nullptr) ? 1 : 0;
   }
+  // 8 epilogue warps for token GEMMs with wide bf16 outputs (q|k|v: K = 128 / 256, 384 / 768 output columns, elu+1 on two
+  // thirds of them): their tiles are epilogue-latency bound, two warps per TMEM quadrant halve that. Vector-store path only.
+  const bool epi8 = d.out_bf16 && d.in_bf16 && d.R == 1 && d.S == 1 && d.stride == 1 && d.H == 1 && d.residual == nullptr && !d.b_batched &&
+                    d.Cout >= 256 && (d.Cout % 4 == 0) && (d.ldo % 4 == 0) && getenv("MFR_CONV_EPI4") == nullptr;
+  p->epi_warps = epi8 ? 8 : 4;
+  p->ring_bytes = epi8 ? kRingBytes8 : kRingBytes;
   const TileCfg cfg = choose_cfg(d.N, p->Ho, p->Wo, d.Cout, d.R, d.S, d.stride, d.pad, p->kb_per_tap, p->ksteps_last,
                                  d.dyn_w == nullptr && d.b_batched != 2, !d.out_bf16 && d.residual == nullptr,
                                  // swapped operands: not with a residual (measured: its transposed epilogue then becomes the bottleneck)
@@ -968,7 +981,7 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
                                  // CTA-pair weight multicast: measured no gain on B200 for these shapes (the layers are not L2-bound once the
                                  // channel tail is narrow), so it is opt-in (MFR_CONV_MCAST=1 or the test hook)
                                  !d.b_batched && d.dyn_w == nullptr && (getenv("MFR_CONV_MCAST") != nullptr || getenv("MFR_CONV_FORCE") != nullptr),
-                                 d.b_batched == 2);
+                                 d.b_batched == 2, p->ring_bytes);
   p->TW = cfg.TW; p->TH = cfg.TH; p->MT = cfg.MT; p->halo = cfg.halo; p->swap = cfg.swap; p->mcast = cfg.mcast;
   p->BN = cfg.BN; p->n_tiles = cfg.n_tiles;
   p->tiles_x = (p->Wo + p->TW - 1) / p->TW;
@@ -980,7 +993,7 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
   p->a_bytes = p->TW * a_rows * 128;
   p->b_bytes = p->BN * 128;                                        // multiple of 2 KB (BN % 16 == 0)
   {
-    const RingCfg rc = ring_cfg(p->halo, p->MT, p->TW, p->TH, p->BN);
+    const RingCfg rc = ring_cfg(p->halo, p->MT, p->TW, p->TH, p->BN, p->ring_bytes);
     p->a_slot_bytes = rc.a_slot_bytes; p->a_slots = rc.a_slots; p->b_slots = rc.b_slots; p->cbatch = rc.cbatch;
   }
   if (p->a_slots < 2 || p->b_slots < 2) return MFR_ERR_ARG;
@@ -1112,7 +1125,9 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
 int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream) {
   static bool attr_seen[64] = {};
   if (first_call_on_device(attr_seen)) {
-    MFR_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tf32_kernel,
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tf32_kernel<4>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tf32_kernel<8>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   }
   const int total = p.N * p.tiles_y * p.tiles_x * p.n_tiles;
@@ -1131,11 +1146,12 @@ int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream) {
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    MFR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_tf32_kernel, p));
+    MFR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_tf32_kernel<4>, p));
     return MFR_OK;
   }
   const int grid = std::min(total, conv_gemm_num_sms());
-  conv_gemm_tf32_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+  if (p.epi_warps == 8 && !p.swap && !p.tma_store && !p.mcast) conv_gemm_tf32_kernel<8><<<grid, 64 + 32 * 8, kSmemBytes, stream>>>(p);
+  else conv_gemm_tf32_kernel<4><<<grid, kThreads, kSmemBytes, stream>>>(p);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }

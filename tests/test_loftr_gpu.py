@@ -134,11 +134,12 @@ def _coarse_match(mfr, mat, h_c, w_c, thr, border, is_conf):
     return [t[:m].cpu() for t in ids] + [mconf[:m].cpu(), mk0[:m].cpu(), mk1[:m].cpu(), off.cpu()]
 
 
-def test_selection_bit_exact_given_conf(mfr):
+@pytest.mark.parametrize("h_c,w_c", [(12, 9), (11, 9)])      # L = 108: fused passes; L = 99 (not a multiple of 4): the row / column kernels
+def test_selection_bit_exact_given_conf(mfr, h_c, w_c):
     """Stage boundary: identical fp32 confidence matrix in -> identical int indices out, including exact
     ties (lowest column wins, coarse_matching.py:187-193) and the 2-cell border removal (:8-25)."""
     g = torch.Generator().manual_seed(3)
-    B, h_c, w_c = 2, 12, 9
+    B = 2
     L = h_c * w_c
     conf = torch.rand(B, L, L, generator=g) * 0.15
     perm = torch.randperm(L, generator=g)
@@ -156,16 +157,19 @@ def test_selection_bit_exact_given_conf(mfr):
     assert off.tolist() == [0, int((bo == 0).sum()), len(bo)]
 
 
-def test_dual_softmax_selection_matches_oracle(mfr):
+@pytest.mark.parametrize("h_c,w_c,thr", [(16, 11, 0.2), (15, 11, 0.2), (16, 11, 0.0), (16, 11, 0.05)])
+def test_dual_softmax_selection_matches_oracle(mfr, h_c, w_c, thr):
+    """Dual softmax + mutual NN from the similarity matrix. thr > 0: the confidence pass screens entries (only candidates of
+    conf > thr are evaluated); thr = 0: exhaustive pass; L = 165 (not a multiple of 4): the unfused row / column kernels."""
     g = torch.Generator().manual_seed(4)
-    B, h_c, w_c = 1, 16, 11
+    B = 1
     L = h_c * w_c
     f0 = torch.randn(B, L, 64, generator=g)
     f1 = f0[:, torch.randperm(L, generator=g)] + 0.05 * torch.randn(B, L, 64, generator=g)
     sim = torch.einsum("nlc,nsc->nls", f0, f1) / 0.8
     conf = torch.softmax(sim, 1) * torch.softmax(sim, 2)
-    bo, io, jo, mo = lo.coarse_select(conf, h_c, w_c, h_c, w_c, 0.2, 2)
-    b_, i_, j_, mc, _, _, _ = _coarse_match(mfr, sim.cuda().contiguous(), h_c, w_c, 0.2, 2, False)
+    bo, io, jo, mo = lo.coarse_select(conf, h_c, w_c, h_c, w_c, thr, 2)
+    b_, i_, j_, mc, _, _, _ = _coarse_match(mfr, sim.cuda().contiguous(), h_c, w_c, thr, 2, False)
     assert len(io) > 20
     assert torch.equal(i_.long(), io) and torch.equal(j_.long(), jo)
     torch.testing.assert_close(mc, mo, rtol=1e-4, atol=1e-6)
