@@ -336,19 +336,19 @@ int mfr_encoder_tail(const void* msg, void* xb, float* x, const void* w_merge, c
   for (int i = 0; i < iters && rc == MFR_OK; ++i) rc = mfr::encoder_tail_launch(p, static_cast<cudaStream_t>(stream));
   if (rc == MFR_OK && getenv("MFR_TAIL_DEBUG") != nullptr) {   // timeline of block 0 (one extra launch)
     long long* d = nullptr;
-    cudaMalloc(&d, 192 * sizeof(long long));
-    cudaMemset(d, 0, 192 * sizeof(long long));
+    cudaMalloc(&d, 256 * sizeof(long long));
+    cudaMemset(d, 0, 256 * sizeof(long long));
     p.dbg = d;
     mfr::encoder_tail_launch(p, static_cast<cudaStream_t>(stream));
     cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
-    long long h[192];
+    long long h[256];
     cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(d);
     long long t0 = 0;
-    for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 4; ++r)
       if (h[r * 64 + 1] && (t0 == 0 || h[r * 64 + 1] < t0)) t0 = h[r * 64 + 1];
-    const char* names[3] = {"mma", "epi", "tma"};
-    for (int r = 0; r < 3; ++r) {
+    const char* names[4] = {"mma", "front", "tma", "back"};
+    for (int r = 0; r < 4; ++r) {
       fprintf(stderr, "[encoder_tail C=%d %s]", C, names[r]);
       for (int k = 0; k < 32 && h[r * 64 + 2 * k + 1]; ++k) fprintf(stderr, " %lld@%lld", h[r * 64 + 2 * k], h[r * 64 + 2 * k + 1] - t0);
       fprintf(stderr, "\n");

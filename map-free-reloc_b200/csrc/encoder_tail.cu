@@ -9,8 +9,9 @@
 // Rows are independent, so one persistent CTA per SM takes 128-row tiles through the whole chain with every
 // intermediate kept on chip:
 //
-//   TMEM   D13 [128 x C]  fp32   accumulator of GEMM1 (merge), later of GEMM3 (mlp.2)
-//          D2  2 x [128 x 128]   double-buffered accumulator of GEMM2 (mlp.0), one 128-column chunk q of the hidden layer
+//   TMEM   D3  [128 x C]  fp32   accumulator of GEMM3 (mlp.2), columns [0, C)
+//          scratch, 256 columns  D1 = accumulator of GEMM1 (merge); once LayerNorm1 has consumed it, the two D2 buffers
+//                                [128 x 128] = double-buffered accumulator of GEMM2 (mlp.0), one 128-column chunk q of the hidden layer
 //   SMEM   L   [128 x C]  bf16   LayerNorm1 output = k-blocks C/64 .. 2C/64-1 of GEMM2's A operand (K-major, 128B swizzle)
 //          M   64 KB             two [128 x 128] bf16 buffers H1[q & 1]: relu(D2_q), the A operand of GEMM3
 //          ring of 16 KB slots   every streamed tile [128 rows x 64 bf16]: message / x k-blocks of this row tile and 128
@@ -20,9 +21,10 @@
 //   warp 0     TMA producer: the ring items in exactly the order the MMA warp consumes them
 //   warp 1     MMA issuer  : GEMM1; then GEMM2 chunk q+1 is issued BEFORE GEMM3 chunk q, so the tensor pipe runs the
 //                            next chunk while the epilogue warps turn chunk q into the bf16 A operand of GEMM3
-//   warps 2-9  epilogue, thread = row, two warps per TMEM lane quadrant splitting the 32-column chunks: LayerNorm1
-//              (TMEM -> registers -> swizzled smem), relu + bf16 (TMEM -> smem), LayerNorm2 + residual (TMEM -> staging ->
-//              coalesced fp32 store of x and its bf16 shadow; the residual rows are prefetched a chunk ahead)
+//   warps 2-5  front epilogue, thread = row: LayerNorm1 (TMEM -> registers -> swizzled smem), relu + bf16 (TMEM -> smem)
+//   warps 6-9  back epilogue, thread = row: LayerNorm2 + residual of the PREVIOUS tile (TMEM -> staging -> coalesced fp32
+//              store of x and its bf16 shadow; the residual rows are prefetched a chunk ahead) while the front group and
+//              the tensor pipe already work on the next tile
 //
 // The hidden layer is produced and consumed in 128-column chunks because GEMM3 accumulates over exactly those
 // columns: D3 += relu(D2_q) @ W2[:, q]^T can start as soon as chunk q exists, and 2C-wide rows never exist anywhere.
@@ -54,10 +56,12 @@ struct Cfg {
   static constexpr int L_BYTES = KB * kKbBytes;
   static constexpr int M_BYTES = 4 * kKbBytes; // message tile (KB k-blocks) / two H1 buffers of two k-blocks
   static constexpr int NH = C / 128;           // 128-column halves of a C-wide output (every MMA is N = 128)
-  static constexpr int NS = (C == 256) ? 6 : 8;  // ring slots of 16 KB
-  static constexpr int SMEM = L_BYTES + M_BYTES + NS * kKbBytes + 1024;
-  static constexpr int D13_STRIDE = C;         // TMEM columns between the accumulators of even / odd tiles
-  static constexpr int D2_BASE_EVEN = 256;     // C = 256: D2 of a tile lives in the D13 columns of the other parity
+  static constexpr int NS = (C == 256) ? 5 : 7;  // ring slots of 16 KB
+  static constexpr int STG_BYTES = 4 * 4096;     // staging tiles of the LayerNorm2 warps (32 rows x 32 fp32 each)
+  static constexpr int SMEM = L_BYTES + M_BYTES + NS * kKbBytes + STG_BYTES + 1024;
+  // TMEM: D3 (mlp.2 accumulator) in columns [0, C); a 256-column scratch at [256, 512) holds D1 (merge accumulator, read by
+  // LayerNorm1) and, once that is consumed, the two 128-column D2 buffers of the hidden-layer chunks.
+  static constexpr int SCRATCH = 256;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
   __shared__ __align__(8) uint64_t s_bars[2 * NS + 12];
   __shared__ uint32_t s_tmem_base;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sL = base, sM = base + G::L_BYTES, sRing = sM + G::M_BYTES;
+  const uint32_t sL = base, sM = base + G::L_BYTES, sRing = sM + G::M_BYTES, sStg = sRing + NS * kKbBytes;
   const uint32_t bb = smem_u32(s_bars);
   auto full = [&](int s) { return bb + 8u * s; };
   auto empty = [&](int s) { return bb + 8u * (NS + s); };
@@ -98,9 +102,9 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmMsg); tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmWm); tma_prefetch_desc(&p.tmW0); tma_prefetch_desc(&p.tmW2);
     for (int s = 0; s < 2 * NS; ++s) mbar_init(bb + 8u * s, 1);
-    mbar_init(m_full, 1); mbar_init(d1_full, 1); mbar_init(ln1_ready, kEpiWarps); mbar_init(d3_full, 1);
+    mbar_init(m_full, 1); mbar_init(d1_full, 1); mbar_init(ln1_ready, 4); mbar_init(d3_full, 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(d2_full(b), 1); mbar_init(h1_full(b), kEpiWarps); mbar_init(h1_empty(b), 1); mbar_init(d13_empty(b), kEpiWarps);
+      mbar_init(d2_full(b), 1); mbar_init(h1_full(b), 4); mbar_init(h1_empty(b), 1); mbar_init(d13_empty(b), 4);
     }
     fence_barrier_init();
   }
@@ -196,26 +200,24 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
     };
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const int par = it & 1;
-      const uint32_t d13 = tmem_base + static_cast<uint32_t>(par * G::D13_STRIDE);
-      const uint32_t d2b = tmem_base + static_cast<uint32_t>(C == 256 ? (1 - par) * 256 : 256);
-      if (it >= 2) mbar_wait(d13_empty(par), ((it >> 1) - 1) & 1, 21);   // LayerNorm2 of tile it-2 has read these columns
+      const uint32_t d3 = tmem_base;                                       // mlp.2 accumulator
+      const uint32_t d1 = tmem_base + G::SCRATCH, d2b = tmem_base + G::SCRATCH;   // merge accumulator, then the two D2 buffers
       stamp(0, 100 * it);
-      // ---- GEMM1: D13 = message @ Wm^T
+      // ---- GEMM1: D1 = message @ Wm^T  (the scratch is free: every D2 chunk of the previous tile was consumed before its last GEMM3)
       for (int kb = 0; kb < KB; ++kb) {
         const uint32_t a = take();
         tc_fence_after();
         for (int h = 0; h < NH; ++h) {
           const uint32_t b = take();
           tc_fence_after();
-          mma4(d13 + 128u * h, a, b, kb == 0);
+          mma4(d1 + 128u * h, a, b, kb == 0);
         }
         if (n_unrel >= kRelBatch) flush(0);
       }
       flush(d1_full);
       stamp(0, 100 * it + 1);
-      if (C == 256 && it >= 1) mbar_wait(d13_empty(1 - par), ((it - 1) >> 1) & 1, 24);   // D2 columns = D13 of the previous tile
-      bool ln_ok = false;
+      mbar_wait(ln1_ready, it & 1, 26);          // LayerNorm1 has read D1 (the D2 buffers overwrite it) and written region L
+      bool d3_ok = it == 0;
       auto g2 = [&](int q) {
         const uint32_t d2 = d2b + static_cast<uint32_t>((q & 1) * 128);
         for (int kb = 0; kb < 2 * KB; ++kb) {
@@ -223,7 +225,6 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
           if (kb < KB) {
             a = take();
           } else {
-            if (!ln_ok) { mbar_wait(ln1_ready, it & 1, 26); ln_ok = true; }
             a = sL + (kb - KB) * kKbBytes;
           }
           const uint32_t b = take();
@@ -237,12 +238,13 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
       auto g3 = [&](int q) {
         const int u = it * (NQ / 2) + (q >> 1);                  // use index of H1 buffer q & 1
         mbar_wait(h1_full(q & 1), u & 1, 27);
+        if (!d3_ok) { mbar_wait(d13_empty(0), (it - 1) & 1, 21); d3_ok = true; }   // LayerNorm2 of the previous tile has read D3
         tc_fence_after();
         for (int j = 0; j < 2; ++j)
           for (int h = 0; h < NH; ++h) {
             const uint32_t b = take();
             tc_fence_after();
-            mma4(d13 + 128u * h, sM + (q & 1) * 2 * kKbBytes + j * kKbBytes, b, q == 0 && j == 0);
+            mma4(d3 + 128u * h, sM + (q & 1) * 2 * kKbBytes + j * kKbBytes, b, q == 0 && j == 0);
           }
         flush(q == NQ - 1 ? 0u : h1_empty(q & 1));
         if (q == NQ - 1 && elect_one_sync()) { tc_commit(h1_empty(q & 1)); tc_commit(d3_full); }
@@ -254,130 +256,116 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
     }
   } else {
     // ------------------------------------------------------------------------------------------ epilogue (thread = row)
+    // Two groups of four warps (one warp per TMEM lane quadrant each) that work on DIFFERENT tiles at the same time:
+    //   front (warps 2-5): LayerNorm1 of the merge output -> region L, then relu + bf16 of every hidden chunk -> H1 buffers
+    //   back  (warps 6-9): LayerNorm2 of the mlp.2 output + residual -> fp32 x and its bf16 shadow in global memory
+    // While the back group streams tile i to HBM (the long, bandwidth-bound phase), the front group and the tensor pipe are
+    // already in tile i+1; the MMA issuer only waits for the back group before the first GEMM3 of tile i+1 overwrites D3.
     const int q4 = warp & 3;                                    // TMEM lane quadrant of this warp
+    const bool back = warp >= 6;
     const int r = q4 * 32 + lane;                               // row of the tile
     const uint32_t lane_off = static_cast<uint32_t>(q4 * 32) << 16;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
-    // staging tile of the LayerNorm2 store phase: the 4 KB of region L that hold THIS warp's rows of k-block 0 — the only
-    // part of L no other warp writes (a faster warp may already be in LayerNorm1 of the next tile). 32 rows x 32 floats,
-    // 16-byte chunk j of row i stored at chunk position j ^ (i & 7): conflict-free for the row-wise writes and the
-    // transposed reads alike.
-    // The two warps of a quadrant (half = 0 / 1) own the same 32 rows and alternate the 32-column chunks. Their private
-    // scratch lives in the rows of region L that only this pair ever writes: the staging tile of warp `half` in its rows
-    // of k-block `half`, the statistics exchange (8 bytes per row and half) at the start of its rows of k-block 0 — read
-    // and overwritten only between two pair barriers.
-    const int half = (warp - 2) >> 2;
-    float* stg = reinterpret_cast<float*>(smem_raw + (sL - smem_u32(smem_raw))) + half * (kKbBytes / 4) + q4 * 1024;
-    float* exch = reinterpret_cast<float*>(smem_raw + (sL - smem_u32(smem_raw))) + q4 * 1024 + lane * 32;   // this row's 128 bytes in k-block 0
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q4) : "memory"); };
-    const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
-    constexpr int kHalfCols = C / 2;
-    const float inv_h = 1.f / static_cast<float>(kHalfCols);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const int par = it & 1;
-      int rin;
-      const long long row0 = tile_row0(tile, rin);
-      const uint32_t d13 = tmem_base + static_cast<uint32_t>(par * G::D13_STRIDE) + lane_off;
-      const uint32_t d2b = tmem_base + static_cast<uint32_t>(C == 256 ? (1 - par) * 256 : 256) + lane_off;
-      // row statistics of a [128 x C] accumulator in one pass: sums of (v - v0), v0 = the row's first element
-      // (v - v0 with v0 = the first element this warp sees), over this warp's chunks; the two halves are merged with the
-      // pairwise-variance formula (equal counts): mean = (m0 + m1) / 2, M2 = M2_0 + M2_1 + (m0 - m1)^2 * n / 2, n = C / 2
-      auto row_stats = [&](uint32_t acc, float& mean, float& rstd) {
-        float v0 = 0.f, s1 = 0.f, s2 = 0.f;
-        for (int c0 = 32 * half; c0 < C; c0 += 64) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(acc + static_cast<uint32_t>(c0), v);
-          tmem_ld_wait();
-          if (c0 == 32 * half) v0 = __uint_as_float(v[0]);
+    const float inv_c = 1.f / static_cast<float>(C);
+    // row statistics of a [128 x C] accumulator in one pass: sums of (v - v0), v0 = the row's first element
+    auto row_stats = [&](uint32_t acc, float& mean, float& rstd) {
+      float v0 = 0.f, s1 = 0.f, s2 = 0.f;
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(acc + static_cast<uint32_t>(c0), v);
+        tmem_ld_wait();
+        if (c0 == 0) v0 = __uint_as_float(v[0]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = __uint_as_float(v[j]) - v0;
-            s1 += d;
-            s2 = fmaf(d, d, s2);
-          }
+        for (int j = 0; j < 32; ++j) {
+          const float d = __uint_as_float(v[j]) - v0;
+          s1 += d;
+          s2 = fmaf(d, d, s2);
         }
-        const float md = s1 * inv_h;
-        const float m_own = v0 + md, M2_own = fmaxf(fmaf(-md, s1, s2), 0.f);      // sum (v - m_own)^2 = s2 - s1^2 / n
-        exch[2 * half] = m_own;
-        exch[2 * half + 1] = M2_own;
-        pair_sync();
-        const float m_oth = exch[2 * (1 - half)], M2_oth = exch[2 * (1 - half) + 1];
-        pair_sync();                                   // both have read: the rows may be overwritten from here on
-        const float dm = m_own - m_oth;
-        mean = 0.5f * (m_own + m_oth);
-        rstd = rsqrtf((M2_own + M2_oth + dm * dm * (0.5f * kHalfCols)) * (1.f / static_cast<float>(C)) + 1e-5f);
-      };
-      // ---- E1: LayerNorm1 of the merge output -> bf16 A operand (region L)
-      mbar_wait(d1_full, it & 1, 31);
-      tc_fence_after();
-      if (warp == 2) stamp(1, 100 * it + 1);
-      {
-        float mean, rstd;
-        row_stats(d13, mean, rstd);
-        for (int c0 = 32 * half; c0 < C; c0 += 64) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(d13 + static_cast<uint32_t>(c0), v);
-          tmem_ld_wait();
-          uint32_t o[16];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {                           // the same 4 gammas / betas for every lane: broadcast 16-byte loads
-            const float4 g = __ldg(reinterpret_cast<const float4*>(p.g1 + c0) + j);
-            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.b1 + c0) + j);
-            o[2 * j] = pack_bf16x2(fmaf((__uint_as_float(v[4 * j]) - mean) * rstd, g.x, bt.x),
-                                   fmaf((__uint_as_float(v[4 * j + 1]) - mean) * rstd, g.y, bt.y));
-            o[2 * j + 1] = pack_bf16x2(fmaf((__uint_as_float(v[4 * j + 2]) - mean) * rstd, g.z, bt.z),
-                                       fmaf((__uint_as_float(v[4 * j + 3]) - mean) * rstd, g.w, bt.w));
-          }
-          const uint32_t rowa = sL + (c0 >> 6) * kKbBytes + r * 128;
-          const uint32_t cc0 = static_cast<uint32_t>((c0 & 63) >> 3);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (((cc0 + i) ^ sw) << 4)), "r"(o[4 * i]),
-                         "r"(o[4 * i + 1]), "r"(o[4 * i + 2]), "r"(o[4 * i + 3]) : "memory");
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(ln1_ready);
-        if (warp == 2) stamp(1, 100 * it + 2);
       }
-      // ---- E2: relu + bf16 of hidden chunk q -> H1 buffer q & 1 (A operand of GEMM3)
-      for (int q = 0; q < NQ; ++q) {
-        const int b = q & 1;
-        const int u = it * (NQ / 2) + (q >> 1);
-        mbar_wait(d2_full(b), u & 1, 32);
+      const float md = s1 * inv_c;
+      mean = v0 + md;
+      rstd = rsqrtf(fmaxf(fmaf(-md, md, s2 * inv_c), 0.f) + 1e-5f);
+    };
+    if (!back) {
+      const uint32_t d1 = tmem_base + G::SCRATCH + lane_off, d2b = d1;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        // ---- E1: LayerNorm1 of the merge output -> bf16 A operand (region L)
+        mbar_wait(d1_full, it & 1, 31);
         tc_fence_after();
-        if (u >= 1) mbar_wait(h1_empty(b), (u - 1) & 1, 33);   // GEMM3 of the previous use of this buffer has read it
-        if (warp == 2) stamp(1, 100 * it + 10 + q);
-        const uint32_t acc = d2b + static_cast<uint32_t>(b * 128);
-        for (int c0 = 32 * half; c0 < 128; c0 += 64) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(acc + static_cast<uint32_t>(c0), v);
-          tmem_ld_wait();
-          uint32_t o[16];
+        if (warp == 2) stamp(1, 100 * it + 1);
+        {
+          float mean, rstd;
+          row_stats(d1, mean, rstd);
+          for (int c0 = 0; c0 < C; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(d1 + static_cast<uint32_t>(c0), v);
+            tmem_ld_wait();
+            uint32_t o[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            o[j] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * j]), 0.f), fmaxf(__uint_as_float(v[2 * j + 1]), 0.f));
-          const uint32_t rowa = sM + b * 2 * kKbBytes + (c0 >> 6) * kKbBytes + r * 128;
-          const uint32_t cc0 = static_cast<uint32_t>((c0 & 63) >> 3);
+            for (int j = 0; j < 8; ++j) {                         // the same 4 gammas / betas for every lane: broadcast 16-byte loads
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.g1 + c0) + j);
+              const float4 bt = __ldg(reinterpret_cast<const float4*>(p.b1 + c0) + j);
+              o[2 * j] = pack_bf16x2(fmaf((__uint_as_float(v[4 * j]) - mean) * rstd, g.x, bt.x),
+                                     fmaf((__uint_as_float(v[4 * j + 1]) - mean) * rstd, g.y, bt.y));
+              o[2 * j + 1] = pack_bf16x2(fmaf((__uint_as_float(v[4 * j + 2]) - mean) * rstd, g.z, bt.z),
+                                         fmaf((__uint_as_float(v[4 * j + 3]) - mean) * rstd, g.w, bt.w));
+            }
+            const uint32_t rowa = sL + (c0 >> 6) * kKbBytes + r * 128;
+            const uint32_t cc0 = static_cast<uint32_t>((c0 & 63) >> 3);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (((cc0 + i) ^ sw) << 4)), "r"(o[4 * i]),
-                         "r"(o[4 * i + 1]), "r"(o[4 * i + 2]), "r"(o[4 * i + 3]) : "memory");
+            for (int i = 0; i < 4; ++i)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (((cc0 + i) ^ sw) << 4)), "r"(o[4 * i]),
+                           "r"(o[4 * i + 1]), "r"(o[4 * i + 2]), "r"(o[4 * i + 3]) : "memory");
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ln1_ready);
+          if (warp == 2) stamp(1, 100 * it + 2);
         }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(h1_full(b));
-        if (warp == 2) stamp(1, 100 * it + 20 + q);
+        // ---- E2: relu + bf16 of hidden chunk q -> H1 buffer q & 1 (A operand of GEMM3)
+        for (int q = 0; q < NQ; ++q) {
+          const int b = q & 1;
+          const int u = it * (NQ / 2) + (q >> 1);
+          mbar_wait(d2_full(b), u & 1, 32);
+          tc_fence_after();
+          if (u >= 1) mbar_wait(h1_empty(b), (u - 1) & 1, 33);   // GEMM3 of the previous use of this buffer has read it
+          if (warp == 2) stamp(1, 100 * it + 10 + q);
+          const uint32_t acc = d2b + static_cast<uint32_t>(b * 128);
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(acc + static_cast<uint32_t>(c0), v);
+            tmem_ld_wait();
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              o[j] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * j]), 0.f), fmaxf(__uint_as_float(v[2 * j + 1]), 0.f));
+            const uint32_t rowa = sM + b * 2 * kKbBytes + (c0 >> 6) * kKbBytes + r * 128;
+            const uint32_t cc0 = static_cast<uint32_t>((c0 & 63) >> 3);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (((cc0 + i) ^ sw) << 4)), "r"(o[4 * i]),
+                           "r"(o[4 * i + 1]), "r"(o[4 * i + 2]), "r"(o[4 * i + 3]) : "memory");
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(h1_full(b));
+          if (warp == 2) stamp(1, 100 * it + 20 + q);
+        }
       }
-      // ---- E3: x += LayerNorm2(mlp.2 output); fp32 x and its bf16 shadow, coalesced through a per-warp staging tile
-      mbar_wait(d3_full, it & 1, 34);
-      tc_fence_after();
-      if (warp == 2) stamp(1, 100 * it + 30);
-      {
-        // the residual rows of a chunk are requested one chunk ahead of their use (the first before the statistics pass):
+    } else {
+      // ---- E3: x += LayerNorm2(mlp.2 output); fp32 x and its bf16 shadow, coalesced through this warp's private staging tile
+      // (32 rows x 32 floats, 16-byte chunk j of row i at chunk position j ^ (i & 7): conflict-free both ways)
+      const uint32_t d3 = tmem_base + lane_off;
+      float* stg = reinterpret_cast<float*>(smem_raw + (sStg - smem_u32(smem_raw))) + q4 * 1024;
+      const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        int rin;
+        const long long row0 = tile_row0(tile, rin);
+        // the residual rows of a chunk are requested one chunk ahead of their use (the first before the accumulator is ready):
         // 8 independent 16-byte loads in flight per lane instead of one DRAM round trip per store
         const long long grow0 = row0 + q4 * 32;                  // first row of this warp
         const bool ok = rin + r < live;
@@ -392,9 +380,12 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
             if ((okm >> k) & 1u) xn[k] = *reinterpret_cast<const float4*>(p.x + (grow0 + k * 4 + sub_r) * p.ldx + c0 + sub_c);
           }
         };
-        load_res(32 * half);
+        load_res(0);
+        mbar_wait(d3_full, it & 1, 34);
+        tc_fence_after();
+        if (warp == 6) stamp(3, 100 * it + 30);
         float mean, rstd;
-        row_stats(d13, mean, rstd);
+        row_stats(d3, mean, rstd);
         float mk[8], rk[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -402,10 +393,15 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
           mk[k] = __shfl_sync(0xffffffffu, mean, rr);
           rk[k] = __shfl_sync(0xffffffffu, rstd, rr);
         }
-        for (int c0 = 32 * half; c0 < C; c0 += 64) {
+        for (int c0 = 0; c0 < C; c0 += 32) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(d13 + static_cast<uint32_t>(c0), v);
+          tmem_ld_32x32b_x32(d3 + static_cast<uint32_t>(c0), v);
           tmem_ld_wait();
+          if (c0 + 32 >= C) {                                    // last read of D3: the tensor pipe may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d13_empty(0));
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -415,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
           float4 xc[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) xc[k] = xn[k];
-          if (c0 + 64 < C) load_res(c0 + 64);
+          if (c0 + 32 < C) load_res(c0 + 32);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             if (!((okm >> k) & 1u)) continue;
@@ -433,11 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) encoder_tail_kernel(const __grid_
           }
           __syncwarp();
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(d13_empty(par));
-        pair_sync();      // the partner's staging tile / this pair's exchange rows are rewritten by the next tile's LayerNorm1
-        if (warp == 2) stamp(1, 100 * it + 31);
+        if (warp == 6) stamp(3, 100 * it + 31);
       }
     }
   }

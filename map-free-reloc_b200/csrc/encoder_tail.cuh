@@ -20,7 +20,7 @@ struct alignas(64) EncoderTailParams {
   int n_img;           // row blocks ("images" / window sides), each rows_cap rows apart
   long long rows_cap;  // rows per block (capacity)
   const int* dyn_rows; // device: live rows per block (null = rows_cap)
-  long long* dbg;      // optional (debug): block 0 appends (id, globaltimer ns) pairs per role: MMA [0,64), epilogue [64,128), TMA [128,192)
+  long long* dbg;      // optional (debug): block 0 appends (id, globaltimer ns) pairs per role: MMA [0,64), front epilogue [64,128), TMA [128,192), back epilogue [192,256)
 };
 
 struct EncoderTailDesc {
