@@ -245,7 +245,8 @@ float mfr_debug_probe_overhead(int mode, int smem_bytes, int grid, int iters);
 /* tensor-pipe probe: ns per tcgen05.mma (128 x BN x 32 B of K, operands resident in shared memory) when one
  * thread issues n_per_commit MMAs per tcgen05.commit, optionally waiting for each commit */
 float mfr_debug_mma_probe(int n_per_commit, int BN, int bf16, int wait_each, int iters, int grid, int two_commits);
-/* flags: bit 0 = x/w are bf16, bit 1 = out/residual are bf16; residual may be NULL */
+/* flags: bit 0 = x/w are bf16, bit 1 = out/residual are bf16, bit 2 = channel strides padded to multiples of 8 elements;
+ * residual may be NULL */
 float mfr_debug_time_conv(const float* x, int N, int H, int W, int Cin, const float* w, int Cout, int R,
                           int stride, float* out, int iters, int flags, const float* residual);
 

@@ -265,6 +265,9 @@ float mfr_debug_time_conv(const float* x, int N, int H, int W, int Cin, const fl
   d.w = w; d.Cout = Cout; d.R = R; d.S = R; d.stride = stride; d.pad = R / 2;
   d.act = 1; d.alpha = 1.f; d.out = out; d.ldo = Cout; d.ldr = Cout;
   d.in_bf16 = flags & 1; d.out_bf16 = (flags >> 1) & 1; d.residual = residual;
+  if (flags & 4) {   // channel strides padded to multiples of 8 elements (how the engine stores the 196-channel maps)
+    d.ldx = (Cin + 7) / 8 * 8; d.ldw = d.ldx; d.ldo = (Cout + 7) / 8 * 8; d.ldr = d.ldo;
+  }
   mfr::ConvGemmParams p;
   if (mfr::conv_gemm_build(d, &p) != MFR_OK) return -1.f;
   return mfr::conv_gemm_time_prebuilt(p, iters, nullptr);

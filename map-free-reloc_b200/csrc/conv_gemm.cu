@@ -51,6 +51,17 @@ __device__ __forceinline__ long long gtime() {
   return t;
 }
 #define MFR_STAMP(i) do { if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[i] = gtime(); } while (0)
+// debug launches only (p.dbg set): SM cycles block 0 spends inside a barrier wait, summed into `acc`
+#define MFR_TIMED_WAIT(acc, bar, parity, tag)                 \
+  do {                                                        \
+    if (dbg_on) {                                             \
+      const long long t0_ = clock64();                        \
+      mbar_wait(bar, parity, tag);                            \
+      acc += clock64() - t0_;                                 \
+    } else {                                                  \
+      mbar_wait(bar, parity, tag);                            \
+    }                                                         \
+  } while (0)
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.f);
@@ -348,7 +359,12 @@ __device__ __forceinline__ uint64_t desc32_at(uint32_t addr) { return kDescHi32 
 
 // EPI = number of epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, alternating 32-column chunks; only the
 // generic vector-store epilogue: token GEMMs with wide bf16 outputs, whose per-chunk latency is what bounds them)
-template <int EPI>
+// PAIR: the CTA-pair instantiation (clusters of two, tcgen05 cta_group::2). The two CTAs take neighbouring pixel tiles of the
+// same N tile; each loads its own A tile and HALF of the filter rows, the leader (cluster rank 0) issues one M = 256 MMA per
+// k-step over both CTAs' shared memory and tensor memory. Per SM and instruction the tensor pipe then reads 128 + BN / 2
+// operand rows instead of 128 + BN (the MMA rate is bound by that read, profiles/r01_mma_probe.txt) and half the weight
+// bytes come through L2. 3x3 halo mode only.
+template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(64 + 32 * EPI, 1)
 conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   constexpr int kEpiWarps = EPI;
@@ -374,29 +390,35 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
+  long long w_a = 0, w_b = 0, w_t = 0, w_c = 0;   // debug (w_c: the MMA issuer's commit sections): cycles waited for A slots / B slots / accumulator hand-over by this warp's role
+  const long long t_role0 = dbg_on ? clock64() : 0;
   if (threadIdx.x == 0) MFR_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < 4 * kMaxSlots; ++s) mbar_init(bar_base + 8u * s, 1);
-    if (p.mcast)   // a shared weight slot is free when BOTH CTAs of the pair have consumed it
-      for (int s = 0; s < kMaxSlots; ++s) mbar_init(b_empty(s), 2);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), kDualIssue ? 2 : 1);   // every MMA issuer commits the accumulator
-      mbar_init(tempty_bar(a), kEpiWarps);
+      mbar_init(tempty_bar(a), PAIR ? 2 * kEpiWarps : kEpiWarps);   // pair: the epilogue warps of both CTAs report to the leader
       mbar_init(tstart_bar(a), 1);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&s_tmem_base), kTmemCols);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc2(smem_u32(&s_tmem_base), kTmemCols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(smem_u32(&s_tmem_base), kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (p.mcast) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   const uint32_t tmem_base = s_tmem_base;
   if (threadIdx.x == 0) MFR_STAMP(1);
 
@@ -410,13 +432,15 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
   const int tile_rows = p.MT * p.TH;          // output rows of one CTA tile
   // work items: tiles (item -> tile), or in multicast mode PAIRS of neighbouring pixel tiles of one N tile
   // (item -> pair; this CTA takes tile 2*pm + rank of the pair, the last odd one is computed twice)
-  const int crank = p.mcast ? static_cast<int>(cluster_ctarank()) : 0;
+  const int crank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
   const int pairs_per_nt = (m_tiles + 1) >> 1;
-  const int item_first = p.mcast ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int item_step = p.mcast ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int item_count = p.mcast ? pairs_per_nt * p.n_tiles : total_tiles;
+  const int item_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int item_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int item_count = PAIR ? pairs_per_nt * p.n_tiles : total_tiles;
+  // the leader's barriers as seen from either CTA of the pair (shared::cluster addresses)
+  const uint32_t lead_off = PAIR ? mapa_shared(bar_base, 0u) - bar_base : 0u;
   auto item_tile = [&](int item, int& mt, int& nt) {
-    if (p.mcast) {
+    if (PAIR) {
       nt = item / pairs_per_nt;
       mt = min(2 * (item - nt * pairs_per_nt) + crank, m_tiles - 1);
     } else {
@@ -452,27 +476,33 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
           const CUtensorMap* tmB = tail ? &p.tmB2 : &p.tmB;
           const uint32_t ab = tail ? p.a_bytes2 : a_bytes, bb = tail ? p.b_bytes2 : b_bytes;
           for (int kx = 0; kx < 3; ++kx) {
-            mbar_wait(a_empty(sa), pa ^ 1u, 1);
+            MFR_TIMED_WAIT(w_a, a_empty(sa), pa ^ 1u, 1);
             if (elect_one_sync()) {
-              mbar_arrive_expect_tx(a_full(sa), ab);
-              tma_load_4d(smem_a + sa * a_slot_bytes, tmA, a_full(sa), c0, x_in0 + kx, y_in0, img);
+              if constexpr (PAIR) {   // both CTAs' boxes are counted on the leader's barrier
+                if (crank == 0) mbar_arrive_expect_tx(a_full(sa), 2 * ab);
+                tma_load_4d_2sm(smem_a + sa * a_slot_bytes, tmA, a_full(sa) + lead_off, c0, x_in0 + kx, y_in0, img);
+              } else {
+                mbar_arrive_expect_tx(a_full(sa), ab);
+                tma_load_4d(smem_a + sa * a_slot_bytes, tmA, a_full(sa), c0, x_in0 + kx, y_in0, img);
+              }
             }
             if (++sa == a_slots) { sa = 0; pa ^= 1u; }
             for (int ky = 0; ky < 3; ++ky) {
-              mbar_wait(b_empty(sb), pb ^ 1u, 5);
+              MFR_TIMED_WAIT(w_b, b_empty(sb), pb ^ 1u, 5);
               if (elect_one_sync()) {
-                mbar_arrive_expect_tx(b_full(sb), bb);
-                if (p.mcast)   // my half of the filter rows, to both CTAs of the pair
-                  tma_load_3d_mcast(smem_b + sb * b_bytes + crank * (bb >> 1), tmB, b_full(sb), c0, ky * 3 + kx,
-                                    n0 + crank * (p.BN >> 1), static_cast<uint16_t>(3));
-                else
+                if constexpr (PAIR) {   // my half of the filter rows (b_bytes = bytes of one half)
+                  if (crank == 0) mbar_arrive_expect_tx(b_full(sb), 2 * bb);
+                  tma_load_3d_2sm(smem_b + sb * b_bytes, tmB, b_full(sb) + lead_off, c0, ky * 3 + kx, n0 + crank * (p.BN >> 1));
+                } else {
+                  mbar_arrive_expect_tx(b_full(sb), bb);
                   tma_load_3d(smem_b + sb * b_bytes, tmB, b_full(sb), c0, ky * 3 + kx, n0);
+                }
               }
               if (++sb == b_slots) { sb = 0; pb ^= 1u; }
             }
           }
         }
-      } else {
+      } else if constexpr (!PAIR) {
         const int bz = p.b_batched ? img : -1;
         for (int cb = 0; cb < kb_per_tap; ++cb) {
           const int c0 = cb * kblk;
@@ -500,6 +530,8 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
         }
       }
     }
+  } else if (PAIR && warp == 1 && crank != 0) {
+    // the leader issues the pair's MMAs
   } else if (warp == 1 || warp == kMma2Warp) {
     // ------------------------------------------------------------------ MMA issuers
     // Two warps issue alternate commit groups into the same accumulator: a tcgen05.commit stalls its issuing thread
@@ -509,7 +541,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     // tells the other one (tstart barrier) once that group is in the pipe.
     const int role = warp == 1 ? 0 : 1;
     int gcount = 0;                           // commit groups issued so far by both issuers together (parity = owner)
-    const uint32_t idesc = umma_idesc(p.in_bf16 ? 1u : 2u, kTileM, static_cast<uint32_t>(p.BN));
+    const uint32_t idesc = umma_idesc(p.in_bf16 ? 1u : 2u, PAIR ? 2 * kTileM : kTileM, static_cast<uint32_t>(p.BN));
     const uint32_t idesc_swap = umma_idesc(p.in_bf16 ? 1u : 2u, kTileM, 2u * kTileM);
     const bool bf16_in = p.in_bf16 != 0;
     const int MT = p.MT, ksteps_last = p.ksteps_last;
@@ -521,7 +553,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int item = item_first; item < item_count; item += item_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
+      MFR_TIMED_WAIT(w_t, tempty_bar(acc), acc_phase ^ 1u, 2);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
       const bool first_owner = !kDualIssue || (gcount & 1) == role;   // this issuer has the tile's first group
@@ -545,13 +577,13 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
               mbar_wait(tstart_bar(acc), acc_phase, 9);
               started = true;
             }
-            mbar_wait(a_full(sa), pa, 3);
+            MFR_TIMED_WAIT(w_a, a_full(sa), pa, 3);
             const uint32_t a_slot = smem_a + sa * a_slot_bytes;
             const int sb0 = sb;
             for (int ky = 0; ky < 3; ++ky) {
-              mbar_wait(b_full(sb), pb, 6);
+              MFR_TIMED_WAIT(w_b, b_full(sb), pb, 6);
               tc_fence_after();
-              if (p.swap) {
+              if (!PAIR && p.swap) {
                 if (elect_one_sync()) {   // filters are the M operand, the tile's 256 pixels the N operand
                   const uint64_t wdesc = dhi | (((smem_b + sb * b_bytes) >> 4) & 0x3fffu);
                   const uint64_t xdesc = dhi | (((a_slot + ky * kyb) >> 4) & 0x3fffu);
@@ -569,8 +601,13 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
                   const uint32_t d_addr = tmem_acc + static_cast<uint32_t>(m * 128);
                   uint32_t acc_m = accum;
                   for (int k = 0; k < nk; ++k) {   // +32 B of K per step = +2 in the descriptor address field
-                    if (bf16_in) tc_mma_bf16(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, acc_m);
-                    else tc_mma_tf32(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, acc_m);
+                    if constexpr (PAIR) {          // the same descriptors address both CTAs' shared memory
+                      if (bf16_in) tc_mma_bf16_2(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, acc_m);
+                      else tc_mma_tf32_2(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, acc_m);
+                    } else {
+                      if (bf16_in) tc_mma_bf16(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, acc_m);
+                      else tc_mma_tf32(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, acc_m);
+                    }
                     acc_m = 1u;
                   }
                 }
@@ -579,23 +616,26 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
               if (++sb == b_slots) { sb = 0; pb ^= 1u; }
             }
             // one pipeline drain per group: release the three B slots and the A slot together
+            const long long tc0 = dbg_on ? clock64() : 0;
             if (elect_one_sync()) {
               int s2 = sb0;
-              if (p.mcast) {   // the weight slots are shared by the pair: tell both producers
-                tc_commit_mcast(b_empty(s2), 3);
+              if constexpr (PAIR) {   // the slots of both CTAs were read: tell both producers
+                tc_commit2_mcast(b_empty(s2), 3);
                 if (++s2 == b_slots) s2 = 0;
-                tc_commit_mcast(b_empty(s2), 3);
+                tc_commit2_mcast(b_empty(s2), 3);
                 if (++s2 == b_slots) s2 = 0;
-                tc_commit_mcast(b_empty(s2), 3);
+                tc_commit2_mcast(b_empty(s2), 3);
+                tc_commit2_mcast(a_empty(sa), 3);
               } else {
                 tc_commit(b_empty(s2));
                 if (++s2 == b_slots) s2 = 0;
                 tc_commit(b_empty(s2));
                 if (++s2 == b_slots) s2 = 0;
                 tc_commit(b_empty(s2));
+                tc_commit(a_empty(sa));
               }
-              tc_commit(a_empty(sa));
             }
+            if (dbg_on) { __syncwarp(); w_c += clock64() - tc0; }
             if (kDualIssue && g == 0) {                // (first_owner) the tile's first MMAs are queued
               __syncwarp();
               if (lane == 0) mbar_arrive(tstart_bar(acc));
@@ -603,7 +643,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
             if (++sa == a_slots) { sa = 0; pa ^= 1u; }
           }
         }
-      } else {
+      } else if constexpr (!PAIR) {
         const int num_kb = R * S * kb_per_tap, taps = R * S;
         int in_batch = 0, batch_first = sa, tap = 0, cb = 0;
         for (int i = 0; i < num_kb; ++i) {
@@ -620,7 +660,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
             mbar_wait(tstart_bar(acc), acc_phase, 9);
             started = true;
           }
-          mbar_wait(a_full(sa), pa, 3);
+          MFR_TIMED_WAIT(w_a, a_full(sa), pa, 3);
           tc_fence_after();
           if (elect_one_sync()) {
             const bool tail = p.tail32 && cb == kb_per_tap - 1;
@@ -658,7 +698,10 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
         }
       }
       gcount += g;
-      if (elect_one_sync()) tc_commit(tfull_bar(acc));
+      if (elect_one_sync()) {
+        if constexpr (PAIR) tc_commit2_mcast(tfull_bar(acc), 3);   // the accumulator halves of both CTAs are complete
+        else tc_commit(tfull_bar(acc));
+      }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (kEpiWarps warps)
@@ -684,6 +727,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       const int ty = (mt / tiles_x) % p.tiles_y;
       const int img = mt / (tiles_x * p.tiles_y);
       const int n0 = nt * p.BN;
+      if (dbg_on) MFR_TIMED_WAIT(w_t, tfull_bar(acc), acc_phase, 4);   // (the epilogue's own wait then falls through)
       if (p.swap) {
         const uint32_t taddr_s = tmem_base + static_cast<uint32_t>(acc * kMaxBN) + (static_cast<uint32_t>(q * 32) << 16);
 #define MFR_EPS(ACTV)                                                                                              \
@@ -765,7 +809,10 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(tempty_bar(acc) + lead_off);
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (it == 0 && threadIdx.x == 64) MFR_STAMP(7);
     }
     if (p.tma_store) {   // bulk stores are tracked per issuing thread: every lane may have been elected
@@ -773,12 +820,17 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   }
 
+  if (dbg_on && lane == 0 && warp < 3) {   // roles: 0 producer, 1 MMA issuer, 2 first epilogue warp
+    p.dbg[16 + 4 * warp] = w_a; p.dbg[17 + 4 * warp] = w_b; p.dbg[18 + 4 * warp] = w_t; p.dbg[19 + 4 * warp] = clock64() - t_role0;
+    if (warp == 1) p.dbg[28] = w_c;
+  }
   tc_fence_before();
   __syncthreads();
-  if (p.mcast) cluster_sync_all();   // no CTA leaves while its peer may still multicast into its shared memory / barriers
+  if constexpr (PAIR) cluster_sync_all();   // no CTA leaves while its peer may still arrive on its barriers / use its tensor memory
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (PAIR) tmem_dealloc2(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
   if (threadIdx.x == 0) MFR_STAMP(8);
 }
@@ -808,7 +860,7 @@ EncodeTiledFn get_encode_fn() {
 
 // Tiling of one op: output tile = MT sub-tiles of TW x TH (<= 128) pixels, BN output channels.
 struct TileCfg {
-  int TW, TH, MT, BN, n_tiles, halo, swap, mcast;
+  int TW, TH, MT, BN, n_tiles, halo, swap, pair;
   double cost;
 };
 
@@ -819,10 +871,10 @@ struct TileCfg {
 //   epilogue : ~500 ns per 32-channel chunk of a 128-pixel sub-tile (4 epilogue warps)
 // times the number of waves of tiles over the SMs.
 struct RingCfg { int a_slots, b_slots, cbatch, a_slot_bytes; };
-RingCfg ring_cfg(int halo, int MT, int TW, int TH, int BN, int ring_bytes = kRingBytes) {
+RingCfg ring_cfg(int halo, int MT, int TW, int TH, int BN, int ring_bytes = kRingBytes, int pair = 0) {
   const int kRingBytes = ring_bytes;      // shadows the constant: the 8-epilogue-warp launches have an 18 KB smaller ring
   RingCfg r{};
-  const int b_bytes = BN * 128;
+  const int b_bytes = (pair ? BN / 2 : BN) * 128;   // CTA pairs: each CTA holds half of the filter rows
   if (halo) {
     r.a_slot_bytes = TW * (MT * TH + 2) * 128;   // multiple of 1 KB (TW % 8 == 0)
     r.a_slots = 3;
@@ -843,7 +895,7 @@ RingCfg ring_cfg(int halo, int MT, int TW, int TH, int BN, int ring_bytes = kRin
 }
 
 TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, int pad, int kb_per_tap,
-                   int ksteps_last, bool allow_mt2, bool tma_store_ok, bool allow_swap, bool allow_mcast,
+                   int ksteps_last, bool allow_mt2, bool tma_store_ok, bool allow_swap, bool allow_pair,
                    bool single_row_tiles = false, int ring_bytes = kRingBytes) {
   const int sms = conv_gemm_num_sms();
   const int c16 = (Cout + 15) / 16 * 16;
@@ -892,15 +944,22 @@ TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, in
           if (f_swap != 1 && f_mc != 1 && (cost < best.cost * (1.0 - 1e-9) || (cost < best.cost * (1.0 + 1e-9) && tw > best.TW))) {
             best = TileCfg{tw, th, MT, BN, nt, halo, 0, 0, cost};
           }
-          // CTA pairs sharing the weight tiles by TMA multicast: half the weight bytes per CTA through L2
-          if (halo && allow_mcast && f_mc != 0 && f_swap != 1 && BN % 16 == 0) {
+          // CTA pairs (cta_group::2): per SM an MMA reads 128 + BN / 2 operand rows (133 B/ns) but cannot beat the math rate
+          // (~0.27 ns per accumulator column); half the weight bytes per CTA through L2
+          // Measured (scripts/pair_check.py, profiles/r02_pair_check.txt): 12-20 % faster than single CTAs on every 3x3 layer
+          // that cannot use the swapped-operand mode, slower than that mode where it applies (Cout <= 128, no residual).
+          const bool swap_applies = c16 <= 128 && allow_swap;
+          if (halo && allow_pair && f_mc != 0 && f_swap != 1 && BN % 16 == 0 && (!swap_applies || f_mc == 1)) {
+            const RingCfg rp = ring_cfg(1, MT, tw, th, BN, ring_bytes, 1);
             const long long m_tiles_c = tiles / nt;
             const long long pairs = ((m_tiles_c + 1) / 2) * nt;
+            const double mma_p = static_cast<double>(MT) * taps * ksteps_tap * std::max(30.5 + 0.12075 * BN, 0.27 * BN) + commits * 215.0;
             const double l2_m = (a_bytes + 0.5 * b_bytes) / 100.0;
-            const double t_m = std::max(mma, std::max(l2_m, epi)) + 800.0;
+            const double t_m = std::max(mma_p, std::max(l2_m, epi)) + 800.0;
             const int clusters = sms / 2;
             const double cost_m = static_cast<double>((pairs + clusters - 1) / clusters) * t_m;
-            if (cost_m < best.cost * (1.0 - 0.03)) best = TileCfg{tw, th, MT, BN, nt, 1, 0, 1, cost_m};   // needs a clear win
+            if (rp.a_slots >= 2 && rp.b_slots >= 4 && (f_mc == 1 || cost_m < best.cost * (1.0 - 0.03)) && (f_mc != 1 || !best.pair || cost_m < best.cost))
+              best = TileCfg{tw, th, MT, BN, nt, 1, 0, 1, cost_m};
           }
           // swapped operands: the MT = 2 halo geometry with the filters as the M operand (Cout <= 128, one N tile)
           if (halo && MT == 2 && nt == nt0 && c16 <= 128 && allow_swap && f_swap != 0 && (tw & (tw - 1)) == 0) {
@@ -916,8 +975,8 @@ TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, in
   }
   }
   if (getenv("MFR_CONV_DEBUG"))
-    fprintf(stderr, "[conv_gemm cfg] N%d %dx%d Cout%d R%d s%d kb%d -> TW%d TH%d MT%d BN%d nt%d halo%d swap%d mcast%d cost %.0f\n", N, Ho, Wo,
-            Cout, R, stride, kb_per_tap, best.TW, best.TH, best.MT, best.BN, best.n_tiles, best.halo, best.swap, best.mcast, best.cost);
+    fprintf(stderr, "[conv_gemm cfg] N%d %dx%d Cout%d R%d s%d kb%d -> TW%d TH%d MT%d BN%d nt%d halo%d swap%d pair%d cost %.0f\n", N, Ho, Wo,
+            Cout, R, stride, kb_per_tap, best.TW, best.TH, best.MT, best.BN, best.n_tiles, best.halo, best.swap, best.pair, best.cost);
   return best;
 }
 
@@ -931,6 +990,11 @@ int conv_gemm_num_sms() {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
   }
   return sms;
+}
+
+static bool pair_allowed() {
+  const char* e = getenv("MFR_CONV_PAIR");
+  return e == nullptr || atoi(e) != 0;
 }
 
 int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
@@ -978,11 +1042,10 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
                                  // swapped operands: not with a residual (measured: its transposed epilogue then becomes the bottleneck)
                                  (d.Cout % 4 == 0) && (d.ldo % 4 == 0) && !d.b_batched &&
                                      (d.residual == nullptr || (getenv("MFR_CONV_FORCE") != nullptr && d.ldr % 4 == 0)),
-                                 // CTA-pair weight multicast: measured no gain on B200 for these shapes (the layers are not L2-bound once the
-                                 // channel tail is narrow), so it is opt-in (MFR_CONV_MCAST=1 or the test hook)
-                                 !d.b_batched && d.dyn_w == nullptr && (getenv("MFR_CONV_MCAST") != nullptr || getenv("MFR_CONV_FORCE") != nullptr),
+                                 // CTA pairs (cta_group::2) for the 3x3 halo mode; MFR_CONV_PAIR=0 switches them off
+                                 !d.b_batched && d.dyn_w == nullptr && pair_allowed(),
                                  d.b_batched == 2, p->ring_bytes);
-  p->TW = cfg.TW; p->TH = cfg.TH; p->MT = cfg.MT; p->halo = cfg.halo; p->swap = cfg.swap; p->mcast = cfg.mcast;
+  p->TW = cfg.TW; p->TH = cfg.TH; p->MT = cfg.MT; p->halo = cfg.halo; p->swap = cfg.swap; p->pair = cfg.pair;
   p->BN = cfg.BN; p->n_tiles = cfg.n_tiles;
   p->tiles_x = (p->Wo + p->TW - 1) / p->TW;
   p->tiles_y = (p->Ho + p->MT * p->TH - 1) / (p->MT * p->TH);
@@ -991,9 +1054,9 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
   p->b_batched = d.b_batched;
   const int a_rows = p->halo ? p->MT * p->TH + 2 : p->MT * p->TH;   // pixel rows of the A box
   p->a_bytes = p->TW * a_rows * 128;
-  p->b_bytes = p->BN * 128;                                        // multiple of 2 KB (BN % 16 == 0)
+  p->b_bytes = (p->pair ? p->BN / 2 : p->BN) * 128;                // multiple of 1 KB (BN % 16 == 0); CTA pairs: one CTA's half
   {
-    const RingCfg rc = ring_cfg(p->halo, p->MT, p->TW, p->TH, p->BN, p->ring_bytes);
+    const RingCfg rc = ring_cfg(p->halo, p->MT, p->TW, p->TH, p->BN, p->ring_bytes, p->pair);
     p->a_slot_bytes = rc.a_slot_bytes; p->a_slots = rc.a_slots; p->b_slots = rc.b_slots; p->cbatch = rc.cbatch;
   }
   if (p->a_slots < 2 || p->b_slots < 2) return MFR_ERR_ARG;
@@ -1097,7 +1160,7 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
       strides[0] = (cuuint64_t)ldw_e * es;
       strides[1] = (cuuint64_t)ldw_e * es * taps;
     }
-    cuuint32_t box[3] = {(cuuint32_t)kblk, 1, (cuuint32_t)(p->mcast ? p->BN / 2 : p->BN)};   // multicast: each CTA of the pair loads half the rows
+    cuuint32_t box[3] = {(cuuint32_t)kblk, 1, (cuuint32_t)(p->pair ? p->BN / 2 : p->BN)};   // CTA pairs: each CTA loads half of the filter rows
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&p->tmB, d.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                      const_cast<float*>(d.w), dims,
@@ -1125,14 +1188,16 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
 int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream) {
   static bool attr_seen[64] = {};
   if (first_call_on_device(attr_seen)) {
-    MFR_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tf32_kernel<4>,
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tf32_kernel<4, false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    MFR_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tf32_kernel<8>,
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tf32_kernel<8, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tf32_kernel<4, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   }
   const int total = p.N * p.tiles_y * p.tiles_x * p.n_tiles;
   if (total <= 0) return MFR_OK;
-  if (p.mcast) {   // clusters of two CTAs, one pair of pixel tiles per cluster iteration
+  if (p.pair) {   // clusters of two CTAs, one pair of pixel tiles per cluster iteration
     const int m_tiles = p.N * p.tiles_y * p.tiles_x;
     const int pairs = ((m_tiles + 1) / 2) * p.n_tiles;
     const int clusters = std::min(pairs, conv_gemm_num_sms() / 2);
@@ -1146,12 +1211,12 @@ int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream) {
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    MFR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_tf32_kernel<4>, p));
+    MFR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_tf32_kernel<4, true>, p));
     return MFR_OK;
   }
   const int grid = std::min(total, conv_gemm_num_sms());
-  if (p.epi_warps == 8 && !p.swap && !p.tma_store && !p.mcast) conv_gemm_tf32_kernel<8><<<grid, 64 + 32 * 8, kSmemBytes, stream>>>(p);
-  else conv_gemm_tf32_kernel<4><<<grid, kThreads, kSmemBytes, stream>>>(p);
+  if (p.epi_warps == 8 && !p.swap && !p.tma_store) conv_gemm_tf32_kernel<8, false><<<grid, 64 + 32 * 8, kSmemBytes, stream>>>(p);
+  else conv_gemm_tf32_kernel<4, false><<<grid, kThreads, kSmemBytes, stream>>>(p);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }
@@ -1244,7 +1309,84 @@ __global__ void __launch_bounds__(kThreads, 1) mma_probe_kernel(int n_per_commit
 }  // namespace
 
 // ns per MMA instruction of the probe above (CUDA events around one launch of `grid` CTAs).
+// CTA-pair version of the probe: clusters of two, the leader issues M = 256 cta_group::2 MMAs over both CTAs' (uninitialised,
+// resident) shared memory; ns per MMA as above.
+__global__ void __launch_bounds__(kThreads, 1) mma_probe_pair_kernel(int n_per_commit, int BN, int bf16, int iters) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t s_tmem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(smem_u32(&s_tmem_base), kTmemCols);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();
+  const uint32_t tmem_base = s_tmem_base;
+  if (warp == 1 && lane == 0 && cluster_ctarank() == 0) {
+    const uint32_t idesc = umma_idesc(bf16 ? 1u : 2u, 2 * kTileM, static_cast<uint32_t>(BN));
+    const uint32_t a_addr = smem_base, b_addr = smem_base + 64 * 1024;
+    for (int it = 0; it < iters; ++it) {
+      for (int k = 0; k < n_per_commit; ++k) {
+        const uint32_t off = static_cast<uint32_t>((k & 3) * 32 + (k >> 2) * 16384) & 0xffffu;
+        const uint64_t adesc = umma_desc_sw128_kmajor(a_addr + off);
+        const uint64_t bdesc = umma_desc_sw128_kmajor(b_addr + ((k & 3) * 32));
+        if (bf16) tc_mma_bf16_2(tmem_base, adesc, bdesc, idesc, 1u);
+        else tc_mma_tf32_2(tmem_base, adesc, bdesc, idesc, 1u);
+      }
+      tc_commit2_mcast(smem_u32(&bars[0]), 1);
+    }
+    tc_commit2_mcast(smem_u32(&bars[1]), 1);
+    mbar_wait(smem_u32(&bars[1]), 0u, 8);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, kTmemCols);
+  }
+}
+
+static void launch_probe_pair(int grid, int n_per_commit, int BN, int bf16, int iters) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid & ~1));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, mma_probe_pair_kernel, n_per_commit, BN, bf16, iters);
+}
+
 float conv_gemm_mma_probe(int n_per_commit, int BN, int bf16, int wait_each, int iters, int grid, int two_commits) {
+  if (two_commits == 4) {   // CTA pairs
+    cudaFuncSetAttribute(mma_probe_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (grid < 2) grid = 2;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    launch_probe_pair(grid, n_per_commit, BN, bf16, 10);
+    cudaEventRecord(e0);
+    launch_probe_pair(grid, n_per_commit, BN, bf16, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (cudaGetLastError() != cudaSuccess) return -1.f;
+    return ms * 1e6f / (static_cast<float>(iters) * n_per_commit);
+  }
   cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
@@ -1299,8 +1441,13 @@ float conv_gemm_time_prebuilt(const ConvGemmParams& p, int iters, cudaStream_t s
                              "c0 tmem loaded", "c0 staged", "c0 stored"};
     fprintf(stderr, "[conv_gemm stamps, block 0, ns since start]");
     for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", names[i], h[i] ? h[i] - h[0] : -1);
-    fprintf(stderr, "\n[conv_gemm cfg] TW%d TH%d MT%d BN%d nt%d halo%d swap%d mcast%d slots %d/%d cbatch %d\n", p.TW, p.TH, p.MT, p.BN,
-            p.n_tiles, p.halo, p.swap, p.mcast, p.a_slots, p.b_slots, p.cbatch);
+    fprintf(stderr, "\n[conv_gemm cfg] TW%d TH%d MT%d BN%d nt%d halo%d swap%d pair%d slots %d/%d cbatch %d\n", p.TW, p.TH, p.MT, p.BN,
+            p.n_tiles, p.halo, p.swap, p.pair, p.a_slots, p.b_slots, p.cbatch);
+    const char* roles[3] = {"producer", "mma", "epilogue warp 2"};
+    for (int r = 0; r < 3; ++r)
+      fprintf(stderr, "[conv_gemm waits, block 0, %s] cycles total %lld: A-slot wait %lld, B-slot wait %lld, accumulator wait %lld\n", roles[r],
+              h[19 + 4 * r], h[16 + 4 * r], h[17 + 4 * r], h[18 + 4 * r]);
+    fprintf(stderr, "[conv_gemm waits, block 0, mma] cycles in commit sections %lld\n", h[28]);
   }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);

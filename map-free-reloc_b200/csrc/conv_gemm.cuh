@@ -29,9 +29,10 @@ struct alignas(64) ConvGemmParams {
                           // ky taps read it at row offsets 0, TW, 2*TW (TW % 8 == 0 keeps the swizzle phase)
   int swap;               // halo mode with swapped operands (Cout <= 128): M = 128 filters, N = the 256 pixels of the tile —
                           // one N = 256 MMA per k-step instead of two N = 128 ones (92 ns vs 2 x 61 ns); TMEM lane = filter
-  int mcast;              // halo mode in clusters of two CTAs: the pair works on neighbouring pixel tiles of the same N tile
-                          // and shares every weight tile — each CTA loads half of its rows and TMA-multicasts them to
-                          // both (the 196-channel layers are bound by L2 -> SM operand traffic, mostly weights)
+  int pair;               // halo mode in clusters of two CTAs (cta_group::2): the pair works on neighbouring pixel tiles of the same N tile
+                          // and the leader issues M = 256 MMAs over both CTAs' shared / tensor memory; each CTA loads its own A
+                          // tile and HALF of the filter rows (b_bytes = that half): the tensor pipe reads 128 + BN / 2 operand
+                          // rows per SM and MMA instead of 128 + BN, half the weight bytes come through L2
   int a_slots, b_slots;   // depth of the A ring / B ring (two rings: one A slot serves 3 B tiles in halo mode)
   int a_slot_bytes;
   int epi_warps;          // 4, or 8 for token GEMMs with wide bf16 outputs (two warps per TMEM lane quadrant)

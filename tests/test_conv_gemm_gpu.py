@@ -88,7 +88,7 @@ def test_conv_matches_torch(mfr, N, H, W, Cin, Cout, R, stride, act, use_bias, u
 def test_conv3x3_tilings_agree(mfr, monkeypatch, force, N, H, W, Cin, Cout, use_res):
     """Every tiling of the 3x3 stride-1 path (per-tap A loads vs halo A box shared by the three ky taps,
     one or two 128-pixel sub-tiles per CTA, swapped operands = filters as M / 256 pixels as N) against the
-    fp64 reference. Force string: halo,MT,TW[,swap[,mcast]] (mcast = CTA pairs sharing the weight tiles by TMA multicast);
+    fp64 reference. Force string: halo,MT,TW[,swap[,pair]] (pair = clusters of two CTAs issuing M = 256 tcgen05 cta_group::2 MMAs);
     shapes a mode cannot take fall back to the free search."""
     monkeypatch.setenv("MFR_CONV_FORCE", force)
     g = torch.Generator(device="cpu").manual_seed(4321)
@@ -142,9 +142,9 @@ def test_batched_xyt(mfr):
     _check(out[:, 0], ref)
 
 
-@pytest.mark.parametrize("force", ["-1,-1,-1,0", "1,2,16,1"])
+@pytest.mark.parametrize("force", ["-1,-1,-1,0", "1,2,16,1", "1,2,16,0,1", "1,1,-1,0,1"])
 def test_bf16_conv_swapped_operands(mfr, monkeypatch, force):
-    """bf16 residual block conv (layer1 shape class) with and without the swapped-operand mode."""
+    """bf16 residual block conv (layer1 shape class) with and without the swapped-operand mode, and as CTA pairs."""
     monkeypatch.setenv("MFR_CONV_FORCE", force)
     _bf16_conv_case(mfr, 2, 72, 48, 128, 128, 3, 1, True, True)
     _bf16_conv_case(mfr, 2, 40, 36, 196, 128, 3, 1, False, False)
