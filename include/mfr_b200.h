@@ -45,7 +45,9 @@ int mfr_conv2d_nhwc_tf32(const float* x, int N, int H, int W, int Cin, long long
 
 /* Same op with bf16 operands (x, w as bf16 bits; tcgen05 kind::f16, fp32 accumulate). ldx / ldw are
  * element strides with ldx*2 and ldw*2 multiples of 16 bytes (ldw = per-tap row stride of w, >= Cin).
- * out / residual are bf16 when out_bf16 != 0 (then Cout % 4 == 0), else fp32. bias is fp32. */
+ * out / residual are bf16 when out_bf16 != 0 (then Cout % 4 == 0), else fp32. bias is fp32.
+ * bf16 output rows whose stride ldo is exactly Cout rounded up to a multiple of 8 own their padding: the
+ * (at most 7) elements past Cout of every pixel may be overwritten with zeros (16-byte store units). */
 int mfr_conv2d_nhwc_bf16(const void* x, int N, int H, int W, int Cin, long long ldx, const void* w,
                          long long ldw, int Cout, int R, int S, int stride, int pad, const float* bias,
                          const void* residual, long long ldr, int act, float alpha, void* out,

@@ -239,6 +239,64 @@ __device__ __forceinline__ void epilogue_subtile_tma(const ConvGemmParams& p, ui
   }
 }
 
+// The same for bf16 outputs: 64 channels (two tcgen05.ld) per staged tile, rows of 64 packed bf16 = 128 bytes.
+// With 8 epilogue warps the two warps of a TMEM lane quadrant alternate 64-channel groups (c_begin = 0 / 64), each with its own
+// staging tile: one warp converts while the other's store drains.
+template <int ACT, int EPI>
+__device__ __forceinline__ void epilogue_subtile_tma_bf16(const ConvGemmParams& p, uint32_t taddr, uint32_t stg_addr, int lane,
+                                                          int n0, int x0, int y0, int img, uint32_t wait_bar,
+                                                          uint32_t wait_phase, bool do_wait, int c_begin) {
+  if (do_wait) {
+    mbar_wait(wait_bar, wait_phase, 4);
+    tc_fence_after();
+  }
+  const float alpha = p.alpha;
+  const uint32_t row_addr = stg_addr + static_cast<uint32_t>(lane) * 128u;
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+  for (int c0 = c_begin; c0 < p.BN; c0 += 64 * (EPI / 4)) {
+    uint32_t o[32];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = n0 + c0 + 32 * h;
+      if (c0 + 32 * h < p.BN) {                           // BN is a multiple of 16: the second half may not exist
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0 + 32 * h), r);
+        tmem_ld_wait();
+        const bool do_act = n < p.act_cols;               // act_cols is a multiple of 32 on this path
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr && n + 4 * j4 < p.Cout) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j4));
+          float v0 = fmaf(__uint_as_float(r[4 * j4]), alpha, b4.x), v1 = fmaf(__uint_as_float(r[4 * j4 + 1]), alpha, b4.y);
+          float v2 = fmaf(__uint_as_float(r[4 * j4 + 2]), alpha, b4.z), v3 = fmaf(__uint_as_float(r[4 * j4 + 3]), alpha, b4.w);
+          if (do_act) {
+            v0 = act_fn<ACT, true>(v0); v1 = act_fn<ACT, true>(v1); v2 = act_fn<ACT, true>(v2); v3 = act_fn<ACT, true>(v3);
+          }
+          o[16 * h + 2 * j4] = pack_bf16x2(v0, v1);
+          o[16 * h + 2 * j4 + 1] = pack_bf16x2(v2, v3);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[16 * h + j] = 0u;  // channels >= Cout: clipped by the tensor map
+      }
+    }
+    // the previous group's store must have finished reading the staging tile
+    if (elect_one_sync()) tma_store_wait_read<0>();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((static_cast<uint32_t>(j) ^ sw) << 4)), "r"(o[4 * j]),
+                   "r"(o[4 * j + 1]), "r"(o[4 * j + 2]), "r"(o[4 * j + 3])
+                   : "memory");
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (elect_one_sync()) {
+      tma_store_4d(&p.tmC, stg_addr, n0 + c0, x0, y0, img);
+      tma_store_commit();
+    }
+  }
+}
+
 // Epilogue of the swapped-operand mode: TMEM lane = output channel (warp q owns channels 32q..32q+31), TMEM column
 // = pixel of the 256-pixel tile. Per 32-pixel chunk: tcgen05.ld (thread = channel, 32 pixels) -> transposing
 // shared-memory write (element (pixel, channel): consecutive lanes hit consecutive banks) -> the same coalesced
@@ -443,6 +501,9 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
     if (PAIR) {
       nt = item / pairs_per_nt;
       mt = min(2 * (item - nt * pairs_per_nt) + crank, m_tiles - 1);
+    } else if (p.nt_fast) {   // the N tiles of a pixel tile run at the same time on neighbouring SMs: its A tiles are read from DRAM once
+      mt = item / p.n_tiles;
+      nt = item - mt * p.n_tiles;
     } else {
       nt = item / m_tiles;
       mt = item - nt * m_tiles;
@@ -513,7 +574,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
           int tap = 0;
           for (int ky = 0; ky < R; ++ky) {
             for (int kx = 0; kx < S; ++kx, ++tap) {
-              mbar_wait(a_empty(sa), pa ^ 1u, 1);
+              MFR_TIMED_WAIT(w_a, a_empty(sa), pa ^ 1u, 1);
               if (elect_one_sync()) {
                 mbar_arrive_expect_tx(a_full(sa), ab);
                 if (p.a_yx) tma_load_4d(smem_a + sa * a_slot_bytes, tmA, a_full(sa), c0, y_in0 + ky, x_in0 + kx, img);
@@ -761,7 +822,16 @@ conv_gemm_tf32_kernel(const __grid_constant__ ConvGemmParams p) {
           const int r0 = q * 32;
           const int bx = tx * p.TW + (r0 % p.TW);
           const int by = ty * tile_rows + m * p.TH + r0 / p.TW;
-          const uint32_t stg_t = smem_stg + static_cast<uint32_t>(q) * 4096u;
+          const uint32_t stg_t = smem_stg + static_cast<uint32_t>(warp - 2) * 4096u;
+          if (p.tma_store == 2) {
+            const int cb64 = 2 * c_begin;   // 8 warps: the second warp of a quadrant starts at the second 64-channel group
+            switch (p.act) {
+              case ACT_RELU: epilogue_subtile_tma_bf16<ACT_RELU, EPI>(p, taddr, stg_t, lane, n0, bx, by, img, tfull_bar(acc), acc_phase, do_wait, cb64); break;
+              case ACT_LEAKY: epilogue_subtile_tma_bf16<ACT_LEAKY, EPI>(p, taddr, stg_t, lane, n0, bx, by, img, tfull_bar(acc), acc_phase, do_wait, cb64); break;
+              case ACT_ELU1: epilogue_subtile_tma_bf16<ACT_ELU1, EPI>(p, taddr, stg_t, lane, n0, bx, by, img, tfull_bar(acc), acc_phase, do_wait, cb64); break;
+              default: epilogue_subtile_tma_bf16<ACT_NONE, EPI>(p, taddr, stg_t, lane, n0, bx, by, img, tfull_bar(acc), acc_phase, do_wait, cb64); break;
+            }
+          } else
           switch (p.act) {
             case ACT_RELU: epilogue_subtile_tma<ACT_RELU>(p, taddr, stg_t, lane, n0, bx, by, img, tfull_bar(acc), acc_phase, do_wait); break;
             case ACT_LEAKY: epilogue_subtile_tma<ACT_LEAKY>(p, taddr, stg_t, lane, n0, bx, by, img, tfull_bar(acc), acc_phase, do_wait); break;
@@ -895,7 +965,7 @@ RingCfg ring_cfg(int halo, int MT, int TW, int TH, int BN, int ring_bytes = kRin
 }
 
 TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, int pad, int kb_per_tap,
-                   int ksteps_last, bool allow_mt2, bool tma_store_ok, bool allow_swap, bool allow_pair,
+                   int ksteps_last, bool allow_mt2, int tma_store_cw, bool allow_swap, bool allow_pair,
                    bool single_row_tiles = false, int ring_bytes = kRingBytes) {
   const int sms = conv_gemm_num_sms();
   const int c16 = (Cout + 15) / 16 * 16;
@@ -937,7 +1007,7 @@ TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, in
           const double b_bytes = static_cast<double>(BN) * 128.0 * taps * kb_per_tap;
           const double l2 = (a_bytes + b_bytes) / 100.0;
           // the TMA-store epilogue (fp32 out, power-of-two TW) costs roughly half of the STG one per chunk
-          const bool tma_epi = tma_store_ok && (tw & (tw - 1)) == 0 && tw >= 8 && tw * th == 128 && (BN % 32 == 0 || nt == 1);
+          const bool tma_epi = tma_store_cw > 0 && (tw & (tw - 1)) == 0 && tw >= 8 && tw * th == 128 && (BN % tma_store_cw == 0 || nt == 1);
           const double epi = MT * ((BN + 31) / 32) * (tma_epi ? 250.0 : 500.0);
           const double t = std::max(mma, std::max(l2, epi)) + 800.0;
           const double cost = static_cast<double>((tiles + sms - 1) / sms) * t;
@@ -1038,7 +1108,8 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
   p->epi_warps = epi8 ? 8 : 4;
   p->ring_bytes = epi8 ? kRingBytes8 : kRingBytes;
   const TileCfg cfg = choose_cfg(d.N, p->Ho, p->Wo, d.Cout, d.R, d.S, d.stride, d.pad, p->kb_per_tap, p->ksteps_last,
-                                 d.dyn_w == nullptr && d.b_batched != 2, !d.out_bf16 && d.residual == nullptr,
+                                 d.dyn_w == nullptr && d.b_batched != 2,
+                                 d.residual != nullptr ? 0 : (d.out_bf16 ? 64 : 32),   // channels per chunk of the TMA-store epilogue
                                  // swapped operands: not with a residual (measured: its transposed epilogue then becomes the bottleneck)
                                  (d.Cout % 4 == 0) && (d.ldo % 4 == 0) && !d.b_batched &&
                                      (d.residual == nullptr || (getenv("MFR_CONV_FORCE") != nullptr && d.ldr % 4 == 0)),
@@ -1047,6 +1118,7 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
                                  d.b_batched == 2, p->ring_bytes);
   p->TW = cfg.TW; p->TH = cfg.TH; p->MT = cfg.MT; p->halo = cfg.halo; p->swap = cfg.swap; p->pair = cfg.pair;
   p->BN = cfg.BN; p->n_tiles = cfg.n_tiles;
+  p->nt_fast = (!p->halo && p->n_tiles > 1 && getenv("MFR_CONV_NT_SLOW") == nullptr) ? 1 : 0;
   p->tiles_x = (p->Wo + p->TW - 1) / p->TW;
   p->tiles_y = (p->Ho + p->MT * p->TH - 1) / (p->MT * p->TH);
   p->in_bf16 = d.in_bf16;
@@ -1106,22 +1178,28 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
       if (r != CUDA_SUCCESS) p->tail32 = 0;
     }
   }
-  {  // TMA-store epilogue: fp32 output without residual, power-of-two TW, whole 32-channel chunks per N tile
+  {  // TMA-store epilogue: output without residual, power-of-two TW, whole 32-channel (fp32) / 64-channel (bf16) chunks per N tile
     const bool pow2 = (p->TW & (p->TW - 1)) == 0;
-    const bool ok = !p->swap && !d.out_bf16 && d.residual == nullptr && pow2 && p->TW >= 8 && p->TW * p->TH == 128 &&
-                    (p->BN % 32 == 0 || p->n_tiles == 1) && (p->act_cols % 32 == 0 || p->act_cols >= d.Cout) &&
-                    (d.ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && (d.Cout % 4 == 0) &&
-                    (p->out_img_stride % 4 == 0) && (p->out_y_stride % 4 == 0) && (d.bias == nullptr || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0) &&
-                    getenv("MFR_CONV_NO_TMA_STORE") == nullptr;
-    p->tma_store = ok ? 1 : 0;
+    const int oes = d.out_bf16 ? 2 : 4, cw = d.out_bf16 ? 64 : 32;   // output element size, channels per stored chunk
+    const bool ok = !p->swap && d.residual == nullptr && pow2 && p->TW >= 8 && p->TW * p->TH == 128 &&
+                    (p->BN % cw == 0 || p->n_tiles == 1) && (p->act_cols % 32 == 0 || p->act_cols >= d.Cout) &&
+                    (d.ldo * oes % 16 == 0) && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && (d.Cout % 4 == 0) &&
+                    // the store engine writes whole 16-byte units: with bf16 outputs and Cout % 8 != 0 the (zero) values of up to 7
+                    // channels past Cout land in the row — allowed only when those are the row's own padding (ldo = Cout rounded up to 8)
+                    (!d.out_bf16 || d.Cout % 8 == 0 || d.ldo == (d.Cout + 7) / 8 * 8) &&
+                    (p->out_img_stride * oes % 16 == 0) && (p->out_y_stride * oes % 16 == 0) &&
+                    (d.bias == nullptr || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0) &&
+                    !(d.out_bf16 && p->epi_warps == 8 && getenv("MFR_CONV_EPI8") != nullptr) &&
+                    !(d.out_bf16 && getenv("MFR_CONV_NO_TMA_STORE_BF16") != nullptr) && getenv("MFR_CONV_NO_TMA_STORE") == nullptr;
+    p->tma_store = ok ? (d.out_bf16 ? 2 : 1) : 0;
     if (ok) {
       const int bw = std::min(p->TW, 32);
       cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)p->Wo, (cuuint64_t)p->Ho, (cuuint64_t)d.N};
-      cuuint64_t strides[3] = {(cuuint64_t)d.ldo * 4, (cuuint64_t)p->out_y_stride * 4, (cuuint64_t)p->out_img_stride * 4};
-      cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)(32 / bw), 1};
+      cuuint64_t strides[3] = {(cuuint64_t)d.ldo * oes, (cuuint64_t)p->out_y_stride * oes, (cuuint64_t)p->out_img_stride * oes};
+      cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)bw, (cuuint32_t)(32 / bw), 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
-      CUresult r = enc(&p->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out, dims, strides, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+      CUresult r = enc(&p->tmC, d.out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out, dims, strides, box,
+                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) p->tma_store = 0;   // e.g. strides the tensor map cannot express: keep the STG epilogue
     }
@@ -1215,7 +1293,7 @@ int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream) {
     return MFR_OK;
   }
   const int grid = std::min(total, conv_gemm_num_sms());
-  if (p.epi_warps == 8 && !p.swap && !p.tma_store) conv_gemm_tf32_kernel<8, false><<<grid, 64 + 32 * 8, kSmemBytes, stream>>>(p);
+  if (p.epi_warps == 8 && !p.swap && p.tma_store != 1) conv_gemm_tf32_kernel<8, false><<<grid, 64 + 32 * 8, kSmemBytes, stream>>>(p);
   else conv_gemm_tf32_kernel<4, false><<<grid, kThreads, kSmemBytes, stream>>>(p);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;

@@ -186,3 +186,47 @@ def _bf16_conv_case(mfr, N, H, W, Cin, Cout, R, stride, out_bf16, use_res):
     ref = torch.relu(ref)
     err = (out.double() - ref).abs().max().item()
     assert err <= 1e-2 * ref.abs().max().item(), err
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,R,stride,act", [
+    (2, 40, 36, 196, 196, 3, 1, 2),      # CTA pairs, BN = 208: the last 64-channel chunk is clipped by the tensor map
+    (2, 37, 50, 128, 196, 1, 1, 0),      # 1x1, ragged tiles
+    (2, 40, 36, 128, 196, 3, 2, 1),      # stride 2
+    (1, 1, 777, 256, 768, 1, 1, 3),      # token GEMM (q|k|v shape): three N tiles, elu+1
+    (1, 1, 300, 128, 384, 1, 1, 3),
+])
+def test_bf16_tma_store_epilogue(mfr, monkeypatch, N, H, W, Cin, Cout, R, stride, act):
+    """bf16 outputs without a residual leave through the TMA-store epilogue (64-channel swizzled chunks); the same launch with
+    the per-thread store epilogue (MFR_CONV_NO_TMA_STORE_BF16) must give identical bits; the channel padding of the
+    output rows (stride 200 for 196 channels) is untouched or zero."""
+    lib = mfr.load()
+    g = torch.Generator(device="cpu").manual_seed(123)
+    Cp, Co = (Cin + 7) // 8 * 8, (Cout + 7) // 8 * 8
+    x = torch.zeros(N, H, W, Cp); x[..., :Cin] = torch.randn(N, H, W, Cin, generator=g)
+    w = torch.zeros(Cout, R * R, Cp); w[..., :Cin] = torch.randn(Cout, R * R, Cin, generator=g) / (R * R * Cin) ** 0.5
+    xb, wb = x.bfloat16().cuda(), w.bfloat16().cuda()
+    pad = R // 2
+    Ho = (H + 2 * pad - R) // stride + 1; Wo = (W + 2 * pad - R) // stride + 1
+    bias = torch.randn(Cout, generator=g).cuda()
+    outs = []
+    for no_tma in (False, True):
+        if no_tma:
+            monkeypatch.setenv("MFR_CONV_NO_TMA_STORE_BF16", "1")
+        out = torch.full((N, Ho, Wo, Co), -7.0, device="cuda", dtype=torch.bfloat16)
+        mfr.check(lib.mfr_conv2d_nhwc_bf16(mfr.ptr(xb), N, H, W, Cin, Cp, mfr.ptr(wb), Cp, Cout, R, R, stride, pad,
+                                           mfr.ptr(bias), None, Co, act, 1.0, mfr.ptr(out), Co, 1, mfr.cur_stream()))
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0][..., :Cout], outs[1][..., :Cout])
+    if Co != Cout:   # the row's own channel padding: untouched, or zero-filled by the 16-byte units of the store engine (mfr_b200.h)
+        assert (outs[1][..., Cout:] == -7.0).all()
+        pad_vals = outs[0][..., Cout:]
+        assert ((pad_vals == -7.0) | (pad_vals == 0.0)).all()
+    xr = xb[..., :Cin].double().permute(0, 3, 1, 2)
+    wr = wb[..., :Cin].double().reshape(Cout, R, R, Cin).permute(0, 3, 1, 2)
+    ref = F.conv2d(xr, wr, None, stride=stride, padding=pad).permute(0, 2, 3, 1) + bias.double()
+    if act == 1: ref = torch.relu(ref)
+    elif act == 2: ref = torch.where(ref > 0, ref, 0.01 * ref)
+    elif act == 3: ref = torch.where(ref > 0, ref + 1, torch.exp(ref))
+    err = (outs[0][..., :Cout].double() - ref).abs().max().item()
+    assert err <= 1e-2 * ref.abs().max().item(), err
