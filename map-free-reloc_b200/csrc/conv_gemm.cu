@@ -76,10 +76,10 @@ __device__ __forceinline__ float act_fn(float v) {
   if constexpr (ACT == ACT_RELU) return fmaxf(v, 0.f);
   if constexpr (ACT == ACT_LEAKY) return v > 0.f ? v : 0.01f * v;
   if constexpr (ACT == ACT_ELU1) {
-    if constexpr (FAST) {
+    if constexpr (FAST) {   // max(v, 0) + 2^min(v log2 e, 0): the same bits as the select form in five instructions
       float e;
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 0.f) * 1.4426950408889634f));
-      return v > 0.f ? v + 1.f : e;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v * 1.4426950408889634f, 0.f)));
+      return fmaxf(v, 0.f) + e;
     } else {
       return v > 0.f ? v + 1.f : __expf(v);
     }
@@ -251,24 +251,31 @@ __device__ __forceinline__ void epilogue_subtile_tma_bf16(const ConvGemmParams& 
     tc_fence_after();
   }
   const float alpha = p.alpha;
+  const bool plain = p.bias == nullptr && alpha == 1.f;
   const uint32_t row_addr = stg_addr + static_cast<uint32_t>(lane) * 128u;
   const uint32_t sw = static_cast<uint32_t>(lane & 7);
   for (int c0 = c_begin; c0 < p.BN; c0 += 64 * (EPI / 4)) {
     uint32_t o[32];
+    uint32_t ra[2][32];
+    const bool has2 = c0 + 32 < p.BN;                     // BN is a multiple of 16: the second half may not exist
+    tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0), ra[0]);        // both halves in flight before the wait
+    tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(has2 ? c0 + 32 : c0), ra[1]);   // (no second half: re-read, ignored)
+    tmem_ld_wait();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int n = n0 + c0 + 32 * h;
-      if (c0 + 32 * h < p.BN) {                           // BN is a multiple of 16: the second half may not exist
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c0 + 32 * h), r);
-        tmem_ld_wait();
+      if (h == 0 || has2) {
+        const uint32_t (&r)[32] = ra[h];
         const bool do_act = n < p.act_cols;               // act_cols is a multiple of 32 on this path
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr && n + 4 * j4 < p.Cout) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j4));
-          float v0 = fmaf(__uint_as_float(r[4 * j4]), alpha, b4.x), v1 = fmaf(__uint_as_float(r[4 * j4 + 1]), alpha, b4.y);
-          float v2 = fmaf(__uint_as_float(r[4 * j4 + 2]), alpha, b4.z), v3 = fmaf(__uint_as_float(r[4 * j4 + 3]), alpha, b4.w);
+          float v0 = __uint_as_float(r[4 * j4]), v1 = __uint_as_float(r[4 * j4 + 1]);
+          float v2 = __uint_as_float(r[4 * j4 + 2]), v3 = __uint_as_float(r[4 * j4 + 3]);
+          if (!plain) {                                     // (uniform) plain: alpha = 1, no bias — fma(v, 1, 0) = v
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr && n + 4 * j4 < p.Cout) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j4));
+            v0 = fmaf(v0, alpha, b4.x); v1 = fmaf(v1, alpha, b4.y); v2 = fmaf(v2, alpha, b4.z); v3 = fmaf(v3, alpha, b4.w);
+          }
           if (do_act) {
             v0 = act_fn<ACT, true>(v0); v1 = act_fn<ACT, true>(v1); v2 = act_fn<ACT, true>(v2); v3 = act_fn<ACT, true>(v3);
           }
@@ -965,7 +972,7 @@ RingCfg ring_cfg(int halo, int MT, int TW, int TH, int BN, int ring_bytes = kRin
 }
 
 TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, int pad, int kb_per_tap,
-                   int ksteps_last, bool allow_mt2, int tma_store_cw, bool allow_swap, bool allow_pair,
+                   int ksteps_last, bool allow_mt2, int tma_store_cw, bool epi8, bool allow_swap, bool allow_pair,
                    bool single_row_tiles = false, int ring_bytes = kRingBytes) {
   const int sms = conv_gemm_num_sms();
   const int c16 = (Cout + 15) / 16 * 16;
@@ -1008,7 +1015,17 @@ TileCfg choose_cfg(int N, int Ho, int Wo, int Cout, int R, int S, int stride, in
           const double l2 = (a_bytes + b_bytes) / 100.0;
           // the TMA-store epilogue (fp32 out, power-of-two TW) costs roughly half of the STG one per chunk
           const bool tma_epi = tma_store_cw > 0 && (tw & (tw - 1)) == 0 && tw >= 8 && tw * th == 128 && (BN % tma_store_cw == 0 || nt == 1);
-          const double epi = MT * ((BN + 31) / 32) * (tma_epi ? 250.0 : 500.0);
+          // epilogue per tile (relative costs): per-thread stores ~500 ns per 32-channel chunk, TMA stores half of that per
+          // channel (fp32: 32-channel chunks, bf16: 64-channel groups); with 8 epilogue warps the two warps of a lane
+          // quadrant alternate chunks / groups
+          double epi;
+          if (tma_epi && tma_store_cw == 64) {
+            const int groups = (BN + 63) / 64;
+            epi = MT * (epi8 ? (groups + 1) / 2 : groups) * 500.0;
+          } else {
+            const int chunks = (BN + 31) / 32;
+            epi = MT * (epi8 && !tma_epi ? (chunks + 1) / 2 : chunks) * (tma_epi ? 250.0 : 500.0);
+          }
           const double t = std::max(mma, std::max(l2, epi)) + 800.0;
           const double cost = static_cast<double>((tiles + sms - 1) / sms) * t;
           if (f_swap != 1 && f_mc != 1 && (cost < best.cost * (1.0 - 1e-9) || (cost < best.cost * (1.0 + 1e-9) && tw > best.TW))) {
@@ -1110,6 +1127,7 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
   const TileCfg cfg = choose_cfg(d.N, p->Ho, p->Wo, d.Cout, d.R, d.S, d.stride, d.pad, p->kb_per_tap, p->ksteps_last,
                                  d.dyn_w == nullptr && d.b_batched != 2,
                                  d.residual != nullptr ? 0 : (d.out_bf16 ? 64 : 32),   // channels per chunk of the TMA-store epilogue
+                                 epi8,
                                  // swapped operands: not with a residual (measured: its transposed epilogue then becomes the bottleneck)
                                  (d.Cout % 4 == 0) && (d.ldo % 4 == 0) && !d.b_batched &&
                                      (d.residual == nullptr || (getenv("MFR_CONV_FORCE") != nullptr && d.ldr % 4 == 0)),
@@ -1202,7 +1220,11 @@ int conv_gemm_build(const ConvGemmDesc& d, ConvGemmParams* p) {
                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) p->tma_store = 0;   // e.g. strides the tensor map cannot express: keep the STG epilogue
+      if (getenv("MFR_CONV_DEBUG") && r != CUDA_SUCCESS) fprintf(stderr, "[conv_gemm cfg] store tensor map rejected (%d)\n", (int)r);
     }
+    if (getenv("MFR_CONV_DEBUG"))
+      fprintf(stderr, "[conv_gemm cfg] Cout%d ldo%lld out_bf16 %d res %d TW%d TH%d BN%d nt%d act_cols %d epi %d -> tma_store %d\n", d.Cout, d.ldo,
+              d.out_bf16, d.residual != nullptr, p->TW, p->TH, p->BN, p->n_tiles, p->act_cols, p->epi_warps, p->tma_store);
   }
   {  // weights: {Cin, Z, Cout}; Z = tap (shared weights) or image (batched B operand)
     const int taps = d.R * d.S;

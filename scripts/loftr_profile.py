@@ -5,7 +5,10 @@ import numpy as np, torch
 import mfr_b200
 from mfr_b200 import loftr, synth
 B = int(os.environ.get("B", 4)); H, W = 720, 544
-eng = loftr.LoFTR(loftr.functional_state_dict() if os.environ.get('WEIGHTS', 'functional') == 'functional' else loftr.synthetic_state_dict(0), batch=B, height=H, width=W, cfg={"thr": float(os.environ.get("THR", 0.2))}, precision=os.environ.get("PRECISION", "tf32"))
+# WEIGHTS: functional (matcher that matches, 99.8 % zero weights), bench (the benchmark's: functional + dense 1e-3 perturbation), dense (random)
+_w = os.environ.get('WEIGHTS', 'functional')
+_sd = loftr.functional_state_dict() if _w == 'functional' else (loftr.functional_state_dict(noise=1e-3) if _w == 'bench' else loftr.synthetic_state_dict(0))
+eng = loftr.LoFTR(_sd, batch=B, height=H, width=W, cfg={"thr": float(os.environ.get("THR", 0.2))}, precision=os.environ.get("PRECISION", "tf32"))
 ps = [synth.make_pair(1000 + b) for b in range(B)]
 g0 = torch.from_numpy(np.stack([synth.rgb_to_gray_u8(p["image0"]).astype(np.float32) / 255.0 for p in ps])).cuda()
 g1 = torch.from_numpy(np.stack([synth.rgb_to_gray_u8(p["image1"]).astype(np.float32) / 255.0 for p in ps])).cuda()
