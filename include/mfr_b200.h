@@ -259,6 +259,19 @@ float mfr_debug_time_conv(const float* x, int N, int H, int W, int Cin, const fl
 int mfr_linear_attention(const void* q, const void* k, const void* v, void* msg, int n, int L, int S, int windows,
                          int bf16, void* stream);
 
+/* Stage entry for tests: the backbone stem, conv 7x7 stride 2 pad 3, 1 -> 128 channels, folded-BN bias, ReLU
+ * (LoFTR/src/loftr/backbone/resnet_fpn.py:52-62,102). img fp32 [NI][H][W]; w fp32 [128][49]; out [NI][H/2][W/2][128], bf16 when
+ * out_bf16 != 0 (the tcgen05 kernel; MFR_STEM_TC=0 selects the mma.sync one), else fp32; exact_fp32: plain FMA kernel. */
+int mfr_stem_conv7x7(const float* img, const float* w, const float* bias, void* out, int NI, int H, int W, int out_bf16,
+                     int exact_fp32, void* stream);
+
+/* Stage entry for tests: the fine level's q|k|v projection + window attention as ONE kernel (bf16 mode; the projection is
+ * LoFTREncoderLayer's q_proj / k_proj / v_proj, transformer.py:21-23,41-46, the attention linear_attention.py:31-45 on 5x5
+ * windows). xq / xs: bf16 token rows [n_items * 25][>= 128] of the query / source side with element strides ldq / lds (the same
+ * pointer = self attention); w_qkv: bf16 [384][128] = rows of Wq, Wk, Wv; msg: bf16 [n_items * 25][ldm]. Device pointers. */
+int mfr_fine_attention_fused(const void* xq, long long ldq, const void* xs, long long lds, const void* w_qkv, void* msg,
+                             long long ldm, int n_items, void* stream);
+
 /* ProcrustesSolver's ICP refinement (PROCRUSTES.REFINE, pose_solver.py:289-315: Open3D registration_icp, point-to-point,
  * correspondence radius max_corr_dist, criteria relative_fitness / relative_rmse / max_iterations = 1e-4 / 1e-4 / 30 in the
  * reference) of the poses (R_in, t_in) [P][9] / [P][3] over the FULL clouds of both depth maps (every pixel with depth > 0),

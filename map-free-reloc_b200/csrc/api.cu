@@ -273,6 +273,25 @@ float mfr_debug_time_conv(const float* x, int N, int H, int W, int Cin, const fl
   return mfr::conv_gemm_time_prebuilt(p, iters, nullptr);
 }
 
+int mfr_stem_conv7x7(const float* img, const float* w, const float* bias, void* out, int NI, int H, int W, int out_bf16,
+                     int exact_fp32, void* stream) {
+  if (!img || !w || !bias || !out || NI <= 0 || H < 7 || W < 7) return MFR_ERR_ARG;
+  return mfr::stem_conv7x7(img, w, bias, static_cast<float*>(out), NI, H, W, static_cast<cudaStream_t>(stream), out_bf16, exact_fp32);
+}
+
+int mfr_fine_attention_fused(const void* xq, long long ldq, const void* xs, long long lds, const void* w_qkv, void* msg,
+                             long long ldm, int n_items, void* stream) {
+  if (!xq || !xs || !w_qkv || !msg || n_items <= 0) return MFR_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int* cnt = nullptr;
+  if (cudaMalloc(&cnt, sizeof(int)) != cudaSuccess) return MFR_ERR_CUDA;
+  cudaMemcpyAsync(cnt, &n_items, sizeof(int), cudaMemcpyHostToDevice, st);
+  const int r = mfr::fine_attention_fused(xq, ldq, xs, lds, w_qkv, msg, ldm, cnt, n_items, 25, st);
+  cudaStreamSynchronize(st);
+  cudaFree(cnt);
+  return r;
+}
+
 int mfr_linear_attention(const void* q, const void* k, const void* v, void* msg, int n, int L, int S, int windows,
                          int bf16, void* stream) {
   if (!q || !k || !v || !msg || n <= 0) return MFR_ERR_ARG;

@@ -50,6 +50,7 @@ struct LoftrEngine {
   int splits_kv = 96, splits_col = 32;   // splits_kv is set from the image count in build()
   int precision = 0;   // MFR_PRECISION_* (include/mfr_b200.h)
   bool fused_tail = getenv("MFR_FUSED_TAIL") == nullptr || atoi(getenv("MFR_FUSED_TAIL")) != 0;   // bf16 mode: encoder_tail.cu
+  bool fused_fine_attn = getenv("MFR_FUSED_FINE_ATTN") == nullptr || atoi(getenv("MFR_FUSED_FINE_ATTN")) != 0;   // bf16 mode, fine level
   struct Bf16Conv { std::string name; int cout, taps, cin, cin_pad; size_t off; };
   std::vector<Bf16Conv> bf16_convs;
   unsigned short* wblob16 = nullptr;
@@ -261,6 +262,19 @@ struct LoftrEngine {
     float* xb = tbf ? shadow(x) : x;
     float* srcb = tbf ? shadow(src) : src;
     const std::string qn = p + ".qkv";
+    if (windows && tbf && fused_fine_attn) {
+      // fine level, bf16 mode: projection + window attention in one kernel (q, k, v stay on the SM; loftr_ops.cu)
+      const unsigned short* wq16 = w16(qn, 3 * C, C);
+      const int items_cap = rows / 25;
+      for (int side = 0; side < n; ++side) {
+        const size_t off2 = static_cast<size_t>(side) * rows * ld2, off1 = static_cast<size_t>(side) * rows * C;
+        const float *xq_ = E(xb, off2), *xs_ = E(srcb, off2);
+        float* mp = E(msg_x, off1);
+        push("fine_attn_fused", [=](cudaStream_t st) {
+          return fine_attention_fused(xq_, ld2, xs_, ld2, wq16, mp, C, dyn_items, items_cap, 25, st);
+        });
+      }
+    } else {
     if (x == src) {
       conv(qn, xb, n, 1, rows, C, ld2, 3 * C, 1, 1, false, nullptr, ACT_ELU1, qkv_x, ld3, 2 * C, dyn_rows, wq, nullptr, tbf, tbf,
            3 * C, 0);
@@ -286,6 +300,7 @@ struct LoftrEngine {
           return linear_attention_windows(qp, ld3, kp, ld3, vp, ld3, mp, C, dyn_items, items_cap, 25, st, tbf);
         });
       }
+    }
     }
     const float *g1 = W_(p + ".norm1.g"), *b1 = W_(p + ".norm1.b");
     const float *g2 = W_(p + ".norm2.g"), *b2 = W_(p + ".norm2.b");

@@ -799,6 +799,159 @@ __global__ void __launch_bounds__(256) attn_windows_mma_kernel(const unsigned sh
   }
 }
 
+// q|k|v projection + window attention of the fine level in ONE kernel (bf16 mode): q, k, v never go to HBM.
+// Persistent blocks, 8 warps = 8 heads. Warp h keeps rows [16 h, 16 h + 16) of Wq, Wk and Wv (its head's 16 output
+// channels, all 128 input channels) as mma.sync B fragments in 96 registers for the lifetime of the block. Per window:
+//   cp.async the 25 x 128 bf16 token rows of the query side and of the source side (the same for self attention) into
+//   shared memory (double-buffered across windows), project them with mma.sync m16n8k16 (tokens padded to 32, zero rows),
+//   elu + 1 on q and k in registers, write the head's Q', K', V slice (bf16) into the shared tile the attention part reads
+//   (only this warp touches its head's columns, so a __syncwarp orders the two), then the attention of
+//   attn_windows_mma_kernel above and the 25 message rows to global memory.
+__device__ __forceinline__ float elu1_fast(float v) {   // the token-GEMM epilogue's elu(x) + 1 (conv_gemm.cu act_fn<ACT_ELU1, true>)
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v * 1.4426950408889634f, 0.f)));
+  return fmaxf(v, 0.f) + e;
+}
+
+template <int T>
+__global__ void __launch_bounds__(256, 1) fine_attn_fused_kernel(const unsigned short* __restrict__ xq, long long ldq,
+                                                                  const unsigned short* __restrict__ xs, long long lds,
+                                                                  const unsigned short* __restrict__ W,   // [3 * 128][128] bf16: Wq, Wk, Wv
+                                                                  unsigned short* __restrict__ msg, long long ldm,
+                                                                  const int* __restrict__ n_items_dev, float eps) {
+  static_assert(T <= 32, "window tokens are padded to 32");
+  extern __shared__ __align__(128) char smf[];            // x tiles [2 buffers][query, source][32][128] bf16, then Q', K', V tiles
+  char* sX = smf;
+  char* sP = smf + 4 * 8192;
+  const int n_items = *n_items_dev;
+  const bool self = xq == xs;
+  const int t = threadIdx.x, h = t >> 5, lane = t & 31;
+  const int j = lane >> 3, r = lane & 7, g = lane >> 2, tq = lane & 3;
+  unsigned wf[3][2][8][2];                                // B fragments: wf[matrix][n tile][k tile]: W[n = g][k = 2 tq (+1)], W[g][k + 8 ...]
+#pragma unroll
+  for (int m = 0; m < 3; ++m)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int kt = 0; kt < 8; ++kt) {
+        const unsigned short* wr = W + static_cast<size_t>(m * 128 + 16 * h + 8 * nt + g) * 128 + 16 * kt + 2 * tq;
+        wf[m][nt][kt][0] = *reinterpret_cast<const unsigned*>(wr);
+        wf[m][nt][kt][1] = *reinterpret_cast<const unsigned*>(wr + 8);
+      }
+  for (int c = t; c < 4 * (32 - T) * 16; c += 256) {      // zero padding rows of the four x tiles (never written again)
+    const int which = c / ((32 - T) * 16), rc = c % ((32 - T) * 16), rr = T + (rc >> 4), ch = rc & 15;
+    *reinterpret_cast<uint4*>(sX + which * 8192 + rr * 256 + (ch << 4)) = make_uint4(0, 0, 0, 0);
+  }
+  auto load_x = [&](int item, int buf) {
+    const size_t row0 = static_cast<size_t>(item) * T;
+    const int n = (self ? 1 : 2) * T * 16;
+    for (int c = t; c < n; c += 256) {
+      const int which = c / (T * 16), rc = c % (T * 16), rr = rc >> 4, ch = rc & 15;
+      const unsigned short* src = (which == 0 ? xq + (row0 + rr) * ldq : xs + (row0 + rr) * lds) + ch * 8;
+      cp_async16(sX + (buf * 2 + which) * 8192 + rr * 256 + ((ch ^ (rr & 7)) << 4), src, true);
+    }
+    cp_async_commit();
+  };
+  auto addr = [&](int which, int row, int chunk) { return sP + which * 8192 + row * 256 + ((chunk ^ (row & 7)) << 4); };
+  int item = blockIdx.x, buf = 0;
+  if (item < n_items) load_x(item, 0);
+  for (; item < n_items; item += gridDim.x, buf ^= 1) {
+    cp_async_wait<0>();
+    __syncthreads();                                      // this window's rows have landed; everyone is done with the other buffer
+    if (item + static_cast<int>(gridDim.x) < n_items) load_x(item + gridDim.x, buf ^ 1);
+    const char* xqb = sX + (buf * 2) * 8192;
+    const char* xsb = self ? xqb : xqb + 8192;
+    // ---- projection: this head's 16 channels of Q', K', V for the 32 (padded) tokens
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float cq[2][4], ck[2][4], cv[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { cq[nt][e] = 0.f; ck[nt][e] = 0.f; cv[nt][e] = 0.f; }
+      const int arow = 16 * mt + r + 8 * (j & 1);
+#pragma unroll
+      for (int kt = 0; kt < 8; ++kt) {
+        const int off = arow * 256 + (((2 * kt + (j >> 1)) ^ (arow & 7)) << 4);
+        unsigned aq[4], as[4];
+        ldsm_x4(aq, xqb + off);
+        if (self) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) as[e] = aq[e];
+        } else {
+          ldsm_x4(as, xsb + off);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          mma_bf16(cq[nt], aq, wf[0][nt][kt][0], wf[0][nt][kt][1]);
+          mma_bf16(ck[nt], as, wf[1][nt][kt][0], wf[1][nt][kt][1]);
+          mma_bf16(cv[nt], as, wf[2][nt][kt][0], wf[2][nt][kt][1]);
+        }
+      }
+      const int l0 = 16 * mt + g, l1 = l0 + 8;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int chunk = 2 * h + nt;
+        *reinterpret_cast<unsigned*>(addr(0, l0, chunk) + 4 * tq) = pack_bf16(elu1_fast(cq[nt][0]), elu1_fast(cq[nt][1]));
+        *reinterpret_cast<unsigned*>(addr(0, l1, chunk) + 4 * tq) = pack_bf16(elu1_fast(cq[nt][2]), elu1_fast(cq[nt][3]));
+        // padding rows of K' must be zero (elu(0) + 1 = 1 would count as tokens); those of V are zero already (zero x rows)
+        *reinterpret_cast<unsigned*>(addr(1, l0, chunk) + 4 * tq) = l0 < T ? pack_bf16(elu1_fast(ck[nt][0]), elu1_fast(ck[nt][1])) : 0u;
+        *reinterpret_cast<unsigned*>(addr(1, l1, chunk) + 4 * tq) = l1 < T ? pack_bf16(elu1_fast(ck[nt][2]), elu1_fast(ck[nt][3])) : 0u;
+        *reinterpret_cast<unsigned*>(addr(2, l0, chunk) + 4 * tq) = pack_bf16(cv[nt][0], cv[nt][1]);
+        *reinterpret_cast<unsigned*>(addr(2, l1, chunk) + 4 * tq) = pack_bf16(cv[nt][2], cv[nt][3]);
+      }
+    }
+    __syncwarp();
+    // ---- attention of this head (see attn_windows_mma_kernel)
+    float ckv[2][4], cks[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { ckv[a][e] = 0.f; cks[a][e] = 0.f; }
+    }
+    const unsigned one = (g == 0) ? 0x3F803F80u : 0u;
+    const unsigned aones[4] = {one, 0u, one, 0u};
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      unsigned a[4], b[4];
+      ldsm_x4_t(a, addr(2, 16 * ks + r + 8 * (j >> 1), 2 * h + (j & 1)));     // A = V^T: m = v, k = token
+      ldsm_x4_t(b, addr(1, 16 * ks + r + 8 * (j & 1), 2 * h + (j >> 1)));     // B = K': k = token, n = d
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        mma_bf16(ckv[nt], a, b[2 * nt], b[2 * nt + 1]);
+        mma_bf16(cks[nt], aones, b[2 * nt], b[2 * nt + 1]);
+      }
+    }
+    const unsigned bv0[2] = {pack_bf16(ckv[0][0], ckv[0][1]), pack_bf16(ckv[1][0], ckv[1][1])};
+    const unsigned bv1[2] = {pack_bf16(ckv[0][2], ckv[0][3]), pack_bf16(ckv[1][2], ckv[1][3])};
+    const unsigned bd[2] = {pack_bf16(cks[0][0], cks[0][1]), pack_bf16(cks[1][0], cks[1][1])};
+    const size_t row0 = static_cast<size_t>(item) * T;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      unsigned a[4];
+      ldsm_x4(a, addr(0, 16 * mt + r + 8 * (j & 1), 2 * h + (j >> 1)));       // A = Q': m = token, k = d
+      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, cd[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16(c0, a, bv0[0], bv0[1]);
+      mma_bf16(c1, a, bv1[0], bv1[1]);
+      mma_bf16(cd, a, bd[0], bd[1]);
+      const float den_lo = __shfl_sync(0xffffffffu, cd[0], lane & ~3), den_hi = __shfl_sync(0xffffffffu, cd[2], lane & ~3);
+      const float z_lo = 1.f / (den_lo + eps), z_hi = 1.f / (den_hi + eps);
+      const int l0 = 16 * mt + g;
+      if (l0 < T) {
+        unsigned short* o = msg + (row0 + l0) * ldm + 16 * h + 2 * tq;
+        *reinterpret_cast<unsigned*>(o) = pack_bf16(c0[0] * z_lo, c0[1] * z_lo);
+        *reinterpret_cast<unsigned*>(o + 8) = pack_bf16(c1[0] * z_lo, c1[1] * z_lo);
+      }
+      if (l0 + 8 < T) {
+        unsigned short* o = msg + (row0 + l0 + 8) * ldm + 16 * h + 2 * tq;
+        *reinterpret_cast<unsigned*>(o) = pack_bf16(c0[2] * z_hi, c0[3] * z_hi);
+        *reinterpret_cast<unsigned*>(o + 8) = pack_bf16(c1[2] * z_hi, c1[3] * z_hi);
+      }
+    }
+    __syncwarp();                                         // the head's tiles are rewritten by the next window's projection
+  }
+}
+
 // ------------------------------------------------------------------------------------------ layernorm
 template <int C>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, long long ldi,
@@ -1627,6 +1780,8 @@ __global__ void __launch_bounds__(128) stem_mma_kernel(const float* __restrict__
 int stem_conv7x7(const float* img, const float* w, const float* bias, float* out, int NI, int H, int W,
                  cudaStream_t st, int out_bf16, int exact_fp32) {
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  if (out_bf16 && !exact_fp32 && (getenv("MFR_STEM_TC") == nullptr || atoi(getenv("MFR_STEM_TC")) != 0))
+    return stem_conv7x7_tc(img, w, bias, out, NI, H, W, st);   // tcgen05 version (stem_tc.cu)
   if (kUseMmaStem && !exact_fp32) {
     const int PW = 32 * ((Wo + 15) / 16) + 8;                 // patch columns: 2 px + kx for every pixel of the padded row
     const int smem = 2 * 8 * PW * 2;
@@ -1732,6 +1887,23 @@ int linear_attention_windows(const void* Q, long long ldq, const void* K, long l
                                                           n_items_dev, 1e-6f);
   } else if (bf16) attn_windows_kernel<25, true><<<max_items, 128, 0, st>>>(Q, ldq, K, ldk, V, ldv, msg, ldm, n_items_dev, 1e-6f);
   else attn_windows_kernel<25, false><<<max_items, 128, 0, st>>>(Q, ldq, K, ldk, V, ldv, msg, ldm, n_items_dev, 1e-6f);
+  MFR_CUDA_CHECK(cudaGetLastError());
+  return MFR_OK;
+}
+
+int fine_attention_fused(const void* xq, long long ldq, const void* xs, long long lds, const void* w_qkv, void* msg,
+                         long long ldm, const int* n_items_dev, int max_items, int T, cudaStream_t st) {
+  if (T != 25 || max_items <= 0) return MFR_ERR_UNSUPPORTED;
+  if (((ldq | lds | ldm) & 7) || ((reinterpret_cast<uintptr_t>(xq) | reinterpret_cast<uintptr_t>(xs) | reinterpret_cast<uintptr_t>(w_qkv)) & 15))
+    return MFR_ERR_ARG;
+  constexpr int kSmem = 7 * 8192;
+  static bool attr_seen[64] = {};
+  if (first_call_on_device(attr_seen))
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(fine_attn_fused_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  const int grid = std::min(max_items, 2 * 148);
+  fine_attn_fused_kernel<25><<<grid, 256, kSmem, st>>>(static_cast<const unsigned short*>(xq), ldq, static_cast<const unsigned short*>(xs), lds,
+                                                       static_cast<const unsigned short*>(w_qkv), static_cast<unsigned short*>(msg), ldm,
+                                                       n_items_dev, 1e-6f);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
 }

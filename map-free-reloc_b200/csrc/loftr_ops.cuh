@@ -10,6 +10,9 @@ namespace mfr {
 int stem_conv7x7(const float* img, const float* w /*[128][49]*/, const float* bias, float* out,
                  int NI, int H, int W, cudaStream_t st, int out_bf16 = 0, int exact_fp32 = 0);
 
+// the same op on tcgen05 (stem_tc.cu): bf16 output only, same hi/lo split arithmetic
+int stem_conv7x7_tc(const float* img, const float* w, const float* bias, void* out_bf16, int NI, int H, int W, cudaStream_t st);
+
 // dst[n,y,x,:] += bilinear_x2_align_corners(src)[n,y,x,:]   (resnet_fpn.py:110,114)
 // pixel strides lds / ldd in elements; src / dst fp32 or bf16
 int upsample2x_add(const void* src, void* dst, int N, int Hs, int Ws, int C, int lds, int ldd, int src_bf16,
@@ -35,6 +38,10 @@ int linear_attention_long(const void* Q, long long ldq, const void* K, long long
 int linear_attention_windows(const void* Q, long long ldq, const void* K, long long ldk, const void* V,
                              long long ldv, void* msg, long long ldm, const int* n_items_dev,
                              int max_items, int T, cudaStream_t st, int bf16 = 0);
+// bf16 mode, fine level: q|k|v projection (w_qkv = [3 * 128][128] bf16: Wq, Wk, Wv rows) + window attention in one kernel.
+// xq / xs: bf16 token rows of the query / source side (equal pointers = self attention), 25 rows per window.
+int fine_attention_fused(const void* xq, long long ldq, const void* xs, long long lds, const void* w_qkv, void* msg,
+                         long long ldm, const int* n_items_dev, int max_items, int T, cudaStream_t st);
 
 // out[r,:] = (res ? res[r,:] : 0) + LayerNorm(in[r,:]) * gamma + beta, C in {128, 256}; rows may be
 // limited by *dyn_rows (device) when non-null.

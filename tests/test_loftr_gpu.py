@@ -9,6 +9,7 @@ import ctypes
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from helpers import GOLDEN, loftr_case
 from oracle import loftr_oracle as lo
@@ -221,3 +222,57 @@ def test_linear_attention_stage(mfr, windows, n, L, S, bf16):
     assert torch.isfinite(got).all()
     tol = 2e-2 if bf16 else 1e-4
     assert ((got - ref).abs().max() / ref.abs().max()).item() < tol
+
+
+@pytest.mark.parametrize("cross", [False, True])
+@pytest.mark.parametrize("n", [1, 301, 1000])
+def test_fine_attention_fused(mfr, cross, n):
+    """Fine level, bf16 mode: projection + window attention in one kernel against the composition it replaces, restated in
+    fp64 on the same bf16 inputs: q' = bf16(elu(x_q Wq^T) + 1), k' = bf16(elu(x_s Wk^T) + 1), v = bf16(x_s Wv^T), then
+    linear attention per window and head. Token rows have the engine's stride (x half of [x | msg] rows). Tolerance 2e-2 of
+    the output range as for the unfused bf16 attention (bf16 KV, bf16 output)."""
+    lib = mfr.load()
+    g = torch.Generator().manual_seed(5 + n + int(cross))
+    C, T, ld = 128, 25, 256
+    xq = torch.randn(n * T, ld, generator=g).to(torch.bfloat16).cuda()
+    xs = torch.randn(n * T, ld, generator=g).to(torch.bfloat16).cuda() if cross else xq
+    w = (torch.randn(3 * C, C, generator=g) / C ** 0.5).to(torch.bfloat16).cuda()
+    out = torch.full((n * T, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    mfr.check(lib.mfr_fine_attention_fused(mfr.ptr(xq), ld, mfr.ptr(xs), ld, mfr.ptr(w), mfr.ptr(out), C, n, mfr.cur_stream()))
+    torch.cuda.synchronize()
+    wd = w.cpu().double()
+    q = (torch.nn.functional.elu(xq[:, :C].cpu().double() @ wd[:C].T) + 1).to(torch.bfloat16).float()
+    k = (torch.nn.functional.elu(xs[:, :C].cpu().double() @ wd[C:2 * C].T) + 1).to(torch.bfloat16).float()
+    v = (xs[:, :C].cpu().double() @ wd[2 * C:].T).to(torch.bfloat16).float()
+    ref = _lin_att_ref(q.view(n, T, C), k.view(n, T, C), v.view(n, T, C), 8).reshape(n * T, C)
+    got = out.cpu().double()
+    assert torch.isfinite(got).all()
+    assert ((got - ref).abs().max() / ref.abs().max()).item() < 2e-2
+
+
+@pytest.mark.parametrize("NI,H,W", [(2, 720, 544), (3, 96, 128), (1, 75, 61)])
+def test_stem_tcgen05_matches_reference(mfr, monkeypatch, NI, H, W):
+    """The tcgen05 stem (bf16 output; hi/lo-split operands, three k-blocks of one GEMM per 128-pixel tile) against an fp64
+    convolution of the same image and weights, and against the mma.sync stem it replaces (same split arithmetic, another
+    summation order: equal up to the bf16 rounding of the output). Ragged sizes exercise the clipped edge tiles."""
+    lib = mfr.load()
+    g = torch.Generator().manual_seed(17 + H)
+    img = torch.rand(NI, H, W, generator=g).cuda()
+    w = (torch.randn(128, 49, generator=g) / 7.0).cuda()
+    bias = torch.randn(128, generator=g).cuda()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    outs = []
+    for tc in ("1", "0"):
+        monkeypatch.setenv("MFR_STEM_TC", tc)
+        out = torch.full((NI, Ho, Wo, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
+        mfr.check(lib.mfr_stem_conv7x7(mfr.ptr(img), mfr.ptr(w), mfr.ptr(bias), mfr.ptr(out), NI, H, W, 1, 0, mfr.cur_stream()))
+        torch.cuda.synchronize()
+        outs.append(out.float().cpu())
+    ref = torch.relu(F.conv2d(img.cpu().double()[:, None], w.cpu().double().view(128, 1, 7, 7), bias.cpu().double(), stride=2, padding=3))
+    ref = ref.permute(0, 2, 3, 1)
+    scale = ref.abs().max().item()
+    for o in outs:
+        assert torch.isfinite(o).all()
+        assert ((o.double() - ref).abs().max().item()) <= 2.0 ** -8 * scale     # bf16 rounding of the output
+    assert (outs[0] - outs[1]).abs().max().item() <= 2.0 ** -7 * scale
+    assert (outs[0] != outs[1]).float().mean().item() < 0.02
