@@ -255,7 +255,8 @@ float mfr_debug_time_conv(const float* x, int N, int H, int W, int Cin, const fl
 /* Stage entry for tests: LoFTR's linear attention (LoFTR/src/loftr/loftr_module/linear_attention.py:31-45) on
  * already feature-mapped q' = elu(q)+1, k' and values. windows = 0: q [n][L][256], k / v [n][S][256], 8 heads of 32
  * (coarse level); windows = 1: q, k, v [n][25][128], 8 heads of 16, n items (fine level, L and S ignored).
- * bf16 = 1: all four tensors are bf16 (the tensor-core kernels), else fp32. Device pointers, dense rows. */
+ * bf16 = 1: all four tensors are bf16 (the tensor-core kernels), else fp32. bf16 = 2: bf16 tensors with RAW q and k (the
+ * projections as the GEMM leaves them): the kernels apply elu(x) + 1 themselves. Device pointers, dense rows. */
 int mfr_linear_attention(const void* q, const void* k, const void* v, void* msg, int n, int L, int S, int windows,
                          int bf16, void* stream);
 

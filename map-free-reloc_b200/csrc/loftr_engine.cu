@@ -50,7 +50,9 @@ struct LoftrEngine {
   int splits_kv = 96, splits_col = 32;   // splits_kv is set from the image count in build()
   int precision = 0;   // MFR_PRECISION_* (include/mfr_b200.h)
   bool fused_tail = getenv("MFR_FUSED_TAIL") == nullptr || atoi(getenv("MFR_FUSED_TAIL")) != 0;   // bf16 mode: encoder_tail.cu
-  bool fused_fine_attn = getenv("MFR_FUSED_FINE_ATTN") == nullptr || atoi(getenv("MFR_FUSED_FINE_ATTN")) != 0;   // bf16 mode, fine level
+  bool fused_fine_attn = getenv("MFR_FUSED_FINE_ATTN") != nullptr && atoi(getenv("MFR_FUSED_FINE_ATTN")) != 0;   // bf16 mode, fine level (opt-in)
+  // bf16 mode: the q|k|v GEMMs store raw projections and the attention kernels apply elu + 1 to their mma fragments
+  bool elu_in_attn = getenv("MFR_ELU_IN_ATTN") == nullptr || atoi(getenv("MFR_ELU_IN_ATTN")) != 0;
   struct Bf16Conv { std::string name; int cout, taps, cin, cin_pad; size_t off; };
   std::vector<Bf16Conv> bf16_convs;
   unsigned short* wblob16 = nullptr;
@@ -275,12 +277,14 @@ struct LoftrEngine {
         });
       }
     } else {
+    const bool raw = tbf && elu_in_attn;            // feature map applied by the attention kernels (bf16 = 2 below)
+    const int qk_act = raw ? ACT_NONE : ACT_ELU1, att_mode = raw ? 2 : tbf;
     if (x == src) {
-      conv(qn, xb, n, 1, rows, C, ld2, 3 * C, 1, 1, false, nullptr, ACT_ELU1, qkv_x, ld3, 2 * C, dyn_rows, wq, nullptr, tbf, tbf,
+      conv(qn, xb, n, 1, rows, C, ld2, 3 * C, 1, 1, false, nullptr, qk_act, qkv_x, ld3, 2 * C, dyn_rows, wq, nullptr, tbf, tbf,
            3 * C, 0);
     } else {
-      conv(qn, xb, n, 1, rows, C, ld2, C, 1, 1, false, nullptr, ACT_ELU1, qkv_x, ld3, C, dyn_rows, wq, nullptr, tbf, tbf, 3 * C, 0);
-      conv(qn, srcb, n, 1, rows, C, ld2, 2 * C, 1, 1, false, nullptr, ACT_ELU1, E(qkv_s, C), ld3, C, dyn_rows,
+      conv(qn, xb, n, 1, rows, C, ld2, C, 1, 1, false, nullptr, qk_act, qkv_x, ld3, C, dyn_rows, wq, nullptr, tbf, tbf, 3 * C, 0);
+      conv(qn, srcb, n, 1, rows, C, ld2, 2 * C, 1, 1, false, nullptr, qk_act, E(qkv_s, C), ld3, C, dyn_rows,
            wq + static_cast<size_t>(C) * C, nullptr, tbf, tbf, 3 * C, C);
     }
     if (!windows) {
@@ -288,7 +292,7 @@ struct LoftrEngine {
       const int Lr = rows, sk = splits_kv * NI / n;   // same partial-buffer footprint for n = B or n = 2B images
       float *kp = E(qkv_s, C), *vp = E(qkv_s, 2 * C);
       push("attn_long", [=](cudaStream_t st) {
-        return linear_attention_long(qkv_x, ld3, kp, ld3, vp, ld3, msg_x, C, kvp_, kv_, n, Lr, Lr, 8, 32, sk, st, tbf);
+        return linear_attention_long(qkv_x, ld3, kp, ld3, vp, ld3, msg_x, C, kvp_, kv_, n, Lr, Lr, 8, 32, sk, st, att_mode);
       }, 3);
     } else {
       const int items_cap = rows / 25;
@@ -297,7 +301,7 @@ struct LoftrEngine {
         const size_t off1 = static_cast<size_t>(side) * rows * C;
         float *qp = E(qkv_x, off3), *kp = E(qkv_s, off3 + C), *vp = E(qkv_s, off3 + 2 * C), *mp = E(msg_x, off1);
         push("attn_windows", [=](cudaStream_t st) {
-          return linear_attention_windows(qp, ld3, kp, ld3, vp, ld3, mp, C, dyn_items, items_cap, 25, st, tbf);
+          return linear_attention_windows(qp, ld3, kp, ld3, vp, ld3, mp, C, dyn_items, items_cap, 25, st, att_mode);
         });
       }
     }

@@ -471,6 +471,20 @@ __device__ __forceinline__ const char* sw_addr(const char* slab, int row, int ch
 }
 
 // kv_part[n][split][h][d*32 + v] = sum_s K'[s][32h+d] V[s][32h+v],  [..][1024 + d] = sum_s K'[s][32h+d]; warp = head
+__device__ __forceinline__ float elu1_fast(float v) {   // the token-GEMM epilogue's elu(x) + 1 (conv_gemm.cu act_fn<ACT_ELU1, true>)
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v * 1.4426950408889634f, 0.f)));
+  return fmaxf(v, 0.f) + e;
+}
+// RAW variants of the attention kernels take q and k as the projection GEMM leaves them and apply the feature map
+// elu(x) + 1 to the mma fragments in registers: the GEMM's 8 epilogue warps were bound by exactly this (MUFU + ALU issue),
+// while these kernels wait for HBM. keep_lo / keep_hi = false zeroes an element (token padding: K' rows past the end).
+__device__ __forceinline__ unsigned elu1_bf16x2(unsigned v, bool keep_lo = true, bool keep_hi = true) {
+  const float lo = elu1_fast(__uint_as_float(v << 16)), hi = elu1_fast(__uint_as_float(v & 0xffff0000u));
+  return pack_bf16(keep_lo ? lo : 0.f, keep_hi ? hi : 0.f);
+}
+
+template <bool RAW>
 __global__ void __launch_bounds__(256) kv_partial_mma_kernel(const void* __restrict__ K, long long ldk,
                                                              const void* __restrict__ V, long long ldv,
                                                              float* __restrict__ kv_part, int S, int splits) {
@@ -523,6 +537,16 @@ __global__ void __launch_bounds__(256) kv_partial_mma_kernel(const void* __restr
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)      // A = K'^T: m = channel d, k = token
         ldsm_x4_t(a[mt], sw_addr(k0, 16 * ks + r + 8 * (j >> 1), 4 * h + 2 * mt + (j & 1)));
+      if constexpr (RAW) {                // registers e = 0, 1 hold tokens 2 tq, 2 tq + 1 of the k-step, e = 2, 3 those + 8
+        const int tok = s_beg + i * kMS + 16 * ks + 2 * tq;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int t0 = tok + 8 * (e >> 1);
+            a[mt][e] = elu1_bf16x2(a[mt][e], t0 < s_end, t0 + 1 < s_end);
+          }
+      }
 #pragma unroll
       for (int pp = 0; pp < 2; ++pp)      // B = V: k = token, n = channel v (two 8-wide tiles per ldmatrix)
         ldsm_x4_t(b[pp], sw_addr(v0, 16 * ks + r + 8 * (j & 1), 4 * h + 2 * pp + (j >> 1)));
@@ -550,6 +574,7 @@ __global__ void __launch_bounds__(256) kv_partial_mma_kernel(const void* __restr
 }
 
 // msg[l][32h+v] = (Q'[l] . KV[:, v]) / (Q'[l] . Ksum + eps), KV / Ksum rounded to bf16 as the B operand; warp = head
+template <bool RAW>
 __global__ void __launch_bounds__(256) attn_apply_mma_kernel(const void* __restrict__ Q, long long ldq,
                                                              const float* __restrict__ kv,
                                                              unsigned short* __restrict__ msg, long long ldm, int L,
@@ -604,6 +629,10 @@ __global__ void __launch_bounds__(256) attn_apply_mma_kernel(const void* __restr
       for (int ks = 0; ks < 2; ++ks) {
         unsigned a[4];                      // A = Q': m = token, k = channel d
         ldsm_x4(a, sw_addr(q0, 16 * mt + r + 8 * (j & 1), 4 * h + 2 * ks + (j >> 1)));
+        if constexpr (RAW) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) a[e] = elu1_bf16x2(a[e]);
+        }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) mma_bf16(c[nt], a, bkv[ks][nt][0], bkv[ks][nt][1]);
         mma_bf16(cd, a, bden[ks][0], bden[ks][1]);
@@ -726,7 +755,7 @@ __global__ void __launch_bounds__(128) attn_windows_kernel(const void* __restric
 // rows. Per head: KV^T[v][d] = sum_s V[s][v] K'[s][d] (A = V^T, B = K') and Ksum through an A tile whose row 0 is all
 // ones; the accumulator fragments ARE the B fragments of the second product out[l][v] = Q'[l][d] KV[d][v] (transposed
 // accumulation puts (d pair, v) in the right lanes), so nothing goes back through shared memory.
-template <int T>
+template <int T, bool RAW>
 __global__ void __launch_bounds__(256) attn_windows_mma_kernel(const unsigned short* __restrict__ Q, long long ldq,
                                                                const unsigned short* __restrict__ K, long long ldk,
                                                                const unsigned short* __restrict__ V, long long ldv,
@@ -766,6 +795,14 @@ __global__ void __launch_bounds__(256) attn_windows_mma_kernel(const unsigned sh
     unsigned a[4], b[4];
     ldsm_x4_t(a, addr(2, 16 * ks + r + 8 * (j >> 1), 2 * h + (j & 1)));     // A = V^T: m = v, k = token
     ldsm_x4_t(b, addr(1, 16 * ks + r + 8 * (j & 1), 2 * h + (j >> 1)));     // B = K': k = token, n = d
+    if constexpr (RAW) {                  // b[2 nt] holds tokens 2 tq, 2 tq + 1 of the k-step, b[2 nt + 1] those + 8; rows >= T stay zero
+      const int tok = 16 * ks + 2 * tq;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int t0 = tok + 8 * (e & 1);
+        b[e] = elu1_bf16x2(b[e], t0 < T, t0 + 1 < T);
+      }
+    }
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
       mma_bf16(ckv[nt], a, b[2 * nt], b[2 * nt + 1]);
@@ -779,6 +816,10 @@ __global__ void __launch_bounds__(256) attn_windows_mma_kernel(const unsigned sh
   for (int mt = 0; mt < 2; ++mt) {
     unsigned a[4];
     ldsm_x4(a, addr(0, 16 * mt + r + 8 * (j & 1), 2 * h + (j >> 1)));       // A = Q': m = token, k = d
+    if constexpr (RAW) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[e] = elu1_bf16x2(a[e]);
+    }
     float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, cd[4] = {0.f, 0.f, 0.f, 0.f};
     mma_bf16(c0, a, bv0[0], bv0[1]);
     mma_bf16(c1, a, bv1[0], bv1[1]);
@@ -807,12 +848,6 @@ __global__ void __launch_bounds__(256) attn_windows_mma_kernel(const unsigned sh
 //   elu + 1 on q and k in registers, write the head's Q', K', V slice (bf16) into the shared tile the attention part reads
 //   (only this warp touches its head's columns, so a __syncwarp orders the two), then the attention of
 //   attn_windows_mma_kernel above and the 25 message rows to global memory.
-__device__ __forceinline__ float elu1_fast(float v) {   // the token-GEMM epilogue's elu(x) + 1 (conv_gemm.cu act_fn<ACT_ELU1, true>)
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v * 1.4426950408889634f, 0.f)));
-  return fmaxf(v, 0.f) + e;
-}
-
 template <int T>
 __global__ void __launch_bounds__(256, 1) fine_attn_fused_kernel(const unsigned short* __restrict__ xq, long long ldq,
                                                                   const unsigned short* __restrict__ xs, long long lds,
@@ -1851,17 +1886,24 @@ int linear_attention_long(const void* Q, long long ldq, const void* K, long long
     MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmem));
     MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmemBf));
     MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmemBf));
-    MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMStages * kMSlabBytes));
-    MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMStages * kMSlabBytes));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMStages * kMSlabBytes));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMStages * kMSlabBytes));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(kv_partial_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMStages * kMSlabBytes));
+    MFR_CUDA_CHECK(cudaFuncSetAttribute(attn_apply_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMStages * kMSlabBytes));
   }
   const int asplits = std::max(1, std::min((L + kSlab - 1) / kSlab, (4 * 148 + n - 1) / n));
   if (bf16) {
     if (kUseMmaAttention) {
       const int msplits = std::max(1, std::min((L + kMS - 1) / kMS, (4 * 148 + n - 1) / n));
-      kv_partial_mma_kernel<<<dim3(splits, n), 256, 2 * kMStages * kMSlabBytes, st>>>(K, ldk, V, ldv, kv_part, S, splits);
+      if (bf16 == 2) kv_partial_mma_kernel<true><<<dim3(splits, n), 256, 2 * kMStages * kMSlabBytes, st>>>(K, ldk, V, ldv, kv_part, S, splits);
+      else kv_partial_mma_kernel<false><<<dim3(splits, n), 256, 2 * kMStages * kMSlabBytes, st>>>(K, ldk, V, ldv, kv_part, S, splits);
       kv_reduce_kernel<<<dim3((8 * 1056 + 255) / 256, n), 256, 0, st>>>(kv_part, kv, splits);
-      attn_apply_mma_kernel<<<dim3(msplits, n), 256, kMStages * kMSlabBytes, st>>>(Q, ldq, kv, static_cast<unsigned short*>(msg), ldm,
-                                                                                  L, 1e-6f, msplits);
+      if (bf16 == 2)
+        attn_apply_mma_kernel<true><<<dim3(msplits, n), 256, kMStages * kMSlabBytes, st>>>(Q, ldq, kv, static_cast<unsigned short*>(msg), ldm, L,
+                                                                                          1e-6f, msplits);
+      else
+        attn_apply_mma_kernel<false><<<dim3(msplits, n), 256, kMStages * kMSlabBytes, st>>>(Q, ldq, kv, static_cast<unsigned short*>(msg), ldm, L,
+                                                                                           1e-6f, msplits);
     } else {
       kv_partial_kernel<true><<<dim3(splits, n), 256, kKvSmemBf, st>>>(K, ldk, V, ldv, kv_part, S, splits);
       kv_reduce_kernel<<<dim3((8 * 1056 + 255) / 256, n), 256, 0, st>>>(kv_part, kv, splits);
@@ -1882,9 +1924,14 @@ int linear_attention_windows(const void* Q, long long ldq, const void* K, long l
   if (T != 25 || max_items <= 0) return MFR_ERR_UNSUPPORTED;
   if (bf16 && kUseMmaAttention) {
     if ((ldq | ldk | ldv) & 7) return MFR_ERR_ARG;
-    attn_windows_mma_kernel<25><<<max_items, 256, 0, st>>>(static_cast<const unsigned short*>(Q), ldq, static_cast<const unsigned short*>(K), ldk,
-                                                          static_cast<const unsigned short*>(V), ldv, static_cast<unsigned short*>(msg), ldm,
-                                                          n_items_dev, 1e-6f);
+    if (bf16 == 2)
+      attn_windows_mma_kernel<25, true><<<max_items, 256, 0, st>>>(static_cast<const unsigned short*>(Q), ldq, static_cast<const unsigned short*>(K), ldk,
+                                                                  static_cast<const unsigned short*>(V), ldv, static_cast<unsigned short*>(msg), ldm,
+                                                                  n_items_dev, 1e-6f);
+    else
+      attn_windows_mma_kernel<25, false><<<max_items, 256, 0, st>>>(static_cast<const unsigned short*>(Q), ldq, static_cast<const unsigned short*>(K), ldk,
+                                                                   static_cast<const unsigned short*>(V), ldv, static_cast<unsigned short*>(msg), ldm,
+                                                                   n_items_dev, 1e-6f);
   } else if (bf16) attn_windows_kernel<25, true><<<max_items, 128, 0, st>>>(Q, ldq, K, ldk, V, ldv, msg, ldm, n_items_dev, 1e-6f);
   else attn_windows_kernel<25, false><<<max_items, 128, 0, st>>>(Q, ldq, K, ldk, V, ldv, msg, ldm, n_items_dev, 1e-6f);
   MFR_CUDA_CHECK(cudaGetLastError());

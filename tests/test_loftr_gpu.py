@@ -276,3 +276,27 @@ def test_stem_tcgen05_matches_reference(mfr, monkeypatch, NI, H, W):
         assert ((o.double() - ref).abs().max().item()) <= 2.0 ** -8 * scale     # bf16 rounding of the output
     assert (outs[0] - outs[1]).abs().max().item() <= 2.0 ** -7 * scale
     assert (outs[0] != outs[1]).float().mean().item() < 0.02
+
+
+@pytest.mark.parametrize("windows,n,L,S", [(0, 3, 301, 417), (0, 2, 64, 4800), (1, 37, 25, 25)])
+def test_linear_attention_raw_qk(mfr, windows, n, L, S):
+    """bf16 = 2: the tensor-core attention kernels take raw q, k (the projection GEMM's output) and apply elu + 1 to their
+    fragments; the result must equal the bf16 = 1 run on inputs feature-mapped beforehand (same bf16 roundings: equal bits up
+    to the ex2.approx of the feature map) and the fp64 restatement within the bf16 tolerance. Ragged L / S: the zero-filled
+    token padding must stay zero (elu(0) + 1 = 1 would count as tokens)."""
+    lib = mfr.load()
+    g = torch.Generator().manual_seed(23 + windows)
+    C = 128 if windows else 256
+    q = torch.randn(n, L, C, generator=g).to(torch.bfloat16)
+    k = torch.randn(n, S, C, generator=g).to(torch.bfloat16)
+    v = torch.randn(n, S, C, generator=g).to(torch.bfloat16)
+    qd, kd, vd = (x.cuda().contiguous() for x in (q, k, v))
+    out = torch.full((n, L, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    mfr.check(lib.mfr_linear_attention(mfr.ptr(qd), mfr.ptr(kd), mfr.ptr(vd), mfr.ptr(out), n, L, S, windows, 2, mfr.cur_stream()))
+    torch.cuda.synchronize()
+    qf = (torch.nn.functional.elu(q.float()) + 1).to(torch.bfloat16).float()
+    kf = (torch.nn.functional.elu(k.float()) + 1).to(torch.bfloat16).float()
+    ref = _lin_att_ref(qf, kf, v.float(), 8)
+    got = out.cpu().double()
+    assert torch.isfinite(got).all()
+    assert ((got - ref).abs().max() / ref.abs().max()).item() < 2e-2
