@@ -1300,7 +1300,7 @@ int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream) {
   if (p.pair) {   // clusters of two CTAs, one pair of pixel tiles per cluster iteration
     const int m_tiles = p.N * p.tiles_y * p.tiles_x;
     const int pairs = ((m_tiles + 1) / 2) * p.n_tiles;
-    const int clusters = std::min(pairs, conv_gemm_num_sms() / 2);
+    const int clusters = std::min(pairs, (p.grid_limit > 0 ? std::min(p.grid_limit, conv_gemm_num_sms()) : conv_gemm_num_sms()) / 2);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
     cfg.blockDim = dim3(kThreads);
@@ -1314,7 +1314,7 @@ int conv_gemm_launch(const ConvGemmParams& p, cudaStream_t stream) {
     MFR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_tf32_kernel<4, true>, p));
     return MFR_OK;
   }
-  const int grid = std::min(total, conv_gemm_num_sms());
+  const int grid = std::min(total, p.grid_limit > 0 ? std::min(p.grid_limit, conv_gemm_num_sms()) : conv_gemm_num_sms());
   if (p.epi_warps == 8 && !p.swap && p.tma_store != 1) conv_gemm_tf32_kernel<8, false><<<grid, 64 + 32 * 8, kSmemBytes, stream>>>(p);
   else conv_gemm_tf32_kernel<4, false><<<grid, kThreads, kSmemBytes, stream>>>(p);
   MFR_CUDA_CHECK(cudaGetLastError());

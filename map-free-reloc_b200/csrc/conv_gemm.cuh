@@ -37,6 +37,7 @@ struct alignas(64) ConvGemmParams {
   int a_slot_bytes;
   int epi_warps;          // 4, or 8 for token GEMMs with wide bf16 outputs (two warps per TMEM lane quadrant)
   int ring_bytes;         // operand ring size (the 8-warp epilogue takes its second staging area out of the ring)
+  int grid_limit;         // > 0: at most this many CTAs (the engine leaves SMs to the pose back end of the previous batch during the first layers)
   int nt_fast;            // work-item order: N tile index fastest (generic mode with several N tiles: the A tiles of a pixel tile stay in L2)
   int tma_store;          // epilogue writes 32 px x 32 ch fp32 chunks with cp.async.bulk.tensor stores (see conv_gemm.cu)
   int cbatch;             // generic mode: k-blocks whose slots are released by one tcgen05.commit batch (pipe drain)

@@ -52,6 +52,13 @@ struct LoftrEngine {
   bool fused_tail = getenv("MFR_FUSED_TAIL") == nullptr || atoi(getenv("MFR_FUSED_TAIL")) != 0;   // bf16 mode: encoder_tail.cu
   bool fused_fine_attn = getenv("MFR_FUSED_FINE_ATTN") != nullptr && atoi(getenv("MFR_FUSED_FINE_ATTN")) != 0;   // bf16 mode, fine level (opt-in)
   // bf16 mode: the q|k|v GEMMs store raw projections and the attention kernels apply elu + 1 to their mma fragments
+  // The pose back end of the previous batch runs on its own stream under the first layers of this batch's matcher. Its blocks
+  // do not fit next to the persistent GEMM CTAs, and a persistent kernel with a static tile assignment whose CTA has to wait
+  // for an SM is late by that CTA's whole share: the first `reserve_layers` conv launches (and the stem) therefore leave
+  // `reserve_sms` SMs free (MFR_RESERVE_SMS / MFR_RESERVE_LAYERS; 0 = use every SM).
+  int reserve_sms = getenv("MFR_RESERVE_SMS") ? atoi(getenv("MFR_RESERVE_SMS")) : 0;
+  int reserve_layers = getenv("MFR_RESERVE_LAYERS") ? atoi(getenv("MFR_RESERVE_LAYERS")) : 4;
+  int conv_count = 0;
   bool elu_in_attn = getenv("MFR_ELU_IN_ATTN") == nullptr || atoi(getenv("MFR_ELU_IN_ATTN")) != 0;
   struct Bf16Conv { std::string name; int cout, taps, cin, cin_pad; size_t off; };
   std::vector<Bf16Conv> bf16_convs;
@@ -183,6 +190,8 @@ struct LoftrEngine {
     ConvGemmParams p;
     int rc = conv_gemm_build(d, &p);
     if (rc != MFR_OK) { build_rc = rc; return; }
+    if (reserve_sms > 0 && conv_count < reserve_layers) p.grid_limit = conv_gemm_num_sms() - reserve_sms;
+    ++conv_count;
     steps.push_back([p](cudaStream_t st) { return conv_gemm_launch(p, st); });
     StepInfo inf;
     inf.name = wname.empty() ? "qkv" : wname;
@@ -443,7 +452,8 @@ struct LoftrEngine {
     {
       float *img_ = img, *a0_ = a0; float* ws = W_("stem.w"); float* bs = W_("stem.b");
       const int NI_ = NI, H_ = H, W_w = W, ob = B16, exact = precision == 2 ? 1 : 0;
-      push("stem", [=](cudaStream_t st) { return stem_conv7x7(img_, ws, bs, a0_, NI_, H_, W_w, st, ob, exact); });
+      const int stem_limit = reserve_sms > 0 ? conv_gemm_num_sms() - reserve_sms : 0;
+      push("stem", [=](cudaStream_t st) { return stem_conv7x7(img_, ws, bs, a0_, NI_, H_, W_w, st, ob, exact, stem_limit); });
     }
     auto bconv = [&](const std::string& name, const float* x, int Hh, int Ww, int Cin, int ldx, int Cout, int R,
                      int stride, bool bias, const float* res, int act, float* out, int ldo, int out16) {

@@ -1813,10 +1813,10 @@ __global__ void __launch_bounds__(128) stem_mma_kernel(const float* __restrict__
 // launch wrappers
 // ================================================================================================
 int stem_conv7x7(const float* img, const float* w, const float* bias, float* out, int NI, int H, int W,
-                 cudaStream_t st, int out_bf16, int exact_fp32) {
+                 cudaStream_t st, int out_bf16, int exact_fp32, int grid_limit) {
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   if (out_bf16 && !exact_fp32 && (getenv("MFR_STEM_TC") == nullptr || atoi(getenv("MFR_STEM_TC")) != 0))
-    return stem_conv7x7_tc(img, w, bias, out, NI, H, W, st);   // tcgen05 version (stem_tc.cu)
+    return stem_conv7x7_tc(img, w, bias, out, NI, H, W, st, grid_limit);   // tcgen05 version (stem_tc.cu)
   if (kUseMmaStem && !exact_fp32) {
     const int PW = 32 * ((Wo + 15) / 16) + 8;                 // patch columns: 2 px + kx for every pixel of the padded row
     const int smem = 2 * 8 * PW * 2;

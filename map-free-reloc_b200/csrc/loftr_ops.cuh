@@ -8,10 +8,11 @@ namespace mfr {
 // stem: conv7x7 stride 2 pad 3, 1 -> 128 channels, folded BN bias, ReLU (resnet_fpn.py:60-62,102)
 // exact_fp32: plain fp32 FMA kernel instead of the tensor-core one (bf16 hi/lo split, ~2^-16 relative)
 int stem_conv7x7(const float* img, const float* w /*[128][49]*/, const float* bias, float* out,
-                 int NI, int H, int W, cudaStream_t st, int out_bf16 = 0, int exact_fp32 = 0);
+                 int NI, int H, int W, cudaStream_t st, int out_bf16 = 0, int exact_fp32 = 0, int grid_limit = 0);
 
 // the same op on tcgen05 (stem_tc.cu): bf16 output only, same hi/lo split arithmetic
-int stem_conv7x7_tc(const float* img, const float* w, const float* bias, void* out_bf16, int NI, int H, int W, cudaStream_t st);
+int stem_conv7x7_tc(const float* img, const float* w, const float* bias, void* out_bf16, int NI, int H, int W, cudaStream_t st,
+                    int grid_limit = 0);
 
 // dst[n,y,x,:] += bilinear_x2_align_corners(src)[n,y,x,:]   (resnet_fpn.py:110,114)
 // pixel strides lds / ldd in elements; src / dst fp32 or bf16

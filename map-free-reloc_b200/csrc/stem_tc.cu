@@ -254,7 +254,7 @@ EncodeTiledFn stem_encode_fn() {
 
 }  // namespace
 
-int stem_conv7x7_tc(const float* img, const float* w, const float* bias, void* out_bf16, int NI, int H, int W, cudaStream_t st) {
+int stem_conv7x7_tc(const float* img, const float* w, const float* bias, void* out_bf16, int NI, int H, int W, cudaStream_t st, int grid_limit) {
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   EncodeTiledFn enc = stem_encode_fn();
   if (!enc) return MFR_ERR_CUDA;
@@ -279,6 +279,7 @@ int stem_conv7x7_tc(const float* img, const float* w, const float* bias, void* o
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int total = NI * p.tiles_x * p.tiles_y;
   if (total <= 0) return MFR_OK;
+  if (grid_limit > 0) sms = std::min(sms, grid_limit);
   stem_tc_kernel<<<std::min(total, sms), kThreadsStem, kSmemStem, st>>>(p);
   MFR_CUDA_CHECK(cudaGetLastError());
   return MFR_OK;
