@@ -30,9 +30,6 @@ import sys
 import threading
 import time
 
-# rank 0 prints ONE JSON line on stdout: NCCL's own banner / debug lines (NCCL_DEBUG in the environment) go to a file
-os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/mfr_bench_nccl.%h.%p.log")
-
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
