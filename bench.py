@@ -218,7 +218,7 @@ class Harness:
     def engine(self, precision, weights, thr):
         from mfr_b200 import loftr
         return loftr.LoFTR(loftr_weights(weights), batch=self.B, height=self.HP, width=self.WP, cfg={"thr": thr},
-                           device=self.local_rank, graph=True, precision=precision)
+                           device=self.local_rank, graph=True, precision=precision, pipelined=True)
 
     def pipeline(self, eng, be):
         from mfr_b200.pipeline import RelocPipeline

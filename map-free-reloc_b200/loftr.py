@@ -6,6 +6,7 @@ All network arithmetic runs in libmfr_b200.so (hand-written sm_100a kernels); to
 device memory and streams only. There is no CPU fallback.
 """
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -277,7 +278,7 @@ class LoFTR:
     """CUDA LoFTR engine for ``batch`` pairs of [H, W] images (H, W multiples of 8)."""
 
     def __init__(self, state_dict, batch=1, height=720, width=544, cfg=None, device=0, graph=True,
-                 precision="tf32"):
+                 precision="tf32", pipelined=False):
         if not torch.cuda.is_available():
             raise _lib.MfrError("mfr_b200.LoFTR needs a CUDA device (no CPU fallback)")
         self._l = _lib.load()
@@ -291,9 +292,19 @@ class LoFTR:
         # correlation, attention); fp32x3: fp32 storage, every GEMM as a 3xTF32 split product (fp32-faithful)
         self.precision = {"tf32": 0, "bf16": 1, "fp32x3": 2, "fp32": 2}[precision]
         self.precision_name = {0: "tf32", 1: "bf16", 2: "fp32x3"}[self.precision]
-        _lib.check(self._l.mfr_loftr_create(self.B, self.H, self.W, float(self.cfg["thr"]),
-                                            int(self.cfg["border_rm"]), float(self.cfg["temperature"]),
-                                            self.precision, ctypes.byref(h)), "mfr_loftr_create")
+        # pipelined: the engine will run under RelocPipeline, where the pose back end of the previous batch shares the GPU
+        # with the first layers of this batch's matcher: those launches then leave 8 SMs to it (loftr_engine.cu,
+        # MFR_RESERVE_SMS; measured +0.8 % pairs/s in the pipeline, -0.6 % for a matcher running alone)
+        prev = os.environ.get("MFR_RESERVE_SMS")
+        if pipelined and prev is None:
+            os.environ["MFR_RESERVE_SMS"] = "8"
+        try:
+            _lib.check(self._l.mfr_loftr_create(self.B, self.H, self.W, float(self.cfg["thr"]),
+                                                int(self.cfg["border_rm"]), float(self.cfg["temperature"]),
+                                                self.precision, ctypes.byref(h)), "mfr_loftr_create")
+        finally:
+            if pipelined and prev is None:
+                del os.environ["MFR_RESERVE_SMS"]
         self._h = h
         self._l.mfr_loftr_set_graph(self._h, int(bool(graph)))
         self.load_state_dict(state_dict)
