@@ -41,7 +41,7 @@ namespace mfr {
 
 namespace {
 
-constexpr int kEpiWarps = 8;          // two per TMEM lane quadrant: the pair splits the 32-column chunks of a phase (even / odd)
+constexpr int kEpiWarps = 8;          // front group (warps 2-5) and back group (warps 6-9), one warp per TMEM lane quadrant each
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kRelBatch = 3;        // ring slots handed back per tcgen05.commit batch
 constexpr int kKbBytes = 16384;     // one k-block of an A operand: [128 rows x 64 bf16], 128B-swizzled
