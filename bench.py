@@ -124,14 +124,21 @@ class ClockSampler:
                 pass
             self._stop.wait(0.1)
 
-    def __enter__(self):
+    def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join(timeout=6)
+
+    def __enter__(self):
+        self.start()
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        self.stop()
 
     def summary(self):
         sm, mx, pw, reasons, capped = [], [], [], set(), 0
@@ -238,13 +245,16 @@ class Harness:
         h = self.h
         return pipe.submit_host(*[[h[k][i] for i in idx] for k in ("g0", "g1", "d0", "d1", "K", "K")])
 
-    def timed(self, pipe, eng, submit, n_batches, warm_batches, gather_at_end=False):
-        """CUDA-event time (ms, max over ranks) of `n_batches` engine batches through `pipe`, after `warm_batches`."""
+    def timed(self, pipe, eng, submit, n_batches, warm_batches, gather_at_end=False, sampler=None):
+        """CUDA-event time (ms, max over ranks) of `n_batches` engine batches through `pipe`, after `warm_batches`.
+        `sampler` (ClockSampler) runs during the timed region only (not during the warm-up)."""
         torch, dist = self.torch, self.dist
         for b in range(warm_batches):
             submit(b)
         pipe.drain()
         self.barrier()
+        if sampler is not None:
+            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(eng.stream):
             e0.record()
@@ -261,6 +271,8 @@ class Harness:
             eng.stream.wait_stream(pipe.s_solve)
             e1.record()
         self.barrier()
+        if sampler is not None:
+            sampler.stop()
         ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
         if self.world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -334,12 +346,11 @@ def run_ours(args):
     outs = eng.device_outputs()
     in_bytes = sum(int(np.prod(hs.h[k].shape[1:])) * hs.h[k].element_size() * B for k in ("g0", "g1", "d0", "d1", "K", "K")) * micro
     out_bytes = int(pipe.slots[0]["rec_host"].numel() * 4) * micro
-    with ClockSampler(hs.local_rank) as clk:
-        ms_res, last = hs.timed(pipe, eng, lambda b: hs.submit_resident(pipe, eng, b), K * micro, Wm * micro, gather_at_end=True)
-        clocks = clk.summary()
-    with ClockSampler(hs.local_rank) as clk2:
-        ms_e2e, _ = hs.timed(pipe, eng, lambda b: hs.submit_host(pipe, b), K * micro, Wm * micro)
-        clocks_e2e = clk2.summary()
+    clk, clk2 = ClockSampler(hs.local_rank), ClockSampler(hs.local_rank)
+    ms_res, last = hs.timed(pipe, eng, lambda b: hs.submit_resident(pipe, eng, b), K * micro, Wm * micro, gather_at_end=True, sampler=clk)
+    clocks = clk.summary()
+    ms_e2e, _ = hs.timed(pipe, eng, lambda b: hs.submit_host(pipe, b), K * micro, Wm * micro, sampler=clk2)
+    clocks_e2e = clk2.summary()
     pairs = K * micro * B * world
     value, e2e_value = pairs / (ms_res / 1e3), pairs / (ms_e2e / 1e3)
     with torch.cuda.stream(eng.stream):
