@@ -47,8 +47,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("MFR_BENCH_BATCH", 16)), help="pairs per engine batch")
-    ap.add_argument("--micro", type=int, default=int(os.environ.get("MFR_BENCH_MICRO", 8)), help="engine batches per step")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("MFR_BENCH_BATCH", 32)), help="pairs per engine batch")
+    ap.add_argument("--micro", type=int, default=int(os.environ.get("MFR_BENCH_MICRO", 4)), help="engine batches per step")
     ap.add_argument("--hyp", type=int, default=1024, help="5-point hypotheses per pair")
     ap.add_argument("--match-thr", type=float, default=0.2, help="LoFTR coarse confidence threshold (reference: 0.2)")
     ap.add_argument("--precision", default=os.environ.get("MFR_BENCH_PRECISION", "bf16"), choices=["tf32", "bf16", "fp32x3"],
