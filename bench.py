@@ -9,7 +9,7 @@ weights are `loftr.functional_state_dict(noise=1e-3)`: full-shape layers that im
 a dense Gaussian perturbation on every conv / linear weight so that no tensor-core operand is structurally zero (a
 chip multiplying zeros draws less power and clocks higher than one running a trained checkpoint).
 
-A "step" = `--micro` engine batches of `--batch` pairs (default 8 x 16 = 128 pairs) through matcher + solver on one
+A "step" = `--micro` engine batches of `--batch` pairs (default 4 x 32 = 128 pairs) through matcher + solver on one
 GPU, so that the driver's 20 steps time >= 5 s of steady state. With N GPUs every rank runs its own pairs (weak
 scaling); one NCCL gather of the pose records at the end of the stream.
 
