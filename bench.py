@@ -9,7 +9,7 @@ weights are `loftr.functional_state_dict(noise=1e-3)`: full-shape layers that im
 a dense Gaussian perturbation on every conv / linear weight so that no tensor-core operand is structurally zero (a
 chip multiplying zeros draws less power and clocks higher than one running a trained checkpoint).
 
-A "step" = `--micro` engine batches of `--batch` pairs (default 4 x 32 = 128 pairs) through matcher + solver on one
+A "step" = `--micro` engine batches of `--batch` pairs (default 5 x 32 = 160 pairs) through matcher + solver on one
 GPU, so that the driver's 20 steps time >= 5 s of steady state. With N GPUs every rank runs its own pairs (weak
 scaling); one NCCL gather of the pose records at the end of the stream.
 
@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("MFR_BENCH_BATCH", 32)), help="pairs per engine batch")
-    ap.add_argument("--micro", type=int, default=int(os.environ.get("MFR_BENCH_MICRO", 4)), help="engine batches per step")
+    ap.add_argument("--micro", type=int, default=int(os.environ.get("MFR_BENCH_MICRO", 5)), help="engine batches per step")
     ap.add_argument("--hyp", type=int, default=1024, help="5-point hypotheses per pair")
     ap.add_argument("--match-thr", type=float, default=0.2, help="LoFTR coarse confidence threshold (reference: 0.2)")
     ap.add_argument("--precision", default=os.environ.get("MFR_BENCH_PRECISION", "bf16"), choices=["tf32", "bf16", "fp32x3"],
